@@ -1,0 +1,216 @@
+"""TEST INFRASTRUCTURE - generate golden vectors from the REAL reference (build container only).
+
+Imports the unmodified reference modules from /root/reference (which does not exist on the GPU
+box), loads the deterministic synthetic weights (vln-imagine_b200/synth.py), runs every mode
+of the hot path on seeded synthetic episodes and writes small fixtures to tests/golden/.
+In the same run it checks that the CPU oracle (oracle/*_oracle.py) reproduces the reference,
+so the oracle is pinned to the reference and not to itself.
+
+    python oracle/gen_golden.py --model duet
+    python oracle/gen_golden.py --model hamt     # separate process: both trees call their package `models`
+
+Harness-side shims only; no reference file is modified or copied.
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+REF = os.environ.get('VLN_REFERENCE', '/root/reference')
+GOLD = os.path.join(ROOT, 'tests', 'golden')
+
+
+def _shim_transformers():
+    from transformers import BertPreTrainedModel, PreTrainedModel
+    orig = PreTrainedModel.init_weights
+
+    def init_weights(self):           # transformers>=5: legacy init_weights() needs post_init() first
+        if 'all_tied_weights_keys' not in self.__dict__:
+            return self.post_init()
+        return orig(self)
+    BertPreTrainedModel.init_weights = init_weights
+
+
+DUET_CFG = dict(max_action_steps=100, image_feat_size=768, angle_feat_size=4, obj_feat_size=0, obj_loc_size=3,
+                num_l_layers=9, num_pano_layers=2, num_x_layers=4, graph_sprels=True, glocal_fuse=True,
+                fix_lang_embedding=False, fix_pano_embedding=False, fix_local_branch=False, update_lang_bert=True,
+                output_attentions=True, pred_head_dropout_prob=0.1, use_lang2visn_attn=False,
+                imagine_enc_pano=True, max_imagination_len=20, fix_imagine_embeds=False, bypass_imag_encoder=True,
+                use_cosine_aux_loss=True, concat_imagine_with='language', fix_lang_inside_cosine_model=True,
+                aux_loss_type='cosine', infonce_temperature=0.007, no_loss_test=False, dataset='r2r')
+HAMT_CFG = dict(image_feat_size=768, angle_feat_size=4, num_l_layers=9, num_r_layers=0, num_h_layers=0,
+                num_x_layers=4, hist_enc_pano=True, num_h_pano_layers=2, fix_lang_embedding=True,
+                fix_hist_embedding=True, fix_obs_embedding=False, update_lang_bert=False, output_attentions=True,
+                pred_head_dropout_prob=0.1, no_lang_ca=False, act_pred_token='ob_txt', max_action_steps=50,
+                imagine_enc_pano=True, max_imagination_len=20, fix_imagine_embeds=False, bypass_imag_encoder=True,
+                use_cosine_aux_loss=True, aux_loss_type='cosine', infonce_temperature=0.3,
+                contrastive_margin_value=0.5, concat_imagine_with='language', no_loss_test=False)
+
+
+def build_reference(model, overrides=None):
+    from transformers import BertConfig
+    _shim_transformers()
+    cfg = BertConfig()                 # defaults == bert-base-uncased
+    cfg.hidden_dropout_prob = 0.0
+    cfg.attention_probs_dropout_prob = 0.0
+    fields = dict(DUET_CFG if model == 'duet' else HAMT_CFG)
+    fields.update(overrides or {})
+    for k, v in fields.items():
+        setattr(cfg, k, v)
+    if model == 'duet':
+        sys.path.insert(0, os.path.join(REF, 'VLN-DUET', 'map_nav_src'))
+        from models.vilmodel import GlocalTextPathNavCMT as Net
+    else:
+        sys.path.insert(0, os.path.join(REF, 'VLN-HAMT', 'finetune_src'))
+        from models.vilmodel_cmt import NavCMT as Net
+        os.environ.pop('CUDA_LAUNCH_BLOCKING', None)     # import side effect, vilmodel_cmt.py:25
+    torch.manual_seed(0)
+    return Net(cfg).eval()
+
+
+def _sub(t):
+    """strided sample of a (B,N,768) tensor, enough to pin it without committing megabytes"""
+    return t[..., ::16].contiguous()
+
+
+def _np(d):
+    return {k: (v.detach().cpu().numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in d.items()}
+
+
+def maxdiff(a, b):
+    fin = torch.isfinite(a)
+    assert torch.equal(fin, torch.isfinite(b)), 'inf pattern differs'
+    if fin.sum() == 0:
+        return 0.0
+    return float((a[fin] - b[fin]).abs().max())
+
+
+def run_duet(args):
+    from importlib import import_module
+    synth = import_module('vln_imagine_b200.synth')
+    from oracle import duet_oracle as O
+    ref = build_reference('duet')
+    manifest = {k: list(v.shape) for k, v in ref.state_dict().items()}
+    with open(os.path.join(GOLD, 'duet_manifest.json'), 'w') as f:
+        json.dump(manifest, f, indent=0)
+    report = {}
+    for tag, shape, seed, stress in [('tiny', synth.TINY, 7, False), ('tiny_gasa', synth.TINY, 8, True),
+                                     ('cfg1', synth.CFG1, 1234, False), ('cfg1_gasa', synth.CFG1, 1234, True)]:
+        sd = synth.synth_state_dict(manifest, seed=0, gasa_stress=stress)
+        ref.load_state_dict(sd)
+        ep = synth.to_torch(synth.duet_episode(shape, seed))
+        out = {}
+        with torch.no_grad():
+            txt = ref('language', {'txt_ids': ep['txt_ids'], 'txt_masks': ep['txt_masks']})
+            img = ref('imagine', {'imagine_feats': ep['imagine_feats'], 'imagine_masks': None})
+            loss, img2 = ref('align_with_contrastive_loss', {
+                'align_txt_embeds': txt, 'txt_masks': ep['txt_masks'], 'align_imagine_embeds': img.clone(),
+                'imagine_masks': ep['imagine_masks'], 'sub_instr_segs': ep['sub_instr_segs'],
+                'sub_instr_imag_flag': ep['sub_instr_imag_flag'], 'noun_phrase_segs': ep['noun_phrase_segs'],
+                'obs_instr_ids': ep['obs_instr_ids']})
+            pano, pano_masks = ref('panorama', {'view_img_fts': ep['view_img_fts'], 'obj_img_fts': None,
+                                                'loc_fts': ep['loc_fts'], 'nav_types': ep['nav_types'],
+                                                'view_lens': ep['view_lens'], 'obj_lens': None})
+            nav = ref('navigation', {k: ep[k] for k in (
+                'txt_masks', 'gmap_img_embeds', 'gmap_step_ids', 'gmap_pos_fts', 'gmap_masks',
+                'gmap_pair_dists', 'gmap_visited_masks', 'gmap_vpids', 'vp_img_embeds', 'vp_pos_fts',
+                'vp_masks', 'vp_nav_masks', 'vp_cand_vpids', 'imagine_masks')} | {
+                'txt_embeds': txt, 'imagine_embeds': img2, 'vp_obj_masks': None})
+            # InfoNCE variant of the aux loss on the same inputs (models/vilmodel.py:689-779)
+            ref.config.aux_loss_type = 'contrastive-InfoNCE'
+            from models.vilmodel import AlignWithContrastiveLossWithNegativeSamples as NCE
+            nce = NCE(ref.config)
+            nce.image_proj.load_state_dict(ref.contrastive_alignment_model.image_proj.state_dict())
+            nce_loss, nce_img = nce.eval()(txt, ep['txt_masks'], img.clone(), ep['imagine_masks'], ep['sub_instr_segs'],
+                                           ep['sub_instr_imag_flag'], ep['noun_phrase_segs'], ep['obs_instr_ids'])
+            ref.config.aux_loss_type = 'cosine'
+
+            # the oracle on the same inputs
+            o_txt, o_img, o_loss, o_img2 = O.episode_prelude(sd, ep)
+            o_pano, o_pmask, o_nav = O.nav_step(sd, ep, o_txt, o_img2)
+            o_nce_loss, o_nce_img = O.forward_align_infonce(sd, o_txt, o_img, ep['sub_instr_imag_flag'],
+                                                            ep['noun_phrase_segs'], 0.007)
+        diffs = {
+            'txt': maxdiff(txt, o_txt), 'img': maxdiff(img, o_img), 'loss': abs(float(loss) - float(o_loss)),
+            'img2': maxdiff(img2, o_img2), 'pano': maxdiff(pano, o_pano),
+            'gmap': maxdiff(nav['gmap_embeds'], o_nav['gmap_embeds']), 'vp': maxdiff(nav['vp_embeds'], o_nav['vp_embeds']),
+            'global': maxdiff(nav['global_logits'], o_nav['global_logits']),
+            'local': maxdiff(nav['local_logits'], o_nav['local_logits']),
+            'fused': maxdiff(nav['fused_logits'], o_nav['fused_logits']),
+            'nce_loss': abs(float(nce_loss) - float(o_nce_loss)), 'nce_img': maxdiff(nce_img, o_nce_img),
+        }
+        assert torch.equal(pano_masks, o_pmask)
+        report[tag] = diffs
+        print(tag, json.dumps(diffs))
+        assert max(diffs.values()) < 2e-4, 'oracle does not reproduce the reference'
+        full = tag.startswith('tiny')
+        f = (lambda t: t) if full else _sub
+        out.update(txt_embeds=f(txt), imagine_embeds=f(img), aux_loss=loss, aligned_imagine_embeds=f(img2),
+                   pano_embeds=f(pano), pano_masks=pano_masks, gmap_embeds=f(nav['gmap_embeds']),
+                   vp_embeds=f(nav['vp_embeds']), global_logits=nav['global_logits'],
+                   local_logits=nav['local_logits'], fused_logits=nav['fused_logits'],
+                   nce_loss=nce_loss, nce_imagine_embeds=f(nce_img))
+        np.savez(os.path.join(GOLD, 'duet_%s.npz' % tag), **_np(out))
+    with open(os.path.join(GOLD, 'duet_oracle_vs_reference.json'), 'w') as f:
+        json.dump(report, f, indent=1)
+
+
+def run_hamt(args):
+    from importlib import import_module
+    synth = import_module('vln_imagine_b200.synth')
+    from oracle import hamt_oracle as O
+    ref = build_reference('hamt')
+    manifest = {k: list(v.shape) for k, v in ref.state_dict().items()}
+    with open(os.path.join(GOLD, 'hamt_manifest.json'), 'w') as f:
+        json.dump(manifest, f, indent=0)
+    sd = synth.synth_state_dict(manifest, seed=0)
+    ref.load_state_dict(sd)
+    report = {}
+    for tag, shape, seed in [('tiny', synth.TINY, 7), ('cfg1', synth.CFG1, 1234)]:
+        ep = synth.to_torch(synth.hamt_episode(shape, seed))
+        with torch.no_grad():
+            txt = ref('language', txt_ids=ep['txt_ids'], txt_masks=ep['txt_masks'])
+            img = ref('imagine', imagine_pano_img_feats=ep['imagine_feats'], imagine_masks=None)
+            loss, img2 = ref('align_with_contrastive_loss', align_txt_embeds=txt, txt_masks=ep['txt_masks'],
+                             align_imagine_embeds=img.clone(), imagine_masks=ep['imagine_masks'],
+                             sub_instr_segs=ep['sub_instr_segs'], sub_instr_imag_flag=ep['sub_instr_imag_flag'],
+                             noun_phrase_segs=ep['noun_phrase_segs'], obs_instr_ids=ep['obs_instr_ids'])
+            hm = O.hist_masks_from_lens(ep['hist_lens'], ep['hist_embeds'].shape[1])
+            logits, txt_o, hist_o, ob_o = ref(
+                'visual', txt_embeds=txt, txt_masks=ep['txt_masks'], hist_embeds=ep['hist_embeds'], hist_masks=hm,
+                ob_img_feats=ep['ob_img_feats'], ob_ang_feats=ep['ob_ang_feats'], ob_nav_types=ep['ob_nav_types'],
+                ob_masks=ep['ob_masks'], imagine_embeds=img2, imagine_masks=ep['imagine_masks'])
+            hist = ref('history', hist_img_feats=ep['hist_img_feats'], hist_ang_feats=ep['hist_ang_feats'],
+                       ob_step_ids=torch.LongTensor([ep['ob_step']]),
+                       hist_pano_img_feats=ep['hist_pano_img_feats'], hist_pano_ang_feats=ep['hist_pano_ang_feats'])
+            cls_hist = ref('history')
+            o_txt, o_img, o_loss, o_img2 = O.episode_prelude(sd, ep)
+            o_logits, o_txt_o, o_hist_o, o_ob_o, o_hist = O.nav_step(sd, ep, o_txt, o_img2)
+            o_cls = O.forward_history(sd, None, None, None, None, None)
+        diffs = {'txt': maxdiff(txt, o_txt), 'loss': abs(float(loss) - float(o_loss)), 'img2': maxdiff(img2, o_img2),
+                 'logits': maxdiff(logits, o_logits), 'txt_o': maxdiff(txt_o, o_txt_o),
+                 'hist_o': maxdiff(hist_o, o_hist_o), 'ob_o': maxdiff(ob_o, o_ob_o), 'hist': maxdiff(hist, o_hist),
+                 'cls_hist': maxdiff(cls_hist, o_cls)}
+        report[tag] = diffs
+        print(tag, json.dumps(diffs))
+        assert max(diffs.values()) < 2e-4, 'oracle does not reproduce the reference'
+        f = (lambda t: t) if tag == 'tiny' else _sub
+        np.savez(os.path.join(GOLD, 'hamt_%s.npz' % tag), **_np(dict(
+            txt_embeds=f(txt), aux_loss=loss, aligned_imagine_embeds=f(img2), act_logits=logits,
+            txt_out=f(txt_o), hist_out=f(hist_o), ob_out=f(ob_o), hist_embed=hist, cls_hist=cls_hist)))
+    with open(os.path.join(GOLD, 'hamt_oracle_vs_reference.json'), 'w') as f:
+        json.dump(report, f, indent=1)
+
+
+if __name__ == '__main__':
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--model', choices=['duet', 'hamt'], required=True)
+    a = ap.parse_args()
+    os.makedirs(GOLD, exist_ok=True)
+    torch.set_num_threads(os.cpu_count())
+    (run_duet if a.model == 'duet' else run_hamt)(a)
