@@ -1,0 +1,183 @@
+/* vlnimagine.h - C ABI of libvlnimagine.so: the sm_100a kernels behind the VLN-Imagine
+ * navigation hot path (DUET GlocalTextPathNavCMT / HAMT NavCMT).
+ *
+ * The reference (akhilperincherry/VLN-Imagine) is 100% PyTorch and has no FFI layer; the seam
+ * is the nn.Module the agents hold as `self.vln_bert`.  Each entry point below replaces a group
+ * of ATen ops that the reference module issues (cited as reference file:line, paths relative to
+ * VLN-DUET/map_nav_src/ = D/ and VLN-HAMT/finetune_src/ = H/).  The Python host modules in
+ * vln-imagine_b200/ bind these with ctypes.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer owned by the caller (PyTorch); the library never
+ *    allocates device memory and borrows pointers only for the asynchronous launch on `stream`;
+ *  - activations are row-major [rows, ld] with ld in ELEMENTS; hidden size is 768, 12 heads of 64;
+ *  - return value: VI_OK or a negative VI_ERR_*; vi_last_error() gives the thread-local message;
+ *    nothing throws or exits across the ABI;
+ *  - re-entrant; no global mutable state besides per-process immutable driver entry points.
+ */
+#ifndef VLNIMAGINE_H_
+#define VLNIMAGINE_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VI_OK 0
+#define VI_ERR_ARG (-1)
+#define VI_ERR_CUDA (-2)
+#define VI_ERR_UNSUPPORTED (-3)
+
+#define VI_HIDDEN 768
+#define VI_HEAD_DIM 64
+
+enum { VI_DT_BF16 = 0, VI_DT_F32 = 1 };
+enum { VI_EPI_NONE = 0, VI_EPI_GELU = 1, VI_EPI_RELU = 2 };
+/* key padding: additive (1-m)*-10000 (D/models/ops.py:25-34) or -inf (nn.MultiheadAttention
+ * key_padding_mask, D/models/transformer.py:176-177) */
+enum { VI_MASK_ADD_NEG10000 = 0, VI_MASK_NEG_INF = 1 };
+
+typedef void* vi_stream_t; /* cudaStream_t */
+
+int vi_version(void);
+const char* vi_last_error(void);
+/* Select the device, resolve cuTensorMapEncodeTiled, raise the dynamic shared-memory limits. */
+int vi_init(int device);
+
+/* ---------------------------------------------------------------------------------------------
+ * Dense contractions.  Replaces nn.Linear (aten::addmm) at D/models/vilmodel.py:93-95,147,172,186,
+ * 315-317 and H/models/vilmodel_cmt.py (same blocks), plus the fused epilogues that follow them:
+ * erf-GELU (:32-38), ReLU (ClsPrediction :1014), residual add (transformer.py:178,181).
+ *
+ *   Y[r, n] = epi( sum_k X[r,k] * W[g(r)*N + n, k] + bias[g(r)*N + n] ) + residual[r, n]
+ *
+ * Grouped form: rows are split into n_groups consecutive row ranges ending at group_row_end[g]
+ * (HOST array; every group but the last must end on a multiple of 128 rows); group g uses rows
+ * [g*N, (g+1)*N) of W / bias.  n_groups == 1 and group_row_end == NULL is the plain GEMM.
+ * vi_gemm_bf16: X, W bf16; fp32 accumulation in TMEM (tcgen05.mma fed by TMA).  K % 64 == 0,
+ *               N % 64 == 0, ldx % 8 == 0.  y_dtype selects bf16 or fp32 output.
+ * vi_gemm_f32 : the fp32 check mode (FFMA, no tensor cores); X, W, Y fp32.
+ * bias / residual may be NULL.  residual is fp32 [M, ldr].
+ * ------------------------------------------------------------------------------------------- */
+int vi_gemm_bf16(const void* x, int64_t ldx, const void* w, const float* bias,
+                 const float* residual, int64_t ldr, void* y, int64_t ldy, int y_dtype,
+                 int M, int N, int K, int epilogue,
+                 int n_groups, const int32_t* group_row_end, vi_stream_t stream);
+int vi_gemm_f32(const float* x, int64_t ldx, const float* w, const float* bias,
+                const float* residual, int64_t ldr, float* y, int64_t ldy,
+                int M, int N, int K, int epilogue,
+                int n_groups, const int32_t* group_row_end, vi_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused masked multi-head attention (scores never reach HBM).  Replaces
+ * matmul/div/add-mask/softmax/matmul at D/models/vilmodel.py:118-134 (BertSelfAttention),
+ * :336-349 (BertOutAttention), the GASA bias add at :392-394 and nn.MultiheadAttention in the
+ * panorama encoder (D/models/transformer.py:176-177).
+ *   q: [B*Lq, ldq], k/v: [B*Lk, ldk/ldv], head h at columns [h*64, h*64+64); o: [B*Lq, ldo].
+ *   key_mask [B, Lk] (1 = valid) or NULL; pair_dist [B, Lq, Lk] fp32 or NULL with
+ *   bias_affine -> device {w, b}: bias = w*dist + b (sprel_linear, D/models/vilmodel.py:1145-1149).
+ *   dtype: VI_DT_BF16 (mma.sync tiles, fp32 softmax) or VI_DT_F32 (check mode).
+ *   lse [B, H, Lq] optional (log-sum-exp per row, kept for the backward pass).
+ * ------------------------------------------------------------------------------------------- */
+int vi_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                void* o, int64_t ldo, int dtype,
+                const uint8_t* key_mask, const float* pair_dist, const float* bias_affine,
+                float* lse, int B, int H, int Lq, int Lk, int mask_mode, vi_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Row kernels (one warp per 768-wide row, fp32 statistics, 16-byte accesses).
+ * ------------------------------------------------------------------------------------------- */
+/* y = LayerNorm(a [+ b]) * gamma + beta.  BertSelfOutput/BertOutput (D/models/vilmodel.py:151-155,
+ * 190-194), norm1/norm2/final norm of the panorama encoder (D/models/transformer.py:171,179,86).
+ * Writes fp32 (y32) and/or bf16 (y16) copies; either may be NULL.  Grouped form as in vi_gemm_*:
+ * rows below group_row_end[g] (HOST array, ascending) use gamma/beta rows g of a [n_groups, 768] stack. */
+int vi_add_ln(const float* a, const float* b, const float* gamma, const float* beta, float eps,
+              float* y32, void* y16, int64_t rows,
+              int n_groups, const int32_t* group_row_end, vi_stream_t stream);
+
+/* Input-embedding composer:
+ *   y = LN_out( [LN_a](a) + LN_f(feat @ feat_w^T + feat_b) + table[idx] + pos_table[row % pos_period]
+ *               + const_row + const_row2 )
+ * every term optional.  Covers BertEmbeddings (D/models/vilmodel.py:49-78), the panorama /
+ * observation embeddings (D/models/vilmodel.py:1091-1121, H/models/vilmodel_cmt.py:521-544),
+ * history embeddings (H/...:576-612), gmap/vp input embeddings (D/...:1141-1152) and the
+ * imagination type embedding (D/...:562-573). */
+typedef struct {
+  const float* a;            /* [rows, 768] or NULL */
+  const float* a_gamma;      /* LayerNorm over a (NULL: add a as is) */
+  const float* a_beta;
+  const float* feat;         /* [rows, feat_dim] small geometric features or NULL (feat_dim <= 16) */
+  int32_t feat_dim;
+  const float* feat_w;       /* [768, feat_dim] */
+  const float* feat_b;       /* [768] */
+  const float* feat_gamma;   /* LayerNorm over the projected features (NULL: none) */
+  const float* feat_beta;
+  const int64_t* idx;        /* [rows] row ids into table, or NULL */
+  const float* table;        /* [*, 768] */
+  const float* pos_table;    /* [>=pos_period, 768] or NULL: adds pos_table[row % pos_period] */
+  int32_t pos_period;
+  const float* const_row;    /* [768] or NULL */
+  const float* const_row2;   /* [768] or NULL */
+  const float* out_gamma;    /* final LayerNorm (NULL: none) */
+  const float* out_beta;
+  float eps;                 /* all LayerNorms here use the same eps (1e-12 in the reference) */
+  float* y32;                /* [rows, 768] or NULL */
+  void* y16;                 /* bf16 [rows, 768] or NULL */
+  int64_t rows;
+} vi_embed_args;
+int vi_embed_compose(const vi_embed_args* args, vi_stream_t stream);
+
+/* out[row] = LayerNorm(h[row]) . w + b   (tail of ClsPrediction / NextActionPrediction:
+ * D/models/vilmodel.py:1009-1020, H/models/vilmodel_cmt.py:953-963).  Grouped like vi_add_ln:
+ * gamma/beta/w are [n_groups, 768] stacks and b is [n_groups]. */
+int vi_ln_dot(const float* h, const float* gamma, const float* beta, float eps,
+              const float* w, const float* b, float* out, int64_t rows,
+              int n_groups, const int32_t* group_row_end, vi_stream_t stream);
+
+/* y[r] = x[r] * s[r / rows_per_batch]  (ob_embeds * txt_embeds[:, :1], H/models/vilmodel_cmt.py:1191).
+ * s has row stride lds. */
+int vi_mul_bcast(const float* x, const float* s, int64_t lds, float* y32, void* y16,
+                 int64_t rows, int rows_per_batch, vi_stream_t stream);
+
+/* Action-logit masking and global/local fusion, D/models/vilmodel.py:1182-1217.
+ *   fuse = sigmoid(fuse_raw[b]); global = g_raw*fuse, -inf at visited|padded nodes;
+ *   local = l_raw*(1-fuse), -inf at non-navigable views;
+ *   fused[b,0] = global[b,0]+local[b,0]; for j>0: gmap_to_cand[b,j] >= 0 -> += local[b, that];
+ *   == -1 -> += sum of local[b, v] over cand_visited[b, v] (in ascending v); == -2 -> nothing.
+ * The int32 map replaces the reference's per-sample dict look-ups on viewpoint-id strings. */
+int vi_duet_fuse_logits(const float* g_raw, const float* l_raw, const float* fuse_raw,
+                        const uint8_t* gmap_masks, const uint8_t* gmap_visited, const uint8_t* vp_nav_masks,
+                        const int32_t* gmap_to_cand, const uint8_t* cand_visited,
+                        float* global_logits, float* local_logits, float* fused_logits,
+                        int B, int G, int P, vi_stream_t stream);
+
+/* act_logits.masked_fill_(ob_nav_types == 0, -inf)  (H/models/vilmodel_cmt.py:1200) */
+int vi_mask_logits_navtype(const float* raw, const int64_t* nav_types, float* out, int64_t n, vi_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Imagination <-> noun-phrase alignment (aux loss), D/models/vilmodel.py:598-655 and 657-779.
+ * ------------------------------------------------------------------------------------------- */
+/* out[r] = mean over t in [offsets[r], offsets[r+1]) of src[row_idx[t]]  (768-wide rows) */
+int vi_gather_mean(const float* src, const int32_t* offsets, const int32_t* row_idx,
+                   float* out32, void* out16, int R, vi_stream_t stream);
+/* dst[dst_rows[r]] = src[r] */
+int vi_scatter_rows(const float* src, const int32_t* dst_rows, float* dst, int R, vi_stream_t stream);
+/* loss_rows[r] = 1 - cos(proj[r], tgt[r]) (eps 1e-8); *loss_mean = mean_r (0 if R == 0) */
+int vi_cosine_loss(const float* proj, const float* tgt, float* loss_rows, float* loss_mean,
+                   int R, vi_stream_t stream);
+/* InfoNCE: logits_r = cos(proj[r], [tgt[r]; negs[n] for neg_episode[n] != row_episode[r]]) / T,
+ * loss_r = -log softmax(logits_r)[0]; *loss_mean = mean_r.  `scratch` must hold
+ * R * (n_negs + 2) floats: the similarity matrix first, then the R per-row losses. */
+int vi_infonce_loss(const float* proj, const float* tgt, const float* negs,
+                    const int32_t* row_episode, const int32_t* neg_episode,
+                    float temperature, float* scratch, float* loss_mean,
+                    int R, int n_negs, vi_stream_t stream);
+
+/* fp32 -> bf16 shadow copy of a weight or activation */
+int vi_cast_bf16(const float* src, void* dst, int64_t n, vi_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VLNIMAGINE_H_ */

@@ -1,0 +1,304 @@
+"""Kernel-level parity (through the C ABI) against plain PyTorch fp32 references of the same op.
+
+Tolerances: the fp32 check-mode kernels must agree to 1e-4 (max-norm relative); the bf16
+tensor-core kernels to 2e-2 against the fp32 reference and to 2e-3 against a reference that
+rounds its operands to bf16 first (which isolates kernel bugs from format rounding).
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def ops(lib_built):
+    import importlib
+    o = importlib.import_module('vln_imagine_b200.ops')
+    o.ensure_init(torch.zeros(1, device='cuda'))
+    return o
+
+
+def relerr(a, b):
+    a, b = a.float(), b.float()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-20))
+
+
+def _rand(*shape, scale=1.0, seed=0):
+    g = torch.Generator(device='cpu').manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).cuda()
+
+
+GEMM_SHAPES = [(1920, 768, 768), (2368, 2304, 768), (5440, 3072, 768), (300, 768, 3072), (128, 64, 64),
+               (1, 768, 768), (129, 1536, 768), (4288, 768, 3072), (37, 512, 768), (2048, 256, 64)]
+
+
+@pytest.mark.parametrize('M,N,K', GEMM_SHAPES)
+@pytest.mark.parametrize('epi', [0, 1, 2])
+def test_gemm_bf16(ops, M, N, K, epi):
+    x = _rand(M, K, seed=1)
+    w = _rand(N, K, scale=0.05, seed=2)
+    b = _rand(N, scale=0.1, seed=3)
+    res = _rand(M, N, seed=4)
+    x16, w16 = x.bfloat16(), w.bfloat16()
+    ref = F.linear(x16.float(), w16.float(), b)
+    ref = [ref, F.gelu(ref), F.relu(ref)][epi]
+    y = ops.gemm(x16, w16, b, epilogue=epi, out_dtype=torch.float32)
+    assert relerr(y, ref) < 2e-3
+    y2 = ops.gemm(x16, w16, b, residual=res, epilogue=epi, out_dtype=torch.float32)
+    assert relerr(y2, ref + res) < 2e-3
+    y3 = ops.gemm(x16, w16, None, epilogue=epi, out_dtype=torch.bfloat16)
+    ref3 = F.linear(x16.float(), w16.float())
+    ref3 = [ref3, F.gelu(ref3), F.relu(ref3)][epi]
+    assert relerr(y3, ref3) < 1e-2
+
+
+@pytest.mark.parametrize('bn', ['64', '128', '256'])
+def test_gemm_bf16_every_tile_width(ops, bn, monkeypatch):
+    monkeypatch.setenv('VI_GEMM_BN', bn)
+    M, N, K = 1000, 768, 1536
+    x16, w16 = _rand(M, K, seed=5).bfloat16(), _rand(N, K, scale=0.05, seed=6).bfloat16()
+    y = ops.gemm(x16, w16, None, out_dtype=torch.float32)
+    assert relerr(y, x16.float() @ w16.float().t()) < 2e-3
+
+
+def test_gemm_bf16_strided_operand_and_output(ops):
+    M, K, N = 640, 768, 768
+    big = _rand(M, 2304, seed=7).bfloat16()
+    x16 = big[:, 768:1536]
+    w16 = _rand(N, K, scale=0.05, seed=8).bfloat16()
+    out = torch.zeros(M, 2 * N, dtype=torch.bfloat16, device='cuda')
+    ops.gemm(x16, w16, None, out=out[:, N:])
+    assert relerr(out[:, N:], x16.float() @ w16.float().t()) < 1e-2
+    assert float(out[:, :N].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize('lowp', [True, False])
+def test_gemm_grouped(ops, lowp):
+    rows = [1920, 2368]
+    K, N = 768, 768
+    M0 = ops.pad128(rows[0])
+    M = M0 + rows[1]
+    x = torch.zeros(M, K, device='cuda')
+    x[:rows[0]] = _rand(rows[0], K, seed=1)
+    x[M0:] = _rand(rows[1], K, seed=2)
+    w = _rand(2 * N, K, scale=0.05, seed=3)
+    b = _rand(2 * N, scale=0.1, seed=4)
+    if lowp:
+        xx, ww = x.bfloat16(), w.bfloat16()
+    else:
+        xx, ww = x, w
+    y = ops.gemm(xx, ww, b, out_dtype=torch.float32, group_row_end=[M0, M])
+    ref0 = F.linear(xx[:rows[0]].float(), ww[:N].float(), b[:N])
+    ref1 = F.linear(xx[M0:].float(), ww[N:].float(), b[N:])
+    tol = 2e-3 if lowp else 1e-4
+    assert relerr(y[:rows[0]], ref0) < tol
+    assert relerr(y[M0:], ref1) < tol
+
+
+@pytest.mark.parametrize('M,N,K', [(300, 768, 768), (77, 3072, 768), (1, 1, 7), (130, 768, 14), (65, 100, 33)])
+@pytest.mark.parametrize('epi', [0, 1, 2])
+def test_gemm_f32(ops, M, N, K, epi):
+    x, w, b, res = _rand(M, K, seed=1), _rand(N, K, scale=0.05, seed=2), _rand(N, seed=3), _rand(M, N, seed=4)
+    ref = F.linear(x.double(), w.double(), b.double())
+    ref = [ref, F.gelu(ref), F.relu(ref)][epi] + res.double()
+    y = ops.gemm(x, w, b, residual=res, epilogue=epi)
+    assert relerr(y, ref.float()) < 1e-5
+
+
+def _attn_ref(q, k, v, B, Lq, Lk, key_mask, pair_dist, affine, neg_inf):
+    H = 12
+    qh = q.float().view(B, Lq, H, 64).permute(0, 2, 1, 3)
+    kh = k.float().view(B, Lk, H, 64).permute(0, 2, 1, 3)
+    vh = v.float().view(B, Lk, H, 64).permute(0, 2, 1, 3)
+    s = qh @ kh.transpose(-1, -2) / 8.0
+    if key_mask is not None:
+        if neg_inf:
+            s = s.masked_fill(~key_mask.bool()[:, None, None, :], float('-inf'))
+        else:
+            s = s + (1.0 - key_mask.float())[:, None, None, :] * -10000.0
+    if pair_dist is not None:
+        s = s + (pair_dist * affine[0] + affine[1])[:, None]
+    o = torch.softmax(s, -1) @ vh
+    lse = torch.logsumexp(s, -1)
+    return o.permute(0, 2, 1, 3).reshape(B * Lq, H * 64), lse
+
+
+ATTN_CASES = [  # B, Lq, Lk, masked, gasa, neg_inf
+    (3, 7, 7, True, True, False), (8, 30, 30, True, True, False), (8, 37, 85, True, False, False),
+    (4, 36, 36, True, False, True), (2, 100, 212, True, False, False), (2, 100, 100, True, True, False),
+    (2, 85, 53, True, False, False), (5, 1, 16, False, False, False), (2, 130, 300, True, False, False),
+    (2, 16, 64, False, False, False), (2, 64, 128, True, False, True),
+]
+
+
+@pytest.mark.parametrize('B,Lq,Lk,masked,gasa,neg_inf', ATTN_CASES)
+@pytest.mark.parametrize('lowp', [True, False])
+def test_attention(ops, B, Lq, Lk, masked, gasa, neg_inf, lowp):
+    dt = torch.bfloat16 if lowp else torch.float32
+    qkv_q = _rand(B * Lq, 2304, seed=1).to(dt)            # strided views, like the fused QKV output
+    qkv_k = _rand(B * Lk, 2304, seed=2).to(dt)
+    q, k, v = qkv_q[:, :768], qkv_k[:, 768:1536], qkv_k[:, 1536:]
+    key_mask = None
+    if masked:
+        g = torch.Generator().manual_seed(3)
+        lens = torch.randint(1, Lk + 1, (B,), generator=g)
+        lens[0] = Lk
+        key_mask = (torch.arange(Lk)[None] < lens[:, None]).to(torch.uint8).cuda()
+        if Lk > 4:
+            key_mask[-1, 1] = 0                            # a hole in the middle (imagination flags)
+    pair_dist = affine = None
+    if gasa:
+        pair_dist = (_rand(B, Lq, Lk, seed=4).abs() * 10).contiguous()
+        affine = torch.tensor([-0.5, 0.1], device='cuda')
+    lse = torch.empty(B, 12, Lq, device='cuda')
+    o = ops.attention(q, k, v, B, Lq, Lk, key_mask=key_mask, pair_dist=pair_dist, bias_affine=affine,
+                      mask_mode=ops.MASK_NEG_INF if neg_inf else ops.MASK_ADD_NEG10000, lse=lse)
+    ref, ref_lse = _attn_ref(q, k, v, B, Lq, Lk, key_mask, pair_dist, affine, neg_inf)
+    assert o.dtype == dt
+    assert relerr(o, ref) < (1.5e-2 if lowp else 1e-5)
+    assert relerr(lse, ref_lse) < (2e-3 if lowp else 1e-5)
+
+
+@pytest.mark.parametrize('rows', [1, 5, 2368])
+@pytest.mark.parametrize('eps', [1e-12, 1e-5])
+def test_add_ln(ops, rows, eps):
+    a, b = _rand(rows, 768, seed=1), _rand(rows, 768, seed=2)
+    g, be = 1 + 0.1 * _rand(768, seed=3), _rand(768, seed=4)
+    y32, y16 = ops.add_ln(a, b, g, be, eps, want16=True)
+    ref = F.layer_norm(a + b, (768,), g, be, eps)
+    assert relerr(y32, ref) < 1e-5
+    assert relerr(y16, ref) < 1e-2
+    y32, _ = ops.add_ln(a, None, g, be, eps, want16=False)
+    assert relerr(y32, F.layer_norm(a, (768,), g, be, eps)) < 1e-5
+
+
+def test_add_ln_grouped(ops):
+    a = _rand(300, 768, seed=1)
+    g, be = 1 + 0.1 * _rand(2, 768, seed=3), _rand(2, 768, seed=4)
+    y32, _ = ops.add_ln(a, None, g, be, 1e-12, want16=False, group_row_end=[128, 300])
+    assert relerr(y32[:128], F.layer_norm(a[:128], (768,), g[0], be[0], 1e-12)) < 1e-5
+    assert relerr(y32[128:], F.layer_norm(a[128:], (768,), g[1], be[1], 1e-12)) < 1e-5
+
+
+def test_embed_compose_bert_embeddings(ops):
+    B, L = 4, 24
+    ids = torch.randint(0, 1000, (B * L,), device='cuda')
+    table, pos, tt = _rand(1000, 768, seed=1), _rand(512, 768, seed=2), _rand(768, seed=3)
+    g, be = 1 + 0.1 * _rand(768, seed=4), _rand(768, seed=5)
+    y32, y16 = ops.embed_compose(B * L, 'cuda', idx=ids, table=table, pos_table=pos, pos_period=L, const_row=tt,
+                                 out_ln=(g, be), want16=True)
+    ref = F.layer_norm(table[ids] + pos[:L].repeat(B, 1) + tt, (768,), g, be, 1e-12)
+    assert relerr(y32, ref) < 1e-5
+    assert relerr(y16, ref) < 1e-2
+
+
+@pytest.mark.parametrize('fd', [4, 7, 14])
+def test_embed_compose_feature_terms(ops, fd):
+    rows = 333
+    a, feat = _rand(rows, 768, seed=1), _rand(rows, fd, seed=2)
+    fw, fb = _rand(768, fd, seed=3), _rand(768, seed=4)
+    ga, ba = 1 + 0.1 * _rand(768, seed=5), _rand(768, seed=6)
+    gf, bf = 1 + 0.1 * _rand(768, seed=7), _rand(768, seed=8)
+    go, bo = 1 + 0.1 * _rand(768, seed=9), _rand(768, seed=10)
+    idx = torch.randint(0, 3, (rows,), device='cuda')
+    table, c1 = _rand(3, 768, seed=11), _rand(768, seed=12)
+    y32, _ = ops.embed_compose(rows, 'cuda', a=a, a_ln=(ga, ba), feat=feat, feat_w=fw, feat_b=fb, feat_ln=(gf, bf),
+                               idx=idx, table=table, const_row=c1, out_ln=(go, bo))
+    ref = F.layer_norm(F.layer_norm(a, (768,), ga, ba, 1e-12) + F.layer_norm(F.linear(feat, fw, fb), (768,), gf, bf, 1e-12)
+                       + table[idx] + c1, (768,), go, bo, 1e-12)
+    assert relerr(y32, ref) < 1e-5
+    y32, _ = ops.embed_compose(rows, 'cuda', a=a, feat=feat, feat_w=fw, feat_b=fb, feat_ln=(gf, bf))   # vp / gmap form
+    assert relerr(y32, a + F.layer_norm(F.linear(feat, fw, fb), (768,), gf, bf, 1e-12)) < 1e-5
+
+
+def test_ln_dot_and_mul_bcast(ops):
+    h = _rand(200, 768, seed=1)
+    g, be, w, b = 1 + 0.1 * _rand(768, seed=2), _rand(768, seed=3), _rand(768, seed=4), _rand(1, seed=5)
+    out = ops.ln_dot(h, g, be, 1e-12, w, b)
+    ref = F.layer_norm(h, (768,), g, be, 1e-12) @ w + b
+    assert relerr(out, ref) < 1e-5
+    x, s = _rand(6 * 37, 768, seed=6), _rand(6 * 85, 768, seed=7)
+    y32, y16 = ops.mul_bcast(x, s.view(6, 85 * 768), 37, want16=True)
+    ref = (x.view(6, 37, 768) * s.view(6, 85, 768)[:, :1]).view(-1, 768)
+    assert torch.equal(y32, ref)
+    assert relerr(y16, ref) < 1e-2
+
+
+def test_gather_mean_scatter_cosine(ops):
+    src = _rand(50, 768, seed=1)
+    offsets = torch.tensor([0, 3, 4, 9], dtype=torch.int32, device='cuda')
+    row_idx = torch.tensor([1, 2, 2, 40, 5, 6, 7, 8, 8], dtype=torch.int32, device='cuda')
+    y32, _ = ops.gather_mean(src, offsets, row_idx, 3, want16=False)
+    ref = torch.stack([src[[1, 2, 2]].mean(0), src[[40]].mean(0), src[[5, 6, 7, 8, 8]].mean(0)])
+    assert relerr(y32, ref) < 1e-6
+    dst = torch.zeros(10, 768, device='cuda')
+    ops.scatter_rows(y32, torch.tensor([7, 0, 3], dtype=torch.int32, device='cuda'), dst)
+    assert torch.equal(dst[[7, 0, 3]], y32) and float(dst[[1, 2, 4, 5, 6, 8, 9]].abs().max()) == 0
+    p, t = _rand(33, 768, seed=2), _rand(33, 768, seed=3)
+    loss, rows = ops.cosine_loss(p, t, 33, 'cuda')
+    ref_rows = 1 - F.cosine_similarity(p, t, dim=-1)
+    assert relerr(rows, ref_rows) < 1e-5
+    assert abs(float(loss) - float(ref_rows.mean())) < 1e-5
+    loss0, _ = ops.cosine_loss(None, None, 0, 'cuda')
+    assert float(loss0) == 0.0
+
+
+def test_infonce(ops):
+    R, Nn = 9, 14
+    p, t, negs = _rand(R, 768, seed=1), _rand(R, 768, seed=2), _rand(Nn, 768, seed=3)
+    row_ep = torch.tensor([0, 0, 1, 1, 1, 2, 3, 3, 3], dtype=torch.int32, device='cuda')
+    neg_ep = torch.tensor([0, 0, 0, 1, 1, 1, 1, 2, 2, 3, 3, 3, 3, 3], dtype=torch.int32, device='cuda')
+    T = 0.07
+    loss = ops.infonce_loss(p, t, negs, row_ep, neg_ep, T, R, Nn, 'cuda')
+    ref = []
+    for r in range(R):
+        keep = negs[neg_ep != row_ep[r]]
+        allt = torch.cat([t[r:r + 1], keep], 0)
+        sim = F.cosine_similarity(p[r:r + 1], allt) / T
+        ref.append(F.cross_entropy(sim[None], torch.zeros(1, dtype=torch.long, device='cuda')))
+    assert abs(float(loss) - float(torch.stack(ref).mean())) < 1e-4
+
+
+def test_fuse_logits_and_navtype_mask(ops):
+    B, G, P = 5, 9, 7
+    g_raw, l_raw, f_raw = _rand(B, G, seed=1), _rand(B, P, seed=2), _rand(B, seed=3)
+    gm = torch.ones(B, G, dtype=torch.uint8, device='cuda'); gm[:, 7:] = 0
+    gv = torch.zeros(B, G, dtype=torch.uint8, device='cuda'); gv[:, 1:3] = 1
+    nav = torch.zeros(B, P, dtype=torch.uint8, device='cuda'); nav[:, :4] = 1
+    to_cand = torch.full((B, G), -1, dtype=torch.int32, device='cuda')
+    to_cand[:, 3] = 2; to_cand[:, 4] = 3; to_cand[:, 1:3] = -2; to_cand[:, 0] = -2
+    cand_vis = torch.zeros(B, P, dtype=torch.uint8, device='cuda'); cand_vis[:, 1] = 1
+    gl, ll, fl = ops.duet_fuse_logits(g_raw, l_raw, f_raw, gm, gv, nav, to_cand, cand_vis, B, G, P)
+    fw = torch.sigmoid(f_raw)[:, None]
+    rg = (g_raw * fw).masked_fill(gv.bool(), float('-inf')).masked_fill(~gm.bool(), float('-inf'))
+    rl = (l_raw * (1 - fw)).masked_fill(~nav.bool(), float('-inf'))
+    rf = rg.clone()
+    rf[:, 0] += rl[:, 0]
+    rf[:, 3] += rl[:, 2]
+    rf[:, 4] += rl[:, 3]
+    rf[:, 5:] += rl[:, 1:2]
+    for a, b in ((gl, rg), (ll, rl), (fl, rf)):
+        assert torch.equal(torch.isinf(a), torch.isinf(b))
+        fin = torch.isfinite(b)
+        assert float((a[fin] - b[fin]).abs().max()) < 1e-6
+    types = torch.randint(0, 3, (B, P), device='cuda')
+    out = ops.mask_logits_navtype(l_raw, types)
+    assert torch.equal(out, l_raw.masked_fill(types == 0, float('-inf')))
+
+
+def test_cast_bf16(ops):
+    x = _rand(1003, seed=1)
+    assert torch.equal(ops.cast_bf16(x), x.bfloat16())
+
+
+def test_argument_errors_are_reported_not_fatal(ops):
+    import importlib
+    _lib = importlib.import_module('vln_imagine_b200._lib')
+    x16 = _rand(128, 100, seed=1).bfloat16()              # K not a multiple of 64
+    with pytest.raises(_lib.VlnImagineError, match='multiple of 64'):
+        ops.gemm(x16, _rand(64, 100, seed=2).bfloat16())
+    with pytest.raises(_lib.VlnImagineError, match='CUDA tensor|no CPU path|must be'):
+        ops.ensure_init(torch.zeros(1))

@@ -1,0 +1,220 @@
+"""Transformer blocks of the navigation hot path, expressed as sequences of libvlnimagine launches.
+
+Shared by the DUET (duet.py) and HAMT (hamt.py) host modules.  Activations travel as a pair
+(fp32 residual stream, bf16 GEMM operand copy); in the fp32 check mode only the fp32 tensor exists.
+Several token streams that run the same layer shape with different weights (DUET global/local
+encoders, HAMT language/vision streams) are stacked along the row axis, each stream starting on
+a 128-row boundary, and go through ONE grouped launch per GEMM / LayerNorm.
+"""
+from __future__ import annotations
+
+import dataclasses
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import ops
+from .ops import BF16, F32, HIDDEN, EPI_GELU, EPI_NONE, EPI_RELU, MASK_ADD_NEG10000, MASK_NEG_INF  # noqa: F401
+
+
+# ----------------------------------------------------------------------------------------------
+# derived weights (bf16 shadow copies, stacked groups), refreshed when a source parameter changes
+# ----------------------------------------------------------------------------------------------
+class Pack:
+    """Device tensors derived from parameters; rebuilt when any source's version / storage changes
+    (optimizer step, load_state_dict, .cuda()).  fp32 masters stay the nn.Parameters themselves."""
+
+    def __init__(self, sources: Sequence[torch.Tensor], build):
+        self.sources = list(sources)
+        self._build = build
+        self._key = None
+        self._val = None
+
+    def get(self):
+        key = tuple((p._version, p.data_ptr()) for p in self.sources)
+        if key != self._key:
+            with torch.no_grad():
+                self._val = self._build()
+            self._key = key
+        return self._val
+
+
+class LinearPack:
+    """Rows-stacked weight [sum N_i, K] (+ bias) of one or several nn.Linear-shaped parameter sets."""
+
+    def __init__(self, weights: Sequence[torch.Tensor], biases: Optional[Sequence[Optional[torch.Tensor]]] = None):
+        self.weights = list(weights)
+        self.biases = None if biases is None or all(b is None for b in biases) else list(biases)
+        srcs = self.weights + ([b for b in self.biases if b is not None] if self.biases else [])
+        self._pack = Pack(srcs, self._make)
+
+    def _make(self):
+        ws = [w.detach() for w in self.weights]
+        w32 = (torch.cat(ws, 0) if len(ws) > 1 else ws[0]).contiguous()
+        b = None
+        if self.biases is not None:
+            bs = [(b.detach() if b is not None else torch.zeros(w.shape[0], device=w.device)) for b, w in zip(self.biases, ws)]
+            b = (torch.cat(bs, 0) if len(bs) > 1 else bs[0]).contiguous().float()
+        return {'w32': w32, 'w16': ops.cast_bf16(w32), 'b': b}
+
+    def get(self, lowp: bool):
+        v = self._pack.get()
+        return (v['w16'] if lowp else v['w32']), v['b']
+
+
+class StackPack:
+    """[n, ...] stack of same-shaped vectors (LayerNorm gains/biases, head vectors) for grouped row kernels."""
+
+    def __init__(self, tensors: Sequence[torch.Tensor]):
+        self.tensors = list(tensors)
+        self._pack = Pack(self.tensors, self._make)
+
+    def _make(self):
+        ts = [t.detach().reshape(-1) for t in self.tensors]
+        return (torch.stack(ts, 0) if len(ts) > 1 else ts[0]).contiguous().float()
+
+    def get(self):
+        return self._pack.get()
+
+
+class LNPack:
+    def __init__(self, lns):
+        self.g = StackPack([ln.weight for ln in lns])
+        self.b = StackPack([ln.bias for ln in lns])
+
+    def get(self):
+        return self.g.get(), self.b.get()
+
+
+# ----------------------------------------------------------------------------------------------
+# activations
+# ----------------------------------------------------------------------------------------------
+@dataclasses.dataclass
+class Act:
+    f32: torch.Tensor                     # [rows, 768] fp32 residual stream
+    b16: Optional[torch.Tensor] = None    # bf16 copy fed to the tensor-core GEMMs (None in fp32 mode)
+
+    def operand(self, lowp: bool):
+        return self.b16 if lowp else self.f32
+
+
+@dataclasses.dataclass
+class Stream:
+    """One token stream inside a row-stacked activation."""
+    row0: int                       # first row (multiple of 128)
+    B: int
+    L: int                          # tokens per episode (padded length)
+    mask: Optional[torch.Tensor]    # uint8 [B, L] key-padding mask (1 = valid) or None
+    group: int = 0                  # weight block this stream uses
+    pair_dist: Optional[torch.Tensor] = None   # fp32 [B, L, L] graph distances (GASA) or None
+    bias_affine: Optional[torch.Tensor] = None  # device {w, b}
+
+    @property
+    def rows(self):
+        return self.B * self.L
+
+    def view(self, t: torch.Tensor):
+        return t[self.row0:self.row0 + self.rows]
+
+
+def stack_layout(token_counts: Sequence[int]):
+    """Row offsets for streams stacked on 128-row boundaries -> (row0 list, group_row_end list, total rows)."""
+    row0, ends, cur = [], [], 0
+    for i, n in enumerate(token_counts):
+        row0.append(cur)
+        last = i == len(token_counts) - 1
+        cur = cur + n if last else ops.pad128(cur + n)
+        ends.append(cur)
+    return row0, ends, cur
+
+
+def layer_norm(x32, res32, ln: LNPack, eps, lowp, ends=None) -> Act:
+    g, b = ln.get()
+    y32, y16 = ops.add_ln(x32, res32, g, b, eps, want16=lowp, group_row_end=ends)
+    return Act(y32, y16)
+
+
+# ----------------------------------------------------------------------------------------------
+# blocks
+# ----------------------------------------------------------------------------------------------
+class SelfFFNPack:
+    """Weights of BertAttention + BertIntermediate + BertOutput for one or several stacked streams."""
+
+    def __init__(self, attns, inters, outs):
+        # attns: modules with .self.{query,key,value} and .output.{dense,LayerNorm}
+        self.qkv = LinearPack([w for a in attns for w in (a.self.query.weight, a.self.key.weight, a.self.value.weight)],
+                              [b for a in attns for b in (a.self.query.bias, a.self.key.bias, a.self.value.bias)])
+        self.o = LinearPack([a.output.dense.weight for a in attns], [a.output.dense.bias for a in attns])
+        self.ln1 = LNPack([a.output.LayerNorm for a in attns])
+        self.w1 = LinearPack([m.dense.weight for m in inters], [m.dense.bias for m in inters])
+        self.w2 = LinearPack([m.dense.weight for m in outs], [m.dense.bias for m in outs])
+        self.ln2 = LNPack([m.LayerNorm for m in outs])
+
+
+def self_attn_ffn(x: Act, pk: SelfFFNPack, streams: List[Stream], ends, lowp: bool, eps=1e-12) -> Act:
+    """Post-LN BERT layer: LN(x + O(attn(QKV(x)))) then LN(y + W2 gelu(W1 y)).
+    Reference: BertLayer, VLN-DUET/map_nav_src/models/vilmodel.py:196-209 (and :80-194)."""
+    xin = x.operand(lowp)
+    rows = xin.shape[0]
+    w, b = pk.qkv.get(lowp)
+    qkv = ops.gemm(xin, w, b, group_row_end=ends)                      # [rows, 2304]
+    ctx = torch.empty((rows, HIDDEN), dtype=xin.dtype, device=xin.device)
+    if len(streams) > 1:
+        ctx.zero_()            # rows between streams feed the next GEMM: keep them finite
+    for s in streams:
+        q = s.view(qkv)
+        ops.attention(q[:, 0:HIDDEN], q[:, HIDDEN:2 * HIDDEN], q[:, 2 * HIDDEN:3 * HIDDEN], s.B, s.L, s.L,
+                      key_mask=s.mask, pair_dist=s.pair_dist, bias_affine=s.bias_affine, out=s.view(ctx))
+    w, b = pk.o.get(lowp)
+    ao = ops.gemm(ctx, w, b, residual=x.f32, out_dtype=F32, group_row_end=ends)
+    y = layer_norm(ao, None, pk.ln1, eps, lowp, ends)
+    return ffn(y, pk.w1, pk.w2, pk.ln2, ends, lowp, eps)
+
+
+def ffn(y: Act, w1: LinearPack, w2: LinearPack, ln2: LNPack, ends, lowp: bool, eps=1e-12) -> Act:
+    w, b = w1.get(lowp)
+    h = ops.gemm(y.operand(lowp), w, b, epilogue=EPI_GELU, group_row_end=ends)   # [rows, 3072]
+    w, b = w2.get(lowp)
+    fo = ops.gemm(h, w, b, residual=y.f32, out_dtype=F32, group_row_end=ends)
+    return layer_norm(fo, None, ln2, eps, lowp, ends)
+
+
+class CrossPack:
+    """BertXAttention weights: query / output per stream group; key+value stacked per context user."""
+
+    def __init__(self, xatts):
+        self.q = LinearPack([x.att.query.weight for x in xatts], [x.att.query.bias for x in xatts])
+        self.kv = LinearPack([w for x in xatts for w in (x.att.key.weight, x.att.value.weight)],
+                             [b for x in xatts for b in (x.att.key.bias, x.att.value.bias)])
+        self.o = LinearPack([x.output.dense.weight for x in xatts], [x.output.dense.bias for x in xatts])
+        self.ln = LNPack([x.output.LayerNorm for x in xatts])
+
+
+def cross_attn(x: Act, kv: torch.Tensor, kv_col0: Sequence[int], ctx_len: int, ctx_mask, pk: CrossPack,
+               streams: List[Stream], ends, lowp: bool, eps=1e-12) -> Act:
+    """LN(x + O(attn(Q(x), K(ctx), V(ctx)))).  kv holds the projected context [B*ctx_len, *] with this
+    stream's K at columns kv_col0[i] and V at kv_col0[i]+768.
+    Reference: BertXAttention, VLN-DUET/map_nav_src/models/vilmodel.py:302-364."""
+    xin = x.operand(lowp)
+    rows = xin.shape[0]
+    w, b = pk.q.get(lowp)
+    q = ops.gemm(xin, w, b, group_row_end=ends)
+    ctx = torch.empty((rows, HIDDEN), dtype=xin.dtype, device=xin.device)
+    if len(streams) > 1:
+        ctx.zero_()
+    for s, c0 in zip(streams, kv_col0):
+        ops.attention(s.view(q), kv[:, c0:c0 + HIDDEN], kv[:, c0 + HIDDEN:c0 + 2 * HIDDEN], s.B, s.L, ctx_len,
+                      key_mask=ctx_mask, out=s.view(ctx))
+    w, b = pk.o.get(lowp)
+    ao = ops.gemm(ctx, w, b, residual=x.f32, out_dtype=F32, group_row_end=ends)
+    return layer_norm(ao, None, pk.ln, eps, lowp, ends)
+
+
+def as_act(x32: torch.Tensor, lowp: bool) -> Act:
+    """fp32 rows -> activation pair (adds the bf16 operand copy in bf16 mode)."""
+    x32 = x32.contiguous()
+    return Act(x32, ops.cast_bf16(x32) if lowp else None)
+
+
+def mask_u8(m: Optional[torch.Tensor]):
+    return None if m is None else m.to(torch.uint8).contiguous()

@@ -1,0 +1,471 @@
+// vi_rows.cu - HBM-bound row kernels: one warp per 768-wide row, fp32 statistics via warp shuffles,
+// 16-byte coalesced accesses (lane l touches float4 #(l + 32 j), j = 0..5, of its row).
+//
+// LayerNorm / residual / embedding sums / action-logit tail / aux-loss reductions of
+// VLN-DUET/map_nav_src/models/vilmodel.py and VLN-HAMT/finetune_src/models/vilmodel_cmt.py; each
+// entry point cites its reference lines in include/vlnimagine.h.
+#include "vi_common.cuh"
+
+namespace {
+
+constexpr int D = VI_HIDDEN;     // 768
+constexpr int V4 = D / 128;      // 6 float4 per lane
+constexpr int ROWS_PER_BLOCK = 4;
+
+struct Row {
+  float v[V4 * 4];
+};
+
+__device__ __forceinline__ void row_zero(Row& r) {
+#pragma unroll
+  for (int i = 0; i < V4 * 4; ++i) r.v[i] = 0.f;
+}
+__device__ __forceinline__ void row_load(Row& r, const float* __restrict__ src, int lane) {
+  const float4* s4 = reinterpret_cast<const float4*>(src);
+#pragma unroll
+  for (int j = 0; j < V4; ++j) {
+    const float4 t = __ldg(s4 + lane + 32 * j);
+    r.v[4 * j] = t.x; r.v[4 * j + 1] = t.y; r.v[4 * j + 2] = t.z; r.v[4 * j + 3] = t.w;
+  }
+}
+__device__ __forceinline__ void row_add(Row& r, const float* __restrict__ src, int lane) {
+  const float4* s4 = reinterpret_cast<const float4*>(src);
+#pragma unroll
+  for (int j = 0; j < V4; ++j) {
+    const float4 t = __ldg(s4 + lane + 32 * j);
+    r.v[4 * j] += t.x; r.v[4 * j + 1] += t.y; r.v[4 * j + 2] += t.z; r.v[4 * j + 3] += t.w;
+  }
+}
+__device__ __forceinline__ void row_acc(Row& r, const Row& o) {
+#pragma unroll
+  for (int i = 0; i < V4 * 4; ++i) r.v[i] += o.v[i];
+}
+// in-place LayerNorm over the 768 values held by the warp (biased variance, like torch)
+__device__ __forceinline__ void row_layernorm(Row& r, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                              float eps, int lane) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < V4 * 4; ++i) s += r.v[i];
+  const float mean = warp_sum(s) * (1.0f / D);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < V4 * 4; ++i) { const float d = r.v[i] - mean; q = fmaf(d, d, q); }
+  const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + eps);
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(beta);
+#pragma unroll
+  for (int j = 0; j < V4; ++j) {
+    const float4 g = __ldg(g4 + lane + 32 * j), b = __ldg(b4 + lane + 32 * j);
+    r.v[4 * j] = (r.v[4 * j] - mean) * rstd * g.x + b.x;
+    r.v[4 * j + 1] = (r.v[4 * j + 1] - mean) * rstd * g.y + b.y;
+    r.v[4 * j + 2] = (r.v[4 * j + 2] - mean) * rstd * g.z + b.z;
+    r.v[4 * j + 3] = (r.v[4 * j + 3] - mean) * rstd * g.w + b.w;
+  }
+}
+__device__ __forceinline__ void row_store(const Row& r, float* y32, bf16* y16, long long row, int lane) {
+  if (y32) {
+    float4* o = reinterpret_cast<float4*>(y32 + row * D);
+#pragma unroll
+    for (int j = 0; j < V4; ++j) o[lane + 32 * j] = make_float4(r.v[4 * j], r.v[4 * j + 1], r.v[4 * j + 2], r.v[4 * j + 3]);
+  }
+  if (y16) {
+    uint2* o = reinterpret_cast<uint2*>(y16 + row * D);
+#pragma unroll
+    for (int j = 0; j < V4; ++j)
+      o[lane + 32 * j] = make_uint2(pack_bf16x2(r.v[4 * j], r.v[4 * j + 1]), pack_bf16x2(r.v[4 * j + 2], r.v[4 * j + 3]));
+  }
+}
+__device__ __forceinline__ float row_dot(const Row& a, const Row& b) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < V4 * 4; ++i) s = fmaf(a.v[i], b.v[i], s);
+  return warp_sum(s);
+}
+
+#define ROW_INDEX()                                                           \
+  const int lane = threadIdx.x & 31;                                          \
+  const long long row = (long long)blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5)
+
+// ---------------------------------------------------------------------------------------------
+struct RowGroups {
+  int n;
+  int end[4];
+};
+__device__ __forceinline__ int group_of_row(const RowGroups& g, long long row) {
+  int i = 0;
+  while (i < g.n - 1 && row >= g.end[i]) ++i;
+  return i;
+}
+
+__global__ void __launch_bounds__(128) add_ln_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                     const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                     float eps, float* y32, bf16* y16, long long rows, const RowGroups grp) {
+  ROW_INDEX();
+  if (row >= rows) return;
+  const int gi = group_of_row(grp, row);
+  gamma += gi * D;
+  beta += gi * D;
+  Row r;
+  row_load(r, a + row * D, lane);
+  if (b) row_add(r, b + row * D, lane);
+  row_layernorm(r, gamma, beta, eps, lane);
+  row_store(r, y32, y16, row, lane);
+}
+
+__global__ void __launch_bounds__(128) embed_compose_kernel(const vi_embed_args p) {
+  ROW_INDEX();
+  if (row >= p.rows) return;
+  Row acc;
+  row_zero(acc);
+  if (p.a) {
+    Row t;
+    row_load(t, p.a + row * D, lane);
+    if (p.a_gamma) row_layernorm(t, p.a_gamma, p.a_beta, p.eps, lane);
+    row_acc(acc, t);
+  }
+  if (p.feat) {
+    Row t;
+    float f[16];
+    for (int k = 0; k < p.feat_dim; ++k) f[k] = __ldg(p.feat + row * p.feat_dim + k);
+#pragma unroll
+    for (int j = 0; j < V4; ++j) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int c = (lane + 32 * j) * 4 + e;
+        float s = p.feat_b ? __ldg(p.feat_b + c) : 0.f;
+        const float* wr = p.feat_w + (long long)c * p.feat_dim;
+        for (int k = 0; k < p.feat_dim; ++k) s = fmaf(f[k], __ldg(wr + k), s);
+        t.v[4 * j + e] = s;
+      }
+    }
+    if (p.feat_gamma) row_layernorm(t, p.feat_gamma, p.feat_beta, p.eps, lane);
+    row_acc(acc, t);
+  }
+  if (p.idx) row_add(acc, p.table + p.idx[row] * D, lane);
+  if (p.pos_table) row_add(acc, p.pos_table + (row % p.pos_period) * D, lane);
+  if (p.const_row) row_add(acc, p.const_row, lane);
+  if (p.const_row2) row_add(acc, p.const_row2, lane);
+  if (p.out_gamma) row_layernorm(acc, p.out_gamma, p.out_beta, p.eps, lane);
+  row_store(acc, p.y32, reinterpret_cast<bf16*>(p.y16), row, lane);
+}
+
+__global__ void __launch_bounds__(128) ln_dot_kernel(const float* __restrict__ h, const float* __restrict__ gamma,
+                                                     const float* __restrict__ beta, float eps,
+                                                     const float* __restrict__ w, const float* __restrict__ bias,
+                                                     float* out, long long rows, const RowGroups grp) {
+  ROW_INDEX();
+  if (row >= rows) return;
+  const int gi = group_of_row(grp, row);
+  gamma += gi * D;
+  beta += gi * D;
+  w += gi * D;
+  if (bias) bias += gi;
+  Row r, wv;
+  row_load(r, h + row * D, lane);
+  row_layernorm(r, gamma, beta, eps, lane);
+  row_load(wv, w, lane);
+  const float d = row_dot(r, wv);
+  if (lane == 0) out[row] = d + (bias ? __ldg(bias) : 0.f);
+}
+
+__global__ void __launch_bounds__(128) mul_bcast_kernel(const float* __restrict__ x, const float* __restrict__ s,
+                                                        long long lds, float* y32, bf16* y16, long long rows,
+                                                        int rows_per_batch) {
+  ROW_INDEX();
+  if (row >= rows) return;
+  Row r, m;
+  row_load(r, x + row * D, lane);
+  row_load(m, s + (row / rows_per_batch) * lds, lane);
+#pragma unroll
+  for (int i = 0; i < V4 * 4; ++i) r.v[i] *= m.v[i];
+  row_store(r, y32, y16, row, lane);
+}
+
+// one thread per episode: the per-episode fusion is a short sequential walk (G, P <= ~100)
+__global__ void duet_fuse_logits_kernel(const float* __restrict__ g_raw, const float* __restrict__ l_raw,
+                                        const float* __restrict__ fuse_raw, const uint8_t* __restrict__ gmap_masks,
+                                        const uint8_t* __restrict__ gmap_visited, const uint8_t* __restrict__ vp_nav,
+                                        const int32_t* __restrict__ gmap_to_cand, const uint8_t* __restrict__ cand_visited,
+                                        float* global_logits, float* local_logits, float* fused_logits, int B, int G,
+                                        int P) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const float fw = 1.0f / (1.0f + expf(-fuse_raw[b]));
+  const float ninf = -INFINITY;
+  float* ll = local_logits + (long long)b * P;
+  float bw = 0.f;
+  for (int v = 0; v < P; ++v) {
+    const float x = vp_nav[(long long)b * P + v] ? l_raw[(long long)b * P + v] * (1.0f - fw) : ninf;
+    ll[v] = x;
+    if (v > 0 && cand_visited[(long long)b * P + v]) bw += x;
+  }
+  for (int j = 0; j < G; ++j) {
+    const long long i = (long long)b * G + j;
+    float x = g_raw[i] * fw;
+    if (gmap_visited[i] || !gmap_masks[i]) x = ninf;
+    global_logits[i] = x;
+    float f = x;
+    if (j == 0) f += ll[0];
+    else {
+      const int c = gmap_to_cand[i];
+      if (c >= 0) f += ll[c];
+      else if (c == -1) f += bw;
+    }
+    fused_logits[i] = f;
+  }
+}
+
+__global__ void mask_logits_navtype_kernel(const float* __restrict__ raw, const int64_t* __restrict__ nav_types,
+                                           float* out, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = nav_types[i] == 0 ? -INFINITY : raw[i];
+}
+
+__global__ void __launch_bounds__(128) gather_mean_kernel(const float* __restrict__ src, const int32_t* __restrict__ offsets,
+                                                          const int32_t* __restrict__ row_idx, float* out32, bf16* out16,
+                                                          long long rows) {
+  ROW_INDEX();
+  if (row >= rows) return;
+  Row acc;
+  row_zero(acc);
+  const int s = offsets[row], e = offsets[row + 1];
+  for (int t = s; t < e; ++t) row_add(acc, src + (long long)row_idx[t] * D, lane);
+  // torch.mean = sum / n (true division); n == 0 never reaches the kernel (host filters empty rows)
+  const float n = (float)(e - s);
+#pragma unroll
+  for (int i = 0; i < V4 * 4; ++i) acc.v[i] = acc.v[i] / n;
+  row_store(acc, out32, out16, row, lane);
+}
+
+__global__ void __launch_bounds__(128) scatter_rows_kernel(const float* __restrict__ src, const int32_t* __restrict__ dst_rows,
+                                                           float* dst, long long rows) {
+  ROW_INDEX();
+  if (row >= rows) return;
+  Row r;
+  row_load(r, src + row * D, lane);
+  row_store(r, dst, nullptr, dst_rows[row], lane);
+}
+
+// 1 - cos(p, t) with torch's cosine_similarity clamping: x.y / (max(|x|,eps) * max(|y|,eps))
+__global__ void __launch_bounds__(128) cosine_loss_kernel(const float* __restrict__ proj, const float* __restrict__ tgt,
+                                                          float* loss_rows, long long rows) {
+  ROW_INDEX();
+  if (row >= rows) return;
+  Row a, b;
+  row_load(a, proj + row * D, lane);
+  row_load(b, tgt + row * D, lane);
+  const float ab = row_dot(a, b), aa = row_dot(a, a), bb = row_dot(b, b);
+  if (lane == 0) loss_rows[row] = 1.0f - ab / (fmaxf(sqrtf(aa), 1e-8f) * fmaxf(sqrtf(bb), 1e-8f));
+}
+
+// single-block deterministic mean of n floats (n <= a few thousand)
+__global__ void __launch_bounds__(256) mean_kernel(const float* __restrict__ x, float* out, int n) {
+  __shared__ float sh[8];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += 256) s += x[i];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += sh[i];
+    *out = n > 0 ? t / (float)n : 0.f;
+  }
+}
+
+// sims[r, 0] = cos(proj r, tgt r)/T ; sims[r, 1+n] = cos(proj r, negs n)/T ; one warp per (r, column)
+__global__ void __launch_bounds__(128) infonce_sims_kernel(const float* __restrict__ proj, const float* __restrict__ tgt,
+                                                           const float* __restrict__ negs, float inv_t, float* sims,
+                                                           int R, int n_negs) {
+  const int lane = threadIdx.x & 31;
+  const long long item = (long long)blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5);
+  const int cols = n_negs + 1;
+  if (item >= (long long)R * cols) return;
+  const int r = (int)(item / cols), c = (int)(item % cols);
+  Row a, b;
+  row_load(a, proj + (long long)r * D, lane);
+  row_load(b, c == 0 ? tgt + (long long)r * D : negs + (long long)(c - 1) * D, lane);
+  const float ab = row_dot(a, b), aa = row_dot(a, a), bb = row_dot(b, b);
+  if (lane == 0) sims[item] = ab / (fmaxf(sqrtf(aa), 1e-8f) * fmaxf(sqrtf(bb), 1e-8f)) * inv_t;
+}
+// loss_r = logsumexp over {col 0} U {negatives of other episodes} - sims[r,0]; one warp per row
+__global__ void __launch_bounds__(128) infonce_rows_kernel(const float* __restrict__ sims, const int32_t* __restrict__ row_ep,
+                                                           const int32_t* __restrict__ neg_ep, float* loss_rows, int R,
+                                                           int n_negs) {
+  ROW_INDEX();
+  if (row >= R) return;
+  const int cols = n_negs + 1;
+  const float* s = sims + row * cols;
+  const int ep = row_ep[row];
+  float mx = s[0];
+  for (int c = 1 + lane; c < cols; c += 32)
+    if (neg_ep[c - 1] != ep) mx = fmaxf(mx, s[c]);
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int c = 1 + lane; c < cols; c += 32)
+    if (neg_ep[c - 1] != ep) sum += expf(s[c] - mx);
+  sum = warp_sum(sum) + expf(s[0] - mx);
+  if (lane == 0) loss_rows[row] = mx + logf(sum) - s[0];
+}
+
+__global__ void cast_bf16_kernel(const float* __restrict__ src, bf16* dst, long long n4, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n4) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(src) + i);
+    reinterpret_cast<uint2*>(dst)[i] = make_uint2(pack_bf16x2(t.x, t.y), pack_bf16x2(t.z, t.w));
+  }
+  if (i == 0) for (long long j = n4 * 4; j < n; ++j) dst[j] = __float2bfloat16_rn(src[j]);
+}
+
+inline unsigned row_grid(long long rows) { return (unsigned)((rows + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK); }
+inline bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+inline bool make_groups(RowGroups& g, int n_groups, const int32_t* ends, long long rows) {
+  if (n_groups < 1 || n_groups > 4 || (n_groups > 1 && !ends)) return false;
+  g.n = n_groups;
+  for (int i = 0; i < 4; ++i) g.end[i] = 0x7fffffff;
+  for (int i = 0; i < n_groups && n_groups > 1; ++i) {
+    if (ends[i] <= 0 || (i > 0 && ends[i] <= ends[i - 1])) return false;
+    g.end[i] = ends[i];
+  }
+  (void)rows;
+  return true;
+}
+
+}  // namespace
+
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" int vi_add_ln(const float* a, const float* b, const float* gamma, const float* beta, float eps, float* y32,
+                         void* y16, int64_t rows, int n_groups, const int32_t* group_row_end, vi_stream_t stream) {
+  RowGroups grp;
+  VI_CHECK_ARG(make_groups(grp, n_groups, group_row_end, rows), "vi_add_ln: bad row groups");
+  VI_CHECK_ARG(a && gamma && beta && (y32 || y16), "vi_add_ln: null operand");
+  VI_CHECK_ARG(aligned16(a) && aligned16(b) && aligned16(gamma) && aligned16(beta) && aligned16(y32) && ((uintptr_t)y16 & 7) == 0,
+               "vi_add_ln: operands must be 16-byte aligned");
+  if (rows <= 0) return VI_OK;
+  add_ln_kernel<<<row_grid(rows), 128, 0, ST(stream)>>>(a, b, gamma, beta, eps, y32, reinterpret_cast<bf16*>(y16), rows, grp);
+  VI_LAUNCH_CHECK();
+  return VI_OK;
+}
+
+extern "C" int vi_embed_compose(const vi_embed_args* args, vi_stream_t stream) {
+  VI_CHECK_ARG(args, "vi_embed_compose: null args");
+  const vi_embed_args& p = *args;
+  VI_CHECK_ARG(p.y32 || p.y16, "vi_embed_compose: no output");
+  VI_CHECK_ARG(!p.feat || (p.feat_dim > 0 && p.feat_dim <= 16 && p.feat_w), "vi_embed_compose: feat_dim=%d out of range (1..16)", p.feat_dim);
+  VI_CHECK_ARG(!p.idx || p.table, "vi_embed_compose: idx without table");
+  VI_CHECK_ARG(!p.pos_table || p.pos_period > 0, "vi_embed_compose: pos_table without pos_period");
+  VI_CHECK_ARG(!p.a_gamma || p.a_beta, "vi_embed_compose: a_gamma without a_beta");
+  VI_CHECK_ARG(!p.feat_gamma || p.feat_beta, "vi_embed_compose: feat_gamma without feat_beta");
+  VI_CHECK_ARG(!p.out_gamma || p.out_beta, "vi_embed_compose: out_gamma without out_beta");
+  VI_CHECK_ARG(aligned16(p.a) && aligned16(p.table) && aligned16(p.pos_table) && aligned16(p.const_row) &&
+                   aligned16(p.const_row2) && aligned16(p.y32) && ((uintptr_t)p.y16 & 7) == 0,
+               "vi_embed_compose: row operands must be 16-byte aligned");
+  if (p.rows <= 0) return VI_OK;
+  embed_compose_kernel<<<row_grid(p.rows), 128, 0, ST(stream)>>>(p);
+  VI_LAUNCH_CHECK();
+  return VI_OK;
+}
+
+extern "C" int vi_ln_dot(const float* h, const float* gamma, const float* beta, float eps, const float* w, const float* b,
+                         float* out, int64_t rows, int n_groups, const int32_t* group_row_end, vi_stream_t stream) {
+  RowGroups grp;
+  VI_CHECK_ARG(make_groups(grp, n_groups, group_row_end, rows), "vi_ln_dot: bad row groups");
+  VI_CHECK_ARG(h && gamma && beta && w && out, "vi_ln_dot: null operand");
+  VI_CHECK_ARG(aligned16(h) && aligned16(gamma) && aligned16(beta) && aligned16(w), "vi_ln_dot: operands must be 16-byte aligned");
+  if (rows <= 0) return VI_OK;
+  ln_dot_kernel<<<row_grid(rows), 128, 0, ST(stream)>>>(h, gamma, beta, eps, w, b, out, rows, grp);
+  VI_LAUNCH_CHECK();
+  return VI_OK;
+}
+
+extern "C" int vi_mul_bcast(const float* x, const float* s, int64_t lds, float* y32, void* y16, int64_t rows,
+                            int rows_per_batch, vi_stream_t stream) {
+  VI_CHECK_ARG(x && s && (y32 || y16) && rows_per_batch > 0, "vi_mul_bcast: bad operands");
+  VI_CHECK_ARG(aligned16(x) && aligned16(s) && lds % 4 == 0 && aligned16(y32) && ((uintptr_t)y16 & 7) == 0, "vi_mul_bcast: misaligned operands");
+  if (rows <= 0) return VI_OK;
+  mul_bcast_kernel<<<row_grid(rows), 128, 0, ST(stream)>>>(x, s, lds, y32, reinterpret_cast<bf16*>(y16), rows, rows_per_batch);
+  VI_LAUNCH_CHECK();
+  return VI_OK;
+}
+
+extern "C" int vi_duet_fuse_logits(const float* g_raw, const float* l_raw, const float* fuse_raw, const uint8_t* gmap_masks,
+                                   const uint8_t* gmap_visited, const uint8_t* vp_nav_masks, const int32_t* gmap_to_cand,
+                                   const uint8_t* cand_visited, float* global_logits, float* local_logits,
+                                   float* fused_logits, int B, int G, int P, vi_stream_t stream) {
+  VI_CHECK_ARG(g_raw && l_raw && fuse_raw && gmap_masks && gmap_visited && vp_nav_masks && gmap_to_cand && cand_visited &&
+                   global_logits && local_logits && fused_logits, "vi_duet_fuse_logits: null operand");
+  VI_CHECK_ARG(B > 0 && G > 0 && P > 0, "vi_duet_fuse_logits: empty problem");
+  duet_fuse_logits_kernel<<<(B + 63) / 64, 64, 0, ST(stream)>>>(g_raw, l_raw, fuse_raw, gmap_masks, gmap_visited, vp_nav_masks,
+                                                               gmap_to_cand, cand_visited, global_logits, local_logits,
+                                                               fused_logits, B, G, P);
+  VI_LAUNCH_CHECK();
+  return VI_OK;
+}
+
+extern "C" int vi_mask_logits_navtype(const float* raw, const int64_t* nav_types, float* out, int64_t n, vi_stream_t stream) {
+  VI_CHECK_ARG(raw && nav_types && out, "vi_mask_logits_navtype: null operand");
+  if (n <= 0) return VI_OK;
+  mask_logits_navtype_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ST(stream)>>>(raw, nav_types, out, n);
+  VI_LAUNCH_CHECK();
+  return VI_OK;
+}
+
+extern "C" int vi_gather_mean(const float* src, const int32_t* offsets, const int32_t* row_idx, float* out32, void* out16,
+                              int R, vi_stream_t stream) {
+  VI_CHECK_ARG(src && offsets && row_idx && (out32 || out16), "vi_gather_mean: null operand");
+  VI_CHECK_ARG(aligned16(src) && aligned16(out32) && ((uintptr_t)out16 & 7) == 0, "vi_gather_mean: misaligned operands");
+  if (R <= 0) return VI_OK;
+  gather_mean_kernel<<<row_grid(R), 128, 0, ST(stream)>>>(src, offsets, row_idx, out32, reinterpret_cast<bf16*>(out16), R);
+  VI_LAUNCH_CHECK();
+  return VI_OK;
+}
+
+extern "C" int vi_scatter_rows(const float* src, const int32_t* dst_rows, float* dst, int R, vi_stream_t stream) {
+  VI_CHECK_ARG(src && dst_rows && dst, "vi_scatter_rows: null operand");
+  VI_CHECK_ARG(aligned16(src) && aligned16(dst), "vi_scatter_rows: misaligned operands");
+  if (R <= 0) return VI_OK;
+  scatter_rows_kernel<<<row_grid(R), 128, 0, ST(stream)>>>(src, dst_rows, dst, R);
+  VI_LAUNCH_CHECK();
+  return VI_OK;
+}
+
+extern "C" int vi_cosine_loss(const float* proj, const float* tgt, float* loss_rows, float* loss_mean, int R,
+                              vi_stream_t stream) {
+  VI_CHECK_ARG(loss_mean && (R == 0 || (proj && tgt && loss_rows)), "vi_cosine_loss: null operand");
+  VI_CHECK_ARG(aligned16(proj) && aligned16(tgt), "vi_cosine_loss: misaligned operands");
+  if (R > 0) cosine_loss_kernel<<<row_grid(R), 128, 0, ST(stream)>>>(proj, tgt, loss_rows, R);
+  mean_kernel<<<1, 256, 0, ST(stream)>>>(loss_rows, loss_mean, R);
+  VI_LAUNCH_CHECK();
+  return VI_OK;
+}
+
+extern "C" int vi_infonce_loss(const float* proj, const float* tgt, const float* negs, const int32_t* row_episode,
+                               const int32_t* neg_episode, float temperature, float* loss_rows, float* loss_mean, int R,
+                               int n_negs, vi_stream_t stream) {
+  // loss_rows doubles as scratch: it must hold R * (n_negs + 1) + R floats (sims first, losses after)
+  VI_CHECK_ARG(loss_mean && (R == 0 || (proj && tgt && loss_rows && row_episode)), "vi_infonce_loss: null operand");
+  VI_CHECK_ARG(n_negs == 0 || (negs && neg_episode), "vi_infonce_loss: negatives missing");
+  VI_CHECK_ARG(temperature > 0.f, "vi_infonce_loss: temperature must be positive");
+  float* sims = loss_rows;
+  float* rows_out = loss_rows + (long long)R * (n_negs + 1);
+  if (R > 0) {
+    const long long items = (long long)R * (n_negs + 1);
+    infonce_sims_kernel<<<row_grid(items), 128, 0, ST(stream)>>>(proj, tgt, negs, 1.0f / temperature, sims, R, n_negs);
+    infonce_rows_kernel<<<row_grid(R), 128, 0, ST(stream)>>>(sims, row_episode, neg_episode, rows_out, R, n_negs);
+  }
+  mean_kernel<<<1, 256, 0, ST(stream)>>>(rows_out, loss_mean, R);
+  VI_LAUNCH_CHECK();
+  return VI_OK;
+}
+
+extern "C" int vi_cast_bf16(const float* src, void* dst, int64_t n, vi_stream_t stream) {
+  VI_CHECK_ARG(src && dst, "vi_cast_bf16: null operand");
+  VI_CHECK_ARG(aligned16(src) && ((uintptr_t)dst & 7) == 0, "vi_cast_bf16: misaligned operands");
+  if (n <= 0) return VI_OK;
+  const long long n4 = n / 4;
+  const long long threads = n4 > 0 ? n4 : 1;
+  cast_bf16_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, ST(stream)>>>(src, reinterpret_cast<bf16*>(dst), n4, n);
+  VI_LAUNCH_CHECK();
+  return VI_OK;
+}

@@ -1,0 +1,215 @@
+"""Thin tensor-level wrappers over the C ABI (include/vlnimagine.h).
+
+PyTorch is used for device memory and streams only: every function here validates its tensors,
+allocates the output with torch.empty and launches one libvlnimagine kernel on the current
+stream.  Nothing falls back to ATen arithmetic.
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import lib, check, EPI_NONE, EPI_GELU, EPI_RELU, MASK_ADD_NEG10000, MASK_NEG_INF  # noqa: F401
+
+HIDDEN = 768
+HEADS = 12
+BF16, F32 = torch.bfloat16, torch.float32
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need_cuda(t: torch.Tensor, name: str):
+    if not t.is_cuda:
+        raise _lib.VlnImagineError('%s must be a CUDA tensor: vln-imagine_b200 has no CPU path' % name)
+
+
+def ensure_init(t: torch.Tensor):
+    _need_cuda(t, 'tensor')
+    _lib.init(t.device.index if t.device.index is not None else torch.cuda.current_device())
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _rows2d(t: torch.Tensor, name: str):
+    if t.dim() != 2 or t.stride(1) != 1:
+        raise _lib.VlnImagineError('%s must be a 2-D row-major view (got shape %s strides %s)' % (name, tuple(t.shape), t.stride()))
+    return t.shape[0], t.shape[1], t.stride(0)
+
+
+def pad128(n: int) -> int:
+    return (n + 127) // 128 * 128
+
+
+def gemm(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None,
+         residual: Optional[torch.Tensor] = None, epilogue: int = EPI_NONE,
+         out_dtype: torch.dtype = BF16, group_row_end: Optional[Sequence[int]] = None,
+         out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Y = epi(X W^T + bias) + residual.  x bf16 -> tcgen05 kernel; x fp32 -> fp32 check-mode kernel.
+    w is [n_groups*N, K]; group_row_end (python ints) splits the rows of x between the weight blocks."""
+    M, K, ldx = _rows2d(x, 'x')
+    n_groups = 1 if group_row_end is None else len(group_row_end)
+    if w.dim() != 2 or not w.is_contiguous() or w.shape[1] != K or w.shape[0] % n_groups:
+        raise _lib.VlnImagineError('weight shape %s does not match x %s / %d groups' % (tuple(w.shape), tuple(x.shape), n_groups))
+    N = w.shape[0] // n_groups
+    ends = _lib.int_array(list(group_row_end)) if group_row_end is not None else None
+    ldr = residual.stride(0) if residual is not None else 0
+    if x.dtype == BF16:
+        if w.dtype != BF16:
+            raise _lib.VlnImagineError('bf16 GEMM needs a bf16 weight')
+        if out is None:
+            out = torch.empty((M, N), dtype=out_dtype, device=x.device)
+        check(lib.vi_gemm_bf16(x.data_ptr(), ldx, w.data_ptr(), _ptr(bias), _ptr(residual), ldr, out.data_ptr(),
+                               out.stride(0), _lib.DT_F32 if out.dtype == F32 else _lib.DT_BF16, M, N, K, epilogue,
+                               n_groups, ends, _stream()), 'vi_gemm_bf16')
+    elif x.dtype == F32:
+        if w.dtype != F32:
+            raise _lib.VlnImagineError('fp32 GEMM needs an fp32 weight')
+        if out is None:
+            out = torch.empty((M, N), dtype=F32, device=x.device)
+        check(lib.vi_gemm_f32(x.data_ptr(), ldx, w.data_ptr(), _ptr(bias), _ptr(residual), ldr, out.data_ptr(),
+                              out.stride(0), M, N, K, epilogue, n_groups, ends, _stream()), 'vi_gemm_f32')
+    else:
+        raise _lib.VlnImagineError('unsupported GEMM dtype %s' % x.dtype)
+    return out
+
+
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, B: int, Lq: int, Lk: int,
+              key_mask: Optional[torch.Tensor] = None, pair_dist: Optional[torch.Tensor] = None,
+              bias_affine: Optional[torch.Tensor] = None, mask_mode: int = MASK_ADD_NEG10000,
+              out: Optional[torch.Tensor] = None, lse: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """q [B*Lq, >=768 view], k/v [B*Lk, view] -> o [B*Lq, 768]; 12 heads of 64."""
+    _, _, ldq = _rows2d(q, 'q')
+    _, _, ldk = _rows2d(k, 'k')
+    _, _, ldv = _rows2d(v, 'v')
+    if out is None:
+        out = torch.empty((B * Lq, HIDDEN), dtype=q.dtype, device=q.device)
+    if key_mask is not None and (key_mask.dtype != torch.uint8 or not key_mask.is_contiguous()):
+        raise _lib.VlnImagineError('key_mask must be a contiguous uint8 tensor')
+    check(lib.vi_attn_fwd(q.data_ptr(), ldq, k.data_ptr(), ldk, v.data_ptr(), ldv, out.data_ptr(), out.stride(0),
+                          _lib.DT_BF16 if q.dtype == BF16 else _lib.DT_F32, _ptr(key_mask), _ptr(pair_dist),
+                          _ptr(bias_affine), _ptr(lse), B, HEADS, Lq, Lk, mask_mode, _stream()), 'vi_attn_fwd')
+    return out
+
+
+def add_ln(a: torch.Tensor, b: Optional[torch.Tensor], gamma: torch.Tensor, beta: torch.Tensor, eps: float,
+           want16: bool, want32: bool = True, group_row_end: Optional[Sequence[int]] = None):
+    """LayerNorm(a [+ b]); returns (y32 or None, y16 or None)."""
+    rows = a.shape[0]
+    y32 = torch.empty((rows, HIDDEN), dtype=F32, device=a.device) if want32 else None
+    y16 = torch.empty((rows, HIDDEN), dtype=BF16, device=a.device) if want16 else None
+    n_groups = 1 if group_row_end is None else len(group_row_end)
+    ends = _lib.int_array(list(group_row_end)) if group_row_end is not None else None
+    check(lib.vi_add_ln(a.data_ptr(), _ptr(b), gamma.data_ptr(), beta.data_ptr(), eps, _ptr(y32), _ptr(y16), rows,
+                        n_groups, ends, _stream()), 'vi_add_ln')
+    return y32, y16
+
+
+def embed_compose(rows: int, device, *, a=None, a_ln=None, feat=None, feat_w=None, feat_b=None, feat_ln=None,
+                  idx=None, table=None, pos_table=None, pos_period=0, const_row=None, const_row2=None,
+                  out_ln=None, eps=1e-12, y32=None, y16=None, want16=False, want32=True):
+    """See vi_embed_compose.  *_ln are (gamma, beta) pairs.  y32 / y16 may be preallocated row views."""
+    if y32 is None and want32:
+        y32 = torch.empty((rows, HIDDEN), dtype=F32, device=device)
+    if y16 is None and want16:
+        y16 = torch.empty((rows, HIDDEN), dtype=BF16, device=device)
+    args = _lib.EmbedArgs()
+    args.a = _ptr(a)
+    if a_ln is not None:
+        args.a_gamma, args.a_beta = a_ln[0].data_ptr(), a_ln[1].data_ptr()
+    if feat is not None:
+        args.feat, args.feat_dim = feat.data_ptr(), feat.shape[-1]
+        args.feat_w, args.feat_b = feat_w.data_ptr(), _ptr(feat_b)
+        if feat_ln is not None:
+            args.feat_gamma, args.feat_beta = feat_ln[0].data_ptr(), feat_ln[1].data_ptr()
+    if idx is not None:
+        args.idx, args.table = idx.data_ptr(), table.data_ptr()
+    if pos_table is not None:
+        args.pos_table, args.pos_period = pos_table.data_ptr(), pos_period
+    args.const_row, args.const_row2 = _ptr(const_row), _ptr(const_row2)
+    if out_ln is not None:
+        args.out_gamma, args.out_beta = out_ln[0].data_ptr(), out_ln[1].data_ptr()
+    args.eps = eps
+    args.y32, args.y16, args.rows = _ptr(y32), _ptr(y16), rows
+    check(lib.vi_embed_compose(args, _stream()), 'vi_embed_compose')
+    return y32, y16
+
+
+def ln_dot(h: torch.Tensor, gamma, beta, eps: float, w, b, group_row_end: Optional[Sequence[int]] = None):
+    rows = h.shape[0]
+    out = torch.empty((rows,), dtype=F32, device=h.device)
+    n_groups = 1 if group_row_end is None else len(group_row_end)
+    ends = _lib.int_array(list(group_row_end)) if group_row_end is not None else None
+    check(lib.vi_ln_dot(h.data_ptr(), gamma.data_ptr(), beta.data_ptr(), eps, w.data_ptr(), _ptr(b), out.data_ptr(),
+                        rows, n_groups, ends, _stream()), 'vi_ln_dot')
+    return out
+
+
+def mul_bcast(x: torch.Tensor, s: torch.Tensor, rows_per_batch: int, want16: bool, want32: bool = True):
+    rows = x.shape[0]
+    y32 = torch.empty((rows, HIDDEN), dtype=F32, device=x.device) if want32 else None
+    y16 = torch.empty((rows, HIDDEN), dtype=BF16, device=x.device) if want16 else None
+    check(lib.vi_mul_bcast(x.data_ptr(), s.data_ptr(), s.stride(0), _ptr(y32), _ptr(y16), rows, rows_per_batch,
+                           _stream()), 'vi_mul_bcast')
+    return y32, y16
+
+
+def duet_fuse_logits(g_raw, l_raw, fuse_raw, gmap_masks_u8, gmap_visited_u8, vp_nav_u8, gmap_to_cand, cand_visited_u8,
+                     B: int, G: int, P: int):
+    dev = g_raw.device
+    gl = torch.empty((B, G), dtype=F32, device=dev)
+    ll = torch.empty((B, P), dtype=F32, device=dev)
+    fl = torch.empty((B, G), dtype=F32, device=dev)
+    check(lib.vi_duet_fuse_logits(g_raw.data_ptr(), l_raw.data_ptr(), fuse_raw.data_ptr(), gmap_masks_u8.data_ptr(),
+                                  gmap_visited_u8.data_ptr(), vp_nav_u8.data_ptr(), gmap_to_cand.data_ptr(),
+                                  cand_visited_u8.data_ptr(), gl.data_ptr(), ll.data_ptr(), fl.data_ptr(), B, G, P,
+                                  _stream()), 'vi_duet_fuse_logits')
+    return gl, ll, fl
+
+
+def mask_logits_navtype(raw: torch.Tensor, nav_types: torch.Tensor):
+    out = torch.empty_like(raw)
+    check(lib.vi_mask_logits_navtype(raw.data_ptr(), nav_types.data_ptr(), out.data_ptr(), raw.numel(), _stream()),
+          'vi_mask_logits_navtype')
+    return out
+
+
+def gather_mean(src: torch.Tensor, offsets: torch.Tensor, row_idx: torch.Tensor, R: int, want16: bool, want32: bool = True):
+    y32 = torch.empty((R, HIDDEN), dtype=F32, device=src.device) if want32 else None
+    y16 = torch.empty((R, HIDDEN), dtype=BF16, device=src.device) if want16 else None
+    check(lib.vi_gather_mean(src.data_ptr(), offsets.data_ptr(), row_idx.data_ptr(), _ptr(y32), _ptr(y16), R, _stream()),
+          'vi_gather_mean')
+    return y32, y16
+
+
+def scatter_rows(src: torch.Tensor, dst_rows: torch.Tensor, dst: torch.Tensor):
+    check(lib.vi_scatter_rows(src.data_ptr(), dst_rows.data_ptr(), dst.data_ptr(), src.shape[0], _stream()), 'vi_scatter_rows')
+    return dst
+
+
+def cosine_loss(proj: Optional[torch.Tensor], tgt: Optional[torch.Tensor], R: int, device):
+    loss = torch.empty((), dtype=F32, device=device)
+    rows = torch.empty((max(R, 1),), dtype=F32, device=device)
+    check(lib.vi_cosine_loss(_ptr(proj), _ptr(tgt), rows.data_ptr(), loss.data_ptr(), R, _stream()), 'vi_cosine_loss')
+    return loss, rows[:R]
+
+
+def infonce_loss(proj, tgt, negs, row_episode, neg_episode, temperature: float, R: int, n_negs: int, device):
+    loss = torch.empty((), dtype=F32, device=device)
+    scratch = torch.empty((max(R, 1) * (n_negs + 2),), dtype=F32, device=device)
+    check(lib.vi_infonce_loss(_ptr(proj), _ptr(tgt), _ptr(negs), _ptr(row_episode), _ptr(neg_episode), temperature,
+                              scratch.data_ptr(), loss.data_ptr(), R, n_negs, _stream()), 'vi_infonce_loss')
+    return loss
+
+
+def cast_bf16(src: torch.Tensor, dst: Optional[torch.Tensor] = None):
+    src = src.contiguous()
+    if dst is None:
+        dst = torch.empty(src.shape, dtype=BF16, device=src.device)
+    check(lib.vi_cast_bf16(src.data_ptr(), dst.data_ptr(), src.numel(), _stream()), 'vi_cast_bf16')
+    return dst
