@@ -141,14 +141,17 @@ int vi_mul_bcast(const float* x, const float* s, int64_t lds, float* y32, void* 
                  int64_t rows, int rows_per_batch, vi_stream_t stream);
 
 /* Action-logit masking and global/local fusion, D/models/vilmodel.py:1182-1217.
- *   fuse = sigmoid(fuse_raw[b]); global = g_raw*fuse, -inf at visited|padded nodes;
- *   local = l_raw*(1-fuse), -inf at non-navigable views;
- *   fused[b,0] = global[b,0]+local[b,0]; for j>0: gmap_to_cand[b,j] >= 0 -> += local[b, that];
- *   == -1 -> += sum of local[b, v] over cand_visited[b, v] (in ascending v); == -2 -> nothing.
- * The int32 map replaces the reference's per-sample dict look-ups on viewpoint-id strings. */
+ *   fuse = sigmoid(fuse_raw[b]) (0.5 when fuse_raw == NULL: sap_fuse_linear is None);
+ *   global = g_raw*fuse, -inf at visited|padded nodes; local = l_raw*(1-fuse), -inf at non-navigable views;
+ *   fused = global; fused[b,0] += local[b,0]; for every node j>0 whose id is not in the visited set:
+ *   += local[b, v] of the (last) unvisited candidate v>0 with the same id, else += the sum of local[b, v]
+ *   over visited candidates v>0 (ascending v).
+ * gmap_ids [B,G] / cand_ids [B,P] are the viewpoint-id strings of gmap_vpids / vp_cand_vpids interned to
+ * int32 on the host (padding: -1 in gmap_ids, -2 in cand_ids); the visited set is derived on the device
+ * from gmap_visited, which replaces the reference's per-sample Python dict look-ups. */
 int vi_duet_fuse_logits(const float* g_raw, const float* l_raw, const float* fuse_raw,
                         const uint8_t* gmap_masks, const uint8_t* gmap_visited, const uint8_t* vp_nav_masks,
-                        const int32_t* gmap_to_cand, const uint8_t* cand_visited,
+                        const int32_t* gmap_ids, const int32_t* cand_ids,
                         float* global_logits, float* local_logits, float* fused_logits,
                         int B, int G, int P, vi_stream_t stream);
 
@@ -173,6 +176,14 @@ int vi_infonce_loss(const float* proj, const float* tgt, const float* negs,
                     const int32_t* row_episode, const int32_t* neg_episode,
                     float temperature, float* scratch, float* loss_mean,
                     int R, int n_negs, vi_stream_t stream);
+
+/* dst[b, r, 0:768] = src[b, r, 0:768] for n_batches x rows_per_batch rows; strides in ELEMENTS.  Writes an
+ * fp32 and/or a bf16 copy.  Builds the cross-attention context cat([txt_embeds, imagine_embeds], 1)
+ * (D/models/vilmodel.py:1157, H/models/vilmodel_cmt.py:1110) and gathers the token-0 rows that feed
+ * sap_fuse_linear (D/models/vilmodel.py:1185-1187). */
+int vi_copy_rows(const float* src, int64_t src_batch_stride, int64_t src_row_stride, float* dst32, void* dst16,
+                 int64_t dst_batch_stride, int64_t dst_row_stride, int64_t n_batches, int rows_per_batch,
+                 vi_stream_t stream);
 
 /* fp32 -> bf16 shadow copy of a weight or activation */
 int vi_cast_bf16(const float* src, void* dst, int64_t n, vi_stream_t stream);

@@ -262,24 +262,62 @@ def test_infonce(ops):
     assert abs(float(loss) - float(torch.stack(ref).mean())) < 1e-4
 
 
-def test_fuse_logits_and_navtype_mask(ops):
-    B, G, P = 5, 9, 7
+def _fuse_reference(global_logits, local_logits, gmap_vpids, visited, vp_cand_vpids):
+    """the per-episode python loop of the reference (VLN-DUET/map_nav_src/models/vilmodel.py:1198-1217)"""
+    fused = global_logits.clone()
+    fused[:, 0] += local_logits[:, 0]
+    for i in range(global_logits.shape[0]):
+        vis = set(vp for vp, m in zip(gmap_vpids[i], visited[i].tolist()) if m)
+        tmp, bw = {}, 0
+        for j, c in enumerate(vp_cand_vpids[i]):
+            if j > 0:
+                if c in vis:
+                    bw = bw + local_logits[i, j]
+                else:
+                    tmp[c] = local_logits[i, j]
+        for j, vp in enumerate(gmap_vpids[i]):
+            if j > 0 and vp not in vis:
+                fused[i, j] += tmp[vp] if vp in tmp else bw
+    return fused
+
+
+@pytest.mark.parametrize('use_fuse', [True, False])
+def test_fuse_logits_and_navtype_mask(ops, use_fuse):
+    import importlib
+    duet = importlib.import_module('vln_imagine_b200.duet')
+    B, G, P = 6, 40, 37
+    g = torch.Generator().manual_seed(0)
     g_raw, l_raw, f_raw = _rand(B, G, seed=1), _rand(B, P, seed=2), _rand(B, seed=3)
-    gm = torch.ones(B, G, dtype=torch.uint8, device='cuda'); gm[:, 7:] = 0
-    gv = torch.zeros(B, G, dtype=torch.uint8, device='cuda'); gv[:, 1:3] = 1
-    nav = torch.zeros(B, P, dtype=torch.uint8, device='cuda'); nav[:, :4] = 1
-    to_cand = torch.full((B, G), -1, dtype=torch.int32, device='cuda')
-    to_cand[:, 3] = 2; to_cand[:, 4] = 3; to_cand[:, 1:3] = -2; to_cand[:, 0] = -2
-    cand_vis = torch.zeros(B, P, dtype=torch.uint8, device='cuda'); cand_vis[:, 1] = 1
-    gl, ll, fl = ops.duet_fuse_logits(g_raw, l_raw, f_raw, gm, gv, nav, to_cand, cand_vis, B, G, P)
-    fw = torch.sigmoid(f_raw)[:, None]
-    rg = (g_raw * fw).masked_fill(gv.bool(), float('-inf')).masked_fill(~gm.bool(), float('-inf'))
-    rl = (l_raw * (1 - fw)).masked_fill(~nav.bool(), float('-inf'))
-    rf = rg.clone()
-    rf[:, 0] += rl[:, 0]
-    rf[:, 3] += rl[:, 2]
-    rf[:, 4] += rl[:, 3]
-    rf[:, 5:] += rl[:, 1:2]
+    gm = torch.zeros(B, G, dtype=torch.bool); gv = torch.zeros(B, G, dtype=torch.bool)
+    nav = torch.zeros(B, P, dtype=torch.bool)
+    gmap_vpids, cand_vpids = [], []
+    for b in range(B):
+        n = int(torch.randint(6, G + 1, (1,), generator=g))
+        nv = int(torch.randint(1, n - 3, (1,), generator=g))
+        gm[b, :n] = True
+        gv[b, 1:1 + nv] = True
+        ids = [None] + ['n%d_%d' % (b, j) for j in range(1, n)]
+        gmap_vpids.append(ids)
+        nc = int(torch.randint(2, min(7, n - nv), (1,), generator=g))
+        cands = [ids[1 + int(torch.randint(0, nv, (1,), generator=g))]]              # one visited candidate
+        cands += [ids[j] for j in range(1 + nv, 1 + nv + nc - 1)]                    # unvisited ones in the graph
+        if b == 0:
+            cands.append('not_in_graph')
+        if b == 1:
+            cands.append(cands[-1])                                                  # duplicate id: the last one wins
+            cands.append(ids[1])                                                     # a second visited candidate
+        cand_vpids.append([None] + cands)
+        nav[b, :len(cands) + 1] = True
+    gids = torch.from_numpy(duet._IdTable().encode(gmap_vpids, G, -1))
+    tab = duet._IdTable()
+    gids = torch.from_numpy(tab.encode(gmap_vpids, G, -1)).cuda()
+    cids = torch.from_numpy(tab.encode(cand_vpids, P, -2)).cuda()
+    u8 = lambda t: t.to(torch.uint8).cuda()   # noqa: E731
+    gl, ll, fl = ops.duet_fuse_logits(g_raw, l_raw, f_raw if use_fuse else None, u8(gm), u8(gv), u8(nav), gids, cids, B, G, P)
+    fw = torch.sigmoid(f_raw)[:, None] if use_fuse else 0.5
+    rg = (g_raw * fw).masked_fill(gv.cuda(), float('-inf')).masked_fill(~gm.cuda(), float('-inf'))
+    rl = (l_raw * (1 - fw)).masked_fill(~nav.cuda(), float('-inf'))
+    rf = _fuse_reference(rg.cpu(), rl.cpu(), gmap_vpids, gv, cand_vpids).cuda()
     for a, b in ((gl, rg), (ll, rl), (fl, rf)):
         assert torch.equal(torch.isinf(a), torch.isinf(b))
         fin = torch.isfinite(b)
@@ -287,6 +325,21 @@ def test_fuse_logits_and_navtype_mask(ops):
     types = torch.randint(0, 3, (B, P), device='cuda')
     out = ops.mask_logits_navtype(l_raw, types)
     assert torch.equal(out, l_raw.masked_fill(types == 0, float('-inf')))
+
+
+def test_copy_rows(ops):
+    B, L, I = 3, 5, 2
+    txt, img = _rand(B, L, 768, seed=1), _rand(B, I, 768, seed=2)
+    C = L + I
+    c32 = torch.zeros(B * C, 768, device='cuda')
+    c16 = torch.zeros(B * C, 768, dtype=torch.bfloat16, device='cuda')
+    ops.copy_rows(txt, L * 768, 768, B, L, c32, c16, C * 768, 768)
+    ops.copy_rows(img, I * 768, 768, B, I, c32[L:], c16[L:], C * 768, 768)
+    ref = torch.cat([txt, img], 1).view(B * C, 768)
+    assert torch.equal(c32, ref) and torch.equal(c16, ref.bfloat16())
+    first = torch.zeros(B, 1536, device='cuda')
+    ops.copy_rows(txt, L * 768, 768, B, 1, first[:, 768:], None, 1536, 768)
+    assert torch.equal(first[:, 768:], txt[:, 0]) and float(first[:, :768].abs().max()) == 0
 
 
 def test_cast_bf16(ops):

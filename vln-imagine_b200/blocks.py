@@ -218,3 +218,52 @@ def as_act(x32: torch.Tensor, lowp: bool) -> Act:
 
 def mask_u8(m: Optional[torch.Tensor]):
     return None if m is None else m.to(torch.uint8).contiguous()
+
+
+class PanoLayerPack:
+    """Weights of one pre-norm TransformerEncoderLayer of the panorama encoder."""
+
+    def __init__(self, layer):
+        self.norm1 = LNPack([layer.norm1])
+        self.qkv = LinearPack([layer.self_attn.in_proj_weight], [layer.self_attn.in_proj_bias])
+        self.o = LinearPack([layer.self_attn.out_proj.weight], [layer.self_attn.out_proj.bias])
+        self.norm2 = LNPack([layer.norm2])
+        self.w1 = LinearPack([layer.linear1.weight], [layer.linear1.bias])
+        self.w2 = LinearPack([layer.linear2.weight], [layer.linear2.bias])
+
+
+def pano_layer(x32: torch.Tensor, pk: PanoLayerPack, B: int, L: int, key_mask, lowp: bool, eps=1e-5) -> torch.Tensor:
+    """Pre-norm layer: x += O(attn(QKV(LN1 x))) ; x += W2 gelu(W1 LN2 x).  The key-padding mask is the
+    -inf kind of nn.MultiheadAttention.  Reference: TransformerEncoderLayer.forward_pre,
+    VLN-DUET/map_nav_src/models/transformer.py:170-182."""
+    h = layer_norm(x32, None, pk.norm1, eps, lowp)
+    w, b = pk.qkv.get(lowp)
+    qkv = ops.gemm(h.operand(lowp), w, b)
+    ctx = ops.attention(qkv[:, 0:HIDDEN], qkv[:, HIDDEN:2 * HIDDEN], qkv[:, 2 * HIDDEN:3 * HIDDEN], B, L, L,
+                        key_mask=key_mask, mask_mode=MASK_NEG_INF)
+    w, b = pk.o.get(lowp)
+    x32 = ops.gemm(ctx, w, b, residual=x32, out_dtype=F32)
+    h = layer_norm(x32, None, pk.norm2, eps, lowp)
+    w, b = pk.w1.get(lowp)
+    f = ops.gemm(h.operand(lowp), w, b, epilogue=EPI_GELU)
+    w, b = pk.w2.get(lowp)
+    return ops.gemm(f, w, b, residual=x32, out_dtype=F32)
+
+
+class ClsHeadPack:
+    """ClsPrediction / NextActionPrediction weights for one or several row groups:
+    Linear -> ReLU -> LayerNorm -> Linear(768, 1)."""
+
+    def __init__(self, heads, last_index=3):
+        self.w0 = LinearPack([h.net[0].weight for h in heads], [h.net[0].bias for h in heads])
+        self.ln = LNPack([h.net[2] for h in heads])
+        self.w1 = StackPack([h.net[last_index].weight for h in heads])
+        self.b1 = StackPack([h.net[last_index].bias for h in heads])
+
+
+def cls_head(x: torch.Tensor, pk: ClsHeadPack, lowp: bool, ends=None, eps=1e-12) -> torch.Tensor:
+    """x [rows, K] operand (bf16 or fp32) -> raw logit per row (fp32)."""
+    w, b = pk.w0.get(lowp)
+    h = ops.gemm(x, w, b, epilogue=EPI_RELU, out_dtype=F32, group_row_end=ends)
+    g, be = pk.ln.get()
+    return ops.ln_dot(h, g, be, eps, pk.w1.get(), pk.b1.get(), group_row_end=ends)

@@ -181,35 +181,70 @@ __global__ void __launch_bounds__(128) mul_bcast_kernel(const float* __restrict_
   row_store(r, y32, y16, row, lane);
 }
 
-// one thread per episode: the per-episode fusion is a short sequential walk (G, P <= ~100)
-__global__ void duet_fuse_logits_kernel(const float* __restrict__ g_raw, const float* __restrict__ l_raw,
-                                        const float* __restrict__ fuse_raw, const uint8_t* __restrict__ gmap_masks,
-                                        const uint8_t* __restrict__ gmap_visited, const uint8_t* __restrict__ vp_nav,
-                                        const int32_t* __restrict__ gmap_to_cand, const uint8_t* __restrict__ cand_visited,
-                                        float* global_logits, float* local_logits, float* fused_logits, int B, int G,
-                                        int P) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
-  const float fw = 1.0f / (1.0f + expf(-fuse_raw[b]));
+// One warp per episode.  Viewpoint-id strings are interned to int32 on the host (gmap_ids: -1 = padding,
+// cand_ids: -2 = padding); set membership / dictionary look-ups of the reference become id comparisons here,
+// so no mask has to travel back to the host.  bw is accumulated sequentially in candidate order like the
+// reference's Python loop (same fp32 association).
+constexpr int FUSE_MAX = 512;
+__global__ void __launch_bounds__(32) duet_fuse_logits_kernel(const float* __restrict__ g_raw, const float* __restrict__ l_raw,
+                                                              const float* __restrict__ fuse_raw,
+                                                              const uint8_t* __restrict__ gmap_masks,
+                                                              const uint8_t* __restrict__ gmap_visited,
+                                                              const uint8_t* __restrict__ vp_nav,
+                                                              const int32_t* __restrict__ gmap_ids,
+                                                              const int32_t* __restrict__ cand_ids, float* global_logits,
+                                                              float* local_logits, float* fused_logits, int G, int P) {
+  __shared__ float ll[FUSE_MAX];
+  __shared__ int gid[FUSE_MAX];
+  __shared__ int cid[FUSE_MAX];
+  __shared__ uint8_t gvis[FUSE_MAX];      // node id is in the reference's `visited_nodes` set
+  __shared__ uint8_t cvis[FUSE_MAX];      // candidate id is in `visited_nodes`
+  __shared__ float bw_s;
+  const int b = blockIdx.x, lane = threadIdx.x;
+  const float fw = fuse_raw ? 1.0f / (1.0f + expf(-fuse_raw[b])) : 0.5f;
   const float ninf = -INFINITY;
-  float* ll = local_logits + (long long)b * P;
-  float bw = 0.f;
-  for (int v = 0; v < P; ++v) {
-    const float x = vp_nav[(long long)b * P + v] ? l_raw[(long long)b * P + v] * (1.0f - fw) : ninf;
+  for (int v = lane; v < P; v += 32) {
+    const long long i = (long long)b * P + v;
+    const float x = vp_nav[i] ? l_raw[i] * (1.0f - fw) : ninf;
     ll[v] = x;
-    if (v > 0 && cand_visited[(long long)b * P + v]) bw += x;
+    local_logits[i] = x;
+    cid[v] = cand_ids[i];
   }
-  for (int j = 0; j < G; ++j) {
+  for (int j = lane; j < G; j += 32) gid[j] = gmap_ids[(long long)b * G + j];
+  __syncwarp();
+  for (int j = lane; j < G; j += 32) {
+    bool in_set = false;
+    if (gid[j] != -1)
+      for (int k = 0; k < G; ++k) in_set |= (gid[k] == gid[j]) && gid[k] != -1 && gmap_visited[(long long)b * G + k];
+    gvis[j] = in_set;
+  }
+  for (int v = lane; v < P; v += 32) {
+    bool in_set = false;
+    if (cid[v] != -2)
+      for (int k = 0; k < G; ++k) in_set |= (gid[k] == cid[v]) && gid[k] != -1 && gmap_visited[(long long)b * G + k];
+    cvis[v] = in_set;
+  }
+  __syncwarp();
+  if (lane == 0) {
+    float bw = 0.f;
+    for (int v = 1; v < P; ++v)
+      if (cid[v] != -2 && cvis[v]) bw += ll[v];
+    bw_s = bw;
+  }
+  __syncwarp();
+  const float bw = bw_s;
+  for (int j = lane; j < G; j += 32) {
     const long long i = (long long)b * G + j;
     float x = g_raw[i] * fw;
     if (gmap_visited[i] || !gmap_masks[i]) x = ninf;
     global_logits[i] = x;
     float f = x;
     if (j == 0) f += ll[0];
-    else {
-      const int c = gmap_to_cand[i];
-      if (c >= 0) f += ll[c];
-      else if (c == -1) f += bw;
+    else if (gid[j] != -1 && !gvis[j]) {
+      int hit = -1;
+      for (int v = 1; v < P; ++v)
+        if (cid[v] != -2 && !cvis[v] && cid[v] == gid[j]) hit = v;      // dict semantics: the last one wins
+      f += hit >= 0 ? ll[hit] : bw;
     }
     fused_logits[i] = f;
   }
@@ -317,6 +352,31 @@ __global__ void cast_bf16_kernel(const float* __restrict__ src, bf16* dst, long 
   if (i == 0) for (long long j = n4 * 4; j < n; ++j) dst[j] = __float2bfloat16_rn(src[j]);
 }
 
+
+// dst[b, r, :] = src[b, r, :] for nb batches of `rpb` 768-wide rows with independent batch / row strides
+// (token concatenation [txt; imagine], token-0 gathers, fp32 -> bf16 operand copies)
+__global__ void __launch_bounds__(128) copy_rows_kernel(const float* __restrict__ src, long long src_bs, long long src_rs,
+                                                        float* dst32, bf16* dst16, long long dst_bs, long long dst_rs,
+                                                        long long rows, int rpb) {
+  ROW_INDEX();
+  if (row >= rows) return;
+  const long long b = row / rpb, r = row % rpb;
+  Row v;
+  row_load(v, src + b * src_bs + r * src_rs, lane);
+  const long long off = b * dst_bs + r * dst_rs;
+  if (dst32) {
+    float4* o = reinterpret_cast<float4*>(dst32 + off);
+#pragma unroll
+    for (int j = 0; j < V4; ++j) o[lane + 32 * j] = make_float4(v.v[4 * j], v.v[4 * j + 1], v.v[4 * j + 2], v.v[4 * j + 3]);
+  }
+  if (dst16) {
+    uint2* o = reinterpret_cast<uint2*>(dst16 + off);
+#pragma unroll
+    for (int j = 0; j < V4; ++j)
+      o[lane + 32 * j] = make_uint2(pack_bf16x2(v.v[4 * j], v.v[4 * j + 1]), pack_bf16x2(v.v[4 * j + 2], v.v[4 * j + 3]));
+  }
+}
+
 inline unsigned row_grid(long long rows) { return (unsigned)((rows + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK); }
 inline bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 inline bool make_groups(RowGroups& g, int n_groups, const int32_t* ends, long long rows) {
@@ -390,15 +450,15 @@ extern "C" int vi_mul_bcast(const float* x, const float* s, int64_t lds, float* 
 }
 
 extern "C" int vi_duet_fuse_logits(const float* g_raw, const float* l_raw, const float* fuse_raw, const uint8_t* gmap_masks,
-                                   const uint8_t* gmap_visited, const uint8_t* vp_nav_masks, const int32_t* gmap_to_cand,
-                                   const uint8_t* cand_visited, float* global_logits, float* local_logits,
+                                   const uint8_t* gmap_visited, const uint8_t* vp_nav_masks, const int32_t* gmap_ids,
+                                   const int32_t* cand_ids, float* global_logits, float* local_logits,
                                    float* fused_logits, int B, int G, int P, vi_stream_t stream) {
-  VI_CHECK_ARG(g_raw && l_raw && fuse_raw && gmap_masks && gmap_visited && vp_nav_masks && gmap_to_cand && cand_visited &&
+  VI_CHECK_ARG(g_raw && l_raw && gmap_masks && gmap_visited && vp_nav_masks && gmap_ids && cand_ids &&
                    global_logits && local_logits && fused_logits, "vi_duet_fuse_logits: null operand");
   VI_CHECK_ARG(B > 0 && G > 0 && P > 0, "vi_duet_fuse_logits: empty problem");
-  duet_fuse_logits_kernel<<<(B + 63) / 64, 64, 0, ST(stream)>>>(g_raw, l_raw, fuse_raw, gmap_masks, gmap_visited, vp_nav_masks,
-                                                               gmap_to_cand, cand_visited, global_logits, local_logits,
-                                                               fused_logits, B, G, P);
+  VI_CHECK_ARG(G <= FUSE_MAX && P <= FUSE_MAX, "vi_duet_fuse_logits: G=%d / P=%d exceed %d", G, P, FUSE_MAX);
+  duet_fuse_logits_kernel<<<B, 32, 0, ST(stream)>>>(g_raw, l_raw, fuse_raw, gmap_masks, gmap_visited, vp_nav_masks, gmap_ids,
+                                                   cand_ids, global_logits, local_logits, fused_logits, G, P);
   VI_LAUNCH_CHECK();
   return VI_OK;
 }
@@ -455,6 +515,23 @@ extern "C" int vi_infonce_loss(const float* proj, const float* tgt, const float*
     infonce_rows_kernel<<<row_grid(R), 128, 0, ST(stream)>>>(sims, row_episode, neg_episode, rows_out, R, n_negs);
   }
   mean_kernel<<<1, 256, 0, ST(stream)>>>(rows_out, loss_mean, R);
+  VI_LAUNCH_CHECK();
+  return VI_OK;
+}
+
+
+extern "C" int vi_copy_rows(const float* src, int64_t src_batch_stride, int64_t src_row_stride, float* dst32, void* dst16,
+                            int64_t dst_batch_stride, int64_t dst_row_stride, int64_t n_batches, int rows_per_batch,
+                            vi_stream_t stream) {
+  VI_CHECK_ARG(src && (dst32 || dst16) && rows_per_batch > 0, "vi_copy_rows: bad operands");
+  VI_CHECK_ARG(aligned16(src) && aligned16(dst32) && ((uintptr_t)dst16 & 7) == 0 && src_batch_stride % 4 == 0 &&
+                   src_row_stride % 4 == 0 && dst_batch_stride % 4 == 0 && dst_row_stride % 4 == 0,
+               "vi_copy_rows: pointers must be 16-byte aligned and strides multiples of 4 elements");
+  const long long rows = (long long)n_batches * rows_per_batch;
+  if (rows <= 0) return VI_OK;
+  copy_rows_kernel<<<row_grid(rows), 128, 0, ST(stream)>>>(src, src_batch_stride, src_row_stride, dst32,
+                                                          reinterpret_cast<bf16*>(dst16), dst_batch_stride, dst_row_stride,
+                                                          rows, rows_per_batch);
   VI_LAUNCH_CHECK();
   return VI_OK;
 }

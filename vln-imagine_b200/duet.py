@@ -1,0 +1,415 @@
+"""DUET-Imagine on libvlnimagine: drop-in for ``models.model.VLNBert`` / ``models.vilmodel.GlocalTextPathNavCMT``.
+
+Same constructor (``VLNBert(args)``), same ``forward(mode, batch)`` modes and return types, same
+parameter names as the reference (VLN-DUET/map_nav_src/models/model.py:12-48,
+models/vilmodel.py:1022-1288), so the reference's unmodified agent (r2r/agent.py) can hold it as
+``self.vln_bert``.  Every floating-point operation is a libvlnimagine kernel launch; torch is used
+for device memory, streams, views and integer / boolean plumbing (mask casts, length -> mask).
+
+Precision: ``model.precision = 'bf16'`` (default: bf16 tensor-core GEMM / attention operands, fp32
+accumulation, fp32 residual stream, LayerNorm, softmax and heads) or ``'fp32'`` (check mode).
+"""
+from __future__ import annotations
+
+import collections
+import os
+from typing import List, Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import blocks, ops, params
+from .blocks import Act, Stream
+from .config import duet_config
+from .ops import BF16, F32, HIDDEN
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    return t if (t.dtype == F32 and t.is_contiguous()) else t.float().contiguous()
+
+
+class _IdTable:
+    """Viewpoint-id strings -> int32 ids.  Ids only need to agree between gmap_vpids and vp_cand_vpids of
+    the same call; one growing table per model is the simplest way to guarantee that."""
+
+    def __init__(self):
+        self.ids = {}
+
+    def encode(self, lists, width: int, pad: int) -> np.ndarray:
+        out = np.full((len(lists), width), pad, np.int32)
+        ids = self.ids
+        for i, row in enumerate(lists):
+            for j, key in enumerate(row[:width]):
+                out[i, j] = ids.setdefault(key, len(ids))
+        return out
+
+
+class AlignRows:
+    """Host-side flattening of the ragged alignment inputs (sub_instr_imag_flag, noun_phrase_segs) of
+    AlignWithContrastiveLoss.forward (models/vilmodel.py:598-655) into index arrays:
+      row r  <->  imagination (b, i) that is flagged 'True' and has >= 1 noun phrase;
+      tok_offsets / tok_rows : tokens of all its noun-phrase spans (inclusive ends, duplicates kept);
+      np_offsets / np_rows / np_episode : one entry per noun phrase of every flagged sub-instruction
+      (the InfoNCE negatives, :716-741)."""
+
+    def __init__(self, B, L, I, flags, noun_phrase_segs):
+        slot, tok_off, tok_rows, ep = [], [0], [], []
+        np_off, np_rows, np_ep = [0], [], []
+        for b in range(B):
+            for i, f in enumerate(flags[b]):
+                if f != 'True':
+                    continue
+                spans = noun_phrase_segs[b][i]
+                for s, e in spans:
+                    if e >= s:
+                        np_rows.extend(b * L + t for t in range(s, e + 1))
+                        np_off.append(len(np_rows))
+                        np_ep.append(b)
+                if len(spans) == 0:
+                    continue
+                for s, e in spans:
+                    if not (0 <= s and e < L):
+                        raise ValueError('noun-phrase span [%d, %d] outside the instruction (L=%d)' % (s, e, L))
+                    tok_rows.extend(b * L + t for t in range(s, e + 1))
+                if i >= I:
+                    raise ValueError('imagination slot %d >= %d' % (i, I))
+                slot.append(b * I + i)
+                tok_off.append(len(tok_rows))
+                ep.append(b)
+        self.R, self.n_negs = len(slot), len(np_ep)
+        i32 = lambda x: torch.tensor(x, dtype=torch.int32)   # noqa: E731
+        self.slot, self.tok_off, self.tok_rows, self.ep = i32(slot), i32(tok_off), i32(tok_rows), i32(ep)
+        self.np_off, self.np_rows, self.np_ep = i32(np_off), i32(np_rows), i32(np_ep)
+        self.unit = torch.arange(self.R + 1, dtype=torch.int32)
+
+    def to(self, device):
+        for k in ('slot', 'tok_off', 'tok_rows', 'ep', 'np_off', 'np_rows', 'np_ep', 'unit'):
+            setattr(self, k, getattr(self, k).to(device, non_blocking=True))
+        return self
+
+
+def align_forward(model, align_txt_embeds, align_imagine_embeds, flags, noun_phrase_segs, lowp: bool):
+    """Shared by DUET and HAMT.  Returns (loss 0-d tensor, imagine embeds with projected rows written back)."""
+    cfg = model.config
+    B, L, _ = align_txt_embeds.shape
+    I = align_imagine_embeds.shape[1]
+    dev = align_txt_embeds.device
+    rows = AlignRows(B, L, I, flags, noun_phrase_segs).to(dev)
+    txt = _f32c(align_txt_embeds).view(B * L, HIDDEN)
+    img = _f32c(align_imagine_embeds).view(B * I, HIDDEN)
+    out = img.clone()
+    if rows.R == 0:
+        # the reference returns the python int 0 here (models/vilmodel.py:650-651); a 0-d tensor is a superset
+        return torch.zeros((), dtype=F32, device=dev), out.view(B, I, HIDDEN)
+    pk = model._pk()['align']
+    x32, x16 = ops.gather_mean(img, rows.unit, rows.slot, rows.R, want16=lowp, want32=not lowp)
+    x = x16 if lowp else x32
+    for j, lp in enumerate(pk):
+        w, _ = lp.get(lowp)
+        last = j == len(pk) - 1
+        x = ops.gemm(x, w, None, epilogue=ops.EPI_NONE if last else ops.EPI_RELU, out_dtype=F32 if (last or not lowp) else BF16)
+    proj = x
+    tgt, _ = ops.gather_mean(txt, rows.tok_off, rows.tok_rows, rows.R, want16=False)
+    if cfg.aux_loss_type == 'cosine':
+        loss, _ = ops.cosine_loss(proj, tgt, rows.R, dev)
+    elif cfg.aux_loss_type == 'contrastive-InfoNCE':
+        negs = None
+        if rows.n_negs:
+            negs, _ = ops.gather_mean(txt, rows.np_off, rows.np_rows, rows.n_negs, want16=False)
+        loss = ops.infonce_loss(proj, tgt, negs, rows.ep, rows.np_ep if rows.n_negs else None,
+                                float(cfg.infonce_temperature), rows.R, rows.n_negs, dev)
+    else:
+        raise NotImplementedError('aux_loss_type %r' % cfg.aux_loss_type)
+    ops.scatter_rows(proj, rows.slot, out)
+    return loss, out.view(B, I, HIDDEN)
+
+
+class GlocalTextPathNavCMT(nn.Module):
+    """models/vilmodel.py:1022-1288 (R2R configuration: no object branch)."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        if config.obj_feat_size > 0:
+            raise NotImplementedError('object branch (REVERIE/SOON, obj_feat_size > 0) is outside the hot path')
+        self.embeddings = params.BertEmbeddingsP(config)
+        self.lang_encoder = params.LayerStack('layer', [params.BertLayerP() for _ in range(config.num_l_layers)])
+        self.img_embeddings = params.DuetImageEmbeddingsP(config)
+        self.local_encoder = params.LocalVPEncoderP(config)
+        self.global_encoder = params.GlobalMapEncoderP(config)
+        self.global_sap_head = params.ClsPredictionP()
+        self.local_sap_head = params.ClsPredictionP()
+        self.sap_fuse_linear = params.ClsPredictionP(input_size=2 * HIDDEN) if config.glocal_fuse else None
+        if config.imagine_enc_pano:
+            if config.bypass_imag_encoder:
+                self.imagine_embeddings = params.BypassImagineEmbeddingsP()
+            else:
+                raise NotImplementedError('bypass_imag_encoder=False (imagination encoder) is not on the released path')
+            if config.use_cosine_aux_loss or config.no_loss_test:
+                if config.dataset == 'reverie':
+                    raise NotImplementedError('REVERIE alignment head is outside the hot path')
+                if config.aux_loss_type not in ('cosine', 'contrastive-InfoNCE'):
+                    raise NotImplementedError('aux_loss_type %r' % config.aux_loss_type)
+                self.contrastive_alignment_model = params.AlignModelP()
+        params.bert_init_(self)
+        if config.fix_lang_embedding or config.fix_local_branch:
+            for m in (self.embeddings, self.lang_encoder):
+                for p in m.parameters():
+                    p.requires_grad = False
+        if config.fix_pano_embedding or config.fix_local_branch:
+            for p in self.img_embeddings.parameters():
+                p.requires_grad = False
+        if config.fix_local_branch:
+            for m in (self.local_encoder, self.local_sap_head):
+                for p in m.parameters():
+                    p.requires_grad = False
+        self.precision = os.environ.get('VLN_IMAGINE_PRECISION', 'bf16')
+        self._packs = None
+        self._ids = _IdTable()
+
+    # -- derived weights ------------------------------------------------------------------------
+    def _pk(self):
+        if self._packs is None:
+            pk = {}
+            pk['lang'] = [blocks.SelfFFNPack([l.attention], [l.intermediate], [l.output]) for l in self.lang_encoder.layer]
+            ie = self.img_embeddings
+            pk['img_linear'] = blocks.LinearPack([ie.img_linear.weight], [ie.img_linear.bias])
+            pk['pano'] = [blocks.PanoLayerPack(l) for l in ie.pano_encoder.layers]
+            pk['pano_norm'] = blocks.LNPack([ie.pano_encoder.norm])
+            gl, ll = self.global_encoder.encoder.x_layers, self.local_encoder.encoder.x_layers
+            pk['x_cross'] = [blocks.CrossPack([g.visual_attention, l.visual_attention]) for g, l in zip(gl, ll)]
+            pk['x_self'] = [blocks.SelfFFNPack([g.visn_self_att, l.visn_self_att], [g.visn_inter, l.visn_inter],
+                                               [g.visn_output, l.visn_output]) for g, l in zip(gl, ll)]
+            pk['sap'] = blocks.ClsHeadPack([self.global_sap_head, self.local_sap_head])
+            if self.sap_fuse_linear is not None:
+                pk['fuse'] = blocks.ClsHeadPack([self.sap_fuse_linear])
+            if hasattr(self, 'contrastive_alignment_model'):
+                ip = self.contrastive_alignment_model.image_proj
+                pk['align'] = [blocks.LinearPack([ip.fc1.weight]), blocks.LinearPack([ip.fc2.weight]),
+                               blocks.LinearPack([ip.fc3.weight])]
+            self._packs = pk
+        return self._packs
+
+    def _apply(self, fn, *a, **k):          # .cuda() / .to(): derived tensors are rebuilt lazily
+        self._packs = None
+        return super()._apply(fn, *a, **k)
+
+    @property
+    def lowp(self):
+        if self.precision not in ('bf16', 'fp32'):
+            raise ValueError("precision must be 'bf16' or 'fp32'")
+        return self.precision == 'bf16'
+
+    def _guard(self, t: torch.Tensor):
+        ops.ensure_init(t)            # raises on CPU tensors: there is no fallback path
+
+    # -- modes ------------------------------------------------------------------------------------
+    def forward_text(self, txt_ids, txt_masks):
+        """'language': BertEmbeddings (:49-78) + 9 post-LN layers (:414-434); entry :1075-1079."""
+        self._guard(txt_ids)
+        lowp = self.lowp
+        B, L = txt_ids.shape
+        e = self.embeddings
+        y32, y16 = ops.embed_compose(B * L, txt_ids.device, idx=txt_ids.long().contiguous().view(-1), table=e.word_embeddings.weight,
+                                     pos_table=e.position_embeddings.weight, pos_period=L,
+                                     const_row=e.token_type_embeddings.weight[0],
+                                     out_ln=(e.LayerNorm.weight, e.LayerNorm.bias), want16=lowp)
+        x = Act(y32, y16)
+        s = [Stream(0, B, L, blocks.mask_u8(txt_masks))]
+        for pk in self._pk()['lang']:
+            x = blocks.self_attn_ffn(x, pk, s, None, lowp)
+        out = x.f32.view(B, L, HIDDEN)
+        if self.config.fix_lang_embedding:
+            out = out.detach()
+        return out
+
+    def forward_imagination(self, imagine_feats, imagine_masks=None):
+        """'imagine' (bypass encoder): features + type embedding 0.  :562-573, :1081-1085."""
+        self._guard(imagine_feats)
+        B, I, _ = imagine_feats.shape
+        y32, _ = ops.embed_compose(B * I, imagine_feats.device, a=_f32c(imagine_feats).view(B * I, HIDDEN),
+                                   const_row=self.imagine_embeddings.type_embedding.weight[0])
+        return y32.view(B, I, HIDDEN)
+
+    def forward_panorama_per_step(self, view_img_fts, obj_img_fts, loc_fts, nav_types, view_lens, obj_lens):
+        """'panorama'.  :1087-1131 + transformer.py:71-89,170-182."""
+        if obj_img_fts is not None:
+            raise NotImplementedError('object features are outside the R2R hot path')
+        self._guard(view_img_fts)
+        lowp = self.lowp
+        B, V, Fd = view_img_fts.shape
+        dev = view_img_fts.device
+        pk = self._pk()
+        ie = self.img_embeddings
+        v32 = _f32c(view_img_fts).view(B * V, Fd)
+        w, b = pk['img_linear'].get(lowp)
+        a = ops.gemm(ops.cast_bf16(v32) if lowp else v32, w, b, out_dtype=F32)
+        x32, _ = ops.embed_compose(
+            B * V, dev, a=a, a_ln=(ie.img_layer_norm.weight, ie.img_layer_norm.bias),
+            feat=_f32c(loc_fts).view(B * V, -1), feat_w=ie.loc_linear.weight, feat_b=ie.loc_linear.bias,
+            feat_ln=(ie.loc_layer_norm.weight, ie.loc_layer_norm.bias),
+            idx=nav_types.long().contiguous().view(-1), table=ie.nav_type_embedding.weight,
+            const_row=self.embeddings.token_type_embeddings.weight[1],
+            out_ln=(ie.layer_norm.weight, ie.layer_norm.bias))
+        pano_masks = torch.arange(V, device=dev)[None, :] < view_lens.to(dev)[:, None]      # ops.py:36-44
+        km = pano_masks.to(torch.uint8)
+        for lp in pk['pano']:
+            x32 = blocks.pano_layer(x32, lp, B, V, km, lowp)
+        g, be = pk['pano_norm'].get()
+        y32, _ = ops.add_ln(x32, None, g, be, 1e-12, want16=False)
+        out = y32.view(B, V, HIDDEN)
+        if self.config.fix_pano_embedding:
+            out = out.detach()
+        return out, pano_masks
+
+    def forward_navigation_per_step(self, txt_embeds, txt_masks, gmap_img_embeds, gmap_step_ids, gmap_pos_fts,
+                                    gmap_masks, gmap_pair_dists, gmap_visited_masks, gmap_vpids,
+                                    vp_img_embeds, vp_pos_fts, vp_masks, vp_nav_masks, vp_obj_masks, vp_cand_vpids,
+                                    imagine_embeds=None, imagine_masks=None):
+        """'navigation'.  :1133-1235."""
+        if vp_obj_masks is not None:
+            raise NotImplementedError('object grounding head is outside the R2R hot path')
+        self._guard(txt_embeds)
+        cfg, lowp, pk = self.config, self.lowp, self._pk()
+        dev = txt_embeds.device
+        B, L, _ = txt_embeds.shape
+        G, P = gmap_img_embeds.shape[1], vp_img_embeds.shape[1]
+        ge, le = self.global_encoder, self.local_encoder
+
+        # ---- input embeddings of both branches into one row-stacked activation (:1141-1152)
+        (r_g, r_l), ends, R = blocks.stack_layout([B * G, B * P])
+        x32 = torch.empty((R, HIDDEN), dtype=F32, device=dev)
+        x16 = torch.empty((R, HIDDEN), dtype=BF16, device=dev) if lowp else None
+        if ends[0] > B * G:
+            x32[B * G:ends[0]].zero_()
+            if lowp:
+                x16[B * G:ends[0]].zero_()
+        ops.embed_compose(B * G, dev, a=_f32c(gmap_img_embeds).view(B * G, HIDDEN),
+                          feat=_f32c(gmap_pos_fts).view(B * G, -1), feat_w=ge.gmap_pos_embeddings[0].weight,
+                          feat_b=ge.gmap_pos_embeddings[0].bias,
+                          feat_ln=(ge.gmap_pos_embeddings[1].weight, ge.gmap_pos_embeddings[1].bias),
+                          idx=gmap_step_ids.long().contiguous().view(-1), table=ge.gmap_step_embeddings.weight,
+                          y32=x32[r_g:r_g + B * G], y16=x16[r_g:r_g + B * G] if lowp else None)
+        ops.embed_compose(B * P, dev, a=_f32c(vp_img_embeds).view(B * P, HIDDEN),
+                          feat=_f32c(vp_pos_fts).view(B * P, -1), feat_w=le.vp_pos_embeddings[0].weight,
+                          feat_b=le.vp_pos_embeddings[0].bias,
+                          feat_ln=(le.vp_pos_embeddings[1].weight, le.vp_pos_embeddings[1].bias),
+                          y32=x32[r_l:r_l + B * P], y16=x16[r_l:r_l + B * P] if lowp else None)
+        x = Act(x32, x16)
+
+        # ---- context = [txt ; imagine] (:1157-1158)
+        txt = _f32c(txt_embeds)
+        if cfg.imagine_enc_pano and cfg.concat_imagine_with == 'language':
+            if imagine_embeds is None or imagine_masks is None:
+                raise ValueError('navigation needs imagine_embeds and imagine_masks when imagine_enc_pano is set')
+            I = imagine_embeds.shape[1]
+            C = L + I
+            ctx = torch.empty((B * C, HIDDEN), dtype=BF16 if lowp else F32, device=dev)
+            c32, c16 = (None, ctx) if lowp else (ctx, None)
+            ops.copy_rows(txt, L * HIDDEN, HIDDEN, B, L, c32, c16, C * HIDDEN, HIDDEN)
+            ops.copy_rows(_f32c(imagine_embeds), I * HIDDEN, HIDDEN, B, I, c32[L:] if c32 is not None else None,
+                          c16[L:] if c16 is not None else None, C * HIDDEN, HIDDEN)
+            ctx_mask = torch.cat([txt_masks, imagine_masks], 1).to(torch.uint8).contiguous()
+        else:
+            C = L
+            ctx = ops.cast_bf16(txt.view(B * L, HIDDEN)) if lowp else txt.view(B * L, HIDDEN)
+            ctx_mask = blocks.mask_u8(txt_masks)
+
+        affine = None
+        dist = None
+        if ge.sprel_linear is not None:                       # GASA bias (:1145-1149), applied inside the attention kernel
+            affine = torch.cat([ge.sprel_linear.weight.detach().view(1), ge.sprel_linear.bias.detach().view(1)]).float()
+            dist = _f32c(gmap_pair_dists)
+        streams = [Stream(r_g, B, G, blocks.mask_u8(gmap_masks), 0, dist, affine),
+                   Stream(r_l, B, P, blocks.mask_u8(vp_masks), 1)]
+
+        # ---- 4 graph-aware cross-modal layers, both branches per launch (:384-399, :444-453)
+        for cp, sp in zip(pk['x_cross'], pk['x_self']):
+            w, b = cp.kv.get(lowp)
+            kv = ops.gemm(ctx, w, b)                          # [B*C, 4*768] = K_g | V_g | K_l | V_l
+            x = blocks.cross_attn(x, kv, [0, 2 * HIDDEN], C, ctx_mask, cp, streams, ends, lowp)
+            x = blocks.self_attn_ffn(x, sp, streams, ends, lowp)
+
+        gmap_out = x.f32[r_g:r_g + B * G].view(B, G, HIDDEN)
+        vp_out = x.f32[r_l:r_l + B * P].view(B, P, HIDDEN)
+
+        # ---- heads (:1182-1196) and global/local fusion (:1198-1217)
+        fuse_raw = None
+        if self.sap_fuse_linear is not None:
+            cat = torch.empty((B, 2 * HIDDEN), dtype=BF16 if lowp else F32, device=dev)
+            c32, c16 = (None, cat) if lowp else (cat, None)
+            ops.copy_rows(x.f32[r_g:], G * HIDDEN, HIDDEN, B, 1, c32, c16, 2 * HIDDEN, HIDDEN)
+            ops.copy_rows(x.f32[r_l:], P * HIDDEN, HIDDEN, B, 1, c32[:, HIDDEN:] if c32 is not None else None,
+                          c16[:, HIDDEN:] if c16 is not None else None, 2 * HIDDEN, HIDDEN)
+            fuse_raw = blocks.cls_head(cat, pk['fuse'], lowp)
+        raw = blocks.cls_head(x.operand(lowp), pk['sap'], lowp, ends)
+        gmap_ids = torch.from_numpy(self._ids.encode(gmap_vpids, G, -1)).to(dev, non_blocking=True)
+        cand_ids = torch.from_numpy(self._ids.encode(vp_cand_vpids, P, -2)).to(dev, non_blocking=True)
+        if len(self._ids.ids) > (1 << 20):
+            self._ids = _IdTable()
+        gl, ll, fl = ops.duet_fuse_logits(raw[r_g:], raw[r_l:], fuse_raw, blocks.mask_u8(gmap_masks),
+                                          blocks.mask_u8(gmap_visited_masks), blocks.mask_u8(vp_nav_masks),
+                                          gmap_ids, cand_ids, B, G, P)
+        return {'gmap_embeds': gmap_out, 'vp_embeds': vp_out, 'global_logits': gl, 'local_logits': ll,
+                'fused_logits': fl, 'obj_logits': None}
+
+    def forward_align(self, batch):
+        """'align_with_contrastive_loss'.  :1246-1262 -> AlignWithContrastiveLoss(.WithNegativeSamples) :598-779."""
+        self._guard(batch['align_txt_embeds'])
+        txt = batch['align_txt_embeds']
+        if self.config.fix_lang_inside_cosine_model:
+            txt = txt.detach()
+        return align_forward(self, txt, batch['align_imagine_embeds'], batch['sub_instr_imag_flag'],
+                             batch['noun_phrase_segs'], self.lowp)
+
+    def forward(self, mode, batch, **kwargs):
+        """Mode dispatch, :1237-1288."""
+        if mode == 'language':
+            return self.forward_text(batch['txt_ids'], batch['txt_masks'])
+        if mode == 'imagine':
+            assert self.config.imagine_enc_pano
+            return self.forward_imagination(batch['imagine_feats'], batch['imagine_masks'])
+        if mode == 'align_with_contrastive_loss':
+            assert self.config.imagine_enc_pano
+            return self.forward_align(batch)
+        if mode == 'panorama':
+            return self.forward_panorama_per_step(batch['view_img_fts'], batch['obj_img_fts'], batch['loc_fts'],
+                                                  batch['nav_types'], batch['view_lens'], batch['obj_lens'])
+        if mode == 'navigation':
+            kw = {}
+            if self.config.imagine_enc_pano:
+                kw = dict(imagine_embeds=batch['imagine_embeds'], imagine_masks=batch['imagine_masks'])
+            return self.forward_navigation_per_step(
+                batch['txt_embeds'], batch['txt_masks'], batch['gmap_img_embeds'], batch['gmap_step_ids'],
+                batch['gmap_pos_fts'], batch['gmap_masks'], batch['gmap_pair_dists'], batch['gmap_visited_masks'],
+                batch['gmap_vpids'], batch['vp_img_embeds'], batch['vp_pos_fts'], batch['vp_masks'],
+                batch['vp_nav_masks'], batch['vp_obj_masks'], batch['vp_cand_vpids'], **kw)
+        raise NotImplementedError('wrong mode: %s' % mode)
+
+
+class VLNBert(nn.Module):
+    """models/model.py:12-48: mode dispatch + environment (feature) dropout on the panorama features."""
+
+    def __init__(self, args):
+        super().__init__()
+        self.args = args
+        self.vln_bert = GlocalTextPathNavCMT(duet_config(args))
+        ckpt = getattr(args, 'bert_ckpt_file', None)
+        if ckpt is not None:                                   # models/vlnbert_init.py:18-28
+            sd = {}
+            for k, v in torch.load(ckpt, map_location='cpu').items():
+                k = k[7:] if k.startswith('module') else k
+                sd[k[5:] if k.startswith('bert.') else k] = v
+            self.vln_bert.load_state_dict(sd, strict=False)
+        self.drop_env = nn.Dropout(p=getattr(args, 'feat_dropout', 0.0))
+
+    def forward(self, mode, batch):
+        batch = collections.defaultdict(lambda: None, batch)
+        if mode == 'panorama':
+            if self.training and self.drop_env.p > 0:
+                raise NotImplementedError('train-mode feature dropout runs through train.py')
+            return self.vln_bert(mode, batch)
+        if mode in ('language', 'imagine', 'align_with_contrastive_loss', 'navigation'):
+            return self.vln_bert(mode, batch)
+        raise NotImplementedError('wrong mode: %s' % mode)

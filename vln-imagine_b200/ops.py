@@ -159,15 +159,15 @@ def mul_bcast(x: torch.Tensor, s: torch.Tensor, rows_per_batch: int, want16: boo
     return y32, y16
 
 
-def duet_fuse_logits(g_raw, l_raw, fuse_raw, gmap_masks_u8, gmap_visited_u8, vp_nav_u8, gmap_to_cand, cand_visited_u8,
+def duet_fuse_logits(g_raw, l_raw, fuse_raw, gmap_masks_u8, gmap_visited_u8, vp_nav_u8, gmap_ids, cand_ids,
                      B: int, G: int, P: int):
     dev = g_raw.device
     gl = torch.empty((B, G), dtype=F32, device=dev)
     ll = torch.empty((B, P), dtype=F32, device=dev)
     fl = torch.empty((B, G), dtype=F32, device=dev)
-    check(lib.vi_duet_fuse_logits(g_raw.data_ptr(), l_raw.data_ptr(), fuse_raw.data_ptr(), gmap_masks_u8.data_ptr(),
-                                  gmap_visited_u8.data_ptr(), vp_nav_u8.data_ptr(), gmap_to_cand.data_ptr(),
-                                  cand_visited_u8.data_ptr(), gl.data_ptr(), ll.data_ptr(), fl.data_ptr(), B, G, P,
+    check(lib.vi_duet_fuse_logits(g_raw.data_ptr(), l_raw.data_ptr(), _ptr(fuse_raw), gmap_masks_u8.data_ptr(),
+                                  gmap_visited_u8.data_ptr(), vp_nav_u8.data_ptr(), gmap_ids.data_ptr(),
+                                  cand_ids.data_ptr(), gl.data_ptr(), ll.data_ptr(), fl.data_ptr(), B, G, P,
                                   _stream()), 'vi_duet_fuse_logits')
     return gl, ll, fl
 
@@ -205,6 +205,13 @@ def infonce_loss(proj, tgt, negs, row_episode, neg_episode, temperature: float, 
     check(lib.vi_infonce_loss(_ptr(proj), _ptr(tgt), _ptr(negs), _ptr(row_episode), _ptr(neg_episode), temperature,
                               scratch.data_ptr(), loss.data_ptr(), R, n_negs, _stream()), 'vi_infonce_loss')
     return loss
+
+
+def copy_rows(src: torch.Tensor, src_bs: int, src_rs: int, n_batches: int, rows_per_batch: int,
+              dst32: Optional[torch.Tensor], dst16: Optional[torch.Tensor], dst_bs: int, dst_rs: int):
+    """dst[b, r] = src[b, r] over 768-wide rows with element strides (see vi_copy_rows)."""
+    check(lib.vi_copy_rows(src.data_ptr(), src_bs, src_rs, _ptr(dst32), _ptr(dst16), dst_bs, dst_rs, n_batches,
+                           rows_per_batch, _stream()), 'vi_copy_rows')
 
 
 def cast_bf16(src: torch.Tensor, dst: Optional[torch.Tensor] = None):
