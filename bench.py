@@ -1,0 +1,453 @@
+#!/usr/bin/env python
+"""bench.py - nav-step decisions/sec of the VLN-Imagine hot path on B200 (BASELINE.json's metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload duet_cfg2|hamt_cfg3|duet_cfg5]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference          # the reference algorithm on the host CPU cores
+
+One "step" = one navigation decision for every episode of the batch = the two per-step model calls the
+reference agent makes (DUET: 'panorama' + 'navigation', VLN-DUET/map_nav_src/r2r/agent.py:467,500; HAMT:
+'visual' + 'history', VLN-HAMT/finetune_src/r2r/agent_cmt.py:538,604) on synthetic R2R-shaped inputs with
+random-init weights.  Episodes are independent, so N GPUs run N independent per-rank batches (weak
+scaling, no data-path collective); the time is the max over ranks of a CUDA-event interval.
+
+The JSON line carries: `value` (inputs resident in HBM, CUDA-graph replay of the step), `e2e` (the public
+module API with pinned HOST inputs copied in and the logits copied out every step), `roofline` (the tcgen05
+GEMM kernel: algorithmic FLOPs / CUDA-event time per launch vs MEASURED_PEAKS.json), `cpu_baseline` (the CPU
+oracle timed on this box's host cores), `clocks`, `gpu_launches`.
+"""
+import argparse
+import dataclasses
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = 'nav-step decisions/sec'
+UNIT = 'decisions/s'
+
+
+# ----------------------------------------------------------------------------------------------
+# workloads and algorithmic FLOPs (GEMM + attention, forward)
+# ----------------------------------------------------------------------------------------------
+def _lin(m, k, n):
+    return 2.0 * m * k * n
+
+
+def _bert(n):
+    return 4 * _lin(n, 768, 768) + 4.0 * n * n * 768 + 2 * _lin(n, 768, 3072)
+
+
+def _x(n, c):
+    return 2 * _lin(n, 768, 768) + 2 * _lin(c, 768, 768) + 4.0 * n * c * 768
+
+
+def _cls(n, k=768):
+    return _lin(n, k, 768) + _lin(n, 768, 1)
+
+
+def flops_per_decision(model, s):
+    C = s.instr_len + s.n_imagine
+    if model == 'duet':
+        G, P, V = s.n_nodes, s.n_views + 1, s.n_views
+        pano = _lin(V, 768, 768) + _lin(V, 7, 768) + 2 * _bert(V)
+        nav = (_lin(G, 7, 768) + _lin(P, 14, 768) + 4 * (_x(G, C) + _bert(G)) + 4 * (_x(P, C) + _bert(P))
+               + _cls(G) + _cls(P) + _cls(1, 1536))
+        return pano + nav
+    V, O = s.n_views, s.n_views + 1
+    nv = s.n_hist + 1 + O
+    hist = _lin(1, 768, 768) + _lin(1, 4, 768) + _lin(V, 768, 768) + _lin(V, 4, 768) + 2 * _bert(V)
+    visual = _lin(O, 768, 768) + _lin(O, 4, 768) + 4 * (_x(C, nv) + _x(nv, C) + _bert(C) + _bert(nv)) + _cls(O)
+    return hist + visual
+
+
+def workload(name):
+    import vln_imagine_b200.synth as synth
+    if name == 'duet_cfg2':
+        return 'duet', synth.CFG2, ('DUET-Imagine panorama+navigation forward, 64 episodes/GPU, 80-token instruction, '
+                                    '5 imaginations, 30-node graph (GASA bias), 36 views')
+    if name == 'duet_cfg5':
+        return 'duet', dataclasses.replace(synth.CFG5, batch=32), ('DUET-Imagine long horizon, 32 episodes/GPU, '
+                                                                   '200-token instruction, 12 imaginations, 100 nodes')
+    if name == 'hamt_cfg3':
+        return 'hamt', synth.CFG3, ('HAMT-Imagine visual+history forward, 64 episodes/GPU, 80-token instruction, '
+                                    '5 imaginations, 15-step history, 37 observations')
+    raise SystemExit('unknown workload %r' % name)
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks during the timed region
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x4: 'sw_power_cap', 0x8: 'hw_slowdown', 0x20: 'sw_thermal_slowdown', 0x40: 'hw_thermal_slowdown',
+               0x80: 'hw_power_brake_slowdown'}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.005)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join()
+
+    def summary(self):
+        return {'sm_mhz': statistics.median(self.samples) if self.samples else None, 'sm_max_mhz': self.max_mhz,
+                'reasons': sorted(self.reasons), 'samples': len(self.samples)}
+
+
+# ----------------------------------------------------------------------------------------------
+# the step (shared by all legs)
+# ----------------------------------------------------------------------------------------------
+DUET_PANO_KEYS = ('view_img_fts', 'loc_fts', 'nav_types', 'view_lens')
+DUET_NAV_KEYS = ('txt_masks', 'gmap_img_embeds', 'gmap_step_ids', 'gmap_pos_fts', 'gmap_masks', 'gmap_pair_dists',
+                 'gmap_visited_masks', 'vp_img_embeds', 'vp_pos_fts', 'vp_masks', 'vp_nav_masks', 'imagine_masks')
+HAMT_VIS_KEYS = ('txt_masks', 'ob_img_feats', 'ob_ang_feats', 'ob_nav_types', 'ob_masks', 'imagine_masks')
+HAMT_HIST_KEYS = ('hist_img_feats', 'hist_ang_feats', 'hist_pano_img_feats', 'hist_pano_ang_feats')
+
+
+def duet_step(model, d, txt, img):
+    pano, pano_masks = model('panorama', {k: d[k] for k in DUET_PANO_KEYS})
+    nav = model('navigation', {**{k: d[k] for k in DUET_NAV_KEYS}, 'txt_embeds': txt, 'imagine_embeds': img,
+                               'gmap_vpids': d['gmap_vpids'], 'vp_cand_vpids': d['vp_cand_vpids']})
+    return nav['fused_logits'], pano
+
+
+def hamt_step(model, d, txt, img):
+    out = model('visual', txt_embeds=txt, hist_embeds=d['hist_list'], hist_lens=d['hist_lens'], imagine_embeds=img,
+                **{k: d[k] for k in HAMT_VIS_KEYS})
+    h = model('history', ob_step=d['ob_step'], **{k: d[k] for k in HAMT_HIST_KEYS})
+    return out[0], h
+
+
+def build(model_kind, shape, rank, precision):
+    import vln_imagine_b200.synth as synth
+    from vln_imagine_b200 import config
+    if model_kind == 'duet':
+        from vln_imagine_b200 import duet
+        model = duet.VLNBert(config.default_duet_args()).cuda().eval()
+        ep = synth.duet_episode(shape, 1234 + rank)
+    else:
+        from vln_imagine_b200 import hamt
+        model = hamt.VLNBertCMT(config.default_hamt_args()).cuda().eval()
+        ep = synth.hamt_episode(shape, 1234 + rank)
+    shapes = {k: list(v.shape) for k, v in model.vln_bert.state_dict().items()}
+    model.vln_bert.load_state_dict(synth.synth_state_dict(shapes, seed=0))
+    model.vln_bert.precision = precision
+    return model, synth.to_torch(ep)
+
+
+def episode_prelude(model_kind, model, d):
+    """once per episode: language -> imagine -> align (not part of a step; timed separately)"""
+    if model_kind == 'duet':
+        txt = model('language', {'txt_ids': d['txt_ids'], 'txt_masks': d['txt_masks']})
+        img = model('imagine', {'imagine_feats': d['imagine_feats'], 'imagine_masks': None})
+        loss, img2 = model('align_with_contrastive_loss', {
+            'align_txt_embeds': txt, 'txt_masks': d['txt_masks'], 'align_imagine_embeds': img,
+            'imagine_masks': d['imagine_masks'], 'sub_instr_segs': d['sub_instr_segs'],
+            'sub_instr_imag_flag': d['sub_instr_imag_flag'], 'noun_phrase_segs': d['noun_phrase_segs'],
+            'obs_instr_ids': d['obs_instr_ids']})
+    else:
+        txt = model('language', txt_ids=d['txt_ids'], txt_masks=d['txt_masks'])
+        img = model('imagine', imagine_pano_img_feats=d['imagine_feats'], imagine_masks=None)
+        loss, img2 = model('align_with_contrastive_loss', align_txt_embeds=txt, txt_masks=d['txt_masks'],
+                           align_imagine_embeds=img, imagine_masks=d['imagine_masks'], sub_instr_segs=d['sub_instr_segs'],
+                           sub_instr_imag_flag=d['sub_instr_imag_flag'], noun_phrase_segs=d['noun_phrase_segs'],
+                           obs_instr_ids=d['obs_instr_ids'])
+    return txt, img2, loss
+
+
+def step_tensor_keys(model_kind):
+    return (DUET_PANO_KEYS + DUET_NAV_KEYS) if model_kind == 'duet' else (HAMT_VIS_KEYS + HAMT_HIST_KEYS + ('hist_embeds',))
+
+
+def device_inputs(model_kind, model, ep, dev):
+    d = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in ep.items()}
+    if model_kind == 'duet':
+        G, P = ep['gmap_img_embeds'].shape[1], ep['vp_img_embeds'].shape[1]
+        d['gmap_vpids'], d['vp_cand_vpids'] = model.vln_bert.intern_vpids(ep['gmap_vpids'], ep['vp_cand_vpids'], G, P, dev)
+    else:
+        d['hist_list'] = [d['hist_embeds'][:, t] for t in range(d['hist_embeds'].shape[1])]
+        d['hist_lens'] = [int(x) for x in ep['hist_lens']]
+    return d
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU legs (the oracle is the checker / reported baseline, never the product)
+# ----------------------------------------------------------------------------------------------
+def cpu_reference(model_kind, shape, budget_s=15.0, batch=8):
+    """The reference algorithm (CPU oracle port, fp32, all host threads) on a bounded sample of the same
+    workload: `batch` episodes of the same shape, repeated for about budget_s seconds."""
+    import vln_imagine_b200.synth as synth
+    from oracle import duet_oracle, hamt_oracle
+    torch.set_num_threads(os.cpu_count())
+    sample = dataclasses.replace(shape, batch=batch)
+    man = json.load(open(os.path.join(ROOT, 'tests', 'golden', '%s_manifest.json' % model_kind)))
+    sd = synth.synth_state_dict(man, seed=0)
+    O = duet_oracle if model_kind == 'duet' else hamt_oracle
+    ep = synth.to_torch((synth.duet_episode if model_kind == 'duet' else synth.hamt_episode)(sample, 1234))
+    with torch.no_grad():
+        txt, img, loss, img2 = O.episode_prelude(sd, ep)
+        O.nav_step(sd, ep, txt, img2)                       # warm-up
+        times = []
+        t_end = time.perf_counter() + budget_s
+        while time.perf_counter() < t_end or len(times) < 3:
+            t0 = time.perf_counter()
+            O.nav_step(sd, ep, txt, img2)
+            times.append(time.perf_counter() - t0)
+    best = min(times)
+    return {'value': batch / best, 'unit': UNIT, 'cores': os.cpu_count(), 'kind': 'port',
+            'sample': '%d episodes of the same shape x %d repeats, best step %.1f ms, fp32 CPU oracle (oracle/%s_oracle.py)'
+                      % (batch, len(times), best * 1e3, model_kind)}, times
+
+
+def run_reference_arm(args, model_kind, shape, desc, rank):
+    if rank != 0:
+        return
+    batch = 8
+    import vln_imagine_b200.synth as synth
+    from oracle import duet_oracle, hamt_oracle
+    torch.set_num_threads(os.cpu_count())
+    sample = dataclasses.replace(shape, batch=batch)
+    man = json.load(open(os.path.join(ROOT, 'tests', 'golden', '%s_manifest.json' % model_kind)))
+    sd = synth.synth_state_dict(man, seed=0)
+    O = duet_oracle if model_kind == 'duet' else hamt_oracle
+    ep = synth.to_torch((synth.duet_episode if model_kind == 'duet' else synth.hamt_episode)(sample, 1234))
+    steps = min(args.steps, 40)
+    warm = min(args.warmup, 3)
+    with torch.no_grad():
+        txt, img, loss, img2 = O.episode_prelude(sd, ep)
+        for _ in range(max(warm, 1)):
+            O.nav_step(sd, ep, txt, img2)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            O.nav_step(sd, ep, txt, img2)
+        dt = time.perf_counter() - t0
+    val = batch * steps / dt
+    line = {'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': steps,
+            'warmup': warm, 'ms_per_step': dt / steps * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': '%s: %s' % (args.workload, desc),
+                       'sample': 'each step = %d episodes of the workload shape on the host CPU' % batch},
+            'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': os.cpu_count(), 'kind': 'port',
+                             'sample': '%d-episode steps x %d, CPU oracle port of the reference (reference is Python and '
+                                       'absent on the GPU box)' % (batch, steps)},
+            'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--warmup', type=int, default=20)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--workload', default='duet_cfg2')
+    ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
+    ap.add_argument('--no-graph', action='store_true', help='time eager launches instead of a CUDA-graph replay')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    model_kind, shape, desc = workload(args.workload)
+
+    if args.impl == 'reference':
+        run_reference_arm(args, model_kind, shape, desc, rank)
+        return
+
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    from vln_imagine_b200 import ops
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t)
+        return ms
+
+    model, ep = build(model_kind, shape, rank, args.precision)
+    step_fn = duet_step if model_kind == 'duet' else hamt_step
+    B = shape.batch
+    K, W = args.steps, args.warmup
+
+    with torch.no_grad():
+        d = device_inputs(model_kind, model, ep, dev)
+        # ---- once-per-episode prelude (reported, not part of the metric)
+        txt, img2, loss = episode_prelude(model_kind, model, d)
+        torch.cuda.synchronize()
+        t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(3):
+            txt, img2, loss = episode_prelude(model_kind, model, d)
+        t1.record(); torch.cuda.synchronize()
+        prelude_ms = t0.elapsed_time(t1) / 3
+
+        # ---- leg 1: inputs resident in HBM; the step replayed as a CUDA graph
+        for _ in range(3):
+            logits, _ = step_fn(model, d, txt, img2)
+        torch.cuda.synchronize()
+        n0 = ops._Counters.launches
+        logits, _ = step_fn(model, d, txt, img2)
+        launches_per_step = ops._Counters.launches - n0
+        graph = None
+        if not args.no_graph:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                step_fn(model, d, txt, img2)
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                g_logits, _ = step_fn(model, d, txt, img2)
+            run = graph.replay
+        else:
+            def run():
+                step_fn(model, d, txt, img2)
+        for _ in range(W):
+            run()
+        sampler = ClockSampler(local_rank)
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        barrier()
+        with sampler:
+            e0.record()
+            for _ in range(K):
+                run()
+            e1.record()
+            torch.cuda.synchronize()
+        barrier()
+        ms = max_over_ranks(e0.elapsed_time(e1))
+        value = world * B * K / (ms * 1e-3)
+
+        # ---- leg 2 (e2e): public module API, pinned HOST inputs copied in and logits copied out every step
+        keys = [k for k in step_tensor_keys(model_kind) if k in ep and torch.is_tensor(ep[k])]
+        host = {k: ep[k].pin_memory() for k in keys}
+        h2d = sum(v.numel() * v.element_size() for v in host.values())
+        out_host = torch.empty(tuple(logits.shape), dtype=logits.dtype).pin_memory()
+        d2h = out_host.numel() * out_host.element_size()
+
+        def e2e_step():
+            dd = dict(d)
+            for k, v in host.items():
+                dd[k] = v.to(dev, non_blocking=True)
+            if model_kind == 'hamt':
+                dd['hist_list'] = [dd['hist_embeds'][:, t] for t in range(dd['hist_embeds'].shape[1])]
+            lg, _ = step_fn(model, dd, txt, img2)
+            out_host.copy_(lg, non_blocking=True)
+            torch.cuda.current_stream().synchronize()          # the agent needs the logits to act
+
+        for _ in range(W):
+            e2e_step()
+        barrier()
+        e0.record()
+        for _ in range(K):
+            e2e_step()
+        e1.record()
+        torch.cuda.synchronize()
+        barrier()
+        ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+        e2e_value = world * B * K / (ms_e2e * 1e-3)
+
+        # ---- roofline of the dominant kernel (tcgen05 GEMM): CUDA events around every launch of 3 eager steps
+        ops._Counters.gemm_trace = []
+        for _ in range(3):
+            step_fn(model, d, txt, img2)
+        torch.cuda.synchronize()
+        trace, ops._Counters.gemm_trace = ops._Counters.gemm_trace, None
+        gemm_flops = sum(2.0 * m * n * k for m, n, k, _, _ in trace)
+        gemm_ms = sum(a.elapsed_time(b) for _, _, _, a, b in trace)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    peak_tf = peaks.get('bf16_tflops_sustained', 1400.0)
+    peak_src = 'MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)' if peaks else 'fallback 1.4 PFLOP/s sustained'
+    fl_dec = flops_per_decision(model_kind, shape)
+    step_tf = fl_dec * B / (ms / K * 1e-3) / 1e12
+    achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    line = {
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W,
+        'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': args.precision, 'data': 'synthetic',
+        'config': {'workload': '%s: %s' % (args.workload, desc), 'episodes_per_gpu': B,
+                   'replay': 'eager launches' if args.no_graph else 'CUDA graph of the step',
+                   'l2': 'no flush: each step streams 181 MB of bf16 weights plus activations, more than the 126 MB L2',
+                   'weights': 'random-init (deterministic synthetic), shared with the oracle'},
+        'clocks': sampler.summary(),
+        'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                'ms_per_step': ms_e2e / K, 'api': "model('panorama'|'navigation', batch) with pinned host inputs, "
+                                                  'logits read back and synchronised every step'},
+        'gpu_launches': launches_per_step * K,
+        'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s',
+                     'frac': achieved / peak_tf, 'traffic': None, 'peak_source': peak_src,
+                     'kernel': 'gemm_bf16_tc_kernel (tcgen05): %d launches/step, %.1f GFLOP/step, %.3f ms/step of GEMM time '
+                               '(CUDA events around each launch, eager pass)' % (len(trace) // 3, gemm_flops / 3 / 1e9, gemm_ms / 3)},
+        'step': {'algorithmic_gflop_per_decision': fl_dec / 1e9, 'tflops': step_tf, 'frac_of_peak': step_tf / peak_tf,
+                 'launches_per_step': launches_per_step, 'prelude_ms_per_episode_batch': prelude_ms},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        cb, _ = cpu_reference(model_kind, shape)
+        line['cpu_baseline'] = cb
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

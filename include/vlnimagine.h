@@ -135,9 +135,10 @@ int vi_ln_dot(const float* h, const float* gamma, const float* beta, float eps,
               const float* w, const float* b, float* out, int64_t rows,
               int n_groups, const int32_t* group_row_end, vi_stream_t stream);
 
-/* y[r] = x[r] * s[r / rows_per_batch]  (ob_embeds * txt_embeds[:, :1], H/models/vilmodel_cmt.py:1191).
- * s has row stride lds. */
-int vi_mul_bcast(const float* x, const float* s, int64_t lds, float* y32, void* y16,
+/* y[b*rpb + r] = x[b*x_batch_stride + r*768 ..] * s[b*lds ..]  (ob_embeds * txt_embeds[:, :1],
+ * H/models/vilmodel_cmt.py:1191; ob_embeds is the tail slice of every episode's [hist; ob] block, hence the
+ * batch stride).  Strides in elements; y rows are dense. */
+int vi_mul_bcast(const float* x, int64_t x_batch_stride, const float* s, int64_t lds, float* y32, void* y16,
                  int64_t rows, int rows_per_batch, vi_stream_t stream);
 
 /* Action-logit masking and global/local fusion, D/models/vilmodel.py:1182-1217.

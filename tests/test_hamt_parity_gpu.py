@@ -1,0 +1,95 @@
+"""HAMT-Imagine module-level parity on the GPU: product vs golden vectors of the real reference and vs the
+CPU oracle, shared weights, both precisions; called through the reference's VLNBertCMT keyword API."""
+import dataclasses
+import importlib
+import os
+
+import pytest
+import torch
+
+from parity_utils import TOL, golden, manifest, max_rel, sub16, to_dev
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def env(lib_built):
+    synth = importlib.import_module('vln_imagine_b200.synth')
+    hamt = importlib.import_module('vln_imagine_b200.hamt')
+    config = importlib.import_module('vln_imagine_b200.config')
+    from oracle import hamt_oracle
+    model = hamt.VLNBertCMT(config.default_hamt_args()).cuda().eval()
+    sd = synth.synth_state_dict(manifest('hamt'), seed=0)
+    model.vln_bert.load_state_dict(sd)
+    return synth, model, hamt_oracle, sd
+
+
+def run_product(model, ep):
+    inner = model.vln_bert
+    with torch.no_grad():
+        txt = model('language', txt_ids=ep['txt_ids'], txt_masks=ep['txt_masks'])
+        img = model('imagine', imagine_pano_img_feats=ep['imagine_feats'], imagine_masks=None)
+        loss, img2 = model('align_with_contrastive_loss', align_txt_embeds=txt, txt_masks=ep['txt_masks'],
+                           align_imagine_embeds=img.clone(), imagine_masks=ep['imagine_masks'],
+                           sub_instr_segs=ep['sub_instr_segs'], sub_instr_imag_flag=ep['sub_instr_imag_flag'],
+                           noun_phrase_segs=ep['noun_phrase_segs'], obs_instr_ids=ep['obs_instr_ids'])
+        hist_list = [ep['hist_embeds'][:, t] for t in range(ep['hist_embeds'].shape[1])]
+        hist_lens = [int(x) for x in ep['hist_lens']]
+        kw = dict(txt_embeds=txt, txt_masks=ep['txt_masks'], hist_embeds=hist_list, hist_lens=hist_lens,
+                  ob_img_feats=ep['ob_img_feats'], ob_ang_feats=ep['ob_ang_feats'], ob_nav_types=ep['ob_nav_types'],
+                  ob_masks=ep['ob_masks'], imagine_embeds=img2, imagine_masks=ep['imagine_masks'])
+        (logits,) = model('visual', **kw)
+        logits2, states = model('visual', return_states=True, **kw)
+        # the inner module also returns the refreshed token streams (used for parity only)
+        hm = torch.arange(ep['hist_embeds'].shape[1], device='cuda')[None] < torch.as_tensor(hist_lens, device='cuda')[:, None]
+        _, txt_o, hist_o, ob_o = inner('visual', txt_embeds=txt, txt_masks=ep['txt_masks'], hist_embeds=ep['hist_embeds'],
+                                       hist_masks=hm, ob_img_feats=ep['ob_img_feats'], ob_ang_feats=ep['ob_ang_feats'],
+                                       ob_nav_types=ep['ob_nav_types'], ob_masks=ep['ob_masks'], imagine_embeds=img2,
+                                       imagine_masks=ep['imagine_masks'])
+        hist = model('history', hist_img_feats=ep['hist_img_feats'], hist_ang_feats=ep['hist_ang_feats'], ob_step=ep['ob_step'],
+                     hist_pano_img_feats=ep['hist_pano_img_feats'], hist_pano_ang_feats=ep['hist_pano_ang_feats'])
+        cls_hist = model('history')
+    assert torch.equal(logits, logits2)
+    return dict(txt_embeds=txt, aux_loss=loss, aligned_imagine_embeds=img2, act_logits=logits, txt_out=txt_o,
+                hist_out=hist_o, ob_out=ob_o, hist_embed=hist, cls_hist=cls_hist, states=states)
+
+
+@pytest.mark.parametrize('tag,shape,seed', [('tiny', 'TINY', 7), ('cfg1', 'CFG1', 1234)])
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_hamt_vs_reference_golden(env, tag, shape, seed, precision):
+    synth, model, _, _ = env
+    model.vln_bert.precision = precision
+    ep = to_dev(synth.to_torch(synth.hamt_episode(getattr(synth, shape), seed)))
+    out = run_product(model, ep)
+    gold = golden('hamt_' + tag)
+    tol = TOL[precision]
+    f = (lambda t: t) if tag == 'tiny' else sub16
+    for k in ('txt_embeds', 'aligned_imagine_embeds', 'txt_out', 'hist_out', 'ob_out'):
+        assert max_rel(f(out[k]), gold[k]) < tol, k
+    for k in ('act_logits', 'hist_embed', 'cls_hist'):
+        assert max_rel(out[k], gold[k]) < tol, k
+    assert abs(float(out['aux_loss']) - float(gold['aux_loss'])) < tol * abs(float(gold['aux_loss']))
+    assert max_rel(out['states'], (out['txt_out'][:, 0] * out['hist_out'][:, 0])) < 1e-6
+    if precision == 'fp32':
+        assert torch.equal(out['act_logits'].cpu().argmax(-1), gold['act_logits'].argmax(-1))
+
+
+def test_hamt_bf16_argmax_agreement_over_many_decisions(env):
+    """>= 99.5 % identical action argmax, logits within 2e-2: bf16 product vs fp32 oracle on 8 x 48 decisions."""
+    synth, model, O, sd = env
+    model.vln_bert.precision = 'bf16'
+    torch.set_num_threads(os.cpu_count())
+    shape = dataclasses.replace(synth.CFG1, batch=48)
+    agree = total = 0
+    worst = 0.0
+    for seed in range(300, 308):
+        ep_cpu = synth.to_torch(synth.hamt_episode(shape, seed))
+        with torch.no_grad():
+            o_txt, o_img, o_loss, o_img2 = O.episode_prelude(sd, ep_cpu)
+            o_logits = O.nav_step(sd, ep_cpu, o_txt, o_img2)[0]
+        out = run_product(model, to_dev(ep_cpu))
+        worst = max(worst, max_rel(out['act_logits'], o_logits))
+        agree += int((out['act_logits'].cpu().argmax(-1) == o_logits.argmax(-1)).sum())
+        total += o_logits.shape[0]
+    assert worst < TOL['bf16']
+    assert agree / total >= 0.995, (agree, total)

@@ -221,8 +221,8 @@ def test_ln_dot_and_mul_bcast(ops):
     ref = F.layer_norm(h, (768,), g, be, 1e-12) @ w + b
     assert relerr(out, ref) < 1e-5
     x, s = _rand(6 * 37, 768, seed=6), _rand(6 * 85, 768, seed=7)
-    y32, y16 = ops.mul_bcast(x, s.view(6, 85 * 768), 37, want16=True)
-    ref = (x.view(6, 37, 768) * s.view(6, 85, 768)[:, :1]).view(-1, 768)
+    y32, y16 = ops.mul_bcast(x.view(6, 37, 768)[:, 5:], 37 * 768, s, 85 * 768, 6, 32, want16=True)
+    ref = (x.view(6, 37, 768)[:, 5:] * s.view(6, 85, 768)[:, :1]).reshape(-1, 768)
     assert torch.equal(y32, ref)
     assert relerr(y16, ref) < 1e-2
 

@@ -47,7 +47,7 @@ PROTOTYPES = {
     'vi_add_ln': [_p, _p, _p, _p, _f, _p, _p, _l, _i, _ip, _p],
     'vi_embed_compose': [C.POINTER(EmbedArgs), _p],
     'vi_ln_dot': [_p, _p, _p, _f, _p, _p, _p, _l, _i, _ip, _p],
-    'vi_mul_bcast': [_p, _p, _l, _p, _p, _l, _i, _p],
+    'vi_mul_bcast': [_p, _l, _p, _l, _p, _p, _l, _i, _p],
     'vi_duet_fuse_logits': [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
     'vi_mask_logits_navtype': [_p, _p, _p, _l, _p],
     'vi_gather_mean': [_p, _p, _p, _p, _p, _i, _p],

@@ -168,14 +168,15 @@ __global__ void __launch_bounds__(128) ln_dot_kernel(const float* __restrict__ h
   if (lane == 0) out[row] = d + (bias ? __ldg(bias) : 0.f);
 }
 
-__global__ void __launch_bounds__(128) mul_bcast_kernel(const float* __restrict__ x, const float* __restrict__ s,
-                                                        long long lds, float* y32, bf16* y16, long long rows,
-                                                        int rows_per_batch) {
+__global__ void __launch_bounds__(128) mul_bcast_kernel(const float* __restrict__ x, long long x_bs,
+                                                        const float* __restrict__ s, long long lds, float* y32,
+                                                        bf16* y16, long long rows, int rows_per_batch) {
   ROW_INDEX();
   if (row >= rows) return;
+  const long long b = row / rows_per_batch;
   Row r, m;
-  row_load(r, x + row * D, lane);
-  row_load(m, s + (row / rows_per_batch) * lds, lane);
+  row_load(r, x + b * x_bs + (row - b * rows_per_batch) * D, lane);
+  row_load(m, s + b * lds, lane);
 #pragma unroll
   for (int i = 0; i < V4 * 4; ++i) r.v[i] *= m.v[i];
   row_store(r, y32, y16, row, lane);
@@ -439,12 +440,14 @@ extern "C" int vi_ln_dot(const float* h, const float* gamma, const float* beta, 
   return VI_OK;
 }
 
-extern "C" int vi_mul_bcast(const float* x, const float* s, int64_t lds, float* y32, void* y16, int64_t rows,
-                            int rows_per_batch, vi_stream_t stream) {
+extern "C" int vi_mul_bcast(const float* x, int64_t x_batch_stride, const float* s, int64_t lds, float* y32, void* y16,
+                            int64_t rows, int rows_per_batch, vi_stream_t stream) {
   VI_CHECK_ARG(x && s && (y32 || y16) && rows_per_batch > 0, "vi_mul_bcast: bad operands");
-  VI_CHECK_ARG(aligned16(x) && aligned16(s) && lds % 4 == 0 && aligned16(y32) && ((uintptr_t)y16 & 7) == 0, "vi_mul_bcast: misaligned operands");
+  VI_CHECK_ARG(aligned16(x) && aligned16(s) && lds % 4 == 0 && x_batch_stride % 4 == 0 && aligned16(y32) &&
+                   ((uintptr_t)y16 & 7) == 0, "vi_mul_bcast: misaligned operands");
   if (rows <= 0) return VI_OK;
-  mul_bcast_kernel<<<row_grid(rows), 128, 0, ST(stream)>>>(x, s, lds, y32, reinterpret_cast<bf16*>(y16), rows, rows_per_batch);
+  mul_bcast_kernel<<<row_grid(rows), 128, 0, ST(stream)>>>(x, x_batch_stride, s, lds, y32, reinterpret_cast<bf16*>(y16), rows,
+                                                          rows_per_batch);
   VI_LAUNCH_CHECK();
   return VI_OK;
 }

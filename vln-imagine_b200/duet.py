@@ -344,15 +344,24 @@ class GlocalTextPathNavCMT(nn.Module):
                           c16[:, HIDDEN:] if c16 is not None else None, 2 * HIDDEN, HIDDEN)
             fuse_raw = blocks.cls_head(cat, pk['fuse'], lowp)
         raw = blocks.cls_head(x.operand(lowp), pk['sap'], lowp, ends)
-        gmap_ids = torch.from_numpy(self._ids.encode(gmap_vpids, G, -1)).to(dev, non_blocking=True)
-        cand_ids = torch.from_numpy(self._ids.encode(vp_cand_vpids, P, -2)).to(dev, non_blocking=True)
-        if len(self._ids.ids) > (1 << 20):
-            self._ids = _IdTable()
+        gmap_ids, cand_ids = self.intern_vpids(gmap_vpids, vp_cand_vpids, G, P, dev)
         gl, ll, fl = ops.duet_fuse_logits(raw[r_g:], raw[r_l:], fuse_raw, blocks.mask_u8(gmap_masks),
                                           blocks.mask_u8(gmap_visited_masks), blocks.mask_u8(vp_nav_masks),
                                           gmap_ids, cand_ids, B, G, P)
         return {'gmap_embeds': gmap_out, 'vp_embeds': vp_out, 'global_logits': gl, 'local_logits': ll,
                 'fused_logits': fl, 'obj_logits': None}
+
+    def intern_vpids(self, gmap_vpids, vp_cand_vpids, G, P, dev):
+        """Viewpoint-id strings -> int32 device tensors (gmap padding -1, candidate padding -2).  Callers that
+        already hold interned ids (a CUDA-graph replay loop, bench.py) may pass the two tensors instead of the
+        lists; they are used as they are."""
+        if torch.is_tensor(gmap_vpids) and torch.is_tensor(vp_cand_vpids):
+            return gmap_vpids, vp_cand_vpids
+        gmap_ids = torch.from_numpy(self._ids.encode(gmap_vpids, G, -1)).to(dev, non_blocking=True)
+        cand_ids = torch.from_numpy(self._ids.encode(vp_cand_vpids, P, -2)).to(dev, non_blocking=True)
+        if len(self._ids.ids) > (1 << 20):
+            self._ids = _IdTable()
+        return gmap_ids, cand_ids
 
     def forward_align(self, batch):
         """'align_with_contrastive_loss'.  :1246-1262 -> AlignWithContrastiveLoss(.WithNegativeSamples) :598-779."""

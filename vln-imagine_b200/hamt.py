@@ -1,0 +1,352 @@
+"""HAMT-Imagine on libvlnimagine: drop-in for ``models.model_HAMT.VLNBertCMT`` / ``models.vilmodel_cmt.NavCMT``.
+
+Same constructor (``VLNBertCMT(args)``), the reference's keyword-style ``forward(mode, ...)`` with modes
+language / history / imagine / align_with_contrastive_loss / visual, same return types and parameter names
+(VLN-HAMT/finetune_src/models/model_HAMT.py:13-96, models/vilmodel_cmt.py:966-1205), so the unmodified
+agent (r2r/agent_cmt.py) can hold it as ``self.vln_bert``.  The released configuration is implemented:
+``concat_imagine_with='language'``, ``no_lang_ca=False``, ``act_pred_token in {'ob_txt', 'ob'}``,
+``bypass_imag_encoder=True``, ``num_h_layers = num_r_layers = 0``.
+
+The two token streams of a cross-modal layer - language+imagination (C tokens) and history+observation
+(Nv tokens) - live in ONE row-stacked activation; the bidirectional cross-attention, which shares its
+weights between the two directions (vilmodel_cmt.py:385-397), is a single QKV GEMM / output GEMM / LayerNorm
+over all rows, and the per-stream self-attention and FFN blocks are grouped launches.
+"""
+from __future__ import annotations
+
+import os
+from typing import List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import blocks, ops, params
+from .blocks import Act, Stream
+from .config import hamt_config
+from .duet import _f32c, align_forward
+from .ops import BF16, F32, HIDDEN
+
+
+class NavCMT(nn.Module):
+    """models/vilmodel_cmt.py:966-1205."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        c = config
+        if c.num_h_layers or c.num_r_layers:
+            raise NotImplementedError('num_h_layers / num_r_layers > 0 are not used by the released HAMT-Imagine runs')
+        if c.no_lang_ca:
+            raise NotImplementedError('no_lang_ca=True is not supported (the reference itself warns that it breaks the imagination path)')
+        if c.act_pred_token not in ('ob_txt', 'ob'):
+            raise NotImplementedError('act_pred_token %r' % c.act_pred_token)
+        self.embeddings = params.BertEmbeddingsP(c)
+        self.img_embeddings = params.HamtImageEmbeddingsP(c)
+        self.hist_embeddings = params.HistoryEmbeddingsP(c)
+        if c.imagine_enc_pano and (c.use_cosine_aux_loss or c.no_loss_test):
+            if c.aux_loss_type not in ('cosine', 'contrastive-InfoNCE'):
+                raise NotImplementedError('aux_loss_type %r' % c.aux_loss_type)
+            self.contrastive_alignment_model = params.AlignModelP()
+        if c.imagine_enc_pano:
+            if not c.bypass_imag_encoder:
+                raise NotImplementedError('bypass_imag_encoder=False (ImagineEmbeddings encoder) is not on the released path')
+            if c.concat_imagine_with != 'language':
+                raise NotImplementedError("concat_imagine_with=%r (only 'language' is on the released path)" % c.concat_imagine_with)
+            self.imagine_embeddings = params.BypassImagineEmbeddingsP()
+        self.encoder = params.HamtEncoderP(c)
+        self.next_action = params.NextActionP(c.pred_head_dropout_prob)
+        params.bert_init_(self)
+        self.fix_lang_embedding = c.fix_lang_embedding
+        self.fix_hist_embedding = c.fix_hist_embedding
+        self.fix_obs_embedding = c.fix_obs_embedding
+        if c.imagine_enc_pano:
+            self.fix_imagine_embeds = c.fix_imagine_embeds
+        self.precision = os.environ.get('VLN_IMAGINE_PRECISION', 'bf16')
+        self._packs = None
+        self._mean_idx = {}
+
+    def _pk(self):
+        if self._packs is None:
+            pk = {}
+            pk['lang'] = [blocks.SelfFFNPack([l.attention], [l.intermediate], [l.output]) for l in self.encoder.layer]
+            xs = self.encoder.x_layers
+            pk['x_cross'] = []
+            for x in xs:
+                va = x.visual_attention
+                pk['x_cross'].append({
+                    'qkv': blocks.LinearPack([va.att.query.weight, va.att.key.weight, va.att.value.weight],
+                                             [va.att.query.bias, va.att.key.bias, va.att.value.bias]),
+                    'o': blocks.LinearPack([va.output.dense.weight], [va.output.dense.bias]),
+                    'ln': blocks.LNPack([va.output.LayerNorm])})
+            pk['x_self'] = [blocks.SelfFFNPack([x.lang_self_att, x.visn_self_att], [x.lang_inter, x.visn_inter],
+                                               [x.lang_output, x.visn_output]) for x in xs]
+            pk['ob_img'] = blocks.LinearPack([self.img_embeddings.img_linear.weight], [self.img_embeddings.img_linear.bias])
+            he = self.hist_embeddings
+            pk['hist_img'] = blocks.LinearPack([he.img_linear.weight], [he.img_linear.bias])
+            if he.pano_encoder is not None:
+                pk['hist_pano_img'] = blocks.LinearPack([he.pano_img_linear.weight], [he.pano_img_linear.bias])
+                pk['hist_pano'] = [blocks.SelfFFNPack([l.attention], [l.intermediate], [l.output]) for l in he.pano_encoder.layer]
+            pk['act'] = blocks.ClsHeadPack([self.next_action], last_index=4)
+            if hasattr(self, 'contrastive_alignment_model'):
+                ip = self.contrastive_alignment_model.image_proj
+                pk['align'] = [blocks.LinearPack([ip.fc1.weight]), blocks.LinearPack([ip.fc2.weight]),
+                               blocks.LinearPack([ip.fc3.weight])]
+            self._packs = pk
+        return self._packs
+
+    def _apply(self, fn, *a, **k):
+        self._packs = None
+        self._mean_idx = {}
+        return super()._apply(fn, *a, **k)
+
+    @property
+    def lowp(self):
+        if self.precision not in ('bf16', 'fp32'):
+            raise ValueError("precision must be 'bf16' or 'fp32'")
+        return self.precision == 'bf16'
+
+    # -- modes ------------------------------------------------------------------------------------
+    def forward_text(self, txt_ids, txt_masks):
+        """'language', :1008-1031."""
+        ops.ensure_init(txt_ids)
+        lowp = self.lowp
+        B, L = txt_ids.shape
+        e = self.embeddings
+        y32, y16 = ops.embed_compose(B * L, txt_ids.device, idx=txt_ids.long().contiguous().view(-1),
+                                     table=e.word_embeddings.weight, pos_table=e.position_embeddings.weight, pos_period=L,
+                                     const_row=e.token_type_embeddings.weight[0],
+                                     out_ln=(e.LayerNorm.weight, e.LayerNorm.bias), want16=lowp)
+        x = Act(y32, y16)
+        s = [Stream(0, B, L, blocks.mask_u8(txt_masks))]
+        for pk in self._pk()['lang']:
+            x = blocks.self_attn_ffn(x, pk, s, None, lowp)
+        out = x.f32.view(B, L, HIDDEN)
+        return out.detach() if self.fix_lang_embedding else out
+
+    def forward_history(self, hist_img_feats, hist_ang_feats, ob_step_ids, hist_pano_img_feats, hist_pano_ang_feats):
+        """'history': HistoryEmbeddings.forward, :576-618."""
+        he = self.hist_embeddings
+        lowp = self.lowp
+        type_row = he.type_embedding.weight[0]
+        ln = (he.layer_norm.weight, he.layer_norm.bias)
+        if hist_img_feats is None:
+            ops.ensure_init(he.cls_token)
+            y32, _ = ops.embed_compose(1, he.cls_token.device, a=he.cls_token.view(1, HIDDEN), const_row=type_row, out_ln=ln)
+            return y32.detach() if self.fix_hist_embedding else y32
+        ops.ensure_init(hist_img_feats)
+        dev = hist_img_feats.device
+        B = hist_img_feats.shape[0]
+        pk = self._pk()
+        f32 = _f32c(hist_img_feats)
+        w, b = pk['hist_img'].get(lowp)
+        a = ops.gemm(ops.cast_bf16(f32) if lowp else f32, w, b, out_dtype=F32)
+        step = int(ob_step_ids.view(-1)[0]) if torch.is_tensor(ob_step_ids) else int(ob_step_ids)
+        e32, _ = ops.embed_compose(B, dev, a=a, a_ln=(he.img_layer_norm.weight, he.img_layer_norm.bias),
+                                   feat=_f32c(hist_ang_feats), feat_w=he.ang_linear.weight, feat_b=he.ang_linear.bias,
+                                   feat_ln=(he.ang_layer_norm.weight, he.ang_layer_norm.bias),
+                                   const_row=he.position_embeddings.weight[step], const_row2=type_row)
+        pano_mean = None
+        if he.pano_encoder is not None:
+            V = hist_pano_img_feats.shape[1]
+            p32 = _f32c(hist_pano_img_feats).view(B * V, -1)
+            w, b = pk['hist_pano_img'].get(lowp)
+            pa = ops.gemm(ops.cast_bf16(p32) if lowp else p32, w, b, out_dtype=F32)
+            y32, y16 = ops.embed_compose(B * V, dev, a=pa, a_ln=(he.pano_img_layer_norm.weight, he.pano_img_layer_norm.bias),
+                                         feat=_f32c(hist_pano_ang_feats).view(B * V, -1), feat_w=he.pano_ang_linear.weight,
+                                         feat_b=he.pano_ang_linear.bias,
+                                         feat_ln=(he.pano_ang_layer_norm.weight, he.pano_ang_layer_norm.bias), want16=lowp)
+            x = Act(y32, y16)
+            s = [Stream(0, B, V, None)]                       # the reference's mask is all ones (:606-607)
+            for lp in pk['hist_pano']:
+                x = blocks.self_attn_ffn(x, lp, s, None, lowp)
+            key = (B, V, str(dev))
+            if key not in self._mean_idx:
+                self._mean_idx[key] = (torch.arange(0, B * V + 1, V, dtype=torch.int32, device=dev),
+                                       torch.arange(B * V, dtype=torch.int32, device=dev))
+            off, idx = self._mean_idx[key]
+            pano_mean, _ = ops.gather_mean(x.f32, off, idx, B, want16=False)
+        y32, _ = ops.add_ln(e32, pano_mean, ln[0], ln[1], 1e-12, want16=False)
+        return y32.detach() if self.fix_hist_embedding else y32
+
+    def forward_imagination(self, imagine_pano_img_feats, imagine_masks=None):
+        """'imagine' (bypass encoder), :620-631, :1040-1048."""
+        ops.ensure_init(imagine_pano_img_feats)
+        B, I, _ = imagine_pano_img_feats.shape
+        y32, _ = ops.embed_compose(B * I, imagine_pano_img_feats.device, a=_f32c(imagine_pano_img_feats).view(B * I, HIDDEN),
+                                   const_row=self.imagine_embeddings.type_embedding.weight[0])
+        out = y32.view(B, I, HIDDEN)
+        return out.detach() if self.fix_imagine_embeds else out
+
+    def forward_visual(self, txt_embeds, txt_masks, hist_embeds, hist_masks, ob_img_feats, ob_ang_feats, ob_nav_types,
+                       ob_masks, imagine_embeds=None, imagine_masks=None):
+        """'visual', :1056-1205."""
+        ops.ensure_init(txt_embeds)
+        cfg, lowp, pk = self.config, self.lowp, self._pk()
+        dev = txt_embeds.device
+        B, L, _ = txt_embeds.shape
+        T, O = hist_embeds.shape[1], ob_img_feats.shape[1]
+        Nv = T + O
+        if cfg.imagine_enc_pano:
+            if imagine_embeds is None or imagine_masks is None:
+                raise ValueError('visual mode needs imagine_embeds and imagine_masks when imagine_enc_pano is set')
+            I = imagine_embeds.shape[1]
+        else:
+            I = 0
+        C = L + I
+        (r_l, r_v), ends, R = blocks.stack_layout([B * C, B * Nv])
+        x32 = torch.empty((R, HIDDEN), dtype=F32, device=dev)
+        x16 = torch.empty((R, HIDDEN), dtype=BF16, device=dev) if lowp else None
+        if ends[0] > B * C:
+            x32[B * C:ends[0]].zero_()
+            if lowp:
+                x16[B * C:ends[0]].zero_()
+        lang32, lang16 = x32[r_l:], (x16[r_l:] if lowp else None)
+        visn32, visn16 = x32[r_v:], (x16[r_v:] if lowp else None)
+        # language stream = [txt ; imagine]  (:1110)
+        ops.copy_rows(_f32c(txt_embeds), L * HIDDEN, HIDDEN, B, L, lang32, lang16, C * HIDDEN, HIDDEN)
+        if I:
+            ops.copy_rows(_f32c(imagine_embeds), I * HIDDEN, HIDDEN, B, I, lang32[L:], lang16[L:] if lowp else None,
+                          C * HIDDEN, HIDDEN)
+        # vision stream = [hist ; ob]  (:1087); observation embedding :521-544, :1073-1077
+        ops.copy_rows(_f32c(hist_embeds), T * HIDDEN, HIDDEN, B, T, visn32, visn16, Nv * HIDDEN, HIDDEN)
+        ie = self.img_embeddings
+        o32 = _f32c(ob_img_feats).view(B * O, -1)
+        w, b = pk['ob_img'].get(lowp)
+        a = ops.gemm(ops.cast_bf16(o32) if lowp else o32, w, b, out_dtype=F32)
+        ob32, _ = ops.embed_compose(B * O, dev, a=a, a_ln=(ie.img_layer_norm.weight, ie.img_layer_norm.bias),
+                                    feat=_f32c(ob_ang_feats).view(B * O, -1), feat_w=ie.ang_linear.weight, feat_b=ie.ang_linear.bias,
+                                    feat_ln=(ie.ang_layer_norm.weight, ie.ang_layer_norm.bias),
+                                    idx=ob_nav_types.long().contiguous().view(-1), table=ie.nav_type_embedding.weight,
+                                    const_row=self.embeddings.token_type_embeddings.weight[1],
+                                    out_ln=(ie.layer_norm.weight, ie.layer_norm.bias))
+        ops.copy_rows(ob32, O * HIDDEN, HIDDEN, B, O, visn32[T:], visn16[T:] if lowp else None, Nv * HIDDEN, HIDDEN)
+        x = Act(x32, x16)
+
+        lang_mask = (torch.cat([txt_masks, imagine_masks], 1) if I else txt_masks).to(torch.uint8).contiguous()
+        visn_mask = torch.cat([hist_masks, ob_masks], 1).to(torch.uint8).contiguous()
+        streams = [Stream(r_l, B, C, lang_mask, 0), Stream(r_v, B, Nv, visn_mask, 1)]
+
+        for cp, sp in zip(pk['x_cross'], pk['x_self']):
+            # bidirectional cross-attention with shared weights, both directions read the layer inputs (:385-397)
+            xin = x.operand(lowp)
+            w, b = cp['qkv'].get(lowp)
+            qkv = ops.gemm(xin, w, b)                          # all rows: Q | K | V
+            ctx = torch.empty((R, HIDDEN), dtype=xin.dtype, device=dev)
+            ctx.zero_()
+            ql, qv = qkv[r_l:r_l + B * C], qkv[r_v:r_v + B * Nv]
+            ops.attention(ql[:, :HIDDEN], qv[:, HIDDEN:2 * HIDDEN], qv[:, 2 * HIDDEN:], B, C, Nv, key_mask=visn_mask,
+                          out=ctx[r_l:r_l + B * C])
+            ops.attention(qv[:, :HIDDEN], ql[:, HIDDEN:2 * HIDDEN], ql[:, 2 * HIDDEN:], B, Nv, C, key_mask=lang_mask,
+                          out=ctx[r_v:r_v + B * Nv])
+            w, b = cp['o'].get(lowp)
+            ao = ops.gemm(ctx, w, b, residual=x.f32, out_dtype=F32)
+            x = blocks.layer_norm(ao, None, cp['ln'], 1e-12, lowp)
+            x = blocks.self_attn_ffn(x, sp, streams, ends, lowp)
+
+        lang_out = x.f32[r_l:r_l + B * C].view(B, C, HIDDEN)
+        visn_out = x.f32[r_v:r_v + B * Nv].view(B, Nv, HIDDEN)
+        txt_out, hist_out, ob_out = lang_out[:, :L], visn_out[:, :T], visn_out[:, T:]
+        if cfg.act_pred_token == 'ob_txt':                     # :1191
+            h32, h16 = ops.mul_bcast(ob_out, Nv * HIDDEN, lang_out, C * HIDDEN, B, O, want16=lowp, want32=not lowp)
+        else:                                                  # 'ob'
+            h32 = torch.empty((B * O, HIDDEN), dtype=F32, device=dev) if not lowp else None
+            h16 = torch.empty((B * O, HIDDEN), dtype=BF16, device=dev) if lowp else None
+            ops.copy_rows(ob_out, Nv * HIDDEN, HIDDEN, B, O, h32, h16, O * HIDDEN, HIDDEN)
+        raw = blocks.cls_head(h16 if lowp else h32, pk['act'], lowp)
+        act_logits = ops.mask_logits_navtype(raw, ob_nav_types.long().contiguous().view(-1)).view(B, O)
+        return act_logits, txt_out, hist_out, ob_out
+
+    def forward(self, mode, txt_ids=None, txt_embeds=None, txt_masks=None, hist_img_feats=None, hist_ang_feats=None,
+                hist_pano_img_feats=None, hist_pano_ang_feats=None, hist_embeds=None, ob_step_ids=None, hist_masks=None,
+                ob_img_feats=None, ob_ang_feats=None, ob_nav_types=None, ob_masks=None, imagine_pano_img_feats=None,
+                imagine_masks=None, imagine_embeds=None, align_txt_embeds=None, align_imagine_embeds=None,
+                sub_instr_segs=None, sub_instr_imag_flag=None, noun_phrase_segs=None, obs_instr_ids=None,
+                return_cross_attention_probs=False):
+        """Mode dispatch, :999-1205."""
+        if return_cross_attention_probs:
+            raise NotImplementedError('attention scores never leave the fused attention kernel')
+        if mode == 'language':
+            return self.forward_text(txt_ids, txt_masks)
+        if mode == 'history':
+            return self.forward_history(hist_img_feats, hist_ang_feats, ob_step_ids, hist_pano_img_feats, hist_pano_ang_feats)
+        if mode == 'imagine':
+            assert imagine_pano_img_feats is not None
+            return self.forward_imagination(imagine_pano_img_feats, imagine_masks)
+        if mode == 'align_with_contrastive_loss':
+            ops.ensure_init(align_txt_embeds)
+            return align_forward(self, align_txt_embeds, align_imagine_embeds, sub_instr_imag_flag, noun_phrase_segs, self.lowp)
+        if mode == 'visual':
+            return self.forward_visual(txt_embeds, txt_masks, hist_embeds, hist_masks, ob_img_feats, ob_ang_feats,
+                                       ob_nav_types, ob_masks, imagine_embeds, imagine_masks)
+        raise NotImplementedError('wrong mode: %s' % mode)
+
+
+def length2mask(lengths, size, device):
+    """utils/misc.py:12-17: True where the position is PADDING."""
+    lens = torch.as_tensor(lengths, dtype=torch.int64, device=device)
+    return torch.arange(size, dtype=torch.int64, device=device)[None, :] >= lens[:, None]
+
+
+class VLNBertCMT(nn.Module):
+    """models/model_HAMT.py:13-96."""
+
+    def __init__(self, args):
+        super().__init__()
+        self.args = args
+        self.vln_bert = NavCMT(hamt_config(args))
+        ckpt = getattr(args, 'bert_ckpt_file', None)
+        if ckpt is not None:                                   # models/vlnbert_init.py:20-31
+            sd = {}
+            for k, v in torch.load(ckpt, map_location='cpu').items():
+                k = k[7:] if k.startswith('module') else k
+                sd[k[5:] if k.startswith('bert.') else k] = v
+            self.vln_bert.load_state_dict(sd, strict=False)
+        self.drop_env = nn.Dropout(p=getattr(args, 'feat_dropout', 0.0))
+
+    def _env_dropout(self, x):
+        if x is not None and self.training and self.drop_env.p > 0:
+            raise NotImplementedError('train-mode feature dropout runs through train.py')
+        return x
+
+    def forward(self, mode, txt_ids=None, txt_masks=None, txt_embeds=None, hist_img_feats=None, hist_ang_feats=None,
+                hist_pano_img_feats=None, hist_pano_ang_feats=None, hist_embeds=None, hist_lens=None, ob_step=None,
+                ob_img_feats=None, ob_ang_feats=None, ob_nav_types=None, ob_masks=None, imagine_pano_img_feats=None,
+                imagine_masks=None, imagine_embeds=None, align_txt_embeds=None, align_imagine_embeds=None,
+                sub_instr_segs=None, sub_instr_imag_flag=None, noun_phrase_segs=None, obs_instr_ids=None,
+                return_states=False, return_cross_attention_probs=False):
+        m = self.vln_bert
+        if mode == 'language':
+            return m('language', txt_ids=txt_ids, txt_masks=txt_masks)
+        if mode == 'imagine':
+            return m('imagine', imagine_pano_img_feats=self._env_dropout(imagine_pano_img_feats), imagine_masks=imagine_masks)
+        if mode == 'align_with_contrastive_loss':
+            return m('align_with_contrastive_loss', align_txt_embeds=align_txt_embeds, txt_masks=txt_masks,
+                     align_imagine_embeds=align_imagine_embeds, imagine_masks=imagine_masks, sub_instr_segs=sub_instr_segs,
+                     sub_instr_imag_flag=sub_instr_imag_flag, noun_phrase_segs=noun_phrase_segs, obs_instr_ids=obs_instr_ids)
+        if mode == 'history':
+            return m('history', hist_img_feats=self._env_dropout(hist_img_feats), hist_ang_feats=hist_ang_feats,
+                     ob_step_ids=ob_step, hist_pano_img_feats=self._env_dropout(hist_pano_img_feats),
+                     hist_pano_ang_feats=hist_pano_ang_feats)
+        if mode == 'visual':
+            hist = torch.stack(hist_embeds, 1)                                   # list of (B, 768) -> (B, T, 768)
+            hist_masks = length2mask(hist_lens, hist.size(1), hist.device).logical_not()
+            act_logits, txt_o, hist_o, ob_o = m('visual', txt_embeds=txt_embeds, txt_masks=txt_masks, hist_embeds=hist,
+                                                hist_masks=hist_masks, ob_img_feats=self._env_dropout(ob_img_feats),
+                                                ob_ang_feats=ob_ang_feats, ob_nav_types=ob_nav_types, ob_masks=ob_masks,
+                                                imagine_embeds=imagine_embeds, imagine_masks=imagine_masks,
+                                                return_cross_attention_probs=return_cross_attention_probs)
+            if return_states:
+                if self.args.no_lang_ca:
+                    states = hist_o[:, 0]
+                else:
+                    states = self._states(txt_o, hist_o)
+                return act_logits, states
+            return (act_logits,)
+        raise NotImplementedError('wrong mode: %s' % mode)
+
+    def _states(self, txt_o, hist_o):
+        """states = txt_embeds[:, 0] * hist_embeds[:, 0]  (model_HAMT.py:86): one mul_bcast launch with
+        one row per episode."""
+        B = txt_o.shape[0]
+        y32, _ = ops.mul_bcast(hist_o, hist_o.stride(0), txt_o, txt_o.stride(0), B, 1, want16=False)
+        return y32

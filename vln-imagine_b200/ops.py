@@ -18,8 +18,19 @@ HEADS = 12
 BF16, F32 = torch.bfloat16, torch.float32
 
 
+class _Counters:
+    """Kernel launches issued through this module (bench.py reports them as gpu_launches) and an optional
+    per-launch CUDA-event trace of the GEMM kernel (bench.py's roofline leg)."""
+    launches = 0
+    gemm_trace = None          # list of (M, N, K, start_event, end_event) when enabled
+
+
 def _stream():
     return torch.cuda.current_stream().cuda_stream
+
+
+def _launched(n: int = 1):
+    _Counters.launches += n
 
 
 def _need_cuda(t: torch.Tensor, name: str):
@@ -64,9 +75,17 @@ def gemm(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None,
             raise _lib.VlnImagineError('bf16 GEMM needs a bf16 weight')
         if out is None:
             out = torch.empty((M, N), dtype=out_dtype, device=x.device)
+        tr = _Counters.gemm_trace
+        if tr is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         check(lib.vi_gemm_bf16(x.data_ptr(), ldx, w.data_ptr(), _ptr(bias), _ptr(residual), ldr, out.data_ptr(),
                                out.stride(0), _lib.DT_F32 if out.dtype == F32 else _lib.DT_BF16, M, N, K, epilogue,
                                n_groups, ends, _stream()), 'vi_gemm_bf16')
+        _launched(1)
+        if tr is not None:
+            e1.record()
+            tr.append((M, N, K, e0, e1))
     elif x.dtype == F32:
         if w.dtype != F32:
             raise _lib.VlnImagineError('fp32 GEMM needs an fp32 weight')
@@ -74,6 +93,7 @@ def gemm(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None,
             out = torch.empty((M, N), dtype=F32, device=x.device)
         check(lib.vi_gemm_f32(x.data_ptr(), ldx, w.data_ptr(), _ptr(bias), _ptr(residual), ldr, out.data_ptr(),
                               out.stride(0), M, N, K, epilogue, n_groups, ends, _stream()), 'vi_gemm_f32')
+        _launched(1)
     else:
         raise _lib.VlnImagineError('unsupported GEMM dtype %s' % x.dtype)
     return out
@@ -94,6 +114,7 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, B: int, Lq: int
     check(lib.vi_attn_fwd(q.data_ptr(), ldq, k.data_ptr(), ldk, v.data_ptr(), ldv, out.data_ptr(), out.stride(0),
                           _lib.DT_BF16 if q.dtype == BF16 else _lib.DT_F32, _ptr(key_mask), _ptr(pair_dist),
                           _ptr(bias_affine), _ptr(lse), B, HEADS, Lq, Lk, mask_mode, _stream()), 'vi_attn_fwd')
+    _launched(1)
     return out
 
 
@@ -107,6 +128,7 @@ def add_ln(a: torch.Tensor, b: Optional[torch.Tensor], gamma: torch.Tensor, beta
     ends = _lib.int_array(list(group_row_end)) if group_row_end is not None else None
     check(lib.vi_add_ln(a.data_ptr(), _ptr(b), gamma.data_ptr(), beta.data_ptr(), eps, _ptr(y32), _ptr(y16), rows,
                         n_groups, ends, _stream()), 'vi_add_ln')
+    _launched(1)
     return y32, y16
 
 
@@ -137,6 +159,7 @@ def embed_compose(rows: int, device, *, a=None, a_ln=None, feat=None, feat_w=Non
     args.eps = eps
     args.y32, args.y16, args.rows = _ptr(y32), _ptr(y16), rows
     check(lib.vi_embed_compose(args, _stream()), 'vi_embed_compose')
+    _launched(1)
     return y32, y16
 
 
@@ -147,15 +170,19 @@ def ln_dot(h: torch.Tensor, gamma, beta, eps: float, w, b, group_row_end: Option
     ends = _lib.int_array(list(group_row_end)) if group_row_end is not None else None
     check(lib.vi_ln_dot(h.data_ptr(), gamma.data_ptr(), beta.data_ptr(), eps, w.data_ptr(), _ptr(b), out.data_ptr(),
                         rows, n_groups, ends, _stream()), 'vi_ln_dot')
+    _launched(1)
     return out
 
 
-def mul_bcast(x: torch.Tensor, s: torch.Tensor, rows_per_batch: int, want16: bool, want32: bool = True):
-    rows = x.shape[0]
+def mul_bcast(x: torch.Tensor, x_batch_stride: int, s: torch.Tensor, s_batch_stride: int, n_batches: int,
+              rows_per_batch: int, want16: bool, want32: bool = True):
+    """y[b, r] = x[b, r] * s[b] over 768-wide rows; x / s are base views with element batch strides."""
+    rows = n_batches * rows_per_batch
     y32 = torch.empty((rows, HIDDEN), dtype=F32, device=x.device) if want32 else None
     y16 = torch.empty((rows, HIDDEN), dtype=BF16, device=x.device) if want16 else None
-    check(lib.vi_mul_bcast(x.data_ptr(), s.data_ptr(), s.stride(0), _ptr(y32), _ptr(y16), rows, rows_per_batch,
-                           _stream()), 'vi_mul_bcast')
+    check(lib.vi_mul_bcast(x.data_ptr(), x_batch_stride, s.data_ptr(), s_batch_stride, _ptr(y32), _ptr(y16), rows,
+                           rows_per_batch, _stream()), 'vi_mul_bcast')
+    _launched(1)
     return y32, y16
 
 
@@ -169,6 +196,7 @@ def duet_fuse_logits(g_raw, l_raw, fuse_raw, gmap_masks_u8, gmap_visited_u8, vp_
                                   gmap_visited_u8.data_ptr(), vp_nav_u8.data_ptr(), gmap_ids.data_ptr(),
                                   cand_ids.data_ptr(), gl.data_ptr(), ll.data_ptr(), fl.data_ptr(), B, G, P,
                                   _stream()), 'vi_duet_fuse_logits')
+    _launched(1)
     return gl, ll, fl
 
 
@@ -176,6 +204,7 @@ def mask_logits_navtype(raw: torch.Tensor, nav_types: torch.Tensor):
     out = torch.empty_like(raw)
     check(lib.vi_mask_logits_navtype(raw.data_ptr(), nav_types.data_ptr(), out.data_ptr(), raw.numel(), _stream()),
           'vi_mask_logits_navtype')
+    _launched(1)
     return out
 
 
@@ -184,11 +213,13 @@ def gather_mean(src: torch.Tensor, offsets: torch.Tensor, row_idx: torch.Tensor,
     y16 = torch.empty((R, HIDDEN), dtype=BF16, device=src.device) if want16 else None
     check(lib.vi_gather_mean(src.data_ptr(), offsets.data_ptr(), row_idx.data_ptr(), _ptr(y32), _ptr(y16), R, _stream()),
           'vi_gather_mean')
+    _launched(1)
     return y32, y16
 
 
 def scatter_rows(src: torch.Tensor, dst_rows: torch.Tensor, dst: torch.Tensor):
     check(lib.vi_scatter_rows(src.data_ptr(), dst_rows.data_ptr(), dst.data_ptr(), src.shape[0], _stream()), 'vi_scatter_rows')
+    _launched(1)
     return dst
 
 
@@ -196,6 +227,7 @@ def cosine_loss(proj: Optional[torch.Tensor], tgt: Optional[torch.Tensor], R: in
     loss = torch.empty((), dtype=F32, device=device)
     rows = torch.empty((max(R, 1),), dtype=F32, device=device)
     check(lib.vi_cosine_loss(_ptr(proj), _ptr(tgt), rows.data_ptr(), loss.data_ptr(), R, _stream()), 'vi_cosine_loss')
+    _launched(2)
     return loss, rows[:R]
 
 
@@ -204,6 +236,7 @@ def infonce_loss(proj, tgt, negs, row_episode, neg_episode, temperature: float, 
     scratch = torch.empty((max(R, 1) * (n_negs + 2),), dtype=F32, device=device)
     check(lib.vi_infonce_loss(_ptr(proj), _ptr(tgt), _ptr(negs), _ptr(row_episode), _ptr(neg_episode), temperature,
                               scratch.data_ptr(), loss.data_ptr(), R, n_negs, _stream()), 'vi_infonce_loss')
+    _launched(3)
     return loss
 
 
@@ -212,6 +245,7 @@ def copy_rows(src: torch.Tensor, src_bs: int, src_rs: int, n_batches: int, rows_
     """dst[b, r] = src[b, r] over 768-wide rows with element strides (see vi_copy_rows)."""
     check(lib.vi_copy_rows(src.data_ptr(), src_bs, src_rs, _ptr(dst32), _ptr(dst16), dst_bs, dst_rs, n_batches,
                            rows_per_batch, _stream()), 'vi_copy_rows')
+    _launched(1)
 
 
 def cast_bf16(src: torch.Tensor, dst: Optional[torch.Tensor] = None):
@@ -219,4 +253,5 @@ def cast_bf16(src: torch.Tensor, dst: Optional[torch.Tensor] = None):
     if dst is None:
         dst = torch.empty(src.shape, dtype=BF16, device=src.device)
     check(lib.vi_cast_bf16(src.data_ptr(), dst.data_ptr(), src.numel(), _stream()), 'vi_cast_bf16')
+    _launched(1)
     return dst
