@@ -80,6 +80,22 @@ int vi_gemm_f32(const float* x, int64_t ldx, const float* w, const float* bias,
  *   dtype: VI_DT_BF16 (mma.sync tiles, fp32 softmax) or VI_DT_F32 (check mode).
  *   lse [B, H, Lq] optional (log-sum-exp per row, kept for the backward pass).
  * ------------------------------------------------------------------------------------------- */
+#define VI_ATTN_MAX_PROBLEMS 4
+typedef struct {
+  const void* q; int64_t ldq;
+  const void* k; int64_t ldk;
+  const void* v; int64_t ldv;
+  void* o; int64_t ldo;
+  const uint8_t* key_mask;     /* [B, Lk] or NULL */
+  const float* pair_dist;      /* [B, Lq, Lk] or NULL */
+  const float* bias_affine;    /* device {w, b} */
+  float* lse;                  /* [B, H, Lq] or NULL */
+  int32_t B, Lq, Lk;
+} vi_attn_problem;
+/* Several independent attention problems (token streams of one row-stacked activation: DUET global | local,
+ * HAMT language | vision) in ONE launch; same arithmetic as vi_attn_fwd per problem. */
+int vi_attn_fwd_multi(const vi_attn_problem* problems, int n_problems, int H, int dtype, int mask_mode,
+                      vi_stream_t stream);
 int vi_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                 void* o, int64_t ldo, int dtype,
                 const uint8_t* key_mask, const float* pair_dist, const float* bias_affine,

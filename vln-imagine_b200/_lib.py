@@ -37,6 +37,12 @@ class EmbedArgs(C.Structure):
     ]
 
 
+class AttnProblem(C.Structure):
+    _fields_ = [('q', _p), ('ldq', _l), ('k', _p), ('ldk', _l), ('v', _p), ('ldv', _l), ('o', _p), ('ldo', _l),
+                ('key_mask', _p), ('pair_dist', _p), ('bias_affine', _p), ('lse', _p),
+                ('B', C.c_int32), ('Lq', C.c_int32), ('Lk', C.c_int32)]
+
+
 # name -> argtypes; every entry of include/vlnimagine.h must appear here (tests check the header against it)
 PROTOTYPES = {
     'vi_version': [],
@@ -44,6 +50,7 @@ PROTOTYPES = {
     'vi_gemm_bf16': [_p, _l, _p, _p, _p, _l, _p, _l, _i, _i, _i, _i, _i, _i, _ip, _p],
     'vi_gemm_f32': [_p, _l, _p, _p, _p, _l, _p, _l, _i, _i, _i, _i, _i, _ip, _p],
     'vi_attn_fwd': [_p, _l, _p, _l, _p, _l, _p, _l, _i, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
+    'vi_attn_fwd_multi': [C.POINTER(AttnProblem), _i, _i, _i, _i, _p],
     'vi_add_ln': [_p, _p, _p, _p, _f, _p, _p, _l, _i, _ip, _p],
     'vi_embed_compose': [C.POINTER(EmbedArgs), _p],
     'vi_ln_dot': [_p, _p, _p, _f, _p, _p, _p, _l, _i, _ip, _p],

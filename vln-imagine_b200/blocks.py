@@ -128,6 +128,17 @@ def stack_layout(token_counts: Sequence[int]):
     return row0, ends, cur
 
 
+def _ctx_buffer(rows: int, like: torch.Tensor, streams) -> torch.Tensor:
+    """Attention output buffer for a row-stacked activation.  The rows between streams (padding up to the next
+    128-row boundary) are never written by the attention kernel but do flow through the following GEMM, whose
+    rows are independent: they are zeroed so that the padding stays finite."""
+    ctx = torch.empty((rows, HIDDEN), dtype=like.dtype, device=like.device)
+    for a, b in zip(streams[:-1], streams[1:]):
+        if b.row0 > a.row0 + a.rows:
+            ctx[a.row0 + a.rows:b.row0].zero_()
+    return ctx
+
+
 def layer_norm(x32, res32, ln: LNPack, eps, lowp, ends=None) -> Act:
     g, b = ln.get()
     y32, y16 = ops.add_ln(x32, res32, g, b, eps, want16=lowp, group_row_end=ends)
@@ -158,13 +169,13 @@ def self_attn_ffn(x: Act, pk: SelfFFNPack, streams: List[Stream], ends, lowp: bo
     rows = xin.shape[0]
     w, b = pk.qkv.get(lowp)
     qkv = ops.gemm(xin, w, b, group_row_end=ends)                      # [rows, 2304]
-    ctx = torch.empty((rows, HIDDEN), dtype=xin.dtype, device=xin.device)
-    if len(streams) > 1:
-        ctx.zero_()            # rows between streams feed the next GEMM: keep them finite
+    ctx = _ctx_buffer(rows, xin, streams)
+    probs = []
     for s in streams:
         q = s.view(qkv)
-        ops.attention(q[:, 0:HIDDEN], q[:, HIDDEN:2 * HIDDEN], q[:, 2 * HIDDEN:3 * HIDDEN], s.B, s.L, s.L,
-                      key_mask=s.mask, pair_dist=s.pair_dist, bias_affine=s.bias_affine, out=s.view(ctx))
+        probs.append(dict(q=q[:, 0:HIDDEN], k=q[:, HIDDEN:2 * HIDDEN], v=q[:, 2 * HIDDEN:3 * HIDDEN], out=s.view(ctx),
+                          B=s.B, Lq=s.L, Lk=s.L, key_mask=s.mask, pair_dist=s.pair_dist, bias_affine=s.bias_affine))
+    ops.attention_multi(probs)
     w, b = pk.o.get(lowp)
     ao = ops.gemm(ctx, w, b, residual=x.f32, out_dtype=F32, group_row_end=ends)
     y = layer_norm(ao, None, pk.ln1, eps, lowp, ends)
@@ -199,12 +210,9 @@ def cross_attn(x: Act, kv: torch.Tensor, kv_col0: Sequence[int], ctx_len: int, c
     rows = xin.shape[0]
     w, b = pk.q.get(lowp)
     q = ops.gemm(xin, w, b, group_row_end=ends)
-    ctx = torch.empty((rows, HIDDEN), dtype=xin.dtype, device=xin.device)
-    if len(streams) > 1:
-        ctx.zero_()
-    for s, c0 in zip(streams, kv_col0):
-        ops.attention(s.view(q), kv[:, c0:c0 + HIDDEN], kv[:, c0 + HIDDEN:c0 + 2 * HIDDEN], s.B, s.L, ctx_len,
-                      key_mask=ctx_mask, out=s.view(ctx))
+    ctx = _ctx_buffer(rows, xin, streams)
+    ops.attention_multi([dict(q=s.view(q), k=kv[:, c0:c0 + HIDDEN], v=kv[:, c0 + HIDDEN:c0 + 2 * HIDDEN], out=s.view(ctx),
+                              B=s.B, Lq=s.L, Lk=ctx_len, key_mask=ctx_mask) for s, c0 in zip(streams, kv_col0)])
     w, b = pk.o.get(lowp)
     ao = ops.gemm(ctx, w, b, residual=x.f32, out_dtype=F32, group_row_end=ends)
     return layer_norm(ao, None, pk.ln, eps, lowp, ends)
@@ -217,7 +225,12 @@ def as_act(x32: torch.Tensor, lowp: bool) -> Act:
 
 
 def mask_u8(m: Optional[torch.Tensor]):
-    return None if m is None else m.to(torch.uint8).contiguous()
+    """bool mask -> the uint8 view the kernels read (zero-copy for contiguous bool tensors)."""
+    if m is None:
+        return None
+    if m.dtype == torch.bool and m.is_contiguous():
+        return m.view(torch.uint8)
+    return m.to(torch.uint8).contiguous()
 
 
 class PanoLayerPack:

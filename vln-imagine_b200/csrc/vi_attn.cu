@@ -15,7 +15,9 @@
 
 namespace {
 
-struct AttnParams {
+// one attention problem = one token stream; a launch runs up to VI_ATTN_MAX_PROBLEMS of them so that the
+// streams of a row-stacked activation (DUET global|local, HAMT language|vision) share one kernel launch
+struct AttnProblem {
   const void* q; long long ldq;
   const void* k; long long ldk;
   const void* v; long long ldv;
@@ -24,11 +26,15 @@ struct AttnParams {
   const float* pair_dist;
   const float* bias_affine;
   float* lse;
-  int B, H, Lq, Lk, LkP, mask_mode;
+  int B, Lq, Lk, LkP;
+};
+struct AttnParams {
+  AttnProblem pr[VI_ATTN_MAX_PROBLEMS];
+  int n_problems, H, mask_mode;
 };
 
 constexpr int DH = 64;
-constexpr int KS_STRIDE = 72;      // bf16 elements per K row in smem (64 + 8: conflict-free fragment loads)
+constexpr int ROW = 72;            // bf16 elements per staged row (64 + 8): 144-byte pitch keeps ldmatrix conflict-free
 
 __device__ __forceinline__ void mma_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
@@ -36,68 +42,83 @@ __device__ __forceinline__ void mma_16816(float (&c)[4], const uint32_t (&a)[4],
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
+  const int sz = valid ? 16 : 0;       // src-size 0 zero-fills the 16 bytes
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory"); }
 
-// grid (ceil(Lq/64), H, B), 128 threads: warp w owns query rows [64*bx + 16w, +16)
+// grid (q-tiles of 64, H, sum of B over problems), 128 threads: warp w owns query rows [64*bx + 16w, +16).
+// K, V (whole head) and the Q tile are staged with cp.async; fragments come from ldmatrix (V through .trans, so no
+// explicit transpose); scores stay in registers with an fp32 online softmax over 64-key chunks.
 __global__ void __launch_bounds__(128) attn_fwd_bf16_kernel(const AttnParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
-  const int LkP = p.LkP;
-  const int vt_stride = LkP + 8;
-  bf16* Ks = reinterpret_cast<bf16*>(smem);                           // [LkP][72]
-  bf16* Vt = Ks + (size_t)LkP * KS_STRIDE;                            // [64][LkP+8]   (V transposed)
-  float* madd = reinterpret_cast<float*>(Vt + (size_t)DH * vt_stride);  // [LkP]
-
-  const int b = blockIdx.z, h = blockIdx.y;
+  int z = blockIdx.z, pi = 0;
+  while (pi < p.n_problems - 1 && z >= p.pr[pi].B) { z -= p.pr[pi].B; ++pi; }
+  const AttnProblem& pr = p.pr[pi];
+  const int q_base = blockIdx.x * 64;
+  if (q_base >= pr.Lq) return;
+  const int b = z, h = blockIdx.y;
+  const int LkP = pr.LkP;
+  bf16* Ks = reinterpret_cast<bf16*>(smem);                 // [LkP][72]
+  bf16* Vs = Ks + (size_t)LkP * ROW;                        // [LkP][72]
+  bf16* Qs = Vs + (size_t)LkP * ROW;                        // [64][72]
+  float* madd = reinterpret_cast<float*>(Qs + 64 * ROW);    // [LkP]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const bf16* kg = reinterpret_cast<const bf16*>(p.k) + (long long)b * p.Lk * p.ldk + h * DH;
-  const bf16* vg = reinterpret_cast<const bf16*>(p.v) + (long long)b * p.Lk * p.ldv + h * DH;
 
-  // ---- stage K (row-major, padded stride) and V (transposed) for this (episode, head) ----
+  const bf16* kg = reinterpret_cast<const bf16*>(pr.k) + (long long)b * pr.Lk * pr.ldk + h * DH;
+  const bf16* vg = reinterpret_cast<const bf16*>(pr.v) + (long long)b * pr.Lk * pr.ldv + h * DH;
+  const bf16* qg = reinterpret_cast<const bf16*>(pr.q) + (long long)b * pr.Lq * pr.ldq + h * DH;
+  const uint32_t ks_u = smem_u32(Ks), vs_u = smem_u32(Vs), qs_u = smem_u32(Qs);
   for (int e = tid; e < LkP * 8; e += 128) {
     const int key = e >> 3, ch = e & 7;
-    uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
-    if (key < p.Lk) {
-      kv = *reinterpret_cast<const uint4*>(kg + (long long)key * p.ldk + ch * 8);
-      vv = *reinterpret_cast<const uint4*>(vg + (long long)key * p.ldv + ch * 8);
-    }
-    *reinterpret_cast<uint4*>(Ks + (size_t)key * KS_STRIDE + ch * 8) = kv;
-    const bf16* ve = reinterpret_cast<const bf16*>(&vv);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) Vt[(size_t)(ch * 8 + i) * vt_stride + key] = ve[i];
+    const bool ok = key < pr.Lk;
+    const int kk = ok ? key : 0;
+    cp_async16(ks_u + (uint32_t)(key * ROW + ch * 8) * 2, kg + (long long)kk * pr.ldk + ch * 8, ok);
+    cp_async16(vs_u + (uint32_t)(key * ROW + ch * 8) * 2, vg + (long long)kk * pr.ldv + ch * 8, ok);
+  }
+  for (int e = tid; e < 64 * 8; e += 128) {
+    const int r = e >> 3, ch = e & 7;
+    const bool ok = q_base + r < pr.Lq;
+    const int rr = ok ? q_base + r : 0;
+    cp_async16(qs_u + (uint32_t)(r * ROW + ch * 8) * 2, qg + (long long)rr * pr.ldq + ch * 8, ok);
   }
   for (int key = tid; key < LkP; key += 128) {
     float m = 0.f;
-    if (key >= p.Lk) m = -INFINITY;
-    else if (p.key_mask && !p.key_mask[(long long)b * p.Lk + key]) m = (p.mask_mode == VI_MASK_NEG_INF) ? -INFINITY : -10000.0f;
+    if (key >= pr.Lk) m = -INFINITY;
+    else if (pr.key_mask && !pr.key_mask[(long long)b * pr.Lk + key]) m = (p.mask_mode == VI_MASK_NEG_INF) ? -INFINITY : -10000.0f;
     madd[key] = m;
   }
+  cp_async_wait_all();
   __syncthreads();
 
-  const int q0 = blockIdx.x * 64 + warp * 16;
-  if (q0 >= p.Lq) return;
+  const int q0 = q_base + warp * 16;
+  if (q0 >= pr.Lq) return;
   const int g = lane >> 2, tg = lane & 3;
   const int r0 = q0 + g, r1 = q0 + g + 8;
+  const int lm = lane >> 3, lr = lane & 7;          // ldmatrix: this lane addresses row lr of matrix lm
 
-  // ---- Q fragments (16 rows x 64) straight from global ----
   uint32_t qa[4][4];
-  {
-    const bf16* qg = reinterpret_cast<const bf16*>(p.q) + (long long)b * p.Lq * p.ldq + h * DH;
 #pragma unroll
-    for (int ks = 0; ks < 4; ++ks) {
-      const int c = ks * 16 + 2 * tg;
-      qa[ks][0] = r0 < p.Lq ? *reinterpret_cast<const uint32_t*>(qg + (long long)r0 * p.ldq + c) : 0u;
-      qa[ks][1] = r1 < p.Lq ? *reinterpret_cast<const uint32_t*>(qg + (long long)r1 * p.ldq + c) : 0u;
-      qa[ks][2] = r0 < p.Lq ? *reinterpret_cast<const uint32_t*>(qg + (long long)r0 * p.ldq + c + 8) : 0u;
-      qa[ks][3] = r1 < p.Lq ? *reinterpret_cast<const uint32_t*>(qg + (long long)r1 * p.ldq + c + 8) : 0u;
-    }
-  }
+  for (int ks = 0; ks < 4; ++ks)
+    ldsm_x4(qa[ks], qs_u + (uint32_t)((warp * 16 + (lm & 1) * 8 + lr) * ROW + ks * 16 + (lm >> 1) * 8) * 2);
+
   float bw = 0.f, bb = 0.f;
   const float* pd0 = nullptr;
   const float* pd1 = nullptr;
-  if (p.pair_dist) {
-    bw = p.bias_affine[0];
-    bb = p.bias_affine[1];
-    pd0 = p.pair_dist + ((long long)b * p.Lq + (r0 < p.Lq ? r0 : 0)) * p.Lk;
-    pd1 = p.pair_dist + ((long long)b * p.Lq + (r1 < p.Lq ? r1 : 0)) * p.Lk;
+  if (pr.pair_dist) {
+    bw = pr.bias_affine[0];
+    bb = pr.bias_affine[1];
+    pd0 = pr.pair_dist + ((long long)b * pr.Lq + (r0 < pr.Lq ? r0 : 0)) * pr.Lk;
+    pd1 = pr.pair_dist + ((long long)b * pr.Lq + (r1 < pr.Lq ? r1 : 0)) * pr.Lk;
   }
 
   float o[8][4];
@@ -106,19 +127,19 @@ __global__ void __launch_bounds__(128) attn_fwd_bf16_kernel(const AttnParams p) 
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
 
   for (int kc = 0; kc < LkP; kc += 64) {
-    const int ntiles = min(8, (LkP - kc) >> 3);       // LkP % 16 == 0 -> even
+    const int npairs = min(4, (LkP - kc) >> 4);       // 16-key blocks in this chunk (LkP % 16 == 0)
     float s[8][4];
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      if (nt < ntiles) {
-        const bf16* kr = Ks + (size_t)(kc + nt * 8 + g) * KS_STRIDE + 2 * tg;
+    for (int np = 0; np < 4; ++np) {
+      if (np < npairs) {
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
-          const uint32_t b0 = *reinterpret_cast<const uint32_t*>(kr + ks * 16);
-          const uint32_t b1 = *reinterpret_cast<const uint32_t*>(kr + ks * 16 + 8);
-          mma_16816(s[nt], qa[ks], b0, b1);
+          uint32_t kb[4];     // (keys 0-7, d 0-7) (keys 0-7, d 8-15) (keys 8-15, d 0-7) (keys 8-15, d 8-15)
+          ldsm_x4(kb, ks_u + (uint32_t)((kc + np * 16 + (lm >> 1) * 8 + lr) * ROW + ks * 16 + (lm & 1) * 8) * 2);
+          mma_16816(s[2 * np], qa[ks], kb[0], kb[1]);
+          mma_16816(s[2 * np + 1], qa[ks], kb[2], kb[3]);
         }
       }
     }
@@ -126,18 +147,18 @@ __global__ void __launch_bounds__(128) attn_fwd_bf16_kernel(const AttnParams p) 
     float cm0 = -INFINITY, cm1 = -INFINITY;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
-      if (nt < ntiles) {
+      if (nt < 2 * npairs) {
         const int key = kc + nt * 8 + 2 * tg;
-        const float ma = madd[key], mb = madd[key + 1];
+        const float2 ma = *reinterpret_cast<const float2*>(madd + key);
         float b00 = 0.f, b01 = 0.f, b10 = 0.f, b11 = 0.f;
         if (pd0) {
-          if (key < p.Lk) { b00 = fmaf(bw, pd0[key], bb); b10 = fmaf(bw, pd1[key], bb); }
-          if (key + 1 < p.Lk) { b01 = fmaf(bw, pd0[key + 1], bb); b11 = fmaf(bw, pd1[key + 1], bb); }
+          if (key < pr.Lk) { b00 = fmaf(bw, __ldg(pd0 + key), bb); b10 = fmaf(bw, __ldg(pd1 + key), bb); }
+          if (key + 1 < pr.Lk) { b01 = fmaf(bw, __ldg(pd0 + key + 1), bb); b11 = fmaf(bw, __ldg(pd1 + key + 1), bb); }
         }
-        s[nt][0] = s[nt][0] * 0.125f + ma + b00;
-        s[nt][1] = s[nt][1] * 0.125f + mb + b01;
-        s[nt][2] = s[nt][2] * 0.125f + ma + b10;
-        s[nt][3] = s[nt][3] * 0.125f + mb + b11;
+        s[nt][0] = s[nt][0] * 0.125f + ma.x + b00;
+        s[nt][1] = s[nt][1] * 0.125f + ma.y + b01;
+        s[nt][2] = s[nt][2] * 0.125f + ma.x + b10;
+        s[nt][3] = s[nt][3] * 0.125f + ma.y + b11;
         cm0 = fmaxf(cm0, fmaxf(s[nt][0], s[nt][1]));
         cm1 = fmaxf(cm1, fmaxf(s[nt][2], s[nt][3]));
       }
@@ -156,28 +177,28 @@ __global__ void __launch_bounds__(128) attn_fwd_bf16_kernel(const AttnParams p) 
     for (int dt = 0; dt < 8; ++dt) { o[dt][0] *= sc0; o[dt][1] *= sc0; o[dt][2] *= sc1; o[dt][3] *= sc1; }
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
-      if (nt < ntiles) {
+      if (nt < 2 * npairs) {
         s[nt][0] = __expf(s[nt][0] - mu0); s[nt][1] = __expf(s[nt][1] - mu0);
         s[nt][2] = __expf(s[nt][2] - mu1); s[nt][3] = __expf(s[nt][3] - mu1);
         l0 += s[nt][0] + s[nt][1];
         l1 += s[nt][2] + s[nt][3];
       }
     }
-    // O += P V : P (accumulator layout) re-packed as the A operand, V^T rows give the B operand
+    // O += P V : P (accumulator layout) re-packed as the A operand; V fragments through ldmatrix.trans
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
-      if (2 * kk < ntiles) {
+      if (kk < npairs) {
         uint32_t pa[4];
         pa[0] = pack_bf16x2(s[2 * kk][0], s[2 * kk][1]);
         pa[1] = pack_bf16x2(s[2 * kk][2], s[2 * kk][3]);
         pa[2] = pack_bf16x2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
         pa[3] = pack_bf16x2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
-        const bf16* vr = Vt + (size_t)g * vt_stride + kc + kk * 16 + 2 * tg;
 #pragma unroll
-        for (int dt = 0; dt < 8; ++dt) {
-          const uint32_t b0 = *reinterpret_cast<const uint32_t*>(vr + (size_t)dt * 8 * vt_stride);
-          const uint32_t b1 = *reinterpret_cast<const uint32_t*>(vr + (size_t)dt * 8 * vt_stride + 8);
-          mma_16816(o[dt], pa, b0, b1);
+        for (int d2 = 0; d2 < 4; ++d2) {
+          uint32_t vb[4];     // (keys 0-7, d 0-7)^T (keys 8-15, d 0-7)^T (keys 0-7, d 8-15)^T (keys 8-15, d 8-15)^T
+          ldsm_x4_trans(vb, vs_u + (uint32_t)((kc + kk * 16 + (lm & 1) * 8 + lr) * ROW + d2 * 16 + (lm >> 1) * 8) * 2);
+          mma_16816(o[2 * d2], pa, vb[0], vb[1]);
+          mma_16816(o[2 * d2 + 1], pa, vb[2], vb[3]);
         }
       }
     }
@@ -187,22 +208,22 @@ __global__ void __launch_bounds__(128) attn_fwd_bf16_kernel(const AttnParams p) 
   l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
   l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
   const float i0 = 1.0f / l0, i1 = 1.0f / l1;
-  bf16* og = reinterpret_cast<bf16*>(p.o) + (long long)b * p.Lq * p.ldo + h * DH;
+  bf16* og = reinterpret_cast<bf16*>(pr.o) + (long long)b * pr.Lq * pr.ldo + h * DH;
 #pragma unroll
   for (int dt = 0; dt < 8; ++dt) {
     const int c = dt * 8 + 2 * tg;
-    if (r0 < p.Lq) *reinterpret_cast<uint32_t*>(og + (long long)r0 * p.ldo + c) = pack_bf16x2(o[dt][0] * i0, o[dt][1] * i0);
-    if (r1 < p.Lq) *reinterpret_cast<uint32_t*>(og + (long long)r1 * p.ldo + c) = pack_bf16x2(o[dt][2] * i1, o[dt][3] * i1);
+    if (r0 < pr.Lq) *reinterpret_cast<uint32_t*>(og + (long long)r0 * pr.ldo + c) = pack_bf16x2(o[dt][0] * i0, o[dt][1] * i0);
+    if (r1 < pr.Lq) *reinterpret_cast<uint32_t*>(og + (long long)r1 * pr.ldo + c) = pack_bf16x2(o[dt][2] * i1, o[dt][3] * i1);
   }
-  if (p.lse && tg == 0) {
-    float* lg = p.lse + ((long long)b * p.H + h) * p.Lq;
-    if (r0 < p.Lq) lg[r0] = m0 + logf(l0);
-    if (r1 < p.Lq) lg[r1] = m1 + logf(l1);
+  if (pr.lse && tg == 0) {
+    float* lg = pr.lse + ((long long)b * p.H + h) * pr.Lq;
+    if (r0 < pr.Lq) lg[r0] = m0 + logf(l0);
+    if (r1 < pr.Lq) lg[r1] = m1 + logf(l1);
   }
 }
 
 // fp32 check mode: grid (H, B), 128 threads; warp w handles query rows w, w+4, ...
-__global__ void __launch_bounds__(128) attn_fwd_f32_kernel(const AttnParams p) {
+__global__ void __launch_bounds__(128) attn_fwd_f32_kernel(const AttnProblem p, const int H, const int mask_mode) {
   extern __shared__ __align__(16) uint8_t smem[];
   float* Ks = reinterpret_cast<float*>(smem);            // [Lk][65]
   float* Vs = Ks + (size_t)p.Lk * 65;                    // [Lk][64]
@@ -220,7 +241,7 @@ __global__ void __launch_bounds__(128) attn_fwd_f32_kernel(const AttnParams p) {
   }
   for (int key = tid; key < p.Lk; key += 128) {
     float m = 0.f;
-    if (p.key_mask && !p.key_mask[(long long)b * p.Lk + key]) m = (p.mask_mode == VI_MASK_NEG_INF) ? -INFINITY : -10000.0f;
+    if (p.key_mask && !p.key_mask[(long long)b * p.Lk + key]) m = (mask_mode == VI_MASK_NEG_INF) ? -INFINITY : -10000.0f;
     madd[key] = m;
   }
   __syncthreads();
@@ -267,49 +288,80 @@ __global__ void __launch_bounds__(128) attn_fwd_f32_kernel(const AttnParams p) {
     const float inv = 1.0f / sum;
     og[(long long)r * p.ldo + lane] = a0 * inv;
     og[(long long)r * p.ldo + lane + 32] = a1 * inv;
-    if (p.lse && lane == 0) p.lse[((long long)b * p.H + h) * p.Lq + r] = mx + logf(sum);
+    if (p.lse && lane == 0) p.lse[((long long)b * H + h) * p.Lq + r] = mx + logf(sum);
     __syncwarp();
   }
 }
 
 }  // namespace
 
+static int check_problem(const vi_attn_problem& a, int H, int dtype, AttnProblem& o) {
+  VI_CHECK_ARG(a.q && a.k && a.v && a.o, "vi_attn_fwd: null operand");
+  VI_CHECK_ARG(a.B > 0 && a.Lq > 0 && a.Lk > 0, "vi_attn_fwd: empty problem B=%d Lq=%d Lk=%d", a.B, a.Lq, a.Lk);
+  VI_CHECK_ARG(a.Lk <= 512, "vi_attn_fwd: Lk=%d exceeds the single-pass limit of 512 keys", a.Lk);
+  VI_CHECK_ARG(!a.pair_dist || a.bias_affine, "vi_attn_fwd: pair_dist needs bias_affine {w,b}");
+  const int64_t hd = (int64_t)H * DH;
+  VI_CHECK_ARG(a.ldq >= hd && a.ldk >= hd && a.ldv >= hd && a.ldo >= hd, "vi_attn_fwd: leading dimensions smaller than H*64");
+  if (dtype == VI_DT_BF16) {
+    VI_CHECK_ARG(a.ldq % 8 == 0 && a.ldk % 8 == 0 && a.ldv % 8 == 0 && a.ldo % 2 == 0,
+                 "vi_attn_fwd: bf16 leading dims must be multiples of 8");
+    VI_CHECK_ARG((((uintptr_t)a.q | (uintptr_t)a.k | (uintptr_t)a.v) & 15) == 0 && ((uintptr_t)a.o & 3) == 0,
+                 "vi_attn_fwd: misaligned bf16 operands");
+  }
+  o.q = a.q; o.ldq = a.ldq; o.k = a.k; o.ldk = a.ldk; o.v = a.v; o.ldv = a.ldv; o.o = a.o; o.ldo = a.ldo;
+  o.key_mask = a.key_mask; o.pair_dist = a.pair_dist; o.bias_affine = a.bias_affine; o.lse = a.lse;
+  o.B = a.B; o.Lq = a.Lq; o.Lk = a.Lk; o.LkP = (a.Lk + 15) & ~15;
+  return VI_OK;
+}
+
+extern "C" int vi_attn_fwd_multi(const vi_attn_problem* problems, int n_problems, int H, int dtype, int mask_mode,
+                                 vi_stream_t stream) {
+  VI_CHECK_ARG(problems && n_problems >= 1 && n_problems <= VI_ATTN_MAX_PROBLEMS, "vi_attn_fwd_multi: 1..%d problems",
+               VI_ATTN_MAX_PROBLEMS);
+  VI_CHECK_ARG(H > 0, "vi_attn_fwd_multi: H must be positive");
+  VI_CHECK_ARG(mask_mode == VI_MASK_ADD_NEG10000 || mask_mode == VI_MASK_NEG_INF, "vi_attn_fwd: bad mask_mode");
+  VI_CHECK_ARG(dtype == VI_DT_BF16 || dtype == VI_DT_F32, "vi_attn_fwd: bad dtype %d", dtype);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  AttnParams p;
+  memset(&p, 0, sizeof(p));
+  p.n_problems = n_problems; p.H = H; p.mask_mode = mask_mode;
+  int total_b = 0, max_lq = 0, max_lkp = 0;
+  for (int i = 0; i < n_problems; ++i) {
+    if (int rc = check_problem(problems[i], H, dtype, p.pr[i])) return rc;
+    total_b += p.pr[i].B;
+    max_lq = p.pr[i].Lq > max_lq ? p.pr[i].Lq : max_lq;
+    max_lkp = p.pr[i].LkP > max_lkp ? p.pr[i].LkP : max_lkp;
+  }
+  if (dtype == VI_DT_BF16) {
+    const size_t smem = (size_t)max_lkp * ROW * 2 * 2 + 64 * ROW * 2 + (size_t)max_lkp * 4;
+    dim3 grid((max_lq + 63) / 64, H, total_b);
+    attn_fwd_bf16_kernel<<<grid, 128, smem, st>>>(p);
+    VI_LAUNCH_CHECK();
+  } else {
+    for (int i = 0; i < n_problems; ++i) {
+      const AttnProblem& a = p.pr[i];
+      const size_t smem = ((size_t)a.Lk * 65 + (size_t)a.Lk * 64 + a.Lk + 4 * (size_t)a.Lk + 4 * 64) * 4;
+      dim3 grid(H, a.B);
+      attn_fwd_f32_kernel<<<grid, 128, smem, st>>>(a, H, mask_mode);
+      VI_LAUNCH_CHECK();
+    }
+  }
+  return VI_OK;
+}
+
 extern "C" int vi_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o,
                            int64_t ldo, int dtype, const uint8_t* key_mask, const float* pair_dist,
                            const float* bias_affine, float* lse, int B, int H, int Lq, int Lk, int mask_mode,
                            vi_stream_t stream) {
-  VI_CHECK_ARG(q && k && v && o, "vi_attn_fwd: null operand");
-  VI_CHECK_ARG(B > 0 && H > 0 && Lq > 0 && Lk > 0, "vi_attn_fwd: empty problem B=%d H=%d Lq=%d Lk=%d", B, H, Lq, Lk);
-  VI_CHECK_ARG(Lk <= 512, "vi_attn_fwd: Lk=%d exceeds the single-pass limit of 512 keys", Lk);
-  VI_CHECK_ARG(mask_mode == VI_MASK_ADD_NEG10000 || mask_mode == VI_MASK_NEG_INF, "vi_attn_fwd: bad mask_mode");
-  VI_CHECK_ARG(!pair_dist || bias_affine, "vi_attn_fwd: pair_dist needs bias_affine {w,b}");
-  VI_CHECK_ARG(ldq >= (int64_t)H * DH && ldk >= (int64_t)H * DH && ldv >= (int64_t)H * DH && ldo >= (int64_t)H * DH,
-               "vi_attn_fwd: leading dimensions smaller than H*64");
-  AttnParams p;
-  p.q = q; p.ldq = ldq; p.k = k; p.ldk = ldk; p.v = v; p.ldv = ldv; p.o = o; p.ldo = ldo;
-  p.key_mask = key_mask; p.pair_dist = pair_dist; p.bias_affine = bias_affine; p.lse = lse;
-  p.B = B; p.H = H; p.Lq = Lq; p.Lk = Lk; p.LkP = (Lk + 15) & ~15; p.mask_mode = mask_mode;
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (dtype == VI_DT_BF16) {
-    VI_CHECK_ARG(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 2 == 0, "vi_attn_fwd: bf16 leading dims must be multiples of 8");
-    VI_CHECK_ARG((((uintptr_t)q | (uintptr_t)k | (uintptr_t)v) & 15) == 0 && ((uintptr_t)o & 3) == 0, "vi_attn_fwd: misaligned bf16 operands");
-    const size_t smem = (size_t)p.LkP * KS_STRIDE * 2 + (size_t)DH * (p.LkP + 8) * 2 + (size_t)p.LkP * 4;
-    dim3 grid((Lq + 63) / 64, H, B);
-    attn_fwd_bf16_kernel<<<grid, 128, smem, st>>>(p);
-  } else if (dtype == VI_DT_F32) {
-    const size_t smem = ((size_t)Lk * 65 + (size_t)Lk * 64 + Lk + 4 * (size_t)Lk + 4 * 64) * 4;
-    dim3 grid(H, B);
-    attn_fwd_f32_kernel<<<grid, 128, smem, st>>>(p);
-  } else {
-    vi_set_error("vi_attn_fwd: bad dtype %d", dtype);
-    return VI_ERR_ARG;
-  }
-  VI_LAUNCH_CHECK();
-  return VI_OK;
+  vi_attn_problem a;
+  a.q = q; a.ldq = ldq; a.k = k; a.ldk = ldk; a.v = v; a.ldv = ldv; a.o = o; a.ldo = ldo;
+  a.key_mask = key_mask; a.pair_dist = pair_dist; a.bias_affine = bias_affine; a.lse = lse;
+  a.B = B; a.Lq = Lq; a.Lk = Lk;
+  return vi_attn_fwd_multi(&a, 1, H, dtype, mask_mode, stream);
 }
 
 int vi_attn_init() {
-  VI_CUDA(cudaFuncSetAttribute(attn_fwd_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  VI_CUDA(cudaFuncSetAttribute(attn_fwd_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 176 * 1024));
   VI_CUDA(cudaFuncSetAttribute(attn_fwd_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   return VI_OK;
 }

@@ -112,41 +112,57 @@ __global__ void __launch_bounds__(128) add_ln_kernel(const float* __restrict__ a
   row_store(r, y32, y16, row, lane);
 }
 
-__global__ void __launch_bounds__(128) embed_compose_kernel(const vi_embed_args p) {
-  ROW_INDEX();
-  if (row >= p.rows) return;
-  Row acc;
-  row_zero(acc);
-  if (p.a) {
-    Row t;
-    row_load(t, p.a + row * D, lane);
-    if (p.a_gamma) row_layernorm(t, p.a_gamma, p.a_beta, p.eps, lane);
-    row_acc(acc, t);
-  }
+// 8 warps per CTA, one row per warp per iteration, CTAs stride over the rows.  The small feature projection
+// (feat_dim <= 16) reads its weight matrix from a transposed shared-memory copy [feat_dim][768] that the CTA
+// loads once, so a row costs feat_dim conflict-free float4 reads per 4 outputs instead of strided global loads.
+constexpr int EMBED_WARPS = 8;
+__global__ void __launch_bounds__(EMBED_WARPS * 32) embed_compose_kernel(const vi_embed_args p) {
+  extern __shared__ __align__(16) float wT[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (p.feat) {
-    Row t;
-    float f[16];
-    for (int k = 0; k < p.feat_dim; ++k) f[k] = __ldg(p.feat + row * p.feat_dim + k);
-#pragma unroll
-    for (int j = 0; j < V4; ++j) {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int c = (lane + 32 * j) * 4 + e;
-        float s = p.feat_b ? __ldg(p.feat_b + c) : 0.f;
-        const float* wr = p.feat_w + (long long)c * p.feat_dim;
-        for (int k = 0; k < p.feat_dim; ++k) s = fmaf(f[k], __ldg(wr + k), s);
-        t.v[4 * j + e] = s;
-      }
+    const int n = D * p.feat_dim;
+    for (int i = threadIdx.x; i < n; i += EMBED_WARPS * 32) {
+      const int c = i / p.feat_dim, k = i - c * p.feat_dim;
+      wT[k * D + c] = __ldg(p.feat_w + i);
     }
-    if (p.feat_gamma) row_layernorm(t, p.feat_gamma, p.feat_beta, p.eps, lane);
-    row_acc(acc, t);
+    __syncthreads();
   }
-  if (p.idx) row_add(acc, p.table + p.idx[row] * D, lane);
-  if (p.pos_table) row_add(acc, p.pos_table + (row % p.pos_period) * D, lane);
-  if (p.const_row) row_add(acc, p.const_row, lane);
-  if (p.const_row2) row_add(acc, p.const_row2, lane);
-  if (p.out_gamma) row_layernorm(acc, p.out_gamma, p.out_beta, p.eps, lane);
-  row_store(acc, p.y32, reinterpret_cast<bf16*>(p.y16), row, lane);
+  for (long long row = (long long)blockIdx.x * EMBED_WARPS + warp; row < p.rows; row += (long long)gridDim.x * EMBED_WARPS) {
+    Row acc;
+    row_zero(acc);
+    if (p.a) {
+      Row t;
+      row_load(t, p.a + row * D, lane);
+      if (p.a_gamma) row_layernorm(t, p.a_gamma, p.a_beta, p.eps, lane);
+      row_acc(acc, t);
+    }
+    if (p.feat) {
+      Row t;
+      if (p.feat_b) row_load(t, p.feat_b, lane);
+      else row_zero(t);
+      const float* fr = p.feat + row * p.feat_dim;
+      for (int k = 0; k < p.feat_dim; ++k) {
+        const float f = __ldg(fr + k);
+        const float4* w4 = reinterpret_cast<const float4*>(wT + k * D);
+#pragma unroll
+        for (int j = 0; j < V4; ++j) {
+          const float4 w = w4[lane + 32 * j];
+          t.v[4 * j] = fmaf(f, w.x, t.v[4 * j]);
+          t.v[4 * j + 1] = fmaf(f, w.y, t.v[4 * j + 1]);
+          t.v[4 * j + 2] = fmaf(f, w.z, t.v[4 * j + 2]);
+          t.v[4 * j + 3] = fmaf(f, w.w, t.v[4 * j + 3]);
+        }
+      }
+      if (p.feat_gamma) row_layernorm(t, p.feat_gamma, p.feat_beta, p.eps, lane);
+      row_acc(acc, t);
+    }
+    if (p.idx) row_add(acc, p.table + p.idx[row] * D, lane);
+    if (p.pos_table) row_add(acc, p.pos_table + (row % p.pos_period) * D, lane);
+    if (p.const_row) row_add(acc, p.const_row, lane);
+    if (p.const_row2) row_add(acc, p.const_row2, lane);
+    if (p.out_gamma) row_layernorm(acc, p.out_gamma, p.out_beta, p.eps, lane);
+    row_store(acc, p.y32, reinterpret_cast<bf16*>(p.y16), row, lane);
+  }
 }
 
 __global__ void __launch_bounds__(128) ln_dot_kernel(const float* __restrict__ h, const float* __restrict__ gamma,
@@ -422,8 +438,13 @@ extern "C" int vi_embed_compose(const vi_embed_args* args, vi_stream_t stream) {
   VI_CHECK_ARG(aligned16(p.a) && aligned16(p.table) && aligned16(p.pos_table) && aligned16(p.const_row) &&
                    aligned16(p.const_row2) && aligned16(p.y32) && ((uintptr_t)p.y16 & 7) == 0,
                "vi_embed_compose: row operands must be 16-byte aligned");
+  VI_CHECK_ARG(aligned16(p.feat_b), "vi_embed_compose: feat_b must be 16-byte aligned");
   if (p.rows <= 0) return VI_OK;
-  embed_compose_kernel<<<row_grid(p.rows), 128, 0, ST(stream)>>>(p);
+  long long blocks = (p.rows + EMBED_WARPS - 1) / EMBED_WARPS;
+  const long long cap = 2LL * vi_num_sms();
+  if (p.feat && blocks > cap) blocks = cap;          // amortise the weight staging over several rows per warp
+  const size_t smem = p.feat ? (size_t)p.feat_dim * D * sizeof(float) : 0;
+  embed_compose_kernel<<<(unsigned)blocks, EMBED_WARPS * 32, smem, ST(stream)>>>(p);
   VI_LAUNCH_CHECK();
   return VI_OK;
 }

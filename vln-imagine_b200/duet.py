@@ -182,6 +182,9 @@ class GlocalTextPathNavCMT(nn.Module):
             pk['x_self'] = [blocks.SelfFFNPack([g.visn_self_att, l.visn_self_att], [g.visn_inter, l.visn_inter],
                                                [g.visn_output, l.visn_output]) for g, l in zip(gl, ll)]
             pk['sap'] = blocks.ClsHeadPack([self.global_sap_head, self.local_sap_head])
+            if self.global_encoder.sprel_linear is not None:
+                sl = self.global_encoder.sprel_linear
+                pk['sprel'] = blocks.StackPack([sl.weight, sl.bias])         # device {w, b} of the GASA bias
             if self.sap_fuse_linear is not None:
                 pk['fuse'] = blocks.ClsHeadPack([self.sap_fuse_linear])
             if hasattr(self, 'contrastive_alignment_model'):
@@ -253,7 +256,7 @@ class GlocalTextPathNavCMT(nn.Module):
             const_row=self.embeddings.token_type_embeddings.weight[1],
             out_ln=(ie.layer_norm.weight, ie.layer_norm.bias))
         pano_masks = torch.arange(V, device=dev)[None, :] < view_lens.to(dev)[:, None]      # ops.py:36-44
-        km = pano_masks.to(torch.uint8)
+        km = blocks.mask_u8(pano_masks)
         for lp in pk['pano']:
             x32 = blocks.pano_layer(x32, lp, B, V, km, lowp)
         g, be = pk['pano_norm'].get()
@@ -310,7 +313,7 @@ class GlocalTextPathNavCMT(nn.Module):
             ops.copy_rows(txt, L * HIDDEN, HIDDEN, B, L, c32, c16, C * HIDDEN, HIDDEN)
             ops.copy_rows(_f32c(imagine_embeds), I * HIDDEN, HIDDEN, B, I, c32[L:] if c32 is not None else None,
                           c16[L:] if c16 is not None else None, C * HIDDEN, HIDDEN)
-            ctx_mask = torch.cat([txt_masks, imagine_masks], 1).to(torch.uint8).contiguous()
+            ctx_mask = blocks.mask_u8(torch.cat([txt_masks.bool(), imagine_masks.bool()], 1))
         else:
             C = L
             ctx = ops.cast_bf16(txt.view(B * L, HIDDEN)) if lowp else txt.view(B * L, HIDDEN)
@@ -319,7 +322,7 @@ class GlocalTextPathNavCMT(nn.Module):
         affine = None
         dist = None
         if ge.sprel_linear is not None:                       # GASA bias (:1145-1149), applied inside the attention kernel
-            affine = torch.cat([ge.sprel_linear.weight.detach().view(1), ge.sprel_linear.bias.detach().view(1)]).float()
+            affine = pk['sprel'].get()
             dist = _f32c(gmap_pair_dists)
         streams = [Stream(r_g, B, G, blocks.mask_u8(gmap_masks), 0, dist, affine),
                    Stream(r_l, B, P, blocks.mask_u8(vp_masks), 1)]

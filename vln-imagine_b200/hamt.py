@@ -222,8 +222,8 @@ class NavCMT(nn.Module):
         ops.copy_rows(ob32, O * HIDDEN, HIDDEN, B, O, visn32[T:], visn16[T:] if lowp else None, Nv * HIDDEN, HIDDEN)
         x = Act(x32, x16)
 
-        lang_mask = (torch.cat([txt_masks, imagine_masks], 1) if I else txt_masks).to(torch.uint8).contiguous()
-        visn_mask = torch.cat([hist_masks, ob_masks], 1).to(torch.uint8).contiguous()
+        lang_mask = blocks.mask_u8(torch.cat([txt_masks.bool(), imagine_masks.bool()], 1) if I else txt_masks)
+        visn_mask = blocks.mask_u8(torch.cat([hist_masks.bool(), ob_masks.bool()], 1))
         streams = [Stream(r_l, B, C, lang_mask, 0), Stream(r_v, B, Nv, visn_mask, 1)]
 
         for cp, sp in zip(pk['x_cross'], pk['x_self']):
@@ -231,13 +231,13 @@ class NavCMT(nn.Module):
             xin = x.operand(lowp)
             w, b = cp['qkv'].get(lowp)
             qkv = ops.gemm(xin, w, b)                          # all rows: Q | K | V
-            ctx = torch.empty((R, HIDDEN), dtype=xin.dtype, device=dev)
-            ctx.zero_()
+            ctx = blocks._ctx_buffer(R, xin, streams)
             ql, qv = qkv[r_l:r_l + B * C], qkv[r_v:r_v + B * Nv]
-            ops.attention(ql[:, :HIDDEN], qv[:, HIDDEN:2 * HIDDEN], qv[:, 2 * HIDDEN:], B, C, Nv, key_mask=visn_mask,
-                          out=ctx[r_l:r_l + B * C])
-            ops.attention(qv[:, :HIDDEN], ql[:, HIDDEN:2 * HIDDEN], ql[:, 2 * HIDDEN:], B, Nv, C, key_mask=lang_mask,
-                          out=ctx[r_v:r_v + B * Nv])
+            ops.attention_multi([
+                dict(q=ql[:, :HIDDEN], k=qv[:, HIDDEN:2 * HIDDEN], v=qv[:, 2 * HIDDEN:], out=ctx[r_l:r_l + B * C],
+                     B=B, Lq=C, Lk=Nv, key_mask=visn_mask),
+                dict(q=qv[:, :HIDDEN], k=ql[:, HIDDEN:2 * HIDDEN], v=ql[:, 2 * HIDDEN:], out=ctx[r_v:r_v + B * Nv],
+                     B=B, Lq=Nv, Lk=C, key_mask=lang_mask)])
             w, b = cp['o'].get(lowp)
             ao = ops.gemm(ctx, w, b, residual=x.f32, out_dtype=F32)
             x = blocks.layer_norm(ao, None, cp['ln'], 1e-12, lowp)

@@ -118,6 +118,32 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, B: int, Lq: int
     return out
 
 
+def attention_multi(problems, mask_mode: int = MASK_ADD_NEG10000):
+    """Several attention problems in one launch.  Each problem is a dict with q, k, v (2-D row views), out,
+    B, Lq, Lk and optional key_mask (uint8 [B, Lk]), pair_dist, bias_affine, lse."""
+    n = len(problems)
+    arr = (_lib.AttnProblem * n)()
+    dtype = None
+    for a, pr in zip(arr, problems):
+        q, k, v, o = pr['q'], pr['k'], pr['v'], pr['out']
+        _, _, a.ldq = _rows2d(q, 'q')
+        _, _, a.ldk = _rows2d(k, 'k')
+        _, _, a.ldv = _rows2d(v, 'v')
+        a.q, a.k, a.v, a.o, a.ldo = q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), o.stride(0)
+        km = pr.get('key_mask')
+        if km is not None and (km.dtype != torch.uint8 or not km.is_contiguous()):
+            raise _lib.VlnImagineError('key_mask must be a contiguous uint8 tensor')
+        a.key_mask, a.pair_dist, a.bias_affine, a.lse = _ptr(km), _ptr(pr.get('pair_dist')), _ptr(pr.get('bias_affine')), _ptr(pr.get('lse'))
+        a.B, a.Lq, a.Lk = pr['B'], pr['Lq'], pr['Lk']
+        if dtype is None:
+            dtype = q.dtype
+        elif dtype != q.dtype:
+            raise _lib.VlnImagineError('attention problems of one launch must share a dtype')
+    check(lib.vi_attn_fwd_multi(arr, n, HEADS, _lib.DT_BF16 if dtype == BF16 else _lib.DT_F32, mask_mode, _stream()),
+          'vi_attn_fwd_multi')
+    _launched(1 if dtype == BF16 else n)
+
+
 def add_ln(a: torch.Tensor, b: Optional[torch.Tensor], gamma: torch.Tensor, beta: torch.Tensor, eps: float,
            want16: bool, want32: bool = True, group_row_end: Optional[Sequence[int]] = None):
     """LayerNorm(a [+ b]); returns (y32 or None, y16 or None)."""
