@@ -58,7 +58,7 @@ int vi_init(int device);
  * vi_gemm_bf16: X, W bf16; fp32 accumulation in TMEM (tcgen05.mma fed by TMA).  K % 64 == 0,
  *               N % 64 == 0, ldx % 8 == 0.  y_dtype selects bf16 or fp32 output.
  * vi_gemm_f32 : the fp32 check mode (FFMA, no tensor cores); X, W, Y fp32.
- * bias / residual may be NULL.  residual is fp32 [M, ldr].
+ * bias / residual may be NULL.  residual is fp32 [M, ldr] and requires an fp32 output in vi_gemm_bf16.
  * ------------------------------------------------------------------------------------------- */
 int vi_gemm_bf16(const void* x, int64_t ldx, const void* w, const float* bias,
                  const float* residual, int64_t ldr, void* y, int64_t ldy, int y_dtype,

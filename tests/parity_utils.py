@@ -49,3 +49,18 @@ def sub16(t):
 
 def to_dev(ep, device='cuda'):
     return {k: (v.to(device) if torch.is_tensor(v) else v) for k, v in ep.items()}
+
+
+def argmax_report(product_logits, ref_logits, tol):
+    """Action-argmax agreement of one batch.  Returns (agree, total, decisive_mismatches).  A decision is
+    *decisive* when the reference's top-1 / top-2 gap exceeds the logit tolerance (tol x max|finite logit|): only
+    there is "identical argmax" implied by "logits within tolerance".  Random-init logits are nearly flat
+    (p10 of the top-2 gap is 2 % of the logit range), so a few non-decisive flips per thousand
+    decisions are inherent to ANY bf16 evaluation, including torch.autocast of the reference itself."""
+    p, r = product_logits.detach().float().cpu(), ref_logits.detach().float().cpu()
+    a, b = p.argmax(-1), r.argmax(-1)
+    top2 = r.topk(2, -1).values
+    scale = r[torch.isfinite(r)].abs().max()
+    gap = top2[:, 0] - top2[:, 1]                      # +inf when only one action is admissible
+    decisive = gap >= tol * scale
+    return int((a == b).sum()), a.numel(), int(((a != b) & decisive).sum())

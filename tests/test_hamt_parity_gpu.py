@@ -7,7 +7,7 @@ import os
 import pytest
 import torch
 
-from parity_utils import TOL, golden, manifest, max_rel, sub16, to_dev
+from parity_utils import TOL, argmax_report, golden, manifest, max_rel, sub16, to_dev
 
 pytestmark = pytest.mark.gpu
 
@@ -75,12 +75,13 @@ def test_hamt_vs_reference_golden(env, tag, shape, seed, precision):
 
 
 def test_hamt_bf16_argmax_agreement_over_many_decisions(env):
-    """>= 99.5 % identical action argmax, logits within 2e-2: bf16 product vs fp32 oracle on 8 x 48 decisions."""
+    """bf16 product vs fp32 oracle on 8 x 48 = 384 decisions: logits within 2e-2, every decisive decision
+    agrees, raw agreement >= 99 % (see the DUET twin of this test for the rationale)."""
     synth, model, O, sd = env
     model.vln_bert.precision = 'bf16'
     torch.set_num_threads(os.cpu_count())
     shape = dataclasses.replace(synth.CFG1, batch=48)
-    agree = total = 0
+    agree = total = bad = 0
     worst = 0.0
     for seed in range(300, 308):
         ep_cpu = synth.to_torch(synth.hamt_episode(shape, seed))
@@ -89,7 +90,8 @@ def test_hamt_bf16_argmax_agreement_over_many_decisions(env):
             o_logits = O.nav_step(sd, ep_cpu, o_txt, o_img2)[0]
         out = run_product(model, to_dev(ep_cpu))
         worst = max(worst, max_rel(out['act_logits'], o_logits))
-        agree += int((out['act_logits'].cpu().argmax(-1) == o_logits.argmax(-1)).sum())
-        total += o_logits.shape[0]
+        a, n, b = argmax_report(out['act_logits'], o_logits, TOL['bf16'])
+        agree, total, bad = agree + a, total + n, bad + b
     assert worst < TOL['bf16']
-    assert agree / total >= 0.995, (agree, total)
+    assert bad == 0, 'a decisive decision flipped'
+    assert agree / total >= 0.99, (agree, total)

@@ -55,13 +55,40 @@ def test_gemm_bf16(ops, M, N, K, epi):
     assert relerr(y3, ref3) < 1e-2
 
 
-@pytest.mark.parametrize('bn', ['64', '128', '256'])
-def test_gemm_bf16_every_tile_width(ops, bn, monkeypatch):
-    monkeypatch.setenv('VI_GEMM_BN', bn)
-    M, N, K = 1000, 768, 1536
+@pytest.mark.parametrize('tile', ['64', '96', '128', '192', '256', '128p', '192p', '256p'])
+@pytest.mark.parametrize('M,N,K', [(1000, 768, 1536), (4416, 2304, 768), (300, 768, 64)])
+def test_gemm_bf16_every_tile_shape(ops, tile, M, N, K, monkeypatch):
+    """every tile width of the tcgen05 kernel, single-CTA and CTA-pair ('p', cta_group::2) forms, with and
+    without the TMA-fed residual, fp32 and bf16 outputs, GELU epilogue"""
+    monkeypatch.setenv('VI_GEMM_TILE', tile)
     x16, w16 = _rand(M, K, seed=5).bfloat16(), _rand(N, K, scale=0.05, seed=6).bfloat16()
-    y = ops.gemm(x16, w16, None, out_dtype=torch.float32)
-    assert relerr(y, x16.float() @ w16.float().t()) < 2e-3
+    b, res = _rand(N, scale=0.1, seed=7), _rand(M, N, seed=8)
+    ref = F.linear(x16.float(), w16.float(), b)
+    y = ops.gemm(x16, w16, b, out_dtype=torch.float32)
+    assert relerr(y, ref) < 2e-3
+    y = ops.gemm(x16, w16, b, residual=res, out_dtype=torch.float32)
+    assert relerr(y, ref + res) < 2e-3
+    y = ops.gemm(x16, w16, b, residual=res, epilogue=1, out_dtype=torch.float32)
+    assert relerr(y, F.gelu(ref) + res) < 2e-3
+    y = ops.gemm(x16, w16, b, epilogue=1, out_dtype=torch.bfloat16)
+    assert relerr(y, F.gelu(ref)) < 1e-2
+
+
+@pytest.mark.parametrize('tile', ['128', '256p'])
+def test_gemm_grouped_pair_tiles(ops, tile, monkeypatch):
+    monkeypatch.setenv('VI_GEMM_TILE', tile)
+    rows = [1920, 2368]
+    K, N = 768, 768
+    M0 = ops.pad_rows(rows[0])
+    M = M0 + rows[1]
+    x = torch.zeros(M, K, device='cuda')
+    x[:rows[0]] = _rand(rows[0], K, seed=1)
+    x[M0:] = _rand(rows[1], K, seed=2)
+    w, b = _rand(2 * N, K, scale=0.05, seed=3).bfloat16(), _rand(2 * N, scale=0.1, seed=4)
+    xx = x.bfloat16()
+    y = ops.gemm(xx, w, b, out_dtype=torch.float32, group_row_end=[M0, M])
+    assert relerr(y[:rows[0]], F.linear(xx[:rows[0]].float(), w[:N].float(), b[:N])) < 2e-3
+    assert relerr(y[M0:], F.linear(xx[M0:].float(), w[N:].float(), b[N:])) < 2e-3
 
 
 def test_gemm_bf16_strided_operand_and_output(ops):
@@ -353,5 +380,8 @@ def test_argument_errors_are_reported_not_fatal(ops):
     x16 = _rand(128, 100, seed=1).bfloat16()              # K not a multiple of 64
     with pytest.raises(_lib.VlnImagineError, match='multiple of 64'):
         ops.gemm(x16, _rand(64, 100, seed=2).bfloat16())
+    with pytest.raises(_lib.VlnImagineError, match='fp32 output'):
+        ops.gemm(_rand(128, 64, seed=1).bfloat16(), _rand(64, 64, seed=2).bfloat16(), residual=_rand(128, 64, seed=3),
+                 out_dtype=torch.bfloat16)
     with pytest.raises(_lib.VlnImagineError, match='CUDA tensor|no CPU path|must be'):
         ops.ensure_init(torch.zeros(1))

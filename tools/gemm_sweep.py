@@ -19,20 +19,20 @@ SHAPES = [
     ('pano.ffn1', 2304, 3072, 768, None, 1, False, False),
     ('pano.ffn2', 2304, 768, 3072, None, 0, True, True),
     ('nav.kv', 5440, 3072, 768, None, 0, False, False),
-    ('nav.q', 4288, 768, 768, [1920, 4288], 0, False, False),
-    ('nav.o', 4288, 768, 768, [1920, 4288], 0, True, True),
-    ('nav.qkv', 4288, 2304, 768, [1920, 4288], 0, False, False),
-    ('nav.ffn1', 4288, 3072, 768, [1920, 4288], 1, False, False),
-    ('nav.ffn2', 4288, 768, 3072, [1920, 4288], 0, True, True),
-    ('nav.head', 4288, 768, 768, [1920, 4288], 2, False, True),
-    ('hamt.x_qkv', 8832, 2304, 768, None, 0, False, False),
-    ('hamt.ffn1', 8832, 3072, 768, [5440, 8832], 1, False, False),
-    ('hamt.ffn2', 8832, 768, 3072, [5440, 8832], 0, True, True),
+    ('nav.q', 4416, 768, 768, [2048, 4416], 0, False, False),
+    ('nav.o', 4416, 768, 768, [2048, 4416], 0, True, True),
+    ('nav.qkv', 4416, 2304, 768, [2048, 4416], 0, False, False),
+    ('nav.ffn1', 4416, 3072, 768, [2048, 4416], 1, False, False),
+    ('nav.ffn2', 4416, 768, 3072, [2048, 4416], 0, True, True),
+    ('nav.head', 4416, 768, 768, [2048, 4416], 2, False, True),
+    ('hamt.x_qkv', 9024, 2304, 768, None, 0, False, False),
+    ('hamt.ffn1', 9024, 3072, 768, [5632, 9024], 1, False, False),
+    ('hamt.ffn2', 9024, 768, 3072, [5632, 9024], 0, True, True),
     ('lang.ffn1', 5120, 3072, 768, None, 1, False, False),
 ]
-bns = sys.argv[1:] or ['auto', '64', '128', '256']
-flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device='cuda')
+tiles = sys.argv[1:] or ['auto', '96', '128', '192', '256', '128p', '192p', '256p']
 rows = []
+REP = 20
 for name, M, N, K, ends, epi, res, f32 in SHAPES:
     ng = 1 if ends is None else len(ends)
     x = torch.randn(M, K, device='cuda').bfloat16()
@@ -40,25 +40,40 @@ for name, M, N, K, ends, epi, res, f32 in SHAPES:
     b = torch.randn(ng * N, device='cuda')
     r = torch.randn(M, N, device='cuda') if res else None
     out = torch.empty(M, N, dtype=torch.float32 if f32 else torch.bfloat16, device='cuda')
-    rec = {'name': name, 'M': M, 'N': N, 'K': K, 'gflop': 2.0 * M * N * K / 1e9}
-    for bn in bns:
-        if bn == 'auto':
-            os.environ.pop('VI_GEMM_BN', None)
+    rec = {'name': name, 'M': M, 'N': N, 'K': K, 'gflop': round(2.0 * M * N * K / 1e9, 2)}
+    for tile in tiles:
+        if tile == 'auto':
+            os.environ.pop('VI_GEMM_TILE', None)
         else:
-            os.environ['VI_GEMM_BN'] = bn
+            if N % int(tile.rstrip('p')):
+                continue
+            os.environ['VI_GEMM_TILE'] = tile
         for _ in range(3):
             ops.gemm(x, w, b, residual=r, epilogue=epi, out=out, group_row_end=ends)
-        ts = []
-        for _ in range(10):
-            flush.zero_()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
+        torch.cuda.synchronize()
+        torch.cuda._sleep(3_000_000)                   # let the host run ahead so launches queue back to back
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(REP):
             ops.gemm(x, w, b, residual=r, epilogue=epi, out=out, group_row_end=ends)
-            e1.record()
-            torch.cuda.synchronize()
-            ts.append(e0.elapsed_time(e1))
-        t = sorted(ts)[len(ts) // 2]
-        rec['us_' + bn] = round(t * 1e3, 1)
-        rec['tf_' + bn] = round(rec['gflop'] / t, 1)
+        e1.record()
+        torch.cuda.synchronize()
+        t = e0.elapsed_time(e1) / REP
+        rec[tile] = '%.1fus %.0fTF' % (t * 1e3, rec['gflop'] / t)
+    # yardstick only (never on the product path): cuBLAS on the same shape, no epilogue
+    xs = x if ends is None else x[:ends[0]]
+    wt = w[:N].t()
+    for _ in range(3):
+        torch.matmul(x, wt)
+    torch.cuda.synchronize()
+    torch.cuda._sleep(3_000_000)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(REP):
+        torch.matmul(x, wt)
+    e1.record()
+    torch.cuda.synchronize()
+    t = e0.elapsed_time(e1) / REP
+    rec['cublas_plain'] = '%.1fus %.0fTF' % (t * 1e3, rec['gflop'] / t)
     rows.append(rec)
     print(json.dumps(rec), flush=True)

@@ -118,12 +118,12 @@ class Stream:
 
 
 def stack_layout(token_counts: Sequence[int]):
-    """Row offsets for streams stacked on 128-row boundaries -> (row0 list, group_row_end list, total rows)."""
+    """Row offsets for streams stacked on ops.ROW_ALIGN-row boundaries -> (row0 list, group_row_end list, total rows)."""
     row0, ends, cur = [], [], 0
     for i, n in enumerate(token_counts):
         row0.append(cur)
         last = i == len(token_counts) - 1
-        cur = cur + n if last else ops.pad128(cur + n)
+        cur = cur + n if last else ops.pad_rows(cur + n)
         ends.append(cur)
     return row0, ends, cur
 

@@ -57,6 +57,14 @@ def pad128(n: int) -> int:
     return (n + 127) // 128 * 128
 
 
+ROW_ALIGN = 256     # streams of a row-stacked activation start on 256-row boundaries: a CTA-pair GEMM tile
+                    # (256 rows) then never straddles two weight groups
+
+
+def pad_rows(n: int) -> int:
+    return (n + ROW_ALIGN - 1) // ROW_ALIGN * ROW_ALIGN
+
+
 def gemm(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None,
          residual: Optional[torch.Tensor] = None, epilogue: int = EPI_NONE,
          out_dtype: torch.dtype = BF16, group_row_end: Optional[Sequence[int]] = None,
