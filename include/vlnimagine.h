@@ -64,6 +64,14 @@ int vi_gemm_bf16(const void* x, int64_t ldx, const void* w, const float* bias,
                  const float* residual, int64_t ldr, void* y, int64_t ldy, int y_dtype,
                  int M, int N, int K, int epilogue,
                  int n_groups, const int32_t* group_row_end, vi_stream_t stream);
+/* Same as vi_gemm_bf16 with the output-tile shape chosen by the caller: tile = width (64, 96, 128, 192, 256),
+ * optionally | VI_TILE_PAIR for the two-CTA (cta_group::2, 256-row) form; 0 = the library's own cost model.
+ * Results do not depend on the tile (the K accumulation order is the same). */
+#define VI_TILE_PAIR 0x1000
+int vi_gemm_bf16_tiled(const void* x, int64_t ldx, const void* w, const float* bias,
+                       const float* residual, int64_t ldr, void* y, int64_t ldy, int y_dtype,
+                       int M, int N, int K, int epilogue,
+                       int n_groups, const int32_t* group_row_end, int tile, vi_stream_t stream);
 int vi_gemm_f32(const float* x, int64_t ldx, const float* w, const float* bias,
                 const float* residual, int64_t ldr, float* y, int64_t ldy,
                 int M, int N, int K, int epilogue,

@@ -120,3 +120,37 @@ def test_duet_bf16_argmax_agreement_over_many_decisions(env):
     assert worst < TOL['bf16']
     assert bad == 0, 'a decisive decision flipped'
     assert agree / total >= 0.99, (agree, total)
+
+
+def test_duet_api_graph_replay_equals_eager_launches(env):
+    """The module API replays CUDA graphs for the per-step modes; results must be bit-identical to eager launches,
+    also when the caller passes pinned HOST tensors, different data of the same shape, or new weights."""
+    synth, model, _ = env
+    sd = synth.synth_state_dict(manifest('duet'), seed=0)
+    model.vln_bert.load_state_dict(sd)
+    model.vln_bert.precision = 'bf16'
+    eps = [synth.to_torch(synth.duet_episode(synth.CFG1, s)) for s in (31, 32, 33)]
+    model.use_cuda_graphs = False
+    eager = [run_product(model, to_dev(ep)) for ep in eps]
+    model.use_cuda_graphs = True
+    try:
+        for rep in range(2):                                   # first pass captures, second replays
+            for ep, ref in zip(eps, eager):
+                host = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in ep.items()}
+                out = run_product(model, to_dev(ep) if rep == 0 else {**to_dev(ep), **{
+                    k: host[k] for k in ('view_img_fts', 'loc_fts', 'gmap_img_embeds', 'vp_img_embeds', 'gmap_pair_dists')}})
+                for k in ('pano_embeds', 'gmap_embeds', 'vp_embeds', 'global_logits', 'local_logits', 'fused_logits'):
+                    assert torch.equal(out[k], ref[k]), (rep, k)
+                assert torch.equal(out['pano_masks'], ref['pano_masks'])
+        assert len(model._g_nav.entries) >= 1 and all(e['graph'] is not None for e in model._g_nav.entries.values())
+        # new weights invalidate the captured graphs
+        sd2 = synth.synth_state_dict(manifest('duet'), seed=1)
+        model.vln_bert.load_state_dict(sd2)
+        out2 = run_product(model, to_dev(eps[0]))
+        model.use_cuda_graphs = False
+        ref2 = run_product(model, to_dev(eps[0]))
+        assert torch.equal(out2['fused_logits'], ref2['fused_logits'])
+        assert not torch.equal(out2['fused_logits'], eager[0]['fused_logits'])
+    finally:
+        model.use_cuda_graphs = True
+        model.vln_bert.load_state_dict(sd)

@@ -95,3 +95,18 @@ def test_hamt_bf16_argmax_agreement_over_many_decisions(env):
     assert worst < TOL['bf16']
     assert bad == 0, 'a decisive decision flipped'
     assert agree / total >= 0.99, (agree, total)
+
+
+def test_hamt_api_graph_replay_equals_eager_launches(env):
+    synth, model, _, _ = env
+    model.vln_bert.precision = 'bf16'
+    eps = [to_dev(synth.to_torch(synth.hamt_episode(synth.CFG1, s))) for s in (41, 42)]
+    model.use_cuda_graphs = False
+    eager = [run_product(model, ep) for ep in eps]
+    model.use_cuda_graphs = True
+    for rep in range(2):
+        for ep, ref in zip(eps, eager):
+            out = run_product(model, ep)
+            for k in ('act_logits', 'hist_embed', 'states'):
+                assert torch.equal(out[k], ref[k]), (rep, k)
+    assert all(e['graph'] is not None for e in model._g_vis.entries.values())

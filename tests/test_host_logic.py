@@ -1,0 +1,161 @@
+"""CPU: host-side logic of the product (no kernel launches): the C ABI surface, parameter trees, configuration,
+ragged-input flattening, id interning, row stacking, synthetic generators, algorithmic FLOP counts."""
+import ctypes
+import importlib
+import json
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, ROOT
+from parity_utils import manifest
+
+synth = importlib.import_module('vln_imagine_b200.synth')
+config = importlib.import_module('vln_imagine_b200.config')
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, 'include', 'vlnimagine.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(vi_[a-z0-9_]+)\s*\(', text)))
+
+
+def test_library_builds_loads_and_exports_every_declared_symbol(lib_built):
+    lib = ctypes.CDLL(lib_built)
+    syms = header_symbols()
+    assert len(syms) >= 18
+    for name in syms:
+        assert hasattr(lib, name), '%s is declared in include/vlnimagine.h but not exported' % name
+    lib.vi_version.restype = ctypes.c_int
+    assert lib.vi_version() >= 100
+
+
+def test_ctypes_prototypes_cover_the_header(lib_built):
+    _lib = importlib.import_module('vln_imagine_b200._lib')
+    declared = set(header_symbols()) - {'vi_last_error'}
+    assert declared == set(_lib.PROTOTYPES), declared ^ set(_lib.PROTOTYPES)
+
+
+def test_library_contains_blackwell_tensor_core_and_tma_code(lib_built):
+    """SASS evidence: UTCHMMA (tcgen05.mma), LDTM (tcgen05.ld), UTMALDG / UTMASTG (TMA load / store)"""
+    try:
+        sass = subprocess.run(['cuobjdump', '-sass', lib_built], capture_output=True, text=True, timeout=300).stdout
+    except FileNotFoundError:
+        pytest.skip('cuobjdump not installed')
+    for mnemonic in ('UTCHMMA', 'LDTM', 'UTMALDG', 'UTMASTG'):
+        assert mnemonic in sass, mnemonic
+    assert 'HGMMA' not in sass
+
+
+def test_no_cpu_fallback(lib_built):
+    ops = importlib.import_module('vln_imagine_b200.ops')
+    _lib = importlib.import_module('vln_imagine_b200._lib')
+    with pytest.raises(_lib.VlnImagineError):
+        ops.ensure_init(torch.zeros(4))
+    duet = importlib.import_module('vln_imagine_b200.duet')
+    model = duet.VLNBert(config.default_duet_args())
+    with pytest.raises(_lib.VlnImagineError):
+        model('language', {'txt_ids': torch.zeros(2, 8, dtype=torch.long), 'txt_masks': torch.ones(2, 8, dtype=torch.bool)})
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, 'vln-imagine_b200')
+    for fn in os.listdir(pkg):
+        if fn.endswith('.py'):
+            src = open(os.path.join(pkg, fn)).read()
+            assert not re.search(r'^\s*(from|import)\s+oracle', src, flags=re.M), fn
+
+
+@pytest.mark.parametrize('kind', ['duet', 'hamt'])
+def test_parameter_tree_matches_the_reference_state_dict(kind):
+    if kind == 'duet':
+        m = importlib.import_module('vln_imagine_b200.duet').VLNBert(config.default_duet_args())
+    else:
+        m = importlib.import_module('vln_imagine_b200.hamt').VLNBertCMT(config.default_hamt_args())
+    man = manifest(kind)
+    sd = m.vln_bert.state_dict()
+    assert set(sd) == set(man)
+    assert all(list(sd[k].shape) == man[k] for k in man)
+    assert sum(v.numel() for v in sd.values()) == {'duet': 181538565, 'hamt': 171442433}[kind]
+    m.vln_bert.load_state_dict(synth.synth_state_dict(man, seed=0))            # reference-layout dict loads verbatim
+    names = [n for n, _ in m.named_parameters()]
+    assert any(n.startswith('vln_bert.contrastive_alignment_model') for n in names)     # agent optimiser groups
+    assert any(n.startswith('vln_bert.imagine_embeddings') for n in names)
+
+
+def test_freeze_flags_follow_the_reference():
+    duet = importlib.import_module('vln_imagine_b200.duet')
+    m = duet.VLNBert(config.default_duet_args(fix_lang_embedding=True, fix_pano_embedding=True)).vln_bert
+    assert not any(p.requires_grad for p in m.lang_encoder.parameters())
+    assert not any(p.requires_grad for p in m.img_embeddings.parameters())
+    assert all(p.requires_grad for p in m.global_encoder.parameters())
+
+
+def test_config_mirrors_get_vlnbert_models():
+    c = config.duet_config(config.default_duet_args(fusion='avg', graph_sprels=False))
+    assert c.glocal_fuse is False and c.graph_sprels is False and c.max_action_steps == 100 and c.layer_norm_eps == 1e-12
+    h = config.hamt_config(config.default_hamt_args())
+    assert h.max_action_steps == 50 and h.num_h_pano_layers == 2 and h.num_r_layers == 0
+    with pytest.raises(NotImplementedError):
+        importlib.import_module('vln_imagine_b200.hamt').NavCMT(config.hamt_config(config.default_hamt_args(no_lang_ca=True)))
+
+
+def test_align_rows_flattening():
+    duet = importlib.import_module('vln_imagine_b200.duet')
+    flags = [['True', 'False', 'True'], ['True']]
+    nps = [[[[2, 3], [5, 5]], [[7, 8]], []], [[[1, 1]]]]
+    r = duet.AlignRows(2, 10, 3, flags, nps)
+    assert r.R == 2                                       # (0,0) and (1,0); (0,2) has no noun phrase, (0,1) is not flagged
+    assert r.slot.tolist() == [0, 3]
+    assert r.tok_off.tolist() == [0, 3, 4] and r.tok_rows.tolist() == [2, 3, 5, 11]
+    assert r.n_negs == 3 and r.np_ep.tolist() == [0, 0, 1] and r.np_off.tolist() == [0, 2, 3, 4]
+    with pytest.raises(ValueError):
+        duet.AlignRows(1, 4, 1, [['True']], [[[[2, 9]]]])
+
+
+def test_id_table_padding_and_consistency():
+    duet = importlib.import_module('vln_imagine_b200.duet')
+    t = duet._IdTable()
+    g = t.encode([[None, 'a', 'b'], [None, 'c']], 4, -1)
+    c = t.encode([[None, 'b'], [None, 'c', 'a']], 3, -2)
+    assert g[0, 3] == -1 and g[1, 2] == -1 and c[0, 2] == -2
+    assert g[0, 2] == c[0, 1] and g[1, 1] == c[1, 1] and g[0, 1] == c[1, 2] and g[0, 0] == c[0, 0]
+
+
+def test_stack_layout_and_pair_alignment():
+    blocks = importlib.import_module('vln_imagine_b200.blocks')
+    row0, ends, total = blocks.stack_layout([1920, 2368])
+    assert row0 == [0, 2048] and ends == [2048, 4416] and total == 4416
+    assert all(e % 256 == 0 for e in ends[:-1])            # a 256-row CTA-pair tile never straddles two groups
+
+
+def test_synthetic_generators_are_deterministic_and_well_formed():
+    a, b = synth.duet_episode(synth.CFG1, 5), synth.duet_episode(synth.CFG1, 5)
+    for k in a:
+        if isinstance(a[k], np.ndarray):
+            assert np.array_equal(a[k], b[k]), k
+    assert a['txt_ids'][:, 0].tolist() == [101] * 8 and (a['txt_ids'][~a['txt_masks']] == 0).all()
+    assert (a['gmap_pair_dists'] == a['gmap_pair_dists'].transpose(0, 2, 1)).all()
+    assert (a['gmap_pair_dists'][:, 0] == 0).all() and a['gmap_lens'].max() == 30
+    for i in range(8):
+        segs, nps, flags = a['sub_instr_segs'][i], a['noun_phrase_segs'][i], a['sub_instr_imag_flag'][i]
+        assert len(segs) == len(nps) == len(flags) and 'True' in flags
+        for (s, e), spans in zip(segs, nps):
+            assert 1 <= s <= e < a['txt_lens'][i] and all(s <= x <= y <= e for x, y in spans)
+    h = synth.hamt_episode(synth.CFG1, 5)
+    assert ((h['ob_nav_types'] == 2).sum(1) == 1).all() and h['hist_embeds'].shape == (8, 16, 768)
+    sd = synth.synth_state_dict(manifest('duet'), seed=0, gasa_stress=True)
+    assert float(sd['global_encoder.sprel_linear.weight']) == -0.5
+
+
+def test_algorithmic_flops_match_the_survey():
+    sys.path.insert(0, ROOT)
+    bench = importlib.import_module('bench')
+    assert abs(bench.flops_per_decision('duet', synth.CFG2) / 1e9 - 7.281) < 2e-3
+    assert abs(bench.flops_per_decision('hamt', synth.CFG3) / 1e9 - 11.811) < 2e-3
+    assert abs(bench.flops_per_decision('duet', synth.CFG5) / 1e9 - 14.784) < 2e-3

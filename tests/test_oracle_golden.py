@@ -1,0 +1,77 @@
+"""CPU: the oracle (oracle/*_oracle.py) against the committed golden vectors of the REAL reference
+(tests/golden/*.npz, produced by oracle/gen_golden.py from /root/reference in the build container).
+This is what pins the oracle to the reference rather than to itself."""
+import importlib
+import json
+import os
+
+import pytest
+import torch
+
+from conftest import GOLDEN
+from parity_utils import golden, manifest, max_rel, sub16
+
+synth = importlib.import_module('vln_imagine_b200.synth')
+
+
+def test_generation_report_says_the_oracle_reproduced_the_reference():
+    for m in ('duet', 'hamt'):
+        rep = json.load(open(os.path.join(GOLDEN, '%s_oracle_vs_reference.json' % m)))
+        assert rep and all(max(case.values()) < 2e-4 for case in rep.values())
+
+
+@pytest.mark.parametrize('tag,shape,seed,stress', [('tiny', 'TINY', 7, False), ('tiny_gasa', 'TINY', 8, True),
+                                                   ('cfg1', 'CFG1', 1234, False), ('cfg1_gasa', 'CFG1', 1234, True)])
+def test_duet_oracle_matches_reference_golden(tag, shape, seed, stress):
+    from oracle import duet_oracle as O
+    sd = synth.synth_state_dict(manifest('duet'), seed=0, gasa_stress=stress)
+    ep = synth.to_torch(synth.duet_episode(getattr(synth, shape), seed))
+    gold = golden('duet_' + tag)
+    with torch.no_grad():
+        txt, img, loss, img2 = O.episode_prelude(sd, ep)
+        pano, pano_masks, nav = O.nav_step(sd, ep, txt, img2)
+        nce_loss, nce_img = O.forward_align_infonce(sd, txt, img, ep['sub_instr_imag_flag'], ep['noun_phrase_segs'], 0.007)
+    f = (lambda t: t) if tag.startswith('tiny') else sub16
+    out = dict(txt_embeds=f(txt), imagine_embeds=f(img), aligned_imagine_embeds=f(img2), pano_embeds=f(pano),
+               gmap_embeds=f(nav['gmap_embeds']), vp_embeds=f(nav['vp_embeds']), global_logits=nav['global_logits'],
+               local_logits=nav['local_logits'], fused_logits=nav['fused_logits'], nce_imagine_embeds=f(nce_img))
+    for k, v in out.items():
+        assert max_rel(v, gold[k]) < 1e-5, k
+    assert torch.equal(pano_masks, gold['pano_masks'])
+    assert abs(float(loss) - float(gold['aux_loss'])) < 1e-6
+    assert abs(float(nce_loss) - float(gold['nce_loss'])) < 1e-4 * abs(float(gold['nce_loss']))
+    assert torch.equal(nav['fused_logits'].argmax(-1), gold['fused_logits'].argmax(-1))
+
+
+@pytest.mark.parametrize('tag,shape,seed', [('tiny', 'TINY', 7), ('cfg1', 'CFG1', 1234)])
+def test_hamt_oracle_matches_reference_golden(tag, shape, seed):
+    from oracle import hamt_oracle as O
+    sd = synth.synth_state_dict(manifest('hamt'), seed=0)
+    ep = synth.to_torch(synth.hamt_episode(getattr(synth, shape), seed))
+    gold = golden('hamt_' + tag)
+    with torch.no_grad():
+        txt, img, loss, img2 = O.episode_prelude(sd, ep)
+        logits, txt_o, hist_o, ob_o, hist = O.nav_step(sd, ep, txt, img2)
+        cls_hist = O.forward_history(sd, None, None, None, None, None)
+    f = (lambda t: t) if tag == 'tiny' else sub16
+    out = dict(txt_embeds=f(txt), aligned_imagine_embeds=f(img2), act_logits=logits, txt_out=f(txt_o), hist_out=f(hist_o),
+               ob_out=f(ob_o), hist_embed=hist, cls_hist=cls_hist)
+    for k, v in out.items():
+        assert max_rel(v, gold[k]) < 1e-5, k
+    assert abs(float(loss) - float(gold['aux_loss'])) < 1e-6
+
+
+def test_oracle_edge_cases_empty_alignment_and_single_admissible_action():
+    """no flagged imagination -> loss 0 and embeds untouched; one admissible action -> every other logit is -inf"""
+    from oracle import duet_oracle as O
+    sd = synth.synth_state_dict(manifest('duet'), seed=0)
+    ep = synth.to_torch(synth.duet_episode(synth.TINY, 11))
+    txt = torch.randn(3, 24, 768)
+    img = torch.randn(3, 3, 768)
+    flags = [['False'] * len(f) for f in ep['sub_instr_imag_flag']]
+    loss, out = O.forward_align_cosine(sd, txt, img, flags, ep['noun_phrase_segs'])
+    assert float(loss) == 0.0 and torch.equal(out, img)
+    g = torch.full((1, 4), float('-inf')); g[0, 0] = 0.3
+    l = torch.full((1, 3), float('-inf')); l[0, 0] = 0.2
+    fused = O.fuse_logits(g, l, [[None, 'a', 'b', 'c']], torch.tensor([[False, True, False, False]]), [[None, 'b', 'c']])
+    assert torch.isfinite(fused).sum() == 1 and abs(float(fused[0, 0]) - 0.5) < 1e-6

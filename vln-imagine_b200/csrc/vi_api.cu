@@ -2,6 +2,7 @@
 #include "vi_common.cuh"
 
 #include <stdarg.h>
+#include <stdlib.h>
 
 static thread_local char g_err[512] = "";
 static int g_num_sms = 0;
@@ -23,6 +24,15 @@ int vi_num_sms() {
       g_num_sms = 148;
   }
   return g_num_sms;
+}
+
+bool vi_pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("VI_PDL");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on != 0;
 }
 
 int vi_attn_init();

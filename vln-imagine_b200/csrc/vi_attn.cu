@@ -60,6 +60,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.com
 // K, V (whole head) and the Q tile are staged with cp.async; fragments come from ldmatrix (V through .trans, so no
 // explicit transpose); scores stay in registers with an fp32 online softmax over 64-key chunks.
 __global__ void __launch_bounds__(128) attn_fwd_bf16_kernel(const AttnParams p) {
+  pdl_enter();
   extern __shared__ __align__(16) uint8_t smem[];
   int z = blockIdx.z, pi = 0;
   while (pi < p.n_problems - 1 && z >= p.pr[pi].B) { z -= p.pr[pi].B; ++pi; }
@@ -224,6 +225,7 @@ __global__ void __launch_bounds__(128) attn_fwd_bf16_kernel(const AttnParams p) 
 
 // fp32 check mode: grid (H, B), 128 threads; warp w handles query rows w, w+4, ...
 __global__ void __launch_bounds__(128) attn_fwd_f32_kernel(const AttnProblem p, const int H, const int mask_mode) {
+  pdl_enter();
   extern __shared__ __align__(16) uint8_t smem[];
   float* Ks = reinterpret_cast<float*>(smem);            // [Lk][65]
   float* Vs = Ks + (size_t)p.Lk * 65;                    // [Lk][64]
@@ -335,14 +337,14 @@ extern "C" int vi_attn_fwd_multi(const vi_attn_problem* problems, int n_problems
   if (dtype == VI_DT_BF16) {
     const size_t smem = (size_t)max_lkp * ROW * 2 * 2 + 64 * ROW * 2 + (size_t)max_lkp * 4;
     dim3 grid((max_lq + 63) / 64, H, total_b);
-    attn_fwd_bf16_kernel<<<grid, 128, smem, st>>>(p);
+    VI_CUDA(vi_launch(attn_fwd_bf16_kernel, dim3(grid), dim3(128), (size_t)(smem), st, p));
     VI_LAUNCH_CHECK();
   } else {
     for (int i = 0; i < n_problems; ++i) {
       const AttnProblem& a = p.pr[i];
       const size_t smem = ((size_t)a.Lk * 65 + (size_t)a.Lk * 64 + a.Lk + 4 * (size_t)a.Lk + 4 * 64) * 4;
       dim3 grid(H, a.B);
-      attn_fwd_f32_kernel<<<grid, 128, smem, st>>>(a, H, mask_mode);
+      VI_CUDA(vi_launch(attn_fwd_f32_kernel, dim3(grid), dim3(128), (size_t)(smem), st, a, H, mask_mode));
       VI_LAUNCH_CHECK();
     }
   }

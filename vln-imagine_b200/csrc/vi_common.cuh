@@ -42,6 +42,27 @@ void vi_set_error(const char* fmt, ...);
   } while (0)
 
 int vi_num_sms();
+bool vi_pdl_enabled();      // programmatic dependent launch on every kernel of the library (VI_PDL=0 disables)
+
+// Launch with the programmatic-stream-serialization attribute: the kernel may start (and run its prologue) while
+// its predecessor in the stream is still draining; it calls pdl_wait() before touching global memory.
+#ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+inline cudaError_t vi_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = vi_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#endif
 
 typedef __nv_bfloat16 bf16;
 
@@ -49,6 +70,12 @@ typedef __nv_bfloat16 bf16;
 // device helpers
 // ----------------------------------------------------------------------------------------------
 #ifdef __CUDACC__
+
+// Programmatic dependent launch: let the next kernel of the stream begin its prologue now; wait for the previous
+// kernel's memory before reading (or overwriting) anything it may touch.  Both are no-ops without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() { pdl_launch_dependents(); pdl_wait(); }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -20,6 +20,7 @@ struct SimtParams {
 };
 
 __global__ void __launch_bounds__(256) gemm_f32_simt_kernel(const SimtParams p) {
+  pdl_enter();
   __shared__ float xs[TK][TM + 4];
   __shared__ float ws[TK][TN + 4];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
@@ -102,7 +103,7 @@ extern "C" int vi_gemm_f32(const float* x, int64_t ldx, const float* w, const fl
     p.group_row_end[g] = e;
   }
   dim3 grid((N + TN - 1) / TN, (M + TM - 1) / TM);
-  gemm_f32_simt_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  VI_CUDA(vi_launch(gemm_f32_simt_kernel, dim3(grid), dim3(256), (size_t)(0), reinterpret_cast<cudaStream_t>(stream), p));
   VI_LAUNCH_CHECK();
   return VI_OK;
 }

@@ -194,6 +194,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   auto tempty_bar = [&](int a) { return bar_base + 8u * (uint32_t)(2 * STAGES + 2 + a); };
   auto res_bar = [&](int w, int b) { return bar_base + 8u * (uint32_t)(2 * STAGES + 4 + 2 * w + b); };
 
+  pdl_launch_dependents();                            // the next kernel may begin its own prologue
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
@@ -226,6 +227,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if constexpr (PAIR) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                                         // everything above overlapped the previous kernel's tail
 
   const int total_tiles = p.num_m_tiles * p.num_n_tiles;
   const int num_kb = p.K / BK;
@@ -501,8 +503,13 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tm
   cfg.blockDim = dim3(NUM_THREADS);
   cfg.dynamicSmemBytes = smem_bytes<BN, STAGES, PAIR, F32OUT>();
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   int nattr = 0;
+  if (vi_pdl_enabled()) {
+    attr[nattr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[nattr].val.programmaticStreamSerializationAllowed = 1;
+    ++nattr;
+  }
   if (PAIR) {
     attr[nattr].id = cudaLaunchAttributeClusterDimension;
     attr[nattr].val.clusterDim.x = 2;
@@ -558,6 +565,13 @@ Choice pick_tile(int M, int N, int K, int nsm, bool pair_ok) {
 extern "C" int vi_gemm_bf16(const void* x, int64_t ldx, const void* w, const float* bias, const float* residual,
                             int64_t ldr, void* y, int64_t ldy, int y_dtype, int M, int N, int K, int epilogue,
                             int n_groups, const int32_t* group_row_end, vi_stream_t stream) {
+  return vi_gemm_bf16_tiled(x, ldx, w, bias, residual, ldr, y, ldy, y_dtype, M, N, K, epilogue, n_groups, group_row_end, 0,
+                            stream);
+}
+
+extern "C" int vi_gemm_bf16_tiled(const void* x, int64_t ldx, const void* w, const float* bias, const float* residual,
+                                  int64_t ldr, void* y, int64_t ldy, int y_dtype, int M, int N, int K, int epilogue,
+                                  int n_groups, const int32_t* group_row_end, int tile, vi_stream_t stream) {
   VI_CHECK_ARG(x && w && y, "vi_gemm_bf16: null operand");
   VI_CHECK_ARG(M > 0 && N > 0 && K > 0, "vi_gemm_bf16: empty problem M=%d N=%d K=%d", M, N, K);
   VI_CHECK_ARG(K % BK == 0, "vi_gemm_bf16: K=%d must be a multiple of %d", K, BK);
@@ -594,7 +608,15 @@ extern "C" int vi_gemm_bf16(const void* x, int64_t ldx, const void* w, const flo
   VI_CHECK_ARG(n_groups == 1 || group_row_end[n_groups - 1] == M, "vi_gemm_bf16: last group must end at M");
 
   const int nsm = vi_num_sms();
-  const Choice c = pick_tile(M, N, K, nsm, pair_ok);
+  Choice c = pick_tile(M, N, K, nsm, pair_ok);
+  if (tile != 0) {                       // caller-selected tile (the Python host autotunes per shape)
+    const int bn = tile & 0xFFF;
+    const bool pr = (tile & VI_TILE_PAIR) != 0;
+    VI_CHECK_ARG((bn == 64 || bn == 96 || bn == 128 || bn == 192 || bn == 256) && N % bn == 0,
+                 "vi_gemm_bf16_tiled: tile width %d does not divide N=%d", bn, N);
+    VI_CHECK_ARG(!pr || (pair_ok && bn >= 128), "vi_gemm_bf16_tiled: CTA-pair tiles need width >= 128 and 256-row group ends");
+    c = Choice{bn, pr};
+  }
   const int tm = c.pair ? 2 * BM : BM;
   p.num_m_tiles = (M + tm - 1) / tm;
   p.num_n_tiles = N / c.bn;

@@ -100,6 +100,7 @@ __device__ __forceinline__ int group_of_row(const RowGroups& g, long long row) {
 __global__ void __launch_bounds__(128) add_ln_kernel(const float* __restrict__ a, const float* __restrict__ b,
                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
                                                      float eps, float* y32, bf16* y16, long long rows, const RowGroups grp) {
+  pdl_enter();
   ROW_INDEX();
   if (row >= rows) return;
   const int gi = group_of_row(grp, row);
@@ -117,6 +118,7 @@ __global__ void __launch_bounds__(128) add_ln_kernel(const float* __restrict__ a
 // loads once, so a row costs feat_dim conflict-free float4 reads per 4 outputs instead of strided global loads.
 constexpr int EMBED_WARPS = 8;
 __global__ void __launch_bounds__(EMBED_WARPS * 32) embed_compose_kernel(const vi_embed_args p) {
+  pdl_enter();
   extern __shared__ __align__(16) float wT[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (p.feat) {
@@ -169,6 +171,7 @@ __global__ void __launch_bounds__(128) ln_dot_kernel(const float* __restrict__ h
                                                      const float* __restrict__ beta, float eps,
                                                      const float* __restrict__ w, const float* __restrict__ bias,
                                                      float* out, long long rows, const RowGroups grp) {
+  pdl_enter();
   ROW_INDEX();
   if (row >= rows) return;
   const int gi = group_of_row(grp, row);
@@ -187,6 +190,7 @@ __global__ void __launch_bounds__(128) ln_dot_kernel(const float* __restrict__ h
 __global__ void __launch_bounds__(128) mul_bcast_kernel(const float* __restrict__ x, long long x_bs,
                                                         const float* __restrict__ s, long long lds, float* y32,
                                                         bf16* y16, long long rows, int rows_per_batch) {
+  pdl_enter();
   ROW_INDEX();
   if (row >= rows) return;
   const long long b = row / rows_per_batch;
@@ -211,6 +215,7 @@ __global__ void __launch_bounds__(32) duet_fuse_logits_kernel(const float* __res
                                                               const int32_t* __restrict__ gmap_ids,
                                                               const int32_t* __restrict__ cand_ids, float* global_logits,
                                                               float* local_logits, float* fused_logits, int G, int P) {
+  pdl_enter();
   __shared__ float ll[FUSE_MAX];
   __shared__ int gid[FUSE_MAX];
   __shared__ int cid[FUSE_MAX];
@@ -269,6 +274,7 @@ __global__ void __launch_bounds__(32) duet_fuse_logits_kernel(const float* __res
 
 __global__ void mask_logits_navtype_kernel(const float* __restrict__ raw, const int64_t* __restrict__ nav_types,
                                            float* out, long long n) {
+  pdl_enter();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = nav_types[i] == 0 ? -INFINITY : raw[i];
 }
@@ -276,6 +282,7 @@ __global__ void mask_logits_navtype_kernel(const float* __restrict__ raw, const 
 __global__ void __launch_bounds__(128) gather_mean_kernel(const float* __restrict__ src, const int32_t* __restrict__ offsets,
                                                           const int32_t* __restrict__ row_idx, float* out32, bf16* out16,
                                                           long long rows) {
+  pdl_enter();
   ROW_INDEX();
   if (row >= rows) return;
   Row acc;
@@ -291,6 +298,7 @@ __global__ void __launch_bounds__(128) gather_mean_kernel(const float* __restric
 
 __global__ void __launch_bounds__(128) scatter_rows_kernel(const float* __restrict__ src, const int32_t* __restrict__ dst_rows,
                                                            float* dst, long long rows) {
+  pdl_enter();
   ROW_INDEX();
   if (row >= rows) return;
   Row r;
@@ -301,6 +309,7 @@ __global__ void __launch_bounds__(128) scatter_rows_kernel(const float* __restri
 // 1 - cos(p, t) with torch's cosine_similarity clamping: x.y / (max(|x|,eps) * max(|y|,eps))
 __global__ void __launch_bounds__(128) cosine_loss_kernel(const float* __restrict__ proj, const float* __restrict__ tgt,
                                                           float* loss_rows, long long rows) {
+  pdl_enter();
   ROW_INDEX();
   if (row >= rows) return;
   Row a, b;
@@ -312,6 +321,7 @@ __global__ void __launch_bounds__(128) cosine_loss_kernel(const float* __restric
 
 // single-block deterministic mean of n floats (n <= a few thousand)
 __global__ void __launch_bounds__(256) mean_kernel(const float* __restrict__ x, float* out, int n) {
+  pdl_enter();
   __shared__ float sh[8];
   float s = 0.f;
   for (int i = threadIdx.x; i < n; i += 256) s += x[i];
@@ -329,6 +339,7 @@ __global__ void __launch_bounds__(256) mean_kernel(const float* __restrict__ x, 
 __global__ void __launch_bounds__(128) infonce_sims_kernel(const float* __restrict__ proj, const float* __restrict__ tgt,
                                                            const float* __restrict__ negs, float inv_t, float* sims,
                                                            int R, int n_negs) {
+  pdl_enter();
   const int lane = threadIdx.x & 31;
   const long long item = (long long)blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5);
   const int cols = n_negs + 1;
@@ -344,6 +355,7 @@ __global__ void __launch_bounds__(128) infonce_sims_kernel(const float* __restri
 __global__ void __launch_bounds__(128) infonce_rows_kernel(const float* __restrict__ sims, const int32_t* __restrict__ row_ep,
                                                            const int32_t* __restrict__ neg_ep, float* loss_rows, int R,
                                                            int n_negs) {
+  pdl_enter();
   ROW_INDEX();
   if (row >= R) return;
   const int cols = n_negs + 1;
@@ -361,6 +373,7 @@ __global__ void __launch_bounds__(128) infonce_rows_kernel(const float* __restri
 }
 
 __global__ void cast_bf16_kernel(const float* __restrict__ src, bf16* dst, long long n4, long long n) {
+  pdl_enter();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n4) {
     const float4 t = __ldg(reinterpret_cast<const float4*>(src) + i);
@@ -375,6 +388,7 @@ __global__ void cast_bf16_kernel(const float* __restrict__ src, bf16* dst, long 
 __global__ void __launch_bounds__(128) copy_rows_kernel(const float* __restrict__ src, long long src_bs, long long src_rs,
                                                         float* dst32, bf16* dst16, long long dst_bs, long long dst_rs,
                                                         long long rows, int rpb) {
+  pdl_enter();
   ROW_INDEX();
   if (row >= rows) return;
   const long long b = row / rpb, r = row % rpb;
@@ -420,7 +434,7 @@ extern "C" int vi_add_ln(const float* a, const float* b, const float* gamma, con
   VI_CHECK_ARG(aligned16(a) && aligned16(b) && aligned16(gamma) && aligned16(beta) && aligned16(y32) && ((uintptr_t)y16 & 7) == 0,
                "vi_add_ln: operands must be 16-byte aligned");
   if (rows <= 0) return VI_OK;
-  add_ln_kernel<<<row_grid(rows), 128, 0, ST(stream)>>>(a, b, gamma, beta, eps, y32, reinterpret_cast<bf16*>(y16), rows, grp);
+  VI_CUDA(vi_launch(add_ln_kernel, dim3(row_grid(rows)), dim3(128), (size_t)(0), ST(stream), a, b, gamma, beta, eps, y32, reinterpret_cast<bf16*>(y16), rows, grp));
   VI_LAUNCH_CHECK();
   return VI_OK;
 }
@@ -444,7 +458,7 @@ extern "C" int vi_embed_compose(const vi_embed_args* args, vi_stream_t stream) {
   const long long cap = 2LL * vi_num_sms();
   if (p.feat && blocks > cap) blocks = cap;          // amortise the weight staging over several rows per warp
   const size_t smem = p.feat ? (size_t)p.feat_dim * D * sizeof(float) : 0;
-  embed_compose_kernel<<<(unsigned)blocks, EMBED_WARPS * 32, smem, ST(stream)>>>(p);
+  VI_CUDA(vi_launch(embed_compose_kernel, dim3((unsigned)blocks), dim3(EMBED_WARPS * 32), (size_t)(smem), ST(stream), p));
   VI_LAUNCH_CHECK();
   return VI_OK;
 }
@@ -456,7 +470,7 @@ extern "C" int vi_ln_dot(const float* h, const float* gamma, const float* beta, 
   VI_CHECK_ARG(h && gamma && beta && w && out, "vi_ln_dot: null operand");
   VI_CHECK_ARG(aligned16(h) && aligned16(gamma) && aligned16(beta) && aligned16(w), "vi_ln_dot: operands must be 16-byte aligned");
   if (rows <= 0) return VI_OK;
-  ln_dot_kernel<<<row_grid(rows), 128, 0, ST(stream)>>>(h, gamma, beta, eps, w, b, out, rows, grp);
+  VI_CUDA(vi_launch(ln_dot_kernel, dim3(row_grid(rows)), dim3(128), (size_t)(0), ST(stream), h, gamma, beta, eps, w, b, out, rows, grp));
   VI_LAUNCH_CHECK();
   return VI_OK;
 }
@@ -467,8 +481,8 @@ extern "C" int vi_mul_bcast(const float* x, int64_t x_batch_stride, const float*
   VI_CHECK_ARG(aligned16(x) && aligned16(s) && lds % 4 == 0 && x_batch_stride % 4 == 0 && aligned16(y32) &&
                    ((uintptr_t)y16 & 7) == 0, "vi_mul_bcast: misaligned operands");
   if (rows <= 0) return VI_OK;
-  mul_bcast_kernel<<<row_grid(rows), 128, 0, ST(stream)>>>(x, x_batch_stride, s, lds, y32, reinterpret_cast<bf16*>(y16), rows,
-                                                          rows_per_batch);
+  VI_CUDA(vi_launch(mul_bcast_kernel, dim3(row_grid(rows)), dim3(128), (size_t)(0), ST(stream), x, x_batch_stride, s, lds, y32, reinterpret_cast<bf16*>(y16), rows,
+                                                          rows_per_batch));
   VI_LAUNCH_CHECK();
   return VI_OK;
 }
@@ -481,8 +495,8 @@ extern "C" int vi_duet_fuse_logits(const float* g_raw, const float* l_raw, const
                    global_logits && local_logits && fused_logits, "vi_duet_fuse_logits: null operand");
   VI_CHECK_ARG(B > 0 && G > 0 && P > 0, "vi_duet_fuse_logits: empty problem");
   VI_CHECK_ARG(G <= FUSE_MAX && P <= FUSE_MAX, "vi_duet_fuse_logits: G=%d / P=%d exceed %d", G, P, FUSE_MAX);
-  duet_fuse_logits_kernel<<<B, 32, 0, ST(stream)>>>(g_raw, l_raw, fuse_raw, gmap_masks, gmap_visited, vp_nav_masks, gmap_ids,
-                                                   cand_ids, global_logits, local_logits, fused_logits, G, P);
+  VI_CUDA(vi_launch(duet_fuse_logits_kernel, dim3(B), dim3(32), (size_t)(0), ST(stream), g_raw, l_raw, fuse_raw, gmap_masks, gmap_visited, vp_nav_masks, gmap_ids,
+                                                   cand_ids, global_logits, local_logits, fused_logits, G, P));
   VI_LAUNCH_CHECK();
   return VI_OK;
 }
@@ -490,7 +504,7 @@ extern "C" int vi_duet_fuse_logits(const float* g_raw, const float* l_raw, const
 extern "C" int vi_mask_logits_navtype(const float* raw, const int64_t* nav_types, float* out, int64_t n, vi_stream_t stream) {
   VI_CHECK_ARG(raw && nav_types && out, "vi_mask_logits_navtype: null operand");
   if (n <= 0) return VI_OK;
-  mask_logits_navtype_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ST(stream)>>>(raw, nav_types, out, n);
+  VI_CUDA(vi_launch(mask_logits_navtype_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), (size_t)(0), ST(stream), raw, nav_types, out, n));
   VI_LAUNCH_CHECK();
   return VI_OK;
 }
@@ -500,7 +514,7 @@ extern "C" int vi_gather_mean(const float* src, const int32_t* offsets, const in
   VI_CHECK_ARG(src && offsets && row_idx && (out32 || out16), "vi_gather_mean: null operand");
   VI_CHECK_ARG(aligned16(src) && aligned16(out32) && ((uintptr_t)out16 & 7) == 0, "vi_gather_mean: misaligned operands");
   if (R <= 0) return VI_OK;
-  gather_mean_kernel<<<row_grid(R), 128, 0, ST(stream)>>>(src, offsets, row_idx, out32, reinterpret_cast<bf16*>(out16), R);
+  VI_CUDA(vi_launch(gather_mean_kernel, dim3(row_grid(R)), dim3(128), (size_t)(0), ST(stream), src, offsets, row_idx, out32, reinterpret_cast<bf16*>(out16), R));
   VI_LAUNCH_CHECK();
   return VI_OK;
 }
@@ -509,7 +523,7 @@ extern "C" int vi_scatter_rows(const float* src, const int32_t* dst_rows, float*
   VI_CHECK_ARG(src && dst_rows && dst, "vi_scatter_rows: null operand");
   VI_CHECK_ARG(aligned16(src) && aligned16(dst), "vi_scatter_rows: misaligned operands");
   if (R <= 0) return VI_OK;
-  scatter_rows_kernel<<<row_grid(R), 128, 0, ST(stream)>>>(src, dst_rows, dst, R);
+  VI_CUDA(vi_launch(scatter_rows_kernel, dim3(row_grid(R)), dim3(128), (size_t)(0), ST(stream), src, dst_rows, dst, R));
   VI_LAUNCH_CHECK();
   return VI_OK;
 }
@@ -518,8 +532,8 @@ extern "C" int vi_cosine_loss(const float* proj, const float* tgt, float* loss_r
                               vi_stream_t stream) {
   VI_CHECK_ARG(loss_mean && (R == 0 || (proj && tgt && loss_rows)), "vi_cosine_loss: null operand");
   VI_CHECK_ARG(aligned16(proj) && aligned16(tgt), "vi_cosine_loss: misaligned operands");
-  if (R > 0) cosine_loss_kernel<<<row_grid(R), 128, 0, ST(stream)>>>(proj, tgt, loss_rows, R);
-  mean_kernel<<<1, 256, 0, ST(stream)>>>(loss_rows, loss_mean, R);
+  if (R > 0) VI_CUDA(vi_launch(cosine_loss_kernel, dim3(row_grid(R)), dim3(128), (size_t)(0), ST(stream), proj, tgt, loss_rows, R));
+  VI_CUDA(vi_launch(mean_kernel, dim3(1), dim3(256), (size_t)(0), ST(stream), loss_rows, loss_mean, R));
   VI_LAUNCH_CHECK();
   return VI_OK;
 }
@@ -535,10 +549,10 @@ extern "C" int vi_infonce_loss(const float* proj, const float* tgt, const float*
   float* rows_out = loss_rows + (long long)R * (n_negs + 1);
   if (R > 0) {
     const long long items = (long long)R * (n_negs + 1);
-    infonce_sims_kernel<<<row_grid(items), 128, 0, ST(stream)>>>(proj, tgt, negs, 1.0f / temperature, sims, R, n_negs);
-    infonce_rows_kernel<<<row_grid(R), 128, 0, ST(stream)>>>(sims, row_episode, neg_episode, rows_out, R, n_negs);
+    VI_CUDA(vi_launch(infonce_sims_kernel, dim3(row_grid(items)), dim3(128), (size_t)(0), ST(stream), proj, tgt, negs, 1.0f / temperature, sims, R, n_negs));
+    VI_CUDA(vi_launch(infonce_rows_kernel, dim3(row_grid(R)), dim3(128), (size_t)(0), ST(stream), sims, row_episode, neg_episode, rows_out, R, n_negs));
   }
-  mean_kernel<<<1, 256, 0, ST(stream)>>>(rows_out, loss_mean, R);
+  VI_CUDA(vi_launch(mean_kernel, dim3(1), dim3(256), (size_t)(0), ST(stream), rows_out, loss_mean, R));
   VI_LAUNCH_CHECK();
   return VI_OK;
 }
@@ -553,9 +567,9 @@ extern "C" int vi_copy_rows(const float* src, int64_t src_batch_stride, int64_t 
                "vi_copy_rows: pointers must be 16-byte aligned and strides multiples of 4 elements");
   const long long rows = (long long)n_batches * rows_per_batch;
   if (rows <= 0) return VI_OK;
-  copy_rows_kernel<<<row_grid(rows), 128, 0, ST(stream)>>>(src, src_batch_stride, src_row_stride, dst32,
+  VI_CUDA(vi_launch(copy_rows_kernel, dim3(row_grid(rows)), dim3(128), (size_t)(0), ST(stream), src, src_batch_stride, src_row_stride, dst32,
                                                           reinterpret_cast<bf16*>(dst16), dst_batch_stride, dst_row_stride,
-                                                          rows, rows_per_batch);
+                                                          rows, rows_per_batch));
   VI_LAUNCH_CHECK();
   return VI_OK;
 }
@@ -566,7 +580,7 @@ extern "C" int vi_cast_bf16(const float* src, void* dst, int64_t n, vi_stream_t 
   if (n <= 0) return VI_OK;
   const long long n4 = n / 4;
   const long long threads = n4 > 0 ? n4 : 1;
-  cast_bf16_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, ST(stream)>>>(src, reinterpret_cast<bf16*>(dst), n4, n);
+  VI_CUDA(vi_launch(cast_bf16_kernel, dim3((unsigned)((threads + 255) / 256)), dim3(256), (size_t)(0), ST(stream), src, reinterpret_cast<bf16*>(dst), n4, n));
   VI_LAUNCH_CHECK();
   return VI_OK;
 }

@@ -19,7 +19,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from . import blocks, ops, params
+from . import blocks, graphs, ops, params
 from .blocks import Act, Stream
 from .config import duet_config
 from .ops import BF16, F32, HIDDEN
@@ -355,15 +355,17 @@ class GlocalTextPathNavCMT(nn.Module):
                 'fused_logits': fl, 'obj_logits': None}
 
     def intern_vpids(self, gmap_vpids, vp_cand_vpids, G, P, dev):
-        """Viewpoint-id strings -> int32 device tensors (gmap padding -1, candidate padding -2).  Callers that
+        """Viewpoint-id strings -> int32 tensors on ``dev`` (gmap padding -1, candidate padding -2).  Callers that
         already hold interned ids (a CUDA-graph replay loop, bench.py) may pass the two tensors instead of the
         lists; they are used as they are."""
         if torch.is_tensor(gmap_vpids) and torch.is_tensor(vp_cand_vpids):
             return gmap_vpids, vp_cand_vpids
-        gmap_ids = torch.from_numpy(self._ids.encode(gmap_vpids, G, -1)).to(dev, non_blocking=True)
-        cand_ids = torch.from_numpy(self._ids.encode(vp_cand_vpids, P, -2)).to(dev, non_blocking=True)
+        gmap_ids = torch.from_numpy(self._ids.encode(gmap_vpids, G, -1))
+        cand_ids = torch.from_numpy(self._ids.encode(vp_cand_vpids, P, -2))
         if len(self._ids.ids) > (1 << 20):
             self._ids = _IdTable()
+        if dev is not None and torch.device(dev).type == 'cuda':
+            gmap_ids, cand_ids = gmap_ids.to(dev, non_blocking=True), cand_ids.to(dev, non_blocking=True)
         return gmap_ids, cand_ids
 
     def forward_align(self, batch):
@@ -401,7 +403,15 @@ class GlocalTextPathNavCMT(nn.Module):
 
 
 class VLNBert(nn.Module):
-    """models/model.py:12-48: mode dispatch + environment (feature) dropout on the panorama features."""
+    """models/model.py:12-48: mode dispatch + environment (feature) dropout on the panorama features.
+
+    Inference calls (eval mode, autograd off) of the two per-step modes are replayed from CUDA graphs
+    (graphs.GraphedCall); set ``use_cuda_graphs = False`` for plain eager launches.  Inputs may live on the host
+    (pinned) or on the device."""
+
+    NAV_TENSORS = ('txt_embeds', 'txt_masks', 'gmap_img_embeds', 'gmap_step_ids', 'gmap_pos_fts', 'gmap_masks',
+                   'gmap_pair_dists', 'gmap_visited_masks', 'vp_img_embeds', 'vp_pos_fts', 'vp_masks', 'vp_nav_masks',
+                   'imagine_embeds', 'imagine_masks')
 
     def __init__(self, args):
         super().__init__()
@@ -415,13 +425,55 @@ class VLNBert(nn.Module):
                 sd[k[5:] if k.startswith('bert.') else k] = v
             self.vln_bert.load_state_dict(sd, strict=False)
         self.drop_env = nn.Dropout(p=getattr(args, 'feat_dropout', 0.0))
+        self.use_cuda_graphs = os.environ.get('VLN_IMAGINE_CUDA_GRAPHS', '1') != '0'
+        self._wt_cache = {}
+        self._g_pano = graphs.GraphedCall(self._pano_fn)
+        self._g_nav = graphs.GraphedCall(self._nav_fn)
+
+    def _apply(self, fn, *a, **k):
+        self._wt_cache = {}
+        self._g_pano.clear()
+        self._g_nav.clear()
+        return super()._apply(fn, *a, **k)
+
+    # pure launch sequences over dicts of device tensors (what the graphs capture)
+    def _pano_fn(self, t):
+        e, m = self.vln_bert.forward_panorama_per_step(t['view_img_fts'], None, t['loc_fts'], t['nav_types'], t['view_lens'], None)
+        return {'pano_embeds': e, 'pano_masks': m}
+
+    def _nav_fn(self, t):
+        return self.vln_bert.forward_navigation_per_step(
+            t['txt_embeds'], t['txt_masks'], t['gmap_img_embeds'], t['gmap_step_ids'], t['gmap_pos_fts'], t['gmap_masks'],
+            t['gmap_pair_dists'], t['gmap_visited_masks'], t['gmap_ids'], t['vp_img_embeds'], t['vp_pos_fts'], t['vp_masks'],
+            t['vp_nav_masks'], None, t['cand_ids'], imagine_embeds=t.get('imagine_embeds'), imagine_masks=t.get('imagine_masks'))
+
+    def _graphable(self):
+        return self.use_cuda_graphs and not self.training and not torch.is_grad_enabled()
 
     def forward(self, mode, batch):
         batch = collections.defaultdict(lambda: None, batch)
+        m = self.vln_bert
         if mode == 'panorama':
             if self.training and self.drop_env.p > 0:
                 raise NotImplementedError('train-mode feature dropout runs through train.py')
-            return self.vln_bert(mode, batch)
-        if mode in ('language', 'imagine', 'align_with_contrastive_loss', 'navigation'):
-            return self.vln_bert(mode, batch)
+            if self._graphable() and batch['obj_img_fts'] is None:
+                dev = m.embeddings.LayerNorm.weight.device
+                tok = graphs.weights_token(m, self._wt_cache)
+                out = self._g_pano({k: batch[k] for k in ('view_img_fts', 'loc_fts', 'nav_types', 'view_lens')}, dev,
+                                   extra_key=(m.precision,), weights_token=tok)
+                return out['pano_embeds'], out['pano_masks']
+            return m(mode, batch)
+        if mode == 'navigation':
+            if self._graphable() and batch['vp_obj_masks'] is None:
+                dev = m.embeddings.LayerNorm.weight.device
+                tok = graphs.weights_token(m, self._wt_cache)
+                t = {k: batch[k] for k in self.NAV_TENSORS if batch[k] is not None}
+                G, P = batch['gmap_img_embeds'].shape[1], batch['vp_img_embeds'].shape[1]
+                t['gmap_ids'], t['cand_ids'] = m.intern_vpids(batch['gmap_vpids'], batch['vp_cand_vpids'], G, P, None)
+                cfg = m.config
+                return self._g_nav(t, dev, extra_key=(m.precision, cfg.imagine_enc_pano, cfg.concat_imagine_with if
+                                                      cfg.imagine_enc_pano else None), weights_token=tok)
+            return m(mode, batch)
+        if mode in ('language', 'imagine', 'align_with_contrastive_loss'):
+            return m(mode, batch)
         raise NotImplementedError('wrong mode: %s' % mode)

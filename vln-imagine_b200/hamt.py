@@ -20,7 +20,7 @@ from typing import List, Optional
 import torch
 import torch.nn as nn
 
-from . import blocks, ops, params
+from . import blocks, graphs, ops, params
 from .blocks import Act, Stream
 from .config import hamt_config
 from .duet import _f32c, align_forward
@@ -140,11 +140,17 @@ class NavCMT(nn.Module):
         f32 = _f32c(hist_img_feats)
         w, b = pk['hist_img'].get(lowp)
         a = ops.gemm(ops.cast_bf16(f32) if lowp else f32, w, b, out_dtype=F32)
-        step = int(ob_step_ids.view(-1)[0]) if torch.is_tensor(ob_step_ids) else int(ob_step_ids)
+        # position embedding of the current step: a [B] index tensor (the same id for every episode, :597), so the
+        # step never becomes a pointer baked into a captured graph
+        if torch.is_tensor(ob_step_ids) and ob_step_ids.numel() == B:
+            step_idx = ob_step_ids.long().contiguous().view(-1)
+        else:
+            step = int(ob_step_ids.view(-1)[0]) if torch.is_tensor(ob_step_ids) else int(ob_step_ids)
+            step_idx = torch.full((B,), step, dtype=torch.int64, device=dev)
         e32, _ = ops.embed_compose(B, dev, a=a, a_ln=(he.img_layer_norm.weight, he.img_layer_norm.bias),
                                    feat=_f32c(hist_ang_feats), feat_w=he.ang_linear.weight, feat_b=he.ang_linear.bias,
                                    feat_ln=(he.ang_layer_norm.weight, he.ang_layer_norm.bias),
-                                   const_row=he.position_embeddings.weight[step], const_row2=type_row)
+                                   idx=step_idx, table=he.position_embeddings.weight, const_row=type_row)
         pano_mean = None
         if he.pano_encoder is not None:
             V = hist_pano_img_feats.shape[1]
@@ -283,12 +289,20 @@ class NavCMT(nn.Module):
 
 def length2mask(lengths, size, device):
     """utils/misc.py:12-17: True where the position is PADDING."""
-    lens = torch.as_tensor(lengths, dtype=torch.int64, device=device)
+    if torch.is_tensor(lengths):                 # superset of the reference: lengths may already be a tensor
+        lens = lengths.to(device=device, dtype=torch.int64)
+    else:
+        lens = torch.as_tensor(lengths, dtype=torch.int64, device=device)
     return torch.arange(size, dtype=torch.int64, device=device)[None, :] >= lens[:, None]
 
 
 class VLNBertCMT(nn.Module):
-    """models/model_HAMT.py:13-96."""
+    """models/model_HAMT.py:13-96.  Inference calls of the per-step modes ('visual', 'history') are replayed from
+    CUDA graphs (graphs.GraphedCall); ``use_cuda_graphs = False`` gives plain eager launches."""
+
+    VIS_TENSORS = ('txt_embeds', 'txt_masks', 'ob_img_feats', 'ob_ang_feats', 'ob_nav_types', 'ob_masks', 'imagine_embeds',
+                   'imagine_masks')
+    HIST_TENSORS = ('hist_img_feats', 'hist_ang_feats', 'hist_pano_img_feats', 'hist_pano_ang_feats')
 
     def __init__(self, args):
         super().__init__()
@@ -302,11 +316,35 @@ class VLNBertCMT(nn.Module):
                 sd[k[5:] if k.startswith('bert.') else k] = v
             self.vln_bert.load_state_dict(sd, strict=False)
         self.drop_env = nn.Dropout(p=getattr(args, 'feat_dropout', 0.0))
+        self.use_cuda_graphs = os.environ.get('VLN_IMAGINE_CUDA_GRAPHS', '1') != '0'
+        self._wt_cache = {}
+        self._g_vis = graphs.GraphedCall(self._vis_fn)
+        self._g_hist = graphs.GraphedCall(self._hist_fn)
+
+    def _apply(self, fn, *a, **k):
+        self._wt_cache = {}
+        self._g_vis.clear()
+        self._g_hist.clear()
+        return super()._apply(fn, *a, **k)
 
     def _env_dropout(self, x):
         if x is not None and self.training and self.drop_env.p > 0:
             raise NotImplementedError('train-mode feature dropout runs through train.py')
         return x
+
+    def _vis_fn(self, t):
+        logits, txt_o, hist_o, ob_o = self.vln_bert.forward_visual(
+            t['txt_embeds'], t['txt_masks'], t['hist_embeds'], t['hist_masks'], t['ob_img_feats'], t['ob_ang_feats'],
+            t['ob_nav_types'], t['ob_masks'], t.get('imagine_embeds'), t.get('imagine_masks'))
+        states = hist_o[:, 0] if self.args.no_lang_ca else self._states(txt_o, hist_o)
+        return {'act_logits': logits, 'states': states}
+
+    def _hist_fn(self, t):
+        return {'hist': self.vln_bert.forward_history(t['hist_img_feats'], t['hist_ang_feats'], t['ob_step_ids'],
+                                                      t.get('hist_pano_img_feats'), t.get('hist_pano_ang_feats'))}
+
+    def _graphable(self):
+        return self.use_cuda_graphs and not self.training and not torch.is_grad_enabled()
 
     def forward(self, mode, txt_ids=None, txt_masks=None, txt_embeds=None, hist_img_feats=None, hist_ang_feats=None,
                 hist_pano_img_feats=None, hist_pano_ang_feats=None, hist_embeds=None, hist_lens=None, ob_step=None,
@@ -324,22 +362,37 @@ class VLNBertCMT(nn.Module):
                      align_imagine_embeds=align_imagine_embeds, imagine_masks=imagine_masks, sub_instr_segs=sub_instr_segs,
                      sub_instr_imag_flag=sub_instr_imag_flag, noun_phrase_segs=noun_phrase_segs, obs_instr_ids=obs_instr_ids)
         if mode == 'history':
+            if hist_img_feats is not None and self._graphable():
+                dev = m.embeddings.LayerNorm.weight.device
+                loc = dict(hist_img_feats=hist_img_feats, hist_ang_feats=hist_ang_feats,
+                           hist_pano_img_feats=hist_pano_img_feats, hist_pano_ang_feats=hist_pano_ang_feats)
+                t = {k: loc[k] for k in self.HIST_TENSORS if loc[k] is not None}
+                t['ob_step_ids'] = torch.full((hist_img_feats.shape[0],), int(ob_step), dtype=torch.int64)
+                return self._g_hist(t, dev, extra_key=(m.precision,), weights_token=graphs.weights_token(m, self._wt_cache))['hist']
             return m('history', hist_img_feats=self._env_dropout(hist_img_feats), hist_ang_feats=hist_ang_feats,
                      ob_step_ids=ob_step, hist_pano_img_feats=self._env_dropout(hist_pano_img_feats),
                      hist_pano_ang_feats=hist_pano_ang_feats)
         if mode == 'visual':
+            if return_cross_attention_probs:
+                raise NotImplementedError('attention scores never leave the fused attention kernel')
             hist = torch.stack(hist_embeds, 1)                                   # list of (B, 768) -> (B, T, 768)
+            if self._graphable():
+                dev = m.embeddings.LayerNorm.weight.device
+                loc = dict(txt_embeds=txt_embeds, txt_masks=txt_masks, ob_img_feats=ob_img_feats, ob_ang_feats=ob_ang_feats,
+                           ob_nav_types=ob_nav_types, ob_masks=ob_masks, imagine_embeds=imagine_embeds, imagine_masks=imagine_masks)
+                t = {k: loc[k] for k in self.VIS_TENSORS if loc[k] is not None}
+                t['hist_embeds'] = hist
+                t['hist_masks'] = length2mask(hist_lens, hist.size(1), 'cpu').logical_not()
+                out = self._g_vis(t, dev, extra_key=(m.precision, m.config.imagine_enc_pano),
+                                  weights_token=graphs.weights_token(m, self._wt_cache))
+                return (out['act_logits'], out['states']) if return_states else (out['act_logits'],)
             hist_masks = length2mask(hist_lens, hist.size(1), hist.device).logical_not()
             act_logits, txt_o, hist_o, ob_o = m('visual', txt_embeds=txt_embeds, txt_masks=txt_masks, hist_embeds=hist,
                                                 hist_masks=hist_masks, ob_img_feats=self._env_dropout(ob_img_feats),
                                                 ob_ang_feats=ob_ang_feats, ob_nav_types=ob_nav_types, ob_masks=ob_masks,
-                                                imagine_embeds=imagine_embeds, imagine_masks=imagine_masks,
-                                                return_cross_attention_probs=return_cross_attention_probs)
+                                                imagine_embeds=imagine_embeds, imagine_masks=imagine_masks)
             if return_states:
-                if self.args.no_lang_ca:
-                    states = hist_o[:, 0]
-                else:
-                    states = self._states(txt_o, hist_o)
+                states = hist_o[:, 0] if self.args.no_lang_ca else self._states(txt_o, hist_o)
                 return act_logits, states
             return (act_logits,)
         raise NotImplementedError('wrong mode: %s' % mode)

@@ -6,6 +6,7 @@ stream.  Nothing falls back to ATen arithmetic.
 """
 from __future__ import annotations
 
+import os
 from typing import Optional, Sequence
 
 import torch
@@ -65,6 +66,44 @@ def pad_rows(n: int) -> int:
     return (n + ROW_ALIGN - 1) // ROW_ALIGN * ROW_ALIGN
 
 
+TILE_PAIR = 0x1000
+_TILE_CANDIDATES = [256 | TILE_PAIR, 192 | TILE_PAIR, 128 | TILE_PAIR, 256, 192, 128, 96, 64]
+_TILE_CACHE = {}           # GEMM signature -> tile code, filled by timing the candidates on first use
+
+
+def autotune_enabled() -> bool:
+    return os.environ.get('VLN_IMAGINE_AUTOTUNE', '1') != '0' and not os.environ.get('VI_GEMM_TILE')
+
+
+def _tune_tile(key, launch, N: int, pair_ok: bool) -> int:
+    """Time every admissible tile shape for this GEMM signature (CUDA events, back-to-back launches) and remember
+    the fastest.  Skipped (library cost model) while a CUDA graph is being captured."""
+    if key in _TILE_CACHE:
+        return _TILE_CACHE[key]
+    if torch.cuda.is_current_stream_capturing():
+        return 0
+    best, best_t = 0, float('inf')
+    for tile in _TILE_CANDIDATES:
+        bn, pair = tile & 0xFFF, bool(tile & TILE_PAIR)
+        if N % bn or (pair and not pair_ok):
+            continue
+        for _ in range(2):
+            launch(tile)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        torch.cuda._sleep(400_000)                     # let the host queue the launches back to back
+        e0.record()
+        for _ in range(6):
+            launch(tile)
+        e1.record()
+        torch.cuda.synchronize()
+        t = e0.elapsed_time(e1)
+        if t < best_t:
+            best, best_t = tile, t
+    _TILE_CACHE[key] = best
+    return best
+
+
 def gemm(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None,
          residual: Optional[torch.Tensor] = None, epilogue: int = EPI_NONE,
          out_dtype: torch.dtype = BF16, group_row_end: Optional[Sequence[int]] = None,
@@ -83,13 +122,23 @@ def gemm(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None,
             raise _lib.VlnImagineError('bf16 GEMM needs a bf16 weight')
         if out is None:
             out = torch.empty((M, N), dtype=out_dtype, device=x.device)
+        ydt = _lib.DT_F32 if out.dtype == F32 else _lib.DT_BF16
+
+        def launch(tile):
+            check(lib.vi_gemm_bf16_tiled(x.data_ptr(), ldx, w.data_ptr(), _ptr(bias), _ptr(residual), ldr, out.data_ptr(),
+                                         out.stride(0), ydt, M, N, K, epilogue, n_groups, ends, tile, _stream()),
+                  'vi_gemm_bf16_tiled')
+        tile = 0
+        if autotune_enabled():
+            ge = tuple(group_row_end) if group_row_end is not None else None
+            pair_ok = ge is None or all(e % 256 == 0 for e in ge[:-1])
+            key = (M, N, K, ge, epilogue, bias is not None, residual is not None, ydt, x.device.index)
+            tile = _tune_tile(key, launch, N, pair_ok)
         tr = _Counters.gemm_trace
         if tr is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        check(lib.vi_gemm_bf16(x.data_ptr(), ldx, w.data_ptr(), _ptr(bias), _ptr(residual), ldr, out.data_ptr(),
-                               out.stride(0), _lib.DT_F32 if out.dtype == F32 else _lib.DT_BF16, M, N, K, epilogue,
-                               n_groups, ends, _stream()), 'vi_gemm_bf16')
+        launch(tile)
         _launched(1)
         if tr is not None:
             e1.record()
