@@ -418,6 +418,19 @@ def main():
         trace, ops._Counters.gemm_trace = ops._Counters.gemm_trace, None
         gemm_flops = sum(2.0 * m * n * k for m, n, k, _, _ in trace)
         gemm_ms = sum(a.elapsed_time(b) for _, _, _, a, b in trace)
+        # per-entry-point breakdown of one step, same method (diagnostic: the event pairs add ~1 us gaps)
+        torch.cuda._sleep(40_000_000)
+        ops._Counters.trace = []
+        for _ in range(3):
+            step_fn(model, d, txt, img2)
+        torch.cuda.synchronize()
+        tr2, ops._Counters.trace = ops._Counters.trace, None
+        breakdown = {}
+        for name, a, b in tr2:
+            n_, t_ = breakdown.get(name, (0, 0.0))
+            breakdown[name] = (n_ + 1, t_ + a.elapsed_time(b))
+        breakdown = {k: {'launches_per_step': v[0] // 3, 'ms_per_step': round(v[1] / 3, 4)} for k, v in
+                     sorted(breakdown.items(), key=lambda kv: -kv[1][1])}
 
     if rank != 0:
         if world > 1:
@@ -453,7 +466,8 @@ def main():
                      'kernel': 'gemm_bf16_tc_kernel (tcgen05): %d launches/step, %.1f GFLOP/step, %.3f ms/step of GEMM time '
                                '(CUDA events around each launch of 3 queued eager steps)' % (len(trace) // 3, gemm_flops / 3 / 1e9, gemm_ms / 3)},
         'step': {'algorithmic_gflop_per_decision': fl_dec / 1e9, 'tflops': step_tf, 'frac_of_peak': step_tf / peak_tf,
-                 'launches_per_step': launches_per_step, 'prelude_ms_per_episode_batch': prelude_ms},
+                 'launches_per_step': launches_per_step, 'prelude_ms_per_episode_batch': prelude_ms,
+                 'breakdown': breakdown},
     }
     if world == 1 and not args.no_cpu_baseline:
         cb, _ = cpu_reference(model_kind, shape)

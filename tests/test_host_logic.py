@@ -159,3 +159,22 @@ def test_algorithmic_flops_match_the_survey():
     assert abs(bench.flops_per_decision('duet', synth.CFG2) / 1e9 - 7.281) < 2e-3
     assert abs(bench.flops_per_decision('hamt', synth.CFG3) / 1e9 - 11.811) < 2e-3
     assert abs(bench.flops_per_decision('duet', synth.CFG5) / 1e9 - 14.784) < 2e-3
+
+
+def test_imagination_feature_loader_semantics(tmp_path):
+    db_mod = importlib.import_module('vln_imagine_b200.imagine_db')
+    rng = np.random.default_rng(0)
+    store = {'10_0': rng.standard_normal((2, 1000)), '11_2': rng.standard_normal((3, 1000)), '12_1': np.zeros((0, 1000))}
+    np.savez(tmp_path / 'feats.npz', **store)
+    for src in (store, str(tmp_path / 'feats.npz')):
+        db = db_mod.ImaginationImageFeaturesDB(src, 768)
+        ft = db.get_image_feature('10_0')
+        assert ft.shape == (2, 768) and ft.dtype == np.float32 and db.get_image_feature('10_0') is ft      # cached
+        flags = {'10_0': ['True', 'False', 'True'], '11_2': ['True', 'True', 'False', 'True'], '12_1': ['False', 'False']}
+        feats, mask = db_mod.collate_imaginations(db, ['10_0', '11_2', '12_1'], flags, 768)
+        assert feats.shape == (3, 4, 768) and mask.tolist() == [[True, False, True, False], [True, True, False, True],
+                                                                 [False] * 4]
+        assert np.array_equal(feats[0, 2], store['10_0'][1, :768].astype(np.float32)) and not feats[0, 1].any()
+        assert np.array_equal(feats[1, 3], store['11_2'][2, :768].astype(np.float32)) and not feats[2].any()
+    with pytest.raises(AssertionError):
+        db_mod.collate_imaginations(db_mod.ImaginationImageFeaturesDB(store, 768), ['10_0'], {'10_0': ['True']}, 768)

@@ -54,12 +54,13 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool v
   const int sz = valid ? 16 : 0;       // src-size 0 zero-fills the 16 bytes
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
 }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // grid (q-tiles of 64, H, sum of B over problems), 128 threads: warp w owns query rows [64*bx + 16w, +16).
 // K, V (whole head) and the Q tile are staged with cp.async; fragments come from ldmatrix (V through .trans, so no
 // explicit transpose); scores stay in registers with an fp32 online softmax over 64-key chunks.
-__global__ void __launch_bounds__(128) attn_fwd_bf16_kernel(const AttnParams p) {
+__global__ void __launch_bounds__(128, 5) attn_fwd_bf16_kernel(const AttnParams p) {
   pdl_enter();
   extern __shared__ __align__(16) uint8_t smem[];
   int z = blockIdx.z, pi = 0;
@@ -79,38 +80,50 @@ __global__ void __launch_bounds__(128) attn_fwd_bf16_kernel(const AttnParams p) 
   const bf16* vg = reinterpret_cast<const bf16*>(pr.v) + (long long)b * pr.Lk * pr.ldv + h * DH;
   const bf16* qg = reinterpret_cast<const bf16*>(pr.q) + (long long)b * pr.Lq * pr.ldq + h * DH;
   const uint32_t ks_u = smem_u32(Ks), vs_u = smem_u32(Vs), qs_u = smem_u32(Qs);
-  for (int e = tid; e < LkP * 8; e += 128) {
-    const int key = e >> 3, ch = e & 7;
-    const bool ok = key < pr.Lk;
-    const int kk = ok ? key : 0;
-    cp_async16(ks_u + (uint32_t)(key * ROW + ch * 8) * 2, kg + (long long)kk * pr.ldk + ch * 8, ok);
-    cp_async16(vs_u + (uint32_t)(key * ROW + ch * 8) * 2, vg + (long long)kk * pr.ldv + ch * 8, ok);
-  }
+  // two cp.async groups: Q + the first 64 keys, then the remaining keys, so the first score chunk can start
+  // while the tail of K / V is still in flight
+  const int first = LkP < 64 ? LkP : 64;
   for (int e = tid; e < 64 * 8; e += 128) {
     const int r = e >> 3, ch = e & 7;
     const bool ok = q_base + r < pr.Lq;
     const int rr = ok ? q_base + r : 0;
     cp_async16(qs_u + (uint32_t)(r * ROW + ch * 8) * 2, qg + (long long)rr * pr.ldq + ch * 8, ok);
   }
+  for (int e = tid; e < first * 8; e += 128) {
+    const int key = e >> 3, ch = e & 7;
+    const bool ok = key < pr.Lk;
+    const int kk = ok ? key : 0;
+    cp_async16(ks_u + (uint32_t)(key * ROW + ch * 8) * 2, kg + (long long)kk * pr.ldk + ch * 8, ok);
+    cp_async16(vs_u + (uint32_t)(key * ROW + ch * 8) * 2, vg + (long long)kk * pr.ldv + ch * 8, ok);
+  }
+  cp_async_commit();
+  for (int e = first * 8 + tid; e < LkP * 8; e += 128) {
+    const int key = e >> 3, ch = e & 7;
+    const bool ok = key < pr.Lk;
+    const int kk = ok ? key : 0;
+    cp_async16(ks_u + (uint32_t)(key * ROW + ch * 8) * 2, kg + (long long)kk * pr.ldk + ch * 8, ok);
+    cp_async16(vs_u + (uint32_t)(key * ROW + ch * 8) * 2, vg + (long long)kk * pr.ldv + ch * 8, ok);
+  }
+  cp_async_commit();
   for (int key = tid; key < LkP; key += 128) {
     float m = 0.f;
     if (key >= pr.Lk) m = -INFINITY;
     else if (pr.key_mask && !pr.key_mask[(long long)b * pr.Lk + key]) m = (p.mask_mode == VI_MASK_NEG_INF) ? -INFINITY : -10000.0f;
     madd[key] = m;
   }
-  cp_async_wait_all();
+  cp_async_wait<1>();
   __syncthreads();
 
   const int q0 = q_base + warp * 16;
-  if (q0 >= pr.Lq) return;
+  if (q0 >= pr.Lq) {                                  // idle warp: still takes part in the second barrier
+    if (LkP > 64) { cp_async_wait<0>(); __syncthreads(); }
+    return;
+  }
   const int g = lane >> 2, tg = lane & 3;
   const int r0 = q0 + g, r1 = q0 + g + 8;
   const int lm = lane >> 3, lr = lane & 7;          // ldmatrix: this lane addresses row lr of matrix lm
 
-  uint32_t qa[4][4];
-#pragma unroll
-  for (int ks = 0; ks < 4; ++ks)
-    ldsm_x4(qa[ks], qs_u + (uint32_t)((warp * 16 + (lm & 1) * 8 + lr) * ROW + ks * 16 + (lm >> 1) * 8) * 2);
+  const uint32_t q_frag = qs_u + (uint32_t)((warp * 16 + (lm & 1) * 8 + lr) * ROW + (lm >> 1) * 8) * 2;
 
   float bw = 0.f, bb = 0.f;
   const float* pd0 = nullptr;
@@ -128,19 +141,25 @@ __global__ void __launch_bounds__(128) attn_fwd_bf16_kernel(const AttnParams p) 
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
 
   for (int kc = 0; kc < LkP; kc += 64) {
+    if (kc == 64) {                                   // (block-uniform) the second cp.async group is needed from here
+      cp_async_wait<0>();
+      __syncthreads();
+    }
     const int npairs = min(4, (LkP - kc) >> 4);       // 16-key blocks in this chunk (LkP % 16 == 0)
     float s[8][4];
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
 #pragma unroll
-    for (int np = 0; np < 4; ++np) {
-      if (np < npairs) {
+    for (int ks = 0; ks < 4; ++ks) {
+      uint32_t qa[4];
+      ldsm_x4(qa, q_frag + (uint32_t)(ks * 32));
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
+      for (int np = 0; np < 4; ++np) {
+        if (np < npairs) {
           uint32_t kb[4];     // (keys 0-7, d 0-7) (keys 0-7, d 8-15) (keys 8-15, d 0-7) (keys 8-15, d 8-15)
           ldsm_x4(kb, ks_u + (uint32_t)((kc + np * 16 + (lm >> 1) * 8 + lr) * ROW + ks * 16 + (lm & 1) * 8) * 2);
-          mma_16816(s[2 * np], qa[ks], kb[0], kb[1]);
-          mma_16816(s[2 * np + 1], qa[ks], kb[2], kb[3]);
+          mma_16816(s[2 * np], qa, kb[0], kb[1]);
+          mma_16816(s[2 * np + 1], qa, kb[2], kb[3]);
         }
       }
     }
@@ -364,6 +383,7 @@ extern "C" int vi_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ld
 
 int vi_attn_init() {
   VI_CUDA(cudaFuncSetAttribute(attn_fwd_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 176 * 1024));
+  VI_CUDA(cudaFuncSetAttribute(attn_fwd_bf16_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   VI_CUDA(cudaFuncSetAttribute(attn_fwd_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   return VI_OK;
 }

@@ -12,7 +12,7 @@ from typing import Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import lib, check, EPI_NONE, EPI_GELU, EPI_RELU, MASK_ADD_NEG10000, MASK_NEG_INF  # noqa: F401
+from ._lib import check, EPI_NONE, EPI_GELU, EPI_RELU, MASK_ADD_NEG10000, MASK_NEG_INF  # noqa: F401
 
 HIDDEN = 768
 HEADS = 12
@@ -20,10 +20,35 @@ BF16, F32 = torch.bfloat16, torch.float32
 
 
 class _Counters:
-    """Kernel launches issued through this module (bench.py reports them as gpu_launches) and an optional
-    per-launch CUDA-event trace of the GEMM kernel (bench.py's roofline leg)."""
+    """Kernel launches issued through this module (bench.py reports them as gpu_launches) and optional
+    per-launch CUDA-event traces: of the GEMM kernel with its shape (bench.py's roofline leg) and of every
+    library entry point by name (bench.py's per-kernel breakdown)."""
     launches = 0
     gemm_trace = None          # list of (M, N, K, start_event, end_event) when enabled
+    trace = None               # list of (entry point, start_event, end_event) when enabled
+
+
+class _Lib:
+    """The ctypes library, with an event pair around each call while _Counters.trace is a list."""
+
+    def __getattr__(self, name):
+        fn = getattr(_lib.lib, name)
+
+        def call(*a):
+            tr = _Counters.trace
+            if tr is None:
+                return fn(*a)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rc = fn(*a)
+            e1.record()
+            tr.append((name, e0, e1))
+            return rc
+        setattr(self, name, call)
+        return call
+
+
+lib = _Lib()
 
 
 def _stream():
@@ -69,6 +94,24 @@ def pad_rows(n: int) -> int:
 TILE_PAIR = 0x1000
 _TILE_CANDIDATES = [256 | TILE_PAIR, 192 | TILE_PAIR, 128 | TILE_PAIR, 256, 192, 128, 96, 64]
 _TILE_CACHE = {}           # GEMM signature -> tile code, filled by timing the candidates on first use
+_TILE_TABLE_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'tile_table.json')
+
+
+def _key_str(key):
+    return repr(key[:-1])      # the device index is not part of the persisted signature
+
+
+def load_tile_table(path: str = _TILE_TABLE_PATH):
+    """Tile choices measured on a B200 by tools/tune_tiles.py; shapes not listed are tuned on first use."""
+    import json
+    try:
+        with open(path) as f:
+            return json.load(f)
+    except (OSError, ValueError):
+        return {}
+
+
+_TILE_TABLE = load_tile_table()
 
 
 def autotune_enabled() -> bool:
@@ -79,6 +122,10 @@ def _tune_tile(key, launch, N: int, pair_ok: bool) -> int:
     """Time every admissible tile shape for this GEMM signature (CUDA events, back-to-back launches) and remember
     the fastest.  Skipped (library cost model) while a CUDA graph is being captured."""
     if key in _TILE_CACHE:
+        return _TILE_CACHE[key]
+    ks = _key_str(key)
+    if ks in _TILE_TABLE and os.environ.get('VLN_IMAGINE_RETUNE', '0') == '0':
+        _TILE_CACHE[key] = int(_TILE_TABLE[ks])
         return _TILE_CACHE[key]
     if torch.cuda.is_current_stream_capturing():
         return 0
