@@ -121,7 +121,7 @@ int vi_add_ln(const float* a, const float* b, const float* gamma, const float* b
               int n_groups, const int32_t* group_row_end, vi_stream_t stream);
 
 /* Input-embedding composer:
- *   y = LN_out( [LN_a](a) + LN_f(feat @ feat_w^T + feat_b) + table[idx] + pos_table[row % pos_period]
+ *   y = LN_out( [LN_a](a) + a2 + a3 + LN_f(feat @ feat_w^T + feat_b) + table[idx] + pos_table[row % pos_period]
  *               + const_row + const_row2 )
  * every term optional.  Covers BertEmbeddings (D/models/vilmodel.py:49-78), the panorama /
  * observation embeddings (D/models/vilmodel.py:1091-1121, H/models/vilmodel_cmt.py:521-544),
@@ -149,6 +149,8 @@ typedef struct {
   float* y32;                /* [rows, 768] or NULL */
   void* y16;                 /* bf16 [rows, 768] or NULL */
   int64_t rows;
+  const float* a2;           /* [rows, 768] plain addends (NULL: none); used by the training-mode decomposition */
+  const float* a3;
 } vi_embed_args;
 int vi_embed_compose(const vi_embed_args* args, vi_stream_t stream);
 
@@ -209,6 +211,49 @@ int vi_infonce_loss(const float* proj, const float* tgt, const float* negs,
 int vi_copy_rows(const float* src, int64_t src_batch_stride, int64_t src_row_stride, float* dst32, void* dst16,
                  int64_t dst_batch_stride, int64_t dst_row_stride, int64_t n_batches, int rows_per_batch,
                  vi_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Backward pass (fine-tuning).  The dense gradients reuse vi_gemm_* on transposed operands:
+ *   dX = dY W  (vi_gemm with the [K, N] transposed weight shadow),  dW = dY^T X  (vi_gemm on vi_transpose'd
+ *   dY and X),  db = vi_colsum(dY).  The entry points below are the adjoints of the remaining forward kernels;
+ *   each mirrors what torch.autograd computes for the reference ops it cites.
+ * ------------------------------------------------------------------------------------------- */
+/* dst[c, r] = src[r, c]; dst is [cols, ldd] with columns rows..pad_rows-1 zero-filled (pad_rows <= ldd) */
+int vi_transpose(const void* src, int64_t ld, void* dst, int64_t ldd, int rows, int cols, int pad_rows, int dtype,
+                 vi_stream_t stream);
+/* out[c] = sum_r x[r, c] (fp32 accumulation, fixed order); bias gradients of nn.Linear */
+int vi_colsum(const void* x, int64_t ld, int dtype, float* out, int64_t rows, int cols, vi_stream_t stream);
+/* y = act(x), dx = dy * act'(x); act = VI_EPI_GELU (erf form, D/models/vilmodel.py:32-38) or VI_EPI_RELU.
+ * The training forward keeps the pre-activation, so activations run as their own kernels there. */
+int vi_act_fwd(const void* x, void* y, int64_t n, int act, int dtype, vi_stream_t stream);
+int vi_act_bwd(const void* x, const void* dy, void* dx, int64_t n, int act, int dtype, vi_stream_t stream);
+/* adjoint of vi_add_ln: dy = dy32 (+ dy16); dx (fp32 and/or bf16 copy) is the gradient of both a and b;
+ * dgamma / dbeta [n_groups, 768] may be NULL; stats is a [rows, 2] fp32 scratch (mean, rstd). */
+int vi_add_ln_bwd(const float* a, const float* b, const float* gamma, float eps, const float* dy32, const void* dy16,
+                  float* dx32, void* dx16, float* dgamma, float* dbeta, float* stats, int64_t rows,
+                  int n_groups, const int32_t* group_row_end, vi_stream_t stream);
+/* small-feature linear of vi_embed_compose: dW[768, feat_dim] = dt^T feat, db[768] = colsum(dt) */
+int vi_feat_wgrad(const float* dt, const float* feat, int feat_dim, float* dW, float* db, int64_t rows, vi_stream_t stream);
+/* dst[idx[r]] += src[r] (idx != NULL) or dst[r % period] += src[r]: embedding / position table adjoints */
+int vi_scatter_add_rows(const float* src, const int64_t* idx, int period, float* dst, int64_t rows, vi_stream_t stream);
+/* adjoint of the dot-product tail of vi_ln_dot (out[r] = x[r] . w[g] + b[g]) */
+int vi_rowdot_bwd(const float* dout, const float* x, const float* w, float* dx, float* dw, float* db, int64_t rows,
+                  int n_groups, const int32_t* group_row_end, vi_stream_t stream);
+/* attention backward for one token stream (same operand conventions as vi_attn_fwd); d_affine -> device {dw, db}
+ * of the GASA affine, accumulated (+=); dq / dk / dv have the dtype of q / k / v. */
+int vi_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                const void* dout, int64_t ldo, void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv,
+                int dtype, const uint8_t* key_mask, const float* pair_dist, const float* bias_affine, float* d_affine,
+                int B, int H, int Lq, int Lk, int mask_mode, vi_stream_t stream);
+/* adjoint of vi_duet_fuse_logits; any of d_global / d_local / d_fused may be NULL (treated as zero) */
+int vi_duet_fuse_logits_bwd(const float* g_raw, const float* l_raw, const float* fuse_raw,
+                            const uint8_t* gmap_masks, const uint8_t* gmap_visited, const uint8_t* vp_nav_masks,
+                            const int32_t* gmap_ids, const int32_t* cand_ids,
+                            const float* d_global, const float* d_local, const float* d_fused,
+                            float* dg_raw, float* dl_raw, float* dfuse_raw, int B, int G, int P, vi_stream_t stream);
+/* adjoint of vi_cosine_loss: dloss is the device scalar gradient of the mean; dproj / dtgt may be NULL */
+int vi_cosine_loss_bwd(const float* proj, const float* tgt, const float* dloss, float* dproj, float* dtgt, int R,
+                       vi_stream_t stream);
 
 /* fp32 -> bf16 shadow copy of a weight or activation */
 int vi_cast_bf16(const float* src, void* dst, int64_t n, vi_stream_t stream);

@@ -33,7 +33,7 @@ class EmbedArgs(C.Structure):
         ('feat', _p), ('feat_dim', C.c_int32), ('feat_w', _p), ('feat_b', _p), ('feat_gamma', _p), ('feat_beta', _p),
         ('idx', _p), ('table', _p), ('pos_table', _p), ('pos_period', C.c_int32),
         ('const_row', _p), ('const_row2', _p), ('out_gamma', _p), ('out_beta', _p),
-        ('eps', _f), ('y32', _p), ('y16', _p), ('rows', _l),
+        ('eps', _f), ('y32', _p), ('y16', _p), ('rows', _l), ('a2', _p), ('a3', _p),
     ]
 
 
@@ -64,6 +64,17 @@ PROTOTYPES = {
     'vi_infonce_loss': [_p, _p, _p, _p, _p, _f, _p, _p, _i, _i, _p],
     'vi_copy_rows': [_p, _l, _l, _p, _p, _l, _l, _l, _i, _p],
     'vi_cast_bf16': [_p, _p, _l, _p],
+    'vi_transpose': [_p, _l, _p, _l, _i, _i, _i, _i, _p],
+    'vi_colsum': [_p, _l, _i, _p, _l, _i, _p],
+    'vi_act_fwd': [_p, _p, _l, _i, _i, _p],
+    'vi_act_bwd': [_p, _p, _p, _l, _i, _i, _p],
+    'vi_add_ln_bwd': [_p, _p, _p, _f, _p, _p, _p, _p, _p, _p, _p, _l, _i, _ip, _p],
+    'vi_feat_wgrad': [_p, _p, _i, _p, _p, _l, _p],
+    'vi_scatter_add_rows': [_p, _p, _i, _p, _l, _p],
+    'vi_rowdot_bwd': [_p, _p, _p, _p, _p, _p, _l, _i, _ip, _p],
+    'vi_attn_bwd': [_p, _l, _p, _l, _p, _l, _p, _l, _p, _l, _p, _l, _p, _l, _i, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
+    'vi_duet_fuse_logits_bwd': [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
+    'vi_cosine_loss_bwd': [_p, _p, _p, _p, _p, _i, _p],
 }
 for _name, _args in PROTOTYPES.items():
     _fn = getattr(lib, _name)            # AttributeError here = header/library mismatch: fail loudly

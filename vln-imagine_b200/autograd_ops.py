@@ -1,0 +1,473 @@
+"""torch.autograd.Function wrappers: forward AND backward of every differentiable step are libvlnimagine kernels.
+
+Used when a mode is called with autograd recording (fine-tuning, BASELINE.json cfg-4).  The autograd engine only
+chains the nodes and accumulates gradients at fan-out points (residual branches) and into ``.grad``; it performs
+no model arithmetic itself.  Conventions:
+
+* dense layers: ``dX = dY W`` runs the tcgen05 GEMM on the transposed bf16 weight shadow, ``dW = dY^T X`` runs it on
+  kernel-transposed copies of dY and X (contraction over the rows, zero-padded to a multiple of 64), ``db`` is a
+  fixed-order column sum; grouped (row-stacked) layers loop the weight gradient over their groups;
+* the training forward keeps pre-activations: GELU / ReLU are their own kernels instead of GEMM epilogues;
+* LayerNorm returns the fp32 residual-stream tensor and its bf16 operand copy; its backward takes both gradients;
+* the embedding composer is decomposed into primitives (small-feature linear, LayerNorm, row gather, sum);
+* dropout is not applied (probabilities must be 0 for gradient parity).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import torch
+from torch.autograd import Function
+
+from . import _lib, ops
+from .ops import BF16, F32, HIDDEN, EPI_GELU, EPI_NONE, EPI_RELU, MASK_ADD_NEG10000, _ptr, _stream, check, lib, _launched
+
+
+def needs_grad(*tensors) -> bool:
+    return torch.is_grad_enabled() and any(t is not None and torch.is_tensor(t) and t.requires_grad for t in tensors)
+
+
+def pad64(n: int) -> int:
+    return (n + 63) // 64 * 64
+
+
+def _dt(t: torch.Tensor) -> int:
+    return _lib.DT_BF16 if t.dtype == BF16 else _lib.DT_F32
+
+
+def transpose(src: torch.Tensor, pad_rows: Optional[int] = None) -> torch.Tensor:
+    """[rows, cols] view -> [cols, pad_rows] (zero padded columns)"""
+    rows, cols = src.shape
+    pr = pad_rows or rows
+    dst = torch.empty((cols, pr), dtype=src.dtype, device=src.device)
+    check(lib.vi_transpose(src.data_ptr(), src.stride(0), dst.data_ptr(), dst.stride(0), rows, cols, pr, _dt(src), _stream()),
+          'vi_transpose')
+    _launched(1)
+    return dst
+
+
+def colsum(x: torch.Tensor) -> torch.Tensor:
+    rows, cols = x.shape
+    out = torch.empty((cols,), dtype=F32, device=x.device)
+    check(lib.vi_colsum(x.data_ptr(), x.stride(0), _dt(x), out.data_ptr(), rows, cols, _stream()), 'vi_colsum')
+    _launched(1)
+    return out
+
+
+def to_operand(t: torch.Tensor, lowp: bool) -> torch.Tensor:
+    """gradient tensor -> GEMM operand dtype of the current precision mode (contiguous)"""
+    t = t.contiguous()
+    if lowp and t.dtype != BF16:
+        return ops.cast_bf16(t)
+    if not lowp and t.dtype != F32:
+        return t.float()
+    return t
+
+
+# ----------------------------------------------------------------------------------------------
+class CastBf16Fn(Function):
+    """fp32 -> bf16 operand copy; the gradient passes back in fp32."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return ops.cast_bf16(x)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return dy.float()
+
+
+class LinearFn(Function):
+    """y = x W^T + b [+ residual] for a (grouped) LinearPack; parameters are passed for gradient routing."""
+
+    @staticmethod
+    def forward(ctx, x, residual, pack, lowp, out_dtype, ends, *params):
+        w, b = pack.get(lowp)
+        y = ops.gemm(x, w, b, residual=residual, epilogue=EPI_NONE, out_dtype=out_dtype, group_row_end=ends)
+        ctx.save_for_backward(x)
+        ctx.pack, ctx.lowp, ctx.ends, ctx.has_res = pack, lowp, ends, residual is not None
+        ctx.x_needs = x.requires_grad
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        pack, lowp, ends = ctx.pack, ctx.lowp, ctx.ends
+        dyo = to_operand(dy, lowp)
+        M, K = x.shape
+        n_groups = 1 if ends is None else len(ends)
+        N = dyo.shape[1]
+        dx = None
+        if ctx.x_needs:
+            wt = pack.get_t(lowp, n_groups)                             # [n_groups*K, N]
+            dx = ops.gemm(dyo, wt, None, out_dtype=x.dtype, group_row_end=ends)
+        dW = torch.empty((n_groups * N, K), dtype=F32, device=x.device)
+        db = torch.empty((n_groups * N,), dtype=F32, device=x.device) if pack.biases is not None else None
+        bounds = [0] + (list(ends) if ends is not None else [M])
+        for g in range(n_groups):
+            r0, r1 = bounds[g], min(bounds[g + 1], M)
+            rp = pad64(r1 - r0) if lowp else r1 - r0
+            dyT = transpose(dyo[r0:r1], rp)                             # [N, rp]
+            xT = transpose(x[r0:r1], rp)                                # [K, rp]
+            ops.gemm(dyT, xT, None, out_dtype=F32, out=dW[g * N:(g + 1) * N])
+            if db is not None:
+                db[g * N:(g + 1) * N] = colsum(dyo[r0:r1])
+        grads, off = [], 0
+        for wsrc in pack.weights:
+            n = wsrc.shape[0]
+            grads.append(dW[off:off + n] if wsrc.requires_grad else None)
+            off += n
+        if pack.biases is not None:
+            off = 0
+            for bsrc, wsrc in zip(pack.biases, pack.weights):
+                n = wsrc.shape[0]
+                if bsrc is not None:
+                    grads.append(db[off:off + n] if bsrc.requires_grad else None)
+                off += n
+        return (dx, dy if ctx.has_res else None, None, None, None, None, *grads)
+
+
+def linear(x, pack, lowp, residual=None, out_dtype=None, ends=None):
+    """differentiable dense layer (no fused activation); pack = blocks.LinearPack"""
+    out_dtype = out_dtype or (BF16 if lowp else F32)
+    return LinearFn.apply(x, residual, pack, lowp, out_dtype, ends, *pack.grad_sources())
+
+
+class ActFn(Function):
+    @staticmethod
+    def forward(ctx, x, act):
+        x = x.contiguous()
+        y = torch.empty_like(x)
+        check(lib.vi_act_fwd(x.data_ptr(), y.data_ptr(), x.numel(), act, _dt(x), _stream()), 'vi_act_fwd')
+        _launched(1)
+        ctx.save_for_backward(x)
+        ctx.act = act
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        dy = dy.contiguous()
+        if dy.dtype != x.dtype:
+            dy = dy.to(x.dtype)
+        dx = torch.empty_like(x)
+        check(lib.vi_act_bwd(x.data_ptr(), dy.data_ptr(), dx.data_ptr(), x.numel(), ctx.act, _dt(x), _stream()), 'vi_act_bwd')
+        _launched(1)
+        return dx, None
+
+
+class LayerNormFn(Function):
+    """(y32, y16) = LN(a [+ b]); y16 is None-like (empty) in fp32 mode.  Backward sums the two incoming gradients."""
+
+    @staticmethod
+    def forward(ctx, a, b, gamma, beta, eps, lowp, ends, n_params, *params):
+        a = a.contiguous()
+        y32, y16 = ops.add_ln(a, b, gamma, beta, eps, want16=lowp, group_row_end=ends)
+        ctx.save_for_backward(a, b if b is not None else a.new_empty(0), gamma)
+        ctx.eps, ctx.ends, ctx.has_b, ctx.n_params = eps, ends, b is not None, n_params
+        ctx.b_needs = b is not None and b.requires_grad
+        ctx.a_needs = a.requires_grad
+        ctx.param_needs = [p.requires_grad for p in params]
+        if y16 is None:
+            y16 = a.new_empty(0)
+            ctx.mark_non_differentiable(y16)
+        return y32, y16
+
+    @staticmethod
+    def backward(ctx, dy32, dy16):
+        a, b, gamma = ctx.saved_tensors
+        b = b if ctx.has_b else None
+        rows = a.shape[0]
+        ends = ctx.ends
+        n_groups = 1 if ends is None else len(ends)
+        if dy16 is not None and dy16.numel() == 0:
+            dy16 = None
+        if dy32 is None and dy16 is None:
+            return (None,) * (8 + ctx.n_params)
+        if dy32 is not None:
+            dy32 = dy32.contiguous()
+        if dy16 is not None:
+            dy16 = dy16.contiguous()
+        dx = torch.empty_like(a)
+        dg = torch.empty((n_groups, HIDDEN), dtype=F32, device=a.device)
+        dbt = torch.empty((n_groups, HIDDEN), dtype=F32, device=a.device)
+        stats = torch.empty((rows, 2), dtype=F32, device=a.device)
+        check(lib.vi_add_ln_bwd(a.data_ptr(), _ptr(b), gamma.data_ptr(), ctx.eps, _ptr(dy32), _ptr(dy16), dx.data_ptr(), None,
+                                dg.data_ptr(), dbt.data_ptr(), stats.data_ptr(), rows, n_groups,
+                                _lib.int_array(list(ends)) if ends is not None else None, _stream()), 'vi_add_ln_bwd')
+        _launched(2)
+        half = ctx.n_params // 2
+        pg = [dg[i] if ctx.param_needs[i] else None for i in range(half)] + \
+             [dbt[i] if ctx.param_needs[half + i] else None for i in range(half)]
+        return (dx if ctx.a_needs else None, dx if ctx.b_needs else None, None, None, None, None, None, None, *pg)
+
+
+def layer_norm(a, b, lnpack, eps, lowp, ends=None):
+    """differentiable LayerNorm(a [+ b]) -> (y32, y16 or None); lnpack = blocks.LNPack"""
+    g, be = lnpack.get()
+    srcs = lnpack.grad_sources()
+    y32, y16 = LayerNormFn.apply(a, b, g, be, eps, lowp, ends, len(srcs), *srcs)
+    return y32, (y16 if lowp else None)
+
+
+class AttentionFn(Function):
+    """Multi-stream attention.  ``spec`` = list of problems {q: (base index, row0, col0), k: ..., v: ..., B, Lq, Lk,
+    key_mask, pair_dist, out_row0}; tensors = distinct base tensors (2-D) [+ the two GASA parameters last]."""
+
+    @staticmethod
+    def forward(ctx, spec, rows_out, mask_mode, n_bases, *tensors):
+        bases = tensors[:n_bases]
+        out = torch.empty((rows_out, HIDDEN), dtype=bases[0].dtype, device=bases[0].device)
+        covered = 0
+        probs = []
+        for s in spec:
+            def view(key, L):
+                bi, r0, c0 = s[key]
+                return bases[bi][r0:r0 + s['B'] * L, c0:c0 + HIDDEN]
+            probs.append(dict(q=view('q', s['Lq']), k=view('k', s['Lk']), v=view('v', s['Lk']),
+                              out=out[s['out_row0']:s['out_row0'] + s['B'] * s['Lq']], B=s['B'], Lq=s['Lq'], Lk=s['Lk'],
+                              key_mask=s.get('key_mask'), pair_dist=s.get('pair_dist'), bias_affine=s.get('bias_affine')))
+            covered += s['B'] * s['Lq']
+        if covered < rows_out:
+            out.zero_()
+        ops.attention_multi(probs, mask_mode)
+        ctx.save_for_backward(*bases)
+        ctx.spec, ctx.mask_mode, ctx.n_bases, ctx.n_extra = spec, mask_mode, n_bases, len(tensors) - n_bases
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        bases = ctx.saved_tensors
+        dout = dout.contiguous()
+        grads = [torch.zeros_like(b) if b.requires_grad else None for b in bases]
+        d_affine = None
+        for s in ctx.spec:
+            def view(t, key, L):
+                bi, r0, c0 = s[key]
+                return t[bi][r0:r0 + s['B'] * L, c0:c0 + HIDDEN]
+            q, k, v = view(bases, 'q', s['Lq']), view(bases, 'k', s['Lk']), view(bases, 'v', s['Lk'])
+            need = [grads[s[key][0]] is not None for key in ('q', 'k', 'v')]
+            if not any(need):
+                continue
+            tmp = lambda n: torch.empty((n, HIDDEN), dtype=q.dtype, device=q.device)   # noqa: E731
+            dq = view(grads, 'q', s['Lq']) if need[0] else tmp(s['B'] * s['Lq'])
+            dk = view(grads, 'k', s['Lk']) if need[1] else tmp(s['B'] * s['Lk'])
+            dv = view(grads, 'v', s['Lk']) if need[2] else tmp(s['B'] * s['Lk'])
+            do = dout[s['out_row0']:s['out_row0'] + s['B'] * s['Lq']]
+            if do.dtype != q.dtype:
+                do = do.to(q.dtype)
+            if s.get('pair_dist') is not None and d_affine is None:
+                d_affine = torch.zeros((2,), dtype=F32, device=q.device)
+            check(lib.vi_attn_bwd(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0), do.data_ptr(),
+                                  do.stride(0), dq.data_ptr(), dq.stride(0), dk.data_ptr(), dk.stride(0), dv.data_ptr(),
+                                  dv.stride(0), _dt(q), _ptr(s.get('key_mask')), _ptr(s.get('pair_dist')),
+                                  _ptr(s.get('bias_affine')), _ptr(d_affine) if s.get('pair_dist') is not None else None,
+                                  s['B'], ops.HEADS, s['Lq'], s['Lk'], ctx.mask_mode, _stream()), 'vi_attn_bwd')
+            _launched(1)
+        extra = [None] * ctx.n_extra
+        if ctx.n_extra == 2 and d_affine is not None:                   # sprel_linear.weight [1,1], .bias [1]
+            extra = [d_affine[0:1].view(1, 1), d_affine[1:2]]
+        return (None, None, None, None, *grads, *extra)
+
+
+class SmallLinearFn(Function):
+    """t = feat W^T + b for the tiny geometric features (feat_dim <= 16), fp32."""
+
+    @staticmethod
+    def forward(ctx, feat, w, b):
+        feat = feat.contiguous()
+        y = ops.gemm(feat, w.detach().contiguous(), b.detach() if b is not None else None)
+        ctx.save_for_backward(feat)
+        ctx.has_b, ctx.wshape = b is not None, w.shape
+        return y
+
+    @staticmethod
+    def backward(ctx, dt):
+        (feat,) = ctx.saved_tensors
+        dt = dt.contiguous()
+        fd = feat.shape[1]
+        dW = torch.empty(ctx.wshape, dtype=F32, device=dt.device)
+        db = torch.empty((HIDDEN,), dtype=F32, device=dt.device) if ctx.has_b else None
+        check(lib.vi_feat_wgrad(dt.data_ptr(), feat.data_ptr(), fd, dW.data_ptr(), _ptr(db), dt.shape[0], _stream()), 'vi_feat_wgrad')
+        _launched(1)
+        return None, dW, db
+
+
+class GatherRowsFn(Function):
+    """rows = table[idx] (or table[row % period] when idx is None); adjoint = scatter-add."""
+
+    @staticmethod
+    def forward(ctx, table, idx, period, rows):
+        table = table.contiguous()
+        if idx is not None:
+            y32, _ = ops.embed_compose(rows, table.device, idx=idx, table=table)
+        else:
+            y32, _ = ops.embed_compose(rows, table.device, pos_table=table, pos_period=period)
+        ctx.save_for_backward(idx if idx is not None else table.new_empty(0, dtype=torch.int64))
+        ctx.has_idx, ctx.period, ctx.tshape = idx is not None, period, table.shape
+        return y32
+
+    @staticmethod
+    def backward(ctx, dy):
+        (idx,) = ctx.saved_tensors
+        dy = dy.contiguous()
+        dt = torch.zeros(ctx.tshape, dtype=F32, device=dy.device)
+        check(lib.vi_scatter_add_rows(dy.data_ptr(), idx.data_ptr() if ctx.has_idx else None, ctx.period or 1, dt.data_ptr(),
+                                      dy.shape[0], _stream()), 'vi_scatter_add_rows')
+        _launched(1)
+        return dt, None, None, None
+
+
+class SumRowsFn(Function):
+    """y = sum of [rows, 768] tensors + broadcast [768] rows."""
+
+    @staticmethod
+    def forward(ctx, n_full, *tensors):
+        full, consts = tensors[:n_full], tensors[n_full:]
+        rows = full[0].shape[0]
+        if n_full > 3 or len(consts) > 2:
+            raise _lib.VlnImagineError('SumRowsFn: at most 3 row tensors and 2 constant rows')
+        y32, _ = ops.embed_compose(rows, full[0].device, a=full[0].contiguous(),
+                                   a2=full[1].contiguous() if n_full > 1 else None,
+                                   a3=full[2].contiguous() if n_full > 2 else None,
+                                   const_row=consts[0].detach() if len(consts) > 0 else None,
+                                   const_row2=consts[1].detach() if len(consts) > 1 else None)
+        ctx.n_full, ctx.n_const = n_full, len(consts)
+        ctx.needs = [t.requires_grad for t in tensors]
+        return y32
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = dy.contiguous()
+        g = [dy if ctx.needs[i] else None for i in range(ctx.n_full)]
+        cs = None
+        for i in range(ctx.n_const):
+            if ctx.needs[ctx.n_full + i]:
+                cs = colsum(dy) if cs is None else cs
+                g.append(cs)
+            else:
+                g.append(None)
+        return (None, *g)
+
+
+class RowDotFn(Function):
+    """out[r] = x[r] . w[g] + b[g]  (tail of ClsPrediction / NextActionPrediction), grouped rows."""
+
+    @staticmethod
+    def forward(ctx, x, wstack, bstack, ends, n_heads, *params):
+        x = x.contiguous()
+        rows = x.shape[0]
+        out = torch.empty((rows,), dtype=F32, device=x.device)
+        # LayerNorm-free dot: reuse vi_ln_dot's kernel is not possible (it normalises), so run the dot through the
+        # fp32 GEMM entry point per group (N = 1)
+        bounds = [0] + (list(ends) if ends is not None else [rows])
+        for g in range(len(bounds) - 1):
+            r0, r1 = bounds[g], min(bounds[g + 1], rows)
+            ops.gemm(x[r0:r1], wstack[g:g + 1] if wstack.dim() == 2 else wstack.view(1, -1), bstack.view(-1)[g:g + 1],
+                     out=out[r0:r1].view(-1, 1))
+        ctx.save_for_backward(x, wstack)
+        ctx.ends, ctx.n_heads = ends, n_heads
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, wstack = ctx.saved_tensors
+        dout = dout.contiguous()
+        rows = x.shape[0]
+        ends = ctx.ends
+        n_groups = 1 if ends is None else len(ends)
+        dx = torch.empty_like(x)
+        dw = torch.empty((n_groups, HIDDEN), dtype=F32, device=x.device)
+        db = torch.empty((n_groups,), dtype=F32, device=x.device)
+        check(lib.vi_rowdot_bwd(dout.data_ptr(), x.data_ptr(), wstack.data_ptr(), dx.data_ptr(), dw.data_ptr(), db.data_ptr(), rows,
+                                n_groups, _lib.int_array(list(ends)) if ends is not None else None, _stream()), 'vi_rowdot_bwd')
+        _launched(2)
+        pg = [dw[i].view(1, HIDDEN) for i in range(ctx.n_heads)] + [db[i:i + 1] for i in range(ctx.n_heads)]
+        return (dx, None, None, None, None, *pg)
+
+
+class FuseLogitsFn(Function):
+    @staticmethod
+    def forward(ctx, g_raw, l_raw, fuse_raw, gm, gv, nav, gids, cids, B, G, P):
+        g_raw, l_raw = g_raw.contiguous(), l_raw.contiguous()
+        gl, ll, fl = ops.duet_fuse_logits(g_raw, l_raw, fuse_raw, gm, gv, nav, gids, cids, B, G, P)
+        ctx.save_for_backward(g_raw, l_raw, fuse_raw if fuse_raw is not None else g_raw.new_empty(0), gm, gv, nav, gids, cids)
+        ctx.dims, ctx.has_fuse = (B, G, P), fuse_raw is not None
+        return gl, ll, fl
+
+    @staticmethod
+    def backward(ctx, dgl, dll, dfl):
+        g_raw, l_raw, fuse_raw, gm, gv, nav, gids, cids = ctx.saved_tensors
+        B, G, P = ctx.dims
+        c = lambda t: t.contiguous() if t is not None else None      # noqa: E731
+        dgl, dll, dfl = c(dgl), c(dll), c(dfl)
+        dg = torch.empty_like(g_raw)
+        dl = torch.empty_like(l_raw)
+        df = torch.empty((B,), dtype=F32, device=g_raw.device) if ctx.has_fuse else None
+        check(lib.vi_duet_fuse_logits_bwd(g_raw.data_ptr(), l_raw.data_ptr(), fuse_raw.data_ptr() if ctx.has_fuse else None,
+                                          gm.data_ptr(), gv.data_ptr(), nav.data_ptr(), gids.data_ptr(), cids.data_ptr(),
+                                          _ptr(dgl), _ptr(dll), _ptr(dfl), dg.data_ptr(), dl.data_ptr(), _ptr(df), B, G, P,
+                                          _stream()), 'vi_duet_fuse_logits_bwd')
+        _launched(1)
+        return dg, dl, df, None, None, None, None, None, None, None, None
+
+
+class GatherSlotsFn(Function):
+    """rows = src[slot[r]] (unit gather of the imagination slots that take part in the alignment loss)."""
+
+    @staticmethod
+    def forward(ctx, src, unit, slot, R, lowp):
+        y32, y16 = ops.gather_mean(src, unit, slot, R, want16=lowp, want32=not lowp)
+        ctx.save_for_backward(slot)
+        ctx.shape = src.shape
+        return y16 if lowp else y32
+
+    @staticmethod
+    def backward(ctx, dy):
+        (slot,) = ctx.saved_tensors
+        d = torch.zeros(ctx.shape, dtype=F32, device=dy.device)
+        ops.scatter_rows(dy.float().contiguous(), slot, d)               # slots are unique: a plain row scatter
+        return d, None, None, None, None
+
+
+class ScatterSlotsFn(Function):
+    """out = base with rows slot[r] replaced by rows[r] (the projected imaginations written back, vilmodel.py:646)."""
+
+    @staticmethod
+    def forward(ctx, base, rows, slot, unit):
+        out = base.clone()
+        ops.scatter_rows(rows.contiguous(), slot, out)
+        ctx.save_for_backward(slot, unit)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        slot, unit = ctx.saved_tensors
+        dout = dout.contiguous()
+        R = slot.shape[0]
+        drows, _ = ops.gather_mean(dout, unit, slot, R, want16=False)
+        dbase = dout.clone()
+        dbase.index_fill_(0, slot.long(), 0.0)
+        return dbase, drows, None, None
+
+
+class CosineLossFn(Function):
+    @staticmethod
+    def forward(ctx, proj, tgt, R):
+        proj, tgt = proj.contiguous(), tgt.contiguous()
+        loss, _ = ops.cosine_loss(proj, tgt, R, proj.device)
+        ctx.save_for_backward(proj, tgt)
+        ctx.R = R
+        ctx.needs = (proj.requires_grad, tgt.requires_grad)
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        proj, tgt = ctx.saved_tensors
+        dloss = dloss.contiguous().float().view(1)
+        dp = torch.empty_like(proj) if ctx.needs[0] else None
+        dt = torch.empty_like(tgt) if ctx.needs[1] else None
+        check(lib.vi_cosine_loss_bwd(proj.data_ptr(), tgt.data_ptr(), dloss.data_ptr(), _ptr(dp), _ptr(dt), ctx.R, _stream()),
+              'vi_cosine_loss_bwd')
+        _launched(1)
+        return dp, dt, None

@@ -13,8 +13,34 @@ from typing import List, Optional, Sequence
 
 import torch
 
+from . import autograd_ops as ag
 from . import ops
 from .ops import BF16, F32, HIDDEN, EPI_GELU, EPI_NONE, EPI_RELU, MASK_ADD_NEG10000, MASK_NEG_INF  # noqa: F401
+
+
+# ----------------------------------------------------------------------------------------------
+# training switch: while it is on, every block below records autograd nodes whose forward AND backward are
+# libvlnimagine kernels (autograd_ops.py); while it is off the blocks are plain launch sequences
+# ----------------------------------------------------------------------------------------------
+class _Mode:
+    train = False
+
+
+class grad_mode:
+    """with blocks.grad_mode(flag): ...  (set by the host modules once per mode call)"""
+
+    def __init__(self, flag: bool):
+        self.flag = bool(flag)
+
+    def __enter__(self):
+        self.prev, _Mode.train = _Mode.train, self.flag
+
+    def __exit__(self, *a):
+        _Mode.train = self.prev
+
+
+def training() -> bool:
+    return _Mode.train
 
 
 # ----------------------------------------------------------------------------------------------
@@ -61,6 +87,22 @@ class LinearPack:
         v = self._pack.get()
         return (v['w16'] if lowp else v['w32']), v['b']
 
+    def get_t(self, lowp: bool, n_groups: int = 1):
+        """per-group transposed weight [n_groups * K, N] (the B operand of the input-gradient GEMM), cached with
+        the pack"""
+        v = self._pack.get()
+        key = ('t', lowp, n_groups)
+        if key not in v:
+            w = v['w16'] if lowp else v['w32']
+            n = w.shape[0] // n_groups
+            with torch.no_grad():
+                v[key] = torch.cat([ag.transpose(w[g * n:(g + 1) * n]) for g in range(n_groups)], 0).contiguous()
+        return v[key]
+
+    def grad_sources(self):
+        """the parameters in the order LinearFn.backward returns their gradients"""
+        return self.weights + ([b for b in self.biases if b is not None] if self.biases else [])
+
 
 class StackPack:
     """[n, ...] stack of same-shaped vectors (LayerNorm gains/biases, head vectors) for grouped row kernels."""
@@ -85,6 +127,9 @@ class LNPack:
     def get(self):
         return self.g.get(), self.b.get()
 
+    def grad_sources(self):
+        return self.g.tensors + self.b.tensors
+
 
 # ----------------------------------------------------------------------------------------------
 # activations
@@ -108,6 +153,7 @@ class Stream:
     group: int = 0                  # weight block this stream uses
     pair_dist: Optional[torch.Tensor] = None   # fp32 [B, L, L] graph distances (GASA) or None
     bias_affine: Optional[torch.Tensor] = None  # device {w, b}
+    affine_params: Optional[tuple] = None       # (sprel_linear.weight, .bias): gradient routing in training
 
     @property
     def rows(self):
@@ -140,6 +186,9 @@ def _ctx_buffer(rows: int, like: torch.Tensor, streams) -> torch.Tensor:
 
 
 def layer_norm(x32, res32, ln: LNPack, eps, lowp, ends=None) -> Act:
+    if _Mode.train:
+        y32, y16 = ag.layer_norm(x32, res32, ln, eps, lowp, ends)
+        return Act(y32, y16)
     g, b = ln.get()
     y32, y16 = ops.add_ln(x32, res32, g, b, eps, want16=lowp, group_row_end=ends)
     return Act(y32, y16)
@@ -167,6 +216,18 @@ def self_attn_ffn(x: Act, pk: SelfFFNPack, streams: List[Stream], ends, lowp: bo
     Reference: BertLayer, VLN-DUET/map_nav_src/models/vilmodel.py:196-209 (and :80-194)."""
     xin = x.operand(lowp)
     rows = xin.shape[0]
+    if _Mode.train:
+        qkv = ag.linear(xin, pk.qkv, lowp, ends=ends)
+        spec, extras = [], ()
+        for s in streams:
+            spec.append(dict(q=(0, s.row0, 0), k=(0, s.row0, HIDDEN), v=(0, s.row0, 2 * HIDDEN), B=s.B, Lq=s.L, Lk=s.L,
+                             key_mask=s.mask, pair_dist=s.pair_dist, bias_affine=s.bias_affine, out_row0=s.row0))
+            if s.pair_dist is not None and s.affine_params is not None:
+                extras = tuple(s.affine_params)
+        ctx = ag.AttentionFn.apply(spec, rows, MASK_ADD_NEG10000, 1, qkv, *extras)
+        ao = ag.linear(ctx, pk.o, lowp, residual=x.f32, out_dtype=F32, ends=ends)
+        y = layer_norm(ao, None, pk.ln1, eps, lowp, ends)
+        return ffn(y, pk.w1, pk.w2, pk.ln2, ends, lowp, eps)
     w, b = pk.qkv.get(lowp)
     qkv = ops.gemm(xin, w, b, group_row_end=ends)                      # [rows, 2304]
     ctx = _ctx_buffer(rows, xin, streams)
@@ -183,6 +244,10 @@ def self_attn_ffn(x: Act, pk: SelfFFNPack, streams: List[Stream], ends, lowp: bo
 
 
 def ffn(y: Act, w1: LinearPack, w2: LinearPack, ln2: LNPack, ends, lowp: bool, eps=1e-12) -> Act:
+    if _Mode.train:
+        h = ag.ActFn.apply(ag.linear(y.operand(lowp), w1, lowp, ends=ends), EPI_GELU)
+        fo = ag.linear(h, w2, lowp, residual=y.f32, out_dtype=F32, ends=ends)
+        return layer_norm(fo, None, ln2, eps, lowp, ends)
     w, b = w1.get(lowp)
     h = ops.gemm(y.operand(lowp), w, b, epilogue=EPI_GELU, group_row_end=ends)   # [rows, 3072]
     w, b = w2.get(lowp)
@@ -208,6 +273,13 @@ def cross_attn(x: Act, kv: torch.Tensor, kv_col0: Sequence[int], ctx_len: int, c
     Reference: BertXAttention, VLN-DUET/map_nav_src/models/vilmodel.py:302-364."""
     xin = x.operand(lowp)
     rows = xin.shape[0]
+    if _Mode.train:
+        q = ag.linear(xin, pk.q, lowp, ends=ends)
+        spec = [dict(q=(0, s.row0, 0), k=(1, 0, c0), v=(1, 0, c0 + HIDDEN), B=s.B, Lq=s.L, Lk=ctx_len, key_mask=ctx_mask,
+                     out_row0=s.row0) for s, c0 in zip(streams, kv_col0)]
+        ctx = ag.AttentionFn.apply(spec, rows, MASK_ADD_NEG10000, 2, q, kv)
+        ao = ag.linear(ctx, pk.o, lowp, residual=x.f32, out_dtype=F32, ends=ends)
+        return layer_norm(ao, None, pk.ln, eps, lowp, ends)
     w, b = pk.q.get(lowp)
     q = ops.gemm(xin, w, b, group_row_end=ends)
     ctx = _ctx_buffer(rows, xin, streams)
@@ -221,7 +293,58 @@ def cross_attn(x: Act, kv: torch.Tensor, kv_col0: Sequence[int], ctx_len: int, c
 def as_act(x32: torch.Tensor, lowp: bool) -> Act:
     """fp32 rows -> activation pair (adds the bf16 operand copy in bf16 mode)."""
     x32 = x32.contiguous()
+    if _Mode.train:
+        return Act(x32, ag.CastBf16Fn.apply(x32) if lowp else None)
     return Act(x32, ops.cast_bf16(x32) if lowp else None)
+
+
+def operand(x32: torch.Tensor, lowp: bool) -> torch.Tensor:
+    """fp32 rows -> GEMM operand of the current precision (differentiable in training)"""
+    x32 = x32.contiguous()
+    if not lowp:
+        return x32
+    return ag.CastBf16Fn.apply(x32) if _Mode.train else ops.cast_bf16(x32)
+
+
+def embed(rows: int, device, *, a=None, a_ln=None, feat=None, feat_lin=None, feat_ln=None, idx=None, table=None,
+          pos_table=None, pos_period=0, const_rows=(), out_ln=None, eps=1e-12, lowp=False, y32=None, y16=None) -> Act:
+    """Input-embedding composer  LN_out([LN_a](a) + LN_f(W feat + b) + table[idx] + pos[row % period] + consts).
+    *_ln are nn.LayerNorm-like parameter holders, feat_lin an nn.Linear-like holder.  Inference: ONE fused kernel
+    (vi_embed_compose).  Training: the same sum built from differentiable primitives (autograd_ops)."""
+    ln_pair = lambda m: (m.weight, m.bias) if m is not None else None      # noqa: E731
+    if not _Mode.train:
+        consts = list(const_rows) + [None, None]
+        o32, o16 = ops.embed_compose(rows, device, a=a, a_ln=ln_pair(a_ln), feat=feat,
+                                     feat_w=feat_lin.weight if feat_lin is not None else None,
+                                     feat_b=feat_lin.bias if feat_lin is not None else None, feat_ln=ln_pair(feat_ln),
+                                     idx=idx, table=table, pos_table=pos_table, pos_period=pos_period,
+                                     const_row=consts[0], const_row2=consts[1], out_ln=ln_pair(out_ln), eps=eps,
+                                     y32=y32, y16=y16, want16=lowp and y16 is None and (y32 is None))
+        return Act(o32, o16)
+    terms = []
+    if a is not None:
+        if a_ln is not None:
+            t, _ = ag.LayerNormFn.apply(a, None, a_ln.weight, a_ln.bias, eps, False, None, 2, a_ln.weight, a_ln.bias)
+            terms.append(t)
+        else:
+            terms.append(a)
+    if feat is not None:
+        t = ag.SmallLinearFn.apply(feat, feat_lin.weight, feat_lin.bias)
+        if feat_ln is not None:
+            t, _ = ag.LayerNormFn.apply(t, None, feat_ln.weight, feat_ln.bias, eps, False, None, 2, feat_ln.weight, feat_ln.bias)
+        terms.append(t)
+    if idx is not None:
+        terms.append(ag.GatherRowsFn.apply(table, idx, 0, rows))
+    if pos_table is not None:
+        terms.append(ag.GatherRowsFn.apply(pos_table, None, pos_period, rows))
+    consts = list(const_rows)
+    while len(terms) > 3:                                     # the fused sum kernel takes three row tensors
+        terms = [ag.SumRowsFn.apply(3, *terms[:3])] + terms[3:]
+    s = ag.SumRowsFn.apply(len(terms), *terms, *consts) if (len(terms) > 1 or consts) else terms[0]
+    if out_ln is not None:
+        o32, o16 = ag.LayerNormFn.apply(s, None, out_ln.weight, out_ln.bias, eps, lowp, None, 2, out_ln.weight, out_ln.bias)
+        return Act(o32, o16 if lowp else None)
+    return Act(s, ag.CastBf16Fn.apply(s) if lowp else None)
 
 
 def mask_u8(m: Optional[torch.Tensor]):
@@ -250,6 +373,14 @@ def pano_layer(x32: torch.Tensor, pk: PanoLayerPack, B: int, L: int, key_mask, l
     -inf kind of nn.MultiheadAttention.  Reference: TransformerEncoderLayer.forward_pre,
     VLN-DUET/map_nav_src/models/transformer.py:170-182."""
     h = layer_norm(x32, None, pk.norm1, eps, lowp)
+    if _Mode.train:
+        qkv = ag.linear(h.operand(lowp), pk.qkv, lowp)
+        spec = [dict(q=(0, 0, 0), k=(0, 0, HIDDEN), v=(0, 0, 2 * HIDDEN), B=B, Lq=L, Lk=L, key_mask=key_mask, out_row0=0)]
+        ctx = ag.AttentionFn.apply(spec, B * L, MASK_NEG_INF, 1, qkv)
+        x32 = ag.linear(ctx, pk.o, lowp, residual=x32, out_dtype=F32)
+        h = layer_norm(x32, None, pk.norm2, eps, lowp)
+        f = ag.ActFn.apply(ag.linear(h.operand(lowp), pk.w1, lowp), EPI_GELU)
+        return ag.linear(f, pk.w2, lowp, residual=x32, out_dtype=F32)
     w, b = pk.qkv.get(lowp)
     qkv = ops.gemm(h.operand(lowp), w, b)
     ctx = ops.attention(qkv[:, 0:HIDDEN], qkv[:, HIDDEN:2 * HIDDEN], qkv[:, 2 * HIDDEN:3 * HIDDEN], B, L, L,
@@ -276,6 +407,11 @@ class ClsHeadPack:
 
 def cls_head(x: torch.Tensor, pk: ClsHeadPack, lowp: bool, ends=None, eps=1e-12) -> torch.Tensor:
     """x [rows, K] operand (bf16 or fp32) -> raw logit per row (fp32)."""
+    if _Mode.train:
+        h = ag.ActFn.apply(ag.linear(x, pk.w0, lowp, out_dtype=F32, ends=ends), EPI_RELU)
+        y32, _ = ag.layer_norm(h, None, pk.ln, eps, False, ends)
+        n = len(pk.w1.tensors)
+        return ag.RowDotFn.apply(y32, pk.w1.get(), pk.b1.get(), ends, n, *pk.w1.tensors, *pk.b1.tensors)
     w, b = pk.w0.get(lowp)
     h = ops.gemm(x, w, b, epilogue=EPI_RELU, out_dtype=F32, group_row_end=ends)
     g, be = pk.ln.get()

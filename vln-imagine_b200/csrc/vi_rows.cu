@@ -138,6 +138,8 @@ __global__ void __launch_bounds__(EMBED_WARPS * 32) embed_compose_kernel(const v
       if (p.a_gamma) row_layernorm(t, p.a_gamma, p.a_beta, p.eps, lane);
       row_acc(acc, t);
     }
+    if (p.a2) row_add(acc, p.a2 + row * D, lane);
+    if (p.a3) row_add(acc, p.a3 + row * D, lane);
     if (p.feat) {
       Row t;
       if (p.feat_b) row_load(t, p.feat_b, lane);
@@ -449,6 +451,7 @@ extern "C" int vi_embed_compose(const vi_embed_args* args, vi_stream_t stream) {
   VI_CHECK_ARG(!p.a_gamma || p.a_beta, "vi_embed_compose: a_gamma without a_beta");
   VI_CHECK_ARG(!p.feat_gamma || p.feat_beta, "vi_embed_compose: feat_gamma without feat_beta");
   VI_CHECK_ARG(!p.out_gamma || p.out_beta, "vi_embed_compose: out_gamma without out_beta");
+  VI_CHECK_ARG(aligned16(p.a2) && aligned16(p.a3), "vi_embed_compose: a2 / a3 must be 16-byte aligned");
   VI_CHECK_ARG(aligned16(p.a) && aligned16(p.table) && aligned16(p.pos_table) && aligned16(p.const_row) &&
                    aligned16(p.const_row2) && aligned16(p.y32) && ((uintptr_t)p.y16 & 7) == 0,
                "vi_embed_compose: row operands must be 16-byte aligned");

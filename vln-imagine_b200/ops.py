@@ -262,7 +262,7 @@ def add_ln(a: torch.Tensor, b: Optional[torch.Tensor], gamma: torch.Tensor, beta
     return y32, y16
 
 
-def embed_compose(rows: int, device, *, a=None, a_ln=None, feat=None, feat_w=None, feat_b=None, feat_ln=None,
+def embed_compose(rows: int, device, *, a=None, a2=None, a3=None, a_ln=None, feat=None, feat_w=None, feat_b=None, feat_ln=None,
                   idx=None, table=None, pos_table=None, pos_period=0, const_row=None, const_row2=None,
                   out_ln=None, eps=1e-12, y32=None, y16=None, want16=False, want32=True):
     """See vi_embed_compose.  *_ln are (gamma, beta) pairs.  y32 / y16 may be preallocated row views."""
@@ -271,7 +271,7 @@ def embed_compose(rows: int, device, *, a=None, a_ln=None, feat=None, feat_w=Non
     if y16 is None and want16:
         y16 = torch.empty((rows, HIDDEN), dtype=BF16, device=device)
     args = _lib.EmbedArgs()
-    args.a = _ptr(a)
+    args.a, args.a2, args.a3 = _ptr(a), _ptr(a2), _ptr(a3)
     if a_ln is not None:
         args.a_gamma, args.a_beta = a_ln[0].data_ptr(), a_ln[1].data_ptr()
     if feat is not None:
