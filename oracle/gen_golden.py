@@ -160,6 +160,94 @@ def run_duet(args):
         json.dump(report, f, indent=1)
 
 
+GRAD_SAMPLES = 32
+
+
+def grad_sample_index(name, numel):
+    """the seeded element positions of parameter ``name`` whose gradient values the fixture keeps"""
+    import zlib
+    g = np.random.Generator(np.random.PCG64([977, zlib.crc32(name.encode())]))
+    return g.integers(0, numel, size=GRAD_SAMPLES)
+
+
+def nav_targets_of(ep):
+    """teacher action per episode for the fixture: the LAST admissible graph node (valid and unvisited), so the
+    cross-entropy gradient reaches the local->global fusion; node 0 ([stop]) when there is no other"""
+    ok = ep['gmap_masks'] & ~ep['gmap_visited_masks']
+    G = ok.shape[1]
+    idx = torch.arange(G, device=ok.device)[None, :].expand_as(ok)
+    return torch.where(ok, idx, torch.zeros_like(idx)).max(1).values
+
+
+def duet_train_step(model, ep, call):
+    """One fine-tuning iteration of the reference agent on one navigation step (r2r/agent.py:407-449 prelude,
+    :466-541 step, :617-622 loss):  loss = CE_sum(fused_logits, teacher) / B + cosine_weight * aux_loss  with
+    cosine_weight 0.5 (scripts/run_r2r.sh:78); vp_img_embeds = [0 ; pano_embeds] as _nav_vp_variable builds it
+    (r2r/agent.py:173-186).  ``call(mode, batch)`` is the model under test."""
+    txt = call('language', {'txt_ids': ep['txt_ids'], 'txt_masks': ep['txt_masks']})
+    img = call('imagine', {'imagine_feats': ep['imagine_feats'], 'imagine_masks': None})
+    aux, img2 = call('align_with_contrastive_loss', {
+        'align_txt_embeds': txt, 'txt_masks': ep['txt_masks'], 'align_imagine_embeds': img,
+        'imagine_masks': ep['imagine_masks'], 'sub_instr_segs': ep['sub_instr_segs'],
+        'sub_instr_imag_flag': ep['sub_instr_imag_flag'], 'noun_phrase_segs': ep['noun_phrase_segs'],
+        'obs_instr_ids': ep['obs_instr_ids']})
+    pano, pano_masks = call('panorama', {'view_img_fts': ep['view_img_fts'], 'obj_img_fts': None,
+                                         'loc_fts': ep['loc_fts'], 'nav_types': ep['nav_types'],
+                                         'view_lens': ep['view_lens'], 'obj_lens': None})
+    vp_img = torch.cat([torch.zeros_like(pano[:, :1]), pano], 1)
+    nav = call('navigation', {k: ep[k] for k in (
+        'txt_masks', 'gmap_img_embeds', 'gmap_step_ids', 'gmap_pos_fts', 'gmap_masks', 'gmap_pair_dists',
+        'gmap_visited_masks', 'gmap_vpids', 'vp_pos_fts', 'vp_masks', 'vp_nav_masks', 'vp_cand_vpids',
+        'imagine_masks')} | {'txt_embeds': txt, 'imagine_embeds': img2, 'vp_obj_masks': None, 'vp_img_embeds': vp_img})
+    tgt = nav_targets_of(ep).to(nav['fused_logits'].device)
+    ce = torch.nn.functional.cross_entropy(nav['fused_logits'], tgt, reduction='sum') / tgt.shape[0]
+    loss = ce + 0.5 * aux
+    return loss, ce, aux, nav
+
+
+class _Clone(torch.nn.Module):
+    """harness-side stand-in for Dropout(p) at p = 0 that keeps the reference's backward alive"""
+
+    def forward(self, x):
+        return x.clone()
+
+
+def run_duet_grads(args):
+    """Gradient fixtures for BASELINE.json cfg-4 from the REAL reference: every parameter's gradient L2 norm and
+    GRAD_SAMPLES seeded element values, plus the loss terms."""
+    from importlib import import_module
+    synth = import_module('vln_imagine_b200.synth')
+    ref = build_reference('duet')
+    ref.contrastive_alignment_model.image_proj.dropout = _Clone()
+    manifest = {k: list(v.shape) for k, v in ref.state_dict().items()}
+    for tag, shape, seed, stress in [('tiny', synth.TINY, 7, True), ('cfg1', synth.CFG1, 1234, False)]:
+        sd = synth.synth_state_dict(manifest, seed=0, gasa_stress=stress)
+        ref.load_state_dict(sd)
+        ref.zero_grad(set_to_none=True)
+        ep = synth.to_torch(synth.duet_episode(shape, seed))
+        loss, ce, aux, nav = duet_train_step(ref, ep, lambda mode, batch: ref(mode, batch))
+        loss.backward()
+        out = {'loss': loss.detach(), 'ce': ce.detach(), 'aux': aux.detach(), 'fused_logits': nav['fused_logits'].detach(),
+               'nav_targets': nav_targets_of(ep)}
+        names, norms, samples = [], [], []
+        for name, p in ref.named_parameters():
+            assert p.grad is not None, name
+            names.append(name)
+            g = p.grad.detach().double().reshape(-1)
+            norms.append(float(g.norm()))
+            samples.append(g[torch.from_numpy(grad_sample_index(name, g.numel()))].float().numpy())
+        out['grad_norms'] = np.asarray(norms, np.float64)
+        out['grad_samples'] = np.stack(samples)
+        for name in ('global_encoder.sprel_linear.weight', 'global_encoder.sprel_linear.bias',
+                     'imagine_embeddings.type_embedding.weight', 'embeddings.LayerNorm.weight',
+                     'sap_fuse_linear.net.3.weight', 'local_encoder.vp_pos_embeddings.0.weight'):
+            out['full::' + name] = dict(ref.named_parameters())[name].grad.detach()
+        np.savez(os.path.join(GOLD, 'duet_grads_%s.npz' % tag), **_np(out))
+        with open(os.path.join(GOLD, 'duet_grads_names.json'), 'w') as f:
+            json.dump(names, f, indent=0)
+        print(tag, 'loss', float(loss), 'ce', float(ce), 'aux', float(aux), 'max grad norm', max(norms), 'min', min(norms))
+
+
 def run_hamt(args):
     from importlib import import_module
     synth = import_module('vln_imagine_b200.synth')
@@ -210,7 +298,12 @@ def run_hamt(args):
 if __name__ == '__main__':
     ap = argparse.ArgumentParser()
     ap.add_argument('--model', choices=['duet', 'hamt'], required=True)
+    ap.add_argument('--grads', action='store_true', help='write the gradient fixtures (cfg-4) instead')
     a = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
-    (run_duet if a.model == 'duet' else run_hamt)(a)
+    if a.grads:
+        assert a.model == 'duet'
+        run_duet_grads(a)
+    else:
+        (run_duet if a.model == 'duet' else run_hamt)(a)

@@ -1,0 +1,353 @@
+"""Backward-pass kernels (fine-tuning path, BASELINE.json cfg-4) against torch.autograd of the same op in fp32.
+
+Every check goes through the autograd wrappers of vln-imagine_b200/autograd_ops.py, i.e. through the C ABI.
+Tolerances: fp32 kernels 1e-4 (max-norm relative); bf16 operand kernels 2e-2 against the fp32 reference.
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def ag(lib_built):
+    import importlib
+    o = importlib.import_module('vln_imagine_b200.ops')
+    o.ensure_init(torch.zeros(1, device='cuda'))
+    return importlib.import_module('vln_imagine_b200.autograd_ops')
+
+
+@pytest.fixture(scope='module')
+def blocks(ag):
+    import importlib
+    return importlib.import_module('vln_imagine_b200.blocks')
+
+
+def relerr(a, b):
+    a, b = a.float(), b.float()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-20))
+
+
+def _rand(*shape, scale=1.0, seed=0):
+    g = torch.Generator(device='cpu').manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).cuda()
+
+
+class _Lin:
+    """nn.Linear-like parameter holder"""
+
+    def __init__(self, n, k, seed, bias=True):
+        self.weight = _rand(n, k, scale=0.05, seed=seed).requires_grad_()
+        self.bias = _rand(n, scale=0.1, seed=seed + 1).requires_grad_() if bias else None
+
+
+class _LN:
+    def __init__(self, seed):
+        self.weight = (1 + _rand(768, scale=0.1, seed=seed)).requires_grad_()
+        self.bias = _rand(768, scale=0.1, seed=seed + 1).requires_grad_()
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('rows,cols,pad', [(37, 768, 64), (300, 2304, 320), (64, 64, 64), (1000, 7, 1000)])
+def test_transpose_and_colsum(ag, dtype, rows, cols, pad):
+    x = _rand(rows, cols, seed=1).to(dtype)
+    t = ag.transpose(x, pad)
+    assert t.shape == (cols, pad)
+    assert torch.equal(t[:, :rows], x.t())
+    assert float(t[:, rows:].float().abs().sum()) == 0.0
+    view = _rand(rows, cols + 24, seed=2).to(dtype)[:, 8:8 + cols]         # strided source
+    assert torch.equal(ag.transpose(view, pad)[:, :rows], view.t())
+    cs = ag.colsum(x)
+    assert relerr(cs, x.float().sum(0)) < 1e-5
+
+
+@pytest.mark.parametrize('act', [1, 2])
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_activation_fwd_bwd(ag, act, dtype):
+    x = _rand(333, 3072, seed=3).to(dtype).requires_grad_()
+    dy = _rand(333, 3072, seed=4).to(dtype)
+    y = ag.ActFn.apply(x, act)
+    y.backward(dy)
+    xr = x.detach().float().requires_grad_()
+    yr = F.gelu(xr) if act == 1 else F.relu(xr)
+    yr.backward(dy.float())
+    tol = 1e-5 if dtype == torch.float32 else 1e-2
+    assert relerr(y, yr) < tol
+    assert relerr(x.grad, xr.grad) < tol
+
+
+@pytest.mark.parametrize('lowp', [False, True])
+@pytest.mark.parametrize('grouped', [False, True])
+@pytest.mark.parametrize('residual', [False, True])
+def test_layer_norm_bwd(ag, blocks, lowp, grouped, residual):
+    rows = 1024 + 777 if grouped else 1000
+    ends = [1024, rows] if grouped else None
+    lns = [_LN(10), _LN(20)] if grouped else [_LN(10)]
+    pack = blocks.LNPack(lns)
+    a = _rand(rows, 768, seed=5).requires_grad_()
+    b = _rand(rows, 768, seed=6).requires_grad_() if residual else None
+    d32 = _rand(rows, 768, seed=7)
+    d16 = _rand(rows, 768, seed=8).bfloat16() if lowp else None
+    y32, y16 = ag.layer_norm(a, b, pack, 1e-12, lowp, ends)
+    if lowp:
+        torch.autograd.backward([y32, y16], [d32, d16])
+    else:
+        y32.backward(d32)
+    # torch reference
+    ar = a.detach().clone().requires_grad_()
+    br = b.detach().clone().requires_grad_() if residual else None
+    pr = [(l.weight.detach().clone().requires_grad_(), l.bias.detach().clone().requires_grad_()) for l in lns]
+    xs = ar + br if residual else ar
+    bounds = [0] + (ends or [rows])
+    yr = torch.cat([F.layer_norm(xs[bounds[i]:bounds[i + 1]], (768,), pr[i][0], pr[i][1], 1e-12) for i in range(len(lns))], 0)
+    dy = d32 + (d16.float() if lowp else 0)
+    yr.backward(dy)
+    assert relerr(y32, yr) < 1e-5
+    assert relerr(a.grad, ar.grad) < 1e-4
+    if residual:
+        assert relerr(b.grad, br.grad) < 1e-4
+    for l, (gw, gb) in zip(lns, pr):
+        assert relerr(l.weight.grad, gw.grad) < 1e-4
+        assert relerr(l.bias.grad, gb.grad) < 1e-4
+
+
+@pytest.mark.parametrize('lowp', [False, True])
+@pytest.mark.parametrize('case', ['plain', 'residual', 'grouped', 'nobias', 'smallM'])
+def test_linear_bwd(ag, blocks, lowp, case):
+    """dX = dY W (dgrad), dW = dY^T X (wgrad on transposed operands), db = colsum(dY); grouped rows -> per-group
+    weight gradients"""
+    K, N = 768, 1536 if case != 'grouped' else 768
+    M = {'plain': 1000, 'residual': 1920, 'grouped': 2048 + 333, 'nobias': 512, 'smallM': 5}[case]
+    ends = [2048, M] if case == 'grouped' else None
+    lins = [_Lin(N, K, 30, bias=case != 'nobias')] + ([_Lin(N, K, 40)] if case == 'grouped' else [])
+    pack = blocks.LinearPack([l.weight for l in lins], [l.bias for l in lins])
+    x32 = _rand(M, K, seed=9)
+    x = (x32.bfloat16() if lowp else x32).requires_grad_()
+    res = _rand(M, N, seed=10).requires_grad_() if case == 'residual' else None
+    dy = _rand(M, N, seed=11)
+    y = ag.linear(x, pack, lowp, residual=res, out_dtype=torch.float32, ends=ends)
+    y.backward(dy)
+    xr = x.detach().float().requires_grad_()
+    rr = res.detach().clone().requires_grad_() if res is not None else None
+    pr = [(l.weight.detach().clone().requires_grad_(), l.bias.detach().clone().requires_grad_() if l.bias is not None else None)
+          for l in lins]
+    if lowp:       # the kernel rounds W (and dY for the gradient GEMMs) to bf16: the reference uses the rounded weight
+        wq = [w.detach().bfloat16().float().requires_grad_() for w, _ in pr]
+    else:
+        wq = [w for w, _ in pr]
+    bounds = [0] + (ends or [M])
+    yr = torch.cat([F.linear(xr[bounds[i]:bounds[i + 1]], wq[i], pr[i][1]) for i in range(len(lins))], 0)
+    if rr is not None:
+        yr = yr + rr
+    yr.backward(dy)
+    tol = 2e-2 if lowp else 1e-4
+    assert relerr(y, yr) < (2e-3 if lowp else 1e-4)
+    assert relerr(x.grad, xr.grad) < tol
+    if rr is not None:
+        assert relerr(res.grad, rr.grad) < 1e-6
+    for l, w, (_, b) in zip(lins, wq, pr):
+        assert relerr(l.weight.grad, w.grad) < tol
+        if b is not None:
+            assert relerr(l.bias.grad, b.grad) < tol
+
+
+def _torch_attention(q, k, v, B, Lq, Lk, key_mask, dist, aw, ab, neg_inf):
+    qh = q.view(B, Lq, 12, 64).transpose(1, 2)
+    kh = k.view(B, Lk, 12, 64).transpose(1, 2)
+    vh = v.view(B, Lk, 12, 64).transpose(1, 2)
+    s = qh @ kh.transpose(-1, -2) / 8.0
+    if key_mask is not None:
+        if neg_inf:
+            s = s.masked_fill(~key_mask[:, None, None, :], float('-inf'))
+        else:
+            s = s + (~key_mask)[:, None, None, :].float() * -10000.0
+    if dist is not None:
+        s = s + (dist * aw + ab)[:, None]
+    p = torch.softmax(s, -1)
+    return (p @ vh).transpose(1, 2).reshape(B * Lq, 768)
+
+
+@pytest.mark.parametrize('lowp', [False, True])
+@pytest.mark.parametrize('case', ['self_gasa', 'cross', 'pano_neg_inf'])
+def test_attention_bwd(ag, case, lowp):
+    from vln_imagine_b200.ops import MASK_ADD_NEG10000, MASK_NEG_INF
+    B = 5
+    dt = torch.bfloat16 if lowp else torch.float32
+    if case == 'cross':
+        Lq, Lk = 30, 85
+    elif case == 'self_gasa':
+        Lq = Lk = 30
+    else:
+        Lq = Lk = 36
+    lens = torch.tensor([Lk, Lk // 2, 3, Lk - 1, 7])
+    key_mask = (torch.arange(Lk)[None, :] < lens[:, None]).cuda()
+    gasa = case == 'self_gasa'
+    dist = (_rand(B, Lq, Lk, seed=12).abs() * 5) if gasa else None
+    aw = torch.tensor([[-0.5]], device='cuda', requires_grad=True)
+    ab = torch.tensor([0.1], device='cuda', requires_grad=True)
+    affine = torch.stack([aw.detach().view(()), ab.detach().view(())]).contiguous()
+    mode = MASK_NEG_INF if case == 'pano_neg_inf' else MASK_ADD_NEG10000
+    dout = _rand(B * Lq, 768, seed=13).to(dt)
+    km = key_mask.view(torch.uint8)
+    if case == 'cross':
+        q = _rand(B * Lq, 768, seed=14).to(dt).requires_grad_()
+        kv = _rand(B * Lk, 1536, seed=15).to(dt).requires_grad_()
+        spec = [dict(q=(0, 0, 0), k=(1, 0, 0), v=(1, 0, 768), B=B, Lq=Lq, Lk=Lk, key_mask=km, out_row0=0)]
+        out = ag.AttentionFn.apply(spec, B * Lq, mode, 2, q, kv)
+        out.backward(dout)
+        qr, kvr = q.detach().float().requires_grad_(), kv.detach().float().requires_grad_()
+        ref = _torch_attention(qr, kvr[:, :768], kvr[:, 768:], B, Lq, Lk, key_mask, None, None, None, False)
+        ref.backward(dout.float())
+        got, want = [q.grad, kv.grad], [qr.grad, kvr.grad]
+    else:
+        qkv = _rand(B * Lq, 2304, seed=16).to(dt).requires_grad_()
+        spec = [dict(q=(0, 0, 0), k=(0, 0, 768), v=(0, 0, 1536), B=B, Lq=Lq, Lk=Lk, key_mask=km, pair_dist=dist,
+                     bias_affine=affine if gasa else None, out_row0=0)]
+        extras = (aw, ab) if gasa else ()
+        out = ag.AttentionFn.apply(spec, B * Lq, mode, 1, qkv, *extras)
+        out.backward(dout)
+        r = qkv.detach().float().requires_grad_()
+        awr, abr = aw.detach().clone().requires_grad_(), ab.detach().clone().requires_grad_()
+        ref = _torch_attention(r[:, :768], r[:, 768:1536], r[:, 1536:], B, Lq, Lk, key_mask, dist,
+                               awr.view(()) if gasa else None, abr.view(()) if gasa else None, case == 'pano_neg_inf')
+        ref.backward(dout.float())
+        got, want = [qkv.grad], [r.grad]
+        if gasa:
+            got += [aw.grad, ab.grad]
+            want += [awr.grad, abr.grad]
+    tol = 2e-2 if lowp else 2e-4
+    assert relerr(out, ref) < (1e-2 if lowp else 1e-4)
+    for g, w in zip(got, want):
+        assert g.shape == w.shape
+        if float(w.abs().max()) < 1e-6 * float(want[0].abs().max()):
+            # the GASA offset shifts every score of a row equally: its gradient is analytically zero
+            assert float(g.abs().max()) < 1e-3 * float(want[0].abs().max())
+        else:
+            assert relerr(g, w) < tol
+
+
+def test_embedding_pieces_bwd(ag):
+    """small-feature linear, row gather (table / position) and the row sum with broadcast constants"""
+    rows = 700
+    feat = _rand(rows, 7, seed=17)
+    lin = _Lin(768, 7, 50)
+    t = ag.SmallLinearFn.apply(feat, lin.weight, lin.bias)
+    table = _rand(100, 768, seed=18).requires_grad_()
+    idx = torch.randint(0, 100, (rows,), generator=torch.Generator().manual_seed(1)).cuda()
+    pos = _rand(512, 768, seed=19).requires_grad_()
+    g1 = ag.GatherRowsFn.apply(table, idx, 0, rows)
+    g2 = ag.GatherRowsFn.apply(pos, None, 35, rows)
+    c = _rand(768, seed=20).requires_grad_()
+    s = ag.SumRowsFn.apply(3, t, g1, g2, c)
+    dy = _rand(rows, 768, seed=21)
+    s.backward(dy)
+    w, b, tb, ps, cr = [x.detach().clone().requires_grad_() for x in (lin.weight, lin.bias, table, pos, c)]
+    ref = F.linear(feat, w, b) + tb[idx] + ps[torch.arange(rows, device='cuda') % 35] + cr
+    ref.backward(dy)
+    assert relerr(s, ref) < 1e-5
+    for got, want in [(lin.weight.grad, w.grad), (lin.bias.grad, b.grad), (table.grad, tb.grad), (pos.grad, ps.grad),
+                      (c.grad, cr.grad)]:
+        assert relerr(got, want) < 1e-4
+
+
+@pytest.mark.parametrize('grouped', [False, True])
+def test_rowdot_bwd(ag, grouped):
+    rows = 1024 + 300 if grouped else 500
+    ends = [1024, rows] if grouped else None
+    n = 2 if grouped else 1
+    ws = [_rand(1, 768, scale=0.1, seed=60 + i).requires_grad_() for i in range(n)]
+    bs = [_rand(1, scale=0.1, seed=70 + i).requires_grad_() for i in range(n)]
+    x = _rand(rows, 768, seed=22).requires_grad_()
+    wst = torch.stack([w.detach().view(-1) for w in ws]).contiguous() if grouped else ws[0].detach().view(-1).contiguous()
+    bst = torch.cat([b.detach() for b in bs]).contiguous()
+    out = ag.RowDotFn.apply(x, wst, bst, ends, n, *ws, *bs)
+    dout = _rand(rows, seed=23)
+    out.backward(dout)
+    xr = x.detach().clone().requires_grad_()
+    wr = [w.detach().clone().requires_grad_() for w in ws]
+    br = [b.detach().clone().requires_grad_() for b in bs]
+    bounds = [0] + (ends or [rows])
+    ref = torch.cat([F.linear(xr[bounds[i]:bounds[i + 1]], wr[i], br[i]).view(-1) for i in range(n)])
+    ref.backward(dout)
+    assert relerr(out, ref) < 1e-5
+    assert relerr(x.grad, xr.grad) < 1e-5
+    for i in range(n):
+        assert relerr(ws[i].grad, wr[i].grad) < 1e-4
+        assert relerr(bs[i].grad, br[i].grad) < 1e-4
+
+
+def test_cosine_loss_bwd(ag):
+    R = 237
+    p = _rand(R, 768, seed=24).requires_grad_()
+    t = _rand(R, 768, seed=25).requires_grad_()
+    loss = ag.CosineLossFn.apply(p, t, R)
+    (loss * 0.5).backward()
+    pr, tr = p.detach().clone().requires_grad_(), t.detach().clone().requires_grad_()
+    ref = (1 - F.cosine_similarity(pr, tr, dim=-1)).mean()
+    (ref * 0.5).backward()
+    assert abs(float(loss) - float(ref)) < 1e-5
+    assert relerr(p.grad, pr.grad) < 1e-4
+    assert relerr(t.grad, tr.grad) < 1e-4
+
+
+def test_slot_gather_scatter_bwd(ag):
+    n, R = 40, 9
+    src = _rand(n, 768, seed=26).requires_grad_()
+    slot = torch.tensor([3, 5, 8, 13, 21, 22, 30, 31, 39], dtype=torch.int32, device='cuda')
+    unit = torch.arange(R + 1, dtype=torch.int32, device='cuda')
+    rows = ag.GatherSlotsFn.apply(src, unit, slot, R, False)
+    proj = rows * 1.0                                    # stands for the projection head
+    proj.retain_grad()
+    out = ag.ScatterSlotsFn.apply(src, proj, slot, unit)
+    w = _rand(n, 768, seed=27)
+    (out * w).sum().backward()
+    sr = src.detach().clone().requires_grad_()
+    rr = sr[slot.long()] * 1.0
+    outr = sr.clone()
+    outr[slot.long()] = rr
+    (outr * w).sum().backward()
+    assert torch.equal(out.detach(), outr.detach())
+    assert relerr(src.grad, sr.grad) < 1e-6
+
+
+def test_fuse_logits_bwd(ag):
+    """adjoint of the global/local fusion against autograd through the oracle's restatement
+    (VLN-DUET/map_nav_src/models/vilmodel.py:1182-1217)"""
+    import numpy as np
+    from oracle import duet_oracle as O
+    from vln_imagine_b200 import synth
+    from vln_imagine_b200.duet import _IdTable
+    ep = synth.to_torch(synth.duet_episode(synth.CFG1, 99), 'cuda')
+    B, G = ep['gmap_masks'].shape
+    P = ep['vp_nav_masks'].shape[1]
+    g_raw = _rand(B * G, seed=28).requires_grad_()
+    l_raw = _rand(B * P, seed=29).requires_grad_()
+    f_raw = _rand(B, seed=30).requires_grad_()
+    ids = _IdTable()
+    gids = torch.from_numpy(ids.encode(ep['gmap_vpids'], G, -1)).cuda()
+    cids = torch.from_numpy(ids.encode(ep['vp_cand_vpids'], P, -2)).cuda()
+    u8 = lambda m: m.contiguous().view(torch.uint8)      # noqa: E731
+    gl, ll, fl = ag.FuseLogitsFn.apply(g_raw, l_raw, f_raw, u8(ep['gmap_masks']), u8(ep['gmap_visited_masks']),
+                                       u8(ep['vp_nav_masks']), gids, cids, B, G, P)
+    wg, wl, wf = _rand(B, G, seed=31), _rand(B, P, seed=32), _rand(B, G, seed=33)
+
+    def scalar(a, b, c):
+        z = lambda t, w: (torch.where(torch.isfinite(t), t, torch.zeros_like(t)) * w).sum()      # noqa: E731
+        return z(a, wg) + z(b, wl) + z(c, wf)
+    scalar(gl, ll, fl).backward()
+    gr, lr, fr = [t.detach().clone().requires_grad_() for t in (g_raw, l_raw, f_raw)]
+    fw = torch.sigmoid(fr)[:, None]
+    glr = (gr.view(B, G) * fw).masked_fill(ep['gmap_visited_masks'], float('-inf')).masked_fill(~ep['gmap_masks'], float('-inf'))
+    llr = (lr.view(B, P) * (1 - fw)).masked_fill(~ep['vp_nav_masks'], float('-inf'))
+    flr = O.fuse_logits(glr, llr, ep['gmap_vpids'], ep['gmap_visited_masks'], ep['vp_cand_vpids'])
+    scalar(glr, llr, flr).backward()
+    for got, want in [(gl, glr), (ll, llr), (fl, flr)]:
+        assert torch.equal(torch.isfinite(got), torch.isfinite(want))
+        fin = torch.isfinite(want)
+        assert relerr(got[fin], want[fin]) < 1e-5
+    assert relerr(g_raw.grad, gr.grad) < 1e-4
+    assert relerr(l_raw.grad, lr.grad) < 1e-4
+    assert relerr(f_raw.grad, fr.grad) < 1e-4

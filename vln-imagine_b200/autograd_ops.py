@@ -86,7 +86,6 @@ class LinearFn(Function):
         y = ops.gemm(x, w, b, residual=residual, epilogue=EPI_NONE, out_dtype=out_dtype, group_row_end=ends)
         ctx.save_for_backward(x)
         ctx.pack, ctx.lowp, ctx.ends, ctx.has_res = pack, lowp, ends, residual is not None
-        ctx.x_needs = x.requires_grad
         return y
 
     @staticmethod
@@ -98,7 +97,7 @@ class LinearFn(Function):
         n_groups = 1 if ends is None else len(ends)
         N = dyo.shape[1]
         dx = None
-        if ctx.x_needs:
+        if ctx.needs_input_grad[0]:
             wt = pack.get_t(lowp, n_groups)                             # [n_groups*K, N]
             dx = ops.gemm(dyo, wt, None, out_dtype=x.dtype, group_row_end=ends)
         dW = torch.empty((n_groups * N, K), dtype=F32, device=x.device)
@@ -239,7 +238,7 @@ class AttentionFn(Function):
     def backward(ctx, dout):
         bases = ctx.saved_tensors
         dout = dout.contiguous()
-        grads = [torch.zeros_like(b) if b.requires_grad else None for b in bases]
+        grads = [torch.zeros_like(b) if ctx.needs_input_grad[4 + i] else None for i, b in enumerate(bases)]
         d_affine = None
         for s in ctx.spec:
             def view(t, key, L):

@@ -290,6 +290,14 @@ def cross_attn(x: Act, kv: torch.Tensor, kv_col0: Sequence[int], ctx_len: int, c
     return layer_norm(ao, None, pk.ln, eps, lowp, ends)
 
 
+def linear(x: torch.Tensor, pk: LinearPack, lowp: bool, out_dtype=None, ends=None, residual=None) -> torch.Tensor:
+    """y = x W^T + b [+ residual] for a LinearPack (no activation); differentiable in training."""
+    if _Mode.train:
+        return ag.linear(x, pk, lowp, residual=residual, out_dtype=out_dtype, ends=ends)
+    w, b = pk.get(lowp)
+    return ops.gemm(x, w, b, residual=residual, out_dtype=out_dtype or (BF16 if lowp else F32), group_row_end=ends)
+
+
 def as_act(x32: torch.Tensor, lowp: bool) -> Act:
     """fp32 rows -> activation pair (adds the bf16 operand copy in bf16 mode)."""
     x32 = x32.contiguous()

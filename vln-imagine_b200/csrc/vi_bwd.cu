@@ -652,7 +652,9 @@ extern "C" int vi_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ld
                            const uint8_t* key_mask, const float* pair_dist, const float* bias_affine, float* d_affine, int B,
                            int H, int Lq, int Lk, int mask_mode, vi_stream_t stream) {
   VI_CHECK_ARG(q && k && v && dout && dq && dk && dv, "vi_attn_bwd: null operand");
-  VI_CHECK_ARG(B > 0 && H > 0 && Lq > 0 && Lk > 0 && Lk <= 320, "vi_attn_bwd: bad sizes B=%d H=%d Lq=%d Lk=%d (Lk <= 320)", B, H, Lq, Lk);
+  VI_CHECK_ARG(B > 0 && H > 0 && Lq > 0 && Lk > 0, "vi_attn_bwd: bad sizes B=%d H=%d Lq=%d Lk=%d", B, H, Lq, Lk);
+  VI_CHECK_ARG(((size_t)Lk * (65 * 2 + 64 * 2 + 1) + 8 * (size_t)(128 + 2 * Lk)) * sizeof(float) <= 220 * 1024,
+               "vi_attn_bwd: Lk=%d keys do not fit the 220 KB shared-memory tile", Lk);
   VI_CHECK_ARG(!pair_dist || bias_affine, "vi_attn_bwd: pair_dist needs bias_affine");
   AttnBwdParams p;
   p.q = q; p.ldq = ldq; p.k = k; p.ldk = ldk; p.v = v; p.ldv = ldv; p.dout = dout; p.ldo = ldo;

@@ -19,6 +19,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
+from . import autograd_ops as ag
 from . import blocks, graphs, ops, params
 from .blocks import Act, Stream
 from .config import duet_config
@@ -103,6 +104,8 @@ def align_forward(model, align_txt_embeds, align_imagine_embeds, flags, noun_phr
         # the reference returns the python int 0 here (models/vilmodel.py:650-651); a 0-d tensor is a superset
         return torch.zeros((), dtype=F32, device=dev), out.view(B, I, HIDDEN)
     pk = model._pk()['align']
+    if blocks.training():
+        return _align_forward_train(model, txt, img, rows, pk, lowp, (B, I))
     x32, x16 = ops.gather_mean(img, rows.unit, rows.slot, rows.R, want16=lowp, want32=not lowp)
     x = x16 if lowp else x32
     for j, lp in enumerate(pk):
@@ -122,6 +125,29 @@ def align_forward(model, align_txt_embeds, align_imagine_embeds, flags, noun_phr
     else:
         raise NotImplementedError('aux_loss_type %r' % cfg.aux_loss_type)
     ops.scatter_rows(proj, rows.slot, out)
+    return loss, out.view(B, I, HIDDEN)
+
+
+def _align_forward_train(model, txt, img, rows, pk, lowp, shape):
+    """align_forward with autograd recording: the projection MLP, the cosine loss and the write-back of the
+    projected rows (models/vilmodel.py:646) are differentiable; the noun-phrase text means are constants
+    (``fix_lang_inside_cosine_model``, :1249-1255 - the released configuration)."""
+    cfg = model.config
+    if txt.requires_grad:
+        raise NotImplementedError('training the text encoder through the alignment loss '
+                                  '(fix_lang_inside_cosine_model=False) is not on the released path')
+    if cfg.aux_loss_type != 'cosine':
+        raise NotImplementedError('backward of aux_loss_type %r' % cfg.aux_loss_type)
+    B, I = shape
+    x = ag.GatherSlotsFn.apply(img, rows.unit, rows.slot, rows.R, lowp)
+    for j, lp in enumerate(pk):
+        last = j == len(pk) - 1
+        x = ag.linear(x, lp, lowp, out_dtype=F32 if (last or not lowp) else BF16)
+        if not last:
+            x = ag.ActFn.apply(x, ops.EPI_RELU)
+    tgt, _ = ops.gather_mean(txt, rows.tok_off, rows.tok_rows, rows.R, want16=False)
+    loss = ag.CosineLossFn.apply(x, tgt, rows.R)
+    out = ag.ScatterSlotsFn.apply(img, x, rows.slot, rows.unit)
     return loss, out.view(B, I, HIDDEN)
 
 
@@ -207,6 +233,17 @@ class GlocalTextPathNavCMT(nn.Module):
     def _guard(self, t: torch.Tensor):
         ops.ensure_init(t)            # raises on CPU tensors: there is no fallback path
 
+    def _recording(self, *inputs) -> bool:
+        """True when this call must record autograd nodes (fine-tuning): gradients are enabled and a parameter
+        or an input asks for one.  Dropout is not implemented: the probabilities must be 0 while training."""
+        if not torch.is_grad_enabled():
+            return False
+        rec = any(torch.is_tensor(t) and t.requires_grad for t in inputs) or any(p.requires_grad for p in self.parameters())
+        if rec and self.training and (self.config.hidden_dropout_prob > 0 or self.config.attention_probs_dropout_prob > 0):
+            raise NotImplementedError('train-mode dropout is not implemented: set hidden_dropout_prob = '
+                                      'attention_probs_dropout_prob = 0 (or call .eval()) for fine-tuning')
+        return rec
+
     # -- modes ------------------------------------------------------------------------------------
     def forward_text(self, txt_ids, txt_masks):
         """'language': BertEmbeddings (:49-78) + 9 post-LN layers (:414-434); entry :1075-1079."""
@@ -214,14 +251,13 @@ class GlocalTextPathNavCMT(nn.Module):
         lowp = self.lowp
         B, L = txt_ids.shape
         e = self.embeddings
-        y32, y16 = ops.embed_compose(B * L, txt_ids.device, idx=txt_ids.long().contiguous().view(-1), table=e.word_embeddings.weight,
-                                     pos_table=e.position_embeddings.weight, pos_period=L,
-                                     const_row=e.token_type_embeddings.weight[0],
-                                     out_ln=(e.LayerNorm.weight, e.LayerNorm.bias), want16=lowp)
-        x = Act(y32, y16)
-        s = [Stream(0, B, L, blocks.mask_u8(txt_masks))]
-        for pk in self._pk()['lang']:
-            x = blocks.self_attn_ffn(x, pk, s, None, lowp)
+        with blocks.grad_mode(self._recording() and not self.config.fix_lang_embedding):
+            x = blocks.embed(B * L, txt_ids.device, idx=txt_ids.long().contiguous().view(-1), table=e.word_embeddings.weight,
+                             pos_table=e.position_embeddings.weight, pos_period=L,
+                             const_rows=(e.token_type_embeddings.weight[0],), out_ln=e.LayerNorm, lowp=lowp)
+            s = [Stream(0, B, L, blocks.mask_u8(txt_masks))]
+            for pk in self._pk()['lang']:
+                x = blocks.self_attn_ffn(x, pk, s, None, lowp)
         out = x.f32.view(B, L, HIDDEN)
         if self.config.fix_lang_embedding:
             out = out.detach()
@@ -231,9 +267,10 @@ class GlocalTextPathNavCMT(nn.Module):
         """'imagine' (bypass encoder): features + type embedding 0.  :562-573, :1081-1085."""
         self._guard(imagine_feats)
         B, I, _ = imagine_feats.shape
-        y32, _ = ops.embed_compose(B * I, imagine_feats.device, a=_f32c(imagine_feats).view(B * I, HIDDEN),
-                                   const_row=self.imagine_embeddings.type_embedding.weight[0])
-        return y32.view(B, I, HIDDEN)
+        with blocks.grad_mode(self._recording(imagine_feats)):
+            y = blocks.embed(B * I, imagine_feats.device, a=_f32c(imagine_feats).view(B * I, HIDDEN),
+                             const_rows=(self.imagine_embeddings.type_embedding.weight[0],))
+        return y.f32.view(B, I, HIDDEN)
 
     def forward_panorama_per_step(self, view_img_fts, obj_img_fts, loc_fts, nav_types, view_lens, obj_lens):
         """'panorama'.  :1087-1131 + transformer.py:71-89,170-182."""
@@ -246,21 +283,17 @@ class GlocalTextPathNavCMT(nn.Module):
         pk = self._pk()
         ie = self.img_embeddings
         v32 = _f32c(view_img_fts).view(B * V, Fd)
-        w, b = pk['img_linear'].get(lowp)
-        a = ops.gemm(ops.cast_bf16(v32) if lowp else v32, w, b, out_dtype=F32)
-        x32, _ = ops.embed_compose(
-            B * V, dev, a=a, a_ln=(ie.img_layer_norm.weight, ie.img_layer_norm.bias),
-            feat=_f32c(loc_fts).view(B * V, -1), feat_w=ie.loc_linear.weight, feat_b=ie.loc_linear.bias,
-            feat_ln=(ie.loc_layer_norm.weight, ie.loc_layer_norm.bias),
-            idx=nav_types.long().contiguous().view(-1), table=ie.nav_type_embedding.weight,
-            const_row=self.embeddings.token_type_embeddings.weight[1],
-            out_ln=(ie.layer_norm.weight, ie.layer_norm.bias))
         pano_masks = torch.arange(V, device=dev)[None, :] < view_lens.to(dev)[:, None]      # ops.py:36-44
         km = blocks.mask_u8(pano_masks)
-        for lp in pk['pano']:
-            x32 = blocks.pano_layer(x32, lp, B, V, km, lowp)
-        g, be = pk['pano_norm'].get()
-        y32, _ = ops.add_ln(x32, None, g, be, 1e-12, want16=False)
+        with blocks.grad_mode(self._recording(view_img_fts) and not self.config.fix_pano_embedding):
+            a = blocks.linear(blocks.operand(v32, lowp), pk['img_linear'], lowp, out_dtype=F32)
+            x32 = blocks.embed(B * V, dev, a=a, a_ln=ie.img_layer_norm, feat=_f32c(loc_fts).view(B * V, -1),
+                               feat_lin=ie.loc_linear, feat_ln=ie.loc_layer_norm,
+                               idx=nav_types.long().contiguous().view(-1), table=ie.nav_type_embedding.weight,
+                               const_rows=(self.embeddings.token_type_embeddings.weight[1],), out_ln=ie.layer_norm).f32
+            for lp in pk['pano']:
+                x32 = blocks.pano_layer(x32, lp, B, V, km, lowp)
+            y32 = blocks.layer_norm(x32, None, pk['pano_norm'], 1e-12, False).f32
         out = y32.view(B, V, HIDDEN)
         if self.config.fix_pano_embedding:
             out = out.detach()
@@ -279,6 +312,12 @@ class GlocalTextPathNavCMT(nn.Module):
         B, L, _ = txt_embeds.shape
         G, P = gmap_img_embeds.shape[1], vp_img_embeds.shape[1]
         ge, le = self.global_encoder, self.local_encoder
+
+        if self._recording(txt_embeds, gmap_img_embeds, vp_img_embeds, imagine_embeds):
+            with blocks.grad_mode(True):
+                return self._navigation_train(txt_embeds, txt_masks, gmap_img_embeds, gmap_step_ids, gmap_pos_fts, gmap_masks,
+                                              gmap_pair_dists, gmap_visited_masks, gmap_vpids, vp_img_embeds, vp_pos_fts,
+                                              vp_masks, vp_nav_masks, vp_cand_vpids, imagine_embeds, imagine_masks)
 
         # ---- input embeddings of both branches into one row-stacked activation (:1141-1152)
         (r_g, r_l), ends, R = blocks.stack_layout([B * G, B * P])
@@ -354,6 +393,66 @@ class GlocalTextPathNavCMT(nn.Module):
         return {'gmap_embeds': gmap_out, 'vp_embeds': vp_out, 'global_logits': gl, 'local_logits': ll,
                 'fused_logits': fl, 'obj_logits': None}
 
+    def _navigation_train(self, txt_embeds, txt_masks, gmap_img_embeds, gmap_step_ids, gmap_pos_fts, gmap_masks,
+                          gmap_pair_dists, gmap_visited_masks, gmap_vpids, vp_img_embeds, vp_pos_fts, vp_masks,
+                          vp_nav_masks, vp_cand_vpids, imagine_embeds, imagine_masks):
+        """'navigation' with autograd recording (fine-tuning, BASELINE.json cfg-4): the same layer sequence as
+        forward_navigation_per_step built from the differentiable blocks; torch only concatenates / slices rows."""
+        cfg, lowp, pk = self.config, self.lowp, self._pk()
+        dev = txt_embeds.device
+        B, L, _ = txt_embeds.shape
+        G, P = gmap_img_embeds.shape[1], vp_img_embeds.shape[1]
+        ge, le = self.global_encoder, self.local_encoder
+        (r_g, r_l), ends, R = blocks.stack_layout([B * G, B * P])
+        g_in = blocks.embed(B * G, dev, a=_f32c(gmap_img_embeds).view(B * G, HIDDEN), feat=_f32c(gmap_pos_fts).view(B * G, -1),
+                            feat_lin=ge.gmap_pos_embeddings[0], feat_ln=ge.gmap_pos_embeddings[1],
+                            idx=gmap_step_ids.long().contiguous().view(-1), table=ge.gmap_step_embeddings.weight).f32
+        l_in = blocks.embed(B * P, dev, a=_f32c(vp_img_embeds).view(B * P, HIDDEN), feat=_f32c(vp_pos_fts).view(B * P, -1),
+                            feat_lin=le.vp_pos_embeddings[0], feat_ln=le.vp_pos_embeddings[1]).f32
+        parts = [g_in]
+        if ends[0] > B * G:
+            parts.append(torch.zeros((ends[0] - B * G, HIDDEN), dtype=F32, device=dev))
+        x = blocks.as_act(torch.cat(parts + [l_in], 0), lowp)
+
+        txt = _f32c(txt_embeds)
+        if cfg.imagine_enc_pano and cfg.concat_imagine_with == 'language':
+            if imagine_embeds is None or imagine_masks is None:
+                raise ValueError('navigation needs imagine_embeds and imagine_masks when imagine_enc_pano is set')
+            C = L + imagine_embeds.shape[1]
+            ctx32 = torch.cat([txt, _f32c(imagine_embeds)], 1).view(B * C, HIDDEN)
+            ctx_mask = blocks.mask_u8(torch.cat([txt_masks.bool(), imagine_masks.bool()], 1))
+        else:
+            C = L
+            ctx32 = txt.view(B * L, HIDDEN)
+            ctx_mask = blocks.mask_u8(txt_masks)
+        ctx = blocks.operand(ctx32, lowp)
+
+        affine = dist = aparams = None
+        if ge.sprel_linear is not None:
+            affine = pk['sprel'].get()
+            dist = _f32c(gmap_pair_dists)
+            aparams = (ge.sprel_linear.weight, ge.sprel_linear.bias)
+        streams = [Stream(r_g, B, G, blocks.mask_u8(gmap_masks), 0, dist, affine, aparams),
+                   Stream(r_l, B, P, blocks.mask_u8(vp_masks), 1)]
+        for cp, sp in zip(pk['x_cross'], pk['x_self']):
+            kv = blocks.linear(ctx, cp.kv, lowp)
+            x = blocks.cross_attn(x, kv, [0, 2 * HIDDEN], C, ctx_mask, cp, streams, ends, lowp)
+            x = blocks.self_attn_ffn(x, sp, streams, ends, lowp)
+
+        gmap_out = x.f32[r_g:r_g + B * G].view(B, G, HIDDEN)
+        vp_out = x.f32[r_l:r_l + B * P].view(B, P, HIDDEN)
+        fuse_raw = None
+        if self.sap_fuse_linear is not None:
+            cat = torch.cat([gmap_out[:, 0], vp_out[:, 0]], 1)
+            fuse_raw = blocks.cls_head(blocks.operand(cat, lowp), pk['fuse'], lowp)
+        raw = blocks.cls_head(x.operand(lowp), pk['sap'], lowp, ends)
+        gmap_ids, cand_ids = self.intern_vpids(gmap_vpids, vp_cand_vpids, G, P, dev)
+        gl, ll, fl = ag.FuseLogitsFn.apply(raw[r_g:r_g + B * G], raw[r_l:r_l + B * P], fuse_raw, blocks.mask_u8(gmap_masks),
+                                           blocks.mask_u8(gmap_visited_masks), blocks.mask_u8(vp_nav_masks), gmap_ids,
+                                           cand_ids, B, G, P)
+        return {'gmap_embeds': gmap_out, 'vp_embeds': vp_out, 'global_logits': gl, 'local_logits': ll,
+                'fused_logits': fl, 'obj_logits': None}
+
     def intern_vpids(self, gmap_vpids, vp_cand_vpids, G, P, dev):
         """Viewpoint-id strings -> int32 tensors on ``dev`` (gmap padding -1, candidate padding -2).  Callers that
         already hold interned ids (a CUDA-graph replay loop, bench.py) may pass the two tensors instead of the
@@ -374,8 +473,9 @@ class GlocalTextPathNavCMT(nn.Module):
         txt = batch['align_txt_embeds']
         if self.config.fix_lang_inside_cosine_model:
             txt = txt.detach()
-        return align_forward(self, txt, batch['align_imagine_embeds'], batch['sub_instr_imag_flag'],
-                             batch['noun_phrase_segs'], self.lowp)
+        with blocks.grad_mode(self._recording(txt, batch['align_imagine_embeds'])):
+            return align_forward(self, txt, batch['align_imagine_embeds'], batch['sub_instr_imag_flag'],
+                                 batch['noun_phrase_segs'], self.lowp)
 
     def forward(self, mode, batch, **kwargs):
         """Mode dispatch, :1237-1288."""

@@ -1,0 +1,110 @@
+"""Data-parallel fine-tuning plumbing for the navigation hot path (BASELINE.json cfg-4).
+
+One process per GPU; episodes are sharded by rank; weights are replicated.  The only collective on the path is ONE
+all-reduce of a flat gradient buffer per iteration (NCCL over NVLink / NVSwitch; average = the reference's
+DistributedDataParallel semantics, VLN-DUET/map_nav_src/r2r/agent_base.py:131-134 + utils/distributed.py).
+Everything before it - forward and backward of every mode - runs in libvlnimagine kernels recorded through
+autograd_ops; the optimiser and the gradient clipping stay the caller's (agent_base.py:223-228).
+
+    flat = FlatGradients(model)                 # .grad of every trainable parameter becomes a view of one buffer
+    loss = duet_finetune_iteration(model, ep)   # prelude + T navigation steps, teacher forcing, loss.backward()
+    flat.all_reduce()                           # one collective
+    torch.nn.utils.clip_grad_norm_(model.parameters(), 40.); optimizer.step(); flat.zero()
+"""
+from __future__ import annotations
+
+from typing import Iterable, List, Optional
+
+import torch
+import torch.distributed as dist
+
+
+class FlatGradients:
+    """All trainable parameters' gradients in ONE contiguous fp32 buffer (parameter order = ``named_parameters()``
+    order, each segment padded to 16 bytes).  ``p.grad`` is a view of the buffer, so autograd accumulates in place
+    and the all-reduce needs no packing copy."""
+
+    ALIGN = 4      # elements (16 bytes)
+
+    def __init__(self, module: torch.nn.Module, params: Optional[Iterable[torch.nn.Parameter]] = None):
+        ps = [p for p in (params if params is not None else module.parameters()) if p.requires_grad]
+        if not ps:
+            raise ValueError('FlatGradients: no trainable parameters')
+        dev, dt = ps[0].device, ps[0].dtype
+        self.params: List[torch.nn.Parameter] = ps
+        self.offsets = []
+        off = 0
+        for p in ps:
+            if p.device != dev or p.dtype != dt:
+                raise ValueError('FlatGradients: parameters must share a device and a dtype')
+            self.offsets.append(off)
+            off += (p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        self.numel = off
+        self.buffer = torch.zeros(off, dtype=dt, device=dev)
+        self.attach()
+
+    def attach(self):
+        """(re)point every .grad at its segment (needed again after ``zero_grad(set_to_none=True)``)"""
+        for p, off in zip(self.params, self.offsets):
+            p.grad = self.buffer[off:off + p.numel()].view_as(p)
+
+    def zero(self):
+        self.buffer.zero_()
+        self.attach()
+
+    def all_reduce(self, group=None, async_op: bool = False):
+        """average over the ranks of ``group``; no-op without an initialised process group or with one rank"""
+        if not dist.is_available() or not dist.is_initialized():
+            return None
+        world = dist.get_world_size(group)
+        if world == 1:
+            return None
+        if dist.get_backend(group) == 'nccl':
+            return dist.all_reduce(self.buffer, op=dist.ReduceOp.AVG, group=group, async_op=async_op)
+        work = dist.all_reduce(self.buffer, op=dist.ReduceOp.SUM, group=group, async_op=False)   # gloo: host-logic tests
+        self.buffer.div_(world)
+        return work
+
+    def bytes(self) -> int:
+        return self.numel * self.buffer.element_size()
+
+
+def teacher_targets(gmap_masks: torch.Tensor, gmap_visited_masks: torch.Tensor) -> torch.Tensor:
+    """Synthetic teacher action: the last admissible graph node (valid and not visited); [stop] (0) if none.
+    Stands in for _teacher_action_r4r (r2r/agent.py:209-262), which needs the simulator."""
+    ok = gmap_masks.bool() & ~gmap_visited_masks.bool()
+    idx = torch.arange(ok.shape[1], device=ok.device)[None, :].expand_as(ok)
+    return torch.where(ok, idx, torch.zeros_like(idx)).max(1).values
+
+
+def duet_finetune_iteration(model, ep: dict, n_steps: int = 1, cosine_weight: float = 0.5, ml_weight: float = 1.0,
+                            backward: bool = True):
+    """One imitation-learning iteration of the reference agent on a batch of episodes (r2r/agent.py:384-623):
+    language + imagine + align once, then ``n_steps`` navigation steps (panorama -> navigation -> summed
+    cross-entropy on the fused logits), loss = ml_weight * CE / B + cosine_weight * aux.  ``model`` is the drop-in
+    VLNBert; ``ep`` holds device tensors (vln-imagine_b200/synth.py layout).  Returns (loss, ce, aux, last nav dict)."""
+    B = ep['txt_ids'].shape[0]
+    txt = model('language', {'txt_ids': ep['txt_ids'], 'txt_masks': ep['txt_masks']})
+    img = model('imagine', {'imagine_feats': ep['imagine_feats'], 'imagine_masks': None})
+    aux, img2 = model('align_with_contrastive_loss', {
+        'align_txt_embeds': txt, 'txt_masks': ep['txt_masks'], 'align_imagine_embeds': img,
+        'imagine_masks': ep['imagine_masks'], 'sub_instr_segs': ep['sub_instr_segs'],
+        'sub_instr_imag_flag': ep['sub_instr_imag_flag'], 'noun_phrase_segs': ep['noun_phrase_segs'],
+        'obs_instr_ids': ep['obs_instr_ids']})
+    tgt = teacher_targets(ep['gmap_masks'], ep['gmap_visited_masks'])
+    ce = None
+    nav = None
+    for _ in range(n_steps):
+        pano, _ = model('panorama', {'view_img_fts': ep['view_img_fts'], 'obj_img_fts': None, 'loc_fts': ep['loc_fts'],
+                                     'nav_types': ep['nav_types'], 'view_lens': ep['view_lens'], 'obj_lens': None})
+        vp_img = torch.cat([torch.zeros_like(pano[:, :1]), pano], 1)                  # r2r/agent.py:173-186
+        nav = model('navigation', {k: ep[k] for k in (
+            'txt_masks', 'gmap_img_embeds', 'gmap_step_ids', 'gmap_pos_fts', 'gmap_masks', 'gmap_pair_dists',
+            'gmap_visited_masks', 'gmap_vpids', 'vp_pos_fts', 'vp_masks', 'vp_nav_masks', 'vp_cand_vpids',
+            'imagine_masks')} | {'txt_embeds': txt, 'imagine_embeds': img2, 'vp_obj_masks': None, 'vp_img_embeds': vp_img})
+        step_ce = torch.nn.functional.cross_entropy(nav['fused_logits'], tgt, reduction='sum')     # agent_base.py:162
+        ce = step_ce if ce is None else ce + step_ce
+    loss = ce * (ml_weight / B) + cosine_weight * aux
+    if backward:
+        loss.backward()
+    return loss, ce / B, aux, nav
