@@ -79,6 +79,9 @@ def workload(name):
     if name == 'hamt_cfg3':
         return 'hamt', synth.CFG3, ('HAMT-Imagine visual+history forward, 64 episodes/GPU, 80-token instruction, '
                                     '5 imaginations, 15-step history, 37 observations')
+    if name == 'duet_cfg4_train':
+        return 'duet', synth.CFG2, ('DUET-Imagine fine-tuning iteration (forward + backward with the imagination-text aux '
+                                    'loss, gradient all-reduce, AdamW step), 64 episodes/GPU x 6 navigation steps')
     raise SystemExit('unknown workload %r' % name)
 
 
@@ -274,6 +277,161 @@ def run_reference_arm(args, model_kind, shape, desc, rank):
     print(json.dumps(line), flush=True)
 
 
+
+# ----------------------------------------------------------------------------------------------
+# fine-tuning workload (BASELINE.json cfg-4): forward + backward + gradient all-reduce + optimiser step
+# ----------------------------------------------------------------------------------------------
+def run_train(args, shape, desc, rank, local_rank, world):
+    import torch.distributed as dist
+    from vln_imagine_b200 import config, duet, ops, synth, train
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    T = 6                                                   # navigation steps per episode
+    B = shape.batch
+    a = config.default_duet_args()
+    model = duet.VLNBert(a).cuda()
+    net = model.vln_bert
+    shapes = {k: list(v.shape) for k, v in net.state_dict().items()}
+    net.load_state_dict(synth.synth_state_dict(shapes, seed=0))
+    net.precision = args.precision
+    # dropout is not implemented in the training path: probabilities 0, as in the gradient-parity runs
+    net.config.hidden_dropout_prob = net.config.attention_probs_dropout_prob = 0.0
+    model.drop_env.p = 0.0
+    model.train()
+    ep_host = synth.to_torch(synth.duet_episode(shape, 1234 + rank))
+    host = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in ep_host.items()}
+    h2d = sum(v.numel() * v.element_size() for v in host.values() if torch.is_tensor(v))
+    flat = train.FlatGradients(net)
+    # the caller's optimiser (r2r/agent_base.py:141-160); capturable: its step is part of the replayed graph
+    opt = torch.optim.AdamW(net.parameters(), lr=1e-5, fused=True, capturable=not args.no_graph)
+
+    def iteration(ep):
+        flat.zero()
+        loss, ce, aux, _ = train.duet_finetune_iteration(model, ep, n_steps=T)
+        flat.all_reduce()
+        torch.nn.utils.clip_grad_norm_(net.parameters(), 40.)         # agent_base.py:225
+        opt.step()
+        return loss.detach()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    d = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in ep_host.items()}
+    G, P = ep_host['gmap_img_embeds'].shape[1], ep_host['vp_img_embeds'].shape[1]
+    d['gmap_vpids'], d['vp_cand_vpids'] = net.intern_vpids(ep_host['gmap_vpids'], ep_host['vp_cand_vpids'], G, P, dev)
+    host['gmap_vpids'], host['vp_cand_vpids'] = d['gmap_vpids'], d['vp_cand_vpids']
+    K, W = args.steps, args.warmup
+    for _ in range(W):
+        iteration(d)
+    torch.cuda.synchronize()
+    n0 = ops._Counters.launches
+    iteration(d)
+    launches = ops._Counters.launches - n0
+    eager_iteration = iteration
+    graphed = None
+    if not args.no_graph:
+        graphed = train.GraphedIteration(net, eager_iteration, d, warmup=0)
+
+        def iteration(ep):
+            graphed.load(ep)
+            return graphed.replay()
+        for _ in range(2):
+            iteration(d)
+        torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    barrier()
+    with sampler:
+        e0.record()
+        for _ in range(K):
+            loss = iteration(d)
+        e1.record()
+        torch.cuda.synchronize()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    # e2e: the iteration's inputs come from pinned host memory, the loss is read back
+    barrier()
+    e0.record()
+    for _ in range(K):
+        if graphed is not None:
+            loss_host = float(iteration(host))              # pinned host tensors copied into the graph's static inputs
+        else:
+            dd = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in host.items()}
+            loss_host = float(iteration(dd))
+    e1.record()
+    torch.cuda.synchronize()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+    # roofline of the GEMM kernel over one EAGER iteration (forward + dgrad + wgrad launches)
+    if graphed is not None:
+        graphed.finish()
+    iteration = eager_iteration
+    torch.cuda.synchronize()
+    torch.cuda._sleep(400_000_000)                          # ~0.2 s head start: the host queues ~4000 launches
+    ops._Counters.gemm_trace = []
+    iteration(d)
+    torch.cuda.synchronize()
+    trace, ops._Counters.gemm_trace = ops._Counters.gemm_trace, None
+    gemm_flops = sum(2.0 * m * n * k for m, n, k, _, _ in trace)
+    gemm_ms = sum(x.elapsed_time(y) for _, _, _, x, y in trace)
+    torch.cuda._sleep(400_000_000)
+    ops._Counters.trace = []
+    iteration(d)
+    torch.cuda.synchronize()
+    tr2, ops._Counters.trace = ops._Counters.trace, None
+    breakdown = {}
+    for name, x, y in tr2:
+        n_, t_ = breakdown.get(name, (0, 0.0))
+        breakdown[name] = (n_ + 1, t_ + x.elapsed_time(y))
+    breakdown = {k: {'launches': v[0], 'ms': round(v[1], 3)} for k, v in sorted(breakdown.items(), key=lambda kv: -kv[1][1])}
+    if world > 1:
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    peak_tf = peaks.get('bf16_tflops_sustained', 1400.0)
+    achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    fl_dec = flops_per_decision('duet', shape)
+    C = shape.instr_len + shape.n_imagine
+    fl_episode = 3.0 * (9 * _bert(shape.instr_len) + T * fl_dec)          # fwd + bwd ~ 3 x fwd
+    line = {
+        'metric': METRIC + ' (fine-tuning: forward + backward + all-reduce + optimiser)', 'value': world * B * T * K / (ms * 1e-3),
+        'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': ms / K, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': args.precision, 'data': 'synthetic',
+        'config': {'workload': '%s: %s' % (args.workload, desc), 'episodes_per_gpu': B, 'nav_steps_per_iteration': T,
+                   'replay': 'eager launches (autograd)' if args.no_graph else 'CUDA graph of the whole iteration '
+                             '(forward, backward, all-reduce, clipping, AdamW)',
+                   'dropout': 'off (not implemented in the training path)',
+                   'l2': 'no flush: an iteration touches > 3 GB of weights, gradients and saved activations',
+                   'collective': 'one NCCL all-reduce (AVG) of the flat fp32 gradient buffer, %.0f MB' % (flat.bytes() / 1e6),
+                   'weights': 'random-init (deterministic synthetic)'},
+        'clocks': sampler.summary(),
+        'e2e': {'value': world * B * T * K / (ms_e2e * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4,
+                'ms_per_step': ms_e2e / K, 'api': 'train.duet_finetune_iteration through the module API; episode batch copied '
+                                                  'from pinned host memory every iteration, loss read back'},
+        'gpu_launches': launches * K,
+        'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': achieved / peak_tf,
+                     'traffic': None, 'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained' if peaks else 'fallback',
+                     'kernel': 'gemm_bf16_tc_kernel (tcgen05): %d launches/iteration (forward, dgrad, wgrad), %.1f GFLOP executed, '
+                               '%.3f ms of GEMM time' % (len(trace), gemm_flops / 1e9, gemm_ms)},
+        'step': {'algorithmic_gflop_per_iteration': fl_episode * B / 1e9,
+                 'tflops': fl_episode * B / (ms / K * 1e-3) / 1e12, 'launches_per_iteration': launches, 'loss': loss_host,
+                 'breakdown': breakdown},
+    }
+    print(json.dumps(line), flush=True)
+
 # ----------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -294,6 +452,9 @@ def main():
 
     if args.impl == 'reference':
         run_reference_arm(args, model_kind, shape, desc, rank)
+        return
+    if args.workload.endswith('_train'):
+        run_train(args, shape, desc, rank, local_rank, world)
         return
 
     import torch.distributed as dist
@@ -319,6 +480,15 @@ def main():
     step_fn = duet_step if model_kind == 'duet' else hamt_step
     B = shape.batch
     K, W = args.steps, args.warmup
+    # DUET keeps the K / V projections of the [txt ; imagine] context for the length of an episode (the reference
+    # recomputes them identically at every step).  The bench is honest about it: every EP_LEN-th step is the first
+    # step of a new episode and projects the context again (R2R paths are 4-6 hops + stop, SURVEY.md 8(d): T = 6).
+    EP_LEN = 6
+    ctx_cache = model_kind == 'duet' and model.vln_bert.context_cache
+
+    def new_episode():
+        if ctx_cache:
+            model.vln_bert.drop_context()
 
     with torch.no_grad():
         d = device_inputs(model_kind, model, ep, dev)
@@ -337,28 +507,45 @@ def main():
         for _ in range(3):
             logits, _ = step_fn(model, d, txt, img2)
         torch.cuda.synchronize()
+        new_episode()
         n0 = ops._Counters.launches
-        logits, _ = step_fn(model, d, txt, img2)
-        launches_per_step = ops._Counters.launches - n0
-        graph = None
+        logits, _ = step_fn(model, d, txt, img2)            # first step of an episode
+        launches_first = ops._Counters.launches - n0
+        n0 = ops._Counters.launches
+        logits, _ = step_fn(model, d, txt, img2)            # a later step
+        launches_later = ops._Counters.launches - n0
+        state = {'i': 0}
         if not args.no_graph:
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                step_fn(model, d, txt, img2)
-            torch.cuda.current_stream().wait_stream(side)
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                g_logits, _ = step_fn(model, d, txt, img2)
-            run = graph.replay
+            def capture(first):
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    step_fn(model, d, txt, img2)
+                torch.cuda.current_stream().wait_stream(side)
+                if first:
+                    new_episode()                           # the capture then contains the context projections
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    step_fn(model, d, txt, img2)
+                return g
+            g_later = capture(False)
+            g_first = capture(True) if ctx_cache else g_later
+
+            def run():
+                (g_first if state['i'] % EP_LEN == 0 else g_later).replay()
+                state['i'] += 1
         else:
             def run():
+                if state['i'] % EP_LEN == 0:
+                    new_episode()
                 step_fn(model, d, txt, img2)
+                state['i'] += 1
         for _ in range(W):
             run()
         sampler = ClockSampler(local_rank)
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         barrier()
+        state['i'] = 0
         with sampler:
             e0.record()
             for _ in range(K):
@@ -366,6 +553,9 @@ def main():
             e1.record()
             torch.cuda.synchronize()
         barrier()
+        n_first = (K + EP_LEN - 1) // EP_LEN
+        total_launches = n_first * launches_first + (K - n_first) * launches_later
+        launches_per_step = launches_first
         ms = max_over_ranks(e0.elapsed_time(e1))
         value = world * B * K / (ms * 1e-3)
 
@@ -383,7 +573,9 @@ def main():
             host_lists = {}
             hist_lens_host = [int(x) for x in ep['hist_lens']]
 
-        def e2e_step():
+        def e2e_step(i):
+            if i % EP_LEN == 0:
+                new_episode()
             dd = dict(d)
             dd.update(host)                              # pinned host tensors: the API copies them in
             dd.update(host_lists)
@@ -395,12 +587,12 @@ def main():
             out_host.copy_(lg, non_blocking=True)
             torch.cuda.current_stream().synchronize()          # the agent needs the logits to act
 
-        for _ in range(W):
-            e2e_step()
+        for i in range(W):
+            e2e_step(i)
         barrier()
         e0.record()
-        for _ in range(K):
-            e2e_step()
+        for i in range(K):
+            e2e_step(i)
         e1.record()
         torch.cuda.synchronize()
         barrier()
@@ -412,7 +604,9 @@ def main():
         torch.cuda.synchronize()
         torch.cuda._sleep(40_000_000)                   # ~20 ms head start for the host: launches then queue back to back
         ops._Counters.gemm_trace = []                   # and an event pair brackets device time only
-        for _ in range(3):
+        TRACE_STEPS = EP_LEN if ctx_cache else 3
+        new_episode()
+        for _ in range(TRACE_STEPS):
             step_fn(model, d, txt, img2)
         torch.cuda.synchronize()
         trace, ops._Counters.gemm_trace = ops._Counters.gemm_trace, None
@@ -421,7 +615,8 @@ def main():
         # per-entry-point breakdown of one step, same method (diagnostic: the event pairs add ~1 us gaps)
         torch.cuda._sleep(40_000_000)
         ops._Counters.trace = []
-        for _ in range(3):
+        new_episode()
+        for _ in range(TRACE_STEPS):
             step_fn(model, d, txt, img2)
         torch.cuda.synchronize()
         tr2, ops._Counters.trace = ops._Counters.trace, None
@@ -429,7 +624,7 @@ def main():
         for name, a, b in tr2:
             n_, t_ = breakdown.get(name, (0, 0.0))
             breakdown[name] = (n_ + 1, t_ + a.elapsed_time(b))
-        breakdown = {k: {'launches_per_step': v[0] // 3, 'ms_per_step': round(v[1] / 3, 4)} for k, v in
+        breakdown = {k: {'launches_per_step': round(v[0] / TRACE_STEPS, 2), 'ms_per_step': round(v[1] / TRACE_STEPS, 4)} for k, v in
                      sorted(breakdown.items(), key=lambda kv: -kv[1][1])}
 
     if rank != 0:
@@ -453,20 +648,27 @@ def main():
         'dtype': args.precision, 'data': 'synthetic',
         'config': {'workload': '%s: %s' % (args.workload, desc), 'episodes_per_gpu': B,
                    'replay': 'eager launches' if args.no_graph else 'CUDA graph of the step',
-                   'l2': 'no flush: each step streams 181 MB of bf16 weights plus activations, more than the 126 MB L2',
+                   'l2': 'no flush: each step streams 150+ MB of bf16 weights plus activations, more than the 126 MB L2',
+                   'episode_len': EP_LEN if ctx_cache else None,
+                   'context_cache': ('K/V projections of [txt;imagine] computed at the first step of each %d-step episode and '
+                                     'reused by the other %d (the reference recomputes them every step); value counts '
+                                     'wall time over all steps' % (EP_LEN, EP_LEN - 1)) if ctx_cache else 'n/a',
                    'weights': 'random-init (deterministic synthetic), shared with the oracle'},
         'clocks': sampler.summary(),
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                 'ms_per_step': ms_e2e / K, 'api': 'the module API (DUET panorama+navigation / HAMT visual+history) called with pinned host tensors; it '
                        'copies them into the static buffers of its per-mode CUDA graphs, replays, and the logits are '
                        'read back and synchronised every step'},
-        'gpu_launches': launches_per_step * K,
+        'gpu_launches': total_launches,
         'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s',
                      'frac': achieved / peak_tf, 'traffic': None, 'peak_source': peak_src,
-                     'kernel': 'gemm_bf16_tc_kernel (tcgen05): %d launches/step, %.1f GFLOP/step, %.3f ms/step of GEMM time '
-                               '(CUDA events around each launch of 3 queued eager steps)' % (len(trace) // 3, gemm_flops / 3 / 1e9, gemm_ms / 3)},
+                     'kernel': 'gemm_bf16_tc_kernel (tcgen05): %.1f launches/step, %.1f GFLOP/step EXECUTED, %.3f ms/step of GEMM '
+                               'time (CUDA events around each launch of %d queued eager steps = one episode)'
+                               % (len(trace) / TRACE_STEPS, gemm_flops / TRACE_STEPS / 1e9, gemm_ms / TRACE_STEPS, TRACE_STEPS)},
         'step': {'algorithmic_gflop_per_decision': fl_dec / 1e9, 'tflops': step_tf, 'frac_of_peak': step_tf / peak_tf,
-                 'launches_per_step': launches_per_step, 'prelude_ms_per_episode_batch': prelude_ms,
+                 'executed_gemm_gflop_per_decision': gemm_flops / TRACE_STEPS / B / 1e9,
+                 'launches_first_step_of_episode': launches_first, 'launches_later_steps': launches_later,
+                 'prelude_ms_per_episode_batch': prelude_ms,
                  'breakdown': breakdown},
     }
     if world == 1 and not args.no_cpu_baseline:

@@ -221,8 +221,12 @@ int vi_copy_rows(const float* src, int64_t src_batch_stride, int64_t src_row_str
 /* dst[c, r] = src[r, c]; dst is [cols, ldd] with columns rows..pad_rows-1 zero-filled (pad_rows <= ldd) */
 int vi_transpose(const void* src, int64_t ld, void* dst, int64_t ldd, int rows, int cols, int pad_rows, int dtype,
                  vi_stream_t stream);
-/* out[c] = sum_r x[r, c] (fp32 accumulation, fixed order); bias gradients of nn.Linear */
-int vi_colsum(const void* x, int64_t ld, int dtype, float* out, int64_t rows, int cols, vi_stream_t stream);
+/* Column reductions over rows run in two deterministic stages (128-row chunks -> a caller-provided fp32 scratch ->
+ * fixed-order sum).  vi_reduce_scratch_elems gives the scratch size for n_out reduced quantities per column. */
+int64_t vi_reduce_scratch_elems(int64_t rows, int cols, int n_out);
+/* out[c] = sum_r x[r, c] (fp32 accumulation, fixed order); bias gradients of nn.Linear.  scratch: n_out = 1 */
+int vi_colsum(const void* x, int64_t ld, int dtype, float* out, int64_t rows, int cols, float* scratch,
+              int64_t scratch_elems, vi_stream_t stream);
 /* y = act(x), dx = dy * act'(x); act = VI_EPI_GELU (erf form, D/models/vilmodel.py:32-38) or VI_EPI_RELU.
  * The training forward keeps the pre-activation, so activations run as their own kernels there. */
 int vi_act_fwd(const void* x, void* y, int64_t n, int act, int dtype, vi_stream_t stream);
@@ -231,14 +235,15 @@ int vi_act_bwd(const void* x, const void* dy, void* dx, int64_t n, int act, int 
  * dgamma / dbeta [n_groups, 768] may be NULL; stats is a [rows, 2] fp32 scratch (mean, rstd). */
 int vi_add_ln_bwd(const float* a, const float* b, const float* gamma, float eps, const float* dy32, const void* dy16,
                   float* dx32, void* dx16, float* dgamma, float* dbeta, float* stats, int64_t rows,
-                  int n_groups, const int32_t* group_row_end, vi_stream_t stream);
+                  int n_groups, const int32_t* group_row_end, float* scratch, int64_t scratch_elems, vi_stream_t stream);
 /* small-feature linear of vi_embed_compose: dW[768, feat_dim] = dt^T feat, db[768] = colsum(dt) */
-int vi_feat_wgrad(const float* dt, const float* feat, int feat_dim, float* dW, float* db, int64_t rows, vi_stream_t stream);
+int vi_feat_wgrad(const float* dt, const float* feat, int feat_dim, float* dW, float* db, int64_t rows, float* scratch,
+                  int64_t scratch_elems, vi_stream_t stream);
 /* dst[idx[r]] += src[r] (idx != NULL) or dst[r % period] += src[r]: embedding / position table adjoints */
 int vi_scatter_add_rows(const float* src, const int64_t* idx, int period, float* dst, int64_t rows, vi_stream_t stream);
 /* adjoint of the dot-product tail of vi_ln_dot (out[r] = x[r] . w[g] + b[g]) */
-int vi_rowdot_bwd(const float* dout, const float* x, const float* w, float* dx, float* dw, float* db, int64_t rows,
-                  int n_groups, const int32_t* group_row_end, vi_stream_t stream);
+int vi_rowdot_bwd(const float* dout, const float* x, const float* w, float* dx, float* dw, float* db_cols, int64_t rows,
+                  int n_groups, const int32_t* group_row_end, float* scratch, int64_t scratch_elems, vi_stream_t stream);
 /* attention backward for one token stream (same operand conventions as vi_attn_fwd); d_affine -> device {dw, db}
  * of the GASA affine, accumulated (+=); dq / dk / dv have the dtype of q / k / v. */
 int vi_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,

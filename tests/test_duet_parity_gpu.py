@@ -154,3 +154,53 @@ def test_duet_api_graph_replay_equals_eager_launches(env):
     finally:
         model.use_cuda_graphs = True
         model.vln_bert.load_state_dict(sd)
+
+
+@pytest.mark.parametrize('graphs', [False, True])
+def test_context_cache_is_invisible(env, graphs):
+    """the per-episode cache of the [txt ; imagine] K / V projections (context_kv) never changes a result: a hit
+    returns what a recomputation returns, a new episode (new tensors, or the same tensor modified in place) misses"""
+    synth, model, _ = env
+    net = model.vln_bert
+    net.load_state_dict(synth.synth_state_dict(manifest('duet'), seed=0, gasa_stress=True))
+    net.precision = 'bf16'
+    model.use_cuda_graphs = graphs
+    eps = [to_dev(synth.to_torch(synth.duet_episode(synth.CFG1, s))) for s in (11, 12)]
+
+    def nav(ep, txt, img):
+        with torch.no_grad():
+            return model('navigation', {k: ep[k] for k in (
+                'txt_masks', 'gmap_img_embeds', 'gmap_step_ids', 'gmap_pos_fts', 'gmap_masks', 'gmap_pair_dists',
+                'gmap_visited_masks', 'gmap_vpids', 'vp_img_embeds', 'vp_pos_fts', 'vp_masks', 'vp_nav_masks',
+                'vp_cand_vpids', 'imagine_masks')} | {'txt_embeds': txt, 'imagine_embeds': img})['fused_logits'].clone()
+
+    try:
+        pre = []
+        for ep in eps:
+            with torch.no_grad():
+                txt = model('language', {'txt_ids': ep['txt_ids'], 'txt_masks': ep['txt_masks']})
+                img = model('imagine', {'imagine_feats': ep['imagine_feats'], 'imagine_masks': None})
+            pre.append((txt, img))
+        net.context_cache = False
+        want = [nav(ep, *p) for ep, p in zip(eps, pre)]
+        want = [nav(ep, *p) for ep, p in zip(eps, pre)]          # (graphs: second call is the replay)
+        net.context_cache = True
+        net.drop_context()
+        h0, m0 = net.context_hits, net.context_misses
+        for _ in range(3):                                        # interleaved episodes: every switch is a miss
+            for ep, p, w in zip(eps, pre, want):
+                assert torch.equal(nav(ep, *p), w)
+        assert net.context_misses - m0 == 6 and net.context_hits == h0
+        for _ in range(3):                                        # same episode again and again: hits
+            assert torch.equal(nav(eps[1], *pre[1]), want[1])
+        assert net.context_misses - m0 == 6 and net.context_hits - h0 == 3
+        txt, img = pre[1]
+        txt.mul_(0.5)                                             # in-place change of the context -> version bump -> miss
+        net.context_cache = False
+        w2 = nav(eps[1], txt, img)
+        net.context_cache = True
+        assert torch.equal(nav(eps[1], txt, img), w2)
+        assert not torch.equal(w2, want[1])
+    finally:
+        model.use_cuda_graphs = True
+        net.context_cache = True

@@ -65,13 +65,14 @@ PROTOTYPES = {
     'vi_copy_rows': [_p, _l, _l, _p, _p, _l, _l, _l, _i, _p],
     'vi_cast_bf16': [_p, _p, _l, _p],
     'vi_transpose': [_p, _l, _p, _l, _i, _i, _i, _i, _p],
-    'vi_colsum': [_p, _l, _i, _p, _l, _i, _p],
+    'vi_colsum': [_p, _l, _i, _p, _l, _i, _p, _l, _p],
+    'vi_reduce_scratch_elems': [_l, _i, _i],
     'vi_act_fwd': [_p, _p, _l, _i, _i, _p],
     'vi_act_bwd': [_p, _p, _p, _l, _i, _i, _p],
-    'vi_add_ln_bwd': [_p, _p, _p, _f, _p, _p, _p, _p, _p, _p, _p, _l, _i, _ip, _p],
-    'vi_feat_wgrad': [_p, _p, _i, _p, _p, _l, _p],
+    'vi_add_ln_bwd': [_p, _p, _p, _f, _p, _p, _p, _p, _p, _p, _p, _l, _i, _ip, _p, _l, _p],
+    'vi_feat_wgrad': [_p, _p, _i, _p, _p, _l, _p, _l, _p],
     'vi_scatter_add_rows': [_p, _p, _i, _p, _l, _p],
-    'vi_rowdot_bwd': [_p, _p, _p, _p, _p, _p, _l, _i, _ip, _p],
+    'vi_rowdot_bwd': [_p, _p, _p, _p, _p, _p, _l, _i, _ip, _p, _l, _p],
     'vi_attn_bwd': [_p, _l, _p, _l, _p, _l, _p, _l, _p, _l, _p, _l, _p, _l, _i, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
     'vi_duet_fuse_logits_bwd': [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
     'vi_cosine_loss_bwd': [_p, _p, _p, _p, _p, _i, _p],
@@ -80,6 +81,7 @@ for _name, _args in PROTOTYPES.items():
     _fn = getattr(lib, _name)            # AttributeError here = header/library mismatch: fail loudly
     _fn.argtypes = _args
     _fn.restype = _i
+lib.vi_reduce_scratch_elems.restype = C.c_int64
 lib.vi_last_error.argtypes = []
 lib.vi_last_error.restype = C.c_char_p
 

@@ -46,11 +46,28 @@ def transpose(src: torch.Tensor, pad_rows: Optional[int] = None) -> torch.Tensor
     return dst
 
 
+_SCRATCH = {}
+RED_CHUNK = 128
+
+
+def reduce_scratch(device, rows: int, cols: int, n_out: int) -> torch.Tensor:
+    """fp32 workspace of the two-stage column reductions (caller-owned, one per device, grown on demand; launches
+    that share it are ordered by the stream they run on)"""
+    need = n_out * ((rows + RED_CHUNK - 1) // RED_CHUNK) * cols
+    t = _SCRATCH.get(device)
+    if t is None or t.numel() < need:
+        t = torch.empty((max(need, 1 << 22),), dtype=F32, device=device)
+        _SCRATCH[device] = t
+    return t
+
+
 def colsum(x: torch.Tensor) -> torch.Tensor:
     rows, cols = x.shape
     out = torch.empty((cols,), dtype=F32, device=x.device)
-    check(lib.vi_colsum(x.data_ptr(), x.stride(0), _dt(x), out.data_ptr(), rows, cols, _stream()), 'vi_colsum')
-    _launched(1)
+    sc = reduce_scratch(x.device, rows, cols, 1)
+    check(lib.vi_colsum(x.data_ptr(), x.stride(0), _dt(x), out.data_ptr(), rows, cols, sc.data_ptr(), sc.numel(), _stream()),
+          'vi_colsum')
+    _launched(2)
     return out
 
 
@@ -191,10 +208,12 @@ class LayerNormFn(Function):
         dg = torch.empty((n_groups, HIDDEN), dtype=F32, device=a.device)
         dbt = torch.empty((n_groups, HIDDEN), dtype=F32, device=a.device)
         stats = torch.empty((rows, 2), dtype=F32, device=a.device)
+        sc = reduce_scratch(a.device, rows, HIDDEN, 2)
         check(lib.vi_add_ln_bwd(a.data_ptr(), _ptr(b), gamma.data_ptr(), ctx.eps, _ptr(dy32), _ptr(dy16), dx.data_ptr(), None,
                                 dg.data_ptr(), dbt.data_ptr(), stats.data_ptr(), rows, n_groups,
-                                _lib.int_array(list(ends)) if ends is not None else None, _stream()), 'vi_add_ln_bwd')
-        _launched(2)
+                                _lib.int_array(list(ends)) if ends is not None else None, sc.data_ptr(), sc.numel(), _stream()),
+              'vi_add_ln_bwd')
+        _launched(4)
         half = ctx.n_params // 2
         pg = [dg[i] if ctx.param_needs[i] else None for i in range(half)] + \
              [dbt[i] if ctx.param_needs[half + i] else None for i in range(half)]
@@ -287,8 +306,10 @@ class SmallLinearFn(Function):
         fd = feat.shape[1]
         dW = torch.empty(ctx.wshape, dtype=F32, device=dt.device)
         db = torch.empty((HIDDEN,), dtype=F32, device=dt.device) if ctx.has_b else None
-        check(lib.vi_feat_wgrad(dt.data_ptr(), feat.data_ptr(), fd, dW.data_ptr(), _ptr(db), dt.shape[0], _stream()), 'vi_feat_wgrad')
-        _launched(1)
+        sc = reduce_scratch(dt.device, dt.shape[0], HIDDEN, 17)
+        check(lib.vi_feat_wgrad(dt.data_ptr(), feat.data_ptr(), fd, dW.data_ptr(), _ptr(db), dt.shape[0], sc.data_ptr(), sc.numel(),
+                                _stream()), 'vi_feat_wgrad')
+        _launched(2)
         return None, dW, db
 
 
@@ -377,11 +398,13 @@ class RowDotFn(Function):
         n_groups = 1 if ends is None else len(ends)
         dx = torch.empty_like(x)
         dw = torch.empty((n_groups, HIDDEN), dtype=F32, device=x.device)
-        db = torch.empty((n_groups,), dtype=F32, device=x.device)
+        db = torch.empty((n_groups, HIDDEN), dtype=F32, device=x.device)       # the sum replicated over the columns
+        sc = reduce_scratch(x.device, rows, HIDDEN, 2)
         check(lib.vi_rowdot_bwd(dout.data_ptr(), x.data_ptr(), wstack.data_ptr(), dx.data_ptr(), dw.data_ptr(), db.data_ptr(), rows,
-                                n_groups, _lib.int_array(list(ends)) if ends is not None else None, _stream()), 'vi_rowdot_bwd')
-        _launched(2)
-        pg = [dw[i].view(1, HIDDEN) for i in range(ctx.n_heads)] + [db[i:i + 1] for i in range(ctx.n_heads)]
+                                n_groups, _lib.int_array(list(ends)) if ends is not None else None, sc.data_ptr(), sc.numel(),
+                                _stream()), 'vi_rowdot_bwd')
+        _launched(4)
+        pg = [dw[i].view(1, HIDDEN) for i in range(ctx.n_heads)] + [db[i, 0:1] for i in range(ctx.n_heads)]
         return (dx, None, None, None, None, *pg)
 
 

@@ -87,6 +87,11 @@ class LinearPack:
         v = self._pack.get()
         return (v['w16'] if lowp else v['w32']), v['b']
 
+    def get_token(self):
+        """changes whenever a source parameter does (in-place update or re-allocation)"""
+        self._pack.get()
+        return self._pack._key
+
     def get_t(self, lowp: bool, n_groups: int = 1):
         """per-group transposed weight [n_groups * K, N] (the B operand of the input-gradient GEMM), cached with
         the pack"""

@@ -14,6 +14,16 @@ constexpr int D = VI_HIDDEN;
 
 template <typename T> __device__ __forceinline__ float ldf(const T* p, long long i) { return to_f32<T>(p[i]); }
 
+struct RowGroups {
+  int n;
+  int end[4];
+};
+__device__ __forceinline__ int group_of_row(const RowGroups& g, long long row) {
+  int i = 0;
+  while (i < g.n - 1 && row >= g.end[i]) ++i;
+  return i;
+}
+
 // ---------------------------------------------------------------------------------------------
 // dst[c, r] = src[r, c]  (rows x cols -> cols x ldd, columns r >= rows of dst are zero up to pad_rows)
 // ---------------------------------------------------------------------------------------------
@@ -38,26 +48,59 @@ __global__ void __launch_bounds__(256) transpose_kernel(const T* __restrict__ sr
 }
 
 // ---------------------------------------------------------------------------------------------
-// out[c] = sum_r x[r, c] over a row range; one CTA per 32-column slab, fixed order -> deterministic
+// Column reductions over rows, deterministic and parallel over the rows: stage 1 reduces RED_CHUNK-row chunks into a
+// caller-provided scratch [n_out][n_chunks][cols]; stage 2 sums the chunks of each output (of each row group) in a
+// fixed order.  Row groups end on multiples of 128 rows (host contract), so a chunk never straddles two groups.
 // ---------------------------------------------------------------------------------------------
+constexpr int RED_CHUNK = 128;
+
+__device__ __forceinline__ float2 ld2f(const float* p) { return *reinterpret_cast<const float2*>(p); }
+__device__ __forceinline__ float2 ld2f(const bf16* p) {
+  const __nv_bfloat162 t = *reinterpret_cast<const __nv_bfloat162*>(p);
+  return __bfloat1622float2(t);
+}
+
+// out[c] = sum_r x[r, c]; grid (cols / 64, n_chunks), 256 threads: warp w takes rows w, w+8, ... of the chunk, a lane 2 columns
 template <typename T>
-__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, long long ld, float* __restrict__ out,
-                                                     long long rows, int cols) {
+__global__ void __launch_bounds__(256) colsum_partial_kernel(const T* __restrict__ x, long long ld, float* __restrict__ part,
+                                                             long long rows, int cols) {
   pdl_enter();
-  __shared__ float part[8][33];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + tx;
-  float s = 0.f;
+  __shared__ float2 red[8][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 64 + 2 * lane;
+  const long long r0 = (long long)blockIdx.y * RED_CHUNK;
+  const long long r1 = r0 + RED_CHUNK < rows ? r0 + RED_CHUNK : rows;
+  float2 s = make_float2(0.f, 0.f);
   if (c < cols)
-    for (long long r = ty; r < rows; r += 8) s += ldf(x, r * ld + c);
-  part[ty][tx] = s;
+    for (long long r = r0 + warp; r < r1; r += 8) {
+      const float2 v = ld2f(x + r * ld + c);
+      s.x += v.x; s.y += v.y;
+    }
+  red[warp][lane] = s;
   __syncthreads();
-  if (ty == 0 && c < cols) {
-    float t = 0.f;
+  if (warp == 0 && c < cols) {
+    float2 t = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) t += part[i][tx];
-    out[c] = t;
+    for (int i = 0; i < 8; ++i) { t.x += red[i][lane].x; t.y += red[i][lane].y; }
+    *reinterpret_cast<float2*>(part + (long long)blockIdx.y * cols + c) = t;
   }
+}
+
+// out[o][g][c] = sum over the chunks of group g of part[o][chunk][c]; grid (ceil(cols / 256), n_groups, n_out)
+__global__ void __launch_bounds__(256) chunk_sum_kernel(const float* __restrict__ part, float* __restrict__ out, int n_chunks,
+                                                        int cols, long long rows, const RowGroups grp, long long out_stride) {
+  pdl_enter();
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= cols) return;
+  const int gi = blockIdx.y, o = blockIdx.z;
+  const long long g0 = gi == 0 ? 0 : grp.end[gi - 1];
+  long long g1 = gi == grp.n - 1 ? rows : grp.end[gi];
+  if (g1 > rows) g1 = rows;
+  const int k0 = (int)(g0 / RED_CHUNK), k1 = (int)((g1 + RED_CHUNK - 1) / RED_CHUNK);
+  const float* pp = part + ((long long)o * n_chunks) * cols + c;
+  float t = 0.f;
+  for (int k = k0; k < k1; ++k) t += pp[(long long)k * cols];
+  out[o * out_stride + (long long)gi * cols + c] = t;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -68,23 +111,83 @@ __device__ __forceinline__ float gelu_grad(float x) {
   const float pdf = 0.39894228040143267794f * expf(-0.5f * x * x);
   return cdf + x * pdf;
 }
+// 8 elements per thread (16-byte accesses for bf16, 2 x 16 for fp32); n is a multiple of 8 on this path (768 / 3072 wide
+// rows); a scalar tail covers anything else
+template <typename T> struct Vec8;
+template <> struct Vec8<bf16> {
+  uint4 raw;
+  __device__ __forceinline__ void load(const bf16* p) { raw = *reinterpret_cast<const uint4*>(p); }
+  __device__ __forceinline__ void store(bf16* p) const { *reinterpret_cast<uint4*>(p) = raw; }
+  __device__ __forceinline__ void get(float (&f)[8]) const {
+    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+      f[2 * i] = t.x; f[2 * i + 1] = t.y;
+    }
+  }
+  __device__ __forceinline__ void set(const float (&f)[8]) {
+    raw.x = pack_bf16x2(f[0], f[1]); raw.y = pack_bf16x2(f[2], f[3]);
+    raw.z = pack_bf16x2(f[4], f[5]); raw.w = pack_bf16x2(f[6], f[7]);
+  }
+};
+template <> struct Vec8<float> {
+  float4 a, b;
+  __device__ __forceinline__ void load(const float* p) { a = *reinterpret_cast<const float4*>(p); b = *reinterpret_cast<const float4*>(p + 4); }
+  __device__ __forceinline__ void store(float* p) const { *reinterpret_cast<float4*>(p) = a; *reinterpret_cast<float4*>(p + 4) = b; }
+  __device__ __forceinline__ void get(float (&f)[8]) const {
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+  }
+  __device__ __forceinline__ void set(const float (&f)[8]) {
+    a = make_float4(f[0], f[1], f[2], f[3]); b = make_float4(f[4], f[5], f[6], f[7]);
+  }
+};
+
 template <typename T>
 __global__ void __launch_bounds__(256) act_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, long long n, int act) {
   pdl_enter();
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
   if (i >= n) return;
-  const float v = ldf(x, i);
-  y[i] = from_f32<T>(act == VI_EPI_GELU ? gelu_erf(v) : fmaxf(v, 0.f));
+  if (i + 8 <= n) {
+    Vec8<T> v;
+    v.load(x + i);
+    float f[8];
+    v.get(f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = act == VI_EPI_GELU ? gelu_erf(f[j]) : fmaxf(f[j], 0.f);
+    v.set(f);
+    v.store(y + i);
+  } else {
+    for (long long j = i; j < n; ++j) {
+      const float v = ldf(x, j);
+      y[j] = from_f32<T>(act == VI_EPI_GELU ? gelu_erf(v) : fmaxf(v, 0.f));
+    }
+  }
 }
 // dx = dy * act'(x)
 template <typename T>
 __global__ void __launch_bounds__(256) act_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dx,
                                                       long long n, int act) {
   pdl_enter();
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
   if (i >= n) return;
-  const float v = ldf(x, i), g = ldf(dy, i);
-  dx[i] = from_f32<T>(act == VI_EPI_GELU ? g * gelu_grad(v) : (v > 0.f ? g : 0.f));
+  if (i + 8 <= n) {
+    Vec8<T> vx, vg;
+    vx.load(x + i);
+    vg.load(dy + i);
+    float f[8], g[8];
+    vx.get(f);
+    vg.get(g);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] = act == VI_EPI_GELU ? g[j] * gelu_grad(f[j]) : (f[j] > 0.f ? g[j] : 0.f);
+    vg.set(g);
+    vg.store(dx + i);
+  } else {
+    for (long long j = i; j < n; ++j) {
+      const float v = ldf(x, j), g = ldf(dy, j);
+      dx[j] = from_f32<T>(act == VI_EPI_GELU ? g * gelu_grad(v) : (v > 0.f ? g : 0.f));
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -92,15 +195,6 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const T* __restrict__ x, c
 //   dx[r] = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma      (one warp per row)
 //   stats[r] = {mean, rstd} for the parameter-gradient pass
 // ---------------------------------------------------------------------------------------------
-struct RowGroups {
-  int n;
-  int end[4];
-};
-__device__ __forceinline__ int group_of_row(const RowGroups& g, long long row) {
-  int i = 0;
-  while (i < g.n - 1 && row >= g.end[i]) ++i;
-  return i;
-}
 
 __global__ void __launch_bounds__(128) ln_bwd_dx_kernel(const float* __restrict__ a, const float* __restrict__ b,
                                                         const float* __restrict__ gamma, float eps,
@@ -168,55 +262,59 @@ __global__ void __launch_bounds__(128) ln_bwd_dx_kernel(const float* __restrict_
   if (lane == 0) { stats[2 * row] = mean; stats[2 * row + 1] = rstd; }
 }
 
-// dgamma[g, c] = sum_r dy * xhat, dbeta[g, c] = sum_r dy   over the rows of group g; grid (24, n_groups)
-__global__ void __launch_bounds__(256) ln_bwd_param_kernel(const float* __restrict__ a, const float* __restrict__ b,
-                                                           const float* __restrict__ dy32, const bf16* __restrict__ dy16,
-                                                           const float* __restrict__ stats, float* __restrict__ dgamma,
-                                                           float* __restrict__ dbeta, long long rows, const RowGroups grp) {
+// stage 1 of dgamma[c] = sum_r dy * xhat, dbeta[c] = sum_r dy: partials per 128-row chunk into part[2][n_chunks][768];
+// grid (768 / 64, n_chunks), 256 threads (stage 2: chunk_sum_kernel per row group)
+__global__ void __launch_bounds__(256) ln_bwd_param_partial_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                                   const float* __restrict__ dy32, const bf16* __restrict__ dy16,
+                                                                   const float* __restrict__ stats, float* __restrict__ part,
+                                                                   long long rows, int n_chunks) {
   pdl_enter();
-  __shared__ float pg[8][33], pb[8][33];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + tx;
-  const int gi = blockIdx.y;
-  const long long r0 = gi == 0 ? 0 : grp.end[gi - 1];
-  long long r1 = gi == grp.n - 1 ? rows : grp.end[gi];
-  if (r1 > rows) r1 = rows;
-  float sg = 0.f, sb = 0.f;
-  for (long long r = r0 + ty; r < r1; r += 8) {
-    float x = a[r * D + c];
-    if (b) x += b[r * D + c];
-    float d = dy32 ? dy32[r * D + c] : 0.f;
-    if (dy16) d += __bfloat162float(dy16[r * D + c]);
-    const float xh = (x - stats[2 * r]) * stats[2 * r + 1];
-    sg = fmaf(d, xh, sg);
-    sb += d;
+  __shared__ float2 rg[8][32], rb[8][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 64 + 2 * lane;
+  const long long r0 = (long long)blockIdx.y * RED_CHUNK;
+  const long long r1 = r0 + RED_CHUNK < rows ? r0 + RED_CHUNK : rows;
+  float2 sg = make_float2(0.f, 0.f), sb = make_float2(0.f, 0.f);
+  for (long long r = r0 + warp; r < r1; r += 8) {
+    float2 x = ld2f(a + r * D + c);
+    if (b) { const float2 u = ld2f(b + r * D + c); x.x += u.x; x.y += u.y; }
+    float2 d = make_float2(0.f, 0.f);
+    if (dy32) d = ld2f(dy32 + r * D + c);
+    if (dy16) { const float2 u = ld2f(dy16 + r * D + c); d.x += u.x; d.y += u.y; }
+    const float mean = stats[2 * r], rstd = stats[2 * r + 1];
+    sg.x = fmaf(d.x, (x.x - mean) * rstd, sg.x);
+    sg.y = fmaf(d.y, (x.y - mean) * rstd, sg.y);
+    sb.x += d.x; sb.y += d.y;
   }
-  pg[ty][tx] = sg;
-  pb[ty][tx] = sb;
+  rg[warp][lane] = sg;
+  rb[warp][lane] = sb;
   __syncthreads();
-  if (ty == 0) {
-    float t = 0.f, u = 0.f;
+  if (warp == 0) {
+    float2 t = make_float2(0.f, 0.f), u = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { t += pg[i][tx]; u += pb[i][tx]; }
-    dgamma[gi * D + c] = t;
-    dbeta[gi * D + c] = u;
+    for (int i = 0; i < 8; ++i) { t.x += rg[i][lane].x; t.y += rg[i][lane].y; u.x += rb[i][lane].x; u.y += rb[i][lane].y; }
+    *reinterpret_cast<float2*>(part + (long long)blockIdx.y * D + c) = t;
+    *reinterpret_cast<float2*>(part + ((long long)n_chunks + blockIdx.y) * D + c) = u;
   }
 }
 
 // ---------------------------------------------------------------------------------------------
 // small-feature linear  t = feat W^T + b  (feat_dim <= 16):  dW[c, k] = sum_r dt[r, c] feat[r, k], db[c] = sum_r dt[r, c]
-// one CTA per 32-column slab, fixed order
+// stage 1: part[17][n_chunks][768] (k = 16 is the bias), grid (768 / 32, n_chunks), 256 threads; stage 2 sums the chunks
+// and writes dW (transposed to [768, fd]) / db
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) feat_wgrad_kernel(const float* __restrict__ dt, const float* __restrict__ feat, int fd,
-                                                         float* __restrict__ dW, float* __restrict__ db, long long rows) {
+__global__ void __launch_bounds__(256) feat_wgrad_partial_kernel(const float* __restrict__ dt, const float* __restrict__ feat, int fd,
+                                                                 float* __restrict__ part, long long rows, int n_chunks) {
   pdl_enter();
-  __shared__ float part[8][17][33];
+  __shared__ float red[8][17][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + tx;
+  const long long r0 = (long long)blockIdx.y * RED_CHUNK;
+  const long long r1 = r0 + RED_CHUNK < rows ? r0 + RED_CHUNK : rows;
   float acc[17];
 #pragma unroll
   for (int k = 0; k < 17; ++k) acc[k] = 0.f;
-  for (long long r = ty; r < rows; r += 8) {
+  for (long long r = r0 + ty; r < r1; r += 8) {
     const float d = dt[r * D + c];
 #pragma unroll
     for (int k = 0; k < 16; ++k)
@@ -224,17 +322,26 @@ __global__ void __launch_bounds__(256) feat_wgrad_kernel(const float* __restrict
     acc[16] += d;
   }
 #pragma unroll
-  for (int k = 0; k < 17; ++k) part[ty][k][tx] = acc[k];
+  for (int k = 0; k < 17; ++k) red[ty][k][tx] = acc[k];
   __syncthreads();
   if (ty == 0) {
     for (int k = 0; k < 17; ++k) {
       float t = 0.f;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) t += part[i][k][tx];
-      if (k < fd) dW[(long long)c * fd + k] = t;
-      else if (k == 16 && db) db[c] = t;
+      for (int i = 0; i < 8; ++i) t += red[i][k][tx];
+      part[((long long)k * n_chunks + blockIdx.y) * D + c] = t;
     }
   }
+}
+__global__ void __launch_bounds__(256) feat_wgrad_final_kernel(const float* __restrict__ part, int fd, float* __restrict__ dW,
+                                                               float* __restrict__ db, int n_chunks) {
+  pdl_enter();
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  const int k = blockIdx.y;                      // 0..16
+  if (c >= D || (k < 16 && k >= fd) || (k == 16 && !db)) return;
+  float t = 0.f;
+  for (int i = 0; i < n_chunks; ++i) t += part[((long long)k * n_chunks + i) * D + c];
+  if (k < 16) dW[(long long)c * fd + k] = t; else db[c] = t;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -263,32 +370,36 @@ __global__ void __launch_bounds__(128) rowdot_bwd_dx_kernel(const float* __restr
   const float g = dout[row];
   for (int c = lane; c < D; c += 32) dx[row * D + c] = g * wg[c];
 }
-__global__ void __launch_bounds__(256) rowdot_bwd_w_kernel(const float* __restrict__ dout, const float* __restrict__ x,
-                                                           float* __restrict__ dw, float* __restrict__ db, long long rows,
-                                                           const RowGroups grp) {
+// stage 1 of dw[g, c] = sum_r dout[r] x[r, c], db[g] = sum_r dout[r]: part[2][n_chunks][768] (the bias partial is replicated
+// over the columns so that stage 2 is the shared chunk_sum_kernel); grid (768 / 64, n_chunks)
+__global__ void __launch_bounds__(256) rowdot_bwd_w_partial_kernel(const float* __restrict__ dout, const float* __restrict__ x,
+                                                                   float* __restrict__ part, long long rows, int n_chunks) {
   pdl_enter();
-  __shared__ float pw[8][33], pb[8][33];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + tx;
-  const int gi = blockIdx.y;
-  const long long r0 = gi == 0 ? 0 : grp.end[gi - 1];
-  long long r1 = gi == grp.n - 1 ? rows : grp.end[gi];
-  if (r1 > rows) r1 = rows;
-  float sw = 0.f, sb = 0.f;
-  for (long long r = r0 + ty; r < r1; r += 8) {
+  __shared__ float2 rw[8][32];
+  __shared__ float rbias[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 64 + 2 * lane;
+  const long long r0 = (long long)blockIdx.y * RED_CHUNK;
+  const long long r1 = r0 + RED_CHUNK < rows ? r0 + RED_CHUNK : rows;
+  float2 sw = make_float2(0.f, 0.f);
+  float sb = 0.f;
+  for (long long r = r0 + warp; r < r1; r += 8) {
     const float g = dout[r];
-    sw = fmaf(g, x[r * D + c], sw);
+    const float2 v = ld2f(x + r * D + c);
+    sw.x = fmaf(g, v.x, sw.x);
+    sw.y = fmaf(g, v.y, sw.y);
     sb += g;
   }
-  pw[ty][tx] = sw;
-  pb[ty][tx] = sb;
+  rw[warp][lane] = sw;
+  if (lane == 0) rbias[warp] = sb;
   __syncthreads();
-  if (ty == 0) {
-    float t = 0.f, u = 0.f;
+  if (warp == 0) {
+    float2 t = make_float2(0.f, 0.f);
+    float u = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { t += pw[i][tx]; u += pb[i][tx]; }
-    dw[gi * D + c] = t;
-    if (blockIdx.x == 0 && tx == 0 && db) db[gi] = u;
+    for (int i = 0; i < 8; ++i) { t.x += rw[i][lane].x; t.y += rw[i][lane].y; u += rbias[i]; }
+    *reinterpret_cast<float2*>(part + (long long)blockIdx.y * D + c) = t;
+    *reinterpret_cast<float2*>(part + ((long long)n_chunks + blockIdx.y) * D + c) = make_float2(u, u);
   }
 }
 
@@ -553,6 +664,12 @@ inline bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
 #define ST(s) reinterpret_cast<cudaStream_t>(s)
 
+// vi_attn_bwd.cu: tensor-core kernel for bf16 operands; returns 1 when the problem does not fit it
+int vi_attn_bwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* dout,
+                   int64_t ldo, void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv,
+                   const uint8_t* key_mask, const float* pair_dist, const float* bias_affine, float* d_affine, int B, int H,
+                   int Lq, int Lk, int mask_mode, cudaStream_t st);
+
 extern "C" int vi_transpose(const void* src, int64_t ld, void* dst, int64_t ldd, int rows, int cols, int pad_rows, int dtype,
                             vi_stream_t stream) {
   VI_CHECK_ARG(src && dst && rows > 0 && cols > 0 && pad_rows >= rows && ld >= cols && ldd >= pad_rows, "vi_transpose: bad operands");
@@ -566,22 +683,42 @@ extern "C" int vi_transpose(const void* src, int64_t ld, void* dst, int64_t ldd,
   return VI_OK;
 }
 
-extern "C" int vi_colsum(const void* x, int64_t ld, int dtype, float* out, int64_t rows, int cols, vi_stream_t stream) {
-  VI_CHECK_ARG(x && out && cols > 0 && ld >= cols, "vi_colsum: bad operands");
-  dim3 grid((cols + 31) / 32);
+inline int red_chunks(long long rows) { return (int)((rows + RED_CHUNK - 1) / RED_CHUNK); }
+inline RowGroups one_group() {
+  RowGroups g;
+  g.n = 1;
+  for (int i = 0; i < 4; ++i) g.end[i] = 0x7fffffff;
+  return g;
+}
+
+extern "C" int64_t vi_reduce_scratch_elems(int64_t rows, int cols, int n_out) {
+  return (int64_t)n_out * ((rows + RED_CHUNK - 1) / RED_CHUNK) * cols;
+}
+
+extern "C" int vi_colsum(const void* x, int64_t ld, int dtype, float* out, int64_t rows, int cols, float* scratch,
+                         int64_t scratch_elems, vi_stream_t stream) {
+  VI_CHECK_ARG(x && out && scratch && rows > 0 && cols > 0 && ld >= cols, "vi_colsum: bad operands");
+  VI_CHECK_ARG(cols % 2 == 0 && ld % 2 == 0 && ((uintptr_t)x & 7) == 0, "vi_colsum: columns / leading dimension must be even, x 8-byte aligned");
+  const int nch = red_chunks(rows);
+  VI_CHECK_ARG(scratch_elems >= (int64_t)nch * cols, "vi_colsum: scratch too small (%lld < %lld)", (long long)scratch_elems,
+               (long long)nch * cols);
+  dim3 grid((cols + 63) / 64, nch);
   if (dtype == VI_DT_BF16)
-    VI_CUDA(vi_launch(colsum_kernel<bf16>, grid, dim3(256), 0, ST(stream), reinterpret_cast<const bf16*>(x), (long long)ld, out,
-                      (long long)rows, cols));
+    VI_CUDA(vi_launch(colsum_partial_kernel<bf16>, grid, dim3(256), 0, ST(stream), reinterpret_cast<const bf16*>(x), (long long)ld,
+                      scratch, (long long)rows, cols));
   else
-    VI_CUDA(vi_launch(colsum_kernel<float>, grid, dim3(256), 0, ST(stream), reinterpret_cast<const float*>(x), (long long)ld, out,
-                      (long long)rows, cols));
+    VI_CUDA(vi_launch(colsum_partial_kernel<float>, grid, dim3(256), 0, ST(stream), reinterpret_cast<const float*>(x), (long long)ld,
+                      scratch, (long long)rows, cols));
+  VI_CUDA(vi_launch(chunk_sum_kernel, dim3((cols + 255) / 256, 1, 1), dim3(256), 0, ST(stream), (const float*)scratch, out, nch, cols,
+                    (long long)rows, one_group(), (long long)0));
   return VI_OK;
 }
 
 extern "C" int vi_act_fwd(const void* x, void* y, int64_t n, int act, int dtype, vi_stream_t stream) {
   VI_CHECK_ARG(x && y && (act == VI_EPI_GELU || act == VI_EPI_RELU), "vi_act_fwd: bad operands");
   if (n <= 0) return VI_OK;
-  dim3 grid((unsigned)((n + 255) / 256));
+  VI_CHECK_ARG((((uintptr_t)x | (uintptr_t)y) & 15) == 0, "vi_act_fwd: operands must be 16-byte aligned");
+  dim3 grid((unsigned)((n + 2047) / 2048));
   if (dtype == VI_DT_BF16)
     VI_CUDA(vi_launch(act_fwd_kernel<bf16>, grid, dim3(256), 0, ST(stream), reinterpret_cast<const bf16*>(x),
                       reinterpret_cast<bf16*>(y), (long long)n, act));
@@ -594,7 +731,8 @@ extern "C" int vi_act_fwd(const void* x, void* y, int64_t n, int act, int dtype,
 extern "C" int vi_act_bwd(const void* x, const void* dy, void* dx, int64_t n, int act, int dtype, vi_stream_t stream) {
   VI_CHECK_ARG(x && dy && dx && (act == VI_EPI_GELU || act == VI_EPI_RELU), "vi_act_bwd: bad operands");
   if (n <= 0) return VI_OK;
-  dim3 grid((unsigned)((n + 255) / 256));
+  VI_CHECK_ARG((((uintptr_t)x | (uintptr_t)dy | (uintptr_t)dx) & 15) == 0, "vi_act_bwd: operands must be 16-byte aligned");
+  dim3 grid((unsigned)((n + 2047) / 2048));
   if (dtype == VI_DT_BF16)
     VI_CUDA(vi_launch(act_bwd_kernel<bf16>, grid, dim3(256), 0, ST(stream), reinterpret_cast<const bf16*>(x),
                       reinterpret_cast<const bf16*>(dy), reinterpret_cast<bf16*>(dx), (long long)n, act));
@@ -606,25 +744,39 @@ extern "C" int vi_act_bwd(const void* x, const void* dy, void* dx, int64_t n, in
 
 extern "C" int vi_add_ln_bwd(const float* a, const float* b, const float* gamma, float eps, const float* dy32, const void* dy16,
                              float* dx32, void* dx16, float* dgamma, float* dbeta, float* stats, int64_t rows, int n_groups,
-                             const int32_t* group_row_end, vi_stream_t stream) {
+                             const int32_t* group_row_end, float* scratch, int64_t scratch_elems, vi_stream_t stream) {
   RowGroups grp;
   VI_CHECK_ARG(make_groups(grp, n_groups, group_row_end), "vi_add_ln_bwd: bad row groups");
+  for (int g = 0; g + 1 < n_groups; ++g)
+    VI_CHECK_ARG(group_row_end[g] % RED_CHUNK == 0, "vi_add_ln_bwd: row groups must end on multiples of %d rows", RED_CHUNK);
   VI_CHECK_ARG(a && gamma && (dy32 || dy16) && (dx32 || dx16) && stats, "vi_add_ln_bwd: null operand");
   VI_CHECK_ARG(aligned16(a) && aligned16(b) && aligned16(gamma) && aligned16(dy32) && aligned16(dx32) &&
                    ((uintptr_t)dx16 & 7) == 0, "vi_add_ln_bwd: misaligned operands");
   if (rows <= 0) return VI_OK;
   VI_CUDA(vi_launch(ln_bwd_dx_kernel, dim3((unsigned)((rows + 3) / 4)), dim3(128), 0, ST(stream), a, b, gamma, eps, dy32,
                     reinterpret_cast<const bf16*>(dy16), dx32, reinterpret_cast<bf16*>(dx16), stats, (long long)rows, grp));
-  if (dgamma && dbeta)
-    VI_CUDA(vi_launch(ln_bwd_param_kernel, dim3(D / 32, n_groups), dim3(256), 0, ST(stream), a, b, dy32,
-                      reinterpret_cast<const bf16*>(dy16), (const float*)stats, dgamma, dbeta, (long long)rows, grp));
+  if (dgamma && dbeta) {
+    const int nch = red_chunks(rows);
+    VI_CHECK_ARG(scratch && scratch_elems >= (int64_t)2 * nch * D, "vi_add_ln_bwd: scratch too small");
+    VI_CUDA(vi_launch(ln_bwd_param_partial_kernel, dim3(D / 64, nch), dim3(256), 0, ST(stream), a, b, dy32,
+                      reinterpret_cast<const bf16*>(dy16), (const float*)stats, scratch, (long long)rows, nch));
+    // output 0 -> dgamma[n_groups, 768], output 1 -> dbeta[n_groups, 768]
+    VI_CUDA(vi_launch(chunk_sum_kernel, dim3(D / 256, n_groups, 1), dim3(256), 0, ST(stream), (const float*)scratch, dgamma, nch, D,
+                      (long long)rows, grp, (long long)0));
+    VI_CUDA(vi_launch(chunk_sum_kernel, dim3(D / 256, n_groups, 1), dim3(256), 0, ST(stream),
+                      (const float*)(scratch + (long long)nch * D), dbeta, nch, D, (long long)rows, grp, (long long)0));
+  }
   return VI_OK;
 }
 
 extern "C" int vi_feat_wgrad(const float* dt, const float* feat, int feat_dim, float* dW, float* db, int64_t rows,
-                             vi_stream_t stream) {
-  VI_CHECK_ARG(dt && feat && dW && feat_dim > 0 && feat_dim <= 16, "vi_feat_wgrad: bad operands");
-  VI_CUDA(vi_launch(feat_wgrad_kernel, dim3(D / 32), dim3(256), 0, ST(stream), dt, feat, feat_dim, dW, db, (long long)rows));
+                             float* scratch, int64_t scratch_elems, vi_stream_t stream) {
+  VI_CHECK_ARG(dt && feat && dW && feat_dim > 0 && feat_dim <= 16 && rows > 0, "vi_feat_wgrad: bad operands");
+  const int nch = red_chunks(rows);
+  VI_CHECK_ARG(scratch && scratch_elems >= (int64_t)17 * nch * D, "vi_feat_wgrad: scratch too small");
+  VI_CUDA(vi_launch(feat_wgrad_partial_kernel, dim3(D / 32, nch), dim3(256), 0, ST(stream), dt, feat, feat_dim, scratch,
+                    (long long)rows, nch));
+  VI_CUDA(vi_launch(feat_wgrad_final_kernel, dim3(D / 256, 17), dim3(256), 0, ST(stream), (const float*)scratch, feat_dim, dW, db, nch));
   return VI_OK;
 }
 
@@ -636,14 +788,24 @@ extern "C" int vi_scatter_add_rows(const float* src, const int64_t* idx, int per
   return VI_OK;
 }
 
-extern "C" int vi_rowdot_bwd(const float* dout, const float* x, const float* w, float* dx, float* dw, float* db, int64_t rows,
-                             int n_groups, const int32_t* group_row_end, vi_stream_t stream) {
+extern "C" int vi_rowdot_bwd(const float* dout, const float* x, const float* w, float* dx, float* dw, float* db_cols, int64_t rows,
+                             int n_groups, const int32_t* group_row_end, float* scratch, int64_t scratch_elems,
+                             vi_stream_t stream) {
   RowGroups grp;
   VI_CHECK_ARG(make_groups(grp, n_groups, group_row_end), "vi_rowdot_bwd: bad row groups");
-  VI_CHECK_ARG(dout && x && w && dx && dw, "vi_rowdot_bwd: null operand");
+  for (int g = 0; g + 1 < n_groups; ++g)
+    VI_CHECK_ARG(group_row_end[g] % RED_CHUNK == 0, "vi_rowdot_bwd: row groups must end on multiples of %d rows", RED_CHUNK);
+  VI_CHECK_ARG(dout && x && w && dx && dw && db_cols, "vi_rowdot_bwd: null operand");
   if (rows <= 0) return VI_OK;
+  const int nch = red_chunks(rows);
+  VI_CHECK_ARG(scratch && scratch_elems >= (int64_t)2 * nch * D, "vi_rowdot_bwd: scratch too small");
   VI_CUDA(vi_launch(rowdot_bwd_dx_kernel, dim3((unsigned)((rows + 3) / 4)), dim3(128), 0, ST(stream), dout, w, dx, (long long)rows, grp));
-  VI_CUDA(vi_launch(rowdot_bwd_w_kernel, dim3(D / 32, n_groups), dim3(256), 0, ST(stream), dout, x, dw, db, (long long)rows, grp));
+  VI_CUDA(vi_launch(rowdot_bwd_w_partial_kernel, dim3(D / 64, nch), dim3(256), 0, ST(stream), dout, x, scratch, (long long)rows, nch));
+  VI_CUDA(vi_launch(chunk_sum_kernel, dim3(D / 256, n_groups, 1), dim3(256), 0, ST(stream), (const float*)scratch, dw, nch, D,
+                    (long long)rows, grp, (long long)0));
+  // db_cols[g, c] = sum_r dout[r] for every column c (replicated); the caller reads column 0
+  VI_CUDA(vi_launch(chunk_sum_kernel, dim3(D / 256, n_groups, 1), dim3(256), 0, ST(stream),
+                    (const float*)(scratch + (long long)nch * D), db_cols, nch, D, (long long)rows, grp, (long long)0));
   return VI_OK;
 }
 
@@ -656,6 +818,12 @@ extern "C" int vi_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ld
   VI_CHECK_ARG(((size_t)Lk * (65 * 2 + 64 * 2 + 1) + 8 * (size_t)(128 + 2 * Lk)) * sizeof(float) <= 220 * 1024,
                "vi_attn_bwd: Lk=%d keys do not fit the 220 KB shared-memory tile", Lk);
   VI_CHECK_ARG(!pair_dist || bias_affine, "vi_attn_bwd: pair_dist needs bias_affine");
+  VI_CHECK_ARG(H * 64 <= ldq && H * 64 <= ldk && H * 64 <= ldv && H * 64 <= ldo, "vi_attn_bwd: leading dimensions smaller than H*64");
+  if (dtype == VI_DT_BF16 && !getenv("VI_ATTN_BWD_SIMT")) {
+    const int rc = vi_attn_bwd_tc(q, ldq, k, ldk, v, ldv, dout, ldo, dq, lddq, dk, lddk, dv, lddv, key_mask, pair_dist,
+                                  bias_affine, d_affine, B, H, Lq, Lk, mask_mode, ST(stream));
+    if (rc <= 0) return rc;            // launched (0) or failed (< 0); 1 = does not fit -> fp32-arithmetic kernel below
+  }
   AttnBwdParams p;
   p.q = q; p.ldq = ldq; p.k = k; p.ldk = ldk; p.v = v; p.ldv = ldv; p.dout = dout; p.ldo = ldo;
   p.dq = dq; p.lddq = lddq; p.dk = dk; p.lddk = lddk; p.dv = dv; p.lddv = lddv;

@@ -90,13 +90,31 @@ class AlignRows:
         return self
 
 
+_ALIGN_ROWS = collections.OrderedDict()
+
+
+def _align_rows(B, L, I, flags, noun_phrase_segs, dev):
+    """AlignRows of a batch, kept for the last few batches: an iteration that is replayed on the same episode batch
+    (CUDA-graph capture of a fine-tuning step, benchmarks) must not rebuild and re-upload the index arrays.  The key holds
+    the CONTENT of the ragged lists, not their identity."""
+    key = (B, L, I, str(dev), tuple(tuple(f) for f in flags),
+           tuple(tuple(tuple(tuple(sp) for sp in spans) for spans in segs) for segs in noun_phrase_segs))
+    rows = _ALIGN_ROWS.get(key)
+    if rows is None:
+        rows = AlignRows(B, L, I, flags, noun_phrase_segs).to(dev)
+        _ALIGN_ROWS[key] = rows
+        while len(_ALIGN_ROWS) > 4:
+            _ALIGN_ROWS.popitem(last=False)
+    return rows
+
+
 def align_forward(model, align_txt_embeds, align_imagine_embeds, flags, noun_phrase_segs, lowp: bool):
     """Shared by DUET and HAMT.  Returns (loss 0-d tensor, imagine embeds with projected rows written back)."""
     cfg = model.config
     B, L, _ = align_txt_embeds.shape
     I = align_imagine_embeds.shape[1]
     dev = align_txt_embeds.device
-    rows = AlignRows(B, L, I, flags, noun_phrase_segs).to(dev)
+    rows = _align_rows(B, L, I, flags, noun_phrase_segs, dev)
     txt = _f32c(align_txt_embeds).view(B * L, HIDDEN)
     img = _f32c(align_imagine_embeds).view(B * I, HIDDEN)
     out = img.clone()
@@ -193,6 +211,9 @@ class GlocalTextPathNavCMT(nn.Module):
         self.precision = os.environ.get('VLN_IMAGINE_PRECISION', 'bf16')
         self._packs = None
         self._ids = _IdTable()
+        self.context_cache = os.environ.get('VLN_IMAGINE_CONTEXT_CACHE', '1') != '0'
+        self._ctx_slots = {}
+        self.context_hits = self.context_misses = 0
 
     # -- derived weights ------------------------------------------------------------------------
     def _pk(self):
@@ -222,6 +243,7 @@ class GlocalTextPathNavCMT(nn.Module):
 
     def _apply(self, fn, *a, **k):          # .cuda() / .to(): derived tensors are rebuilt lazily
         self._packs = None
+        self._ctx_slots = {}
         return super()._apply(fn, *a, **k)
 
     @property
@@ -302,18 +324,19 @@ class GlocalTextPathNavCMT(nn.Module):
     def forward_navigation_per_step(self, txt_embeds, txt_masks, gmap_img_embeds, gmap_step_ids, gmap_pos_fts,
                                     gmap_masks, gmap_pair_dists, gmap_visited_masks, gmap_vpids,
                                     vp_img_embeds, vp_pos_fts, vp_masks, vp_nav_masks, vp_obj_masks, vp_cand_vpids,
-                                    imagine_embeds=None, imagine_masks=None):
-        """'navigation'.  :1133-1235."""
+                                    imagine_embeds=None, imagine_masks=None, ctx_kv=None):
+        """'navigation'.  :1133-1235.  ``ctx_kv`` (internal): context projections already looked up by the caller
+        (VLNBert's graph path); txt_embeds / imagine_embeds are then not read."""
         if vp_obj_masks is not None:
             raise NotImplementedError('object grounding head is outside the R2R hot path')
-        self._guard(txt_embeds)
+        self._guard(gmap_img_embeds)
         cfg, lowp, pk = self.config, self.lowp, self._pk()
-        dev = txt_embeds.device
-        B, L, _ = txt_embeds.shape
+        dev = gmap_img_embeds.device
+        B, L = txt_masks.shape
         G, P = gmap_img_embeds.shape[1], vp_img_embeds.shape[1]
         ge, le = self.global_encoder, self.local_encoder
 
-        if self._recording(txt_embeds, gmap_img_embeds, vp_img_embeds, imagine_embeds):
+        if ctx_kv is None and self._recording(txt_embeds, gmap_img_embeds, vp_img_embeds, imagine_embeds):
             with blocks.grad_mode(True):
                 return self._navigation_train(txt_embeds, txt_masks, gmap_img_embeds, gmap_step_ids, gmap_pos_fts, gmap_masks,
                                               gmap_pair_dists, gmap_visited_masks, gmap_vpids, vp_img_embeds, vp_pos_fts,
@@ -340,23 +363,10 @@ class GlocalTextPathNavCMT(nn.Module):
                           y32=x32[r_l:r_l + B * P], y16=x16[r_l:r_l + B * P] if lowp else None)
         x = Act(x32, x16)
 
-        # ---- context = [txt ; imagine] (:1157-1158)
-        txt = _f32c(txt_embeds)
-        if cfg.imagine_enc_pano and cfg.concat_imagine_with == 'language':
-            if imagine_embeds is None or imagine_masks is None:
-                raise ValueError('navigation needs imagine_embeds and imagine_masks when imagine_enc_pano is set')
-            I = imagine_embeds.shape[1]
-            C = L + I
-            ctx = torch.empty((B * C, HIDDEN), dtype=BF16 if lowp else F32, device=dev)
-            c32, c16 = (None, ctx) if lowp else (ctx, None)
-            ops.copy_rows(txt, L * HIDDEN, HIDDEN, B, L, c32, c16, C * HIDDEN, HIDDEN)
-            ops.copy_rows(_f32c(imagine_embeds), I * HIDDEN, HIDDEN, B, I, c32[L:] if c32 is not None else None,
-                          c16[L:] if c16 is not None else None, C * HIDDEN, HIDDEN)
-            ctx_mask = blocks.mask_u8(torch.cat([txt_masks.bool(), imagine_masks.bool()], 1))
-        else:
-            C = L
-            ctx = ops.cast_bf16(txt.view(B * L, HIDDEN)) if lowp else txt.view(B * L, HIDDEN)
-            ctx_mask = blocks.mask_u8(txt_masks)
+        # ---- context = [txt ; imagine] (:1157-1158) and its K / V projections for the 4 layers: the context never
+        # changes inside an episode (use_lang2visn_attn is off), so the projections are kept per episode
+        kvs = ctx_kv if ctx_kv is not None else self.context_kv(txt_embeds, imagine_embeds)
+        ctx_mask, C = self.context_mask(txt_masks, imagine_masks)
 
         affine = None
         dist = None
@@ -367,9 +377,7 @@ class GlocalTextPathNavCMT(nn.Module):
                    Stream(r_l, B, P, blocks.mask_u8(vp_masks), 1)]
 
         # ---- 4 graph-aware cross-modal layers, both branches per launch (:384-399, :444-453)
-        for cp, sp in zip(pk['x_cross'], pk['x_self']):
-            w, b = cp.kv.get(lowp)
-            kv = ops.gemm(ctx, w, b)                          # [B*C, 4*768] = K_g | V_g | K_l | V_l
+        for cp, sp, kv in zip(pk['x_cross'], pk['x_self'], kvs):
             x = blocks.cross_attn(x, kv, [0, 2 * HIDDEN], C, ctx_mask, cp, streams, ends, lowp)
             x = blocks.self_attn_ffn(x, sp, streams, ends, lowp)
 
@@ -392,6 +400,77 @@ class GlocalTextPathNavCMT(nn.Module):
                                           gmap_ids, cand_ids, B, G, P)
         return {'gmap_embeds': gmap_out, 'vp_embeds': vp_out, 'global_logits': gl, 'local_logits': ll,
                 'fused_logits': fl, 'obj_logits': None}
+
+    # -- per-episode context cache ----------------------------------------------------------------------------
+    def _with_imagine(self):
+        cfg = self.config
+        return bool(cfg.imagine_enc_pano and cfg.concat_imagine_with == 'language')
+
+    def context_mask(self, txt_masks, imagine_masks):
+        """key-padding mask and length of the [txt ; imagine] context (:1157-1158)"""
+        if self._with_imagine():
+            if imagine_masks is None:
+                raise ValueError('navigation needs imagine_embeds and imagine_masks when imagine_enc_pano is set')
+            return (blocks.mask_u8(torch.cat([txt_masks.bool(), imagine_masks.bool()], 1)),
+                    txt_masks.shape[1] + imagine_masks.shape[1])
+        return blocks.mask_u8(txt_masks), txt_masks.shape[1]
+
+    def context_kv(self, txt_embeds, imagine_embeds):
+        """[txt ; imagine] context (:1157-1158) projected to K | V for every cross-modal layer of both branches:
+        one [B*C, 4*768] tensor (K_g | V_g | K_l | V_l) per layer.
+
+        The reference recomputes these 8 projections per layer identically at every navigation step
+        (use_lang2visn_attn=False, vlnbert_init.py:57: the context is never updated).  Here they are computed when
+        the context changes and reused while the caller keeps passing the SAME txt_embeds / imagine_embeds tensor
+        objects at the same version (what the agents do for the length of an episode, r2r/agent.py:409,449 -> :485-500).
+        The projections live in buffers owned by the cache (one set per shape / precision), so CUDA graphs that
+        captured their addresses stay valid across episodes.  ``context_cache = False`` restores per-step
+        recomputation."""
+        lowp, pk = self.lowp, self._pk()
+        with_img = self._with_imagine()
+        if with_img and imagine_embeds is None:
+            raise ValueError('navigation needs imagine_embeds and imagine_masks when imagine_enc_pano is set')
+        B, L, _ = txt_embeds.shape
+        I = imagine_embeds.shape[1] if with_img else 0
+        C = L + I
+        dev = self.embeddings.LayerNorm.weight.device
+        slot_key = (B, L, I, lowp)
+        slot = self._ctx_slots.get(slot_key)
+        wtok = tuple(cp.kv.get_token() for cp in pk['x_cross'])
+        ident = (id(txt_embeds), txt_embeds._version, txt_embeds.data_ptr(),
+                 id(imagine_embeds) if with_img else 0, imagine_embeds._version if with_img else 0,
+                 imagine_embeds.data_ptr() if with_img else 0, wtok)
+        if slot is not None and self.context_cache and slot['ident'] == ident:
+            self.context_hits += 1
+            return slot['kv']
+        if slot is None:
+            slot = {'ctx': torch.empty((B * C, HIDDEN), dtype=BF16 if lowp else F32, device=dev),
+                    'kv': [torch.empty((B * C, 4 * HIDDEN), dtype=BF16 if lowp else F32, device=dev) for _ in pk['x_cross']]}
+            self._ctx_slots[slot_key] = slot
+        ctx = slot['ctx']
+        c32, c16 = (None, ctx) if lowp else (ctx, None)
+        txt = _f32c(txt_embeds.to(dev, non_blocking=True))
+        if with_img:
+            img = _f32c(imagine_embeds.to(dev, non_blocking=True))
+            ops.copy_rows(txt, L * HIDDEN, HIDDEN, B, L, c32, c16, C * HIDDEN, HIDDEN)
+            ops.copy_rows(img, I * HIDDEN, HIDDEN, B, I, c32[L:] if c32 is not None else None,
+                          c16[L:] if c16 is not None else None, C * HIDDEN, HIDDEN)
+        elif lowp:
+            ops.cast_bf16(txt.view(B * L, HIDDEN), ctx)
+        else:
+            ctx.copy_(txt.view(B * L, HIDDEN))
+        for cp, kv in zip(pk['x_cross'], slot['kv']):
+            w, b = cp.kv.get(lowp)
+            ops.gemm(ctx, w, b, out=kv)                      # [B*C, 4*768] = K_g | V_g | K_l | V_l
+        # the cache keeps the source tensors alive, so their ids / addresses cannot be recycled while it is valid
+        slot['ident'], slot['refs'] = ident, (txt_embeds, imagine_embeds)
+        self.context_misses += 1
+        return slot['kv']
+
+    def drop_context(self):
+        """forget the cached context projections (new episode with recycled tensors, or to bound memory)"""
+        for slot in self._ctx_slots.values():
+            slot['ident'], slot['refs'] = None, None
 
     def _navigation_train(self, txt_embeds, txt_masks, gmap_img_embeds, gmap_step_ids, gmap_pos_fts, gmap_masks,
                           gmap_pair_dists, gmap_visited_masks, gmap_vpids, vp_img_embeds, vp_pos_fts, vp_masks,
@@ -509,9 +588,9 @@ class VLNBert(nn.Module):
     (graphs.GraphedCall); set ``use_cuda_graphs = False`` for plain eager launches.  Inputs may live on the host
     (pinned) or on the device."""
 
-    NAV_TENSORS = ('txt_embeds', 'txt_masks', 'gmap_img_embeds', 'gmap_step_ids', 'gmap_pos_fts', 'gmap_masks',
+    NAV_TENSORS = ('txt_masks', 'gmap_img_embeds', 'gmap_step_ids', 'gmap_pos_fts', 'gmap_masks',
                    'gmap_pair_dists', 'gmap_visited_masks', 'vp_img_embeds', 'vp_pos_fts', 'vp_masks', 'vp_nav_masks',
-                   'imagine_embeds', 'imagine_masks')
+                   'imagine_masks')
 
     def __init__(self, args):
         super().__init__()
@@ -542,10 +621,11 @@ class VLNBert(nn.Module):
         return {'pano_embeds': e, 'pano_masks': m}
 
     def _nav_fn(self, t):
+        kv = [t['ctx_kv%d' % i] for i in range(len(self.vln_bert.global_encoder.encoder.x_layers))]
         return self.vln_bert.forward_navigation_per_step(
-            t['txt_embeds'], t['txt_masks'], t['gmap_img_embeds'], t['gmap_step_ids'], t['gmap_pos_fts'], t['gmap_masks'],
+            None, t['txt_masks'], t['gmap_img_embeds'], t['gmap_step_ids'], t['gmap_pos_fts'], t['gmap_masks'],
             t['gmap_pair_dists'], t['gmap_visited_masks'], t['gmap_ids'], t['vp_img_embeds'], t['vp_pos_fts'], t['vp_masks'],
-            t['vp_nav_masks'], None, t['cand_ids'], imagine_embeds=t.get('imagine_embeds'), imagine_masks=t.get('imagine_masks'))
+            t['vp_nav_masks'], None, t['cand_ids'], imagine_embeds=None, imagine_masks=t.get('imagine_masks'), ctx_kv=kv)
 
     def _graphable(self):
         return self.use_cuda_graphs and not self.training and not torch.is_grad_enabled()
@@ -571,8 +651,11 @@ class VLNBert(nn.Module):
                 G, P = batch['gmap_img_embeds'].shape[1], batch['vp_img_embeds'].shape[1]
                 t['gmap_ids'], t['cand_ids'] = m.intern_vpids(batch['gmap_vpids'], batch['vp_cand_vpids'], G, P, None)
                 cfg = m.config
+                # context projections: looked up (or recomputed, eagerly) outside the graph, which only reads them
+                kv = m.context_kv(batch['txt_embeds'], batch['imagine_embeds'])
                 return self._g_nav(t, dev, extra_key=(m.precision, cfg.imagine_enc_pano, cfg.concat_imagine_with if
-                                                      cfg.imagine_enc_pano else None), weights_token=tok)
+                                                      cfg.imagine_enc_pano else None), weights_token=tok,
+                                   borrowed={'ctx_kv%d' % i: x for i, x in enumerate(kv)})
             return m(mode, batch)
         if mode in ('language', 'imagine', 'align_with_contrastive_loss'):
             return m(mode, batch)

@@ -33,11 +33,17 @@ class GraphedCall:
     def clear(self):
         self.entries.clear()
 
-    def __call__(self, inputs: Dict[str, torch.Tensor], device: torch.device, extra_key=(), weights_token=None):
+    def __call__(self, inputs: Dict[str, torch.Tensor], device: torch.device, extra_key=(), weights_token=None,
+                 borrowed: Dict[str, torch.Tensor] = None):
+        """``borrowed``: device tensors the graph reads IN PLACE (no copy into static buffers): persistent buffers
+        owned by the caller, e.g. the per-episode context projections.  Their addresses are part of the signature
+        and the entry keeps them alive."""
         if weights_token != self.token:
             self.clear()
             self.token = weights_token
-        key = (extra_key, tuple((k, tuple(v.shape), v.dtype) for k, v in inputs.items()))
+        borrowed = borrowed or {}
+        key = (extra_key, tuple((k, tuple(v.shape), v.dtype) for k, v in inputs.items()),
+               tuple((k, v.data_ptr(), tuple(v.shape), v.dtype) for k, v in borrowed.items()))
         ent = self.entries.get(key)
         if ent is None:
             ent = {'seen': 0, 'graph': None}
@@ -50,8 +56,10 @@ class GraphedCall:
             dev_in = {k: (v if v.device == device else v.to(device, non_blocking=True)) for k, v in inputs.items()}
             if ent['seen'] < self.capture_after:
                 ent['seen'] += 1
-                return self.fn(dev_in)                       # eager: also warms autotuning and weight packs
+                return self.fn({**dev_in, **borrowed})       # eager: also warms autotuning and weight packs
             static_in = {k: v.clone() for k, v in dev_in.items()}
+            static_in.update(borrowed)
+            ent['borrowed'] = dict(borrowed)
             torch.cuda.synchronize(device)
             side = torch.cuda.Stream(device)
             side.wait_stream(torch.cuda.current_stream(device))

@@ -108,3 +108,51 @@ def duet_finetune_iteration(model, ep: dict, n_steps: int = 1, cosine_weight: fl
     if backward:
         loss.backward()
     return loss, ce / B, aux, nav
+
+
+class GraphedIteration:
+    """A whole fine-tuning iteration (forward, backward, gradient all-reduce, clipping, optimiser step) captured into ONE
+    CUDA graph over static inputs and replayed: an iteration is ~4000 kernel launches whose host cost (ctypes, autograd
+    bookkeeping) exceeds their device time at batch 64.
+
+        it = GraphedIteration(model, step_fn, static_inputs)       # step_fn(static_inputs) -> loss (0-d tensor)
+        it.load(host_or_device_batch); loss = it.replay()
+
+    Requirements: fixed shapes; viewpoint ids passed as interned tensors (duet.GlocalTextPathNavCMT.intern_vpids);
+    gradients living in a FlatGradients buffer (static .grad storage); the optimiser created with ``capturable=True``.
+    The derived weight copies (bf16 shadows, transposes) are rebuilt INSIDE the graph at the start of every iteration; call
+    ``finish()`` before using the model outside the graph again."""
+
+    def __init__(self, model, step_fn, static_inputs: dict, warmup: int = 3):
+        self.model, self.static = model, static_inputs
+        dev = next(model.parameters()).device
+        for _ in range(warmup):                               # autotuning, allocator and lazy-initialisation warm-up
+            step_fn(static_inputs)
+        torch.cuda.synchronize(dev)
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            step_fn(static_inputs)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self._invalidate_packs()                              # the capture must contain the weight re-cast
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = step_fn(static_inputs)
+
+    def _invalidate_packs(self):
+        for m in self.model.modules():
+            if hasattr(m, '_packs'):
+                m._packs = None
+
+    def load(self, batch: dict):
+        for k, v in self.static.items():
+            if torch.is_tensor(v) and k in batch and batch[k] is not v:
+                v.copy_(batch[k], non_blocking=True)
+
+    def replay(self):
+        self.graph.replay()
+        return self.loss
+
+    def finish(self):
+        self._invalidate_packs()
