@@ -178,3 +178,29 @@ def test_imagination_feature_loader_semantics(tmp_path):
         assert np.array_equal(feats[1, 3], store['11_2'][2, :768].astype(np.float32)) and not feats[2].any()
     with pytest.raises(AssertionError):
         db_mod.collate_imaginations(db_mod.ImaginationImageFeaturesDB(store, 768), ['10_0'], {'10_0': ['True']}, 768)
+
+
+def test_derived_weights_follow_fused_optimizers():
+    """torch.optim.AdamW(fused=True) updates parameters in place WITHOUT bumping their version counters; the derived
+    weight copies (blocks.Pack) must still be rebuilt after such a step (global optimizer-step hook)."""
+    import importlib
+    blocks = importlib.import_module('vln_imagine_b200.blocks')
+    p = torch.nn.Parameter(torch.randn(8))
+    p.grad = torch.randn(8)
+    builds = {'n': 0}
+
+    def build():
+        builds['n'] += 1
+        return p.detach().clone()
+    pk = blocks.Pack([p], build)
+    pk.get(); pk.get()
+    assert builds['n'] == 1
+    try:
+        opt = torch.optim.AdamW([p], lr=1e-2, fused=True)
+    except (RuntimeError, TypeError):                    # no fused CPU implementation in this torch build
+        opt = torch.optim.AdamW([p], lr=1e-2)
+    opt.step()
+    assert torch.equal(pk.get(), p.detach())
+    assert builds['n'] == 2
+    pk.get()
+    assert builds['n'] == 2

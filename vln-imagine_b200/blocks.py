@@ -46,18 +46,50 @@ def training() -> bool:
 # ----------------------------------------------------------------------------------------------
 # derived weights (bf16 shadow copies, stacked groups), refreshed when a source parameter changes
 # ----------------------------------------------------------------------------------------------
+class _WeightsEpoch:
+    """Counts optimiser steps process-wide.  Fused optimisers (torch.optim.AdamW(fused=True), apex) update parameters
+    in place WITHOUT bumping their autograd version counters, so the version alone cannot tell that a derived copy is
+    stale; a global optimizer-step hook can."""
+    value = 0
+    hooked = False
+
+    @classmethod
+    def install(cls):
+        if cls.hooked:
+            return
+        cls.hooked = True
+        try:
+            from torch.optim.optimizer import register_optimizer_step_post_hook
+
+            def _bump(optimizer, args, kwargs):
+                cls.value += 1
+            register_optimizer_step_post_hook(_bump)
+        except ImportError:                                    # very old torch: version counters only
+            pass
+
+
+def weights_epoch() -> int:
+    return _WeightsEpoch.value
+
+
+def touch_weights():
+    """call after updating parameters by any means that neither bumps tensor versions nor runs an optimizer step"""
+    _WeightsEpoch.value += 1
+
+
 class Pack:
-    """Device tensors derived from parameters; rebuilt when any source's version / storage changes
-    (optimizer step, load_state_dict, .cuda()).  fp32 masters stay the nn.Parameters themselves."""
+    """Device tensors derived from parameters; rebuilt when any source's version / storage changes or an optimiser
+    has stepped (in-place update, load_state_dict, .cuda()).  fp32 masters stay the nn.Parameters themselves."""
 
     def __init__(self, sources: Sequence[torch.Tensor], build):
+        _WeightsEpoch.install()
         self.sources = list(sources)
         self._build = build
         self._key = None
         self._val = None
 
     def get(self):
-        key = tuple((p._version, p.data_ptr()) for p in self.sources)
+        key = (_WeightsEpoch.value,) + tuple((p._version, p.data_ptr()) for p in self.sources)
         if key != self._key:
             with torch.no_grad():
                 self._val = self._build()

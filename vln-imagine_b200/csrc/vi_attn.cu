@@ -172,8 +172,8 @@ __global__ void __launch_bounds__(128, 5) attn_fwd_bf16_kernel(const AttnParams 
         const float2 ma = *reinterpret_cast<const float2*>(madd + key);
         float b00 = 0.f, b01 = 0.f, b10 = 0.f, b11 = 0.f;
         if (pd0) {
-          if (key < pr.Lk) { b00 = fmaf(bw, __ldg(pd0 + key), bb); b10 = fmaf(bw, __ldg(pd1 + key), bb); }
-          if (key + 1 < pr.Lk) { b01 = fmaf(bw, __ldg(pd0 + key + 1), bb); b11 = fmaf(bw, __ldg(pd1 + key + 1), bb); }
+          if (key < pr.Lk) { b00 = fmaf(bw, (*(pd0 + key)), bb); b10 = fmaf(bw, (*(pd1 + key)), bb); }
+          if (key + 1 < pr.Lk) { b01 = fmaf(bw, (*(pd0 + key + 1)), bb); b11 = fmaf(bw, (*(pd1 + key + 1)), bb); }
         }
         s[nt][0] = s[nt][0] * 0.125f + ma.x + b00;
         s[nt][1] = s[nt][1] * 0.125f + ma.y + b01;

@@ -153,8 +153,8 @@ __global__ void __launch_bounds__(128) attn_bwd_bf16_kernel(const AttnBwdTcParam
         const float2 ma = *reinterpret_cast<const float2*>(madd + key);
         float b00 = 0.f, b01 = 0.f, b10 = 0.f, b11 = 0.f;
         if (pd0) {
-          if (key < p.Lk) { b00 = fmaf(bw, __ldg(pd0 + key), bb); b10 = fmaf(bw, __ldg(pd1 + key), bb); }
-          if (key + 1 < p.Lk) { b01 = fmaf(bw, __ldg(pd0 + key + 1), bb); b11 = fmaf(bw, __ldg(pd1 + key + 1), bb); }
+          if (key < p.Lk) { b00 = fmaf(bw, (*(pd0 + key)), bb); b10 = fmaf(bw, (*(pd1 + key)), bb); }
+          if (key + 1 < p.Lk) { b01 = fmaf(bw, (*(pd0 + key + 1)), bb); b11 = fmaf(bw, (*(pd1 + key + 1)), bb); }
         }
         s[nt][0] = s[nt][0] * 0.125f + ma.x + b00;
         s[nt][1] = s[nt][1] * 0.125f + ma.y + b01;
@@ -208,12 +208,12 @@ __global__ void __launch_bounds__(128) attn_bwd_bf16_kernel(const AttnBwdTcParam
         dp[nt][3] = s[nt][3] * (dp[nt][3] - d1);
         if (pd0) {
           if (r0 < p.Lq) {
-            if (key < p.Lk) { aw = fmaf(dp[nt][0], __ldg(pd0 + key), aw); ab += dp[nt][0]; }
-            if (key + 1 < p.Lk) { aw = fmaf(dp[nt][1], __ldg(pd0 + key + 1), aw); ab += dp[nt][1]; }
+            if (key < p.Lk) { aw = fmaf(dp[nt][0], (*(pd0 + key)), aw); ab += dp[nt][0]; }
+            if (key + 1 < p.Lk) { aw = fmaf(dp[nt][1], (*(pd0 + key + 1)), aw); ab += dp[nt][1]; }
           }
           if (r1 < p.Lq) {
-            if (key < p.Lk) { aw = fmaf(dp[nt][2], __ldg(pd1 + key), aw); ab += dp[nt][2]; }
-            if (key + 1 < p.Lk) { aw = fmaf(dp[nt][3], __ldg(pd1 + key + 1), aw); ab += dp[nt][3]; }
+            if (key < p.Lk) { aw = fmaf(dp[nt][2], (*(pd1 + key)), aw); ab += dp[nt][2]; }
+            if (key + 1 < p.Lk) { aw = fmaf(dp[nt][3], (*(pd1 + key + 1)), aw); ab += dp[nt][3]; }
           }
         }
         *reinterpret_cast<uint32_t*>(Ps + (size_t)r0 * PP + key) = pack_bf16x2(s[nt][0], s[nt][1]);

@@ -28,7 +28,7 @@ __device__ __forceinline__ int group_of_row(const RowGroups& g, long long row) {
 // dst[c, r] = src[r, c]  (rows x cols -> cols x ldd, columns r >= rows of dst are zero up to pad_rows)
 // ---------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(256) transpose_kernel(const T* __restrict__ src, long long ld, T* __restrict__ dst,
+__global__ void __launch_bounds__(256) transpose_kernel(const T* src, long long ld, T* __restrict__ dst,
                                                         long long ldd, int rows, int cols, int pad_rows) {
   pdl_enter();
   __shared__ T tile[32][33];
@@ -62,7 +62,7 @@ __device__ __forceinline__ float2 ld2f(const bf16* p) {
 
 // out[c] = sum_r x[r, c]; grid (cols / 64, n_chunks), 256 threads: warp w takes rows w, w+8, ... of the chunk, a lane 2 columns
 template <typename T>
-__global__ void __launch_bounds__(256) colsum_partial_kernel(const T* __restrict__ x, long long ld, float* __restrict__ part,
+__global__ void __launch_bounds__(256) colsum_partial_kernel(const T* x, long long ld, float* __restrict__ part,
                                                              long long rows, int cols) {
   pdl_enter();
   __shared__ float2 red[8][32];
@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const T* __restrict
 }
 
 // out[o][g][c] = sum over the chunks of group g of part[o][chunk][c]; grid (ceil(cols / 256), n_groups, n_out)
-__global__ void __launch_bounds__(256) chunk_sum_kernel(const float* __restrict__ part, float* __restrict__ out, int n_chunks,
+__global__ void __launch_bounds__(256) chunk_sum_kernel(const float* part, float* __restrict__ out, int n_chunks,
                                                         int cols, long long rows, const RowGroups grp, long long out_stride) {
   pdl_enter();
   const int c = blockIdx.x * 256 + threadIdx.x;
@@ -144,7 +144,7 @@ template <> struct Vec8<float> {
 };
 
 template <typename T>
-__global__ void __launch_bounds__(256) act_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, long long n, int act) {
+__global__ void __launch_bounds__(256) act_fwd_kernel(const T* x, T* __restrict__ y, long long n, int act) {
   pdl_enter();
   const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
   if (i >= n) return;
@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(256) act_fwd_kernel(const T* __restrict__ x, T
 }
 // dx = dy * act'(x)
 template <typename T>
-__global__ void __launch_bounds__(256) act_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dx,
+__global__ void __launch_bounds__(256) act_bwd_kernel(const T* x, const T* dy, T* __restrict__ dx,
                                                       long long n, int act) {
   pdl_enter();
   const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
@@ -196,9 +196,9 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const T* __restrict__ x, c
 //   stats[r] = {mean, rstd} for the parameter-gradient pass
 // ---------------------------------------------------------------------------------------------
 
-__global__ void __launch_bounds__(128) ln_bwd_dx_kernel(const float* __restrict__ a, const float* __restrict__ b,
-                                                        const float* __restrict__ gamma, float eps,
-                                                        const float* __restrict__ dy32, const bf16* __restrict__ dy16,
+__global__ void __launch_bounds__(128) ln_bwd_dx_kernel(const float* a, const float* b,
+                                                        const float* gamma, float eps,
+                                                        const float* dy32, const bf16* dy16,
                                                         float* __restrict__ dx32, bf16* __restrict__ dx16,
                                                         float* __restrict__ stats, long long rows, const RowGroups grp) {
   pdl_enter();
@@ -264,9 +264,9 @@ __global__ void __launch_bounds__(128) ln_bwd_dx_kernel(const float* __restrict_
 
 // stage 1 of dgamma[c] = sum_r dy * xhat, dbeta[c] = sum_r dy: partials per 128-row chunk into part[2][n_chunks][768];
 // grid (768 / 64, n_chunks), 256 threads (stage 2: chunk_sum_kernel per row group)
-__global__ void __launch_bounds__(256) ln_bwd_param_partial_kernel(const float* __restrict__ a, const float* __restrict__ b,
-                                                                   const float* __restrict__ dy32, const bf16* __restrict__ dy16,
-                                                                   const float* __restrict__ stats, float* __restrict__ part,
+__global__ void __launch_bounds__(256) ln_bwd_param_partial_kernel(const float* a, const float* b,
+                                                                   const float* dy32, const bf16* dy16,
+                                                                   const float* stats, float* __restrict__ part,
                                                                    long long rows, int n_chunks) {
   pdl_enter();
   __shared__ float2 rg[8][32], rb[8][32];
@@ -303,7 +303,7 @@ __global__ void __launch_bounds__(256) ln_bwd_param_partial_kernel(const float* 
 // stage 1: part[17][n_chunks][768] (k = 16 is the bias), grid (768 / 32, n_chunks), 256 threads; stage 2 sums the chunks
 // and writes dW (transposed to [768, fd]) / db
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) feat_wgrad_partial_kernel(const float* __restrict__ dt, const float* __restrict__ feat, int fd,
+__global__ void __launch_bounds__(256) feat_wgrad_partial_kernel(const float* dt, const float* feat, int fd,
                                                                  float* __restrict__ part, long long rows, int n_chunks) {
   pdl_enter();
   __shared__ float red[8][17][33];
@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(256) feat_wgrad_partial_kernel(const float* __
     const float d = dt[r * D + c];
 #pragma unroll
     for (int k = 0; k < 16; ++k)
-      if (k < fd) acc[k] = fmaf(d, __ldg(feat + r * fd + k), acc[k]);
+      if (k < fd) acc[k] = fmaf(d, (*(feat + r * fd + k)), acc[k]);
     acc[16] += d;
   }
 #pragma unroll
@@ -333,7 +333,7 @@ __global__ void __launch_bounds__(256) feat_wgrad_partial_kernel(const float* __
     }
   }
 }
-__global__ void __launch_bounds__(256) feat_wgrad_final_kernel(const float* __restrict__ part, int fd, float* __restrict__ dW,
+__global__ void __launch_bounds__(256) feat_wgrad_final_kernel(const float* part, int fd, float* __restrict__ dW,
                                                                float* __restrict__ db, int n_chunks) {
   pdl_enter();
   const int c = blockIdx.x * 256 + threadIdx.x;
@@ -347,7 +347,7 @@ __global__ void __launch_bounds__(256) feat_wgrad_final_kernel(const float* __re
 // ---------------------------------------------------------------------------------------------
 // dst[idx[r]] += src[r]   (embedding-table adjoint; fp32 atomics: rows may repeat)
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) scatter_add_rows_kernel(const float* __restrict__ src, const int64_t* __restrict__ idx,
+__global__ void __launch_bounds__(128) scatter_add_rows_kernel(const float* src, const int64_t* idx,
                                                                float* __restrict__ dst, long long rows, int period) {
   pdl_enter();
   const int lane = threadIdx.x & 31;
@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(128) scatter_add_rows_kernel(const float* __re
 // ---------------------------------------------------------------------------------------------
 // out[r] = x[r] . w + b  adjoint:  dx[r, :] = dout[r] * w[g],  dw[g, c] = sum_r dout[r] x[r, c],  db[g] = sum_r dout[r]
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) rowdot_bwd_dx_kernel(const float* __restrict__ dout, const float* __restrict__ w,
+__global__ void __launch_bounds__(128) rowdot_bwd_dx_kernel(const float* dout, const float* w,
                                                             float* __restrict__ dx, long long rows, const RowGroups grp) {
   pdl_enter();
   const int lane = threadIdx.x & 31;
@@ -372,7 +372,7 @@ __global__ void __launch_bounds__(128) rowdot_bwd_dx_kernel(const float* __restr
 }
 // stage 1 of dw[g, c] = sum_r dout[r] x[r, c], db[g] = sum_r dout[r]: part[2][n_chunks][768] (the bias partial is replicated
 // over the columns so that stage 2 is the shared chunk_sum_kernel); grid (768 / 64, n_chunks)
-__global__ void __launch_bounds__(256) rowdot_bwd_w_partial_kernel(const float* __restrict__ dout, const float* __restrict__ x,
+__global__ void __launch_bounds__(256) rowdot_bwd_w_partial_kernel(const float* dout, const float* x,
                                                                    float* __restrict__ part, long long rows, int n_chunks) {
   pdl_enter();
   __shared__ float2 rw[8][32];
@@ -546,10 +546,10 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const AttnBwdParams p) {
 // ---------------------------------------------------------------------------------------------
 constexpr int FUSE_MAX = 512;
 __global__ void __launch_bounds__(32) duet_fuse_logits_bwd_kernel(
-    const float* __restrict__ g_raw, const float* __restrict__ l_raw, const float* __restrict__ fuse_raw,
-    const uint8_t* __restrict__ gmap_masks, const uint8_t* __restrict__ gmap_visited, const uint8_t* __restrict__ vp_nav,
-    const int32_t* __restrict__ gmap_ids, const int32_t* __restrict__ cand_ids, const float* __restrict__ d_global,
-    const float* __restrict__ d_local, const float* __restrict__ d_fused, float* __restrict__ dg_raw,
+    const float* g_raw, const float* l_raw, const float* fuse_raw,
+    const uint8_t* gmap_masks, const uint8_t* gmap_visited, const uint8_t* vp_nav,
+    const int32_t* gmap_ids, const int32_t* cand_ids, const float* d_global,
+    const float* d_local, const float* d_fused, float* __restrict__ dg_raw,
     float* __restrict__ dl_raw, float* __restrict__ dfuse_raw, int G, int P) {
   pdl_enter();
   __shared__ float dll[FUSE_MAX];          // gradient w.r.t. the masked local logits
@@ -622,8 +622,8 @@ __global__ void __launch_bounds__(32) duet_fuse_logits_bwd_kernel(
 // cosine alignment loss adjoint:  loss = mean_r (1 - cos(p_r, t_r));  dp_r = -(dloss / R) d cos / d p_r
 // (torch clamps each norm at eps = 1e-8; the clamp is inactive for non-degenerate rows and is treated as such)
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) cosine_loss_bwd_kernel(const float* __restrict__ proj, const float* __restrict__ tgt,
-                                                              const float* __restrict__ dloss, float* __restrict__ dproj,
+__global__ void __launch_bounds__(128) cosine_loss_bwd_kernel(const float* proj, const float* tgt,
+                                                              const float* dloss, float* __restrict__ dproj,
                                                               float* __restrict__ dtgt, long long rows) {
   pdl_enter();
   const int lane = threadIdx.x & 31;

@@ -76,6 +76,10 @@ typedef __nv_bfloat16 bf16;
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_enter() { pdl_launch_dependents(); pdl_wait(); }
+// NOTE on loads: a kernel launched this way is RESIDENT before its predecessor has finished writing, so data produced by
+// earlier kernels must never be read through the non-coherent path (ld.global.nc: __ldg, or loads the compiler proves
+// read-only from `const T* __restrict__`): such a load may hit a stale L1 line of the SM.  The kernels of this library
+// therefore take plain `const T*` inputs (coherent ld.global), cp.async.cg or TMA.
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -317,7 +317,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (worker < total_tiles) {
       const int mt = worker / p.num_n_tiles, nt = worker - mt * p.num_n_tiles;
       if (res && lane == 0) issue_residual(0, mt * TILES_PER_M * BM + row_in_tile, nt * BN + half * 32);
-      if (p.bias) my_bias[lane] = __ldg(p.bias + (long long)group_of(mt * TILES_PER_M) * p.N + nt * BN + half * 32 + lane);
+      if (p.bias) my_bias[lane] = (*(p.bias + (long long)group_of(mt * TILES_PER_M) * p.N + nt * BN + half * 32 + lane));
       __syncwarp();
     }
     for (int t = worker; t < total_tiles; t += n_workers, ++it) {
@@ -356,8 +356,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
           // bias slice of the NEXT chunk (possibly the first one of the next tile): loaded now, parked at the end
           float bias_next = 0.f;
-          if (k + 1 < cpw) { if (bias_g) bias_next = __ldg(bias_g + col0 + 64 + lane); }
-          else if (bias_gn) bias_next = __ldg(bias_gn + tcol0n + lane);
+          if (k + 1 < cpw) { if (bias_g) bias_next = (*(bias_g + col0 + 64 + lane)); }
+          else if (bias_gn) bias_next = (*(bias_gn + tcol0n + lane));
           tmem_ld_wait();
           if (k + 1 < cpw) {
             tmem_ld_32x32(tbase + (uint32_t)((k + 1) * 64), r[(k + 1) & 1]);   // next chunk in flight during the math

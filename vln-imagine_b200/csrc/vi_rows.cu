@@ -20,19 +20,19 @@ __device__ __forceinline__ void row_zero(Row& r) {
 #pragma unroll
   for (int i = 0; i < V4 * 4; ++i) r.v[i] = 0.f;
 }
-__device__ __forceinline__ void row_load(Row& r, const float* __restrict__ src, int lane) {
+__device__ __forceinline__ void row_load(Row& r, const float* src, int lane) {
   const float4* s4 = reinterpret_cast<const float4*>(src);
 #pragma unroll
   for (int j = 0; j < V4; ++j) {
-    const float4 t = __ldg(s4 + lane + 32 * j);
+    const float4 t = (*(s4 + lane + 32 * j));
     r.v[4 * j] = t.x; r.v[4 * j + 1] = t.y; r.v[4 * j + 2] = t.z; r.v[4 * j + 3] = t.w;
   }
 }
-__device__ __forceinline__ void row_add(Row& r, const float* __restrict__ src, int lane) {
+__device__ __forceinline__ void row_add(Row& r, const float* src, int lane) {
   const float4* s4 = reinterpret_cast<const float4*>(src);
 #pragma unroll
   for (int j = 0; j < V4; ++j) {
-    const float4 t = __ldg(s4 + lane + 32 * j);
+    const float4 t = (*(s4 + lane + 32 * j));
     r.v[4 * j] += t.x; r.v[4 * j + 1] += t.y; r.v[4 * j + 2] += t.z; r.v[4 * j + 3] += t.w;
   }
 }
@@ -41,7 +41,7 @@ __device__ __forceinline__ void row_acc(Row& r, const Row& o) {
   for (int i = 0; i < V4 * 4; ++i) r.v[i] += o.v[i];
 }
 // in-place LayerNorm over the 768 values held by the warp (biased variance, like torch)
-__device__ __forceinline__ void row_layernorm(Row& r, const float* __restrict__ gamma, const float* __restrict__ beta,
+__device__ __forceinline__ void row_layernorm(Row& r, const float* gamma, const float* beta,
                                               float eps, int lane) {
   float s = 0.f;
 #pragma unroll
@@ -55,7 +55,7 @@ __device__ __forceinline__ void row_layernorm(Row& r, const float* __restrict__ 
   const float4* b4 = reinterpret_cast<const float4*>(beta);
 #pragma unroll
   for (int j = 0; j < V4; ++j) {
-    const float4 g = __ldg(g4 + lane + 32 * j), b = __ldg(b4 + lane + 32 * j);
+    const float4 g = (*(g4 + lane + 32 * j)), b = (*(b4 + lane + 32 * j));
     r.v[4 * j] = (r.v[4 * j] - mean) * rstd * g.x + b.x;
     r.v[4 * j + 1] = (r.v[4 * j + 1] - mean) * rstd * g.y + b.y;
     r.v[4 * j + 2] = (r.v[4 * j + 2] - mean) * rstd * g.z + b.z;
@@ -97,8 +97,8 @@ __device__ __forceinline__ int group_of_row(const RowGroups& g, long long row) {
   return i;
 }
 
-__global__ void __launch_bounds__(128) add_ln_kernel(const float* __restrict__ a, const float* __restrict__ b,
-                                                     const float* __restrict__ gamma, const float* __restrict__ beta,
+__global__ void __launch_bounds__(128) add_ln_kernel(const float* a, const float* b,
+                                                     const float* gamma, const float* beta,
                                                      float eps, float* y32, bf16* y16, long long rows, const RowGroups grp) {
   pdl_enter();
   ROW_INDEX();
@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(EMBED_WARPS * 32) embed_compose_kernel(const v
     const int n = D * p.feat_dim;
     for (int i = threadIdx.x; i < n; i += EMBED_WARPS * 32) {
       const int c = i / p.feat_dim, k = i - c * p.feat_dim;
-      wT[k * D + c] = __ldg(p.feat_w + i);
+      wT[k * D + c] = (*(p.feat_w + i));
     }
     __syncthreads();
   }
@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(EMBED_WARPS * 32) embed_compose_kernel(const v
       else row_zero(t);
       const float* fr = p.feat + row * p.feat_dim;
       for (int k = 0; k < p.feat_dim; ++k) {
-        const float f = __ldg(fr + k);
+        const float f = (*(fr + k));
         const float4* w4 = reinterpret_cast<const float4*>(wT + k * D);
 #pragma unroll
         for (int j = 0; j < V4; ++j) {
@@ -169,9 +169,9 @@ __global__ void __launch_bounds__(EMBED_WARPS * 32) embed_compose_kernel(const v
   }
 }
 
-__global__ void __launch_bounds__(128) ln_dot_kernel(const float* __restrict__ h, const float* __restrict__ gamma,
-                                                     const float* __restrict__ beta, float eps,
-                                                     const float* __restrict__ w, const float* __restrict__ bias,
+__global__ void __launch_bounds__(128) ln_dot_kernel(const float* h, const float* gamma,
+                                                     const float* beta, float eps,
+                                                     const float* w, const float* bias,
                                                      float* out, long long rows, const RowGroups grp) {
   pdl_enter();
   ROW_INDEX();
@@ -186,11 +186,11 @@ __global__ void __launch_bounds__(128) ln_dot_kernel(const float* __restrict__ h
   row_layernorm(r, gamma, beta, eps, lane);
   row_load(wv, w, lane);
   const float d = row_dot(r, wv);
-  if (lane == 0) out[row] = d + (bias ? __ldg(bias) : 0.f);
+  if (lane == 0) out[row] = d + (bias ? (*(bias)) : 0.f);
 }
 
-__global__ void __launch_bounds__(128) mul_bcast_kernel(const float* __restrict__ x, long long x_bs,
-                                                        const float* __restrict__ s, long long lds, float* y32,
+__global__ void __launch_bounds__(128) mul_bcast_kernel(const float* x, long long x_bs,
+                                                        const float* s, long long lds, float* y32,
                                                         bf16* y16, long long rows, int rows_per_batch) {
   pdl_enter();
   ROW_INDEX();
@@ -209,13 +209,13 @@ __global__ void __launch_bounds__(128) mul_bcast_kernel(const float* __restrict_
 // so no mask has to travel back to the host.  bw is accumulated sequentially in candidate order like the
 // reference's Python loop (same fp32 association).
 constexpr int FUSE_MAX = 512;
-__global__ void __launch_bounds__(32) duet_fuse_logits_kernel(const float* __restrict__ g_raw, const float* __restrict__ l_raw,
-                                                              const float* __restrict__ fuse_raw,
-                                                              const uint8_t* __restrict__ gmap_masks,
-                                                              const uint8_t* __restrict__ gmap_visited,
-                                                              const uint8_t* __restrict__ vp_nav,
-                                                              const int32_t* __restrict__ gmap_ids,
-                                                              const int32_t* __restrict__ cand_ids, float* global_logits,
+__global__ void __launch_bounds__(32) duet_fuse_logits_kernel(const float* g_raw, const float* l_raw,
+                                                              const float* fuse_raw,
+                                                              const uint8_t* gmap_masks,
+                                                              const uint8_t* gmap_visited,
+                                                              const uint8_t* vp_nav,
+                                                              const int32_t* gmap_ids,
+                                                              const int32_t* cand_ids, float* global_logits,
                                                               float* local_logits, float* fused_logits, int G, int P) {
   pdl_enter();
   __shared__ float ll[FUSE_MAX];
@@ -274,15 +274,15 @@ __global__ void __launch_bounds__(32) duet_fuse_logits_kernel(const float* __res
   }
 }
 
-__global__ void mask_logits_navtype_kernel(const float* __restrict__ raw, const int64_t* __restrict__ nav_types,
+__global__ void mask_logits_navtype_kernel(const float* raw, const int64_t* nav_types,
                                            float* out, long long n) {
   pdl_enter();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = nav_types[i] == 0 ? -INFINITY : raw[i];
 }
 
-__global__ void __launch_bounds__(128) gather_mean_kernel(const float* __restrict__ src, const int32_t* __restrict__ offsets,
-                                                          const int32_t* __restrict__ row_idx, float* out32, bf16* out16,
+__global__ void __launch_bounds__(128) gather_mean_kernel(const float* src, const int32_t* offsets,
+                                                          const int32_t* row_idx, float* out32, bf16* out16,
                                                           long long rows) {
   pdl_enter();
   ROW_INDEX();
@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(128) gather_mean_kernel(const float* __restric
   row_store(acc, out32, out16, row, lane);
 }
 
-__global__ void __launch_bounds__(128) scatter_rows_kernel(const float* __restrict__ src, const int32_t* __restrict__ dst_rows,
+__global__ void __launch_bounds__(128) scatter_rows_kernel(const float* src, const int32_t* dst_rows,
                                                            float* dst, long long rows) {
   pdl_enter();
   ROW_INDEX();
@@ -309,7 +309,7 @@ __global__ void __launch_bounds__(128) scatter_rows_kernel(const float* __restri
 }
 
 // 1 - cos(p, t) with torch's cosine_similarity clamping: x.y / (max(|x|,eps) * max(|y|,eps))
-__global__ void __launch_bounds__(128) cosine_loss_kernel(const float* __restrict__ proj, const float* __restrict__ tgt,
+__global__ void __launch_bounds__(128) cosine_loss_kernel(const float* proj, const float* tgt,
                                                           float* loss_rows, long long rows) {
   pdl_enter();
   ROW_INDEX();
@@ -322,7 +322,7 @@ __global__ void __launch_bounds__(128) cosine_loss_kernel(const float* __restric
 }
 
 // single-block deterministic mean of n floats (n <= a few thousand)
-__global__ void __launch_bounds__(256) mean_kernel(const float* __restrict__ x, float* out, int n) {
+__global__ void __launch_bounds__(256) mean_kernel(const float* x, float* out, int n) {
   pdl_enter();
   __shared__ float sh[8];
   float s = 0.f;
@@ -338,8 +338,8 @@ __global__ void __launch_bounds__(256) mean_kernel(const float* __restrict__ x, 
 }
 
 // sims[r, 0] = cos(proj r, tgt r)/T ; sims[r, 1+n] = cos(proj r, negs n)/T ; one warp per (r, column)
-__global__ void __launch_bounds__(128) infonce_sims_kernel(const float* __restrict__ proj, const float* __restrict__ tgt,
-                                                           const float* __restrict__ negs, float inv_t, float* sims,
+__global__ void __launch_bounds__(128) infonce_sims_kernel(const float* proj, const float* tgt,
+                                                           const float* negs, float inv_t, float* sims,
                                                            int R, int n_negs) {
   pdl_enter();
   const int lane = threadIdx.x & 31;
@@ -354,8 +354,8 @@ __global__ void __launch_bounds__(128) infonce_sims_kernel(const float* __restri
   if (lane == 0) sims[item] = ab / (fmaxf(sqrtf(aa), 1e-8f) * fmaxf(sqrtf(bb), 1e-8f)) * inv_t;
 }
 // loss_r = logsumexp over {col 0} U {negatives of other episodes} - sims[r,0]; one warp per row
-__global__ void __launch_bounds__(128) infonce_rows_kernel(const float* __restrict__ sims, const int32_t* __restrict__ row_ep,
-                                                           const int32_t* __restrict__ neg_ep, float* loss_rows, int R,
+__global__ void __launch_bounds__(128) infonce_rows_kernel(const float* sims, const int32_t* row_ep,
+                                                           const int32_t* neg_ep, float* loss_rows, int R,
                                                            int n_negs) {
   pdl_enter();
   ROW_INDEX();
@@ -374,11 +374,11 @@ __global__ void __launch_bounds__(128) infonce_rows_kernel(const float* __restri
   if (lane == 0) loss_rows[row] = mx + logf(sum) - s[0];
 }
 
-__global__ void cast_bf16_kernel(const float* __restrict__ src, bf16* dst, long long n4, long long n) {
+__global__ void cast_bf16_kernel(const float* src, bf16* dst, long long n4, long long n) {
   pdl_enter();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n4) {
-    const float4 t = __ldg(reinterpret_cast<const float4*>(src) + i);
+    const float4 t = (*(reinterpret_cast<const float4*>(src) + i));
     reinterpret_cast<uint2*>(dst)[i] = make_uint2(pack_bf16x2(t.x, t.y), pack_bf16x2(t.z, t.w));
   }
   if (i == 0) for (long long j = n4 * 4; j < n; ++j) dst[j] = __float2bfloat16_rn(src[j]);
@@ -387,7 +387,7 @@ __global__ void cast_bf16_kernel(const float* __restrict__ src, bf16* dst, long 
 
 // dst[b, r, :] = src[b, r, :] for nb batches of `rpb` 768-wide rows with independent batch / row strides
 // (token concatenation [txt; imagine], token-0 gathers, fp32 -> bf16 operand copies)
-__global__ void __launch_bounds__(128) copy_rows_kernel(const float* __restrict__ src, long long src_bs, long long src_rs,
+__global__ void __launch_bounds__(128) copy_rows_kernel(const float* src, long long src_bs, long long src_rs,
                                                         float* dst32, bf16* dst16, long long dst_bs, long long dst_rs,
                                                         long long rows, int rpb) {
   pdl_enter();

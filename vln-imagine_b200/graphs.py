@@ -82,7 +82,8 @@ def weights_token(module: torch.nn.Module, cache: dict):
     params = cache.get('params')
     if params is None:
         params = cache['params'] = list(module.parameters())
+    from .blocks import weights_epoch
     v = 0
     for p in params:
         v += p._version
-    return (v, params[0].data_ptr() if params else 0, len(params))
+    return (v, weights_epoch(), params[0].data_ptr() if params else 0, len(params))

@@ -111,34 +111,55 @@ def duet_finetune_iteration(model, ep: dict, n_steps: int = 1, cosine_weight: fl
 
 
 class GraphedIteration:
-    """A whole fine-tuning iteration (forward, backward, gradient all-reduce, clipping, optimiser step) captured into ONE
-    CUDA graph over static inputs and replayed: an iteration is ~4000 kernel launches whose host cost (ctypes, autograd
-    bookkeeping) exceeds their device time at batch 64.
+    """A whole fine-tuning iteration replayed from CUDA graphs over static inputs: an iteration is ~4000 kernel launches
+    whose host cost (ctypes, autograd bookkeeping) exceeds their device time at batch 64.  Two graphs bracket the one
+    collective, which stays an ordinary (eager) NCCL call between them:
 
-        it = GraphedIteration(model, step_fn, static_inputs)       # step_fn(static_inputs) -> loss (0-d tensor)
+        graph 1: zero the flat gradient buffer, forward, backward          (grad_fn(static_inputs) -> loss)
+        eager  : FlatGradients.all_reduce()                                 (between())
+        graph 2: gradient clipping + optimiser step                         (update_fn())
+
+        it = GraphedIteration(model, grad_fn, update_fn, static_inputs, between=flat.all_reduce)
         it.load(host_or_device_batch); loss = it.replay()
 
     Requirements: fixed shapes; viewpoint ids passed as interned tensors (duet.GlocalTextPathNavCMT.intern_vpids);
     gradients living in a FlatGradients buffer (static .grad storage); the optimiser created with ``capturable=True``.
-    The derived weight copies (bf16 shadows, transposes) are rebuilt INSIDE the graph at the start of every iteration; call
-    ``finish()`` before using the model outside the graph again."""
+    The derived weight copies (bf16 shadows, transposes) are rebuilt INSIDE graph 1 at the start of every iteration; call
+    ``finish()`` before using the model outside the graphs again."""
 
-    def __init__(self, model, step_fn, static_inputs: dict, warmup: int = 3):
-        self.model, self.static = model, static_inputs
+    def __init__(self, model, grad_fn, update_fn, static_inputs: dict, between=None, warmup: int = 3):
+        self.model, self.static, self.between = model, static_inputs, between
         dev = next(model.parameters()).device
+
+        def eager():
+            loss = grad_fn(static_inputs)
+            if between is not None:
+                between()
+            update_fn()
+            return loss
         for _ in range(warmup):                               # autotuning, allocator and lazy-initialisation warm-up
-            step_fn(static_inputs)
+            eager()
         torch.cuda.synchronize(dev)
         side = torch.cuda.Stream(dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
-            step_fn(static_inputs)
+            eager()
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
-        self._invalidate_packs()                              # the capture must contain the weight re-cast
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.loss = step_fn(static_inputs)
+        self._invalidate_packs()                              # graph 1 must contain the weight re-cast
+        self.g_grad = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g_grad):
+            self.loss = grad_fn(static_inputs)
+        if between is not None:
+            between()
+        self.g_update = torch.cuda.CUDAGraph()
+        import os
+        if os.environ.get('VI_TRAIN_SHARED_POOL', '0') == '1':
+            with torch.cuda.graph(self.g_update, pool=self.g_grad.pool()):
+                update_fn()
+        else:
+            with torch.cuda.graph(self.g_update):
+                update_fn()
 
     def _invalidate_packs(self):
         for m in self.model.modules():
@@ -151,7 +172,10 @@ class GraphedIteration:
                 v.copy_(batch[k], non_blocking=True)
 
     def replay(self):
-        self.graph.replay()
+        self.g_grad.replay()
+        if self.between is not None:
+            self.between()
+        self.g_update.replay()
         return self.loss
 
     def finish(self):
