@@ -120,6 +120,17 @@ int vi_add_ln(const float* a, const float* b, const float* gamma, const float* b
               float* y32, void* y16, int64_t rows,
               int n_groups, const int32_t* group_row_end, vi_stream_t stream);
 
+/* Row-block GEMM with the residual add and LayerNorm fused into the epilogue (N = 768 only; vi_gemm_rb.cu):
+ *   pre = x w^T + bias + residual        (optional fp32 output pre32 [M, 768]: pre-norm residual stream)
+ *   y   = LayerNorm(pre) * gamma + beta  (y32 fp32 and / or y16 bf16, [M, 768])
+ * A cluster of 4 CTAs owns 128 rows x 768 columns: the x tile is TMA-multicast to the four CTAs, row statistics are
+ * exchanged through distributed shared memory.  w is [n_groups * 768, K] bf16, gamma / beta / bias [n_groups * 768].
+ * Replaces dense -> + input -> LayerNorm of BertSelfOutput / BertOutput (D/models/vilmodel.py:147-155,183-194) and
+ * out_proj / linear2 followed by norm1 / norm2 of the pre-norm encoder layer (D/models/transformer.py:170-182). */
+int vi_gemm_ln_bf16(const void* x, int64_t ldx, const void* w, const float* bias, const float* residual, int64_t ldr,
+                    const float* gamma, const float* beta, float eps, float* pre32, float* y32, void* y16, int M, int K,
+                    int n_groups, const int32_t* group_row_end, vi_stream_t stream);
+
 /* Input-embedding composer:
  *   y = LN_out( [LN_a](a) + a2 + a3 + LN_f(feat @ feat_w^T + feat_b) + table[idx] + pos_table[row % pos_period]
  *               + const_row + const_row2 )

@@ -385,3 +385,44 @@ def test_argument_errors_are_reported_not_fatal(ops):
                  out_dtype=torch.bfloat16)
     with pytest.raises(_lib.VlnImagineError, match='CUDA tensor|no CPU path|must be'):
         ops.ensure_init(torch.zeros(1))
+
+
+@pytest.mark.parametrize('M,K,grouped', [(4416, 768, True), (4416, 3072, True), (2304, 768, False), (5120, 3072, False),
+                                          (300, 768, False), (1, 768, False), (9024, 768, False)])
+@pytest.mark.parametrize('mode', ['post_ln', 'pre_norm', 'no_residual'])
+def test_gemm_ln_rowblock(ops, M, K, grouped, mode):
+    """cluster GEMM with residual + LayerNorm in the epilogue (TMA multicast, DSMEM row statistics) against
+    F.linear -> + residual -> F.layer_norm on bf16-rounded operands"""
+    n_groups = 2 if grouped else 1
+    ends = [2048, M] if grouped else None
+    x16 = _rand(M, K, seed=41).bfloat16()
+    w16 = _rand(n_groups * 768, K, scale=0.05, seed=42).bfloat16()
+    b = _rand(n_groups * 768, scale=0.1, seed=43)
+    res = None if mode == 'no_residual' else _rand(M, 768, seed=44) * 3.0 + 0.5
+    g = 1 + _rand(n_groups * 768, scale=0.1, seed=45)
+    be = _rand(n_groups * 768, scale=0.1, seed=46)
+    eps = 1e-5 if mode == 'pre_norm' else 1e-12
+    pre, y32, y16 = ops.gemm_ln(x16, w16, b, res, g, be, eps, want32=mode != 'pre_norm', want16=True,
+                                want_pre=mode == 'pre_norm', group_row_end=ends)
+    bounds = [0] + (ends or [M])
+    ref_pre, ref = [], []
+    for i in range(n_groups):
+        r0, r1 = bounds[i], bounds[i + 1]
+        t = F.linear(x16[r0:r1].float(), w16[i * 768:(i + 1) * 768].float(), b[i * 768:(i + 1) * 768])
+        if res is not None:
+            t = t + res[r0:r1]
+        ref_pre.append(t)
+        ref.append(F.layer_norm(t, (768,), g[i * 768:(i + 1) * 768], be[i * 768:(i + 1) * 768], eps))
+    ref_pre, ref = torch.cat(ref_pre), torch.cat(ref)
+    if pre is not None:
+        assert relerr(pre, ref_pre) < 2e-3
+    if y32 is not None:
+        assert relerr(y32, ref) < 2e-3
+        assert relerr(y16, y32) < 5e-3
+    else:
+        assert relerr(y16, ref) < 1e-2
+    # the fused kernel against the two-kernel path it replaces (same operands): fp32 outputs agree closely
+    ao = ops.gemm(x16, w16, b, residual=res, out_dtype=torch.float32, group_row_end=ends)
+    z32, z16 = ops.add_ln(ao, None, g.view(n_groups, 768), be.view(n_groups, 768), eps, want16=True, group_row_end=ends)
+    if y32 is not None:
+        assert relerr(y32, z32) < 1e-4

@@ -222,6 +222,19 @@ def _ctx_buffer(rows: int, like: torch.Tensor, streams) -> torch.Tensor:
     return ctx
 
 
+def linear_residual_ln(x, lin: 'LinearPack', res32, ln: LNPack, eps, lowp, ends=None) -> Act:
+    """LN(x W^T + b + res) (inference): one cluster GEMM with the LayerNorm in its epilogue in bf16 mode, GEMM + row
+    kernel in the fp32 check mode (or with VLN_IMAGINE_FUSED_LN=0)."""
+    w, b = lin.get(lowp)
+    g, be = ln.get()
+    if lowp and ops.fused_ln_enabled() and w.shape[0] == (1 if ends is None else len(ends)) * HIDDEN:
+        _, y32, y16 = ops.gemm_ln(x, w, b, res32, g, be, eps, group_row_end=ends)
+        return Act(y32, y16)
+    ao = ops.gemm(x, w, b, residual=res32, out_dtype=F32, group_row_end=ends)
+    y32, y16 = ops.add_ln(ao, None, g, be, eps, want16=lowp, group_row_end=ends)
+    return Act(y32, y16)
+
+
 def layer_norm(x32, res32, ln: LNPack, eps, lowp, ends=None) -> Act:
     if _Mode.train:
         y32, y16 = ag.layer_norm(x32, res32, ln, eps, lowp, ends)
@@ -274,9 +287,7 @@ def self_attn_ffn(x: Act, pk: SelfFFNPack, streams: List[Stream], ends, lowp: bo
         probs.append(dict(q=q[:, 0:HIDDEN], k=q[:, HIDDEN:2 * HIDDEN], v=q[:, 2 * HIDDEN:3 * HIDDEN], out=s.view(ctx),
                           B=s.B, Lq=s.L, Lk=s.L, key_mask=s.mask, pair_dist=s.pair_dist, bias_affine=s.bias_affine))
     ops.attention_multi(probs)
-    w, b = pk.o.get(lowp)
-    ao = ops.gemm(ctx, w, b, residual=x.f32, out_dtype=F32, group_row_end=ends)
-    y = layer_norm(ao, None, pk.ln1, eps, lowp, ends)
+    y = linear_residual_ln(ctx, pk.o, x.f32, pk.ln1, eps, lowp, ends)
     return ffn(y, pk.w1, pk.w2, pk.ln2, ends, lowp, eps)
 
 
@@ -287,9 +298,7 @@ def ffn(y: Act, w1: LinearPack, w2: LinearPack, ln2: LNPack, ends, lowp: bool, e
         return layer_norm(fo, None, ln2, eps, lowp, ends)
     w, b = w1.get(lowp)
     h = ops.gemm(y.operand(lowp), w, b, epilogue=EPI_GELU, group_row_end=ends)   # [rows, 3072]
-    w, b = w2.get(lowp)
-    fo = ops.gemm(h, w, b, residual=y.f32, out_dtype=F32, group_row_end=ends)
-    return layer_norm(fo, None, ln2, eps, lowp, ends)
+    return linear_residual_ln(h, w2, y.f32, ln2, eps, lowp, ends)
 
 
 class CrossPack:
@@ -322,9 +331,7 @@ def cross_attn(x: Act, kv: torch.Tensor, kv_col0: Sequence[int], ctx_len: int, c
     ctx = _ctx_buffer(rows, xin, streams)
     ops.attention_multi([dict(q=s.view(q), k=kv[:, c0:c0 + HIDDEN], v=kv[:, c0 + HIDDEN:c0 + 2 * HIDDEN], out=s.view(ctx),
                               B=s.B, Lq=s.L, Lk=ctx_len, key_mask=ctx_mask) for s, c0 in zip(streams, kv_col0)])
-    w, b = pk.o.get(lowp)
-    ao = ops.gemm(ctx, w, b, residual=x.f32, out_dtype=F32, group_row_end=ends)
-    return layer_norm(ao, None, pk.ln, eps, lowp, ends)
+    return linear_residual_ln(ctx, pk.o, x.f32, pk.ln, eps, lowp, ends)
 
 
 def linear(x: torch.Tensor, pk: LinearPack, lowp: bool, out_dtype=None, ends=None, residual=None) -> torch.Tensor:
@@ -431,8 +438,13 @@ def pano_layer(x32: torch.Tensor, pk: PanoLayerPack, B: int, L: int, key_mask, l
     ctx = ops.attention(qkv[:, 0:HIDDEN], qkv[:, HIDDEN:2 * HIDDEN], qkv[:, 2 * HIDDEN:3 * HIDDEN], B, L, L,
                         key_mask=key_mask, mask_mode=MASK_NEG_INF)
     w, b = pk.o.get(lowp)
-    x32 = ops.gemm(ctx, w, b, residual=x32, out_dtype=F32)
-    h = layer_norm(x32, None, pk.norm2, eps, lowp)
+    if lowp and ops.fused_ln_enabled():
+        g2, b2 = pk.norm2.get()
+        x32, _, h16 = ops.gemm_ln(ctx, w, b, x32, g2, b2, eps, want32=False, want16=True, want_pre=True)
+        h = Act(None, h16)
+    else:
+        x32 = ops.gemm(ctx, w, b, residual=x32, out_dtype=F32)
+        h = layer_norm(x32, None, pk.norm2, eps, lowp)
     w, b = pk.w1.get(lowp)
     f = ops.gemm(h.operand(lowp), w, b, epilogue=EPI_GELU)
     w, b = pk.w2.get(lowp)

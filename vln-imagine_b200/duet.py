@@ -32,17 +32,24 @@ def _f32c(t: torch.Tensor) -> torch.Tensor:
 
 class _IdTable:
     """Viewpoint-id strings -> int32 ids.  Ids only need to agree between gmap_vpids and vp_cand_vpids of
-    the same call; one growing table per model is the simplest way to guarantee that."""
+    the same call; one growing table per model is the simplest way to guarantee that.  The hot loop is one
+    C-level ``map`` over the flattened keys (the agent hands ~1400 strings per step at batch 64)."""
 
     def __init__(self):
         self.ids = {}
 
     def encode(self, lists, width: int, pad: int) -> np.ndarray:
-        out = np.full((len(lists), width), pad, np.int32)
+        rows = [row[:width] if len(row) > width else row for row in lists]
+        lens = np.fromiter(map(len, rows), dtype=np.int64, count=len(rows))
+        flat = [k for row in rows for k in row]
         ids = self.ids
-        for i, row in enumerate(lists):
-            for j, key in enumerate(row[:width]):
-                out[i, j] = ids.setdefault(key, len(ids))
+        try:
+            vals = list(map(ids.__getitem__, flat))
+        except KeyError:
+            vals = [ids.setdefault(k, len(ids)) for k in flat]
+        out = np.full((len(rows), width), pad, np.int32)
+        if flat:
+            out[np.arange(width)[None, :] < lens[:, None]] = np.asarray(vals, np.int32)
         return out
 
 

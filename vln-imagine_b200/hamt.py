@@ -244,9 +244,7 @@ class NavCMT(nn.Module):
                      B=B, Lq=C, Lk=Nv, key_mask=visn_mask),
                 dict(q=qv[:, :HIDDEN], k=ql[:, HIDDEN:2 * HIDDEN], v=ql[:, 2 * HIDDEN:], out=ctx[r_v:r_v + B * Nv],
                      B=B, Lq=Nv, Lk=C, key_mask=lang_mask)])
-            w, b = cp['o'].get(lowp)
-            ao = ops.gemm(ctx, w, b, residual=x.f32, out_dtype=F32)
-            x = blocks.layer_norm(ao, None, cp['ln'], 1e-12, lowp)
+            x = blocks.linear_residual_ln(ctx, cp['o'], x.f32, cp['ln'], 1e-12, lowp)
             x = blocks.self_attn_ffn(x, sp, streams, ends, lowp)
 
         lang_out = x.f32[r_l:r_l + B * C].view(B, C, HIDDEN)

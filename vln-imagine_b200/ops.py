@@ -203,6 +203,42 @@ def gemm(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None,
     return out
 
 
+def fused_ln_enabled() -> bool:
+    """vi_gemm_ln_bf16 (cluster GEMM with residual + LayerNorm in the epilogue) is correct (tests/test_kernels_gpu.py::
+    test_gemm_ln_rowblock) but not yet faster than the tuned GEMM + row kernel it replaces (B200, M = 4416: 44.9 vs 17.1 us
+    at K = 768, 66.8 vs 29.2 us at K = 3072; 14.9 / 35.6 us with its epilogue I/O switched off - DESIGN.md section 5), so
+    it is opt-in: VLN_IMAGINE_FUSED_LN=1."""
+    return os.environ.get('VLN_IMAGINE_FUSED_LN', '0') == '1'
+
+
+def gemm_ln(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], residual: Optional[torch.Tensor],
+            gamma: torch.Tensor, beta: torch.Tensor, eps: float, want32: bool = True, want16: bool = True,
+            want_pre: bool = False, group_row_end: Optional[Sequence[int]] = None):
+    """(pre32 or None, y32 or None, y16 or None) with y = LayerNorm(x w^T + bias + residual) * gamma + beta over 768
+    columns (vi_gemm_ln_bf16: cluster GEMM with the LayerNorm in its epilogue).  x bf16 [M, K], w bf16 [n_groups*768, K]."""
+    M, K, ldx = _rows2d(x, 'x')
+    n_groups = 1 if group_row_end is None else len(group_row_end)
+    if x.dtype != BF16 or w.dtype != BF16 or not w.is_contiguous() or w.shape != (n_groups * HIDDEN, K):
+        raise _lib.VlnImagineError('gemm_ln: x / w must be bf16 with w of shape [%d, %d] (got %s)' % (n_groups * HIDDEN, K, tuple(w.shape)))
+    dev = x.device
+    pre = torch.empty((M, HIDDEN), dtype=F32, device=dev) if want_pre else None
+    y32 = torch.empty((M, HIDDEN), dtype=F32, device=dev) if want32 else None
+    y16 = torch.empty((M, HIDDEN), dtype=BF16, device=dev) if want16 else None
+    ends = _lib.int_array(list(group_row_end)) if group_row_end is not None else None
+    ldr = residual.stride(0) if residual is not None else 0
+    tr = _Counters.gemm_trace
+    if tr is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    check(lib.vi_gemm_ln_bf16(x.data_ptr(), ldx, w.data_ptr(), _ptr(bias), _ptr(residual), ldr, gamma.data_ptr(), beta.data_ptr(),
+                              eps, _ptr(pre), _ptr(y32), _ptr(y16), M, K, n_groups, ends, _stream()), 'vi_gemm_ln_bf16')
+    _launched(1)
+    if tr is not None:
+        e1.record()
+        tr.append((M, HIDDEN, K, e0, e1))
+    return pre, y32, y16
+
+
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, B: int, Lq: int, Lk: int,
               key_mask: Optional[torch.Tensor] = None, pair_dist: Optional[torch.Tensor] = None,
               bias_affine: Optional[torch.Tensor] = None, mask_mode: int = MASK_ADD_NEG10000,
