@@ -99,6 +99,9 @@ typedef struct {
   const float* bias_affine;    /* device {w, b} */
   float* lse;                  /* [B, H, Lq] or NULL */
   int32_t B, Lq, Lk;
+  float drop_p;                /* attention-probability dropout (training only); 0 = none */
+  uint32_t drop_site;          /* dropout site id (see vi_dropout) */
+  const uint32_t* drop_seed;   /* device pointer to the dropout seed, or NULL */
 } vi_attn_problem;
 /* Several independent attention problems (token streams of one row-stacked activation: DUET global | local,
  * HAMT language | vision) in ONE launch; same arithmetic as vi_attn_fwd per problem. */
@@ -260,7 +263,8 @@ int vi_rowdot_bwd(const float* dout, const float* x, const float* w, float* dx, 
 int vi_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                 const void* dout, int64_t ldo, void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv,
                 int dtype, const uint8_t* key_mask, const float* pair_dist, const float* bias_affine, float* d_affine,
-                int B, int H, int Lq, int Lk, int mask_mode, vi_stream_t stream);
+                int B, int H, int Lq, int Lk, int mask_mode, float drop_p, uint32_t drop_site, const uint32_t* drop_seed,
+                vi_stream_t stream);
 /* adjoint of vi_duet_fuse_logits; any of d_global / d_local / d_fused may be NULL (treated as zero) */
 int vi_duet_fuse_logits_bwd(const float* g_raw, const float* l_raw, const float* fuse_raw,
                             const uint8_t* gmap_masks, const uint8_t* gmap_visited, const uint8_t* vp_nav_masks,
@@ -270,6 +274,13 @@ int vi_duet_fuse_logits_bwd(const float* g_raw, const float* l_raw, const float*
 /* adjoint of vi_cosine_loss: dloss is the device scalar gradient of the mean; dproj / dtgt may be NULL */
 int vi_cosine_loss_bwd(const float* proj, const float* tgt, const float* dloss, float* dproj, float* dtgt, int R,
                        vi_stream_t stream);
+
+/* Dropout (training only): y = x * keep / (1 - p) with keep(i) = hash(i, *seed, site) >= p * 2^32; the backward pass is the
+ * same call on the gradient.  `seed` is a device pointer (the host module advances it once per optimiser step, also inside
+ * replayed CUDA graphs); `site` distinguishes the dropout layers of one iteration.  nn.Dropout of BertEmbeddings /
+ * BertSelfOutput / BertOutput (D/models/vilmodel.py:77,153,192), ImageEmbeddings (:1124), the panorama encoder layers
+ * (D/models/transformer.py:178-181), MLPProjectionHead (:585) and VLNBert.drop_env (D/models/model.py:27). */
+int vi_dropout(const void* x, void* y, int64_t n, float p, const uint32_t* seed, uint32_t site, int dtype, vi_stream_t stream);
 
 /* fp32 -> bf16 shadow copy of a weight or activation */
 int vi_cast_bf16(const float* src, void* dst, int64_t n, vi_stream_t stream);

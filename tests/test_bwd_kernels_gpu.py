@@ -351,3 +351,103 @@ def test_fuse_logits_bwd(ag):
     assert relerr(g_raw.grad, gr.grad) < 1e-4
     assert relerr(l_raw.grad, lr.grad) < 1e-4
     assert relerr(f_raw.grad, fr.grad) < 1e-4
+
+
+M32 = 0xFFFFFFFF
+
+
+def _hash32(idx, key):
+    """vi_hash32 of vi_common.cuh on int64 tensors"""
+    h = (idx * 0x9E3779B1 + key) & M32
+    h = h ^ (h >> 16)
+    h = (h * 0x7FEB352D) & M32
+    h = h ^ (h >> 15)
+    h = (h * 0x846CA68B) & M32
+    return h ^ (h >> 16)
+
+
+def _keep_mask(idx, seed, site, p):
+    key = _hash32(torch.tensor(site, dtype=torch.int64), (int(seed) ^ 0xA511E9B3) & M32)
+    return _hash32(idx, int(key)) >= int(p * 4294967296.0)
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_dropout_mask_and_backward(ag, dtype):
+    p = 0.3
+    x = (_rand(1000, 768, seed=50) + 3.0).to(dtype).requires_grad_()
+    ag._DropState.site = 100
+    y = ag.dropout(x, p)
+    site = ag._DropState.site
+    seed = int(ag.dropout_seed(x.device).item()) & M32
+    keep = _keep_mask(torch.arange(x.numel(), device='cuda', dtype=torch.int64), seed, site, p).view_as(x)
+    ref = torch.where(keep, x.detach().float() / (1 - p), torch.zeros_like(x, dtype=torch.float32))
+    assert relerr(y.detach(), ref) < (1e-6 if dtype == torch.float32 else 1e-2)
+    assert abs(float(keep.float().mean()) - (1 - p)) < 5e-3
+    dy = _rand(1000, 768, seed=51).to(dtype)
+    y.backward(dy)
+    assert relerr(x.grad, torch.where(keep, dy.float() / (1 - p), torch.zeros_like(ref))) < (1e-6 if dtype == torch.float32 else 1e-2)
+    y2 = ag.dropout(x.detach(), p)                      # next site: an independent mask
+    assert 0.3 < float(((y2 != 0) == (y.detach() != 0)).float().mean()) < 0.75
+    ag.advance_dropout_seeds()                          # what the optimizer-step hook does
+    y3 = ag.dropout_raw(x.detach(), p, site)
+    assert 0.3 < float(((y3 != 0) == (y.detach() != 0)).float().mean()) < 0.75
+
+
+@pytest.mark.parametrize('case', ['self_gasa', 'cross'])
+def test_attention_dropout_fwd_bwd(ag, case):
+    """attention-probability dropout inside the fused kernels against torch with the SAME mask (rebuilt from the hash)"""
+    from vln_imagine_b200.ops import MASK_ADD_NEG10000
+    B, p = 4, 0.25
+    Lq, Lk = (30, 30) if case == 'self_gasa' else (37, 85)
+    LkP = (Lk + 15) // 16 * 16
+    lens = torch.tensor([Lk, Lk // 2, 5, Lk - 1])
+    key_mask = (torch.arange(Lk)[None, :] < lens[:, None]).cuda()
+    km = key_mask.view(torch.uint8)
+    seed_t = ag.dropout_seed(torch.device('cuda', 0))
+    site = 777
+    dout = _rand(B * Lq, 768, seed=60).bfloat16()
+    if case == 'cross':
+        q = _rand(B * Lq, 768, seed=61).bfloat16().requires_grad_()
+        kv = _rand(B * Lk, 1536, seed=62).bfloat16().requires_grad_()
+        spec = [dict(q=(0, 0, 0), k=(1, 0, 0), v=(1, 0, 768), B=B, Lq=Lq, Lk=Lk, key_mask=km, out_row0=0, drop=(p, site, seed_t))]
+        out = ag.AttentionFn.apply(spec, B * Lq, MASK_ADD_NEG10000, 2, q, kv)
+        leaves = [q, kv]
+        qr, kvr = q.detach().float().requires_grad_(), kv.detach().float().requires_grad_()
+        Q, K, V = qr, kvr[:, :768], kvr[:, 768:]
+        refs, dist, aw, ab = [qr, kvr], None, None, None
+    else:
+        qkv = _rand(B * Lq, 2304, seed=63).bfloat16().requires_grad_()
+        dist = _rand(B, Lq, Lk, seed=64).abs() * 5
+        aw = torch.tensor([[-0.5]], device='cuda', requires_grad=True)
+        ab = torch.tensor([0.1], device='cuda', requires_grad=True)
+        affine = torch.stack([aw.detach().view(()), ab.detach().view(())]).contiguous()
+        spec = [dict(q=(0, 0, 0), k=(0, 0, 768), v=(0, 0, 1536), B=B, Lq=Lq, Lk=Lk, key_mask=km, pair_dist=dist, bias_affine=affine,
+                     out_row0=0, drop=(p, site, seed_t))]
+        out = ag.AttentionFn.apply(spec, B * Lq, MASK_ADD_NEG10000, 1, qkv, aw, ab)
+        leaves = [qkv]
+        r = qkv.detach().float().requires_grad_()
+        Q, K, V = r[:, :768], r[:, 768:1536], r[:, 1536:]
+        refs = [r]
+    out.backward(dout)
+    # torch reference with the identical mask
+    seed = int(seed_t.item()) & M32
+    b_i, h_i, q_i, k_i = torch.meshgrid(torch.arange(B), torch.arange(12), torch.arange(Lq), torch.arange(Lk), indexing='ij')
+    eid = ((((b_i * 12 + h_i) * Lq + q_i) * LkP + k_i) & M32).cuda()
+    keep = _keep_mask(eid, seed, site, p)
+    qh = Q.reshape(B, Lq, 12, 64).transpose(1, 2)
+    kh = K.reshape(B, Lk, 12, 64).transpose(1, 2)
+    vh = V.reshape(B, Lk, 12, 64).transpose(1, 2)
+    sc = qh @ kh.transpose(-1, -2) / 8.0 + (~key_mask)[:, None, None, :].float() * -10000.0
+    if dist is not None:
+        awr, abr = aw.detach().clone().requires_grad_(), ab.detach().clone().requires_grad_()
+        sc = sc + (dist * awr.view(()) + abr.view(()))[:, None]
+    pr = torch.softmax(sc, -1)
+    pr = torch.where(keep, pr / (1 - p), torch.zeros_like(pr))
+    ref = (pr @ vh).transpose(1, 2).reshape(B * Lq, 768)
+    ref.backward(dout.float())
+    assert abs(float(keep.float().mean()) - (1 - p)) < 1e-2
+    assert relerr(out, ref) < 1e-2
+    for got, want in zip(leaves, refs):
+        assert relerr(got.grad, want.grad) < 2e-2
+    if dist is not None:
+        assert relerr(aw.grad, awr.grad) < 2e-2

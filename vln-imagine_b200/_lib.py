@@ -40,7 +40,8 @@ class EmbedArgs(C.Structure):
 class AttnProblem(C.Structure):
     _fields_ = [('q', _p), ('ldq', _l), ('k', _p), ('ldk', _l), ('v', _p), ('ldv', _l), ('o', _p), ('ldo', _l),
                 ('key_mask', _p), ('pair_dist', _p), ('bias_affine', _p), ('lse', _p),
-                ('B', C.c_int32), ('Lq', C.c_int32), ('Lk', C.c_int32)]
+                ('B', C.c_int32), ('Lq', C.c_int32), ('Lk', C.c_int32),
+                ('drop_p', C.c_float), ('drop_site', C.c_uint32), ('drop_seed', _p)]
 
 
 # name -> argtypes; every entry of include/vlnimagine.h must appear here (tests check the header against it)
@@ -74,7 +75,8 @@ PROTOTYPES = {
     'vi_feat_wgrad': [_p, _p, _i, _p, _p, _l, _p, _l, _p],
     'vi_scatter_add_rows': [_p, _p, _i, _p, _l, _p],
     'vi_rowdot_bwd': [_p, _p, _p, _p, _p, _p, _l, _i, _ip, _p, _l, _p],
-    'vi_attn_bwd': [_p, _l, _p, _l, _p, _l, _p, _l, _p, _l, _p, _l, _p, _l, _i, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
+    'vi_attn_bwd': [_p, _l, _p, _l, _p, _l, _p, _l, _p, _l, _p, _l, _p, _l, _i, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, C.c_uint32, _p, _p],
+    'vi_dropout': [_p, _p, _l, _f, _p, C.c_uint32, _i, _p],
     'vi_duet_fuse_logits_bwd': [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
     'vi_cosine_loss_bwd': [_p, _p, _p, _p, _p, _i, _p],
 }

@@ -82,6 +82,61 @@ def to_operand(t: torch.Tensor, lowp: bool) -> torch.Tensor:
 
 
 # ----------------------------------------------------------------------------------------------
+# dropout: counter-based masks keyed by (device seed, site id, element index); nothing is stored for the backward pass
+class _DropState:
+    seeds = {}              # device -> int32 [1] tensor (read by the kernels as uint32)
+    site = 0                # python-side site counter: every dropout layer call of the process gets its own id
+
+
+def dropout_seed(device) -> torch.Tensor:
+    t = _DropState.seeds.get(device)
+    if t is None:
+        base = int(torch.randint(0, 2 ** 31 - 1, (1,)).item())          # CPU generator: follows torch.manual_seed
+        t = torch.full((1,), base, dtype=torch.int32, device=device)
+        _DropState.seeds[device] = t
+    return t
+
+
+def advance_dropout_seeds():
+    """called from the optimizer-step hook (blocks._WeightsEpoch): eager or captured into the update graph"""
+    for t in _DropState.seeds.values():
+        t.add_(1)
+
+
+def next_site() -> int:
+    _DropState.site = (_DropState.site + 1) & 0x7FFFFFFF
+    return _DropState.site
+
+
+def dropout_raw(x: torch.Tensor, p: float, site: int) -> torch.Tensor:
+    """y = x * keep / (1 - p) (no autograd); the same call on a gradient is the backward pass"""
+    x = x.contiguous()
+    y = torch.empty_like(x)
+    check(lib.vi_dropout(x.data_ptr(), y.data_ptr(), x.numel(), float(p), dropout_seed(x.device).data_ptr(), site, _dt(x), _stream()),
+          'vi_dropout')
+    _launched(1)
+    return y
+
+
+class DropoutFn(Function):
+    @staticmethod
+    def forward(ctx, x, p, site):
+        ctx.p, ctx.site = p, site
+        return dropout_raw(x, p, site)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return dropout_raw(dy, ctx.p, ctx.site), None, None
+
+
+def dropout(x: torch.Tensor, p: float) -> torch.Tensor:
+    if p <= 0:
+        return x
+    if x.dtype not in (BF16, F32):
+        raise _lib.VlnImagineError('dropout: bf16 / fp32 tensors only')
+    return DropoutFn.apply(x, p, next_site())
+
+
 class CastBf16Fn(Function):
     """fp32 -> bf16 operand copy; the gradient passes back in fp32."""
 
@@ -244,7 +299,8 @@ class AttentionFn(Function):
                 return bases[bi][r0:r0 + s['B'] * L, c0:c0 + HIDDEN]
             probs.append(dict(q=view('q', s['Lq']), k=view('k', s['Lk']), v=view('v', s['Lk']),
                               out=out[s['out_row0']:s['out_row0'] + s['B'] * s['Lq']], B=s['B'], Lq=s['Lq'], Lk=s['Lk'],
-                              key_mask=s.get('key_mask'), pair_dist=s.get('pair_dist'), bias_affine=s.get('bias_affine')))
+                              key_mask=s.get('key_mask'), pair_dist=s.get('pair_dist'), bias_affine=s.get('bias_affine'),
+                              drop=s.get('drop')))
             covered += s['B'] * s['Lq']
         if covered < rows_out:
             out.zero_()
@@ -276,11 +332,14 @@ class AttentionFn(Function):
                 do = do.to(q.dtype)
             if s.get('pair_dist') is not None and d_affine is None:
                 d_affine = torch.zeros((2,), dtype=F32, device=q.device)
+            drop = s.get('drop') if (s.get('drop') is not None and s['drop'][0] > 0) else None
             check(lib.vi_attn_bwd(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0), do.data_ptr(),
                                   do.stride(0), dq.data_ptr(), dq.stride(0), dk.data_ptr(), dk.stride(0), dv.data_ptr(),
                                   dv.stride(0), _dt(q), _ptr(s.get('key_mask')), _ptr(s.get('pair_dist')),
                                   _ptr(s.get('bias_affine')), _ptr(d_affine) if s.get('pair_dist') is not None else None,
-                                  s['B'], ops.HEADS, s['Lq'], s['Lk'], ctx.mask_mode, _stream()), 'vi_attn_bwd')
+                                  s['B'], ops.HEADS, s['Lq'], s['Lk'], ctx.mask_mode,
+                                  float(drop[0]) if drop else 0.0, (int(drop[1]) & 0xFFFFFFFF) if drop else 0,
+                                  drop[2].data_ptr() if drop else None, _stream()), 'vi_attn_bwd')
             _launched(1)
         extra = [None] * ctx.n_extra
         if ctx.n_extra == 2 and d_affine is not None:                   # sprel_linear.weight [1,1], .bias [1]

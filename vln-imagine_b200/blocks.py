@@ -24,19 +24,37 @@ from .ops import BF16, F32, HIDDEN, EPI_GELU, EPI_NONE, EPI_RELU, MASK_ADD_NEG10
 # ----------------------------------------------------------------------------------------------
 class _Mode:
     train = False
+    p_hidden = 0.0          # nn.Dropout(hidden_dropout_prob) sites (train() mode only)
+    p_attn = 0.0            # attention_probs_dropout_prob
 
 
 class grad_mode:
-    """with blocks.grad_mode(flag): ...  (set by the host modules once per mode call)"""
+    """with blocks.grad_mode(flag, drop=(p_hidden, p_attn)): ...  (set by the host modules once per mode call)"""
 
-    def __init__(self, flag: bool):
+    def __init__(self, flag: bool, drop=(0.0, 0.0)):
         self.flag = bool(flag)
+        self.drop = drop if self.flag else (0.0, 0.0)
 
     def __enter__(self):
-        self.prev, _Mode.train = _Mode.train, self.flag
+        self.prev = (_Mode.train, _Mode.p_hidden, _Mode.p_attn)
+        _Mode.train, _Mode.p_hidden, _Mode.p_attn = self.flag, float(self.drop[0]), float(self.drop[1])
 
     def __exit__(self, *a):
-        _Mode.train = self.prev
+        _Mode.train, _Mode.p_hidden, _Mode.p_attn = self.prev
+
+
+def _attn_drop(device, p=None):
+    """(p, site, seed tensor) for an attention problem, or None"""
+    p = _Mode.p_attn if p is None else p
+    return (p, ag.next_site(), ag.dropout_seed(device)) if p > 0 else None
+
+
+def _dense_res_ln(x, lin: 'LinearPack', res32, ln: 'LNPack', eps, lowp, ends):
+    """training: LN(dropout(x W^T + b) + res)  (BertSelfOutput / BertOutput, D/models/vilmodel.py:151-155,190-194)"""
+    if _Mode.p_hidden > 0:
+        d = ag.dropout(ag.linear(x, lin, lowp, out_dtype=F32, ends=ends), _Mode.p_hidden)
+        return layer_norm(d, res32, ln, eps, lowp, ends)
+    return layer_norm(ag.linear(x, lin, lowp, residual=res32, out_dtype=F32, ends=ends), None, ln, eps, lowp, ends)
 
 
 def training() -> bool:
@@ -63,6 +81,7 @@ class _WeightsEpoch:
 
             def _bump(optimizer, args, kwargs):
                 cls.value += 1
+                ag.advance_dropout_seeds()
             register_optimizer_step_post_hook(_bump)
         except ImportError:                                    # very old torch: version counters only
             pass
@@ -271,12 +290,12 @@ def self_attn_ffn(x: Act, pk: SelfFFNPack, streams: List[Stream], ends, lowp: bo
         spec, extras = [], ()
         for s in streams:
             spec.append(dict(q=(0, s.row0, 0), k=(0, s.row0, HIDDEN), v=(0, s.row0, 2 * HIDDEN), B=s.B, Lq=s.L, Lk=s.L,
-                             key_mask=s.mask, pair_dist=s.pair_dist, bias_affine=s.bias_affine, out_row0=s.row0))
+                             key_mask=s.mask, pair_dist=s.pair_dist, bias_affine=s.bias_affine, out_row0=s.row0,
+                             drop=_attn_drop(xin.device)))
             if s.pair_dist is not None and s.affine_params is not None:
                 extras = tuple(s.affine_params)
         ctx = ag.AttentionFn.apply(spec, rows, MASK_ADD_NEG10000, 1, qkv, *extras)
-        ao = ag.linear(ctx, pk.o, lowp, residual=x.f32, out_dtype=F32, ends=ends)
-        y = layer_norm(ao, None, pk.ln1, eps, lowp, ends)
+        y = _dense_res_ln(ctx, pk.o, x.f32, pk.ln1, eps, lowp, ends)
         return ffn(y, pk.w1, pk.w2, pk.ln2, ends, lowp, eps)
     w, b = pk.qkv.get(lowp)
     qkv = ops.gemm(xin, w, b, group_row_end=ends)                      # [rows, 2304]
@@ -294,8 +313,7 @@ def self_attn_ffn(x: Act, pk: SelfFFNPack, streams: List[Stream], ends, lowp: bo
 def ffn(y: Act, w1: LinearPack, w2: LinearPack, ln2: LNPack, ends, lowp: bool, eps=1e-12) -> Act:
     if _Mode.train:
         h = ag.ActFn.apply(ag.linear(y.operand(lowp), w1, lowp, ends=ends), EPI_GELU)
-        fo = ag.linear(h, w2, lowp, residual=y.f32, out_dtype=F32, ends=ends)
-        return layer_norm(fo, None, ln2, eps, lowp, ends)
+        return _dense_res_ln(h, w2, y.f32, ln2, eps, lowp, ends)
     w, b = w1.get(lowp)
     h = ops.gemm(y.operand(lowp), w, b, epilogue=EPI_GELU, group_row_end=ends)   # [rows, 3072]
     return linear_residual_ln(h, w2, y.f32, ln2, eps, lowp, ends)
@@ -322,10 +340,9 @@ def cross_attn(x: Act, kv: torch.Tensor, kv_col0: Sequence[int], ctx_len: int, c
     if _Mode.train:
         q = ag.linear(xin, pk.q, lowp, ends=ends)
         spec = [dict(q=(0, s.row0, 0), k=(1, 0, c0), v=(1, 0, c0 + HIDDEN), B=s.B, Lq=s.L, Lk=ctx_len, key_mask=ctx_mask,
-                     out_row0=s.row0) for s, c0 in zip(streams, kv_col0)]
+                     out_row0=s.row0, drop=_attn_drop(xin.device)) for s, c0 in zip(streams, kv_col0)]
         ctx = ag.AttentionFn.apply(spec, rows, MASK_ADD_NEG10000, 2, q, kv)
-        ao = ag.linear(ctx, pk.o, lowp, residual=x.f32, out_dtype=F32, ends=ends)
-        return layer_norm(ao, None, pk.ln, eps, lowp, ends)
+        return _dense_res_ln(ctx, pk.o, x.f32, pk.ln, eps, lowp, ends)
     w, b = pk.q.get(lowp)
     q = ops.gemm(xin, w, b, group_row_end=ends)
     ctx = _ctx_buffer(rows, xin, streams)
@@ -359,7 +376,8 @@ def operand(x32: torch.Tensor, lowp: bool) -> torch.Tensor:
 
 
 def embed(rows: int, device, *, a=None, a_ln=None, feat=None, feat_lin=None, feat_ln=None, idx=None, table=None,
-          pos_table=None, pos_period=0, const_rows=(), out_ln=None, eps=1e-12, lowp=False, y32=None, y16=None) -> Act:
+          pos_table=None, pos_period=0, const_rows=(), out_ln=None, eps=1e-12, lowp=False, y32=None, y16=None,
+          dropout=False) -> Act:
     """Input-embedding composer  LN_out([LN_a](a) + LN_f(W feat + b) + table[idx] + pos[row % period] + consts).
     *_ln are nn.LayerNorm-like parameter holders, feat_lin an nn.Linear-like holder.  Inference: ONE fused kernel
     (vi_embed_compose).  Training: the same sum built from differentiable primitives (autograd_ops)."""
@@ -393,9 +411,15 @@ def embed(rows: int, device, *, a=None, a_ln=None, feat=None, feat_lin=None, fea
     while len(terms) > 3:                                     # the fused sum kernel takes three row tensors
         terms = [ag.SumRowsFn.apply(3, *terms[:3])] + terms[3:]
     s = ag.SumRowsFn.apply(len(terms), *terms, *consts) if (len(terms) > 1 or consts) else terms[0]
+    drop = dropout and _Mode.p_hidden > 0                     # nn.Dropout after the embedding LayerNorm (vilmodel.py:77,1124)
     if out_ln is not None:
-        o32, o16 = ag.LayerNormFn.apply(s, None, out_ln.weight, out_ln.bias, eps, lowp, None, 2, out_ln.weight, out_ln.bias)
+        o32, o16 = ag.LayerNormFn.apply(s, None, out_ln.weight, out_ln.bias, eps, lowp and not drop, None, 2, out_ln.weight, out_ln.bias)
+        if drop:
+            o32 = ag.dropout(o32, _Mode.p_hidden)
+            return Act(o32, ag.CastBf16Fn.apply(o32) if lowp else None)
         return Act(o32, o16 if lowp else None)
+    if drop:
+        s = ag.dropout(s, _Mode.p_hidden)
     return Act(s, ag.CastBf16Fn.apply(s) if lowp else None)
 
 
@@ -427,8 +451,15 @@ def pano_layer(x32: torch.Tensor, pk: PanoLayerPack, B: int, L: int, key_mask, l
     h = layer_norm(x32, None, pk.norm1, eps, lowp)
     if _Mode.train:
         qkv = ag.linear(h.operand(lowp), pk.qkv, lowp)
-        spec = [dict(q=(0, 0, 0), k=(0, 0, HIDDEN), v=(0, 0, 2 * HIDDEN), B=B, Lq=L, Lk=L, key_mask=key_mask, out_row0=0)]
+        ph = _Mode.p_hidden
+        spec = [dict(q=(0, 0, 0), k=(0, 0, HIDDEN), v=(0, 0, 2 * HIDDEN), B=B, Lq=L, Lk=L, key_mask=key_mask, out_row0=0,
+                     drop=_attn_drop(x32.device, ph))]
         ctx = ag.AttentionFn.apply(spec, B * L, MASK_NEG_INF, 1, qkv)
+        if ph > 0:                                            # src + dropout1(src2); linear2(dropout(act)); src + dropout2
+            x32 = ag.SumRowsFn.apply(2, x32, ag.dropout(ag.linear(ctx, pk.o, lowp, out_dtype=F32), ph))
+            h = layer_norm(x32, None, pk.norm2, eps, lowp)
+            f = ag.dropout(ag.ActFn.apply(ag.linear(h.operand(lowp), pk.w1, lowp), EPI_GELU), ph)
+            return ag.SumRowsFn.apply(2, x32, ag.dropout(ag.linear(f, pk.w2, lowp, out_dtype=F32), ph))
         x32 = ag.linear(ctx, pk.o, lowp, residual=x32, out_dtype=F32)
         h = layer_norm(x32, None, pk.norm2, eps, lowp)
         f = ag.ActFn.apply(ag.linear(h.operand(lowp), pk.w1, lowp), EPI_GELU)

@@ -27,6 +27,10 @@ struct AttnProblem {
   const float* bias_affine;
   float* lse;
   int B, Lq, Lk, LkP;
+  uint32_t drop_thresh;      // attention-probability dropout (training): 0 = none
+  float drop_scale;
+  uint32_t drop_site;
+  const uint32_t* drop_seed;
 };
 struct AttnParams {
   AttnProblem pr[VI_ATTN_MAX_PROBLEMS];
@@ -139,6 +143,9 @@ __global__ void __launch_bounds__(128, 5) attn_fwd_bf16_kernel(const AttnParams 
 #pragma unroll
   for (int i = 0; i < 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+  const bool drop = pr.drop_thresh != 0;
+  const uint32_t dkey = drop ? vi_drop_key(pr.drop_seed, pr.drop_site) : 0u;
+  const uint32_t dbase = (uint32_t)((b * p.H + h) * pr.Lq) * (uint32_t)LkP;     // element id = dbase + q * LkP + key
 
   for (int kc = 0; kc < LkP; kc += 64) {
     if (kc == 64) {                                   // (block-uniform) the second cp.async group is needed from here
@@ -202,6 +209,14 @@ __global__ void __launch_bounds__(128, 5) attn_fwd_bf16_kernel(const AttnParams 
         s[nt][2] = __expf(s[nt][2] - mu1); s[nt][3] = __expf(s[nt][3] - mu1);
         l0 += s[nt][0] + s[nt][1];
         l1 += s[nt][2] + s[nt][3];
+        if (drop) {      // dropout on the probabilities (vilmodel.py:128,347): the denominator keeps the undropped sum
+          const uint32_t e0 = dbase + (uint32_t)r0 * (uint32_t)LkP + (uint32_t)(kc + nt * 8 + 2 * tg);
+          const uint32_t e1 = dbase + (uint32_t)r1 * (uint32_t)LkP + (uint32_t)(kc + nt * 8 + 2 * tg);
+          s[nt][0] *= vi_hash32(e0, dkey) >= pr.drop_thresh ? pr.drop_scale : 0.f;
+          s[nt][1] *= vi_hash32(e0 + 1, dkey) >= pr.drop_thresh ? pr.drop_scale : 0.f;
+          s[nt][2] *= vi_hash32(e1, dkey) >= pr.drop_thresh ? pr.drop_scale : 0.f;
+          s[nt][3] *= vi_hash32(e1 + 1, dkey) >= pr.drop_thresh ? pr.drop_scale : 0.f;
+        }
       }
     }
     // O += P V : P (accumulator layout) re-packed as the A operand; V fragments through ldmatrix.trans
@@ -332,6 +347,12 @@ static int check_problem(const vi_attn_problem& a, int H, int dtype, AttnProblem
   o.q = a.q; o.ldq = a.ldq; o.k = a.k; o.ldk = a.ldk; o.v = a.v; o.ldv = a.ldv; o.o = a.o; o.ldo = a.ldo;
   o.key_mask = a.key_mask; o.pair_dist = a.pair_dist; o.bias_affine = a.bias_affine; o.lse = a.lse;
   o.B = a.B; o.Lq = a.Lq; o.Lk = a.Lk; o.LkP = (a.Lk + 15) & ~15;
+  VI_CHECK_ARG(a.drop_p >= 0.f && a.drop_p < 1.f && (a.drop_p == 0.f || (a.drop_seed && dtype == VI_DT_BF16)),
+               "vi_attn_fwd: attention dropout needs 0 <= p < 1, a device seed pointer and the bf16 kernel");
+  o.drop_thresh = a.drop_p > 0.f ? vi_drop_threshold(a.drop_p) : 0u;
+  if (a.drop_p > 0.f && o.drop_thresh == 0u) o.drop_thresh = 1u;
+  o.drop_scale = a.drop_p > 0.f ? 1.0f / (1.0f - a.drop_p) : 1.0f;
+  o.drop_site = a.drop_site; o.drop_seed = a.drop_seed;
   return VI_OK;
 }
 
@@ -378,6 +399,7 @@ extern "C" int vi_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ld
   a.q = q; a.ldq = ldq; a.k = k; a.ldk = ldk; a.v = v; a.ldv = ldv; a.o = o; a.ldo = ldo;
   a.key_mask = key_mask; a.pair_dist = pair_dist; a.bias_affine = bias_affine; a.lse = lse;
   a.B = B; a.Lq = Lq; a.Lk = Lk;
+  a.drop_p = 0.f; a.drop_site = 0; a.drop_seed = nullptr;
   return vi_attn_fwd_multi(&a, 1, H, dtype, mask_mode, stream);
 }
 

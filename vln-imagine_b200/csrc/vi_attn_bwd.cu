@@ -31,6 +31,10 @@ struct AttnBwdTcParams {
   const float* bias_affine;
   float* d_affine;
   int B, H, Lq, Lk, LqP, LkP, mask_mode;
+  uint32_t drop_thresh;        // 0 = no attention dropout
+  float drop_scale;
+  uint32_t drop_site;
+  const uint32_t* drop_seed;
 };
 
 __device__ __forceinline__ void mma_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
@@ -105,6 +109,10 @@ __global__ void __launch_bounds__(128) attn_bwd_bf16_kernel(const AttnBwdTcParam
   float bw = 0.f, bb = 0.f;
   if (p.pair_dist) { bw = p.bias_affine[0]; bb = p.bias_affine[1]; }
   float aw = 0.f, ab = 0.f;                                  // GASA affine gradients of this thread
+  const bool drop = p.drop_thresh != 0;
+  const uint32_t dkey = drop ? vi_drop_key(p.drop_seed, p.drop_site) : 0u;
+  // dropout element id = ((b * H + h) * Lq + q) * LkP + key, the same as in the forward kernel
+  const uint32_t dbase = (uint32_t)((b * p.H + h) * p.Lq) * (uint32_t)LkP;
 
   // ------------------------------------------------ phase 1: a warp per 16-query tile
   for (int qt = warp; qt < (LqP >> 4); qt += 4) {
@@ -189,6 +197,14 @@ __global__ void __launch_bounds__(128) attn_bwd_bf16_kernel(const AttnBwdTcParam
     for (int nt = 0; nt < NT; ++nt) {
       if (nt < nt_run) {
         s[nt][0] *= i0; s[nt][1] *= i0; s[nt][2] *= i1; s[nt][3] *= i1;
+        if (drop) {      // O = (P o mask / (1 - p)) V: the mask scales dP here and P where it feeds dV below
+          const uint32_t e0 = dbase + (uint32_t)r0 * (uint32_t)LkP + (uint32_t)(nt * 8 + 2 * tg);
+          const uint32_t e1 = dbase + (uint32_t)r1 * (uint32_t)LkP + (uint32_t)(nt * 8 + 2 * tg);
+          dp[nt][0] *= vi_hash32(e0, dkey) >= p.drop_thresh ? p.drop_scale : 0.f;
+          dp[nt][1] *= vi_hash32(e0 + 1, dkey) >= p.drop_thresh ? p.drop_scale : 0.f;
+          dp[nt][2] *= vi_hash32(e1, dkey) >= p.drop_thresh ? p.drop_scale : 0.f;
+          dp[nt][3] *= vi_hash32(e1 + 1, dkey) >= p.drop_thresh ? p.drop_scale : 0.f;
+        }
         d0 = fmaf(s[nt][0], dp[nt][0], fmaf(s[nt][1], dp[nt][1], d0));
         d1 = fmaf(s[nt][2], dp[nt][2], fmaf(s[nt][3], dp[nt][3], d1));
       }
@@ -215,6 +231,14 @@ __global__ void __launch_bounds__(128) attn_bwd_bf16_kernel(const AttnBwdTcParam
             if (key < p.Lk) { aw = fmaf(dp[nt][2], (*(pd1 + key)), aw); ab += dp[nt][2]; }
             if (key + 1 < p.Lk) { aw = fmaf(dp[nt][3], (*(pd1 + key + 1)), aw); ab += dp[nt][3]; }
           }
+        }
+        if (drop) {      // dV = (P o mask / (1 - p))^T dO
+          const uint32_t e0 = dbase + (uint32_t)r0 * (uint32_t)LkP + (uint32_t)key;
+          const uint32_t e1 = dbase + (uint32_t)r1 * (uint32_t)LkP + (uint32_t)key;
+          s[nt][0] *= vi_hash32(e0, dkey) >= p.drop_thresh ? p.drop_scale : 0.f;
+          s[nt][1] *= vi_hash32(e0 + 1, dkey) >= p.drop_thresh ? p.drop_scale : 0.f;
+          s[nt][2] *= vi_hash32(e1, dkey) >= p.drop_thresh ? p.drop_scale : 0.f;
+          s[nt][3] *= vi_hash32(e1 + 1, dkey) >= p.drop_thresh ? p.drop_scale : 0.f;
         }
         *reinterpret_cast<uint32_t*>(Ps + (size_t)r0 * PP + key) = pack_bf16x2(s[nt][0], s[nt][1]);
         *reinterpret_cast<uint32_t*>(Ps + (size_t)r1 * PP + key) = pack_bf16x2(s[nt][2], s[nt][3]);
@@ -321,7 +345,7 @@ int launch_tc(const AttnBwdTcParams& p, size_t smem, cudaStream_t st) {
 int vi_attn_bwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* dout,
                    int64_t ldo, void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv,
                    const uint8_t* key_mask, const float* pair_dist, const float* bias_affine, float* d_affine, int B, int H,
-                   int Lq, int Lk, int mask_mode, cudaStream_t st) {
+                   int Lq, int Lk, int mask_mode, float drop_p, uint32_t drop_site, const uint32_t* drop_seed, cudaStream_t st) {
   const int LqP = (Lq + 15) & ~15, LkP = (Lk + 15) & ~15;
   if (LkP > 128 || LqP > 256) return 1;
   const uintptr_t al = (uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)dout;
@@ -336,6 +360,10 @@ int vi_attn_bwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const
   p.dv = reinterpret_cast<bf16*>(dv); p.lddv = lddv;
   p.key_mask = key_mask; p.pair_dist = pair_dist; p.bias_affine = bias_affine; p.d_affine = d_affine;
   p.B = B; p.H = H; p.Lq = Lq; p.Lk = Lk; p.LqP = LqP; p.LkP = LkP; p.mask_mode = mask_mode;
+  p.drop_thresh = drop_p > 0.f ? vi_drop_threshold(drop_p) : 0u;
+  if (drop_p > 0.f && p.drop_thresh == 0u) p.drop_thresh = 1u;
+  p.drop_scale = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
+  p.drop_site = drop_site; p.drop_seed = drop_seed;
   if (LkP <= 48) return launch_tc<6>(p, smem, st);
   if (LkP <= 96) return launch_tc<12>(p, smem, st);
   return launch_tc<16>(p, smem, st);

@@ -190,6 +190,28 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const T* x, const T* dy, T
   }
 }
 
+// y = x * keep / (1 - p); 8 elements per thread, the mask is a pure function of (element index, seed, site)
+template <typename T>
+__global__ void __launch_bounds__(256) dropout_kernel(const T* x, T* __restrict__ y, long long n, uint32_t thresh, float scale,
+                                                      const uint32_t* seed, uint32_t site) {
+  pdl_enter();
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (i >= n) return;
+  const uint32_t key = vi_drop_key(seed, site);
+  if (i + 8 <= n) {
+    Vec8<T> v;
+    v.load(x + i);
+    float f[8];
+    v.get(f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = vi_hash32((uint32_t)(i + j), key) >= thresh ? f[j] * scale : 0.f;
+    v.set(f);
+    v.store(y + i);
+  } else {
+    for (long long j = i; j < n; ++j) y[j] = from_f32<T>(vi_hash32((uint32_t)j, key) >= thresh ? ldf(x, j) * scale : 0.f);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // LayerNorm backward.  y = LN(a [+ b]) * gamma + beta;  dy = dy32 [+ dy16].
 //   dx[r] = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma      (one warp per row)
@@ -668,7 +690,7 @@ inline bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 int vi_attn_bwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* dout,
                    int64_t ldo, void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv,
                    const uint8_t* key_mask, const float* pair_dist, const float* bias_affine, float* d_affine, int B, int H,
-                   int Lq, int Lk, int mask_mode, cudaStream_t st);
+                   int Lq, int Lk, int mask_mode, float drop_p, uint32_t drop_site, const uint32_t* drop_seed, cudaStream_t st);
 
 extern "C" int vi_transpose(const void* src, int64_t ld, void* dst, int64_t ldd, int rows, int cols, int pad_rows, int dtype,
                             vi_stream_t stream) {
@@ -711,6 +733,23 @@ extern "C" int vi_colsum(const void* x, int64_t ld, int dtype, float* out, int64
                       scratch, (long long)rows, cols));
   VI_CUDA(vi_launch(chunk_sum_kernel, dim3((cols + 255) / 256, 1, 1), dim3(256), 0, ST(stream), (const float*)scratch, out, nch, cols,
                     (long long)rows, one_group(), (long long)0));
+  return VI_OK;
+}
+
+extern "C" int vi_dropout(const void* x, void* y, int64_t n, float p, const uint32_t* seed, uint32_t site, int dtype,
+                          vi_stream_t stream) {
+  VI_CHECK_ARG(x && y && seed && p >= 0.f && p < 1.f, "vi_dropout: bad operands (0 <= p < 1, seed must be a device pointer)");
+  VI_CHECK_ARG((((uintptr_t)x | (uintptr_t)y) & 15) == 0, "vi_dropout: operands must be 16-byte aligned");
+  if (n <= 0) return VI_OK;
+  const uint32_t thresh = vi_drop_threshold(p);
+  const float scale = 1.0f / (1.0f - p);
+  dim3 grid((unsigned)((n + 2047) / 2048));
+  if (dtype == VI_DT_BF16)
+    VI_CUDA(vi_launch(dropout_kernel<bf16>, grid, dim3(256), 0, ST(stream), reinterpret_cast<const bf16*>(x),
+                      reinterpret_cast<bf16*>(y), (long long)n, thresh, scale, seed, site));
+  else
+    VI_CUDA(vi_launch(dropout_kernel<float>, grid, dim3(256), 0, ST(stream), reinterpret_cast<const float*>(x),
+                      reinterpret_cast<float*>(y), (long long)n, thresh, scale, seed, site));
   return VI_OK;
 }
 
@@ -812,18 +851,21 @@ extern "C" int vi_rowdot_bwd(const float* dout, const float* x, const float* w, 
 extern "C" int vi_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* dout,
                            int64_t ldo, void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, int dtype,
                            const uint8_t* key_mask, const float* pair_dist, const float* bias_affine, float* d_affine, int B,
-                           int H, int Lq, int Lk, int mask_mode, vi_stream_t stream) {
+                           int H, int Lq, int Lk, int mask_mode, float drop_p, uint32_t drop_site, const uint32_t* drop_seed,
+                           vi_stream_t stream) {
   VI_CHECK_ARG(q && k && v && dout && dq && dk && dv, "vi_attn_bwd: null operand");
   VI_CHECK_ARG(B > 0 && H > 0 && Lq > 0 && Lk > 0, "vi_attn_bwd: bad sizes B=%d H=%d Lq=%d Lk=%d", B, H, Lq, Lk);
   VI_CHECK_ARG(((size_t)Lk * (65 * 2 + 64 * 2 + 1) + 8 * (size_t)(128 + 2 * Lk)) * sizeof(float) <= 220 * 1024,
                "vi_attn_bwd: Lk=%d keys do not fit the 220 KB shared-memory tile", Lk);
   VI_CHECK_ARG(!pair_dist || bias_affine, "vi_attn_bwd: pair_dist needs bias_affine");
+  VI_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f && (drop_p == 0.f || drop_seed), "vi_attn_bwd: bad dropout arguments");
   VI_CHECK_ARG(H * 64 <= ldq && H * 64 <= ldk && H * 64 <= ldv && H * 64 <= ldo, "vi_attn_bwd: leading dimensions smaller than H*64");
   if (dtype == VI_DT_BF16 && !getenv("VI_ATTN_BWD_SIMT")) {
     const int rc = vi_attn_bwd_tc(q, ldq, k, ldk, v, ldv, dout, ldo, dq, lddq, dk, lddk, dv, lddv, key_mask, pair_dist,
-                                  bias_affine, d_affine, B, H, Lq, Lk, mask_mode, ST(stream));
+                                  bias_affine, d_affine, B, H, Lq, Lk, mask_mode, drop_p, drop_site, drop_seed, ST(stream));
     if (rc <= 0) return rc;            // launched (0) or failed (< 0); 1 = does not fit -> fp32-arithmetic kernel below
   }
+  VI_CHECK_ARG(drop_p == 0.f, "vi_attn_bwd: attention dropout is implemented by the bf16 tensor-core kernel only");
   AttnBwdParams p;
   p.q = q; p.ldq = ldq; p.k = k; p.ldk = ldk; p.v = v; p.ldv = ldv; p.dout = dout; p.ldo = ldo;
   p.dq = dq; p.lddq = lddq; p.dk = dk; p.lddk = lddk; p.dv = dv; p.lddv = lddv;

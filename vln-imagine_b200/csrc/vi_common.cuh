@@ -81,6 +81,24 @@ __device__ __forceinline__ void pdl_enter() { pdl_launch_dependents(); pdl_wait(
 // read-only from `const T* __restrict__`): such a load may hit a stale L1 line of the SM.  The kernels of this library
 // therefore take plain `const T*` inputs (coherent ld.global), cp.async.cg or TMA.
 
+// Counter-based dropout mask: element `idx` of dropout site `site` is kept iff hash(idx, seed + site) >= threshold, with
+// threshold = p * 2^32.  `seed` lives in device memory (it advances once per optimiser step, also inside replayed CUDA
+// graphs); the same (seed, site, idx) regenerates the mask in the backward pass, so no mask is ever stored.
+__device__ __forceinline__ uint32_t vi_hash32(uint32_t idx, uint32_t key) {
+  uint32_t h = idx * 0x9E3779B1u + key;
+  h ^= h >> 16; h *= 0x7FEB352Du;
+  h ^= h >> 15; h *= 0x846CA68Bu;
+  h ^= h >> 16;
+  return h;
+}
+__device__ __forceinline__ uint32_t vi_drop_key(const uint32_t* seed, uint32_t site) {
+  return vi_hash32(site, *seed ^ 0xA511E9B3u);
+}
+__host__ __device__ __forceinline__ uint32_t vi_drop_threshold(float p) {
+  const double t = (double)p * 4294967296.0;
+  return t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -165,6 +165,8 @@ def _align_forward_train(model, txt, img, rows, pk, lowp, shape):
         raise NotImplementedError('backward of aux_loss_type %r' % cfg.aux_loss_type)
     B, I = shape
     x = ag.GatherSlotsFn.apply(img, rows.unit, rows.slot, rows.R, lowp)
+    if model.training:
+        x = ag.dropout(x, 0.15)                               # MLPProjectionHead.dropout (models/vilmodel.py:578,585)
     for j, lp in enumerate(pk):
         last = j == len(pk) - 1
         x = ag.linear(x, lp, lowp, out_dtype=F32 if (last or not lowp) else BF16)
@@ -264,14 +266,22 @@ class GlocalTextPathNavCMT(nn.Module):
 
     def _recording(self, *inputs) -> bool:
         """True when this call must record autograd nodes (fine-tuning): gradients are enabled and a parameter
-        or an input asks for one.  Dropout is not implemented: the probabilities must be 0 while training."""
+        or an input asks for one."""
         if not torch.is_grad_enabled():
             return False
-        rec = any(torch.is_tensor(t) and t.requires_grad for t in inputs) or any(p.requires_grad for p in self.parameters())
-        if rec and self.training and (self.config.hidden_dropout_prob > 0 or self.config.attention_probs_dropout_prob > 0):
-            raise NotImplementedError('train-mode dropout is not implemented: set hidden_dropout_prob = '
-                                      'attention_probs_dropout_prob = 0 (or call .eval()) for fine-tuning')
-        return rec
+        return any(torch.is_tensor(t) and t.requires_grad for t in inputs) or any(p.requires_grad for p in self.parameters())
+
+    def _drop(self):
+        """(hidden, attention-probability) dropout of this call: the config's probabilities in train() mode, else none.
+        Dropout exists on the autograd-recording path only (as in the reference, eval() / no_grad inference has none)."""
+        if not self.training:
+            return (0.0, 0.0)
+        ph, pa = float(self.config.hidden_dropout_prob), float(self.config.attention_probs_dropout_prob)
+        if (ph > 0 or pa > 0) and not self.lowp:
+            raise NotImplementedError('dropout is implemented for the bf16 kernels only: use eval() or p = 0 in the fp32 check mode')
+        if (ph > 0 or pa > 0) and not torch.is_grad_enabled():
+            raise NotImplementedError('train() mode with dropout under torch.no_grad() is not supported: call .eval() for inference')
+        return (ph, pa)
 
     # -- modes ------------------------------------------------------------------------------------
     def forward_text(self, txt_ids, txt_masks):
@@ -280,10 +290,10 @@ class GlocalTextPathNavCMT(nn.Module):
         lowp = self.lowp
         B, L = txt_ids.shape
         e = self.embeddings
-        with blocks.grad_mode(self._recording() and not self.config.fix_lang_embedding):
+        with blocks.grad_mode(self._recording() and not self.config.fix_lang_embedding, self._drop()):
             x = blocks.embed(B * L, txt_ids.device, idx=txt_ids.long().contiguous().view(-1), table=e.word_embeddings.weight,
                              pos_table=e.position_embeddings.weight, pos_period=L,
-                             const_rows=(e.token_type_embeddings.weight[0],), out_ln=e.LayerNorm, lowp=lowp)
+                             const_rows=(e.token_type_embeddings.weight[0],), out_ln=e.LayerNorm, lowp=lowp, dropout=True)
             s = [Stream(0, B, L, blocks.mask_u8(txt_masks))]
             for pk in self._pk()['lang']:
                 x = blocks.self_attn_ffn(x, pk, s, None, lowp)
@@ -296,7 +306,7 @@ class GlocalTextPathNavCMT(nn.Module):
         """'imagine' (bypass encoder): features + type embedding 0.  :562-573, :1081-1085."""
         self._guard(imagine_feats)
         B, I, _ = imagine_feats.shape
-        with blocks.grad_mode(self._recording(imagine_feats)):
+        with blocks.grad_mode(self._recording(imagine_feats), self._drop()):
             y = blocks.embed(B * I, imagine_feats.device, a=_f32c(imagine_feats).view(B * I, HIDDEN),
                              const_rows=(self.imagine_embeddings.type_embedding.weight[0],))
         return y.f32.view(B, I, HIDDEN)
@@ -314,12 +324,13 @@ class GlocalTextPathNavCMT(nn.Module):
         v32 = _f32c(view_img_fts).view(B * V, Fd)
         pano_masks = torch.arange(V, device=dev)[None, :] < view_lens.to(dev)[:, None]      # ops.py:36-44
         km = blocks.mask_u8(pano_masks)
-        with blocks.grad_mode(self._recording(view_img_fts) and not self.config.fix_pano_embedding):
+        with blocks.grad_mode(self._recording(view_img_fts) and not self.config.fix_pano_embedding, self._drop()):
             a = blocks.linear(blocks.operand(v32, lowp), pk['img_linear'], lowp, out_dtype=F32)
             x32 = blocks.embed(B * V, dev, a=a, a_ln=ie.img_layer_norm, feat=_f32c(loc_fts).view(B * V, -1),
                                feat_lin=ie.loc_linear, feat_ln=ie.loc_layer_norm,
                                idx=nav_types.long().contiguous().view(-1), table=ie.nav_type_embedding.weight,
-                               const_rows=(self.embeddings.token_type_embeddings.weight[1],), out_ln=ie.layer_norm).f32
+                               const_rows=(self.embeddings.token_type_embeddings.weight[1],), out_ln=ie.layer_norm,
+                               dropout=True).f32
             for lp in pk['pano']:
                 x32 = blocks.pano_layer(x32, lp, B, V, km, lowp)
             y32 = blocks.layer_norm(x32, None, pk['pano_norm'], 1e-12, False).f32
@@ -344,7 +355,7 @@ class GlocalTextPathNavCMT(nn.Module):
         ge, le = self.global_encoder, self.local_encoder
 
         if ctx_kv is None and self._recording(txt_embeds, gmap_img_embeds, vp_img_embeds, imagine_embeds):
-            with blocks.grad_mode(True):
+            with blocks.grad_mode(True, self._drop()):
                 return self._navigation_train(txt_embeds, txt_masks, gmap_img_embeds, gmap_step_ids, gmap_pos_fts, gmap_masks,
                                               gmap_pair_dists, gmap_visited_masks, gmap_vpids, vp_img_embeds, vp_pos_fts,
                                               vp_masks, vp_nav_masks, vp_cand_vpids, imagine_embeds, imagine_masks)
@@ -559,7 +570,7 @@ class GlocalTextPathNavCMT(nn.Module):
         txt = batch['align_txt_embeds']
         if self.config.fix_lang_inside_cosine_model:
             txt = txt.detach()
-        with blocks.grad_mode(self._recording(txt, batch['align_imagine_embeds'])):
+        with blocks.grad_mode(self._recording(txt, batch['align_imagine_embeds']), self._drop()):
             return align_forward(self, txt, batch['align_imagine_embeds'], batch['sub_instr_imag_flag'],
                                  batch['noun_phrase_segs'], self.lowp)
 
@@ -641,8 +652,13 @@ class VLNBert(nn.Module):
         batch = collections.defaultdict(lambda: None, batch)
         m = self.vln_bert
         if mode == 'panorama':
-            if self.training and self.drop_env.p > 0:
-                raise NotImplementedError('train-mode feature dropout runs through train.py')
+            if self.training and self.drop_env.p > 0:                      # models/model.py:27: nn.Dropout on the view features
+                batch = dict(batch)
+                feats = batch['view_img_fts']
+                feats = feats if feats.is_cuda else feats.to(m.embeddings.LayerNorm.weight.device, non_blocking=True)
+                ops.ensure_init(feats)
+                batch['view_img_fts'] = ag.dropout(feats.float(), float(self.drop_env.p))
+                batch = collections.defaultdict(lambda: None, batch)
             if self._graphable() and batch['obj_img_fts'] is None:
                 dev = m.embeddings.LayerNorm.weight.device
                 tok = graphs.weights_token(m, self._wt_cache)

@@ -275,6 +275,9 @@ def attention_multi(problems, mask_mode: int = MASK_ADD_NEG10000):
             raise _lib.VlnImagineError('key_mask must be a contiguous uint8 tensor')
         a.key_mask, a.pair_dist, a.bias_affine, a.lse = _ptr(km), _ptr(pr.get('pair_dist')), _ptr(pr.get('bias_affine')), _ptr(pr.get('lse'))
         a.B, a.Lq, a.Lk = pr['B'], pr['Lq'], pr['Lk']
+        drop = pr.get('drop')                      # (p, site, seed tensor) or None: attention-probability dropout
+        if drop is not None and drop[0] > 0:
+            a.drop_p, a.drop_site, a.drop_seed = float(drop[0]), int(drop[1]) & 0xFFFFFFFF, drop[2].data_ptr()
         if dtype is None:
             dtype = q.dtype
         elif dtype != q.dtype:
