@@ -296,9 +296,8 @@ def run_train(args, shape, desc, rank, local_rank, world):
     shapes = {k: list(v.shape) for k, v in net.state_dict().items()}
     net.load_state_dict(synth.synth_state_dict(shapes, seed=0))
     net.precision = args.precision
-    # dropout is not implemented in the training path: probabilities 0, as in the gradient-parity runs
-    net.config.hidden_dropout_prob = net.config.attention_probs_dropout_prob = 0.0
-    model.drop_env.p = 0.0
+    # train() mode with the released recipe's dropout (hidden / attention 0.1, feature dropout 0.4, projection head 0.15;
+    # D/scripts/run_r2r.sh:66): counter-based masks, regenerated in the backward pass
     model.train()
     ep_host = synth.to_torch(synth.duet_episode(shape, 1234 + rank + int(os.environ.get('VI_BENCH_SEED_OFFSET', '0'))))
     host = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in ep_host.items()}
@@ -420,7 +419,8 @@ def run_train(args, shape, desc, rank, local_rank, world):
         'config': {'workload': '%s: %s' % (args.workload, desc), 'episodes_per_gpu': B, 'nav_steps_per_iteration': T,
                    'replay': 'eager launches (autograd)' if args.no_graph else 'two CUDA graphs per iteration (forward + backward | '
                              'clipping + AdamW) around the eager NCCL all-reduce',
-                   'dropout': 'off (not implemented in the training path)',
+                   'dropout': 'on: hidden %.2f, attention %.2f, features %.2f, projection head 0.15'
+                              % (net.config.hidden_dropout_prob, net.config.attention_probs_dropout_prob, model.drop_env.p),
                    'l2': 'no flush: an iteration touches > 3 GB of weights, gradients and saved activations',
                    'collective': 'one NCCL all-reduce (AVG) of the flat fp32 gradient buffer, %.0f MB' % (flat.bytes() / 1e6),
                    'weights': 'random-init (deterministic synthetic)'},
