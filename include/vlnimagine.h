@@ -271,6 +271,9 @@ int vi_duet_fuse_logits_bwd(const float* g_raw, const float* l_raw, const float*
                             const int32_t* gmap_ids, const int32_t* cand_ids,
                             const float* d_global, const float* d_local, const float* d_fused,
                             float* dg_raw, float* dl_raw, float* dfuse_raw, int B, int G, int P, vi_stream_t stream);
+/* adjoint of vi_mul_bcast w.r.t. the broadcast row s: ds[b, :] = sum_r dy[b, r, :] * x[b, r, :] (contiguous [B, rows, 768];
+ * the gradient w.r.t. x is vi_mul_bcast(dy, s)).  HAMT act_pred_token 'ob_txt' (H/models/vilmodel_cmt.py:1191). */
+int vi_mul_bcast_bwd_s(const float* dy, const float* x, float* ds, int64_t n_batches, int rows_per_batch, vi_stream_t stream);
 /* adjoint of vi_cosine_loss: dloss is the device scalar gradient of the mean; dproj / dtgt may be NULL */
 int vi_cosine_loss_bwd(const float* proj, const float* tgt, const float* dloss, float* dproj, float* dtgt, int R,
                        vi_stream_t stream);

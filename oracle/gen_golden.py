@@ -248,6 +248,65 @@ def run_duet_grads(args):
         print(tag, 'loss', float(loss), 'ce', float(ce), 'aux', float(aux), 'max grad norm', max(norms), 'min', min(norms))
 
 
+def hamt_targets_of(ep):
+    """teacher action for the HAMT fixture: the last admissible observation token (nav_type != 0), i.e. [stop]"""
+    ok = ep['ob_nav_types'] != 0
+    idx = torch.arange(ok.shape[1], device=ok.device)[None, :].expand_as(ok)
+    return torch.where(ok, idx, torch.zeros_like(idx)).max(1).values
+
+
+def hamt_train_step(call, ep, hist_masks):
+    """One fine-tuning step of the HAMT agent on one navigation step (r2r/agent_cmt.py:371-605 + loss :610-640):
+    loss = CE_sum(act_logits, teacher) / B + 0.5 * aux.  ``call(mode, **kw)`` is the NavCMT-level model under test; the
+    history embeddings are inputs (fix_hist_embedding, the released configuration)."""
+    txt = call('language', txt_ids=ep['txt_ids'], txt_masks=ep['txt_masks'])
+    img = call('imagine', imagine_pano_img_feats=ep['imagine_feats'], imagine_masks=None)
+    aux, img2 = call('align_with_contrastive_loss', align_txt_embeds=txt, txt_masks=ep['txt_masks'],
+                     align_imagine_embeds=img, imagine_masks=ep['imagine_masks'], sub_instr_segs=ep['sub_instr_segs'],
+                     sub_instr_imag_flag=ep['sub_instr_imag_flag'], noun_phrase_segs=ep['noun_phrase_segs'],
+                     obs_instr_ids=ep['obs_instr_ids'])
+    logits, txt_o, hist_o, ob_o = call(
+        'visual', txt_embeds=txt, txt_masks=ep['txt_masks'], hist_embeds=ep['hist_embeds'], hist_masks=hist_masks,
+        ob_img_feats=ep['ob_img_feats'], ob_ang_feats=ep['ob_ang_feats'], ob_nav_types=ep['ob_nav_types'],
+        ob_masks=ep['ob_masks'], imagine_embeds=img2, imagine_masks=ep['imagine_masks'])
+    tgt = hamt_targets_of(ep)
+    ce = torch.nn.functional.cross_entropy(logits, tgt, reduction='sum') / tgt.shape[0]
+    return ce + 0.5 * aux, ce, aux, logits
+
+
+def run_hamt_grads(args):
+    from importlib import import_module
+    synth = import_module('vln_imagine_b200.synth')
+    from oracle import hamt_oracle as O
+    ref = build_reference('hamt')
+    ref.contrastive_alignment_model.image_proj.dropout = _Clone()
+    manifest = {k: list(v.shape) for k, v in ref.state_dict().items()}
+    sd = synth.synth_state_dict(manifest, seed=0)
+    ref.load_state_dict(sd)
+    for tag, shape, seed in [('tiny', synth.TINY, 7), ('cfg1', synth.CFG1, 1234)]:
+        ref.zero_grad(set_to_none=True)
+        ep = synth.to_torch(synth.hamt_episode(shape, seed))
+        hm = O.hist_masks_from_lens(ep['hist_lens'], ep['hist_embeds'].shape[1])
+        loss, ce, aux, logits = hamt_train_step(lambda mode, **kw: ref(mode, **kw), ep, hm)
+        loss.backward()
+        out = {'loss': loss.detach(), 'ce': ce.detach(), 'aux': aux.detach(), 'act_logits': logits.detach()}
+        names, norms, samples = [], [], []
+        for name, p in ref.named_parameters():
+            if p.grad is None:
+                continue
+            names.append(name)
+            g = p.grad.detach().double().reshape(-1)
+            norms.append(float(g.norm()))
+            samples.append(g[torch.from_numpy(grad_sample_index(name, g.numel()))].float().numpy())
+        out['grad_norms'] = np.asarray(norms, np.float64)
+        out['grad_samples'] = np.stack(samples)
+        np.savez(os.path.join(GOLD, 'hamt_grads_%s.npz' % tag), **_np(out))
+        with open(os.path.join(GOLD, 'hamt_grads_names.json'), 'w') as f:
+            json.dump(names, f, indent=0)
+        print(tag, 'loss', float(loss.detach()), 'ce', float(ce.detach()), 'aux', float(aux.detach()), 'params with grad', len(names),
+              'of', len(list(ref.named_parameters())))
+
+
 def run_hamt(args):
     from importlib import import_module
     synth = import_module('vln_imagine_b200.synth')
@@ -303,7 +362,6 @@ if __name__ == '__main__':
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
     if a.grads:
-        assert a.model == 'duet'
-        run_duet_grads(a)
+        (run_duet_grads if a.model == 'duet' else run_hamt_grads)(a)
     else:
         (run_duet if a.model == 'duet' else run_hamt)(a)

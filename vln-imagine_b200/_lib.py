@@ -78,6 +78,7 @@ PROTOTYPES = {
     'vi_attn_bwd': [_p, _l, _p, _l, _p, _l, _p, _l, _p, _l, _p, _l, _p, _l, _i, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, C.c_uint32, _p, _p],
     'vi_dropout': [_p, _p, _l, _f, _p, C.c_uint32, _i, _p],
     'vi_duet_fuse_logits_bwd': [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
+    'vi_mul_bcast_bwd_s': [_p, _p, _p, _l, _i, _p],
     'vi_cosine_loss_bwd': [_p, _p, _p, _p, _p, _i, _p],
 }
 for _name, _args in PROTOTYPES.items():

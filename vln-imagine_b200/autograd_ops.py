@@ -552,3 +552,26 @@ class CosineLossFn(Function):
               'vi_cosine_loss_bwd')
         _launched(1)
         return dp, dt, None
+
+
+class MulBcastFn(Function):
+    """y[b, r, :] = x[b, r, :] * s[b, :]   (x [B, R, 768], s [B, 768], both contiguous fp32) -> bf16 or fp32 rows [B*R, 768]"""
+
+    @staticmethod
+    def forward(ctx, x, s, lowp):
+        x, s = x.contiguous(), s.contiguous()
+        B, R, _ = x.shape
+        y32, y16 = ops.mul_bcast(x, R * HIDDEN, s, HIDDEN, B, R, want16=lowp, want32=not lowp)
+        ctx.save_for_backward(x, s)
+        return y16 if lowp else y32
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, s = ctx.saved_tensors
+        B, R, _ = x.shape
+        dy = dy.float().contiguous().view(B, R, HIDDEN)
+        dx, _ = ops.mul_bcast(dy, R * HIDDEN, s, HIDDEN, B, R, want16=False)
+        ds = torch.empty_like(s)
+        check(lib.vi_mul_bcast_bwd_s(dy.data_ptr(), x.data_ptr(), ds.data_ptr(), B, R, _stream()), 'vi_mul_bcast_bwd_s')
+        _launched(1)
+        return dx.view(B, R, HIDDEN), ds, None

@@ -26,6 +26,7 @@ class _Mode:
     train = False
     p_hidden = 0.0          # nn.Dropout(hidden_dropout_prob) sites (train() mode only)
     p_attn = 0.0            # attention_probs_dropout_prob
+    p_head = 0.0            # pred_head_dropout_prob (HAMT NextActionPrediction)
 
 
 class grad_mode:
@@ -36,11 +37,12 @@ class grad_mode:
         self.drop = drop if self.flag else (0.0, 0.0)
 
     def __enter__(self):
-        self.prev = (_Mode.train, _Mode.p_hidden, _Mode.p_attn)
+        self.prev = (_Mode.train, _Mode.p_hidden, _Mode.p_attn, _Mode.p_head)
         _Mode.train, _Mode.p_hidden, _Mode.p_attn = self.flag, float(self.drop[0]), float(self.drop[1])
+        _Mode.p_head = float(self.drop[2]) if len(self.drop) > 2 else 0.0
 
     def __exit__(self, *a):
-        _Mode.train, _Mode.p_hidden, _Mode.p_attn = self.prev
+        _Mode.train, _Mode.p_hidden, _Mode.p_attn, _Mode.p_head = self.prev
 
 
 def _attn_drop(device, p=None):
@@ -491,6 +493,7 @@ class ClsHeadPack:
         self.ln = LNPack([h.net[2] for h in heads])
         self.w1 = StackPack([h.net[last_index].weight for h in heads])
         self.b1 = StackPack([h.net[last_index].bias for h in heads])
+        self.has_dropout = last_index == 4
 
 
 def cls_head(x: torch.Tensor, pk: ClsHeadPack, lowp: bool, ends=None, eps=1e-12) -> torch.Tensor:
@@ -498,6 +501,8 @@ def cls_head(x: torch.Tensor, pk: ClsHeadPack, lowp: bool, ends=None, eps=1e-12)
     if _Mode.train:
         h = ag.ActFn.apply(ag.linear(x, pk.w0, lowp, out_dtype=F32, ends=ends), EPI_RELU)
         y32, _ = ag.layer_norm(h, None, pk.ln, eps, False, ends)
+        if pk.has_dropout and _Mode.p_head > 0:               # NextActionPrediction net.3 (H/models/vilmodel_cmt.py:953-963)
+            y32 = ag.dropout(y32, _Mode.p_head)
         n = len(pk.w1.tensors)
         return ag.RowDotFn.apply(y32, pk.w1.get(), pk.b1.get(), ends, n, *pk.w1.tensors, *pk.b1.tensors)
     w, b = pk.w0.get(lowp)

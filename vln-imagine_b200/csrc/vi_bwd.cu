@@ -564,6 +564,23 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const AttnBwdParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// adjoint of vi_mul_bcast w.r.t. the broadcast row:  ds[b, c] = sum_r dy[b, r, c] * x[b, r, c]   (one CTA per episode)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) mul_bcast_bwd_s_kernel(const float* dy, const float* x, float* __restrict__ ds,
+                                                              int rows_per_batch) {
+  pdl_enter();
+  const long long b = blockIdx.x;
+  for (int c = threadIdx.x; c < D; c += 256) {
+    float t = 0.f;
+    for (int r = 0; r < rows_per_batch; ++r) {
+      const long long i = (b * rows_per_batch + r) * D + c;
+      t = fmaf(dy[i], x[i], t);
+    }
+    ds[b * D + c] = t;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // adjoint of vi_duet_fuse_logits (one warp per episode, same id matching as the forward kernel)
 // ---------------------------------------------------------------------------------------------
 constexpr int FUSE_MAX = 512;
@@ -894,6 +911,13 @@ extern "C" int vi_duet_fuse_logits_bwd(const float* g_raw, const float* l_raw, c
   VI_CHECK_ARG(B > 0 && G > 0 && P > 0 && G <= FUSE_MAX && P <= FUSE_MAX, "vi_duet_fuse_logits_bwd: bad sizes");
   VI_CUDA(vi_launch(duet_fuse_logits_bwd_kernel, dim3(B), dim3(32), 0, ST(stream), g_raw, l_raw, fuse_raw, gmap_masks,
                     gmap_visited, vp_nav_masks, gmap_ids, cand_ids, d_global, d_local, d_fused, dg_raw, dl_raw, dfuse_raw, G, P));
+  return VI_OK;
+}
+
+extern "C" int vi_mul_bcast_bwd_s(const float* dy, const float* x, float* ds, int64_t n_batches, int rows_per_batch,
+                                  vi_stream_t stream) {
+  VI_CHECK_ARG(dy && x && ds && n_batches > 0 && rows_per_batch > 0, "vi_mul_bcast_bwd_s: bad operands");
+  VI_CUDA(vi_launch(mul_bcast_bwd_s_kernel, dim3((unsigned)n_batches), dim3(256), 0, ST(stream), dy, x, ds, rows_per_batch));
   return VI_OK;
 }
 

@@ -20,6 +20,7 @@ from typing import List, Optional
 import torch
 import torch.nn as nn
 
+from . import autograd_ops as ag
 from . import blocks, graphs, ops, params
 from .blocks import Act, Stream
 from .config import hamt_config
@@ -56,6 +57,9 @@ class NavCMT(nn.Module):
         self.encoder = params.HamtEncoderP(c)
         self.next_action = params.NextActionP(c.pred_head_dropout_prob)
         params.bert_init_(self)
+        if not c.update_lang_bert:                             # H/models/vilmodel_cmt.py:461-463
+            for p_ in self.encoder.layer.parameters():
+                p_.requires_grad = False
         self.fix_lang_embedding = c.fix_lang_embedding
         self.fix_hist_embedding = c.fix_hist_embedding
         self.fix_obs_embedding = c.fix_obs_embedding
@@ -105,6 +109,23 @@ class NavCMT(nn.Module):
             raise ValueError("precision must be 'bf16' or 'fp32'")
         return self.precision == 'bf16'
 
+    def _recording(self, *inputs) -> bool:
+        if not torch.is_grad_enabled():
+            return False
+        return any(torch.is_tensor(t) and t.requires_grad for t in inputs) or any(p.requires_grad for p in self.parameters())
+
+    def _drop(self):
+        """(hidden, attention, prediction-head) dropout of this call: the config's probabilities in train() mode"""
+        if not self.training:
+            return (0.0, 0.0, 0.0)
+        c = self.config
+        ps = (float(c.hidden_dropout_prob), float(c.attention_probs_dropout_prob), float(c.pred_head_dropout_prob))
+        if max(ps) > 0 and not self.lowp:
+            raise NotImplementedError('dropout is implemented for the bf16 kernels only: use eval() or p = 0 in the fp32 check mode')
+        if max(ps) > 0 and not torch.is_grad_enabled():
+            raise NotImplementedError('train() mode with dropout under torch.no_grad() is not supported: call .eval() for inference')
+        return ps
+
     # -- modes ------------------------------------------------------------------------------------
     def forward_text(self, txt_ids, txt_masks):
         """'language', :1008-1031."""
@@ -112,21 +133,23 @@ class NavCMT(nn.Module):
         lowp = self.lowp
         B, L = txt_ids.shape
         e = self.embeddings
-        y32, y16 = ops.embed_compose(B * L, txt_ids.device, idx=txt_ids.long().contiguous().view(-1),
-                                     table=e.word_embeddings.weight, pos_table=e.position_embeddings.weight, pos_period=L,
-                                     const_row=e.token_type_embeddings.weight[0],
-                                     out_ln=(e.LayerNorm.weight, e.LayerNorm.bias), want16=lowp)
-        x = Act(y32, y16)
-        s = [Stream(0, B, L, blocks.mask_u8(txt_masks))]
-        for pk in self._pk()['lang']:
-            x = blocks.self_attn_ffn(x, pk, s, None, lowp)
+        frozen = self.fix_lang_embedding or not self.config.update_lang_bert
+        with blocks.grad_mode(self._recording() and not frozen, self._drop() if not frozen else (0.0, 0.0)):
+            x = blocks.embed(B * L, txt_ids.device, idx=txt_ids.long().contiguous().view(-1), table=e.word_embeddings.weight,
+                             pos_table=e.position_embeddings.weight, pos_period=L,
+                             const_rows=(e.token_type_embeddings.weight[0],), out_ln=e.LayerNorm, lowp=lowp, dropout=True)
+            s = [Stream(0, B, L, blocks.mask_u8(txt_masks))]
+            for pk in self._pk()['lang']:
+                x = blocks.self_attn_ffn(x, pk, s, None, lowp)
         out = x.f32.view(B, L, HIDDEN)
-        return out.detach() if self.fix_lang_embedding else out
+        return out.detach() if frozen else out
 
     def forward_history(self, hist_img_feats, hist_ang_feats, ob_step_ids, hist_pano_img_feats, hist_pano_ang_feats):
         """'history': HistoryEmbeddings.forward, :576-618."""
         he = self.hist_embeddings
         lowp = self.lowp
+        if not self.fix_hist_embedding and self._recording(hist_img_feats) and any(p.requires_grad for p in he.parameters()):
+            raise NotImplementedError('training the history embeddings (fix_hist_embedding=False) is not on the released path')
         type_row = he.type_embedding.weight[0]
         ln = (he.layer_norm.weight, he.layer_norm.bias)
         if hist_img_feats is None:
@@ -178,9 +201,10 @@ class NavCMT(nn.Module):
         """'imagine' (bypass encoder), :620-631, :1040-1048."""
         ops.ensure_init(imagine_pano_img_feats)
         B, I, _ = imagine_pano_img_feats.shape
-        y32, _ = ops.embed_compose(B * I, imagine_pano_img_feats.device, a=_f32c(imagine_pano_img_feats).view(B * I, HIDDEN),
-                                   const_row=self.imagine_embeddings.type_embedding.weight[0])
-        out = y32.view(B, I, HIDDEN)
+        with blocks.grad_mode(self._recording(imagine_pano_img_feats) and not self.fix_imagine_embeds):
+            y = blocks.embed(B * I, imagine_pano_img_feats.device, a=_f32c(imagine_pano_img_feats).view(B * I, HIDDEN),
+                             const_rows=(self.imagine_embeddings.type_embedding.weight[0],))
+        out = y.f32.view(B, I, HIDDEN)
         return out.detach() if self.fix_imagine_embeds else out
 
     def forward_visual(self, txt_embeds, txt_masks, hist_embeds, hist_masks, ob_img_feats, ob_ang_feats, ob_nav_types,
@@ -199,6 +223,10 @@ class NavCMT(nn.Module):
         else:
             I = 0
         C = L + I
+        if self._recording(txt_embeds, hist_embeds, ob_img_feats, imagine_embeds):
+            with blocks.grad_mode(True, self._drop()):
+                return self._visual_train(txt_embeds, txt_masks, hist_embeds, hist_masks, ob_img_feats, ob_ang_feats,
+                                          ob_nav_types, ob_masks, imagine_embeds, imagine_masks)
         (r_l, r_v), ends, R = blocks.stack_layout([B * C, B * Nv])
         x32 = torch.empty((R, HIDDEN), dtype=F32, device=dev)
         x16 = torch.empty((R, HIDDEN), dtype=BF16, device=dev) if lowp else None
@@ -260,6 +288,56 @@ class NavCMT(nn.Module):
         act_logits = ops.mask_logits_navtype(raw, ob_nav_types.long().contiguous().view(-1)).view(B, O)
         return act_logits, txt_out, hist_out, ob_out
 
+    def _visual_train(self, txt_embeds, txt_masks, hist_embeds, hist_masks, ob_img_feats, ob_ang_feats, ob_nav_types,
+                      ob_masks, imagine_embeds, imagine_masks):
+        """'visual' with autograd recording: the same layer sequence as forward_visual from the differentiable blocks
+        (torch only concatenates / slices rows).  :1056-1205."""
+        cfg, lowp, pk = self.config, self.lowp, self._pk()
+        dev = txt_embeds.device
+        B, L, _ = txt_embeds.shape
+        T, O = hist_embeds.shape[1], ob_img_feats.shape[1]
+        Nv = T + O
+        I = imagine_embeds.shape[1] if cfg.imagine_enc_pano else 0
+        C = L + I
+        (r_l, r_v), ends, R = blocks.stack_layout([B * C, B * Nv])
+        ie = self.img_embeddings
+        o32 = _f32c(ob_img_feats).view(B * O, -1)
+        a = blocks.linear(blocks.operand(o32, lowp), pk['ob_img'], lowp, out_dtype=F32)
+        ob = blocks.embed(B * O, dev, a=a, a_ln=ie.img_layer_norm, feat=_f32c(ob_ang_feats).view(B * O, -1), feat_lin=ie.ang_linear,
+                          feat_ln=ie.ang_layer_norm, idx=ob_nav_types.long().contiguous().view(-1), table=ie.nav_type_embedding.weight,
+                          const_rows=(self.embeddings.token_type_embeddings.weight[1],), out_ln=ie.layer_norm, dropout=True).f32
+        if self.fix_obs_embedding:
+            ob = ob.detach()
+        lang = torch.cat([_f32c(txt_embeds), _f32c(imagine_embeds)], 1) if I else _f32c(txt_embeds)
+        visn = torch.cat([_f32c(hist_embeds), ob.view(B, O, HIDDEN)], 1)
+        parts = [lang.reshape(B * C, HIDDEN)]
+        if ends[0] > B * C:
+            parts.append(torch.zeros((ends[0] - B * C, HIDDEN), dtype=F32, device=dev))
+        x = blocks.as_act(torch.cat(parts + [visn.reshape(B * Nv, HIDDEN)], 0), lowp)
+        lang_mask = blocks.mask_u8(torch.cat([txt_masks.bool(), imagine_masks.bool()], 1) if I else txt_masks)
+        visn_mask = blocks.mask_u8(torch.cat([hist_masks.bool(), ob_masks.bool()], 1))
+        streams = [Stream(r_l, B, C, lang_mask, 0), Stream(r_v, B, Nv, visn_mask, 1)]
+        for cp, sp in zip(pk['x_cross'], pk['x_self']):
+            # bidirectional cross-attention with shared weights, both directions read the layer inputs (:385-397)
+            qkv = ag.linear(x.operand(lowp), cp['qkv'], lowp)
+            spec = [dict(q=(0, r_l, 0), k=(0, r_v, HIDDEN), v=(0, r_v, 2 * HIDDEN), B=B, Lq=C, Lk=Nv, key_mask=visn_mask, out_row0=r_l,
+                         drop=blocks._attn_drop(dev)),
+                    dict(q=(0, r_v, 0), k=(0, r_l, HIDDEN), v=(0, r_l, 2 * HIDDEN), B=B, Lq=Nv, Lk=C, key_mask=lang_mask, out_row0=r_v,
+                         drop=blocks._attn_drop(dev))]
+            ctx = ag.AttentionFn.apply(spec, R, blocks.MASK_ADD_NEG10000, 1, qkv)
+            x = blocks._dense_res_ln(ctx, cp['o'], x.f32, cp['ln'], 1e-12, lowp, None)
+            x = blocks.self_attn_ffn(x, sp, streams, ends, lowp)
+        lang_out = x.f32[r_l:r_l + B * C].view(B, C, HIDDEN)
+        visn_out = x.f32[r_v:r_v + B * Nv].view(B, Nv, HIDDEN)
+        txt_out, hist_out, ob_out = lang_out[:, :L], visn_out[:, :T], visn_out[:, T:]
+        if cfg.act_pred_token == 'ob_txt':                     # :1191
+            h = ag.MulBcastFn.apply(ob_out, lang_out[:, 0], lowp)
+        else:
+            h = blocks.operand(ob_out.reshape(B * O, HIDDEN), lowp)
+        raw = blocks.cls_head(h, pk['act'], lowp)
+        act_logits = raw.view(B, O).masked_fill(ob_nav_types.view(B, O) == 0, float('-inf'))
+        return act_logits, txt_out, hist_out, ob_out
+
     def forward(self, mode, txt_ids=None, txt_embeds=None, txt_masks=None, hist_img_feats=None, hist_ang_feats=None,
                 hist_pano_img_feats=None, hist_pano_ang_feats=None, hist_embeds=None, ob_step_ids=None, hist_masks=None,
                 ob_img_feats=None, ob_ang_feats=None, ob_nav_types=None, ob_masks=None, imagine_pano_img_feats=None,
@@ -278,7 +356,8 @@ class NavCMT(nn.Module):
             return self.forward_imagination(imagine_pano_img_feats, imagine_masks)
         if mode == 'align_with_contrastive_loss':
             ops.ensure_init(align_txt_embeds)
-            return align_forward(self, align_txt_embeds, align_imagine_embeds, sub_instr_imag_flag, noun_phrase_segs, self.lowp)
+            with blocks.grad_mode(self._recording(align_txt_embeds, align_imagine_embeds), self._drop()):
+                return align_forward(self, align_txt_embeds, align_imagine_embeds, sub_instr_imag_flag, noun_phrase_segs, self.lowp)
         if mode == 'visual':
             return self.forward_visual(txt_embeds, txt_masks, hist_embeds, hist_masks, ob_img_feats, ob_ang_feats,
                                        ob_nav_types, ob_masks, imagine_embeds, imagine_masks)
@@ -326,8 +405,12 @@ class VLNBertCMT(nn.Module):
         return super()._apply(fn, *a, **k)
 
     def _env_dropout(self, x):
+        """models/model_HAMT.py: nn.Dropout(feat_dropout) on image features in train() mode"""
         if x is not None and self.training and self.drop_env.p > 0:
-            raise NotImplementedError('train-mode feature dropout runs through train.py')
+            dev = self.vln_bert.embeddings.LayerNorm.weight.device
+            x = x if x.is_cuda else x.to(dev, non_blocking=True)
+            ops.ensure_init(x)
+            return ag.dropout(x.float(), float(self.drop_env.p))
         return x
 
     def _vis_fn(self, t):
