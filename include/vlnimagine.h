@@ -277,6 +277,11 @@ int vi_mul_bcast_bwd_s(const float* dy, const float* x, float* ds, int64_t n_bat
 /* adjoint of vi_cosine_loss: dloss is the device scalar gradient of the mean; dproj / dtgt may be NULL */
 int vi_cosine_loss_bwd(const float* proj, const float* tgt, const float* dloss, float* dproj, float* dtgt, int R,
                        vi_stream_t stream);
+/* adjoint of vi_infonce_loss w.r.t. proj (the noun-phrase means are constants under fix_lang_inside_cosine_model,
+ * D/models/vilmodel.py:1249-1255); `sims` = the first R * (n_negs + 1) floats the forward call left in its loss_rows scratch */
+int vi_infonce_loss_bwd(const float* proj, const float* tgt, const float* negs, const int32_t* row_episode,
+                        const int32_t* neg_episode, float temperature, const float* sims, const float* dloss,
+                        float* dproj, int R, int n_negs, vi_stream_t stream);
 
 /* Dropout (training only): y = x * keep / (1 - p) with keep(i) = hash(i, *seed, site) >= p * 2^32; the backward pass is the
  * same call on the gradient.  `seed` is a device pointer (the host module advances it once per optimiser step, also inside
@@ -287,6 +292,37 @@ int vi_dropout(const void* x, void* y, int64_t n, float p, const uint32_t* seed,
 
 /* fp32 -> bf16 shadow copy of a weight or activation */
 int vi_cast_bf16(const float* src, void* dst, int64_t n, vi_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Per-step graph glue of a DUET rollout.  Replaces the Python GraphMap /
+ * FloydGraph objects (D/models/graph_utils.py:42-148) and the agent's per-step collate loops
+ * (D/r2r/agent.py:98-207, 466-479) by dense per-episode arrays in HBM, caller-owned:
+ *   pos f64 [B,N,3]   dis f64 [B,N,N] (95959595 = never reached, graph_utils.py:44)   point i32 [B,N,N] (-1 = direct edge)
+ *   visited u8 [B,N]  esum f32 [B,N,H]   ecnt f32 [B,N]
+ * Node indices are the order in which viewpoints entered GraphMap.node_positions (the host interns the id strings);
+ * -1 marks the [stop] slot / padding.  fp64 state: distances, path lengths and the distance features are bit-identical
+ * to the reference's Python-float arithmetic; sin / cos of the fp32-cast angles agree to 1 ulp. */
+int vi_graph_init(double* dis, int32_t* point, uint8_t* visited, float* ecnt, int B, int N, vi_stream_t stream);
+/* GraphMap.update_graph (graph_utils.py:109-115): positions, add_edge (:53-58) to every candidate of the current
+ * viewpoint, FloydGraph.update(k) (:60-70).  cur_node[b] = -1 leaves episode b untouched (ended, agent.py:601-603);
+ * n_nodes[b] = nodes known after this update; cand_node [B,C] padded with -1. */
+int vi_graph_update(double* pos, double* dis, int32_t* point, uint8_t* visited, int B, int N, const int32_t* cur_node,
+                    const double* cur_pos, const int32_t* cand_node, const double* cand_pos, int C,
+                    const int32_t* n_nodes, vi_stream_t stream);
+/* agent.py:466-479: masked mean of pano_embeds [B,V,H] rewrites the current node, each UNVISITED candidate view j < C
+ * adds pano_embeds[b,j] to its node (GraphMap.update_node_embed, graph_utils.py:117-126); then (agent.py:125-129,
+ * 176-178) gmap_img_embeds[b,g] = esum / ecnt of gmap_node[b,g] (zeros for -1) and vp_img_embeds = [0 ; pano_embeds]
+ * ([B,V+1,H]); either output may be NULL.  cur_node[b] = -1 skips the update of an ended episode. */
+int vi_graph_embed_step(const float* pano_embeds, const uint8_t* pano_masks, int B, int V, int H, const int32_t* cur_node,
+                        const int32_t* cand_node, int C, const uint8_t* visited, float* esum, float* ecnt, int N,
+                        const int32_t* gmap_node, int G, float* gmap_img_embeds, float* vp_img_embeds, vi_stream_t stream);
+/* GraphMap.get_pos_fts (graph_utils.py:14-40,131-148) for the gmap slots ([B,G,7], zero beyond gmap_lens[b]) and the
+ * candidate views (vp_pos_fts [B,P,14] = start-viewpoint features | candidate features in rows 1..C, agent.py:182-196);
+ * gmap_pair_dists [B,G,G] raw metres with zero row / column 0 and diagonal (agent.py:137-141).  Outputs may be NULL. */
+int vi_graph_features(const double* pos, const double* dis, const int32_t* point, int B, int N, const int32_t* cur_node,
+                      const double* heading, const double* elevation, const int32_t* gmap_node, const int32_t* gmap_lens,
+                      int G, float* gmap_pos_fts, float* gmap_pair_dists, const int32_t* cand_node, int C,
+                      const int32_t* start_node, int P, float* vp_pos_fts, vi_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -293,6 +293,35 @@ def test_cosine_loss_bwd(ag):
     assert relerr(t.grad, tr.grad) < 1e-4
 
 
+@pytest.mark.parametrize('T', [0.07, 0.3])
+def test_infonce_loss_bwd(ag, T):
+    """InfoNCE alignment loss (models/vilmodel.py:657-687): negatives = noun-phrase means of OTHER episodes; the gradient
+    w.r.t. the projected imagination rows against torch autograd of F.cosine_similarity + F.cross_entropy"""
+    R, Nn = 41, 57
+    p = _rand(R, 768, seed=31).requires_grad_()
+    t, negs = _rand(R, 768, seed=32), _rand(Nn, 768, seed=33)
+    g = torch.Generator().manual_seed(5)
+    row_ep = torch.sort(torch.randint(0, 8, (R,), generator=g)).values.int().cuda()
+    neg_ep = torch.sort(torch.randint(0, 8, (Nn,), generator=g)).values.int().cuda()
+    loss = ag.InfoNCELossFn.apply(p, t, negs, row_ep, neg_ep, T, R, Nn)
+    (loss * 0.7).backward()
+    pr = p.detach().clone().requires_grad_()
+    ref = []
+    for r in range(R):
+        allt = torch.cat([t[r:r + 1], negs[neg_ep != row_ep[r]]], 0)
+        sim = F.cosine_similarity(pr[r:r + 1], allt) / T
+        ref.append(F.cross_entropy(sim[None], torch.zeros(1, dtype=torch.long, device='cuda')))
+    ref = torch.stack(ref).mean()
+    (ref * 0.7).backward()
+    assert abs(float(loss) - float(ref)) < 1e-4 * max(1.0, abs(float(ref)))
+    assert relerr(p.grad, pr.grad) < 1e-4
+    # no negatives at all: the loss is log(1) = 0 and so is the gradient
+    p2 = _rand(3, 768, seed=34).requires_grad_()
+    l2 = ag.InfoNCELossFn.apply(p2, _rand(3, 768, seed=35), None, torch.zeros(3, dtype=torch.int32, device='cuda'), None, T, 3, 0)
+    l2.backward()
+    assert abs(float(l2)) < 1e-6 and float(p2.grad.abs().max()) < 1e-6
+
+
 def test_slot_gather_scatter_bwd(ag):
     n, R = 40, 9
     src = _rand(n, 768, seed=26).requires_grad_()

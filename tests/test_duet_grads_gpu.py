@@ -153,3 +153,55 @@ def test_train_mode_dropout_step(env):
         net.precision = 'bf16'
         model.drop_env.p = 0.0
         model.eval()
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_duet_infonce_alignment_gradients(env, precision):
+    """aux_loss_type 'contrastive-InfoNCE' (models/vilmodel.py:657-779) through the module API with autograd recording:
+    the loss, the gradient of the three projection-head weights and of the incoming imagination embeddings against
+    torch autograd of the CPU oracle (which oracle/gen_golden.py pinned to the reference, nce_loss of duet_cfg1.npz)."""
+    from oracle import duet_oracle as O
+    synth, model = env
+    net = model.vln_bert
+    sd = synth.synth_state_dict(manifest('duet'), seed=0)
+    net.load_state_dict(sd)
+    net.precision = precision
+    net.zero_grad(set_to_none=True)
+    ep_cpu = synth.to_torch(synth.duet_episode(synth.CFG1, 1234))
+    ep = to_dev(ep_cpu)
+    T = 0.07                                  # HAMT-like temperature range; 0.007 (DUET default) is covered by the forward test
+    cfg = net.config
+    old = (cfg.aux_loss_type, cfg.infonce_temperature)
+    cfg.aux_loss_type, cfg.infonce_temperature = 'contrastive-InfoNCE', T
+    try:
+        with torch.no_grad():
+            txt = model('language', {'txt_ids': ep['txt_ids'], 'txt_masks': ep['txt_masks']})
+        img = model('imagine', {'imagine_feats': ep['imagine_feats'], 'imagine_masks': None}).detach().requires_grad_()
+        loss, img2 = model('align_with_contrastive_loss', {
+            'align_txt_embeds': txt, 'txt_masks': ep['txt_masks'], 'align_imagine_embeds': img,
+            'imagine_masks': ep['imagine_masks'], 'sub_instr_segs': ep['sub_instr_segs'],
+            'sub_instr_imag_flag': ep['sub_instr_imag_flag'], 'noun_phrase_segs': ep['noun_phrase_segs'],
+            'obs_instr_ids': ep['obs_instr_ids']})
+        (loss + 0.01 * img2.sum()).backward()
+    finally:
+        cfg.aux_loss_type, cfg.infonce_temperature = old
+    names = ['contrastive_alignment_model.image_proj.fc%d.weight' % i for i in (1, 2, 3)]
+    sdr = {k: (v.clone().requires_grad_() if k in names else v) for k, v in sd.items()}
+    txt_c = txt.detach().float().cpu()
+    img_c = img.detach().float().cpu().requires_grad_()
+    ref_loss, ref_img2 = O.forward_align_infonce(sdr, txt_c, img_c, ep_cpu['sub_instr_imag_flag'], ep_cpu['noun_phrase_segs'], T)
+    (ref_loss + 0.01 * ref_img2.sum()).backward()
+    tol = 1e-3 if precision == 'fp32' else 5e-2
+    assert abs(float(loss) - float(ref_loss)) < (1e-4 if precision == 'fp32' else 2e-2) * abs(float(ref_loss))
+    params = dict(net.named_parameters())
+    pairs = [(n, params[n].grad.float().cpu(), sdr[n].grad) for n in names] + [('d imagine_embeds', img.grad.float().cpu(), img_c.grad)]
+    for n, got, want in pairs:
+        if precision == 'fp32':
+            assert max_rel(got, want) < tol, n
+        else:
+            # bf16: a pre-activation that rounds across zero flips a ReLU of the projection head, which moves single
+            # elements of the ~30-row weight gradients by O(1) of the largest one (the reference under bf16 autocast
+            # does the same, see the module docstring): the bound is on the norm and on the direction
+            nerr = abs(float(got.norm()) - float(want.norm())) / float(want.norm())
+            cos = float((got * want).sum() / (got.norm() * want.norm()))
+            assert nerr < tol and cos > 0.99, (n, nerr, cos)

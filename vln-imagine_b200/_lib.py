@@ -80,6 +80,11 @@ PROTOTYPES = {
     'vi_duet_fuse_logits_bwd': [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
     'vi_mul_bcast_bwd_s': [_p, _p, _p, _l, _i, _p],
     'vi_cosine_loss_bwd': [_p, _p, _p, _p, _p, _i, _p],
+    'vi_infonce_loss_bwd': [_p, _p, _p, _p, _p, _f, _p, _p, _p, _i, _i, _p],
+    'vi_graph_init': [_p, _p, _p, _p, _i, _i, _p],
+    'vi_graph_update': [_p, _p, _p, _p, _i, _i, _p, _p, _p, _p, _i, _p, _p],
+    'vi_graph_embed_step': [_p, _p, _i, _i, _i, _p, _p, _i, _p, _p, _p, _i, _p, _i, _p, _p, _p],
+    'vi_graph_features': [_p, _p, _p, _i, _i, _p, _p, _p, _p, _p, _i, _p, _p, _p, _i, _p, _i, _p, _p],
 }
 for _name, _args in PROTOTYPES.items():
     _fn = getattr(lib, _name)            # AttributeError here = header/library mismatch: fail loudly

@@ -554,6 +554,30 @@ class CosineLossFn(Function):
         return dp, dt, None
 
 
+class InfoNCELossFn(Function):
+    """compute_contrastive_loss_infonce (models/vilmodel.py:657-687) with constant noun-phrase means; grad w.r.t. proj"""
+
+    @staticmethod
+    def forward(ctx, proj, tgt, negs, row_ep, neg_ep, temperature, R, n_negs):
+        proj = proj.contiguous()
+        loss, scratch = ops.infonce_loss_with_sims(proj, tgt, negs, row_ep, neg_ep, temperature, R, n_negs, proj.device)
+        ctx.save_for_backward(proj, tgt, scratch)
+        ctx.extra = (negs, row_ep, neg_ep, float(temperature), R, n_negs)
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        proj, tgt, scratch = ctx.saved_tensors
+        negs, row_ep, neg_ep, temperature, R, n_negs = ctx.extra
+        dloss = dloss.contiguous().float().view(1)
+        dp = torch.empty_like(proj)
+        check(lib.vi_infonce_loss_bwd(proj.data_ptr(), tgt.data_ptr(), _ptr(negs), row_ep.data_ptr(), _ptr(neg_ep), temperature,
+                                      scratch.data_ptr(), dloss.data_ptr(), dp.data_ptr(), R, n_negs, _stream()),
+              'vi_infonce_loss_bwd')
+        _launched(1)
+        return dp, None, None, None, None, None, None, None
+
+
 class MulBcastFn(Function):
     """y[b, r, :] = x[b, r, :] * s[b, :]   (x [B, R, 768], s [B, 768], both contiguous fp32) -> bf16 or fp32 rows [B*R, 768]"""
 

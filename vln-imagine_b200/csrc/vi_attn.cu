@@ -59,9 +59,17 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool v
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+// exp(x) as one MUFU.EX2: ex2.approx.ftz skips the denormal range fix-up that __expf's ex2.approx carries (results below
+// 2^-126 flush to zero, which a softmax numerator cannot tell from the 1e-38 it would otherwise be)
+__device__ __forceinline__ float fast_exp(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+  return y;
+}
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// grid (q-tiles of 64, H, sum of B over problems), 128 threads: warp w owns query rows [64*bx + 16w, +16).
+// grid (q-tiles, H, sum of B over problems), 32..128 threads (one warp per 16 queries of the longest stream, so that
+// no warp of a CTA idles on registers another CTA could use): warp w owns query rows [qrows*bx + 16w, +16).
 // K, V (whole head) and the Q tile are staged with cp.async; fragments come from ldmatrix (V through .trans, so no
 // explicit transpose); scores stay in registers with an fp32 online softmax over 64-key chunks.
 __global__ void __launch_bounds__(128, 5) attn_fwd_bf16_kernel(const AttnParams p) {
@@ -70,14 +78,15 @@ __global__ void __launch_bounds__(128, 5) attn_fwd_bf16_kernel(const AttnParams 
   int z = blockIdx.z, pi = 0;
   while (pi < p.n_problems - 1 && z >= p.pr[pi].B) { z -= p.pr[pi].B; ++pi; }
   const AttnProblem& pr = p.pr[pi];
-  const int q_base = blockIdx.x * 64;
+  const int nthr = blockDim.x, qrows = (blockDim.x >> 5) * 16;      // 1..4 warps: a 16-query tile each
+  const int q_base = blockIdx.x * qrows;
   if (q_base >= pr.Lq) return;
   const int b = z, h = blockIdx.y;
   const int LkP = pr.LkP;
   bf16* Ks = reinterpret_cast<bf16*>(smem);                 // [LkP][72]
   bf16* Vs = Ks + (size_t)LkP * ROW;                        // [LkP][72]
-  bf16* Qs = Vs + (size_t)LkP * ROW;                        // [64][72]
-  float* madd = reinterpret_cast<float*>(Qs + 64 * ROW);    // [LkP]
+  bf16* Qs = Vs + (size_t)LkP * ROW;                        // [qrows][72]
+  float* madd = reinterpret_cast<float*>(Qs + qrows * ROW); // [LkP]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   const bf16* kg = reinterpret_cast<const bf16*>(pr.k) + (long long)b * pr.Lk * pr.ldk + h * DH;
@@ -87,13 +96,13 @@ __global__ void __launch_bounds__(128, 5) attn_fwd_bf16_kernel(const AttnParams 
   // two cp.async groups: Q + the first 64 keys, then the remaining keys, so the first score chunk can start
   // while the tail of K / V is still in flight
   const int first = LkP < 64 ? LkP : 64;
-  for (int e = tid; e < 64 * 8; e += 128) {
+  for (int e = tid; e < qrows * 8; e += nthr) {
     const int r = e >> 3, ch = e & 7;
     const bool ok = q_base + r < pr.Lq;
     const int rr = ok ? q_base + r : 0;
     cp_async16(qs_u + (uint32_t)(r * ROW + ch * 8) * 2, qg + (long long)rr * pr.ldq + ch * 8, ok);
   }
-  for (int e = tid; e < first * 8; e += 128) {
+  for (int e = tid; e < first * 8; e += nthr) {
     const int key = e >> 3, ch = e & 7;
     const bool ok = key < pr.Lk;
     const int kk = ok ? key : 0;
@@ -101,7 +110,7 @@ __global__ void __launch_bounds__(128, 5) attn_fwd_bf16_kernel(const AttnParams 
     cp_async16(vs_u + (uint32_t)(key * ROW + ch * 8) * 2, vg + (long long)kk * pr.ldv + ch * 8, ok);
   }
   cp_async_commit();
-  for (int e = first * 8 + tid; e < LkP * 8; e += 128) {
+  for (int e = first * 8 + tid; e < LkP * 8; e += nthr) {
     const int key = e >> 3, ch = e & 7;
     const bool ok = key < pr.Lk;
     const int kk = ok ? key : 0;
@@ -109,7 +118,7 @@ __global__ void __launch_bounds__(128, 5) attn_fwd_bf16_kernel(const AttnParams 
     cp_async16(vs_u + (uint32_t)(key * ROW + ch * 8) * 2, vg + (long long)kk * pr.ldv + ch * 8, ok);
   }
   cp_async_commit();
-  for (int key = tid; key < LkP; key += 128) {
+  for (int key = tid; key < LkP; key += nthr) {
     float m = 0.f;
     if (key >= pr.Lk) m = -INFINITY;
     else if (pr.key_mask && !pr.key_mask[(long long)b * pr.Lk + key]) m = (p.mask_mode == VI_MASK_NEG_INF) ? -INFINITY : -10000.0f;
@@ -196,8 +205,8 @@ __global__ void __launch_bounds__(128, 5) attn_fwd_bf16_kernel(const AttnParams 
     cm1 = fmaxf(cm1, __shfl_xor_sync(0xffffffffu, cm1, 2));
     const float mn0 = fmaxf(m0, cm0), mn1 = fmaxf(m1, cm1);
     const float mu0 = (mn0 == -INFINITY) ? 0.f : mn0, mu1 = (mn1 == -INFINITY) ? 0.f : mn1;
-    const float sc0 = (m0 == -INFINITY) ? 0.f : __expf(m0 - mu0);
-    const float sc1 = (m1 == -INFINITY) ? 0.f : __expf(m1 - mu1);
+    const float sc0 = (m0 == -INFINITY) ? 0.f : fast_exp(m0 - mu0);
+    const float sc1 = (m1 == -INFINITY) ? 0.f : fast_exp(m1 - mu1);
     m0 = mn0; m1 = mn1;
     l0 *= sc0; l1 *= sc1;
 #pragma unroll
@@ -205,8 +214,8 @@ __global__ void __launch_bounds__(128, 5) attn_fwd_bf16_kernel(const AttnParams 
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
       if (nt < 2 * npairs) {
-        s[nt][0] = __expf(s[nt][0] - mu0); s[nt][1] = __expf(s[nt][1] - mu0);
-        s[nt][2] = __expf(s[nt][2] - mu1); s[nt][3] = __expf(s[nt][3] - mu1);
+        s[nt][0] = fast_exp(s[nt][0] - mu0); s[nt][1] = fast_exp(s[nt][1] - mu0);
+        s[nt][2] = fast_exp(s[nt][2] - mu1); s[nt][3] = fast_exp(s[nt][3] - mu1);
         l0 += s[nt][0] + s[nt][1];
         l1 += s[nt][2] + s[nt][3];
         if (drop) {      // dropout on the probabilities (vilmodel.py:128,347): the denominator keeps the undropped sum
@@ -375,9 +384,12 @@ extern "C" int vi_attn_fwd_multi(const vi_attn_problem* problems, int n_problems
     max_lkp = p.pr[i].LkP > max_lkp ? p.pr[i].LkP : max_lkp;
   }
   if (dtype == VI_DT_BF16) {
-    const size_t smem = (size_t)max_lkp * ROW * 2 * 2 + 64 * ROW * 2 + (size_t)max_lkp * 4;
-    dim3 grid((max_lq + 63) / 64, H, total_b);
-    VI_CUDA(vi_launch(attn_fwd_bf16_kernel, dim3(grid), dim3(128), (size_t)(smem), st, p));
+    const int q_tiles = (max_lq + 15) / 16;
+    const int nwarp = q_tiles < 4 ? q_tiles : 4;
+    const int qrows = nwarp * 16;
+    const size_t smem = (size_t)max_lkp * ROW * 2 * 2 + (size_t)qrows * ROW * 2 + (size_t)max_lkp * 4;
+    dim3 grid((max_lq + qrows - 1) / qrows, H, total_b);
+    VI_CUDA(vi_launch(attn_fwd_bf16_kernel, dim3(grid), dim3(nwarp * 32), (size_t)(smem), st, p));
     VI_LAUNCH_CHECK();
   } else {
     for (int i = 0; i < n_problems; ++i) {

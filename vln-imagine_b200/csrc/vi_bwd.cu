@@ -687,6 +687,58 @@ __global__ void __launch_bounds__(128) cosine_loss_bwd_kernel(const float* proj,
   }
 }
 
+// InfoNCE alignment loss adjoint (vilmodel.py:657-687):  loss = mean_r [ logsumexp_{c valid} s_rc - s_r0 ],
+// s_rc = cos(p_r, t_c) / tau with t_0 = the row's own noun-phrase mean and t_c (c >= 1) the noun-phrase means of OTHER
+// episodes.  With w_rc = softmax_c(s_rc) - [c == 0]:
+//     dp_r = (dloss / (R tau)) * sum_c w_rc ( t_c / (|p_r| |t_c|) - cos_rc p_r / |p_r|^2 )
+// `sims` is what the forward pass left in its scratch (s_rc for every column, valid or not).  One warp per row.
+__global__ void __launch_bounds__(128) infonce_loss_bwd_kernel(const float* proj, const float* tgt, const float* negs,
+                                                               const int32_t* row_ep, const int32_t* neg_ep, float inv_t,
+                                                               const float* sims, const float* dloss,
+                                                               float* __restrict__ dproj, int R, int n_negs) {
+  pdl_enter();
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (row >= R) return;
+  const int cols = n_negs + 1;
+  const float* s = sims + row * cols;
+  const int ep = row_ep[row];
+  float mx = s[0];
+  for (int c = 1 + lane; c < cols; c += 32)
+    if (neg_ep[c - 1] != ep) mx = fmaxf(mx, s[c]);
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int c = 1 + lane; c < cols; c += 32)
+    if (neg_ep[c - 1] != ep) sum += expf(s[c] - mx);
+  sum = warp_sum(sum) + expf(s[0] - mx);
+  const float inv_sum = 1.0f / sum;
+  float a[24], acc[24];
+  float aa = 0.f;
+#pragma unroll
+  for (int i = 0; i < 24; ++i) { a[i] = proj[row * D + lane + 32 * i]; aa = fmaf(a[i], a[i], aa); acc[i] = 0.f; }
+  aa = warp_sum(aa);
+  const float na = fmaxf(sqrtf(aa), 1e-8f);
+  float wcos = 0.f;                                    // sum_c w_rc cos_rc
+  for (int c = 0; c < cols; ++c) {
+    if (c > 0 && neg_ep[c - 1] == ep) continue;        // warp-uniform
+    const float w = expf(s[c] - mx) * inv_sum - (c == 0 ? 1.f : 0.f);
+    const float* t = c == 0 ? tgt + row * D : negs + (long long)(c - 1) * D;
+    float tv[24];
+    float bb = 0.f;
+#pragma unroll
+    for (int i = 0; i < 24; ++i) { tv[i] = t[lane + 32 * i]; bb = fmaf(tv[i], tv[i], bb); }
+    bb = warp_sum(bb);
+    const float k = w / fmaxf(sqrtf(bb), 1e-8f);
+#pragma unroll
+    for (int i = 0; i < 24; ++i) acc[i] = fmaf(k, tv[i], acc[i]);
+    wcos = fmaf(w, s[c], wcos);                        // s = cos / tau
+  }
+  wcos /= inv_t;
+  const float scale = dloss[0] * inv_t / (float)R;
+#pragma unroll
+  for (int i = 0; i < 24; ++i) dproj[row * D + lane + 32 * i] = scale * (acc[i] / na - wcos * a[i] / (na * na));
+}
+
 inline bool make_groups(RowGroups& g, int n_groups, const int32_t* ends) {
   if (n_groups < 1 || n_groups > 4 || (n_groups > 1 && !ends)) return false;
   g.n = n_groups;
@@ -927,5 +979,17 @@ extern "C" int vi_cosine_loss_bwd(const float* proj, const float* tgt, const flo
   if (R <= 0) return VI_OK;
   VI_CUDA(vi_launch(cosine_loss_bwd_kernel, dim3((unsigned)((R + 3) / 4)), dim3(128), 0, ST(stream), proj, tgt, dloss, dproj, dtgt,
                     (long long)R));
+  return VI_OK;
+}
+
+extern "C" int vi_infonce_loss_bwd(const float* proj, const float* tgt, const float* negs, const int32_t* row_episode,
+                                   const int32_t* neg_episode, float temperature, const float* sims, const float* dloss,
+                                   float* dproj, int R, int n_negs, vi_stream_t stream) {
+  VI_CHECK_ARG(proj && tgt && row_episode && sims && dloss && dproj, "vi_infonce_loss_bwd: null operand");
+  VI_CHECK_ARG(n_negs == 0 || (negs && neg_episode), "vi_infonce_loss_bwd: negatives missing");
+  VI_CHECK_ARG(temperature > 0.f, "vi_infonce_loss_bwd: temperature must be positive");
+  if (R <= 0) return VI_OK;
+  VI_CUDA(vi_launch(infonce_loss_bwd_kernel, dim3((unsigned)((R + 3) / 4)), dim3(128), 0, ST(stream), proj, tgt, negs, row_episode,
+                    neg_episode, 1.0f / temperature, sims, dloss, dproj, R, n_negs));
   return VI_OK;
 }

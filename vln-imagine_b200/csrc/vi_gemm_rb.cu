@@ -437,7 +437,30 @@ extern "C" int vi_gemm_ln_bf16(const void* x, int64_t ldx, const void* w, const 
     VI_CUDA(cudaFuncSetAttribute(gemm_rowblock_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr_set = true;
   }
-  const int max_clusters = vi_num_sms() / NCL;
+  // Clusters of 4 cannot use every SM (GPCs hold 16 / 18 / 20 SMs: 33 co-resident clusters on a B200, not 148 / 4 = 37).
+  // The grid is clamped to what is co-resident so that the row blocks beyond it are walked by the persistent loop
+  // (main loop of block i + 1 under the epilogue of block i) instead of waiting for a whole cluster to retire.
+  static int max_clusters = 0;
+  if (max_clusters == 0) {
+    cudaLaunchConfig_t q;
+    memset(&q, 0, sizeof(q));
+    q.gridDim = dim3((unsigned)(vi_num_sms() / NCL * NCL));
+    q.blockDim = dim3(NUM_THREADS);
+    q.dynamicSmemBytes = SMEM_BYTES;
+    cudaLaunchAttribute qa[1];
+    qa[0].id = cudaLaunchAttributeClusterDimension;
+    qa[0].val.clusterDim.x = NCL; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+    q.attrs = qa;
+    q.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, gemm_rowblock_ln_kernel, &q) != cudaSuccess || n <= 0) {
+      cudaGetLastError();
+      n = vi_num_sms() / NCL;
+    }
+    if (const char* e = getenv("VI_RB_CLUSTERS")) { const int v = atoi(e); if (v > 0) n = v; }
+    max_clusters = n;
+    if (getenv("VI_RB_VERBOSE")) fprintf(stderr, "vi_gemm_ln_bf16: %d co-resident clusters of %d CTAs\n", n, NCL);
+  }
   const int n_clusters = p.num_m_tiles < max_clusters ? p.num_m_tiles : max_clusters;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));

@@ -161,7 +161,7 @@ def _align_forward_train(model, txt, img, rows, pk, lowp, shape):
     if txt.requires_grad:
         raise NotImplementedError('training the text encoder through the alignment loss '
                                   '(fix_lang_inside_cosine_model=False) is not on the released path')
-    if cfg.aux_loss_type != 'cosine':
+    if cfg.aux_loss_type not in ('cosine', 'contrastive-InfoNCE'):
         raise NotImplementedError('backward of aux_loss_type %r' % cfg.aux_loss_type)
     B, I = shape
     x = ag.GatherSlotsFn.apply(img, rows.unit, rows.slot, rows.R, lowp)
@@ -173,7 +173,14 @@ def _align_forward_train(model, txt, img, rows, pk, lowp, shape):
         if not last:
             x = ag.ActFn.apply(x, ops.EPI_RELU)
     tgt, _ = ops.gather_mean(txt, rows.tok_off, rows.tok_rows, rows.R, want16=False)
-    loss = ag.CosineLossFn.apply(x, tgt, rows.R)
+    if cfg.aux_loss_type == 'cosine':
+        loss = ag.CosineLossFn.apply(x, tgt, rows.R)
+    else:                                                     # AlignWithContrastiveLossWithNegativeSamples (:689-779)
+        negs = None
+        if rows.n_negs:
+            negs, _ = ops.gather_mean(txt, rows.np_off, rows.np_rows, rows.n_negs, want16=False)
+        loss = ag.InfoNCELossFn.apply(x, tgt, negs, rows.ep, rows.np_ep if rows.n_negs else None,
+                                      float(cfg.infonce_temperature), rows.R, rows.n_negs)
     out = ag.ScatterSlotsFn.apply(img, x, rows.slot, rows.unit)
     return loss, out.view(B, I, HIDDEN)
 

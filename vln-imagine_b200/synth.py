@@ -281,3 +281,62 @@ def to_torch(ep: dict, device='cpu') -> dict:
         else:
             out[k] = v
     return out
+
+
+# ----------------------------------------------------------------------------------------------
+# a synthetic navigation world for the per-step graph glue
+# ----------------------------------------------------------------------------------------------
+
+def nav_world(seed: int = 7, n_vp: int = 24, batch: int = 4, steps: int = 6, n_views: int = 36, hidden: int = 768,
+              degree: int = 3) -> List[dict]:
+    """A rollout's worth of observations over a random viewpoint graph, in the shape the reference agent sees them
+    (VLN-DUET/map_nav_src/r2r/env.py observations: 'viewpoint', 'position', 'heading', 'elevation',
+    'candidate': [{'viewpointId', 'position'}]).  Returns one dict per step:
+
+        obs          list[batch] of observation dicts (the state BEFORE acting at this step)
+        ended        bool [batch]    episodes that stopped at an earlier step (agent.py:452, 609)
+        pano_embeds  fp32 [batch, n_views, hidden]   stand-in for the panorama encoder's output of this step
+        view_lens    int64 [batch]; nav_types int64 [batch, n_views] (1 for the candidate views, which come first)
+    """
+    g = _rng(seed, 'nav_world')
+    pos = np.concatenate([g.uniform(-12, 12, (n_vp, 2)), g.uniform(-1.5, 1.5, (n_vp, 1))], 1)
+    names = ['vp%03d' % i for i in range(n_vp)]
+    d = np.linalg.norm(pos[:, None] - pos[None], axis=-1)
+    nbr = [set() for _ in range(n_vp)]
+    for i in range(n_vp):                                     # symmetric k-nearest-neighbour connectivity
+        for j in np.argsort(d[i])[1:degree + 1]:
+            nbr[i].add(int(j)); nbr[int(j)].add(i)
+    for i in range(n_vp - 1):                                 # a spanning chain keeps the graph connected
+        nbr[i].add(i + 1); nbr[i + 1].add(i)
+    cur = [int(x) for x in g.integers(0, n_vp, batch)]
+    seen = [{c} for c in cur]
+    stop_at = [int(x) for x in g.integers(max(2, steps // 2), steps + 1, batch)]
+    stop_at[0] = steps                                        # at least one episode runs the whole horizon
+    out = []
+    ended = np.zeros(batch, bool)
+    for t in range(steps):
+        obs = []
+        nav_types = np.zeros((batch, n_views), np.int64)
+        for b in range(batch):
+            cands = sorted(nbr[cur[b]])
+            order = g.permutation(len(cands))
+            cands = [cands[i] for i in order]
+            obs.append({'viewpoint': names[cur[b]], 'position': tuple(float(x) for x in pos[cur[b]]),
+                        'heading': float(g.uniform(0, 2 * np.pi)), 'elevation': float(g.uniform(-0.5, 0.5)),
+                        'candidate': [{'viewpointId': names[c], 'position': tuple(float(x) for x in pos[c])} for c in cands]})
+            nav_types[b, :len(cands)] = 1
+        out.append({'obs': obs, 'ended': ended.copy(),
+                    'pano_embeds': g.standard_normal((batch, n_views, hidden)).astype(np.float32),
+                    'view_lens': np.full((batch,), n_views, np.int64), 'nav_types': nav_types})
+        for b in range(batch):                                # act: prefer an unseen neighbour, stop when scheduled
+            if ended[b]:
+                continue
+            if t + 1 >= stop_at[b]:
+                ended[b] = True
+                continue
+            cands = sorted(nbr[cur[b]])
+            fresh = [c for c in cands if c not in seen[b]]
+            pool = fresh if fresh else cands
+            cur[b] = pool[int(g.integers(0, len(pool)))]
+            seen[b].add(cur[b])
+    return out
