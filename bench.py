@@ -28,6 +28,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 METRIC = 'nav-step decisions/sec'
@@ -216,6 +217,84 @@ def device_inputs(model_kind, model, ep, dev):
 # ----------------------------------------------------------------------------------------------
 # CPU legs (the oracle is the checker / reported baseline, never the product)
 # ----------------------------------------------------------------------------------------------
+def ncu_gemm_traffic(workload_name):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the tcgen05 GEMM, averaged over the GEMM launches of one
+    step, from the committed `ncu --set full` capture of this workload (profiles/*_<workload>_step_full.csv, written by
+    tools/profile.sh + tools/ncu_summary.py).  None when no capture of the workload is committed."""
+    import csv
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, 'profiles', '*_%s_step_full.csv' % workload_name)))
+    if not files:
+        return None, None
+    tot, n = 0.0, 0
+    with open(files[-1]) as f:
+        for row in csv.DictReader(f):
+            if row['kernel'].startswith('gemm_bf16_tc_kernel'):
+                tot += float(row['dram_read_B']) + float(row['dram_write_B'])
+                n += 1
+    if n == 0:
+        return None, None
+    return tot / n, 'bytes per launch, mean over %d GEMM launches of one step in profiles/%s' % (n, os.path.basename(files[-1]))
+
+
+def glue_leg(dev, batch, with_cpu):
+    """Per-step graph glue of a DUET rollout: DeviceGraphMaps (csrc/vi_graph.cu) through its host
+    API, host packing and the packed upload included, against the CPU oracle of the reference's GraphMap loops on the same
+    synthetic rollout.  Reported next to the metric, not part of it (the reference runs this in Python on the host)."""
+    import vln_imagine_b200.synth as synth
+    from vln_imagine_b200 import graph_map
+    world = synth.nav_world(seed=21, n_vp=80, batch=batch, steps=7, hidden=768, degree=4)
+
+    def rollout():
+        gm = graph_map.DeviceGraphMaps(world[0]['obs'], dev)
+        for t, st in enumerate(world):
+            obs, ended = st['obs'], st['ended']
+            gm.set_step_ids(obs, t, ended)
+            pin = {'cand_vpids': [[c['viewpointId'] for c in ob['candidate']] for ob in obs], 'view_lens': st['view_lens_d'],
+                   'nav_types': st['nav_types_d']}
+            out = gm.nav_inputs(obs, st['pano_d'], st['masks_d'], pin, ended)
+            if t + 1 < len(world):
+                gm.update_graph(world[t + 1]['obs'], ended)
+        return out
+    for st in world:
+        st['pano_d'] = torch.from_numpy(st['pano_embeds']).to(dev)
+        st['masks_d'] = torch.ones(st['pano_d'].shape[:2], dtype=torch.bool, device=dev)
+        st['view_lens_d'] = torch.from_numpy(st['view_lens']).to(dev)
+        st['nav_types_d'] = torch.from_numpy(st['nav_types']).to(dev)
+    rollout()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    reps = 5
+    for _ in range(reps):
+        rollout()
+    torch.cuda.synchronize()
+    ms = (time.perf_counter() - t0) / reps / len(world) * 1e3
+    res = {'what': 'graph update + node embeddings + position features + pair distances for %d episodes, ~%d known nodes, '
+                   'wall time per step incl. host id interning and the packed upload' % (batch, 30),
+           'ms_per_step': ms, 'launches_per_step': 3}
+    if with_cpu:
+        from oracle import graph_oracle as GO
+        t0 = time.perf_counter()
+        obs0 = world[0]['obs']
+        states = [GO.GraphState(ob['viewpoint'], 768) for ob in obs0]
+        for b, ob in enumerate(obs0):
+            states[b].update_graph(ob['viewpoint'], ob['position'], [(c['viewpointId'], c['position']) for c in ob['candidate']])
+        for t, st in enumerate(world):
+            obs, ended = st['obs'], st['ended']
+            cur = [s_.index[ob['viewpoint']] for s_, ob in zip(states, obs)]
+            cands = [[s_.index[c['viewpointId']] for c in ob['candidate']] for s_, ob in zip(states, obs)]
+            GO.update_node_embeds(states, cur, cands, st['pano_embeds'], np.ones(st['pano_embeds'].shape[:2], bool), ended)
+            heads, elevs = [ob['heading'] for ob in obs], [ob['elevation'] for ob in obs]
+            GO.nav_gmap_variable(states, cur, heads, elevs)
+            GO.nav_vp_variable(states, cur, heads, elevs, st['pano_embeds'], cands, st['view_lens'], st['nav_types'])
+            if t + 1 < len(world):
+                for b, ob in enumerate(world[t + 1]['obs']):
+                    if not ended[b]:
+                        states[b].update_graph(ob['viewpoint'], ob['position'], [(c['viewpointId'], c['position']) for c in ob['candidate']])
+        res['cpu_oracle_ms_per_step'] = (time.perf_counter() - t0) / len(world) * 1e3
+    return res
+
+
 def cpu_reference(model_kind, shape, budget_s=15.0, batch=8):
     """The reference algorithm (CPU oracle port, fp32, all host threads) on a bounded sample of the same
     workload: `batch` episodes of the same shape, repeated for about budget_s seconds."""
@@ -663,6 +742,7 @@ def main():
         pass
     peak_tf = peaks.get('bf16_tflops_sustained', 1400.0)
     peak_src = 'MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)' if peaks else 'fallback 1.4 PFLOP/s sustained'
+    traffic, traffic_src = ncu_gemm_traffic(args.workload)
     fl_dec = flops_per_decision(model_kind, shape)
     step_tf = fl_dec * B / (ms / K * 1e-3) / 1e12
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
@@ -688,7 +768,7 @@ def main():
                        'logits are read back and synchronised every step'},
         'gpu_launches': total_launches,
         'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s',
-                     'frac': achieved / peak_tf, 'traffic': None, 'peak_source': peak_src,
+                     'frac': achieved / peak_tf, 'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': peak_src,
                      'kernel': 'gemm_bf16_tc_kernel (tcgen05): %.1f launches/step, %.1f GFLOP/step EXECUTED, %.3f ms/step of GEMM '
                                'time (CUDA events around each launch of %d queued eager steps = one episode)'
                                % (len(trace) / TRACE_STEPS, gemm_flops / TRACE_STEPS / 1e9, gemm_ms / TRACE_STEPS, TRACE_STEPS)},
@@ -701,6 +781,8 @@ def main():
     if world == 1 and not args.no_cpu_baseline:
         cb, _ = cpu_reference(model_kind, shape)
         line['cpu_baseline'] = cb
+    if world == 1 and model_kind == 'duet':
+        line['step']['graph_glue'] = glue_leg(dev, B, with_cpu=not args.no_cpu_baseline)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

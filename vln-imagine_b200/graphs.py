@@ -29,6 +29,7 @@ class GraphedCall:
         self.capture_after = capture_after
         self.entries = collections.OrderedDict()
         self.token = None
+        self._copy_streams = {}
 
     def clear(self):
         self.entries.clear()
@@ -71,10 +72,39 @@ class GraphedCall:
                 static_out = self.fn(static_in)
             ent.update(graph=graph, static_in=static_in, static_out=static_out)
         static_in = ent['static_in']
+        main = torch.cuda.current_stream(device)
+        host_items = [(k, v) for k, v in inputs.items() if not v.is_cuda]
+        if host_items:
+            # Host inputs go through a copy stream: they depend only on this graph's PREVIOUS replay having consumed the
+            # static buffers, so the navigation call's uploads overlap the panorama graph still running on the main stream.
+            cs = self._copy_stream(device)
+            if ent.get('done') is not None:
+                cs.wait_event(ent['done'])
+            else:
+                cs.wait_stream(main)
+            with torch.cuda.stream(cs):
+                for k, v in host_items:
+                    static_in[k].copy_(v, non_blocking=True)
+            ev = ent.get('uploaded')
+            if ev is None:
+                ev = ent['uploaded'] = torch.cuda.Event()
+            ev.record(cs)
+            main.wait_event(ev)
         for k, v in inputs.items():
-            static_in[k].copy_(v, non_blocking=True)
+            if v.is_cuda:
+                static_in[k].copy_(v, non_blocking=True)
         ent['graph'].replay()
+        if host_items:
+            if ent.get('done') is None:
+                ent['done'] = torch.cuda.Event()
+            ent['done'].record(main)
         return {k: (v.clone() if torch.is_tensor(v) else v) for k, v in ent['static_out'].items()}
+
+    def _copy_stream(self, device):
+        cs = self._copy_streams.get(device)
+        if cs is None:
+            cs = self._copy_streams[device] = torch.cuda.Stream(device)
+        return cs
 
 
 def weights_token(module: torch.nn.Module, cache: dict):
