@@ -12,6 +12,8 @@ accumulation, fp32 residual stream, LayerNorm, softmax and heads) or ``'fp32'`` 
 from __future__ import annotations
 
 import collections
+import itertools
+import struct
 import os
 from typing import List, Optional
 
@@ -32,8 +34,10 @@ def _f32c(t: torch.Tensor) -> torch.Tensor:
 
 class _IdTable:
     """Viewpoint-id strings -> int32 ids.  Ids only need to agree between gmap_vpids and vp_cand_vpids of
-    the same call; one growing table per model is the simplest way to guarantee that.  The hot loop is one
-    C-level ``map`` over the flattened keys (the agent hands ~1400 strings per step at batch 64)."""
+    the same call; one growing table per model is the simplest way to guarantee that.  The agent hands ~1700
+    strings per step at batch 64, so the hot loop is C-level end to end: the table maps a key to the 4 bytes of
+    its id, one ``map`` + ``bytes.join`` over the chained rows builds the int32 buffer (converting a Python list
+    of ints to numpy costs more than the dictionary look-ups)."""
 
     def __init__(self):
         self.ids = {}
@@ -41,15 +45,17 @@ class _IdTable:
     def encode(self, lists, width: int, pad: int) -> np.ndarray:
         rows = [row[:width] if len(row) > width else row for row in lists]
         lens = np.fromiter(map(len, rows), dtype=np.int64, count=len(rows))
-        flat = [k for row in rows for k in row]
         ids = self.ids
         try:
-            vals = list(map(ids.__getitem__, flat))
+            buf = b''.join(map(ids.__getitem__, itertools.chain.from_iterable(rows)))
         except KeyError:
-            vals = [ids.setdefault(k, len(ids)) for k in flat]
+            for k in itertools.chain.from_iterable(rows):
+                if k not in ids:
+                    ids[k] = struct.pack('<i', len(ids))
+            buf = b''.join(map(ids.__getitem__, itertools.chain.from_iterable(rows)))
         out = np.full((len(rows), width), pad, np.int32)
-        if flat:
-            out[np.arange(width)[None, :] < lens[:, None]] = np.asarray(vals, np.int32)
+        if buf:
+            out[np.arange(width)[None, :] < lens[:, None]] = np.frombuffer(buf, dtype='<i4')
         return out
 
 
@@ -349,9 +355,10 @@ class GlocalTextPathNavCMT(nn.Module):
     def forward_navigation_per_step(self, txt_embeds, txt_masks, gmap_img_embeds, gmap_step_ids, gmap_pos_fts,
                                     gmap_masks, gmap_pair_dists, gmap_visited_masks, gmap_vpids,
                                     vp_img_embeds, vp_pos_fts, vp_masks, vp_nav_masks, vp_obj_masks, vp_cand_vpids,
-                                    imagine_embeds=None, imagine_masks=None, ctx_kv=None):
+                                    imagine_embeds=None, imagine_masks=None, ctx_kv=None, defer_fuse=False):
         """'navigation'.  :1133-1235.  ``ctx_kv`` (internal): context projections already looked up by the caller
-        (VLNBert's graph path); txt_embeds / imagine_embeds are then not read."""
+        (VLNBert's graph path); txt_embeds / imagine_embeds are then not read.  ``defer_fuse`` (internal): stop before the
+        global / local fusion (:1198-1217) and return its operands under '_fuse' for ``fuse_logits``."""
         if vp_obj_masks is not None:
             raise NotImplementedError('object grounding head is outside the R2R hot path')
         self._guard(gmap_img_embeds)
@@ -419,11 +426,26 @@ class GlocalTextPathNavCMT(nn.Module):
                           c16[:, HIDDEN:] if c16 is not None else None, 2 * HIDDEN, HIDDEN)
             fuse_raw = blocks.cls_head(cat, pk['fuse'], lowp)
         raw = blocks.cls_head(x.operand(lowp), pk['sap'], lowp, ends)
+        if defer_fuse:
+            return {'gmap_embeds': gmap_out, 'vp_embeds': vp_out, '_g_raw': raw[r_g:], '_l_raw': raw[r_l:], '_fuse_raw': fuse_raw,
+                    '_gmap_masks': blocks.mask_u8(gmap_masks), '_visited': blocks.mask_u8(gmap_visited_masks),
+                    '_nav_masks': blocks.mask_u8(vp_nav_masks)}
         gmap_ids, cand_ids = self.intern_vpids(gmap_vpids, vp_cand_vpids, G, P, dev)
         gl, ll, fl = ops.duet_fuse_logits(raw[r_g:], raw[r_l:], fuse_raw, blocks.mask_u8(gmap_masks),
                                           blocks.mask_u8(gmap_visited_masks), blocks.mask_u8(vp_nav_masks),
                                           gmap_ids, cand_ids, B, G, P)
         return {'gmap_embeds': gmap_out, 'vp_embeds': vp_out, 'global_logits': gl, 'local_logits': ll,
+                'fused_logits': fl, 'obj_logits': None}
+
+    def fuse_logits(self, pre: dict, gmap_vpids, vp_cand_vpids, G: int, P: int) -> dict:
+        """Second half of a ``defer_fuse`` navigation call: intern the viewpoint ids (host work that then overlaps the
+        encoder kernels already queued), upload them and launch the fusion kernel (:1198-1217)."""
+        dev = pre['_g_raw'].device
+        gmap_ids, cand_ids = self.intern_vpids(gmap_vpids, vp_cand_vpids, G, P, dev)
+        B = pre['_gmap_masks'].shape[0]
+        gl, ll, fl = ops.duet_fuse_logits(pre['_g_raw'], pre['_l_raw'], pre['_fuse_raw'], pre['_gmap_masks'], pre['_visited'],
+                                          pre['_nav_masks'], gmap_ids, cand_ids, B, G, P)
+        return {'gmap_embeds': pre['gmap_embeds'], 'vp_embeds': pre['vp_embeds'], 'global_logits': gl, 'local_logits': ll,
                 'fused_logits': fl, 'obj_logits': None}
 
     # -- per-episode context cache ----------------------------------------------------------------------------
@@ -649,8 +671,8 @@ class VLNBert(nn.Module):
         kv = [t['ctx_kv%d' % i] for i in range(len(self.vln_bert.global_encoder.encoder.x_layers))]
         return self.vln_bert.forward_navigation_per_step(
             None, t['txt_masks'], t['gmap_img_embeds'], t['gmap_step_ids'], t['gmap_pos_fts'], t['gmap_masks'],
-            t['gmap_pair_dists'], t['gmap_visited_masks'], t['gmap_ids'], t['vp_img_embeds'], t['vp_pos_fts'], t['vp_masks'],
-            t['vp_nav_masks'], None, t['cand_ids'], imagine_embeds=None, imagine_masks=t.get('imagine_masks'), ctx_kv=kv)
+            t['gmap_pair_dists'], t['gmap_visited_masks'], None, t['vp_img_embeds'], t['vp_pos_fts'], t['vp_masks'],
+            t['vp_nav_masks'], None, None, imagine_embeds=None, imagine_masks=t.get('imagine_masks'), ctx_kv=kv, defer_fuse=True)
 
     def _graphable(self):
         return self.use_cuda_graphs and not self.training and not torch.is_grad_enabled()
@@ -679,13 +701,16 @@ class VLNBert(nn.Module):
                 tok = graphs.weights_token(m, self._wt_cache)
                 t = {k: batch[k] for k in self.NAV_TENSORS if batch[k] is not None}
                 G, P = batch['gmap_img_embeds'].shape[1], batch['vp_img_embeds'].shape[1]
-                t['gmap_ids'], t['cand_ids'] = m.intern_vpids(batch['gmap_vpids'], batch['vp_cand_vpids'], G, P, None)
                 cfg = m.config
                 # context projections: looked up (or recomputed, eagerly) outside the graph, which only reads them
                 kv = m.context_kv(batch['txt_embeds'], batch['imagine_embeds'])
-                return self._g_nav(t, dev, extra_key=(m.precision, cfg.imagine_enc_pano, cfg.concat_imagine_with if
-                                                      cfg.imagine_enc_pano else None), weights_token=tok,
-                                   borrowed={'ctx_kv%d' % i: x for i, x in enumerate(kv)})
+                # The graph stops before the global / local fusion: the ~1700 viewpoint-id strings of a batch are
+                # interned on the host AFTER the encoder has been queued (the GPU would otherwise idle for that long),
+                # then the one fusion kernel is launched eagerly on the graph's outputs.
+                pre = self._g_nav(t, dev, extra_key=(m.precision, cfg.imagine_enc_pano, cfg.concat_imagine_with if
+                                                     cfg.imagine_enc_pano else None), weights_token=tok,
+                                  borrowed={'ctx_kv%d' % i: x for i, x in enumerate(kv)}, no_clone_prefix='_')
+                return m.fuse_logits(pre, batch['gmap_vpids'], batch['vp_cand_vpids'], G, P)
             return m(mode, batch)
         if mode in ('language', 'imagine', 'align_with_contrastive_loss'):
             return m(mode, batch)

@@ -35,10 +35,12 @@ class GraphedCall:
         self.entries.clear()
 
     def __call__(self, inputs: Dict[str, torch.Tensor], device: torch.device, extra_key=(), weights_token=None,
-                 borrowed: Dict[str, torch.Tensor] = None):
+                 borrowed: Dict[str, torch.Tensor] = None, no_clone_prefix: str = None):
         """``borrowed``: device tensors the graph reads IN PLACE (no copy into static buffers): persistent buffers
         owned by the caller, e.g. the per-episode context projections.  Their addresses are part of the signature
-        and the entry keeps them alive."""
+        and the entry keeps them alive.  Outputs whose key starts with ``no_clone_prefix`` are handed out as the graph's
+        own static buffers (valid until the next replay of the same signature): for intermediates the caller consumes at
+        once on the same stream."""
         if weights_token != self.token:
             self.clear()
             self.token = weights_token
@@ -98,7 +100,8 @@ class GraphedCall:
             if ent.get('done') is None:
                 ent['done'] = torch.cuda.Event()
             ent['done'].record(main)
-        return {k: (v.clone() if torch.is_tensor(v) else v) for k, v in ent['static_out'].items()}
+        return {k: (v.clone() if torch.is_tensor(v) and not (no_clone_prefix and k.startswith(no_clone_prefix)) else v)
+                for k, v in ent['static_out'].items()}
 
     def _copy_stream(self, device):
         cs = self._copy_streams.get(device)
