@@ -143,3 +143,48 @@ def test_device_graph_maps_match_oracle_hidden768(lib_built, seed, n_vp, batch, 
     n = len(gm.names[0])
     d = gm.dis[0, :n, :n].cpu().numpy()
     assert np.array_equal(d, d.T) and (d[~np.eye(n, dtype=bool)] > 0).all()
+
+
+@pytest.mark.gpu
+def test_rollout_glue_feeds_the_navigation_call(lib_built):
+    """The dict DeviceGraphMaps.nav_inputs returns goes straight into model('navigation', ...) - device tensors plus the
+    pre-interned viewpoint ids - and must score actions exactly like the inputs the reference agent would have collated
+    on the host (oracle arrays, lists of id strings interned by the model)."""
+    import dataclasses
+    from parity_utils import manifest, max_rel
+    duet = importlib.import_module('vln_imagine_b200.duet')
+    config = importlib.import_module('vln_imagine_b200.config')
+    graph_map = importlib.import_module('vln_imagine_b200.graph_map')
+    B = 6
+    world = synth.nav_world(seed=5, n_vp=30, batch=B, steps=4, hidden=768)
+    model = duet.VLNBert(config.default_duet_args()).cuda().eval()
+    model.vln_bert.load_state_dict(synth.synth_state_dict(manifest('duet'), seed=0, gasa_stress=True))
+    model.vln_bert.precision = 'fp32'      # the two input sets differ by ~1e-6 (sin / cos, mean order): fp32 mode keeps it visible
+    ep = synth.to_torch(synth.duet_episode(dataclasses.replace(synth.TINY, batch=B), 3))
+    dev = torch.device('cuda')
+    with torch.no_grad():
+        txt = model('language', {'txt_ids': ep['txt_ids'].to(dev), 'txt_masks': ep['txt_masks'].to(dev)})
+        img = model('imagine', {'imagine_feats': ep['imagine_feats'].to(dev), 'imagine_masks': None})
+        common = {'txt_embeds': txt, 'txt_masks': ep['txt_masks'].to(dev), 'imagine_embeds': img,
+                  'imagine_masks': ep['imagine_masks'].to(dev)}
+        gm = graph_map.DeviceGraphMaps(world[0]['obs'], dev)
+        for t, step, og, ov in _oracle_rollout(world, 768):
+            obs, ended = step['obs'], step['ended']
+            gm.set_step_ids(obs, t, ended)
+            pano = torch.from_numpy(step['pano_embeds']).to(dev)
+            pin = {'cand_vpids': [[c['viewpointId'] for c in ob['candidate']] for ob in obs],
+                   'view_lens': torch.from_numpy(step['view_lens']).to(dev), 'nav_types': torch.from_numpy(step['nav_types']).to(dev)}
+            a = gm.nav_inputs(obs, pano, torch.ones(pano.shape[:2], dtype=torch.bool, device=dev), pin, ended)
+            assert torch.is_tensor(a['gmap_vpids'].ids) and torch.is_tensor(a['vp_cand_vpids'].ids)
+            out_a = model('navigation', {**common, **{k: v for k, v in a.items() if k != 'no_vp_left'}})
+            host = {'gmap_vpids': og['names'], 'vp_cand_vpids': [[None] + c for c in pin['cand_vpids']]}
+            for k in ('gmap_img_embeds', 'gmap_step_ids', 'gmap_pos_fts', 'gmap_masks', 'gmap_pair_dists', 'gmap_visited_masks'):
+                host[k] = torch.from_numpy(og[k]).to(dev)
+            for k in ('vp_img_embeds', 'vp_pos_fts', 'vp_masks', 'vp_nav_masks'):
+                host[k] = torch.from_numpy(ov[k]).to(dev)
+            out_b = model('navigation', {**common, **host})
+            for k in ('global_logits', 'local_logits', 'fused_logits'):
+                assert max_rel(out_a[k], out_b[k]) < 1e-4, (t, k)
+            assert torch.equal(out_a['fused_logits'].argmax(-1), out_b['fused_logits'].argmax(-1)), t
+            if t + 1 < len(world):
+                gm.update_graph(world[t + 1]['obs'], ended)

@@ -585,6 +585,9 @@ class GlocalTextPathNavCMT(nn.Module):
         lists; they are used as they are."""
         if torch.is_tensor(gmap_vpids) and torch.is_tensor(vp_cand_vpids):
             return gmap_vpids, vp_cand_vpids
+        gi, ci = getattr(gmap_vpids, 'ids', None), getattr(vp_cand_vpids, 'ids', None)
+        if torch.is_tensor(gi) and torch.is_tensor(ci):       # rows built by graph_map.DeviceGraphMaps: already interned
+            return gi, ci
         gmap_ids = torch.from_numpy(self._ids.encode(gmap_vpids, G, -1))
         cand_ids = torch.from_numpy(self._ids.encode(vp_cand_vpids, P, -2))
         if len(self._ids.ids) > (1 << 20):

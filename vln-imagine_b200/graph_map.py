@@ -16,6 +16,7 @@ No CPU path: every array below is computed on the GPU; the oracle (oracle/graph_
 """
 from __future__ import annotations
 
+import collections.abc
 from typing import Dict, List, Optional, Sequence
 
 import numpy as np
@@ -64,6 +65,43 @@ def _pack(staging: _Staging, device, arrays: Dict[str, np.ndarray]) -> Dict[str,
     return out
 
 
+STOP_ID = 1 << 20      # id of the [stop] slot (None) in the interned-id tensors handed to the fusion kernel
+
+
+class VpidRows(collections.abc.Sequence):
+    """``gmap_vpids`` / ``vp_cand_vpids`` of a step as the agent reads them (a list of per-episode lists of viewpoint-id
+    strings, None for [stop]: r2r/agent.py:113-118, 205), materialised row by row on first access, plus the same rows as an
+    int32 device tensor (``ids``: node indices, [stop] = STOP_ID, padding = ``pad``) which the navigation call uses instead of
+    interning ~1700 strings per step (duet.GlocalTextPathNavCMT.intern_vpids)."""
+
+    def __init__(self, names, nodes: np.ndarray, lens: np.ndarray, ids: torch.Tensor, pad: int):
+        self._names, self._nodes, self._lens, self.ids, self.pad = names, nodes, lens, ids, pad
+        self._rows = [None] * len(lens)
+
+    def __len__(self):
+        return len(self._rows)
+
+    def __getitem__(self, b):
+        if isinstance(b, slice):
+            return [self[i] for i in range(*b.indices(len(self)))]
+        row = self._rows[b]
+        if row is None:
+            names = self._names[b]
+            row = self._rows[b] = [None] + [names[i] for i in self._nodes[b, 1:self._lens[b]]]
+        return row
+
+    def __eq__(self, other):
+        return list(self) == list(other)
+
+
+class _CandRows(list):
+    """vp_cand_vpids (agent.py:205) with the same rows as interned ids on the device (``ids``, padding -2)"""
+
+    def __init__(self, rows, ids: torch.Tensor):
+        super().__init__(rows)
+        self.ids = ids
+
+
 class DeviceGraphMaps:
     def __init__(self, obs: Sequence[dict], device, hidden: int = 768, max_nodes: int = MAX_NODES):
         self.device = torch.device(device)
@@ -83,8 +121,10 @@ class DeviceGraphMaps:
         self.start_vps = [ob['viewpoint'] for ob in obs]            # GraphMap.start_vp
         self.index: List[Dict[str, int]] = [dict() for _ in obs]    # viewpoint id -> node index (node_positions order)
         self.names: List[List[str]] = [[] for _ in obs]
-        self.visited: List[List[bool]] = [[] for _ in obs]          # FloydGraph._visited
-        self.step_ids: List[Dict[str, int]] = [dict() for _ in obs]  # GraphMap.node_step_ids
+        self.visited = np.zeros((B, N), bool)                       # FloydGraph._visited
+        self.step_ids = np.zeros((B, N), np.int64)                  # GraphMap.node_step_ids, by node index
+        self.n_nodes = np.zeros((B,), np.int32)
+        self._ar = np.arange(N)
         self._staging = _Staging()
         self.update_graph(obs)
 
@@ -97,7 +137,7 @@ class DeviceGraphMaps:
             if i >= self.N:
                 raise _lib.VlnImagineError('episode %d exceeds max_nodes=%d graph nodes' % (b, self.N))
             self.names[b].append(vp)
-            self.visited[b].append(False)
+            self.n_nodes[b] = i + 1
         return i
 
     def update_graph(self, obs: Sequence[dict], ended=None):
@@ -108,18 +148,20 @@ class DeviceGraphMaps:
         cur_pos = np.zeros((B, 3), np.float64)
         cand = np.full((B, C), -1, np.int32)
         cand_pos = np.zeros((B, C, 3), np.float64)
-        n_nodes = np.zeros((B,), np.int32)
+        node = self._node
         for b, ob in enumerate(obs):
             if ended is not None and ended[b]:
-                n_nodes[b] = len(self.names[b])
                 continue
-            k = cur[b] = self._node(b, ob['viewpoint'])
+            cur[b] = node(b, ob['viewpoint'])
             cur_pos[b] = ob['position']
-            for j, cc in enumerate(ob['candidate']):
-                cand[b, j] = self._node(b, cc['viewpointId'])
-                cand_pos[b, j] = cc['position']
-            self.visited[b][k] = True
-            n_nodes[b] = len(self.names[b])
+            cc = ob['candidate']
+            if cc:
+                n = len(cc)
+                cand[b, :n] = [node(b, c['viewpointId']) for c in cc]
+                cand_pos[b, :n] = [c['position'] for c in cc]
+        act = cur >= 0
+        self.visited[act, cur[act]] = True
+        n_nodes = self.n_nodes.copy()
         d = _pack(self._staging, self.device, dict(cur_pos=cur_pos, cand_pos=cand_pos, cur=cur, cand=cand, n_nodes=n_nodes))
         check(lib.vi_graph_update(self.pos.data_ptr(), self.dis.data_ptr(), self.point.data_ptr(), self.visited_dev.data_ptr(),
                                   B, self.N, d['cur'].data_ptr(), d['cur_pos'].data_ptr(), d['cand'].data_ptr(),
@@ -129,7 +171,7 @@ class DeviceGraphMaps:
     def set_step_ids(self, obs: Sequence[dict], t: int, ended):
         for b, ob in enumerate(obs):                                 # agent.py:461-464
             if not ended[b]:
-                self.step_ids[b][ob['viewpoint']] = t + 1
+                self.step_ids[b, self.index[b][ob['viewpoint']]] = t + 1
 
     # ------------------------------------------------------------------ agent.py:466-493
     def nav_inputs(self, obs: Sequence[dict], pano_embeds: torch.Tensor, pano_masks: torch.Tensor, pano_inputs: dict,
@@ -142,43 +184,42 @@ class DeviceGraphMaps:
                                        % (tuple(pano_embeds.shape), self.B, self.H))
         cand_vpids = pano_inputs['cand_vpids']
         C = max(1, max(len(c) for c in cand_vpids))
-        gmap_vpids, lens = [], np.zeros((B,), np.int32)
-        for b in range(B):
-            vis = self.visited[b]
-            names = self.names[b]
-            row = [None] + [v for v, f in zip(names, vis) if f] + [v for v, f in zip(names, vis) if not f]
-            gmap_vpids.append(row)
-            lens[b] = len(row)
+        N, ar = self.N, self._ar
+        # [stop] + visited + unvisited nodes, each group in node_positions order (agent.py:103-118): one stable sort
+        n = self.n_nodes
+        known = ar[None, :] < n[:, None]
+        order = np.argsort(np.where(known, np.where(self.visited, 0, 1), 2).astype(np.int8), axis=1, kind='stable')
+        lens = (n + 1).astype(np.int32)
         G = int(lens.max())
-        cur = np.full((B,), -1, np.int32)          # -1: no embedding update (ended)
-        cur_all = np.zeros((B,), np.int32)         # the position features are computed for ended episodes as well
-        cand = np.full((B, C), -1, np.int32)
-        start = np.zeros((B,), np.int32)
+        col = ar[None, :G]
+        live = col < lens[:, None]
         gnode = np.full((B, G), -1, np.int32)
+        gnode[:, 1:] = order[:, :G - 1]
+        gnode[~live] = -1
+        gnode[:, 0] = -1
         step_ids = np.zeros((B, G), np.int64)
-        vmask = np.zeros((B, G), bool)
-        heading = np.zeros((B,), np.float64)
-        elevation = np.zeros((B,), np.float64)
-        no_vp_left = []
-        for b, ob in enumerate(obs):
-            idx = self.index[b]
-            cur_all[b] = idx[ob['viewpoint']]
-            if not ended[b]:
-                cur[b] = cur_all[b]
-            for j, vp in enumerate(cand_vpids[b]):
-                cand[b, j] = idx[vp]
-            start[b] = idx[self.start_vps[b]]
-            row = gmap_vpids[b]
-            n = len(row)
-            gnode[b, 1:n] = [idx[v] for v in row[1:]]
-            sid = self.step_ids[b]
-            step_ids[b, 1:n] = [sid.get(v, 0) for v in row[1:]]
-            n_vis = sum(self.visited[b])
-            vmask[b, 1:1 + n_vis] = True
-            no_vp_left.append(n_vis == len(self.names[b]))
-            heading[b], elevation[b] = ob['heading'], ob['elevation']
+        step_ids[:, 1:] = np.take_along_axis(self.step_ids, order[:, :G - 1], 1)
+        step_ids[~live] = 0
+        n_vis = self.visited.sum(1)
+        vmask = (col >= 1) & (col < 1 + n_vis[:, None])
+        no_vp_left = (n_vis == n).tolist()
+        cur_all = np.fromiter((idx[ob['viewpoint']] for idx, ob in zip(self.index, obs)), np.int32, B)
+        cur = np.where(np.asarray(ended, bool), -1, cur_all).astype(np.int32)        # -1: no embedding update (ended)
+        start = np.fromiter((idx[s] for idx, s in zip(self.index, self.start_vps)), np.int32, B)
+        heading = np.fromiter((ob['heading'] for ob in obs), np.float64, B)
+        elevation = np.fromiter((ob['elevation'] for ob in obs), np.float64, B)
+        cand = np.full((B, C), -1, np.int32)
+        for b, vps in enumerate(cand_vpids):
+            if vps:
+                cand[b, :len(vps)] = [self.index[b][v] for v in vps]
+        gids = np.where(live, gnode, -1).astype(np.int32)
+        gids[:, 0] = STOP_ID
+        cids = np.full((B, V + 1), -2, np.int32)
+        cids[:, 0] = STOP_ID
+        cids[:, 1:C + 1] = np.where(cand >= 0, cand, -2)[:, :V]
         d = _pack(self._staging, self.device, dict(heading=heading, elevation=elevation, step_ids=step_ids, cur=cur, cur_all=cur_all,
-                                                   cand=cand, start=start, gnode=gnode, lens=lens, vmask=vmask.view(np.uint8)))
+                                                   cand=cand, start=start, gnode=gnode, lens=lens, vmask=vmask.view(np.uint8),
+                                                   gids=gids, cids=cids))
         pano_embeds = pano_embeds.float().contiguous()
         pm = pano_masks.to(torch.uint8).contiguous()
         dev = self.device
@@ -204,10 +245,10 @@ class DeviceGraphMaps:
         vp_masks = ar[None, :V + 1] < (view_lens.to(dev)[:, None] + 1)
         vp_nav_masks = torch.cat([torch.ones((B, 1), dtype=torch.bool, device=dev), nav_types.to(dev) == 1], 1)
         return {
-            'gmap_vpids': gmap_vpids, 'gmap_img_embeds': gmap_img, 'gmap_step_ids': d['step_ids'], 'gmap_pos_fts': gmap_pos,
+            'gmap_vpids': VpidRows(self.names, gnode, lens, d['gids'], -1), 'gmap_img_embeds': gmap_img, 'gmap_step_ids': d['step_ids'], 'gmap_pos_fts': gmap_pos,
             'gmap_visited_masks': d['vmask'].bool(), 'gmap_pair_dists': pair, 'gmap_masks': gmap_masks, 'no_vp_left': no_vp_left,
             'vp_img_embeds': vp_img, 'vp_pos_fts': vp_pos, 'vp_masks': vp_masks, 'vp_nav_masks': vp_nav_masks,
-            'vp_cand_vpids': [[None] + list(x) for x in cand_vpids],
+            'vp_cand_vpids': _CandRows([[None] + list(x) for x in cand_vpids], d['cids']),
         }
 
     # ------------------------------------------------------------------ reads used by the agent after acting
