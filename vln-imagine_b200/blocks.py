@@ -232,14 +232,31 @@ def stack_layout(token_counts: Sequence[int]):
     return row0, ends, cur
 
 
+_CTX_BUFFERS = {}
+
+
 def _ctx_buffer(rows: int, like: torch.Tensor, streams) -> torch.Tensor:
     """Attention output buffer for a row-stacked activation.  The rows between streams (padding up to the next
     128-row boundary) are never written by the attention kernel but do flow through the following GEMM, whose
-    rows are independent: they are zeroed so that the padding stays finite."""
+    rows are independent: they are zeroed so that the padding stays finite.
+    Inference consumes the buffer at once (the output projection that follows reads it on the same stream), so one
+    buffer per layout is allocated and zeroed ONCE and reused by every layer and every step - it used to cost one fill
+    launch per attention call (8 of the ~70 launches of a DUET step).  Autograd keeps the attention output for the
+    backward pass and therefore gets a fresh buffer each time."""
+    pads = [(a.row0 + a.rows, b.row0) for a, b in zip(streams[:-1], streams[1:]) if b.row0 > a.row0 + a.rows]
+    key = None
+    if not _Mode.train and not torch.is_grad_enabled():
+        key = (rows, like.dtype, like.device, tuple((s.row0, s.rows) for s in streams))
+        ctx = _CTX_BUFFERS.get(key)
+        if ctx is not None:
+            return ctx
     ctx = torch.empty((rows, HIDDEN), dtype=like.dtype, device=like.device)
-    for a, b in zip(streams[:-1], streams[1:]):
-        if b.row0 > a.row0 + a.rows:
-            ctx[a.row0 + a.rows:b.row0].zero_()
+    for r0, r1 in pads:
+        ctx[r0:r1].zero_()
+    if key is not None and not torch.cuda.is_current_stream_capturing():      # never keep memory of a graph's private pool
+        if len(_CTX_BUFFERS) > 64:
+            _CTX_BUFFERS.clear()
+        _CTX_BUFFERS[key] = ctx
     return ctx
 
 

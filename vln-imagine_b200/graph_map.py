@@ -47,6 +47,10 @@ class _Staging:
         return b
 
 
+_TORCH_DTYPE = {np.dtype(k).char: v for k, v in (('float64', torch.float64), ('float32', torch.float32), ('int64', torch.int64),
+                                                 ('int32', torch.int32), ('uint8', torch.uint8))}
+
+
 def _pack(staging: _Staging, device, arrays: Dict[str, np.ndarray]) -> Dict[str, torch.Tensor]:
     """Concatenate numpy arrays (8-byte aligned each) into one pinned buffer, copy once, return device views."""
     offs, total = {}, 0
@@ -60,8 +64,7 @@ def _pack(staging: _Staging, device, arrays: Dict[str, np.ndarray]) -> Dict[str,
     dev = host[:total].to(device, non_blocking=True)
     out = {}
     for k, a in arrays.items():
-        t = dev[offs[k]:offs[k] + a.nbytes].view(getattr(torch, str(a.dtype)))
-        out[k] = t.view(a.shape)
+        out[k] = dev[offs[k]:offs[k] + a.nbytes].view(_TORCH_DTYPE[a.dtype.char]).view(a.shape)
     return out
 
 
