@@ -354,9 +354,56 @@ def run_hamt(args):
         json.dump(report, f, indent=1)
 
 
+def run_hamt_encvis(args):
+    """HAMT-Imagine with the PARSER DEFAULTS of the imagination flags (r2r/parser.py:109,122): the ImagineEmbeddings encoder
+    (bypass_imag_encoder=False) and the imagination tokens on the vision stream (concat_imagine_with='visual')."""
+    from importlib import import_module
+    synth = import_module('vln_imagine_b200.synth')
+    from oracle import hamt_oracle as O
+    ref = build_reference('hamt', dict(bypass_imag_encoder=False, concat_imagine_with='visual'))
+    manifest = {k: list(v.shape) for k, v in ref.state_dict().items()}
+    with open(os.path.join(GOLD, 'hamt_encvis_manifest.json'), 'w') as f:
+        json.dump(manifest, f, indent=0)
+    sd = synth.synth_state_dict(manifest, seed=0)
+    ref.load_state_dict(sd)
+    report = {}
+    for tag, shape, seed in [('tiny', synth.TINY, 7), ('cfg1', synth.CFG1, 1234)]:
+        ep = synth.to_torch(synth.hamt_episode(shape, seed))
+        with torch.no_grad():
+            txt = ref('language', txt_ids=ep['txt_ids'], txt_masks=ep['txt_masks'])
+            img = ref('imagine', imagine_pano_img_feats=ep['imagine_feats'], imagine_masks=ep['imagine_masks'])
+            loss, img2 = ref('align_with_contrastive_loss', align_txt_embeds=txt, txt_masks=ep['txt_masks'],
+                             align_imagine_embeds=img.clone(), imagine_masks=ep['imagine_masks'],
+                             sub_instr_segs=ep['sub_instr_segs'], sub_instr_imag_flag=ep['sub_instr_imag_flag'],
+                             noun_phrase_segs=ep['noun_phrase_segs'], obs_instr_ids=ep['obs_instr_ids'])
+            hm = O.hist_masks_from_lens(ep['hist_lens'], ep['hist_embeds'].shape[1])
+            logits, txt_o, hist_o, ob_o = ref(
+                'visual', txt_embeds=txt, txt_masks=ep['txt_masks'], hist_embeds=ep['hist_embeds'], hist_masks=hm,
+                ob_img_feats=ep['ob_img_feats'], ob_ang_feats=ep['ob_ang_feats'], ob_nav_types=ep['ob_nav_types'],
+                ob_masks=ep['ob_masks'], imagine_embeds=img2, imagine_masks=ep['imagine_masks'])
+            o_txt = O.forward_text(sd, ep['txt_ids'], ep['txt_masks'])
+            o_img = O.forward_imagination_encoder(sd, ep['imagine_feats'], ep['imagine_masks'])
+            o_loss, o_img2 = O.forward_align_cosine(sd, o_txt, o_img, ep['sub_instr_imag_flag'], ep['noun_phrase_segs'])
+            o_logits, o_txt_o, o_hist_o, o_ob_o = O.forward_visual(
+                sd, o_txt, ep['txt_masks'], ep['hist_embeds'], hm, ep['ob_img_feats'], ep['ob_ang_feats'], ep['ob_nav_types'],
+                ep['ob_masks'], o_img2, ep['imagine_masks'], concat_imagine_with='visual')
+        diffs = {'img': maxdiff(img, o_img), 'loss': abs(float(loss) - float(o_loss)), 'img2': maxdiff(img2, o_img2),
+                 'logits': maxdiff(logits, o_logits), 'txt_o': maxdiff(txt_o, o_txt_o), 'hist_o': maxdiff(hist_o, o_hist_o),
+                 'ob_o': maxdiff(ob_o, o_ob_o)}
+        report[tag] = diffs
+        print(tag, json.dumps(diffs))
+        assert max(diffs.values()) < 2e-4, 'oracle does not reproduce the reference'
+        f = (lambda t: t) if tag == 'tiny' else _sub
+        np.savez(os.path.join(GOLD, 'hamt_encvis_%s.npz' % tag), **_np(dict(
+            imagine_embeds=f(img), aux_loss=loss, aligned_imagine_embeds=f(img2), act_logits=logits,
+            txt_out=f(txt_o), hist_out=f(hist_o), ob_out=f(ob_o))))
+    with open(os.path.join(GOLD, 'hamt_encvis_oracle_vs_reference.json'), 'w') as f:
+        json.dump(report, f, indent=1)
+
+
 if __name__ == '__main__':
     ap = argparse.ArgumentParser()
-    ap.add_argument('--model', choices=['duet', 'hamt'], required=True)
+    ap.add_argument('--model', choices=['duet', 'hamt', 'hamt_encvis'], required=True)
     ap.add_argument('--grads', action='store_true', help='write the gradient fixtures (cfg-4) instead')
     a = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
@@ -364,4 +411,4 @@ if __name__ == '__main__':
     if a.grads:
         (run_duet_grads if a.model == 'duet' else run_hamt_grads)(a)
     else:
-        (run_duet if a.model == 'duet' else run_hamt)(a)
+        {'duet': run_duet, 'hamt': run_hamt, 'hamt_encvis': run_hamt_encvis}[a.model](a)

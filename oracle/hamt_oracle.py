@@ -78,20 +78,40 @@ def next_action(sd, x):
     return lin(sd, 'next_action.net.4', lnorm(sd, 'next_action.net.2', h, 1e-12))
 
 
+def forward_imagination_encoder(sd, imagine_feats, imagine_masks, num_layers=2):
+    """mode 'imagine' with bypass_imag_encoder=False: ImagineEmbeddings.forward, models/vilmodel_cmt.py:634-703
+    (position + type embedding on the raw features, Linear + LN, a post-LN BertEncoder over the imaginations of an
+    episode with the additive -10000 mask, final LN)."""
+    p = 'imagine_embeddings'
+    n = imagine_feats.shape[1]
+    x = imagine_feats + sd[p + '.position_embeddings.weight'][:n][None] + sd[p + '.type_embedding.weight'][0]
+    x = lnorm(sd, p + '.pano_img_layer_norm', lin(sd, p + '.pano_img_linear', x), 1e-12)
+    m = neg_mask(imagine_masks)
+    for i in range(num_layers):
+        x = bert_layer(sd, '%s.pano_encoder.layer.%d' % (p, i), x, m)
+    return lnorm(sd, p + '.layer_norm', x, 1e-12)
+
+
 def forward_visual(sd, txt_embeds, txt_masks, hist_embeds, hist_masks, ob_img_feats, ob_ang_feats,
-                   ob_nav_types, ob_masks, imagine_embeds, imagine_masks, num_x_layers=4):
-    """mode 'visual', concat_imagine_with='language', act_pred_token='ob_txt', no_lang_ca=False.
+                   ob_nav_types, ob_masks, imagine_embeds, imagine_masks, num_x_layers=4, concat_imagine_with='language'):
+    """mode 'visual', act_pred_token='ob_txt', no_lang_ca=False; the imagination tokens ride on the language stream
+    (concat_imagine_with='language', the released recipe) or on the vision stream ('visual', the parser default).
     models/vilmodel_cmt.py:1056-1205."""
     ob = observation_embeddings(sd, ob_img_feats, ob_ang_feats, ob_nav_types)
-    n_hist = hist_embeds.shape[1]
+    n_hist, n_ob = hist_embeds.shape[1], ob.shape[1]
     visn = torch.cat([hist_embeds, ob], 1)
     visn_add = torch.cat([neg_mask(hist_masks), neg_mask(ob_masks)], -1)
     L = txt_embeds.shape[1]
-    lang = torch.cat([txt_embeds, imagine_embeds], 1)
-    lang_add = torch.cat([neg_mask(txt_masks), neg_mask(imagine_masks)], -1)
+    lang, lang_add = txt_embeds, neg_mask(txt_masks)
+    if concat_imagine_with == 'language':                       # :1109-1112
+        lang = torch.cat([txt_embeds, imagine_embeds], 1)
+        lang_add = torch.cat([lang_add, neg_mask(imagine_masks)], -1)
+    else:                                                       # :1106-1108
+        visn = torch.cat([visn, imagine_embeds], 1)
+        visn_add = torch.cat([visn_add, neg_mask(imagine_masks)], -1)
     for i in range(num_x_layers):
         lang, visn = lxrt_x_layer(sd, 'encoder.x_layers.%d' % i, lang, lang_add, visn, visn_add)
-    hist_out, ob_out = visn[:, :n_hist], visn[:, n_hist:]
+    hist_out, ob_out = visn[:, :n_hist], visn[:, n_hist:n_hist + n_ob]      # :1173-1182
     txt_out = lang[:, :L]
     logits = next_action(sd, ob_out * txt_out[:, :1]).squeeze(-1)
     logits = logits.masked_fill(ob_nav_types == 0, float('-inf'))

@@ -110,3 +110,46 @@ def test_hamt_api_graph_replay_equals_eager_launches(env):
             for k in ('act_logits', 'hist_embed', 'states'):
                 assert torch.equal(out[k], ref[k]), (rep, k)
     assert all(e['graph'] is not None for e in model._g_vis.entries.values())
+
+
+@pytest.mark.parametrize('tag,shape,seed', [('tiny', 'TINY', 7), ('cfg1', 'CFG1', 1234)])
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_hamt_encoder_visual_variant_vs_reference_golden(lib_built, tag, shape, seed, precision):
+    """HAMT-Imagine with the parser defaults of the imagination flags (r2r/parser.py:109,122): the ImagineEmbeddings encoder
+    (bypass_imag_encoder=False) and the imagination tokens on the vision stream (concat_imagine_with='visual'), against the
+    real reference's outputs (oracle/gen_golden.py --model hamt_encvis)."""
+    synth = importlib.import_module('vln_imagine_b200.synth')
+    hamt = importlib.import_module('vln_imagine_b200.hamt')
+    config = importlib.import_module('vln_imagine_b200.config')
+    model = hamt.VLNBertCMT(config.default_hamt_args(bypass_imag_encoder=False, concat_imagine_with='visual')).cuda().eval()
+    model.vln_bert.load_state_dict(synth.synth_state_dict(manifest('hamt_encvis'), seed=0))
+    model.vln_bert.precision = precision
+    ep = to_dev(synth.to_torch(synth.hamt_episode(getattr(synth, shape), seed)))
+    inner = model.vln_bert
+    with torch.no_grad():
+        txt = model('language', txt_ids=ep['txt_ids'], txt_masks=ep['txt_masks'])
+        img = model('imagine', imagine_pano_img_feats=ep['imagine_feats'], imagine_masks=ep['imagine_masks'])
+        loss, img2 = model('align_with_contrastive_loss', align_txt_embeds=txt, txt_masks=ep['txt_masks'],
+                           align_imagine_embeds=img.clone(), imagine_masks=ep['imagine_masks'],
+                           sub_instr_segs=ep['sub_instr_segs'], sub_instr_imag_flag=ep['sub_instr_imag_flag'],
+                           noun_phrase_segs=ep['noun_phrase_segs'], obs_instr_ids=ep['obs_instr_ids'])
+        hist_lens = [int(x) for x in ep['hist_lens']]
+        hist_list = [ep['hist_embeds'][:, t] for t in range(ep['hist_embeds'].shape[1])]
+        kw = dict(txt_embeds=txt, txt_masks=ep['txt_masks'], ob_img_feats=ep['ob_img_feats'], ob_ang_feats=ep['ob_ang_feats'],
+                  ob_nav_types=ep['ob_nav_types'], ob_masks=ep['ob_masks'], imagine_embeds=img2, imagine_masks=ep['imagine_masks'])
+        (logits_a,) = model('visual', hist_embeds=hist_list, hist_lens=hist_lens, **kw)        # eager, then the graphed replay
+        (logits_b,) = model('visual', hist_embeds=hist_list, hist_lens=hist_lens, **kw)
+        (logits_c,) = model('visual', hist_embeds=hist_list, hist_lens=hist_lens, **kw)
+        hm = torch.arange(ep['hist_embeds'].shape[1], device='cuda')[None] < torch.as_tensor(hist_lens, device='cuda')[:, None]
+        logits, txt_o, hist_o, ob_o = inner('visual', hist_embeds=ep['hist_embeds'], hist_masks=hm, **kw)
+    assert torch.equal(logits_a, logits_b) and torch.equal(logits_b, logits_c) and torch.equal(logits_a, logits)
+    gold = golden('hamt_encvis_' + tag)
+    tol = TOL[precision]
+    f = (lambda t: t) if tag == 'tiny' else sub16
+    out = dict(imagine_embeds=img, aligned_imagine_embeds=img2, txt_out=txt_o, hist_out=hist_o, ob_out=ob_o)
+    for k, v in out.items():
+        assert max_rel(f(v), gold[k]) < tol, k
+    assert max_rel(logits, gold['act_logits']) < tol
+    assert abs(float(loss) - float(gold['aux_loss'])) < tol * abs(float(gold['aux_loss']))
+    if precision == 'fp32':
+        assert torch.equal(logits.cpu().argmax(-1), gold['act_logits'].argmax(-1))

@@ -88,6 +88,17 @@ def test_parameter_tree_matches_the_reference_state_dict(kind):
     assert any(n.startswith('vln_bert.imagine_embeddings') for n in names)
 
 
+def test_parameter_tree_of_the_hamt_imagination_encoder_variant():
+    """bypass_imag_encoder=False (the HAMT parser default): imagine_embeddings.* are the ImagineEmbeddings tensors of the reference"""
+    m = importlib.import_module('vln_imagine_b200.hamt').VLNBertCMT(
+        config.default_hamt_args(bypass_imag_encoder=False, concat_imagine_with='visual'))
+    man = manifest('hamt_encvis')
+    sd = m.vln_bert.state_dict()
+    assert set(sd) == set(man) and all(list(sd[k].shape) == man[k] for k in man)
+    assert 'imagine_embeddings.pano_encoder.layer.1.output.LayerNorm.weight' in sd
+    m.vln_bert.load_state_dict(synth.synth_state_dict(man, seed=0))
+
+
 def test_freeze_flags_follow_the_reference():
     duet = importlib.import_module('vln_imagine_b200.duet')
     m = duet.VLNBert(config.default_duet_args(fix_lang_embedding=True, fix_pano_embedding=True)).vln_bert

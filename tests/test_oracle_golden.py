@@ -61,6 +61,31 @@ def test_hamt_oracle_matches_reference_golden(tag, shape, seed):
     assert abs(float(loss) - float(gold['aux_loss'])) < 1e-6
 
 
+@pytest.mark.parametrize('tag,shape,seed', [('tiny', 'TINY', 7), ('cfg1', 'CFG1', 1234)])
+def test_hamt_encoder_visual_variant_oracle_matches_reference_golden(tag, shape, seed):
+    """the parser-default imagination flags of HAMT-Imagine: ImagineEmbeddings encoder + concat_imagine_with='visual'"""
+    from oracle import hamt_oracle as O
+    rep = json.load(open(os.path.join(GOLDEN, 'hamt_encvis_oracle_vs_reference.json')))
+    assert all(max(case.values()) < 2e-4 for case in rep.values())
+    sd = synth.synth_state_dict(manifest('hamt_encvis'), seed=0)
+    ep = synth.to_torch(synth.hamt_episode(getattr(synth, shape), seed))
+    gold = golden('hamt_encvis_' + tag)
+    with torch.no_grad():
+        txt = O.forward_text(sd, ep['txt_ids'], ep['txt_masks'])
+        img = O.forward_imagination_encoder(sd, ep['imagine_feats'], ep['imagine_masks'])
+        loss, img2 = O.forward_align_cosine(sd, txt, img, ep['sub_instr_imag_flag'], ep['noun_phrase_segs'])
+        hm = O.hist_masks_from_lens(ep['hist_lens'], ep['hist_embeds'].shape[1])
+        logits, txt_o, hist_o, ob_o = O.forward_visual(sd, txt, ep['txt_masks'], ep['hist_embeds'], hm, ep['ob_img_feats'],
+                                                       ep['ob_ang_feats'], ep['ob_nav_types'], ep['ob_masks'], img2,
+                                                       ep['imagine_masks'], concat_imagine_with='visual')
+    f = (lambda t: t) if tag == 'tiny' else sub16
+    out = dict(imagine_embeds=f(img), aligned_imagine_embeds=f(img2), act_logits=logits, txt_out=f(txt_o), hist_out=f(hist_o),
+               ob_out=f(ob_o))
+    for k, v in out.items():
+        assert max_rel(v, gold[k]) < 1e-5, k
+    assert abs(float(loss) - float(gold['aux_loss'])) < 1e-6
+
+
 def test_oracle_edge_cases_empty_alignment_and_single_admissible_action():
     """no flagged imagination -> loss 0 and embeds untouched; one admissible action -> every other logit is -inf"""
     from oracle import duet_oracle as O

@@ -9,7 +9,7 @@ wl=${2:-duet_cfg2}
 mkdir -p gpurun_out
 CMD="python bench.py --steps 3 --warmup 3 --no-cpu-baseline --workload $wl"
 $CMD > gpurun_out/plain_$tag.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/launches_$tag.csv $CMD > gpurun_out/ncu_list_$tag.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/launches_$tag.csv $CMD > gpurun_out/ncu_list_$tag.log 2>&1
 CMD2="python tools/step_once.py $wl"
 $CMD2 > gpurun_out/plain2_$tag.log 2>&1 &&
 ncu --set full --clock-control none --import-source on --profile-from-start off -c 120 -f -o gpurun_out/step_$tag $CMD2 > gpurun_out/ncu_full_$tag.log 2>&1

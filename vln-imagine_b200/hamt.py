@@ -49,11 +49,11 @@ class NavCMT(nn.Module):
                 raise NotImplementedError('aux_loss_type %r' % c.aux_loss_type)
             self.contrastive_alignment_model = params.AlignModelP()
         if c.imagine_enc_pano:
-            if not c.bypass_imag_encoder:
-                raise NotImplementedError('bypass_imag_encoder=False (ImagineEmbeddings encoder) is not on the released path')
-            if c.concat_imagine_with != 'language':
-                raise NotImplementedError("concat_imagine_with=%r (only 'language' is on the released path)" % c.concat_imagine_with)
-            self.imagine_embeddings = params.BypassImagineEmbeddingsP()
+            if c.concat_imagine_with not in ('language', 'visual'):
+                raise NotImplementedError('concat_imagine_with=%r' % c.concat_imagine_with)
+            # the released recipe: bypass + 'language' (scripts/run_r2r.sh:70-74); the parser defaults (r2r/parser.py:109,122):
+            # ImagineEmbeddings encoder + 'visual' - inference only here, fine-tuning them raises NotImplementedError
+            self.imagine_embeddings = params.BypassImagineEmbeddingsP() if c.bypass_imag_encoder else params.ImagineEmbeddingsP(c)
         self.encoder = params.HamtEncoderP(c)
         self.next_action = params.NextActionP(c.pred_head_dropout_prob)
         params.bert_init_(self)
@@ -90,6 +90,10 @@ class NavCMT(nn.Module):
             if he.pano_encoder is not None:
                 pk['hist_pano_img'] = blocks.LinearPack([he.pano_img_linear.weight], [he.pano_img_linear.bias])
                 pk['hist_pano'] = [blocks.SelfFFNPack([l.attention], [l.intermediate], [l.output]) for l in he.pano_encoder.layer]
+            if self.config.imagine_enc_pano and not self.config.bypass_imag_encoder:
+                im = self.imagine_embeddings
+                pk['imag_img'] = blocks.LinearPack([im.pano_img_linear.weight], [im.pano_img_linear.bias])
+                pk['imag_enc'] = [blocks.SelfFFNPack([l.attention], [l.intermediate], [l.output]) for l in im.pano_encoder.layer]
             pk['act'] = blocks.ClsHeadPack([self.next_action], last_index=4)
             if hasattr(self, 'contrastive_alignment_model'):
                 ip = self.contrastive_alignment_model.image_proj
@@ -198,14 +202,40 @@ class NavCMT(nn.Module):
         return y32.detach() if self.fix_hist_embedding else y32
 
     def forward_imagination(self, imagine_pano_img_feats, imagine_masks=None):
-        """'imagine' (bypass encoder), :620-631, :1040-1048."""
+        """'imagine', :1040-1048: the bypass embedding (:620-631) or the ImagineEmbeddings encoder (:634-703)."""
         ops.ensure_init(imagine_pano_img_feats)
         B, I, _ = imagine_pano_img_feats.shape
+        if not self.config.bypass_imag_encoder:
+            return self._imagination_encoder(imagine_pano_img_feats, imagine_masks)
         with blocks.grad_mode(self._recording(imagine_pano_img_feats) and not self.fix_imagine_embeds):
             y = blocks.embed(B * I, imagine_pano_img_feats.device, a=_f32c(imagine_pano_img_feats).view(B * I, HIDDEN),
                              const_rows=(self.imagine_embeddings.type_embedding.weight[0],))
         out = y.f32.view(B, I, HIDDEN)
         return out.detach() if self.fix_imagine_embeds else out
+
+    def _imagination_encoder(self, feats, imagine_masks):
+        """ImagineEmbeddings.forward, :634-703: features + position + type embedding -> Linear + LN -> post-LN BertEncoder over
+        the imaginations of an episode (additive -10000 mask) -> LN.  Inference only."""
+        im, lowp, pk = self.imagine_embeddings, self.lowp, self._pk()
+        if imagine_masks is None:
+            raise ValueError("mode 'imagine' needs imagine_masks when bypass_imag_encoder is off (r2r/agent_cmt.py:413-417)")
+        if self._recording(feats) and any(p.requires_grad for p in im.parameters()) and not self.fix_imagine_embeds:
+            raise NotImplementedError('fine-tuning the ImagineEmbeddings encoder (bypass_imag_encoder=False) is not built')
+        B, I, _ = feats.shape
+        if I >= im.position_embeddings.weight.shape[0]:
+            raise ValueError('imagination length %d out of bounds (max_imagination_len %d, :683)' % (I, im.position_embeddings.weight.shape[0]))
+        dev = feats.device
+        x32, x16 = ops.embed_compose(B * I, dev, a=_f32c(feats).view(B * I, -1), pos_table=im.position_embeddings.weight, pos_period=I,
+                                     const_row=im.type_embedding.weight[0], want16=lowp, want32=not lowp)
+        w, b = pk['imag_img'].get(lowp)
+        a = ops.gemm(x16 if lowp else x32, w, b, out_dtype=F32)
+        y32, y16 = ops.add_ln(a, None, im.pano_img_layer_norm.weight, im.pano_img_layer_norm.bias, 1e-12, want16=lowp)
+        x = Act(y32, y16)
+        s = [Stream(0, B, I, blocks.mask_u8(imagine_masks))]
+        for lp in pk['imag_enc']:
+            x = blocks.self_attn_ffn(x, lp, s, None, lowp)
+        out, _ = ops.add_ln(x.f32, None, im.layer_norm.weight, im.layer_norm.bias, 1e-12, want16=False)
+        return out.view(B, I, HIDDEN).detach()
 
     def forward_visual(self, txt_embeds, txt_masks, hist_embeds, hist_masks, ob_img_feats, ob_ang_feats, ob_nav_types,
                        ob_masks, imagine_embeds=None, imagine_masks=None):
@@ -215,15 +245,19 @@ class NavCMT(nn.Module):
         dev = txt_embeds.device
         B, L, _ = txt_embeds.shape
         T, O = hist_embeds.shape[1], ob_img_feats.shape[1]
-        Nv = T + O
         if cfg.imagine_enc_pano:
             if imagine_embeds is None or imagine_masks is None:
                 raise ValueError('visual mode needs imagine_embeds and imagine_masks when imagine_enc_pano is set')
             I = imagine_embeds.shape[1]
         else:
             I = 0
-        C = L + I
+        # the imagination tokens ride on the language stream (:1109-1112) or on the vision stream (:1106-1108)
+        on_visn = bool(I) and cfg.concat_imagine_with == 'visual'
+        Il, Iv = (0, I) if on_visn else (I, 0)
+        C, Nv = L + Il, T + O + Iv
         if self._recording(txt_embeds, hist_embeds, ob_img_feats, imagine_embeds):
+            if on_visn:
+                raise NotImplementedError("fine-tuning with concat_imagine_with='visual' is not built")
             with blocks.grad_mode(True, self._drop()):
                 return self._visual_train(txt_embeds, txt_masks, hist_embeds, hist_masks, ob_img_feats, ob_ang_feats,
                                           ob_nav_types, ob_masks, imagine_embeds, imagine_masks)
@@ -238,7 +272,7 @@ class NavCMT(nn.Module):
         visn32, visn16 = x32[r_v:], (x16[r_v:] if lowp else None)
         # language stream = [txt ; imagine]  (:1110)
         ops.copy_rows(_f32c(txt_embeds), L * HIDDEN, HIDDEN, B, L, lang32, lang16, C * HIDDEN, HIDDEN)
-        if I:
+        if Il:
             ops.copy_rows(_f32c(imagine_embeds), I * HIDDEN, HIDDEN, B, I, lang32[L:], lang16[L:] if lowp else None,
                           C * HIDDEN, HIDDEN)
         # vision stream = [hist ; ob]  (:1087); observation embedding :521-544, :1073-1077
@@ -254,10 +288,13 @@ class NavCMT(nn.Module):
                                     const_row=self.embeddings.token_type_embeddings.weight[1],
                                     out_ln=(ie.layer_norm.weight, ie.layer_norm.bias))
         ops.copy_rows(ob32, O * HIDDEN, HIDDEN, B, O, visn32[T:], visn16[T:] if lowp else None, Nv * HIDDEN, HIDDEN)
+        if Iv:
+            ops.copy_rows(_f32c(imagine_embeds), I * HIDDEN, HIDDEN, B, I, visn32[T + O:], visn16[T + O:] if lowp else None,
+                          Nv * HIDDEN, HIDDEN)
         x = Act(x32, x16)
 
-        lang_mask = blocks.mask_u8(torch.cat([txt_masks.bool(), imagine_masks.bool()], 1) if I else txt_masks)
-        visn_mask = blocks.mask_u8(torch.cat([hist_masks.bool(), ob_masks.bool()], 1))
+        lang_mask = blocks.mask_u8(torch.cat([txt_masks.bool(), imagine_masks.bool()], 1) if Il else txt_masks)
+        visn_mask = blocks.mask_u8(torch.cat([hist_masks.bool(), ob_masks.bool()] + ([imagine_masks.bool()] if Iv else []), 1))
         streams = [Stream(r_l, B, C, lang_mask, 0), Stream(r_v, B, Nv, visn_mask, 1)]
 
         for cp, sp in zip(pk['x_cross'], pk['x_self']):
@@ -277,7 +314,7 @@ class NavCMT(nn.Module):
 
         lang_out = x.f32[r_l:r_l + B * C].view(B, C, HIDDEN)
         visn_out = x.f32[r_v:r_v + B * Nv].view(B, Nv, HIDDEN)
-        txt_out, hist_out, ob_out = lang_out[:, :L], visn_out[:, :T], visn_out[:, T:]
+        txt_out, hist_out, ob_out = lang_out[:, :L], visn_out[:, :T], visn_out[:, T:T + O]      # :1173-1182
         if cfg.act_pred_token == 'ob_txt':                     # :1191
             h32, h16 = ops.mul_bcast(ob_out, Nv * HIDDEN, lang_out, C * HIDDEN, B, O, want16=lowp, want32=not lowp)
         else:                                                  # 'ob'

@@ -221,6 +221,19 @@ class BypassImagineEmbeddingsP(_Container):
         self.type_embedding = nn.Embedding(1, H)
 
 
+class ImagineEmbeddingsP(_Container):
+    """ImagineEmbeddings, H/models/vilmodel_cmt.py:634-703 (bypass_imag_encoder=False, imagine_enc_pano=True)"""
+
+    def __init__(self, cfg):
+        super().__init__()
+        self.position_embeddings = nn.Embedding(cfg.max_imagination_len, H)
+        self.type_embedding = nn.Embedding(1, H)
+        self.layer_norm = nn.LayerNorm(H, eps=1e-12)
+        self.pano_img_linear = nn.Linear(cfg.image_feat_size, H)
+        self.pano_img_layer_norm = nn.LayerNorm(H, eps=1e-12)
+        self.pano_encoder = LayerStack('layer', [BertLayerP() for _ in range(cfg.num_h_pano_layers)])
+
+
 class MLPProjectionHeadP(_Container):
     """MLPProjectionHead :575-589: 768 -> 512 -> 512 -> 768, no bias, dropout 0.15 on the input"""
 
