@@ -217,6 +217,12 @@ int vi_infonce_loss(const float* proj, const float* tgt, const float* negs,
                     const int32_t* row_episode, const int32_t* neg_episode,
                     float temperature, float* scratch, float* loss_mean,
                     int R, int n_negs, vi_stream_t stream);
+/* margin form of the same alignment loss (aux_loss_type 'constrastive-margin', H/models/vilmodel_cmt.py:825-856, 939-942):
+ * (1 - cos(p, t)) + mean over the noun-phrase means of OTHER episodes of relu(margin + cos(p, neg) - cos(p, t)); same operands
+ * and scratch layout as vi_infonce_loss.  Forward only. */
+int vi_margin_loss(const float* proj, const float* tgt, const float* negs, const int32_t* row_episode,
+                   const int32_t* neg_episode, float margin, float* loss_rows, float* loss_mean, int R, int n_negs,
+                   vi_stream_t stream);
 
 /* dst[b, r, 0:768] = src[b, r, 0:768] for n_batches x rows_per_batch rows; strides in ELEMENTS.  Writes an
  * fp32 and/or a bf16 copy.  Builds the cross-attention context cat([txt_embeds, imagine_embeds], 1)

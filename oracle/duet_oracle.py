@@ -298,6 +298,34 @@ def forward_align_infonce(sd, align_txt_embeds, align_imagine_embeds, sub_instr_
     return loss, out
 
 
+def forward_align_margin(sd, align_txt_embeds, align_imagine_embeds, sub_instr_imag_flag, noun_phrase_segs, margin):
+    """aux_loss_type 'constrastive-margin' (HAMT only: VLN-HAMT/finetune_src/models/vilmodel_cmt.py:825-856, 858-950): the
+    negatives of forward_align_infonce; loss_i = (1 - cos(proj, pos)) + mean_neg relu(margin + cos(proj, neg) - cos(proj, pos))."""
+    B = align_imagine_embeds.shape[0]
+    per_ep: List[List[torch.Tensor]] = [[] for _ in range(B)]
+    for b, flags in enumerate(sub_instr_imag_flag):
+        for i, f in enumerate(flags):
+            if f != 'True':
+                continue
+            for s, e in noun_phrase_segs[b][i]:
+                if e >= s:
+                    per_ep[b].append(align_txt_embeds[b, s:e + 1].mean(0))
+    out = align_imagine_embeds.clone()
+    losses = []
+    p = 'contrastive_alignment_model.image_proj'
+    for b, i, toks, n_np in _noun_phrase_rows(sub_instr_imag_flag, noun_phrase_segs):
+        proj = mlp_projection(sd, p, align_imagine_embeds[b, i])
+        if n_np > 0:
+            pos = align_txt_embeds[b, toks].mean(0)
+            negs = torch.stack([t for bb in range(B) if bb != b for t in per_ep[bb]], 0)
+            pos_sim = F.cosine_similarity(proj[None], pos[None]).squeeze()
+            neg_sims = F.cosine_similarity(proj[None], negs)
+            out[b, i] = proj
+            losses.append((1 - pos_sim) + torch.relu(margin + neg_sims - pos_sim).mean())
+    loss = torch.stack(losses).mean() if losses else torch.zeros(())
+    return loss, out
+
+
 # ---------------------------------------------------------------------------------------------
 # whole-episode helpers used by tests / bench
 # ---------------------------------------------------------------------------------------------

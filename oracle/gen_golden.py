@@ -401,9 +401,42 @@ def run_hamt_encvis(args):
         json.dump(report, f, indent=1)
 
 
+def run_hamt_margin(args):
+    """HAMT-Imagine alignment loss with aux_loss_type 'constrastive-margin' (sic, r2r/parser.py:117)."""
+    from importlib import import_module
+    synth = import_module('vln_imagine_b200.synth')
+    from oracle import duet_oracle as D
+    from oracle import hamt_oracle as O
+    ref = build_reference('hamt', dict(aux_loss_type='constrastive-margin', contrastive_margin_value=0.5))
+    manifest = {k: list(v.shape) for k, v in ref.state_dict().items()}
+    assert manifest == json.load(open(os.path.join(GOLD, 'hamt_manifest.json'))), 'the margin variant shares the parameter tree'
+    sd = synth.synth_state_dict(manifest, seed=0)
+    ref.load_state_dict(sd)
+    report = {}
+    for tag, shape, seed in [('tiny', synth.TINY, 7), ('cfg1', synth.CFG1, 1234)]:
+        ep = synth.to_torch(synth.hamt_episode(shape, seed))
+        with torch.no_grad():
+            txt = ref('language', txt_ids=ep['txt_ids'], txt_masks=ep['txt_masks'])
+            img = ref('imagine', imagine_pano_img_feats=ep['imagine_feats'], imagine_masks=None)
+            loss, img2 = ref('align_with_contrastive_loss', align_txt_embeds=txt, txt_masks=ep['txt_masks'],
+                             align_imagine_embeds=img.clone(), imagine_masks=ep['imagine_masks'],
+                             sub_instr_segs=ep['sub_instr_segs'], sub_instr_imag_flag=ep['sub_instr_imag_flag'],
+                             noun_phrase_segs=ep['noun_phrase_segs'], obs_instr_ids=ep['obs_instr_ids'])
+            o_txt = O.forward_text(sd, ep['txt_ids'], ep['txt_masks'])
+            o_img = O.forward_imagination(sd, ep['imagine_feats'])
+            o_loss, o_img2 = D.forward_align_margin(sd, o_txt, o_img, ep['sub_instr_imag_flag'], ep['noun_phrase_segs'], 0.5)
+        diffs = {'loss': abs(float(loss) - float(o_loss)), 'img2': maxdiff(img2, o_img2)}
+        report[tag] = diffs
+        print(tag, json.dumps(diffs), float(loss))
+        assert max(diffs.values()) < 2e-4, 'oracle does not reproduce the reference'
+        np.savez(os.path.join(GOLD, 'hamt_margin_%s.npz' % tag), **_np(dict(margin_loss=loss, margin_imagine_embeds=_sub(img2))))
+    with open(os.path.join(GOLD, 'hamt_margin_oracle_vs_reference.json'), 'w') as f:
+        json.dump(report, f, indent=1)
+
+
 if __name__ == '__main__':
     ap = argparse.ArgumentParser()
-    ap.add_argument('--model', choices=['duet', 'hamt', 'hamt_encvis'], required=True)
+    ap.add_argument('--model', choices=['duet', 'hamt', 'hamt_encvis', 'hamt_margin'], required=True)
     ap.add_argument('--grads', action='store_true', help='write the gradient fixtures (cfg-4) instead')
     a = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
@@ -411,4 +444,4 @@ if __name__ == '__main__':
     if a.grads:
         (run_duet_grads if a.model == 'duet' else run_hamt_grads)(a)
     else:
-        {'duet': run_duet, 'hamt': run_hamt, 'hamt_encvis': run_hamt_encvis}[a.model](a)
+        {'duet': run_duet, 'hamt': run_hamt, 'hamt_encvis': run_hamt_encvis, 'hamt_margin': run_hamt_margin}[a.model](a)

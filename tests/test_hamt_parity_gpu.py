@@ -153,3 +153,27 @@ def test_hamt_encoder_visual_variant_vs_reference_golden(lib_built, tag, shape, 
     assert abs(float(loss) - float(gold['aux_loss'])) < tol * abs(float(gold['aux_loss']))
     if precision == 'fp32':
         assert torch.equal(logits.cpu().argmax(-1), gold['act_logits'].argmax(-1))
+
+
+@pytest.mark.parametrize('tag,shape,seed', [('tiny', 'TINY', 7), ('cfg1', 'CFG1', 1234)])
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_hamt_margin_alignment_loss_vs_reference_golden(lib_built, tag, shape, seed, precision):
+    """aux_loss_type 'constrastive-margin' (sic; H/r2r/parser.py:117, H/models/vilmodel_cmt.py:825-856) against the real reference"""
+    synth = importlib.import_module('vln_imagine_b200.synth')
+    hamt = importlib.import_module('vln_imagine_b200.hamt')
+    config = importlib.import_module('vln_imagine_b200.config')
+    model = hamt.VLNBertCMT(config.default_hamt_args(aux_loss_type='constrastive-margin', contrastive_margin_value=0.5)).cuda().eval()
+    model.vln_bert.load_state_dict(synth.synth_state_dict(manifest('hamt'), seed=0))
+    model.vln_bert.precision = precision
+    ep = to_dev(synth.to_torch(synth.hamt_episode(getattr(synth, shape), seed)))
+    with torch.no_grad():
+        txt = model('language', txt_ids=ep['txt_ids'], txt_masks=ep['txt_masks'])
+        img = model('imagine', imagine_pano_img_feats=ep['imagine_feats'], imagine_masks=None)
+        loss, img2 = model('align_with_contrastive_loss', align_txt_embeds=txt, txt_masks=ep['txt_masks'],
+                           align_imagine_embeds=img.clone(), imagine_masks=ep['imagine_masks'],
+                           sub_instr_segs=ep['sub_instr_segs'], sub_instr_imag_flag=ep['sub_instr_imag_flag'],
+                           noun_phrase_segs=ep['noun_phrase_segs'], obs_instr_ids=ep['obs_instr_ids'])
+    gold = golden('hamt_margin_' + tag)
+    tol = TOL[precision]
+    assert abs(float(loss) - float(gold['margin_loss'])) < tol * abs(float(gold['margin_loss']))
+    assert max_rel(sub16(img2), gold['margin_imagine_embeds']) < tol

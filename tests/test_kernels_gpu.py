@@ -289,6 +289,26 @@ def test_infonce(ops):
     assert abs(float(loss) - float(torch.stack(ref).mean())) < 1e-4
 
 
+def test_margin_loss(ops):
+    """margin alignment loss (H/models/vilmodel_cmt.py:825-856) against torch; a row without admissible negatives is NaN
+    there (mean of an empty tensor) and here"""
+    R, Nn = 9, 14
+    p, t, negs = _rand(R, 768, seed=1), _rand(R, 768, seed=2), _rand(Nn, 768, seed=3)
+    row_ep = torch.tensor([0, 0, 1, 1, 1, 2, 3, 3, 3], dtype=torch.int32, device='cuda')
+    neg_ep = torch.tensor([0, 0, 0, 1, 1, 1, 1, 2, 2, 3, 3, 3, 3, 3], dtype=torch.int32, device='cuda')
+    margin = 0.5
+    loss = ops.margin_loss(p, t, negs, row_ep, neg_ep, margin, R, Nn, 'cuda')
+    ref = []
+    for r in range(R):
+        pos = F.cosine_similarity(p[r:r + 1], t[r:r + 1]).squeeze()
+        neg = F.cosine_similarity(p[r:r + 1], negs[neg_ep != row_ep[r]])
+        ref.append((1 - pos) + F.relu(margin + neg - pos).mean())
+    assert abs(float(loss) - float(torch.stack(ref).mean())) < 1e-5
+    same = torch.zeros(Nn, dtype=torch.int32, device='cuda')
+    lone = ops.margin_loss(p[:2], t[:2], negs, torch.zeros(2, dtype=torch.int32, device='cuda'), same, margin, 2, Nn, 'cuda')
+    assert torch.isnan(lone)
+
+
 def _fuse_reference(global_logits, local_logits, gmap_vpids, visited, vp_cand_vpids):
     """the per-episode python loop of the reference (VLN-DUET/map_nav_src/models/vilmodel.py:1198-1217)"""
     fused = global_logits.clone()

@@ -86,6 +86,21 @@ def test_hamt_encoder_visual_variant_oracle_matches_reference_golden(tag, shape,
     assert abs(float(loss) - float(gold['aux_loss'])) < 1e-6
 
 
+@pytest.mark.parametrize('tag,shape,seed', [('tiny', 'TINY', 7), ('cfg1', 'CFG1', 1234)])
+def test_hamt_margin_alignment_oracle_matches_reference_golden(tag, shape, seed):
+    from oracle import duet_oracle as D
+    from oracle import hamt_oracle as O
+    sd = synth.synth_state_dict(manifest('hamt'), seed=0)
+    ep = synth.to_torch(synth.hamt_episode(getattr(synth, shape), seed))
+    gold = golden('hamt_margin_' + tag)
+    with torch.no_grad():
+        txt = O.forward_text(sd, ep['txt_ids'], ep['txt_masks'])
+        img = O.forward_imagination(sd, ep['imagine_feats'])
+        loss, img2 = D.forward_align_margin(sd, txt, img, ep['sub_instr_imag_flag'], ep['noun_phrase_segs'], 0.5)
+    assert abs(float(loss) - float(gold['margin_loss'])) < 1e-6
+    assert max_rel(sub16(img2), gold['margin_imagine_embeds']) < 1e-5
+
+
 def test_oracle_edge_cases_empty_alignment_and_single_admissible_action():
     """no flagged imagination -> loss 0 and embeds untouched; one admissible action -> every other logit is -inf"""
     from oracle import duet_oracle as O

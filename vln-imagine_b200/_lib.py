@@ -64,6 +64,7 @@ PROTOTYPES = {
     'vi_scatter_rows': [_p, _p, _p, _i, _p],
     'vi_cosine_loss': [_p, _p, _p, _p, _i, _p],
     'vi_infonce_loss': [_p, _p, _p, _p, _p, _f, _p, _p, _i, _i, _p],
+    'vi_margin_loss': [_p, _p, _p, _p, _p, _f, _p, _p, _i, _i, _p],
     'vi_copy_rows': [_p, _l, _l, _p, _p, _l, _l, _l, _i, _p],
     'vi_cast_bf16': [_p, _p, _l, _p],
     'vi_transpose': [_p, _l, _p, _l, _i, _i, _i, _i, _p],

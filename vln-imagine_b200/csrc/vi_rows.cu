@@ -374,6 +374,26 @@ __global__ void __launch_bounds__(128) infonce_rows_kernel(const float* sims, co
   if (lane == 0) loss_rows[row] = mx + logf(sum) - s[0];
 }
 
+// margin form (H/models/vilmodel_cmt.py:825-856): loss_r = (1 - cos_pos) + mean over the negatives of OTHER episodes of
+// relu(margin + cos_neg - cos_pos); `sims` holds plain cosines (inv_t = 1).  No admissible negative -> 0 / 0 = NaN, as
+// torch.mean of an empty tensor in the reference.
+__global__ void __launch_bounds__(128) margin_rows_kernel(const float* sims, const int32_t* row_ep, const int32_t* neg_ep,
+                                                          float margin, float* loss_rows, int R, int n_negs) {
+  pdl_enter();
+  ROW_INDEX();
+  if (row >= R) return;
+  const int cols = n_negs + 1;
+  const float* s = sims + row * cols;
+  const int ep = row_ep[row];
+  const float pos = s[0];
+  float sum = 0.f, cnt = 0.f;
+  for (int c = 1 + lane; c < cols; c += 32)
+    if (neg_ep[c - 1] != ep) { sum += fmaxf(margin + s[c] - pos, 0.f); cnt += 1.f; }
+  sum = warp_sum(sum);
+  cnt = warp_sum(cnt);
+  if (lane == 0) loss_rows[row] = (1.0f - pos) + sum / cnt;
+}
+
 __global__ void cast_bf16_kernel(const float* src, bf16* dst, long long n4, long long n) {
   pdl_enter();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -560,6 +580,24 @@ extern "C" int vi_infonce_loss(const float* proj, const float* tgt, const float*
   return VI_OK;
 }
 
+
+extern "C" int vi_margin_loss(const float* proj, const float* tgt, const float* negs, const int32_t* row_episode,
+                              const int32_t* neg_episode, float margin, float* loss_rows, float* loss_mean, int R, int n_negs,
+                              vi_stream_t stream) {
+  // loss_rows doubles as scratch exactly as in vi_infonce_loss: R * (n_negs + 1) cosines first, the R losses after
+  VI_CHECK_ARG(loss_mean && (R == 0 || (proj && tgt && loss_rows && row_episode)), "vi_margin_loss: null operand");
+  VI_CHECK_ARG(n_negs == 0 || (negs && neg_episode), "vi_margin_loss: negatives missing");
+  float* sims = loss_rows;
+  float* rows_out = loss_rows + (long long)R * (n_negs + 1);
+  if (R > 0) {
+    const long long items = (long long)R * (n_negs + 1);
+    VI_CUDA(vi_launch(infonce_sims_kernel, dim3(row_grid(items)), dim3(128), (size_t)(0), ST(stream), proj, tgt, negs, 1.0f, sims, R, n_negs));
+    VI_CUDA(vi_launch(margin_rows_kernel, dim3(row_grid(R)), dim3(128), (size_t)(0), ST(stream), sims, row_episode, neg_episode, margin, rows_out, R, n_negs));
+  }
+  VI_CUDA(vi_launch(mean_kernel, dim3(1), dim3(256), (size_t)(0), ST(stream), rows_out, loss_mean, R));
+  VI_LAUNCH_CHECK();
+  return VI_OK;
+}
 
 extern "C" int vi_copy_rows(const float* src, int64_t src_batch_stride, int64_t src_row_stride, float* dst32, void* dst16,
                             int64_t dst_batch_stride, int64_t dst_row_stride, int64_t n_batches, int rows_per_batch,

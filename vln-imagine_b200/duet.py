@@ -153,6 +153,12 @@ def align_forward(model, align_txt_embeds, align_imagine_embeds, flags, noun_phr
             negs, _ = ops.gather_mean(txt, rows.np_off, rows.np_rows, rows.n_negs, want16=False)
         loss = ops.infonce_loss(proj, tgt, negs, rows.ep, rows.np_ep if rows.n_negs else None,
                                 float(cfg.infonce_temperature), rows.R, rows.n_negs, dev)
+    elif cfg.aux_loss_type == 'constrastive-margin':          # (sic) H/r2r/parser.py:117, H/models/vilmodel_cmt.py:825-856
+        negs = None
+        if rows.n_negs:
+            negs, _ = ops.gather_mean(txt, rows.np_off, rows.np_rows, rows.n_negs, want16=False)
+        loss = ops.margin_loss(proj, tgt, negs, rows.ep, rows.np_ep if rows.n_negs else None,
+                               float(cfg.contrastive_margin_value), rows.R, rows.n_negs, dev)
     else:
         raise NotImplementedError('aux_loss_type %r' % cfg.aux_loss_type)
     ops.scatter_rows(proj, rows.slot, out)

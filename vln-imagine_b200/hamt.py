@@ -45,7 +45,7 @@ class NavCMT(nn.Module):
         self.img_embeddings = params.HamtImageEmbeddingsP(c)
         self.hist_embeddings = params.HistoryEmbeddingsP(c)
         if c.imagine_enc_pano and (c.use_cosine_aux_loss or c.no_loss_test):
-            if c.aux_loss_type not in ('cosine', 'contrastive-InfoNCE'):
+            if c.aux_loss_type not in ('cosine', 'contrastive-InfoNCE', 'constrastive-margin'):
                 raise NotImplementedError('aux_loss_type %r' % c.aux_loss_type)
             self.contrastive_alignment_model = params.AlignModelP()
         if c.imagine_enc_pano:

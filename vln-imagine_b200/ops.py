@@ -409,6 +409,15 @@ def infonce_loss(proj, tgt, negs, row_episode, neg_episode, temperature: float, 
     return loss
 
 
+def margin_loss(proj, tgt, negs, row_episode, neg_episode, margin: float, R: int, n_negs: int, device):
+    loss = torch.empty((), dtype=F32, device=device)
+    scratch = torch.empty((max(R, 1) * (n_negs + 2),), dtype=F32, device=device)
+    check(lib.vi_margin_loss(_ptr(proj), _ptr(tgt), _ptr(negs), _ptr(row_episode), _ptr(neg_episode), margin,
+                             scratch.data_ptr(), loss.data_ptr(), R, n_negs, _stream()), 'vi_margin_loss')
+    _launched(3)
+    return loss
+
+
 def infonce_loss_with_sims(proj, tgt, negs, row_episode, neg_episode, temperature: float, R: int, n_negs: int, device):
     """infonce_loss that also hands back the forward scratch (its first R * (n_negs + 1) floats are the scaled
     similarities the backward pass needs)."""
