@@ -401,6 +401,43 @@ def run_hamt_encvis(args):
         json.dump(report, f, indent=1)
 
 
+def run_hamt_actpred(args):
+    """act_pred_token variants of HAMT's action head (r2r/parser.py:67, models/vilmodel_cmt.py:1189-1199) with the imagination
+    tokens on either stream: only the logits change."""
+    from importlib import import_module
+    synth = import_module('vln_imagine_b200.synth')
+    from oracle import hamt_oracle as O
+    out, report = {}, {}
+    for concat in ('language', 'visual'):
+        for tok in ('ob', 'ob_hist', 'ob_txt_hist', 'ob_imagine_text'):
+            ref = build_reference('hamt', dict(act_pred_token=tok, concat_imagine_with=concat))
+            manifest = {k: list(v.shape) for k, v in ref.state_dict().items()}
+            sd = synth.synth_state_dict(manifest, seed=0)
+            ref.load_state_dict(sd)
+            for tag, shape, seed in [('tiny', synth.TINY, 7), ('cfg1', synth.CFG1, 1234)]:
+                ep = synth.to_torch(synth.hamt_episode(shape, seed))
+                with torch.no_grad():
+                    txt = ref('language', txt_ids=ep['txt_ids'], txt_masks=ep['txt_masks'])
+                    img = ref('imagine', imagine_pano_img_feats=ep['imagine_feats'], imagine_masks=None)
+                    hm = O.hist_masks_from_lens(ep['hist_lens'], ep['hist_embeds'].shape[1])
+                    logits = ref('visual', txt_embeds=txt, txt_masks=ep['txt_masks'], hist_embeds=ep['hist_embeds'], hist_masks=hm,
+                                 ob_img_feats=ep['ob_img_feats'], ob_ang_feats=ep['ob_ang_feats'], ob_nav_types=ep['ob_nav_types'],
+                                 ob_masks=ep['ob_masks'], imagine_embeds=img, imagine_masks=ep['imagine_masks'])[0]
+                    o_txt = O.forward_text(sd, ep['txt_ids'], ep['txt_masks'])
+                    o_img = O.forward_imagination(sd, ep['imagine_feats'])
+                    o_logits = O.forward_visual(sd, o_txt, ep['txt_masks'], ep['hist_embeds'], hm, ep['ob_img_feats'], ep['ob_ang_feats'],
+                                                ep['ob_nav_types'], ep['ob_masks'], o_img, ep['imagine_masks'],
+                                                concat_imagine_with=concat, act_pred_token=tok)[0]
+                key = '%s_%s_%s' % (tag, concat, tok)
+                report[key] = maxdiff(logits, o_logits)
+                assert report[key] < 2e-4, key
+                out[key] = logits
+            print(concat, tok, 'ok')
+    np.savez(os.path.join(GOLD, 'hamt_actpred.npz'), **_np(out))
+    with open(os.path.join(GOLD, 'hamt_actpred_oracle_vs_reference.json'), 'w') as f:
+        json.dump(report, f, indent=1)
+
+
 def run_hamt_margin(args):
     """HAMT-Imagine alignment loss with aux_loss_type 'constrastive-margin' (sic, r2r/parser.py:117)."""
     from importlib import import_module
@@ -436,7 +473,7 @@ def run_hamt_margin(args):
 
 if __name__ == '__main__':
     ap = argparse.ArgumentParser()
-    ap.add_argument('--model', choices=['duet', 'hamt', 'hamt_encvis', 'hamt_margin'], required=True)
+    ap.add_argument('--model', choices=['duet', 'hamt', 'hamt_encvis', 'hamt_margin', 'hamt_actpred'], required=True)
     ap.add_argument('--grads', action='store_true', help='write the gradient fixtures (cfg-4) instead')
     a = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
@@ -444,4 +481,4 @@ if __name__ == '__main__':
     if a.grads:
         (run_duet_grads if a.model == 'duet' else run_hamt_grads)(a)
     else:
-        {'duet': run_duet, 'hamt': run_hamt, 'hamt_encvis': run_hamt_encvis, 'hamt_margin': run_hamt_margin}[a.model](a)
+        {'duet': run_duet, 'hamt': run_hamt, 'hamt_encvis': run_hamt_encvis, 'hamt_margin': run_hamt_margin, 'hamt_actpred': run_hamt_actpred}[a.model](a)

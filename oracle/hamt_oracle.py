@@ -93,7 +93,8 @@ def forward_imagination_encoder(sd, imagine_feats, imagine_masks, num_layers=2):
 
 
 def forward_visual(sd, txt_embeds, txt_masks, hist_embeds, hist_masks, ob_img_feats, ob_ang_feats,
-                   ob_nav_types, ob_masks, imagine_embeds, imagine_masks, num_x_layers=4, concat_imagine_with='language'):
+                   ob_nav_types, ob_masks, imagine_embeds, imagine_masks, num_x_layers=4, concat_imagine_with='language',
+                   act_pred_token='ob_txt'):
     """mode 'visual', act_pred_token='ob_txt', no_lang_ca=False; the imagination tokens ride on the language stream
     (concat_imagine_with='language', the released recipe) or on the vision stream ('visual', the parser default).
     models/vilmodel_cmt.py:1056-1205."""
@@ -113,7 +114,12 @@ def forward_visual(sd, txt_embeds, txt_masks, hist_embeds, hist_masks, ob_img_fe
         lang, visn = lxrt_x_layer(sd, 'encoder.x_layers.%d' % i, lang, lang_add, visn, visn_add)
     hist_out, ob_out = visn[:, :n_hist], visn[:, n_hist:n_hist + n_ob]      # :1173-1182
     txt_out = lang[:, :L]
-    logits = next_action(sd, ob_out * txt_out[:, :1]).squeeze(-1)
+    imagine_out = lang[:, L:] if concat_imagine_with == 'language' else visn[:, n_hist + n_ob:]
+    gate = {'ob_txt': lambda: txt_out[:, :1], 'ob_hist': lambda: hist_out[:, :1],                  # :1189-1199
+            'ob_txt_hist': lambda: txt_out[:, :1] + hist_out[:, :1],
+            'ob_imagine_text': lambda: txt_out[:, :1] + imagine_out.mean(1).unsqueeze(1)}
+    pred_in = ob_out if act_pred_token == 'ob' else ob_out * gate[act_pred_token]()
+    logits = next_action(sd, pred_in).squeeze(-1)
     logits = logits.masked_fill(ob_nav_types == 0, float('-inf'))
     return logits, txt_out, hist_out, ob_out
 

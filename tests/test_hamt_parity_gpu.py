@@ -177,3 +177,33 @@ def test_hamt_margin_alignment_loss_vs_reference_golden(lib_built, tag, shape, s
     tol = TOL[precision]
     assert abs(float(loss) - float(gold['margin_loss'])) < tol * abs(float(gold['margin_loss']))
     assert max_rel(sub16(img2), gold['margin_imagine_embeds']) < tol
+
+
+@pytest.mark.parametrize('concat', ['language', 'visual'])
+@pytest.mark.parametrize('tok', ['ob', 'ob_hist', 'ob_txt_hist', 'ob_imagine_text'])
+def test_hamt_action_token_variants_vs_reference_golden(lib_built, concat, tok):
+    """every act_pred_token of H/r2r/parser.py:67 (models/vilmodel_cmt.py:1189-1199) with the imagination tokens on either
+    stream, logits against the real reference (oracle/gen_golden.py --model hamt_actpred), both precisions, both sizes"""
+    synth = importlib.import_module('vln_imagine_b200.synth')
+    hamt = importlib.import_module('vln_imagine_b200.hamt')
+    config = importlib.import_module('vln_imagine_b200.config')
+    model = hamt.VLNBertCMT(config.default_hamt_args(act_pred_token=tok, concat_imagine_with=concat)).cuda().eval()
+    model.vln_bert.load_state_dict(synth.synth_state_dict(manifest('hamt'), seed=0))
+    gold = golden('hamt_actpred')
+    for tag, shape, seed in (('tiny', synth.TINY, 7), ('cfg1', synth.CFG1, 1234)):
+        ep = to_dev(synth.to_torch(synth.hamt_episode(shape, seed)))
+        hist_lens = [int(x) for x in ep['hist_lens']]
+        hist_list = [ep['hist_embeds'][:, t] for t in range(ep['hist_embeds'].shape[1])]
+        for precision in ('fp32', 'bf16'):
+            model.vln_bert.precision = precision
+            with torch.no_grad():
+                txt = model('language', txt_ids=ep['txt_ids'], txt_masks=ep['txt_masks'])
+                img = model('imagine', imagine_pano_img_feats=ep['imagine_feats'], imagine_masks=None)
+                outs = [model('visual', txt_embeds=txt, txt_masks=ep['txt_masks'], hist_embeds=hist_list, hist_lens=hist_lens,
+                              ob_img_feats=ep['ob_img_feats'], ob_ang_feats=ep['ob_ang_feats'], ob_nav_types=ep['ob_nav_types'],
+                              ob_masks=ep['ob_masks'], imagine_embeds=img, imagine_masks=ep['imagine_masks'])[0] for _ in range(3)]
+            assert torch.equal(outs[0], outs[1]) and torch.equal(outs[1], outs[2])          # eager call == graph replays
+            ref = gold['%s_%s_%s' % (tag, concat, tok)]
+            assert max_rel(outs[0], ref) < TOL[precision], (tag, precision)
+            if precision == 'fp32':
+                assert torch.equal(outs[0].cpu().argmax(-1), ref.argmax(-1))

@@ -101,6 +101,25 @@ def test_hamt_margin_alignment_oracle_matches_reference_golden(tag, shape, seed)
     assert max_rel(sub16(img2), gold['margin_imagine_embeds']) < 1e-5
 
 
+def test_hamt_action_token_variants_oracle_matches_reference_golden():
+    from oracle import hamt_oracle as O
+    rep = json.load(open(os.path.join(GOLDEN, 'hamt_actpred_oracle_vs_reference.json')))
+    assert len(rep) == 16 and max(rep.values()) < 2e-4
+    sd = synth.synth_state_dict(manifest('hamt'), seed=0)
+    ep = synth.to_torch(synth.hamt_episode(synth.TINY, 7))
+    gold = golden('hamt_actpred')
+    with torch.no_grad():
+        txt = O.forward_text(sd, ep['txt_ids'], ep['txt_masks'])
+        img = O.forward_imagination(sd, ep['imagine_feats'])
+        hm = O.hist_masks_from_lens(ep['hist_lens'], ep['hist_embeds'].shape[1])
+        for concat in ('language', 'visual'):
+            for tok in ('ob', 'ob_hist', 'ob_txt_hist', 'ob_imagine_text'):
+                logits = O.forward_visual(sd, txt, ep['txt_masks'], ep['hist_embeds'], hm, ep['ob_img_feats'], ep['ob_ang_feats'],
+                                          ep['ob_nav_types'], ep['ob_masks'], img, ep['imagine_masks'], concat_imagine_with=concat,
+                                          act_pred_token=tok)[0]
+                assert max_rel(logits, gold['tiny_%s_%s' % (concat, tok)]) < 1e-5, (concat, tok)
+
+
 def test_oracle_edge_cases_empty_alignment_and_single_admissible_action():
     """no flagged imagination -> loss 0 and embeds untouched; one admissible action -> every other logit is -inf"""
     from oracle import duet_oracle as O

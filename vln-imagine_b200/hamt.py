@@ -39,8 +39,10 @@ class NavCMT(nn.Module):
             raise NotImplementedError('num_h_layers / num_r_layers > 0 are not used by the released HAMT-Imagine runs')
         if c.no_lang_ca:
             raise NotImplementedError('no_lang_ca=True is not supported (the reference itself warns that it breaks the imagination path)')
-        if c.act_pred_token not in ('ob_txt', 'ob'):
+        if c.act_pred_token not in ('ob_txt', 'ob', 'ob_hist', 'ob_txt_hist', 'ob_imagine_text'):      # H/r2r/parser.py:67
             raise NotImplementedError('act_pred_token %r' % c.act_pred_token)
+        if c.act_pred_token == 'ob_imagine_text' and not c.imagine_enc_pano:
+            raise NotImplementedError("act_pred_token 'ob_imagine_text' needs imagine_enc_pano")
         self.embeddings = params.BertEmbeddingsP(c)
         self.img_embeddings = params.HamtImageEmbeddingsP(c)
         self.hist_embeddings = params.HistoryEmbeddingsP(c)
@@ -256,8 +258,9 @@ class NavCMT(nn.Module):
         Il, Iv = (0, I) if on_visn else (I, 0)
         C, Nv = L + Il, T + O + Iv
         if self._recording(txt_embeds, hist_embeds, ob_img_feats, imagine_embeds):
-            if on_visn:
-                raise NotImplementedError("fine-tuning with concat_imagine_with='visual' is not built")
+            if on_visn or cfg.act_pred_token not in ('ob_txt', 'ob'):
+                raise NotImplementedError("fine-tuning with concat_imagine_with='visual' or act_pred_token=%r is not built"
+                                          % cfg.act_pred_token)
             with blocks.grad_mode(True, self._drop()):
                 return self._visual_train(txt_embeds, txt_masks, hist_embeds, hist_masks, ob_img_feats, ob_ang_feats,
                                           ob_nav_types, ob_masks, imagine_embeds, imagine_masks)
@@ -315,8 +318,27 @@ class NavCMT(nn.Module):
         lang_out = x.f32[r_l:r_l + B * C].view(B, C, HIDDEN)
         visn_out = x.f32[r_v:r_v + B * Nv].view(B, Nv, HIDDEN)
         txt_out, hist_out, ob_out = lang_out[:, :L], visn_out[:, :T], visn_out[:, T:T + O]      # :1173-1182
-        if cfg.act_pred_token == 'ob_txt':                     # :1191
+        tok = cfg.act_pred_token                               # :1189-1199
+        if tok == 'ob_txt':
             h32, h16 = ops.mul_bcast(ob_out, Nv * HIDDEN, lang_out, C * HIDDEN, B, O, want16=lowp, want32=not lowp)
+        elif tok == 'ob_hist':                                 # ob * hist[:, :1]: token 0 of the vision stream
+            h32, h16 = ops.mul_bcast(ob_out, Nv * HIDDEN, visn_out, Nv * HIDDEN, B, O, want16=lowp, want32=not lowp)
+        elif tok in ('ob_txt_hist', 'ob_imagine_text'):        # ob * (txt[:, :1] + hist[:, :1] | mean over the imagination tokens)
+            t0 = torch.empty((B, HIDDEN), dtype=F32, device=dev)
+            ops.copy_rows(lang_out, C * HIDDEN, HIDDEN, B, 1, t0, None, HIDDEN, HIDDEN)
+            if tok == 'ob_txt_hist':
+                other = torch.empty((B, HIDDEN), dtype=F32, device=dev)
+                ops.copy_rows(visn_out, Nv * HIDDEN, HIDDEN, B, 1, other, None, HIDDEN, HIDDEN)
+            else:                                              # torch.mean(imagine_embeds, 1): all I output tokens, unmasked
+                row0, per = (r_v + T + O, Nv) if on_visn else (r_l + L, C)
+                key = ('imag', B, I, row0, per, str(dev))
+                if key not in self._mean_idx:
+                    idx = (row0 + torch.arange(B, device=dev)[:, None] * per + torch.arange(I, device=dev)[None, :]).reshape(-1)
+                    self._mean_idx[key] = (torch.arange(0, B * I + 1, I, dtype=torch.int32, device=dev), idx.to(torch.int32))
+                off, idx = self._mean_idx[key]
+                other, _ = ops.gather_mean(x.f32, off, idx, B, want16=False)
+            gate, _ = ops.embed_compose(B, dev, a=t0, a2=other)
+            h32, h16 = ops.mul_bcast(ob_out, Nv * HIDDEN, gate, HIDDEN, B, O, want16=lowp, want32=not lowp)
         else:                                                  # 'ob'
             h32 = torch.empty((B * O, HIDDEN), dtype=F32, device=dev) if not lowp else None
             h16 = torch.empty((B * O, HIDDEN), dtype=BF16, device=dev) if lowp else None
