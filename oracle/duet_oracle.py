@@ -160,16 +160,31 @@ def pano_encoder_layer(sd, p, x, key_pad):
     return x + lin(sd, p + '.linear2', F.gelu(lin(sd, p + '.linear1', h)))
 
 
-def forward_panorama(sd, view_img_fts, loc_fts, nav_types, view_lens, num_pano_layers=2):
-    """mode 'panorama' (no object branch: obj_feat_size=0 on R2R).  models/vilmodel.py:1087-1131."""
+def forward_panorama(sd, view_img_fts, loc_fts, nav_types, view_lens, num_pano_layers=2, obj_img_fts=None, obj_lens=None):
+    """mode 'panorama'.  models/vilmodel.py:1087-1131.  R2R has no object branch (obj_feat_size=0); REVERIE appends the
+    object boxes of a panorama behind its views, per episode, zero padded to the longest (:1096-1114)."""
     p = 'img_embeddings'
-    e = (lnorm(sd, p + '.img_layer_norm', lin(sd, p + '.img_linear', view_img_fts), 1e-12)
+    img = lnorm(sd, p + '.img_layer_norm', lin(sd, p + '.img_linear', view_img_fts), 1e-12)
+    pano_lens = view_lens
+    if obj_img_fts is not None:
+        if (p + '.obj_linear.weight') in sd:                    # obj_feat_size != image_feat_size (:464-468)
+            obj = lnorm(sd, p + '.obj_layer_norm', lin(sd, p + '.obj_linear', obj_img_fts), 1e-12)
+        else:
+            obj = lnorm(sd, p + '.img_layer_norm', lin(sd, p + '.img_linear', obj_img_fts), 1e-12)
+        pano_lens = view_lens + obj_lens
+        rows = torch.zeros(img.shape[0], int(pano_lens.max()), img.shape[2])
+        for b in range(img.shape[0]):
+            vl, ol = int(view_lens[b]), int(obj_lens[b])
+            rows[b, :vl] = img[b, :vl]
+            rows[b, vl:vl + ol] = obj[b, :ol]
+        img = rows
+    e = (img
          + lnorm(sd, p + '.loc_layer_norm', lin(sd, p + '.loc_linear', loc_fts), 1e-12)
          + F.embedding(nav_types, sd[p + '.nav_type_embedding.weight'])
          + sd['embeddings.token_type_embeddings.weight'][1])
     x = lnorm(sd, p + '.layer_norm', e, 1e-12)
-    V = view_img_fts.shape[1]
-    pano_masks = torch.arange(V)[None, :] < view_lens[:, None]      # models/ops.py:36-44
+    V = img.shape[1]
+    pano_masks = torch.arange(V)[None, :] < pano_lens[:, None]      # models/ops.py:36-44
     pad = ~pano_masks
     for i in range(num_pano_layers):
         x = pano_encoder_layer(sd, '%s.pano_encoder.layers.%d' % (p, i), x, pad)
@@ -199,9 +214,9 @@ def fuse_logits(global_logits, local_logits, gmap_vpids, gmap_visited_masks, vp_
 def forward_navigation(sd, txt_embeds, txt_masks, gmap_img_embeds, gmap_step_ids, gmap_pos_fts,
                        gmap_masks, gmap_pair_dists, gmap_visited_masks, gmap_vpids,
                        vp_img_embeds, vp_pos_fts, vp_masks, vp_nav_masks, vp_cand_vpids,
-                       imagine_embeds, imagine_masks, num_x_layers=4):
+                       imagine_embeds, imagine_masks, num_x_layers=4, vp_obj_masks=None):
     """mode 'navigation' with imaginations concatenated to the text stream.
-    models/vilmodel.py:1133-1235."""
+    models/vilmodel.py:1133-1235; vp_obj_masks (REVERIE) adds the object-grounding logits (:1220-1225)."""
     g = 'global_encoder'
     gmap = (gmap_img_embeds
             + F.embedding(gmap_step_ids, sd[g + '.gmap_step_embeddings.weight'])
@@ -223,8 +238,11 @@ def forward_navigation(sd, txt_embeds, txt_masks, gmap_img_embeds, gmap_step_ids
     local_logits = cls_prediction(sd, 'local_sap_head', vp).squeeze(2) * (1 - fuse_w)
     local_logits = local_logits.masked_fill(~vp_nav_masks, float('-inf'))
     fused = fuse_logits(global_logits, local_logits, gmap_vpids, gmap_visited_masks, vp_cand_vpids)
+    obj_logits = None
+    if vp_obj_masks is not None:
+        obj_logits = cls_prediction(sd, 'og_head', vp).squeeze(2).masked_fill(~vp_obj_masks, float('-inf'))
     return {'gmap_embeds': gmap, 'vp_embeds': vp, 'global_logits': global_logits,
-            'local_logits': local_logits, 'fused_logits': fused, 'obj_logits': None}
+            'local_logits': local_logits, 'fused_logits': fused, 'obj_logits': obj_logits}
 
 
 def mlp_projection(sd, p, x):
@@ -296,6 +314,27 @@ def forward_align_infonce(sd, align_txt_embeds, align_imagine_embeds, sub_instr_
             losses.append(F.cross_entropy(sim[None], torch.zeros(1, dtype=torch.long)))
     loss = torch.stack(losses).mean() if losses else torch.zeros(())
     return loss, out
+
+
+def forward_align_reverie(sd, align_txt_embeds, txt_masks, align_imagine_embeds, aux_loss_type='cosine', temperature=0.007):
+    """REVERIE alignment (one imagination per instruction, no sub-instruction annotation): the projected imagination
+    against the mean of ALL valid instruction tokens (AlignWithContrastiveLossReverie, models/vilmodel.py:781-828); the
+    InfoNCE form takes the instruction means of the OTHER episodes as negatives (:830-888, :657-687)."""
+    B = align_imagine_embeds.shape[0]
+    p = 'contrastive_alignment_model.image_proj'
+    means = [align_txt_embeds[b, txt_masks[b]].mean(0) for b in range(B)]
+    out = align_imagine_embeds.clone()
+    losses = []
+    for b in range(B):
+        proj = mlp_projection(sd, p, align_imagine_embeds[b, 0])
+        out[b, 0] = proj
+        if aux_loss_type == 'cosine':
+            losses.append(1 - F.cosine_similarity(proj, means[b], dim=-1))
+        else:
+            allt = torch.stack([means[b]] + [means[o] for o in range(B) if o != b], 0)
+            sim = F.cosine_similarity(proj[None], allt) / temperature
+            losses.append(F.cross_entropy(sim[None], torch.zeros(1, dtype=torch.long)))
+    return torch.stack(losses).mean(), out
 
 
 def forward_align_margin(sd, align_txt_embeds, align_imagine_embeds, sub_instr_imag_flag, noun_phrase_segs, margin):

@@ -401,6 +401,64 @@ def run_hamt_encvis(args):
         json.dump(report, f, indent=1)
 
 
+def run_duet_reverie(args):
+    """DUET-Imagine as released for REVERIE (scripts/run_reverie.sh: dataset reverie, obj_feat_size 768 -> objects through
+    img_linear, og_head, one imagination per instruction, AlignWithContrastiveLossReverie); both aux-loss types."""
+    from importlib import import_module
+    synth = import_module('vln_imagine_b200.synth')
+    from oracle import duet_oracle as O
+    report = {}
+    for aux in ('cosine', 'contrastive-InfoNCE'):
+        ref = build_reference('duet', dict(dataset='reverie', obj_feat_size=768, aux_loss_type=aux))
+        manifest = {k: list(v.shape) for k, v in ref.state_dict().items()}
+        if aux == 'cosine':
+            with open(os.path.join(GOLD, 'duet_reverie_manifest.json'), 'w') as f:
+                json.dump(manifest, f, indent=0)
+        for tag, shape, seed in [('tiny', synth.TINY, 7), ('cfg1', synth.CFG1, 1234)]:
+            sd = synth.synth_state_dict(manifest, seed=0, gasa_stress=(tag == 'tiny'))
+            ref.load_state_dict(sd)
+            ep = synth.to_torch(synth.duet_reverie_episode(shape, seed))
+            with torch.no_grad():
+                txt = ref('language', {'txt_ids': ep['txt_ids'], 'txt_masks': ep['txt_masks']})
+                img = ref('imagine', {'imagine_feats': ep['imagine_feats'], 'imagine_masks': None})
+                loss, img2 = ref('align_with_contrastive_loss', {
+                    'align_txt_embeds': txt, 'txt_masks': ep['txt_masks'], 'align_imagine_embeds': img.clone(),
+                    'imagine_masks': ep['imagine_masks'], 'obs_instr_ids': ep['obs_instr_ids']})
+                o_txt = O.forward_text(sd, ep['txt_ids'], ep['txt_masks'])
+                o_img = O.forward_imagination(sd, ep['imagine_feats'])
+                o_loss, o_img2 = O.forward_align_reverie(sd, o_txt, ep['txt_masks'], o_img, aux, 0.007)
+                diffs = {'loss': abs(float(loss) - float(o_loss)), 'img2': maxdiff(img2, o_img2)}
+                out = {'aux_loss': loss, 'aligned_imagine_embeds': img2}
+                if aux == 'cosine':
+                    pano, pano_masks = ref('panorama', {k: ep[k] for k in ('view_img_fts', 'obj_img_fts', 'loc_fts', 'nav_types',
+                                                                               'view_lens', 'obj_lens')})
+                    nav = ref('navigation', {**{k: ep[k] for k in (
+                        'txt_masks', 'gmap_img_embeds', 'gmap_step_ids', 'gmap_pos_fts', 'gmap_masks', 'gmap_pair_dists',
+                        'gmap_visited_masks', 'gmap_vpids', 'vp_img_embeds', 'vp_pos_fts', 'vp_masks', 'vp_nav_masks',
+                        'vp_obj_masks', 'vp_cand_vpids', 'imagine_masks')}, 'txt_embeds': txt, 'imagine_embeds': img2})
+                    o_pano, o_pm = O.forward_panorama(sd, ep['view_img_fts'], ep['loc_fts'], ep['nav_types'], ep['view_lens'],
+                                                      obj_img_fts=ep['obj_img_fts'], obj_lens=ep['obj_lens'])
+                    o_nav = O.forward_navigation(
+                        sd, o_txt, ep['txt_masks'], ep['gmap_img_embeds'], ep['gmap_step_ids'], ep['gmap_pos_fts'], ep['gmap_masks'],
+                        ep['gmap_pair_dists'], ep['gmap_visited_masks'], ep['gmap_vpids'], ep['vp_img_embeds'], ep['vp_pos_fts'],
+                        ep['vp_masks'], ep['vp_nav_masks'], ep['vp_cand_vpids'], o_img2, ep['imagine_masks'],
+                        vp_obj_masks=ep['vp_obj_masks'])
+                    assert torch.equal(pano_masks, o_pm)
+                    diffs.update(pano=maxdiff(pano, o_pano), fused=maxdiff(nav['fused_logits'], o_nav['fused_logits']),
+                                 obj=maxdiff(nav['obj_logits'], o_nav['obj_logits']), vp=maxdiff(nav['vp_embeds'], o_nav['vp_embeds']))
+                    f = (lambda t: t) if tag == 'tiny' else _sub
+                    out.update(pano_embeds=f(pano), pano_masks=pano_masks, vp_embeds=f(nav['vp_embeds']), gmap_embeds=f(nav['gmap_embeds']),
+                               fused_logits=nav['fused_logits'], local_logits=nav['local_logits'], global_logits=nav['global_logits'],
+                               obj_logits=nav['obj_logits'])
+            key = '%s_%s' % (tag, 'cos' if aux == 'cosine' else 'nce')
+            report[key] = diffs
+            print(key, json.dumps(diffs))
+            assert max(diffs.values()) < 2e-4, 'oracle does not reproduce the reference'
+            np.savez(os.path.join(GOLD, 'duet_reverie_%s.npz' % key), **_np(out))
+    with open(os.path.join(GOLD, 'duet_reverie_oracle_vs_reference.json'), 'w') as f:
+        json.dump(report, f, indent=1)
+
+
 def run_hamt_actpred(args):
     """act_pred_token variants of HAMT's action head (r2r/parser.py:67, models/vilmodel_cmt.py:1189-1199) with the imagination
     tokens on either stream: only the logits change."""
@@ -473,7 +531,7 @@ def run_hamt_margin(args):
 
 if __name__ == '__main__':
     ap = argparse.ArgumentParser()
-    ap.add_argument('--model', choices=['duet', 'hamt', 'hamt_encvis', 'hamt_margin', 'hamt_actpred'], required=True)
+    ap.add_argument('--model', choices=['duet', 'hamt', 'hamt_encvis', 'hamt_margin', 'hamt_actpred', 'duet_reverie'], required=True)
     ap.add_argument('--grads', action='store_true', help='write the gradient fixtures (cfg-4) instead')
     a = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
@@ -481,4 +539,4 @@ if __name__ == '__main__':
     if a.grads:
         (run_duet_grads if a.model == 'duet' else run_hamt_grads)(a)
     else:
-        {'duet': run_duet, 'hamt': run_hamt, 'hamt_encvis': run_hamt_encvis, 'hamt_margin': run_hamt_margin, 'hamt_actpred': run_hamt_actpred}[a.model](a)
+        {'duet': run_duet, 'hamt': run_hamt, 'hamt_encvis': run_hamt_encvis, 'hamt_margin': run_hamt_margin, 'hamt_actpred': run_hamt_actpred, 'duet_reverie': run_duet_reverie}[a.model](a)

@@ -204,3 +204,51 @@ def test_context_cache_is_invisible(env, graphs):
     finally:
         model.use_cuda_graphs = True
         net.context_cache = True
+
+
+@pytest.mark.parametrize('tag,shape,seed', [('tiny', 'TINY', 7), ('cfg1', 'CFG1', 1234)])
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_duet_reverie_recipe_vs_reference_golden(lib_built, tag, shape, seed, precision):
+    """The REVERIE recipe (scripts/run_reverie.sh: dataset reverie, obj_feat_size 768): ragged object boxes behind the views of
+    every panorama, the object-grounding head, one imagination per instruction aligned to the mean of all instruction tokens
+    (cosine and InfoNCE), against the real reference's outputs (oracle/gen_golden.py --model duet_reverie)."""
+    synth = importlib.import_module('vln_imagine_b200.synth')
+    duet = importlib.import_module('vln_imagine_b200.duet')
+    config = importlib.import_module('vln_imagine_b200.config')
+    model = duet.VLNBert(config.default_duet_args(dataset='reverie', obj_feat_size=768)).cuda().eval()
+    model.vln_bert.load_state_dict(synth.synth_state_dict(manifest('duet_reverie'), seed=0, gasa_stress=(tag == 'tiny')))
+    model.vln_bert.precision = precision
+    ep = to_dev(synth.to_torch(synth.duet_reverie_episode(getattr(synth, shape), seed)))
+    gold, gold_nce = golden('duet_reverie_%s_cos' % tag), golden('duet_reverie_%s_nce' % tag)
+    cfg = model.vln_bert.config
+    with torch.no_grad():
+        txt = model('language', {'txt_ids': ep['txt_ids'], 'txt_masks': ep['txt_masks']})
+        img = model('imagine', {'imagine_feats': ep['imagine_feats'], 'imagine_masks': None})
+        align = {'align_txt_embeds': txt, 'txt_masks': ep['txt_masks'], 'align_imagine_embeds': img.clone(),
+                 'imagine_masks': ep['imagine_masks'], 'obs_instr_ids': ep['obs_instr_ids']}
+        loss, img2 = model('align_with_contrastive_loss', align)
+        cfg.aux_loss_type = 'contrastive-InfoNCE'
+        try:
+            nce, nce_img2 = model('align_with_contrastive_loss', dict(align, align_imagine_embeds=img.clone()))
+        finally:
+            cfg.aux_loss_type = 'cosine'
+        pano, pano_masks = model('panorama', {k: ep[k] for k in ('view_img_fts', 'obj_img_fts', 'loc_fts', 'nav_types', 'view_lens', 'obj_lens')})
+        nav = model('navigation', {**{k: ep[k] for k in (
+            'txt_masks', 'gmap_img_embeds', 'gmap_step_ids', 'gmap_pos_fts', 'gmap_masks', 'gmap_pair_dists', 'gmap_visited_masks',
+            'gmap_vpids', 'vp_img_embeds', 'vp_pos_fts', 'vp_masks', 'vp_nav_masks', 'vp_obj_masks', 'vp_cand_vpids',
+            'imagine_masks')}, 'txt_embeds': txt, 'imagine_embeds': img2})
+    tol = TOL[precision]
+    f = (lambda t: t) if tag == 'tiny' else sub16
+    assert torch.equal(pano_masks.cpu(), gold['pano_masks'])
+    valid = gold['pano_masks'][:, :, None]
+    assert max_rel(f(pano).cpu() * valid, gold['pano_embeds'] * valid) < tol           # rows behind an episode's own length are padding
+    for k in ('vp_embeds', 'gmap_embeds'):
+        assert max_rel(f(nav[k]), gold[k]) < tol, k
+    for k in ('fused_logits', 'local_logits', 'global_logits', 'obj_logits'):
+        assert max_rel(nav[k], gold[k]) < tol, k
+    assert max_rel(img2, gold['aligned_imagine_embeds']) < tol
+    assert abs(float(loss) - float(gold['aux_loss'])) < tol * abs(float(gold['aux_loss']))
+    assert abs(float(nce) - float(gold_nce['aux_loss'])) < (5e-2 if precision == 'bf16' else 1e-3) * abs(float(gold_nce['aux_loss']))
+    assert max_rel(nce_img2, gold_nce['aligned_imagine_embeds']) < tol
+    if precision == 'fp32':
+        assert torch.equal(nav['obj_logits'].cpu().argmax(-1), gold['obj_logits'].argmax(-1))

@@ -99,6 +99,17 @@ def test_parameter_tree_of_the_hamt_imagination_encoder_variant():
     m.vln_bert.load_state_dict(synth.synth_state_dict(man, seed=0))
 
 
+def test_parameter_tree_of_the_duet_reverie_recipe():
+    """dataset 'reverie', obj_feat_size 768 (scripts/run_reverie.sh): og_head.* joins the tree, objects share img_linear"""
+    m = importlib.import_module('vln_imagine_b200.duet').VLNBert(config.default_duet_args(dataset='reverie', obj_feat_size=768))
+    man = manifest('duet_reverie')
+    sd = m.vln_bert.state_dict()
+    assert set(sd) == set(man) and all(list(sd[k].shape) == man[k] for k in man)
+    assert 'og_head.net.3.weight' in sd and not any(k.startswith('img_embeddings.obj_linear') for k in sd)
+    m2 = importlib.import_module('vln_imagine_b200.duet').VLNBert(config.default_duet_args(dataset='reverie', obj_feat_size=2048))
+    assert list(m2.vln_bert.state_dict()['img_embeddings.obj_linear.weight'].shape) == [768, 2048]
+
+
 def test_freeze_flags_follow_the_reference():
     duet = importlib.import_module('vln_imagine_b200.duet')
     m = duet.VLNBert(config.default_duet_args(fix_lang_embedding=True, fix_pano_embedding=True)).vln_bert

@@ -101,6 +101,37 @@ def test_hamt_margin_alignment_oracle_matches_reference_golden(tag, shape, seed)
     assert max_rel(sub16(img2), gold['margin_imagine_embeds']) < 1e-5
 
 
+@pytest.mark.parametrize('tag,shape,seed', [('tiny', 'TINY', 7), ('cfg1', 'CFG1', 1234)])
+def test_duet_reverie_oracle_matches_reference_golden(tag, shape, seed):
+    """REVERIE recipe of DUET-Imagine (scripts/run_reverie.sh): object boxes in the panorama, object-grounding head, one
+    imagination per instruction with the REVERIE alignment modules (cosine and InfoNCE)"""
+    from oracle import duet_oracle as O
+    rep = json.load(open(os.path.join(GOLDEN, 'duet_reverie_oracle_vs_reference.json')))
+    assert len(rep) == 4 and all(max(c.values()) < 2e-4 for c in rep.values())
+    sd = synth.synth_state_dict(manifest('duet_reverie'), seed=0, gasa_stress=(tag == 'tiny'))
+    ep = synth.to_torch(synth.duet_reverie_episode(getattr(synth, shape), seed))
+    gold, gold_nce = golden('duet_reverie_%s_cos' % tag), golden('duet_reverie_%s_nce' % tag)
+    with torch.no_grad():
+        txt = O.forward_text(sd, ep['txt_ids'], ep['txt_masks'])
+        img = O.forward_imagination(sd, ep['imagine_feats'])
+        loss, img2 = O.forward_align_reverie(sd, txt, ep['txt_masks'], img, 'cosine')
+        nce, nce_img2 = O.forward_align_reverie(sd, txt, ep['txt_masks'], img, 'contrastive-InfoNCE', 0.007)
+        pano, pano_masks = O.forward_panorama(sd, ep['view_img_fts'], ep['loc_fts'], ep['nav_types'], ep['view_lens'],
+                                              obj_img_fts=ep['obj_img_fts'], obj_lens=ep['obj_lens'])
+        nav = O.forward_navigation(sd, txt, ep['txt_masks'], ep['gmap_img_embeds'], ep['gmap_step_ids'], ep['gmap_pos_fts'],
+                                   ep['gmap_masks'], ep['gmap_pair_dists'], ep['gmap_visited_masks'], ep['gmap_vpids'],
+                                   ep['vp_img_embeds'], ep['vp_pos_fts'], ep['vp_masks'], ep['vp_nav_masks'], ep['vp_cand_vpids'],
+                                   img2, ep['imagine_masks'], vp_obj_masks=ep['vp_obj_masks'])
+    f = (lambda t: t) if tag == 'tiny' else sub16
+    assert torch.equal(pano_masks, gold['pano_masks'])
+    for k, v in dict(pano_embeds=f(pano), vp_embeds=f(nav['vp_embeds']), gmap_embeds=f(nav['gmap_embeds']), fused_logits=nav['fused_logits'],
+                     local_logits=nav['local_logits'], global_logits=nav['global_logits'], obj_logits=nav['obj_logits'],
+                     aligned_imagine_embeds=img2).items():
+        assert max_rel(v, gold[k]) < 1e-5, k
+    assert abs(float(loss) - float(gold['aux_loss'])) < 1e-6 and abs(float(nce) - float(gold_nce['aux_loss'])) < 1e-5
+    assert max_rel(nce_img2, gold_nce['aligned_imagine_embeds']) < 1e-5
+
+
 def test_hamt_action_token_variants_oracle_matches_reference_golden():
     from oracle import hamt_oracle as O
     rep = json.load(open(os.path.join(GOLDEN, 'hamt_actpred_oracle_vs_reference.json')))

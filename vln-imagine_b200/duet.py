@@ -103,6 +103,26 @@ class AlignRows:
         return self
 
 
+def reverie_align_rows(B, L, I, txt_masks) -> AlignRows:
+    """AlignRows of the REVERIE alignment modules (models/vilmodel.py:781-888): one imagination per instruction (slot 0), its
+    target = the mean of ALL valid instruction tokens; the InfoNCE negatives = the instruction means of the other episodes."""
+    valid = txt_masks.detach().to('cpu', torch.bool).numpy()
+    r = AlignRows.__new__(AlignRows)
+    tok_rows, tok_off = [], [0]
+    for b in range(B):
+        cols = np.flatnonzero(valid[b])
+        if cols.size == 0:
+            raise ValueError('episode %d has no valid instruction token' % b)
+        tok_rows.extend((b * L + cols).tolist())
+        tok_off.append(len(tok_rows))
+    i32 = lambda x: torch.tensor(x, dtype=torch.int32)   # noqa: E731
+    r.R, r.n_negs = B, B
+    r.slot, r.tok_off, r.tok_rows, r.ep = i32([b * I for b in range(B)]), i32(tok_off), i32(tok_rows), i32(list(range(B)))
+    r.np_off, r.np_rows, r.np_ep = i32(tok_off), i32(tok_rows), i32(list(range(B)))
+    r.unit = torch.arange(B + 1, dtype=torch.int32)
+    return r
+
+
 _ALIGN_ROWS = collections.OrderedDict()
 
 
@@ -121,13 +141,14 @@ def _align_rows(B, L, I, flags, noun_phrase_segs, dev):
     return rows
 
 
-def align_forward(model, align_txt_embeds, align_imagine_embeds, flags, noun_phrase_segs, lowp: bool):
-    """Shared by DUET and HAMT.  Returns (loss 0-d tensor, imagine embeds with projected rows written back)."""
+def align_forward(model, align_txt_embeds, align_imagine_embeds, flags, noun_phrase_segs, lowp: bool, rows: AlignRows = None):
+    """Shared by DUET and HAMT.  Returns (loss 0-d tensor, imagine embeds with projected rows written back).  ``rows``: index
+    arrays already built by the caller (REVERIE) instead of the sub-instruction annotation."""
     cfg = model.config
     B, L, _ = align_txt_embeds.shape
     I = align_imagine_embeds.shape[1]
     dev = align_txt_embeds.device
-    rows = _align_rows(B, L, I, flags, noun_phrase_segs, dev)
+    rows = rows.to(dev) if rows is not None else _align_rows(B, L, I, flags, noun_phrase_segs, dev)
     txt = _f32c(align_txt_embeds).view(B * L, HIDDEN)
     img = _f32c(align_imagine_embeds).view(B * I, HIDDEN)
     out = img.clone()
@@ -203,8 +224,6 @@ class GlocalTextPathNavCMT(nn.Module):
     def __init__(self, config):
         super().__init__()
         self.config = config
-        if config.obj_feat_size > 0:
-            raise NotImplementedError('object branch (REVERIE/SOON, obj_feat_size > 0) is outside the hot path')
         self.embeddings = params.BertEmbeddingsP(config)
         self.lang_encoder = params.LayerStack('layer', [params.BertLayerP() for _ in range(config.num_l_layers)])
         self.img_embeddings = params.DuetImageEmbeddingsP(config)
@@ -213,14 +232,14 @@ class GlocalTextPathNavCMT(nn.Module):
         self.global_sap_head = params.ClsPredictionP()
         self.local_sap_head = params.ClsPredictionP()
         self.sap_fuse_linear = params.ClsPredictionP(input_size=2 * HIDDEN) if config.glocal_fuse else None
+        if config.obj_feat_size > 0:                           # REVERIE object grounding (:1039-1040); inference only here
+            self.og_head = params.ClsPredictionP()
         if config.imagine_enc_pano:
             if config.bypass_imag_encoder:
                 self.imagine_embeddings = params.BypassImagineEmbeddingsP()
             else:
                 raise NotImplementedError('bypass_imag_encoder=False (imagination encoder) is not on the released path')
             if config.use_cosine_aux_loss or config.no_loss_test:
-                if config.dataset == 'reverie':
-                    raise NotImplementedError('REVERIE alignment head is outside the hot path')
                 if config.aux_loss_type not in ('cosine', 'contrastive-InfoNCE'):
                     raise NotImplementedError('aux_loss_type %r' % config.aux_loss_type)
                 self.contrastive_alignment_model = params.AlignModelP()
@@ -233,7 +252,7 @@ class GlocalTextPathNavCMT(nn.Module):
             for p in self.img_embeddings.parameters():
                 p.requires_grad = False
         if config.fix_local_branch:
-            for m in (self.local_encoder, self.local_sap_head):
+            for m in (self.local_encoder, self.local_sap_head) + ((self.og_head,) if config.obj_feat_size > 0 else ()):
                 for p in m.parameters():
                     p.requires_grad = False
         self.precision = os.environ.get('VLN_IMAGINE_PRECISION', 'bf16')
@@ -257,6 +276,10 @@ class GlocalTextPathNavCMT(nn.Module):
             pk['x_self'] = [blocks.SelfFFNPack([g.visn_self_att, l.visn_self_att], [g.visn_inter, l.visn_inter],
                                                [g.visn_output, l.visn_output]) for g, l in zip(gl, ll)]
             pk['sap'] = blocks.ClsHeadPack([self.global_sap_head, self.local_sap_head])
+            if self.config.obj_feat_size > 0:
+                pk['og'] = blocks.ClsHeadPack([self.og_head])
+                if ie.obj_linear is not None:
+                    pk['obj_linear'] = blocks.LinearPack([ie.obj_linear.weight], [ie.obj_linear.bias])
             if self.global_encoder.sprel_linear is not None:
                 sl = self.global_encoder.sprel_linear
                 pk['sprel'] = blocks.StackPack([sl.weight, sl.bias])         # device {w, b} of the GASA bias
@@ -333,7 +356,7 @@ class GlocalTextPathNavCMT(nn.Module):
     def forward_panorama_per_step(self, view_img_fts, obj_img_fts, loc_fts, nav_types, view_lens, obj_lens):
         """'panorama'.  :1087-1131 + transformer.py:71-89,170-182."""
         if obj_img_fts is not None:
-            raise NotImplementedError('object features are outside the R2R hot path')
+            return self._panorama_with_objects(view_img_fts, obj_img_fts, loc_fts, nav_types, view_lens, obj_lens)
         self._guard(view_img_fts)
         lowp = self.lowp
         B, V, Fd = view_img_fts.shape
@@ -358,6 +381,55 @@ class GlocalTextPathNavCMT(nn.Module):
             out = out.detach()
         return out, pano_masks
 
+    def _panorama_with_objects(self, view_img_fts, obj_img_fts, loc_fts, nav_types, view_lens, obj_lens):
+        """'panorama' with the REVERIE object boxes (:1096-1114): per episode the LayerNorm-ed object embeddings follow the
+        LayerNorm-ed view embeddings, zero padded to the longest; everything after that is the R2R path over P = max(view_len
+        + obj_len) tokens.  The ragged concatenation is one row gather over [views ; objects ; a zero row].  Inference only."""
+        self._guard(view_img_fts)
+        if self._recording(view_img_fts, obj_img_fts) and not self.config.fix_pano_embedding:
+            raise NotImplementedError('fine-tuning the panorama encoder with object features (REVERIE) is not built')
+        lowp, pk, ie = self.lowp, self._pk(), self.img_embeddings
+        B, V, _ = view_img_fts.shape
+        O = obj_img_fts.shape[1]
+        dev = view_img_fts.device
+        vl = [int(x) for x in view_lens.tolist()]              # host lengths: the reference loops over them as well (:1106-1113)
+        ol = [int(x) for x in obj_lens.tolist()]
+        P = max(a + b for a, b in zip(vl, ol))
+        if loc_fts.shape[1] != P or nav_types.shape[1] != P:
+            raise ValueError('loc_fts / nav_types must cover max(view_len + obj_len) = %d tokens' % P)
+        v32 = _f32c(view_img_fts).view(B * V, -1)
+        o32 = _f32c(obj_img_fts).view(B * O, -1)
+        w, b = pk['img_linear'].get(lowp)
+        nv, _ = ops.add_ln(ops.gemm(ops.cast_bf16(v32) if lowp else v32, w, b, out_dtype=F32), None, ie.img_layer_norm.weight,
+                           ie.img_layer_norm.bias, 1e-12, want16=False)
+        if ie.obj_linear is not None:                          # obj_feat_size != image_feat_size (:464-468)
+            w, b = pk['obj_linear'].get(lowp)
+            oln = ie.obj_layer_norm
+        else:
+            oln = ie.img_layer_norm
+        no, _ = ops.add_ln(ops.gemm(ops.cast_bf16(o32) if lowp else o32, w, b, out_dtype=F32), None, oln.weight, oln.bias, 1e-12,
+                           want16=False)
+        src = torch.cat([nv, no, torch.zeros((1, HIDDEN), dtype=F32, device=dev)], 0)
+        zero_row = B * V + B * O
+        idx = np.full((B, P), zero_row, np.int32)
+        for i in range(B):
+            idx[i, :vl[i]] = i * V + np.arange(vl[i])
+            idx[i, vl[i]:vl[i] + ol[i]] = B * V + i * O + np.arange(ol[i])
+        idx_d = torch.from_numpy(idx.reshape(-1)).to(dev, non_blocking=True)
+        unit = torch.arange(B * P + 1, dtype=torch.int32, device=dev)
+        a, _ = ops.gather_mean(src, unit, idx_d, B * P, want16=False)
+        pano_lens = (view_lens + obj_lens).to(dev)
+        pano_masks = torch.arange(P, device=dev)[None, :] < pano_lens[:, None]
+        km = blocks.mask_u8(pano_masks)
+        with blocks.grad_mode(False, (0.0, 0.0)):
+            x32 = blocks.embed(B * P, dev, a=a, feat=_f32c(loc_fts).view(B * P, -1), feat_lin=ie.loc_linear, feat_ln=ie.loc_layer_norm,
+                               idx=nav_types.long().contiguous().view(-1), table=ie.nav_type_embedding.weight,
+                               const_rows=(self.embeddings.token_type_embeddings.weight[1],), out_ln=ie.layer_norm).f32
+            for lp in pk['pano']:
+                x32 = blocks.pano_layer(x32, lp, B, P, km, lowp)
+            y32 = blocks.layer_norm(x32, None, pk['pano_norm'], 1e-12, False).f32
+        return y32.view(B, P, HIDDEN).detach(), pano_masks
+
     def forward_navigation_per_step(self, txt_embeds, txt_masks, gmap_img_embeds, gmap_step_ids, gmap_pos_fts,
                                     gmap_masks, gmap_pair_dists, gmap_visited_masks, gmap_vpids,
                                     vp_img_embeds, vp_pos_fts, vp_masks, vp_nav_masks, vp_obj_masks, vp_cand_vpids,
@@ -365,8 +437,8 @@ class GlocalTextPathNavCMT(nn.Module):
         """'navigation'.  :1133-1235.  ``ctx_kv`` (internal): context projections already looked up by the caller
         (VLNBert's graph path); txt_embeds / imagine_embeds are then not read.  ``defer_fuse`` (internal): stop before the
         global / local fusion (:1198-1217) and return its operands under '_fuse' for ``fuse_logits``."""
-        if vp_obj_masks is not None:
-            raise NotImplementedError('object grounding head is outside the R2R hot path')
+        if vp_obj_masks is not None and not hasattr(self, 'og_head'):
+            raise ValueError('vp_obj_masks given but the model has no object-grounding head (obj_feat_size = 0)')
         self._guard(gmap_img_embeds)
         cfg, lowp, pk = self.config, self.lowp, self._pk()
         dev = gmap_img_embeds.device
@@ -375,6 +447,8 @@ class GlocalTextPathNavCMT(nn.Module):
         ge, le = self.global_encoder, self.local_encoder
 
         if ctx_kv is None and self._recording(txt_embeds, gmap_img_embeds, vp_img_embeds, imagine_embeds):
+            if vp_obj_masks is not None:
+                raise NotImplementedError('fine-tuning with the object-grounding head (REVERIE) is not built')
             with blocks.grad_mode(True, self._drop()):
                 return self._navigation_train(txt_embeds, txt_masks, gmap_img_embeds, gmap_step_ids, gmap_pos_fts, gmap_masks,
                                               gmap_pair_dists, gmap_visited_masks, gmap_vpids, vp_img_embeds, vp_pos_fts,
@@ -440,8 +514,12 @@ class GlocalTextPathNavCMT(nn.Module):
         gl, ll, fl = ops.duet_fuse_logits(raw[r_g:], raw[r_l:], fuse_raw, blocks.mask_u8(gmap_masks),
                                           blocks.mask_u8(gmap_visited_masks), blocks.mask_u8(vp_nav_masks),
                                           gmap_ids, cand_ids, B, G, P)
+        obj_logits = None
+        if vp_obj_masks is not None:                           # object grounding logits (:1220-1225): -inf outside the object tokens
+            og_raw = blocks.cls_head(x.operand(lowp)[r_l:r_l + B * P], pk['og'], lowp)
+            obj_logits = ops.mask_logits_navtype(og_raw, vp_obj_masks.long().contiguous().view(-1)).view(B, P)
         return {'gmap_embeds': gmap_out, 'vp_embeds': vp_out, 'global_logits': gl, 'local_logits': ll,
-                'fused_logits': fl, 'obj_logits': None}
+                'fused_logits': fl, 'obj_logits': obj_logits}
 
     def fuse_logits(self, pre: dict, gmap_vpids, vp_cand_vpids, G: int, P: int) -> dict:
         """Second half of a ``defer_fuse`` navigation call: intern the viewpoint ids (host work that then overlaps the
@@ -609,6 +687,10 @@ class GlocalTextPathNavCMT(nn.Module):
         if self.config.fix_lang_inside_cosine_model:
             txt = txt.detach()
         with blocks.grad_mode(self._recording(txt, batch['align_imagine_embeds']), self._drop()):
+            if self.config.dataset == 'reverie':               # :781-888: no sub-instruction annotation, one imagination
+                B, L, _ = txt.shape
+                rows = reverie_align_rows(B, L, batch['align_imagine_embeds'].shape[1], batch['txt_masks'])
+                return align_forward(self, txt, batch['align_imagine_embeds'], None, None, self.lowp, rows=rows)
             return align_forward(self, txt, batch['align_imagine_embeds'], batch['sub_instr_imag_flag'],
                                  batch['noun_phrase_segs'], self.lowp)
 

@@ -156,6 +156,11 @@ class DuetImageEmbeddingsP(_Container):
         self.img_layer_norm = nn.LayerNorm(H, eps=1e-12)
         self.loc_linear = nn.Linear(cfg.angle_feat_size + 3, H)
         self.loc_layer_norm = nn.LayerNorm(H, eps=1e-12)
+        if cfg.obj_feat_size > 0 and cfg.obj_feat_size != cfg.image_feat_size:      # :464-468 (REVERIE / SOON object boxes)
+            self.obj_linear = nn.Linear(cfg.obj_feat_size, H)
+            self.obj_layer_norm = nn.LayerNorm(H, eps=1e-12)
+        else:
+            self.obj_linear = self.obj_layer_norm = None
         self.nav_type_embedding = nn.Embedding(3, H)
         self.layer_norm = nn.LayerNorm(H, eps=1e-12)
         self.pano_encoder = PanoEncoderP(cfg.num_pano_layers)

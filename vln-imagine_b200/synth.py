@@ -233,6 +233,49 @@ def duet_episode(shape: EpisodeShape, seed: int = 1234) -> dict:
     return ep
 
 
+def duet_reverie_episode(shape: EpisodeShape, seed: int = 1234, max_objects: int = 8) -> dict:
+    """duet_episode in the shape the REVERIE agent collates (VLN-DUET/map_nav_src/reverie/agent_obj.py:50-212): a ragged
+    number of object boxes per panorama ([views ; objects] per episode, nav_type 2 for objects, zero padded to the longest),
+    the matching local tokens with ``vp_obj_masks``, and ONE imagination per instruction (imagine tensors [B, 1, ...])."""
+    ep = duet_episode(shape, seed)
+    B, V = shape.batch, shape.n_views
+    g = _rng(seed, 'duet_reverie')
+    view_lens, n_cand = ep['view_lens'], ep['n_cand']
+    obj_lens = g.integers(0, max_objects + 1, size=B).astype(np.int64)
+    obj_lens[0], obj_lens[-1] = 0, max_objects                 # an episode without objects and a full one
+    O = int(obj_lens.max())
+    obj_img_fts = g.standard_normal((B, O, 768), dtype=np.float32)
+    obj_img_fts[~_mask_from_lens(obj_lens, O)] = 0
+    pano_lens = view_lens + obj_lens
+    P = int(pano_lens.max())
+    loc_fts = np.zeros((B, P, 7), np.float32)
+    nav_types = np.zeros((B, P), np.int64)
+    obj_loc = _rel_pos7(g, (B, max(O, 1)))
+    for b in range(B):
+        vl, ol = int(view_lens[b]), int(obj_lens[b])
+        loc_fts[b, :vl] = ep['loc_fts'][b, :vl]
+        loc_fts[b, vl:vl + ol] = obj_loc[b, :ol]
+        nav_types[b, :vl] = ep['nav_types'][b, :vl]
+        nav_types[b, vl:vl + ol] = 2
+    ep.update(obj_img_fts=obj_img_fts, obj_lens=obj_lens, loc_fts=loc_fts, nav_types=nav_types)
+    vp_masks = _mask_from_lens(pano_lens + 1, P + 1)
+    vp_img_embeds = g.standard_normal((B, P + 1, 768), dtype=np.float32)
+    vp_img_embeds[:, 0] = 0
+    vp_img_embeds[~vp_masks] = 0
+    vp_pos_fts = np.zeros((B, P + 1, 14), np.float32)
+    vp_pos_fts[:, :, :7] = ep['vp_pos_fts'][:, :1, :7]
+    for b in range(B):
+        vp_pos_fts[b, 1:1 + n_cand[b], 7:] = ep['vp_pos_fts'][b, 1:1 + n_cand[b], 7:]
+    ep.update(vp_img_embeds=vp_img_embeds, vp_pos_fts=vp_pos_fts, vp_masks=vp_masks,
+              vp_nav_masks=np.concatenate([np.ones((B, 1), bool), nav_types == 1], 1),
+              vp_obj_masks=np.concatenate([np.zeros((B, 1), bool), nav_types == 2], 1))
+    ep['imagine_feats'] = g.standard_normal((B, 1, 768), dtype=np.float32)
+    ep['imagine_masks'] = np.ones((B, 1), bool)
+    for k in ('sub_instr_imag_flag', 'sub_instr_segs', 'noun_phrase_segs'):      # REVERIE has no sub-instruction annotation
+        ep.pop(k)
+    return ep
+
+
 # ----------------------------------------------------------------------------------------------
 # HAMT inputs
 # ----------------------------------------------------------------------------------------------
