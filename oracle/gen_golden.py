@@ -459,6 +459,45 @@ def run_duet_reverie(args):
         json.dump(report, f, indent=1)
 
 
+def run_duet_soon(args):
+    """The model side of the SOON recipe (scripts/run_soon.sh): 2048-d butd object boxes through their own obj_linear /
+    obj_layer_norm (models/vilmodel.py:464-468), object-grounding head, NO imagination (imagine_enc_pano off)."""
+    from importlib import import_module
+    synth = import_module('vln_imagine_b200.synth')
+    from oracle import duet_oracle as O
+    ref = build_reference('duet', dict(dataset='soon', obj_feat_size=2048, imagine_enc_pano=False))
+    manifest = {k: list(v.shape) for k, v in ref.state_dict().items()}
+    with open(os.path.join(GOLD, 'duet_soon_manifest.json'), 'w') as f:
+        json.dump(manifest, f, indent=0)
+    sd = synth.synth_state_dict(manifest, seed=0, gasa_stress=True)
+    ref.load_state_dict(sd)
+    ep = synth.to_torch(synth.duet_reverie_episode(synth.TINY, 9, obj_dim=2048))
+    with torch.no_grad():
+        txt = ref('language', {'txt_ids': ep['txt_ids'], 'txt_masks': ep['txt_masks']})
+        pano, pano_masks = ref('panorama', {k: ep[k] for k in ('view_img_fts', 'obj_img_fts', 'loc_fts', 'nav_types', 'view_lens', 'obj_lens')})
+        nav = ref('navigation', {**{k: ep[k] for k in (
+            'txt_masks', 'gmap_img_embeds', 'gmap_step_ids', 'gmap_pos_fts', 'gmap_masks', 'gmap_pair_dists', 'gmap_visited_masks',
+            'gmap_vpids', 'vp_img_embeds', 'vp_pos_fts', 'vp_masks', 'vp_nav_masks', 'vp_obj_masks', 'vp_cand_vpids')}, 'txt_embeds': txt})
+        o_txt = O.forward_text(sd, ep['txt_ids'], ep['txt_masks'])
+        o_pano, o_pm = O.forward_panorama(sd, ep['view_img_fts'], ep['loc_fts'], ep['nav_types'], ep['view_lens'],
+                                          obj_img_fts=ep['obj_img_fts'], obj_lens=ep['obj_lens'])
+        B = ep['txt_ids'].shape[0]
+        o_nav = O.forward_navigation(
+            sd, o_txt, ep['txt_masks'], ep['gmap_img_embeds'], ep['gmap_step_ids'], ep['gmap_pos_fts'], ep['gmap_masks'],
+            ep['gmap_pair_dists'], ep['gmap_visited_masks'], ep['gmap_vpids'], ep['vp_img_embeds'], ep['vp_pos_fts'], ep['vp_masks'],
+            ep['vp_nav_masks'], ep['vp_cand_vpids'], torch.zeros(B, 0, 768), torch.zeros(B, 0, dtype=torch.bool),
+            vp_obj_masks=ep['vp_obj_masks'])
+    diffs = {'pano': maxdiff(pano, o_pano), 'fused': maxdiff(nav['fused_logits'], o_nav['fused_logits']),
+             'obj': maxdiff(nav['obj_logits'], o_nav['obj_logits']), 'vp': maxdiff(nav['vp_embeds'], o_nav['vp_embeds'])}
+    print('soon', json.dumps(diffs))
+    assert torch.equal(pano_masks, o_pm) and max(diffs.values()) < 2e-4
+    np.savez(os.path.join(GOLD, 'duet_soon_tiny.npz'), **_np(dict(
+        pano_embeds=pano, pano_masks=pano_masks, vp_embeds=nav['vp_embeds'], fused_logits=nav['fused_logits'],
+        local_logits=nav['local_logits'], global_logits=nav['global_logits'], obj_logits=nav['obj_logits'])))
+    with open(os.path.join(GOLD, 'duet_soon_oracle_vs_reference.json'), 'w') as f:
+        json.dump({'tiny': diffs}, f, indent=1)
+
+
 def run_hamt_actpred(args):
     """act_pred_token variants of HAMT's action head (r2r/parser.py:67, models/vilmodel_cmt.py:1189-1199) with the imagination
     tokens on either stream: only the logits change."""
@@ -531,7 +570,7 @@ def run_hamt_margin(args):
 
 if __name__ == '__main__':
     ap = argparse.ArgumentParser()
-    ap.add_argument('--model', choices=['duet', 'hamt', 'hamt_encvis', 'hamt_margin', 'hamt_actpred', 'duet_reverie'], required=True)
+    ap.add_argument('--model', choices=['duet', 'hamt', 'hamt_encvis', 'hamt_margin', 'hamt_actpred', 'duet_reverie', 'duet_soon'], required=True)
     ap.add_argument('--grads', action='store_true', help='write the gradient fixtures (cfg-4) instead')
     a = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
@@ -539,4 +578,4 @@ if __name__ == '__main__':
     if a.grads:
         (run_duet_grads if a.model == 'duet' else run_hamt_grads)(a)
     else:
-        {'duet': run_duet, 'hamt': run_hamt, 'hamt_encvis': run_hamt_encvis, 'hamt_margin': run_hamt_margin, 'hamt_actpred': run_hamt_actpred, 'duet_reverie': run_duet_reverie}[a.model](a)
+        {'duet': run_duet, 'hamt': run_hamt, 'hamt_encvis': run_hamt_encvis, 'hamt_margin': run_hamt_margin, 'hamt_actpred': run_hamt_actpred, 'duet_reverie': run_duet_reverie, 'duet_soon': run_duet_soon}[a.model](a)

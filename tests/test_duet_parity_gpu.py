@@ -252,3 +252,29 @@ def test_duet_reverie_recipe_vs_reference_golden(lib_built, tag, shape, seed, pr
     assert max_rel(nce_img2, gold_nce['aligned_imagine_embeds']) < tol
     if precision == 'fp32':
         assert torch.equal(nav['obj_logits'].cpu().argmax(-1), gold['obj_logits'].argmax(-1))
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_duet_soon_model_side_vs_reference_golden(lib_built, precision):
+    """The model side of scripts/run_soon.sh: 2048-d object boxes through their own obj_linear / obj_layer_norm
+    (models/vilmodel.py:464-468), the object-grounding head, and NO imagination (plain DUET context = the instruction)."""
+    synth = importlib.import_module('vln_imagine_b200.synth')
+    duet = importlib.import_module('vln_imagine_b200.duet')
+    config = importlib.import_module('vln_imagine_b200.config')
+    model = duet.VLNBert(config.default_duet_args(dataset='soon', obj_feat_size=2048, imagine_enc_pano=False)).cuda().eval()
+    model.vln_bert.load_state_dict(synth.synth_state_dict(manifest('duet_soon'), seed=0, gasa_stress=True))
+    model.vln_bert.precision = precision
+    ep = to_dev(synth.to_torch(synth.duet_reverie_episode(synth.TINY, 9, obj_dim=2048)))
+    gold = golden('duet_soon_tiny')
+    with torch.no_grad():
+        txt = model('language', {'txt_ids': ep['txt_ids'], 'txt_masks': ep['txt_masks']})
+        pano, pano_masks = model('panorama', {k: ep[k] for k in ('view_img_fts', 'obj_img_fts', 'loc_fts', 'nav_types', 'view_lens', 'obj_lens')})
+        nav = model('navigation', {**{k: ep[k] for k in (
+            'txt_masks', 'gmap_img_embeds', 'gmap_step_ids', 'gmap_pos_fts', 'gmap_masks', 'gmap_pair_dists', 'gmap_visited_masks',
+            'gmap_vpids', 'vp_img_embeds', 'vp_pos_fts', 'vp_masks', 'vp_nav_masks', 'vp_obj_masks', 'vp_cand_vpids')}, 'txt_embeds': txt})
+    tol = TOL[precision]
+    assert torch.equal(pano_masks.cpu(), gold['pano_masks'])
+    valid = gold['pano_masks'][:, :, None]
+    assert max_rel(pano.cpu() * valid, gold['pano_embeds'] * valid) < tol
+    for k in ('vp_embeds', 'fused_logits', 'local_logits', 'global_logits', 'obj_logits'):
+        assert max_rel(nav[k], gold[k]) < tol, k

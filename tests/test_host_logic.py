@@ -106,8 +106,12 @@ def test_parameter_tree_of_the_duet_reverie_recipe():
     sd = m.vln_bert.state_dict()
     assert set(sd) == set(man) and all(list(sd[k].shape) == man[k] for k in man)
     assert 'og_head.net.3.weight' in sd and not any(k.startswith('img_embeddings.obj_linear') for k in sd)
-    m2 = importlib.import_module('vln_imagine_b200.duet').VLNBert(config.default_duet_args(dataset='reverie', obj_feat_size=2048))
-    assert list(m2.vln_bert.state_dict()['img_embeddings.obj_linear.weight'].shape) == [768, 2048]
+    m2 = importlib.import_module('vln_imagine_b200.duet').VLNBert(
+        config.default_duet_args(dataset='soon', obj_feat_size=2048, imagine_enc_pano=False))       # scripts/run_soon.sh
+    man2 = manifest('duet_soon')
+    sd2 = m2.vln_bert.state_dict()
+    assert set(sd2) == set(man2) and all(list(sd2[k].shape) == man2[k] for k in man2)
+    assert list(sd2['img_embeddings.obj_linear.weight'].shape) == [768, 2048] and not any('imagine' in k for k in sd2)
 
 
 def test_freeze_flags_follow_the_reference():

@@ -132,6 +132,27 @@ def test_duet_reverie_oracle_matches_reference_golden(tag, shape, seed):
     assert max_rel(nce_img2, gold_nce['aligned_imagine_embeds']) < 1e-5
 
 
+def test_duet_soon_model_side_oracle_matches_reference_golden():
+    """scripts/run_soon.sh on the model side: 2048-d object boxes through obj_linear / obj_layer_norm, no imagination"""
+    from oracle import duet_oracle as O
+    rep = json.load(open(os.path.join(GOLDEN, 'duet_soon_oracle_vs_reference.json')))
+    assert max(rep['tiny'].values()) < 2e-4
+    sd = synth.synth_state_dict(manifest('duet_soon'), seed=0, gasa_stress=True)
+    ep = synth.to_torch(synth.duet_reverie_episode(synth.TINY, 9, obj_dim=2048))
+    gold = golden('duet_soon_tiny')
+    B = ep['txt_ids'].shape[0]
+    with torch.no_grad():
+        txt = O.forward_text(sd, ep['txt_ids'], ep['txt_masks'])
+        pano, pano_masks = O.forward_panorama(sd, ep['view_img_fts'], ep['loc_fts'], ep['nav_types'], ep['view_lens'],
+                                              obj_img_fts=ep['obj_img_fts'], obj_lens=ep['obj_lens'])
+        nav = O.forward_navigation(sd, txt, ep['txt_masks'], ep['gmap_img_embeds'], ep['gmap_step_ids'], ep['gmap_pos_fts'],
+                                   ep['gmap_masks'], ep['gmap_pair_dists'], ep['gmap_visited_masks'], ep['gmap_vpids'],
+                                   ep['vp_img_embeds'], ep['vp_pos_fts'], ep['vp_masks'], ep['vp_nav_masks'], ep['vp_cand_vpids'],
+                                   torch.zeros(B, 0, 768), torch.zeros(B, 0, dtype=torch.bool), vp_obj_masks=ep['vp_obj_masks'])
+    for k, v in dict(pano_embeds=pano, vp_embeds=nav['vp_embeds'], fused_logits=nav['fused_logits'], obj_logits=nav['obj_logits']).items():
+        assert max_rel(v, gold[k]) < 1e-5, k
+
+
 def test_hamt_action_token_variants_oracle_matches_reference_golden():
     from oracle import hamt_oracle as O
     rep = json.load(open(os.path.join(GOLDEN, 'hamt_actpred_oracle_vs_reference.json')))

@@ -233,7 +233,7 @@ def duet_episode(shape: EpisodeShape, seed: int = 1234) -> dict:
     return ep
 
 
-def duet_reverie_episode(shape: EpisodeShape, seed: int = 1234, max_objects: int = 8) -> dict:
+def duet_reverie_episode(shape: EpisodeShape, seed: int = 1234, max_objects: int = 8, obj_dim: int = 768) -> dict:
     """duet_episode in the shape the REVERIE agent collates (VLN-DUET/map_nav_src/reverie/agent_obj.py:50-212): a ragged
     number of object boxes per panorama ([views ; objects] per episode, nav_type 2 for objects, zero padded to the longest),
     the matching local tokens with ``vp_obj_masks``, and ONE imagination per instruction (imagine tensors [B, 1, ...])."""
@@ -244,7 +244,7 @@ def duet_reverie_episode(shape: EpisodeShape, seed: int = 1234, max_objects: int
     obj_lens = g.integers(0, max_objects + 1, size=B).astype(np.int64)
     obj_lens[0], obj_lens[-1] = 0, max_objects                 # an episode without objects and a full one
     O = int(obj_lens.max())
-    obj_img_fts = g.standard_normal((B, O, 768), dtype=np.float32)
+    obj_img_fts = g.standard_normal((B, O, obj_dim), dtype=np.float32)     # 768: REVERIE ViT boxes; 2048: SOON butd boxes
     obj_img_fts[~_mask_from_lens(obj_lens, O)] = 0
     pano_lens = view_lens + obj_lens
     P = int(pano_lens.max())
