@@ -548,6 +548,7 @@ def main():
     dev = torch.device('cuda', local_rank)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
+    from vln_imagine_b200 import graphs as vgraphs
     from vln_imagine_b200 import ops
 
     def barrier():
@@ -611,7 +612,7 @@ def main():
                 if first:
                     new_episode()                           # the capture then contains the context projections
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
+                with vgraphs.capture(g):
                     step_fn(model, d, txt, img2)
                 return g
             g_later = capture(False)

@@ -253,9 +253,8 @@ def _ctx_buffer(rows: int, like: torch.Tensor, streams) -> torch.Tensor:
     ctx = torch.empty((rows, HIDDEN), dtype=like.dtype, device=like.device)
     for r0, r1 in pads:
         ctx[r0:r1].zero_()
-    if key is not None and not torch.cuda.is_current_stream_capturing():      # never keep memory of a graph's private pool
-        if len(_CTX_BUFFERS) > 64:
-            _CTX_BUFFERS.clear()
+    # never keep memory of a graph's private pool, and never evict: captured graphs hold raw pointers to these buffers
+    if key is not None and not torch.cuda.is_current_stream_capturing() and len(_CTX_BUFFERS) < 256:
         _CTX_BUFFERS[key] = ctx
     return ctx
 

@@ -14,9 +14,28 @@ Nothing here is used when autograd is recording.
 from __future__ import annotations
 
 import collections
+import contextlib
+import gc
 from typing import Callable, Dict
 
 import torch
+
+
+@contextlib.contextmanager
+def capture(graph: 'torch.cuda.CUDAGraph', **kw):
+    """``torch.cuda.graph`` with the cyclic garbage collector held off.  A GC pass in the middle of a capture may free dead
+    modules that own CUDAGraphs (GraphedCall <-> module cycles are only reclaimed by the cyclic collector); destroying a graph
+    or releasing its memory pool is "not permitted when stream is capturing" and invalidates the capture in progress.  PyTorch
+    no longer collects before a capture (torch.compiler.config.force_cudagraph_gc), so it is done here."""
+    gc.collect()
+    enabled = gc.isenabled()
+    gc.disable()
+    try:
+        with torch.cuda.graph(graph, **kw):
+            yield
+    finally:
+        if enabled:
+            gc.enable()
 
 
 class GraphedCall:
@@ -70,7 +89,7 @@ class GraphedCall:
                 self.fn(static_in)                           # once more on the side stream (allocator warm-up)
             torch.cuda.current_stream(device).wait_stream(side)
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            with capture(graph):
                 static_out = self.fn(static_in)
             ent.update(graph=graph, static_in=static_in, static_out=static_out)
         static_in = ent['static_in']

@@ -18,6 +18,8 @@ from typing import Iterable, List, Optional
 import torch
 import torch.distributed as dist
 
+from . import graphs
+
 
 class FlatGradients:
     """All trainable parameters' gradients in ONE contiguous fp32 buffer (parameter order = ``named_parameters()``
@@ -148,17 +150,17 @@ class GraphedIteration:
         torch.cuda.synchronize(dev)
         self._invalidate_packs()                              # graph 1 must contain the weight re-cast
         self.g_grad = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.g_grad):
+        with graphs.capture(self.g_grad):
             self.loss = grad_fn(static_inputs)
         if between is not None:
             between()
         self.g_update = torch.cuda.CUDAGraph()
         import os
         if os.environ.get('VI_TRAIN_SHARED_POOL', '0') == '1':
-            with torch.cuda.graph(self.g_update, pool=self.g_grad.pool()):
+            with graphs.capture(self.g_update, pool=self.g_grad.pool()):
                 update_fn()
         else:
-            with torch.cuda.graph(self.g_update):
+            with graphs.capture(self.g_update):
                 update_fn()
 
     def _invalidate_packs(self):
