@@ -114,6 +114,26 @@ def test_parameter_tree_of_the_duet_reverie_recipe():
     assert list(sd2['img_embeddings.obj_linear.weight'].shape) == [768, 2048] and not any('imagine' in k for k in sd2)
 
 
+def test_reverie_align_rows_and_lazy_vpid_rows():
+    """host-side index builders: REVERIE alignment rows (all valid instruction tokens, slot 0, other episodes as negatives) and the
+    lazily materialised viewpoint-id rows DeviceGraphMaps hands to the agent"""
+    import numpy as np
+    duet = importlib.import_module('vln_imagine_b200.duet')
+    masks = torch.tensor([[1, 1, 1, 0, 0], [1, 1, 1, 1, 1], [1, 0, 1, 0, 0]], dtype=torch.bool)
+    r = duet.reverie_align_rows(3, 5, 1, masks)
+    assert r.R == 3 and r.n_negs == 3 and r.slot.tolist() == [0, 1, 2] and r.ep.tolist() == r.np_ep.tolist() == [0, 1, 2]
+    assert r.tok_off.tolist() == [0, 3, 8, 10] and r.tok_rows.tolist() == [0, 1, 2, 5, 6, 7, 8, 9, 10, 12]
+    assert r.np_rows.tolist() == r.tok_rows.tolist() and r.np_off.tolist() == r.tok_off.tolist()
+    with pytest.raises(ValueError):
+        duet.reverie_align_rows(1, 3, 1, torch.zeros(1, 3, dtype=torch.bool))
+    gm = importlib.import_module('vln_imagine_b200.graph_map')
+    names = [['a', 'b', 'c'], ['x', 'y']]
+    nodes = np.array([[-1, 1, 0, 2], [-1, 0, 1, -1]], np.int32)
+    rows = gm.VpidRows(names, nodes, np.array([4, 3], np.int32), torch.zeros(2, 4, dtype=torch.int32), -1)
+    assert len(rows) == 2 and rows[0] == [None, 'b', 'a', 'c'] and rows[1] == [None, 'x', 'y']
+    assert rows == [[None, 'b', 'a', 'c'], [None, 'x', 'y']] and list(rows)[1][2] == 'y' and rows[0] is rows[0]
+
+
 def test_freeze_flags_follow_the_reference():
     duet = importlib.import_module('vln_imagine_b200.duet')
     m = duet.VLNBert(config.default_duet_args(fix_lang_embedding=True, fix_pano_embedding=True)).vln_bert
