@@ -123,6 +123,14 @@ int vi_add_ln(const float* a, const float* b, const float* gamma, const float* b
               float* y32, void* y16, int64_t rows,
               int n_groups, const int32_t* group_row_end, vi_stream_t stream);
 
+/* EXPERIMENTAL, not on the default path: vi_gemm_bf16_tiled with the W tile shared by a cluster of two CTAs through TMA
+ * multicast (two vertically adjacent 128-row tiles per cluster; every SM pulls its X tile and HALF of the W tile per k-block).
+ * tile = 128 | 192 | 256 columns; grouped calls need every group but the last to end on a multiple of 256 rows.  Same
+ * arithmetic, operands and error behaviour as vi_gemm_bf16_tiled (csrc/vi_gemm_mc.cu; validated by tools/gemm_mc_check.py). */
+int vi_gemm_bf16_mc(const void* x, int64_t ldx, const void* w, const float* bias, const float* residual, int64_t ldr,
+                    void* y, int64_t ldy, int y_dtype, int M, int N, int K, int epilogue, int n_groups,
+                    const int32_t* group_row_end, int tile, vi_stream_t stream);
+
 /* Row-block GEMM with the residual add and LayerNorm fused into the epilogue (N = 768 only; vi_gemm_rb.cu):
  *   pre = x w^T + bias + residual        (optional fp32 output pre32 [M, 768]: pre-norm residual stream)
  *   y   = LayerNorm(pre) * gamma + beta  (y32 fp32 and / or y16 bf16, [M, 768])

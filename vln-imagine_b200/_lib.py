@@ -50,6 +50,7 @@ PROTOTYPES = {
     'vi_init': [_i],
     'vi_gemm_bf16': [_p, _l, _p, _p, _p, _l, _p, _l, _i, _i, _i, _i, _i, _i, _ip, _p],
     'vi_gemm_bf16_tiled': [_p, _l, _p, _p, _p, _l, _p, _l, _i, _i, _i, _i, _i, _i, _ip, _i, _p],
+    'vi_gemm_bf16_mc': [_p, _l, _p, _p, _p, _l, _p, _l, _i, _i, _i, _i, _i, _i, _ip, _i, _p],
     'vi_gemm_ln_bf16': [_p, _l, _p, _p, _p, _l, _p, _p, _f, _p, _p, _p, _i, _i, _i, _ip, _p],
     'vi_gemm_f32': [_p, _l, _p, _p, _p, _l, _p, _l, _i, _i, _i, _i, _i, _ip, _p],
     'vi_attn_fwd': [_p, _l, _p, _l, _p, _l, _p, _l, _i, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p],

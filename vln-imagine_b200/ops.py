@@ -203,6 +203,23 @@ def gemm(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None,
     return out
 
 
+def gemm_mc(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
+            epilogue: int = EPI_NONE, out_dtype: torch.dtype = BF16, group_row_end: Optional[Sequence[int]] = None,
+            tile: int = 256) -> torch.Tensor:
+    """EXPERIMENTAL: ``gemm`` through vi_gemm_bf16_mc (W tile multicast across a 2-CTA cluster).  Not used by the model code;
+    tools/gemm_mc_check.py compares it with ``gemm`` and times both."""
+    M, K, ldx = _rows2d(x, 'x')
+    n_groups = 1 if group_row_end is None else len(group_row_end)
+    N = w.shape[0] // n_groups
+    out = torch.empty((M, N), dtype=out_dtype, device=x.device)
+    ends = _lib.int_array(list(group_row_end)) if group_row_end is not None else None
+    check(lib.vi_gemm_bf16_mc(x.data_ptr(), ldx, w.data_ptr(), _ptr(bias), _ptr(residual), residual.stride(0) if residual is not None else 0,
+                              out.data_ptr(), out.stride(0), _lib.DT_F32 if out_dtype == F32 else _lib.DT_BF16, M, N, K, epilogue,
+                              n_groups, ends, tile, _stream()), 'vi_gemm_bf16_mc')
+    _launched(1)
+    return out
+
+
 def fused_ln_enabled() -> bool:
     """vi_gemm_ln_bf16 (cluster GEMM with residual + LayerNorm in the epilogue) is correct (tests/test_kernels_gpu.py::
     test_gemm_ln_rowblock) but not yet faster than the tuned GEMM + row kernel it replaces (B200, M = 4416: 44.9 vs 17.1 us
