@@ -27,6 +27,19 @@ def timeit(fn, n=20):
     return e0.elapsed_time(e1) / n * 1e3
 
 
+if '--gelu' in sys.argv:
+    # what does the erf-GELU epilogue cost?  Same kernel, same shape, epilogue none / erf form / one-MUFU tanh form
+    M, N, K = 4416, 3072, 768
+    x = torch.randn(M, K, device='cuda').bfloat16()
+    w = (torch.randn(N, K, device='cuda') * 0.05).bfloat16()
+    b = torch.randn(N, device='cuda')
+    ys = {e: ops.gemm_mc(x, w, b, epilogue=e, tile=256) for e in (0, 1, 3)}
+    ts = {e: timeit(lambda e=e: ops.gemm_mc(x, w, b, epilogue=e, tile=256)) for e in (0, 1, 3)}
+    d = (ys[1].float() - ys[3].float()).abs()
+    print('FFN1 shape, multicast kernel: no activation %.1f us, erf GELU %.1f us, tanh-form GELU %.1f us; erf vs tanh outputs: '
+          'max |diff| %.3g, %.2f %% of the bf16 outputs differ' % (ts[0], ts[1], ts[3], float(d.max()), 100 * float((d > 0).float().mean())))
+    sys.exit(0)
+
 CASES = [  # name, M, N, K, epilogue, residual, f32 out, row groups, tile
     ('odd sizes', 300, 256, 128, 0, False, False, None, 128),
     ('one row', 1, 128, 64, 2, False, True, None, 128),

@@ -1,19 +1,19 @@
-// vi_gemm_mc.cu - EXPERIMENTAL (opt-in, VLN_IMAGINE_GEMM_MC=1): the tcgen05 GEMM of vi_gemm_tc.cu with the weight tile shared
-// across a thread-block cluster by TMA multicast.
+// vi_gemm_mc.cu - EXPERIMENTAL, not on the default path: the tcgen05 GEMM of vi_gemm_tc.cu with the weight tile shared across
+// a thread-block cluster by TMA multicast.  Kept as the measurement instrument it was built to be.
 //
-// Why: the wide GEMMs of the navigation step (FFN1, QKV, FFN2, context K | V) are bound by operand delivery into the SMs, not by
-// the tensor pipe or the L2 slices (profiles/r01b_gemm_source_level.md: a 128 x 256 tile pulls 48 KB per k-block per SM, the
-// launch runs at ~70 % of the chip-wide TMA throughput while the tensor pipe is 41 % active).  Here a cluster of TWO CTAs works
-// on two vertically adjacent 128-row tiles of the same BN columns: both need the same W tile, so each CTA TMA-loads HALF of it
-// and multicasts that half into the shared memory of both (cp.async.bulk.tensor ... .multicast::cluster).  Every SM then pulls
-// 16 KB (its X tile) + BN / 2 x 128 B (its half of W) per k-block: 32 KB instead of 48 KB at BN = 256.
+// Hypothesis it tested: the wide GEMMs of the navigation step (FFN1, QKV, FFN2, context K | V) are bound by operand delivery into
+// the SMs (profiles/r01b_gemm_source_level.md: a 128 x 256 tile pulls 48 KB per k-block per SM; tensor pipe 41 % active).  Here a
+// cluster of TWO CTAs works on two vertically adjacent 128-row tiles of the same BN columns: both need the same W tile, so each
+// CTA TMA-loads HALF of it and multicasts that half into the shared memory of both (cp.async.bulk.tensor ... .multicast::cluster).
+// Every SM then pulls 16 KB (its X tile) + BN / 2 x 128 B (its half of W) per k-block: 32 KB instead of 48 KB at BN = 256.
 //   * each CTA issues its own cta_group::1 MMAs (M = 128, N = BN) on the full W tile the two halves form in ITS shared memory;
 //   * a ring slot is recycled when BOTH CTAs' MMAs on it have retired: every MMA warp commits with a multicast arrive on the
 //     "empty" barrier of both CTAs (count 2) - the scheme vi_gemm_rb.cu already uses for its activation tile;
 //   * accumulators, epilogue (bias, GELU / ReLU, TMA-fetched fp32 residual, swizzled staging, TMA store) and the tile walk are
 //     those of the CTA-pair mode of vi_gemm_tc.cu: a cluster walks 256-row x BN tiles, rank r owns rows [128 r, 128 r + 128).
-// Same arithmetic and operand conventions as vi_gemm_bf16_tiled.  Not on the default path: compiled and exported so that it can be
-// validated and tuned against the measured tile table (tools/gemm_mc_check.py) before it becomes a tile candidate.
+// Result on B200 (tools/gemm_mc_check.py): bit-identical to vi_gemm_bf16_tiled on every shape and 3-13 % SLOWER - halving the W
+// traffic per SM buys nothing, so operand delivery is not the bound.  The same kernel, FFN1 shape, isolates the activation:
+// no activation 20.5 us, erf-form GELU 27.0 us, one-MUFU tanh-form GELU 21.9 us (`--gelu`).
 #include "vi_common.cuh"
 
 #include <mutex>
@@ -66,6 +66,16 @@ __device__ __forceinline__ float gelu_fast(float x) {      // as in vi_gemm_tc.c
   poly *= t;
   const float erf_abs = fmaf(-poly, __expf(-z * z), 1.0f);
   return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+}
+// one-MUFU GELU (tanh form) - measurement only (epilogue code 3 of THIS kernel, tools/gemm_mc_check.py --gelu): its distance from
+// the erf form (< 5e-4 absolute) is below the bf16 rounding of the output, but whether it may replace the erf form is a parity
+// decision for the default kernel, not taken here
+__device__ __forceinline__ float gelu_tanh_fast(float x) {
+  const float u = x * fmaf(0.0356774081f, x * x, 0.7978845608f);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+  const float h = 0.5f * x;
+  return fmaf(h, t, h);
 }
 __device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
@@ -316,6 +326,9 @@ gemm_bf16_mc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           } else if (p.epilogue == VI_EPI_RELU) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+          } else if (p.epilogue == 3) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = gelu_tanh_fast(v[j]);
           }
           __syncwarp();
           if (res) {
@@ -471,7 +484,7 @@ extern "C" int vi_gemm_bf16_mc(const void* x, int64_t ldx, const void* w, const 
   VI_CHECK_ARG(!residual || (y_dtype == VI_DT_F32 && ldr >= N && ldr % 4 == 0 && ((uintptr_t)residual & 15) == 0),
                "vi_gemm_bf16_mc: a residual needs an fp32 output, ldr >= N, 16-byte alignment");
   VI_CHECK_ARG(y_dtype == VI_DT_BF16 || y_dtype == VI_DT_F32, "vi_gemm_bf16_mc: bad y_dtype %d", y_dtype);
-  VI_CHECK_ARG(epilogue >= VI_EPI_NONE && epilogue <= VI_EPI_RELU, "vi_gemm_bf16_mc: bad epilogue %d", epilogue);
+  VI_CHECK_ARG(epilogue >= VI_EPI_NONE && epilogue <= 3, "vi_gemm_bf16_mc: bad epilogue %d (3 = tanh-form GELU, measurement only)", epilogue);
   VI_CHECK_ARG(n_groups >= 1 && n_groups <= MAX_GROUPS && (n_groups == 1 || group_row_end), "vi_gemm_bf16_mc: bad row groups");
   if (int rc = resolve_encode()) return rc;
 
