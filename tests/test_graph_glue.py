@@ -80,6 +80,74 @@ def test_graph_oracle_edge_cases():
     assert st.distance(0, 1) == 5.0 and st.distance(1, 2) == GO.UNREACHED and st.path_len(1, 2) == 1
 
 
+def test_device_graph_maps_host_bookkeeping_without_a_gpu(monkeypatch):
+    """The host side of DeviceGraphMaps (viewpoint interning, [stop] + visited + unvisited ordering, step ids, masks, the id
+    tensors handed to the fusion kernel, the index arrays the kernels receive) against the oracle, with the library calls
+    stubbed out: everything that is NOT arithmetic is checked on the CPU."""
+    from oracle import graph_oracle as GO
+    gm_mod = importlib.import_module('vln_imagine_b200.graph_map')
+    ops = importlib.import_module('vln_imagine_b200.ops')
+
+    calls = []
+
+    class FakeLib:
+        def __getattr__(self, name):
+            def f(*a):
+                calls.append(name)
+                return 0
+            return f
+    monkeypatch.setattr(gm_mod, 'lib', FakeLib())
+    monkeypatch.setattr(ops, 'ensure_init', lambda t: None)
+    monkeypatch.setattr(ops, '_stream', lambda: 0)
+    monkeypatch.setattr(ops, '_launched', lambda n: None)
+    monkeypatch.setattr(torch.Tensor, 'pin_memory', lambda self: self)
+    packed = {}
+    real_pack = gm_mod._pack
+
+    def spy_pack(staging, device, arrays):
+        packed.update({k: np.array(v) for k, v in arrays.items()})
+        return real_pack(staging, device, arrays)
+    monkeypatch.setattr(gm_mod, '_pack', spy_pack)
+
+    world = synth.nav_world(seed=31, n_vp=40, batch=5, steps=6, hidden=8)
+    gm = gm_mod.DeviceGraphMaps(world[0]['obs'], 'cpu', hidden=8)
+    for t, step, og, ov in _oracle_rollout(world, 8):
+        obs, ended = step['obs'], step['ended']
+        gm.set_step_ids(obs, t, ended)
+        pano = torch.from_numpy(step['pano_embeds'])
+        pin = {'cand_vpids': [[c['viewpointId'] for c in ob['candidate']] for ob in obs],
+               'view_lens': torch.from_numpy(step['view_lens']), 'nav_types': torch.from_numpy(step['nav_types'])}
+        out = gm.nav_inputs(obs, pano, torch.ones(pano.shape[:2], dtype=torch.bool), pin, ended)
+        B, G = og['gmap_masks'].shape
+        assert out['gmap_vpids'] == og['names'] and out['no_vp_left'] == og['no_vp_left'], t
+        assert np.array_equal(out['gmap_step_ids'].numpy(), og['gmap_step_ids']), t
+        assert np.array_equal(out['gmap_visited_masks'].numpy(), og['gmap_visited_masks']), t
+        assert np.array_equal(out['gmap_masks'].numpy(), og['gmap_masks']), t
+        assert np.array_equal(out['vp_masks'].numpy(), ov['vp_masks']) and np.array_equal(out['vp_nav_masks'].numpy(), ov['vp_nav_masks']), t
+        assert out['vp_cand_vpids'] == [[None] + c for c in pin['cand_vpids']], t
+        # index arrays the kernels receive: node order, candidates, current / start nodes, lengths
+        assert np.array_equal(packed['gnode'], og['gmap_nodes']) and np.array_equal(packed['lens'], og['gmap_lens']), t
+        assert packed['cur'].tolist() == [(-1 if e else gm.index[b][ob['viewpoint']]) for b, (ob, e) in enumerate(zip(obs, ended))], t
+        assert packed['start'].tolist() == [gm.index[b][gm.start_vps[b]] for b in range(B)], t
+        for b, vps in enumerate(pin['cand_vpids']):
+            assert packed['cand'][b, :len(vps)].tolist() == [gm.index[b][v] for v in vps] and (packed['cand'][b, len(vps):] == -1).all(), t
+        # interned ids for the fusion kernel: equal strings <-> equal ids inside an episode, [stop] and padding as documented
+        gids, cids = out['gmap_vpids'].ids.numpy(), out['vp_cand_vpids'].ids.numpy()
+        assert (gids[:, 0] == gm_mod.STOP_ID).all() and (cids[:, 0] == gm_mod.STOP_ID).all()
+        for b in range(B):
+            row = og['names'][b]
+            assert (gids[b, len(row):] == -1).all() and (cids[b, 1 + len(pin['cand_vpids'][b]):] == -2).all()
+            for j, vp in enumerate(row[1:], 1):
+                for k, cvp in enumerate(pin['cand_vpids'][b], 1):
+                    assert (gids[b, j] == cids[b, k]) == (vp == cvp)
+        if t + 1 < len(world):
+            gm.update_graph(world[t + 1]['obs'], ended)
+            nxt = world[t + 1]['obs']
+            assert packed['cur'].tolist() == [(-1 if e else gm.index[b][ob['viewpoint']]) for b, (ob, e) in enumerate(zip(nxt, ended))]
+            assert packed['n_nodes'].tolist() == [len(n) for n in gm.names]
+    assert {'vi_graph_init', 'vi_graph_update', 'vi_graph_embed_step', 'vi_graph_features'} <= set(calls)
+
+
 def _run_device(world, hidden, check):
     from vln_imagine_b200 import graph_map
     dev = torch.device('cuda')
