@@ -498,6 +498,59 @@ def run_duet_soon(args):
         json.dump({'tiny': diffs}, f, indent=1)
 
 
+def run_duet_pretrain(args):
+    """DUET pre-training forward (R2R recipe: mlm + mrc + sap, VLN-DUET/pretrain_src/config/r2r_*.json) - groundwork for SURVEY 8(f) N4."""
+    from importlib import import_module
+    from transformers import BertConfig
+    synth = import_module('vln_imagine_b200.synth')
+    from oracle import pretrain_oracle as P
+    _shim_transformers()
+    src = os.path.join(REF, 'VLN-DUET', 'pretrain_src')
+    sys.path.insert(0, src)
+    from model.pretrain_cmt import GlocalTextPathCMTPreTraining as Net
+
+    def tie(self, *a, **kw):          # transformers >= 5 calls tie_weights(recompute_mapping=...); _tie_or_clone_weights is gone
+        if 'mlm' in self.config.pretrain_tasks:
+            self.mlm_head.predictions.decoder.weight = self.bert.embeddings.word_embeddings.weight
+    Net.tie_weights = tie
+    cfg = BertConfig()
+    for k, v in json.load(open(os.path.join(src, 'config', 'r2r_model_config.json'))).items():
+        setattr(cfg, k, v)
+    cfg.hidden_dropout_prob = cfg.attention_probs_dropout_prob = 0.0
+    cfg.pretrain_tasks = ['mlm', 'mrc', 'sap']
+    torch.manual_seed(0)
+    ref = Net(cfg).eval()
+    manifest = {k: list(v.shape) for k, v in ref.state_dict().items()}
+    with open(os.path.join(GOLD, 'duet_pretrain_manifest.json'), 'w') as f:
+        json.dump(manifest, f, indent=0)
+    sd = synth.synth_state_dict(manifest, seed=0, gasa_stress=False)
+    sd['mlm_head.predictions.decoder.weight'] = sd['bert.embeddings.word_embeddings.weight']        # tied
+    sd['bert.global_encoder.sprel_linear.weight'] = torch.full((1, 1), -0.3)
+    ref.load_state_dict(sd)
+    ep = synth.to_torch(synth.duet_pretrain_batch())
+    batch = dict(ep)
+    with torch.no_grad():
+        gl, ll, fl, _, _ = ref(batch, 'sap', compute_loss=False)
+        scores = ref(batch, 'mlm', compute_loss=False)
+        mlm_loss = ref(batch, 'mlm', compute_loss=True)
+        logits, targets, _, _ = ref(batch, 'mrc', compute_loss=False)
+        mrc_loss = ref(batch, 'mrc', compute_loss=True)
+        o_gl, o_ll, o_fl = P.forward_sap(sd, ep)
+        o_scores = P.forward_mlm(sd, ep)
+        o_logits, o_targets = P.forward_mrc(sd, ep)
+        o_mlm, o_mrc = P.losses(sd, ep)
+    diffs = {'global': maxdiff(gl, o_gl), 'local': maxdiff(ll, o_ll), 'fused': maxdiff(fl, o_fl), 'mlm_scores': maxdiff(scores, o_scores),
+             'mlm_loss': maxdiff(mlm_loss, o_mlm), 'mrc_logits': maxdiff(logits, o_logits), 'mrc_targets': maxdiff(targets, o_targets),
+             'mrc_loss': maxdiff(mrc_loss, o_mrc)}
+    print('duet_pretrain', json.dumps(diffs))
+    assert max(diffs.values()) < 2e-4, 'oracle does not reproduce the reference'
+    np.savez_compressed(os.path.join(GOLD, 'duet_pretrain.npz'), **_np(dict(
+        global_logits=gl, local_logits=ll, fused_logits=fl, mlm_scores=scores[:, ::64].contiguous(), mlm_loss=mlm_loss,
+        mrc_logits=logits, mrc_loss=mrc_loss)))
+    with open(os.path.join(GOLD, 'duet_pretrain_oracle_vs_reference.json'), 'w') as f:
+        json.dump(diffs, f, indent=1)
+
+
 def run_hamt_actpred(args):
     """act_pred_token variants of HAMT's action head (r2r/parser.py:67, models/vilmodel_cmt.py:1189-1199) with the imagination
     tokens on either stream: only the logits change."""
@@ -570,7 +623,7 @@ def run_hamt_margin(args):
 
 if __name__ == '__main__':
     ap = argparse.ArgumentParser()
-    ap.add_argument('--model', choices=['duet', 'hamt', 'hamt_encvis', 'hamt_margin', 'hamt_actpred', 'duet_reverie', 'duet_soon'], required=True)
+    ap.add_argument('--model', choices=['duet', 'hamt', 'hamt_encvis', 'hamt_margin', 'hamt_actpred', 'duet_reverie', 'duet_soon', 'duet_pretrain'], required=True)
     ap.add_argument('--grads', action='store_true', help='write the gradient fixtures (cfg-4) instead')
     a = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
@@ -578,4 +631,4 @@ if __name__ == '__main__':
     if a.grads:
         (run_duet_grads if a.model == 'duet' else run_hamt_grads)(a)
     else:
-        {'duet': run_duet, 'hamt': run_hamt, 'hamt_encvis': run_hamt_encvis, 'hamt_margin': run_hamt_margin, 'hamt_actpred': run_hamt_actpred, 'duet_reverie': run_duet_reverie, 'duet_soon': run_duet_soon}[a.model](a)
+        {'duet': run_duet, 'hamt': run_hamt, 'hamt_encvis': run_hamt_encvis, 'hamt_margin': run_hamt_margin, 'hamt_actpred': run_hamt_actpred, 'duet_reverie': run_duet_reverie, 'duet_soon': run_duet_soon, 'duet_pretrain': run_duet_pretrain}[a.model](a)

@@ -153,6 +153,27 @@ def test_duet_soon_model_side_oracle_matches_reference_golden():
         assert max_rel(v, gold[k]) < 1e-5, k
 
 
+def test_duet_pretraining_oracle_matches_reference_golden():
+    """groundwork for SURVEY 8(f) N4: the DUET pre-training forward (mlm + mrc + sap heads over whole trajectories) restated in
+    oracle/pretrain_oracle.py against outputs of the real GlocalTextPathCMTPreTraining"""
+    from oracle import pretrain_oracle as P
+    rep = json.load(open(os.path.join(GOLDEN, 'duet_pretrain_oracle_vs_reference.json')))
+    assert len(rep) == 8 and max(rep.values()) < 2e-4
+    sd = synth.synth_state_dict(manifest('duet_pretrain'), seed=0)
+    sd['mlm_head.predictions.decoder.weight'] = sd['bert.embeddings.word_embeddings.weight']
+    sd['bert.global_encoder.sprel_linear.weight'] = torch.full((1, 1), -0.3)
+    ep = synth.to_torch(synth.duet_pretrain_batch())
+    gold = golden('duet_pretrain')
+    with torch.no_grad():
+        gl, ll, fl = P.forward_sap(sd, ep)
+        scores = P.forward_mlm(sd, ep)
+        logits, _ = P.forward_mrc(sd, ep)
+        mlm, mrc = P.losses(sd, ep)
+    for k, v in dict(global_logits=gl, local_logits=ll, fused_logits=fl, mlm_scores=scores[:, ::64], mlm_loss=mlm, mrc_logits=logits,
+                     mrc_loss=mrc).items():
+        assert max_rel(v, gold[k]) < 1e-5, k
+
+
 def test_hamt_action_token_variants_oracle_matches_reference_golden():
     from oracle import hamt_oracle as O
     rep = json.load(open(os.path.join(GOLDEN, 'hamt_actpred_oracle_vs_reference.json')))

@@ -383,3 +383,103 @@ def nav_world(seed: int = 7, n_vp: int = 24, batch: int = 4, steps: int = 6, n_v
             cur[b] = pool[int(g.integers(0, len(pool)))]
             seen[b].add(cur[b])
     return out
+
+
+# ----------------------------------------------------------------------------------------------
+# DUET pre-training batches (whole trajectories; VLN-DUET/pretrain_src/data/tasks.py collate functions)
+# ----------------------------------------------------------------------------------------------
+
+def duet_pretrain_batch(seed: int = 5, batch: int = 3, n_vp: int = 20, max_steps: int = 4, n_views: int = 12, instr_len: int = 24,
+                        n_probs: int = 1000) -> dict:
+    """One synthetic pre-training batch in the layout of the reference's mlm / mrc / sap collate functions: trajectories of
+    1..max_steps panoramas flattened along dim 0 (``traj_step_lens`` splits them), the graph built from the visited viewpoints
+    and every candidate seen on the way, the last panorama as the local branch.  R2R: no object features."""
+    g = _rng(seed, 'duet_pretrain')
+    pos = g.uniform(-10, 10, (n_vp, 3))
+    d = np.linalg.norm(pos[:, None] - pos[None], axis=-1)
+    nbr = [sorted(int(j) for j in np.argsort(d[i])[1:5]) for i in range(n_vp)]
+    names = ['pv%02d' % i for i in range(n_vp)]
+    B, V, L = batch, n_views, instr_len
+    step_lens = [int(x) for x in g.integers(1, max_steps + 1, B)]
+    step_lens[0] = max_steps
+    traj_vpids, traj_cand_vpids, view_lens, nav_types_rows = [], [], [], []
+    for b in range(B):
+        cur = int(g.integers(0, n_vp))
+        path, cands_b = [], []
+        for t in range(step_lens[b]):
+            path.append(cur)
+            cands = [c for c in nbr[cur]]
+            order = g.permutation(len(cands))
+            cands = [cands[int(i)] for i in order]
+            cands_b.append(cands)
+            vl = int(g.integers(max(len(cands), V - 3), V + 1))
+            view_lens.append(vl)
+            nt = np.zeros(V, np.int64)
+            nt[:len(cands)] = 1
+            nav_types_rows.append(nt)
+            fresh = [c for c in cands if c not in path]
+            cur = (fresh or cands)[int(g.integers(0, len(fresh or cands)))]
+        traj_vpids.append([names[i] for i in path])
+        traj_cand_vpids.append([[names[c] for c in cs] for cs in cands_b])
+    N = sum(step_lens)
+    view_lens = np.array(view_lens, np.int64)
+    vmask = _mask_from_lens(view_lens, V)
+    traj_view_img_fts = g.standard_normal((N, V, 768), dtype=np.float32)
+    traj_view_img_fts[~vmask] = 0
+    traj_loc_fts = _rel_pos7(g, (N, V))
+    traj_loc_fts[~vmask] = 0
+    traj_nav_types = np.stack(nav_types_rows, 0)
+    traj_nav_types[~vmask] = 0
+    gmap_vpids, visited = [], []
+    for b in range(B):
+        vis = list(dict.fromkeys(traj_vpids[b]))
+        unv = [v for v in dict.fromkeys(c for cs in traj_cand_vpids[b] for c in cs) if v not in vis]
+        gmap_vpids.append([None] + vis + unv)
+        visited.append([False] + [True] * len(vis) + [False] * len(unv))
+    gmap_lens = np.array([len(x) for x in gmap_vpids], np.int64)
+    G = int(gmap_lens.max())
+    gmask = _mask_from_lens(gmap_lens, G)
+    gmap_step_ids = g.integers(0, 10, (B, G)).astype(np.int64)
+    gmap_step_ids[:, 0] = 0
+    gmap_step_ids[~gmask] = 0
+    gmap_pos_fts = _rel_pos7(g, (B, G))
+    gmap_pos_fts[~gmask] = 0
+    pd = np.triu(g.uniform(0, 20, (B, G, G)).astype(np.float32), 1)
+    pd = pd + pd.transpose(0, 2, 1)
+    pd[:, 0, :] = 0
+    pd[:, :, 0] = 0
+    pd[~(gmask[:, :, None] & gmask[:, None, :])] = 0
+    gmap_visited_masks = np.zeros((B, G), bool)
+    for b in range(B):
+        gmap_visited_masks[b, :len(visited[b])] = visited[b]
+    last = np.cumsum(step_lens) - 1
+    P = int(view_lens[last].max()) + 1
+    vp_pos_fts = np.zeros((B, P, 14), np.float32)
+    vp_pos_fts[:, :, :7] = _rel_pos7(g, (B, 1))
+    c7 = _rel_pos7(g, (B, V))
+    for b in range(B):
+        nc = len(traj_cand_vpids[b][-1])
+        vp_pos_fts[b, 1:1 + nc, 7:] = c7[b, :nc]
+    txt_lens = _lens(g, B, max(L // 3, 6), L, True)
+    txt_ids = g.integers(1000, 30000, (B, L)).astype(np.int64)
+    txt_ids[:, 0] = 101
+    tmask = _mask_from_lens(txt_lens, L)
+    txt_ids[~tmask] = 0
+    txt_labels = np.full((B, L), -1, np.int64)
+    for b in range(B):                                        # a few masked tokens per instruction (103 = [MASK])
+        for j in g.choice(np.arange(1, txt_lens[b]), size=min(3, int(txt_lens[b]) - 1), replace=False):
+            txt_labels[b, j] = txt_ids[b, j]
+            txt_ids[b, j] = 103
+    Vl = int(view_lens[last].max())
+    vp_view_mrc_masks = np.zeros((B, Vl), bool)
+    for b in range(B):
+        k = g.choice(np.arange(view_lens[last[b]]), size=2, replace=False)
+        vp_view_mrc_masks[b, k] = True
+    probs = g.gamma(0.3, size=(B, Vl, n_probs)).astype(np.float32) + 1e-6
+    vp_view_probs = probs / probs.sum(-1, keepdims=True)
+    return dict(txt_ids=txt_ids, txt_lens=txt_lens, txt_labels=txt_labels, traj_view_img_fts=traj_view_img_fts,
+                traj_obj_img_fts=None, traj_loc_fts=traj_loc_fts, traj_nav_types=traj_nav_types, traj_step_lens=step_lens,
+                traj_vp_view_lens=view_lens, traj_vp_obj_lens=None, traj_vpids=traj_vpids, traj_cand_vpids=traj_cand_vpids,
+                gmap_lens=gmap_lens, gmap_step_ids=gmap_step_ids, gmap_pos_fts=gmap_pos_fts, gmap_pair_dists=pd,
+                gmap_vpids=gmap_vpids, vp_pos_fts=vp_pos_fts, gmap_visited_masks=gmap_visited_masks,
+                vp_view_mrc_masks=vp_view_mrc_masks, vp_view_probs=vp_view_probs)
