@@ -783,7 +783,10 @@ def main():
         cb, _ = cpu_reference(model_kind, shape)
         line['cpu_baseline'] = cb
     if world == 1 and model_kind == 'duet':
-        line['step']['graph_glue'] = glue_leg(dev, B, with_cpu=not args.no_cpu_baseline)
+        try:                                            # an auxiliary figure must never cost the bench line
+            line['step']['graph_glue'] = glue_leg(dev, B, with_cpu=not args.no_cpu_baseline)
+        except Exception as e:                          # noqa: BLE001
+            line['step']['graph_glue'] = {'error': '%s: %s' % (type(e).__name__, e)}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
