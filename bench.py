@@ -295,6 +295,34 @@ def glue_leg(dev, batch, with_cpu):
     return res
 
 
+def eager_gpu_reference(shape, budget_s=2.0):
+    """The same algorithm (the oracle's plain fp32 torch ops: no fusion, no graphs, the reference's Python fusion loop) on THIS
+    GPU at the workload's own batch size - what running the reference's modules on the same box looks like ("the
+    real bar").  A reported figure of the cpu_baseline leg; never a product path."""
+    import vln_imagine_b200.synth as synth
+    from oracle import duet_oracle as O
+    man = json.load(open(os.path.join(ROOT, 'tests', 'golden', 'duet_manifest.json')))
+    sd = synth.synth_state_dict(man, seed=0)
+    ep = synth.to_torch(synth.duet_episode(shape, 1234))
+    with torch.no_grad():
+        B = shape.batch                                   # the step's cost does not depend on the context VALUES: random ones
+        g = torch.Generator().manual_seed(1)
+        txt = torch.randn(B, shape.instr_len, 768, generator=g).cuda()
+        img2 = torch.randn(B, shape.n_imagine, 768, generator=g).cuda()
+        sd = {k: v.cuda() for k, v in sd.items()}
+        ep = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in ep.items()}
+        O.nav_step(sd, ep, txt, img2)
+        torch.cuda.synchronize()
+        n, t0 = 0, time.perf_counter()
+        while time.perf_counter() - t0 < budget_s or n < 3:
+            O.nav_step(sd, ep, txt, img2)
+            torch.cuda.synchronize()
+            n += 1
+        dt = (time.perf_counter() - t0) / n
+    return {'value': B / dt, 'unit': UNIT, 'ms_per_step': dt * 1e3,
+            'what': 'the oracle (plain fp32 torch ops, eager, Python fusion loop) on this GPU, %d episodes per step' % B}
+
+
 def cpu_reference(model_kind, shape, budget_s=15.0, batch=8):
     """The reference algorithm (CPU oracle port, fp32, all host threads) on a bounded sample of the same
     workload: `batch` episodes of the same shape, repeated for about budget_s seconds."""
@@ -782,6 +810,11 @@ def main():
     if world == 1 and not args.no_cpu_baseline:
         cb, _ = cpu_reference(model_kind, shape)
         line['cpu_baseline'] = cb
+        if model_kind == 'duet':
+            try:                                        # an auxiliary figure must never cost the bench line
+                cb['same_algorithm_torch_eager_on_this_gpu'] = eager_gpu_reference(shape)
+            except Exception as e:                      # noqa: BLE001
+                cb['same_algorithm_torch_eager_on_this_gpu'] = {'error': '%s: %s' % (type(e).__name__, str(e)[:200])}
     if world == 1 and model_kind == 'duet':
         try:                                            # an auxiliary figure must never cost the bench line
             line['step']['graph_glue'] = glue_leg(dev, B, with_cpu=not args.no_cpu_baseline)

@@ -130,7 +130,7 @@ def forward_text(sd, txt_ids, txt_masks, num_l_layers=9):
     """mode 'language'.  BertEmbeddings (models/vilmodel.py:49-78) + LanguageEncoder (:414-434);
     entry at :1075-1079."""
     B, L = txt_ids.shape
-    pos = torch.arange(L)[None, :].expand(B, L)
+    pos = torch.arange(L, device=txt_ids.device)[None, :].expand(B, L)
     e = (F.embedding(txt_ids, sd['embeddings.word_embeddings.weight'])
          + F.embedding(pos, sd['embeddings.position_embeddings.weight'])
          + sd['embeddings.token_type_embeddings.weight'][0])
@@ -153,7 +153,7 @@ def pano_encoder_layer(sd, p, x, key_pad):
     h = lnorm(sd, p + '.norm1', x, 1e-5)
     qkv = F.linear(h, sd[p + '.self_attn.in_proj_weight'], sd[p + '.self_attn.in_proj_bias'])
     q, k, v = [split_heads(t) for t in qkv.chunk(3, -1)]
-    add = torch.zeros(key_pad.shape, dtype=torch.float32).masked_fill(key_pad, float('-inf'))[:, None, None, :]
+    add = torch.zeros(key_pad.shape, dtype=torch.float32, device=key_pad.device).masked_fill(key_pad, float('-inf'))[:, None, None, :]
     a = merge_heads(attend(q, k, v, add))
     x = x + lin(sd, p + '.self_attn.out_proj', a)
     h = lnorm(sd, p + '.norm2', x, 1e-5)
@@ -184,7 +184,7 @@ def forward_panorama(sd, view_img_fts, loc_fts, nav_types, view_lens, num_pano_l
          + sd['embeddings.token_type_embeddings.weight'][1])
     x = lnorm(sd, p + '.layer_norm', e, 1e-12)
     V = img.shape[1]
-    pano_masks = torch.arange(V)[None, :] < pano_lens[:, None]      # models/ops.py:36-44
+    pano_masks = torch.arange(V, device=pano_lens.device)[None, :] < pano_lens[:, None]      # models/ops.py:36-44
     pad = ~pano_masks
     for i in range(num_pano_layers):
         x = pano_encoder_layer(sd, '%s.pano_encoder.layers.%d' % (p, i), x, pad)
