@@ -134,6 +134,25 @@ def test_reverie_align_rows_and_lazy_vpid_rows():
     assert rows == [[None, 'b', 'a', 'c'], [None, 'x', 'y']] and list(rows)[1][2] == 'y' and rows[0] is rows[0]
 
 
+def test_pretraining_gmap_aggregation_rows_match_the_oracle():
+    """N4 groundwork: the segment-mean index arrays for GlobalMapEncoder._aggregate_gmap_features against the oracle's loop"""
+    import numpy as np
+    from oracle import pretrain_oracle as P
+    pre = importlib.import_module('vln_imagine_b200.pretrain')
+    ep = synth.duet_pretrain_batch(seed=9, batch=4, max_steps=5)
+    N, V = ep['traj_view_img_fts'].shape[:2]
+    emb = np.random.default_rng(0).standard_normal((N, V, 16)).astype(np.float32)
+    t = torch.from_numpy(emb)
+    steps = list(ep['traj_step_lens'])
+    ref = P.aggregate_gmap_features(torch.split(t, steps, 0), torch.split(torch.from_numpy(ep['traj_vp_view_lens']), steps, 0),
+                                    ep['traj_vpids'], ep['traj_cand_vpids'], ep['gmap_vpids']).numpy()
+    off, rows, G = pre.gmap_aggregation_rows(steps, ep['traj_vp_view_lens'], ep['traj_vpids'], ep['traj_cand_vpids'], ep['gmap_vpids'], V)
+    src = np.concatenate([emb.reshape(N * V, 16), np.zeros((1, 16), np.float32)], 0)
+    got = np.stack([src[rows[off[r]:off[r + 1]]].mean(0) for r in range(len(off) - 1)]).reshape(len(steps), G, 16)
+    assert G == ref.shape[1] and np.abs(got - ref).max() < 1e-6
+    assert (got[:, 0] == 0).all()
+
+
 def test_freeze_flags_follow_the_reference():
     duet = importlib.import_module('vln_imagine_b200.duet')
     m = duet.VLNBert(config.default_duet_args(fix_lang_embedding=True, fix_pano_embedding=True)).vln_bert
