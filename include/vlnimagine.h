@@ -32,7 +32,7 @@ extern "C" {
 #define VI_HIDDEN 768
 #define VI_HEAD_DIM 64
 
-enum { VI_DT_BF16 = 0, VI_DT_F32 = 1 };
+enum { VI_DT_BF16 = 0, VI_DT_F32 = 1, VI_DT_F16 = 2 };
 enum { VI_EPI_NONE = 0, VI_EPI_GELU = 1, VI_EPI_RELU = 2 };
 /* key padding: additive (1-m)*-10000 (D/models/ops.py:25-34) or -inf (nn.MultiheadAttention
  * key_padding_mask, D/models/transformer.py:176-177) */
@@ -72,6 +72,40 @@ int vi_gemm_bf16_tiled(const void* x, int64_t ldx, const void* w, const float* b
                        const float* residual, int64_t ldr, void* y, int64_t ldy, int y_dtype,
                        int M, int N, int K, int epilogue,
                        int n_groups, const int32_t* group_row_end, int tile, vi_stream_t stream);
+/* The general form behind vi_gemm_bf16(_tiled): 16-bit operands of either format (bf16, or fp16 for tensors whose range
+ * the caller has bounded: LayerNorm outputs, probabilities, their projections - same tensor-core rate, 8x smaller rounding
+ * error; 16-bit outputs saturate at +-65504 instead of overflowing), an optional 16-bit copy of an fp32 output, and
+ * LayerNorm folded into the neighbouring contractions so that BertSelfOutput / BertOutput (D/models/vilmodel.py:151-155,
+ * 190-194) and norm1 / norm2 of the panorama encoder (D/models/transformer.py:171,179) need no pass of their own:
+ *   stats_out  : the producer (dense + residual) writes, for every output row and every 32-column chunk, (mean, M2) of the
+ *                chunk: float2 [N / 32][stats_ld].  Its fp32 output is the RAW pre-LayerNorm sum z (plus y16 = z in 16 bits).
+ *   VI_LN_FOLD : the consumer computes LayerNorm(z) W^T + b from z itself:  x = z in 16 bits, w = W * gamma (columnwise),
+ *                bias = W beta + b, ln_vec_a = row sums of w; the epilogue applies  y = (acc - mu * s_n) / sigma + bias_n
+ *                with (mu, sigma) of each row combined from ln_stats (ln_chunks chunks, Chan's formula), then the activation.
+ *   VI_LN_RESIDUAL : the residual operand is LayerNorm(z) given as the RAW fp32 rows z: the epilogue adds
+ *                (z - mu) / sigma * gamma + beta with ln_vec_a = gamma and bias = beta + b ([n_groups * N], N = 32 * ln_chunks;
+ *                no activation).
+ * Grouped calls index bias / ln_vec_* as [g * N + n]. */
+enum { VI_LN_NONE = 0, VI_LN_FOLD = 1, VI_LN_RESIDUAL = 2 };
+typedef struct {
+  const void* x; int64_t ldx;      /* [M, K] 16-bit */
+  const void* w;                   /* [n_groups * N, K] 16-bit, same format as x */
+  int in_dtype;                    /* VI_DT_BF16 or VI_DT_F16 */
+  const float* bias;               /* [n_groups * N] or NULL */
+  const float* residual; int64_t ldr;   /* fp32 [M, ldr] or NULL */
+  void* y; int64_t ldy; int y_dtype;    /* primary output: in_dtype or VI_DT_F32 */
+  void* y16; int64_t ldy16;        /* optional 16-bit copy (in_dtype) of an fp32 output, or NULL */
+  int M, N, K, epilogue;
+  int n_groups; const int32_t* group_row_end;   /* HOST array */
+  int tile;                        /* 0 or width | VI_TILE_PAIR */
+  int ln_mode;                     /* VI_LN_* */
+  const float* ln_vec_a;
+  const float* ln_stats;           /* float2 [ln_chunks][stats_ld] written by the producer of the rows being normalised */
+  int ln_chunks; float ln_eps;
+  float* stats_out;                /* float2 [N / 32][stats_ld] or NULL */
+  int64_t stats_ld;                /* row stride (in float2) of ln_stats and stats_out, >= M */
+} vi_gemm_args;
+int vi_gemm16(const vi_gemm_args* args, vi_stream_t stream);
 int vi_gemm_f32(const float* x, int64_t ldx, const float* w, const float* bias,
                 const float* residual, int64_t ldr, float* y, int64_t ldy,
                 int M, int N, int K, int epilogue,
@@ -85,7 +119,7 @@ int vi_gemm_f32(const float* x, int64_t ldx, const float* w, const float* bias,
  *   q: [B*Lq, ldq], k/v: [B*Lk, ldk/ldv], head h at columns [h*64, h*64+64); o: [B*Lq, ldo].
  *   key_mask [B, Lk] (1 = valid) or NULL; pair_dist [B, Lq, Lk] fp32 or NULL with
  *   bias_affine -> device {w, b}: bias = w*dist + b (sprel_linear, D/models/vilmodel.py:1145-1149).
- *   dtype: VI_DT_BF16 (mma.sync tiles, fp32 softmax) or VI_DT_F32 (check mode).
+ *   dtype: VI_DT_BF16 / VI_DT_F16 (tensor-core tiles, fp32 softmax) or VI_DT_F32 (check mode).
  *   lse [B, H, Lq] optional (log-sum-exp per row, kept for the backward pass).
  * ------------------------------------------------------------------------------------------- */
 #define VI_ATTN_MAX_PROBLEMS 4
@@ -117,30 +151,12 @@ int vi_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const vo
  * ------------------------------------------------------------------------------------------- */
 /* y = LayerNorm(a [+ b]) * gamma + beta.  BertSelfOutput/BertOutput (D/models/vilmodel.py:151-155,
  * 190-194), norm1/norm2/final norm of the panorama encoder (D/models/transformer.py:171,179,86).
- * Writes fp32 (y32) and/or bf16 (y16) copies; either may be NULL.  Grouped form as in vi_gemm_*:
- * rows below group_row_end[g] (HOST array, ascending) use gamma/beta rows g of a [n_groups, 768] stack. */
+ * Writes fp32 (y32) and/or 16-bit (y16: VI_DT_BF16 or VI_DT_F16 per y16_dtype, as everywhere below) copies; either may be
+ * NULL.  Grouped form as in vi_gemm_*: rows below group_row_end[g] (HOST array, ascending) use gamma/beta rows g of a
+ * [n_groups, 768] stack. */
 int vi_add_ln(const float* a, const float* b, const float* gamma, const float* beta, float eps,
-              float* y32, void* y16, int64_t rows,
+              float* y32, void* y16, int y16_dtype, int64_t rows,
               int n_groups, const int32_t* group_row_end, vi_stream_t stream);
-
-/* EXPERIMENTAL, not on the default path: vi_gemm_bf16_tiled with the W tile shared by a cluster of two CTAs through TMA
- * multicast (two vertically adjacent 128-row tiles per cluster; every SM pulls its X tile and HALF of the W tile per k-block).
- * tile = 128 | 192 | 256 columns; grouped calls need every group but the last to end on a multiple of 256 rows.  Same
- * arithmetic, operands and error behaviour as vi_gemm_bf16_tiled (csrc/vi_gemm_mc.cu; validated by tools/gemm_mc_check.py). */
-int vi_gemm_bf16_mc(const void* x, int64_t ldx, const void* w, const float* bias, const float* residual, int64_t ldr,
-                    void* y, int64_t ldy, int y_dtype, int M, int N, int K, int epilogue, int n_groups,
-                    const int32_t* group_row_end, int tile, vi_stream_t stream);
-
-/* Row-block GEMM with the residual add and LayerNorm fused into the epilogue (N = 768 only; vi_gemm_rb.cu):
- *   pre = x w^T + bias + residual        (optional fp32 output pre32 [M, 768]: pre-norm residual stream)
- *   y   = LayerNorm(pre) * gamma + beta  (y32 fp32 and / or y16 bf16, [M, 768])
- * A cluster of 4 CTAs owns 128 rows x 768 columns: the x tile is TMA-multicast to the four CTAs, row statistics are
- * exchanged through distributed shared memory.  w is [n_groups * 768, K] bf16, gamma / beta / bias [n_groups * 768].
- * Replaces dense -> + input -> LayerNorm of BertSelfOutput / BertOutput (D/models/vilmodel.py:147-155,183-194) and
- * out_proj / linear2 followed by norm1 / norm2 of the pre-norm encoder layer (D/models/transformer.py:170-182). */
-int vi_gemm_ln_bf16(const void* x, int64_t ldx, const void* w, const float* bias, const float* residual, int64_t ldr,
-                    const float* gamma, const float* beta, float eps, float* pre32, float* y32, void* y16, int M, int K,
-                    int n_groups, const int32_t* group_row_end, vi_stream_t stream);
 
 /* Input-embedding composer:
  *   y = LN_out( [LN_a](a) + a2 + a3 + LN_f(feat @ feat_w^T + feat_b) + table[idx] + pos_table[row % pos_period]
@@ -169,10 +185,14 @@ typedef struct {
   const float* out_beta;
   float eps;                 /* all LayerNorms here use the same eps (1e-12 in the reference) */
   float* y32;                /* [rows, 768] or NULL */
-  void* y16;                 /* bf16 [rows, 768] or NULL */
+  void* y16;                 /* 16-bit [rows, 768] or NULL */
   int64_t rows;
   const float* a2;           /* [rows, 768] plain addends (NULL: none); used by the training-mode decomposition */
   const float* a3;
+  int32_t y16_dtype;         /* VI_DT_BF16 or VI_DT_F16 */
+  const float* ln2_gamma;    /* optional second LayerNorm chained on the result: y32 keeps the first result, y16 = LN2(y32) */
+  const float* ln2_beta;     /* (norm1 of the first pre-norm panorama layer, D/models/transformer.py:171) */
+  float ln2_eps;
 } vi_embed_args;
 int vi_embed_compose(const vi_embed_args* args, vi_stream_t stream);
 
@@ -186,7 +206,7 @@ int vi_ln_dot(const float* h, const float* gamma, const float* beta, float eps,
 /* y[b*rpb + r] = x[b*x_batch_stride + r*768 ..] * s[b*lds ..]  (ob_embeds * txt_embeds[:, :1],
  * H/models/vilmodel_cmt.py:1191; ob_embeds is the tail slice of every episode's [hist; ob] block, hence the
  * batch stride).  Strides in elements; y rows are dense. */
-int vi_mul_bcast(const float* x, int64_t x_batch_stride, const float* s, int64_t lds, float* y32, void* y16,
+int vi_mul_bcast(const float* x, int64_t x_batch_stride, const float* s, int64_t lds, float* y32, void* y16, int y16_dtype,
                  int64_t rows, int rows_per_batch, vi_stream_t stream);
 
 /* Action-logit masking and global/local fusion, D/models/vilmodel.py:1182-1217.
@@ -212,7 +232,7 @@ int vi_mask_logits_navtype(const float* raw, const int64_t* nav_types, float* ou
  * ------------------------------------------------------------------------------------------- */
 /* out[r] = mean over t in [offsets[r], offsets[r+1]) of src[row_idx[t]]  (768-wide rows) */
 int vi_gather_mean(const float* src, const int32_t* offsets, const int32_t* row_idx,
-                   float* out32, void* out16, int R, vi_stream_t stream);
+                   float* out32, void* out16, int out16_dtype, int R, vi_stream_t stream);
 /* dst[dst_rows[r]] = src[r] */
 int vi_scatter_rows(const float* src, const int32_t* dst_rows, float* dst, int R, vi_stream_t stream);
 /* loss_rows[r] = 1 - cos(proj[r], tgt[r]) (eps 1e-8); *loss_mean = mean_r (0 if R == 0) */
@@ -233,11 +253,11 @@ int vi_margin_loss(const float* proj, const float* tgt, const float* negs, const
                    vi_stream_t stream);
 
 /* dst[b, r, 0:768] = src[b, r, 0:768] for n_batches x rows_per_batch rows; strides in ELEMENTS.  Writes an
- * fp32 and/or a bf16 copy.  Builds the cross-attention context cat([txt_embeds, imagine_embeds], 1)
+ * fp32 and/or a 16-bit copy.  Builds the cross-attention context cat([txt_embeds, imagine_embeds], 1)
  * (D/models/vilmodel.py:1157, H/models/vilmodel_cmt.py:1110) and gathers the token-0 rows that feed
  * sap_fuse_linear (D/models/vilmodel.py:1185-1187). */
 int vi_copy_rows(const float* src, int64_t src_batch_stride, int64_t src_row_stride, float* dst32, void* dst16,
-                 int64_t dst_batch_stride, int64_t dst_row_stride, int64_t n_batches, int rows_per_batch,
+                 int dst16_dtype, int64_t dst_batch_stride, int64_t dst_row_stride, int64_t n_batches, int rows_per_batch,
                  vi_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
@@ -306,6 +326,8 @@ int vi_dropout(const void* x, void* y, int64_t n, float p, const uint32_t* seed,
 
 /* fp32 -> bf16 shadow copy of a weight or activation */
 int vi_cast_bf16(const float* src, void* dst, int64_t n, vi_stream_t stream);
+/* fp32 -> bf16 or fp16 (saturating at +-65504) */
+int vi_cast_h16(const float* src, void* dst, int dst_dtype, int64_t n, vi_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Per-step graph glue of a DUET rollout.  Replaces the Python GraphMap /

@@ -407,42 +407,119 @@ def test_argument_errors_are_reported_not_fatal(ops):
         ops.ensure_init(torch.zeros(1))
 
 
-@pytest.mark.parametrize('M,K,grouped', [(4416, 768, True), (4416, 3072, True), (2304, 768, False), (5120, 3072, False),
-                                          (300, 768, False), (1, 768, False), (9024, 768, False)])
-@pytest.mark.parametrize('mode', ['post_ln', 'pre_norm', 'no_residual'])
-def test_gemm_ln_rowblock(ops, M, K, grouped, mode):
-    """cluster GEMM with residual + LayerNorm in the epilogue (TMA multicast, DSMEM row statistics) against
-    F.linear -> + residual -> F.layer_norm on bf16-rounded operands"""
-    n_groups = 2 if grouped else 1
-    ends = [2048, M] if grouped else None
-    x16 = _rand(M, K, seed=41).bfloat16()
-    w16 = _rand(n_groups * 768, K, scale=0.05, seed=42).bfloat16()
-    b = _rand(n_groups * 768, scale=0.1, seed=43)
-    res = None if mode == 'no_residual' else _rand(M, 768, seed=44) * 3.0 + 0.5
-    g = 1 + _rand(n_groups * 768, scale=0.1, seed=45)
-    be = _rand(n_groups * 768, scale=0.1, seed=46)
-    eps = 1e-5 if mode == 'pre_norm' else 1e-12
-    pre, y32, y16 = ops.gemm_ln(x16, w16, b, res, g, be, eps, want32=mode != 'pre_norm', want16=True,
-                                want_pre=mode == 'pre_norm', group_row_end=ends)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# vi_gemm16: fp16 operands, the packed-polynomial GELU, LayerNorm folded into the neighbouring contractions
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('M,N,K', [(1920, 768, 768), (4416, 3072, 768), (300, 768, 3072), (37, 512, 768)])
+@pytest.mark.parametrize('epi', [0, 1, 2])
+def test_gemm_f16_operands(ops, M, N, K, epi):
+    """fp16 operands through the same tcgen05 kernel (instruction-descriptor formats 0): exact up to fp32 accumulation
+    against a reference that rounds its operands to fp16 first, and 8x closer to the unrounded product than bf16"""
+    x, w, b = _rand(M, K, seed=1), _rand(N, K, scale=0.05, seed=2), _rand(N, scale=0.1, seed=3)
+    res = _rand(M, N, seed=4)
+    xh, wh = x.half(), w.half()
+    ref = F.linear(xh.float(), wh.float(), b)
+    ref = [ref, F.gelu(ref), F.relu(ref)][epi]
+    y = ops.gemm(xh, wh, b, residual=res, epilogue=epi, out_dtype=torch.float32)
+    assert relerr(y, ref + res) < 1e-4
+    y16 = ops.gemm(xh, wh, b, epilogue=epi)
+    assert y16.dtype == torch.float16 and relerr(y16, ref) < 2e-3
+    exact = F.linear(x, w, b)
+    exact = [exact, F.gelu(exact), F.relu(exact)][epi]
+    e16 = relerr(ops.gemm(xh, wh, b, epilogue=epi, out_dtype=torch.float32), exact)
+    eb = relerr(ops.gemm(x.bfloat16(), w.bfloat16(), b, epilogue=epi, out_dtype=torch.float32), exact)
+    assert e16 < 0.3 * eb, (e16, eb)
+
+
+def test_gemm_f16_saturates_instead_of_overflowing(ops):
+    x = torch.full((128, 64), 60.0, device='cuda').half()
+    w = torch.full((64, 64), 60.0, device='cuda').half()
+    y = ops.gemm(x, w)                                   # 64 * 3600 = 230400 > 65504
+    assert torch.isfinite(y.float()).all() and float(y.float().max()) == 65504.0
+
+
+def test_gelu_polynomial_epilogue(ops):
+    """the MUFU-free erf polynomial of the GEMM epilogue against F.gelu over the whole input range"""
+    M, K = 512, 64
+    x16 = torch.zeros((M, K), device='cuda').bfloat16()
+    x16[:, 0] = 1.0
+    w16 = torch.zeros((64, K), device='cuda').bfloat16()
+    outs = []
+    # y[m, n] = x[m, :] . w[n, :] + b[n] with w = 0: the bias sweeps the input range of the activation
+    for i in range(8):
+        b = torch.linspace(-12 + 3 * i, -9 + 3 * i, 64, device='cuda')
+        y = ops.gemm(x16[:128], w16, b, epilogue=1, out_dtype=torch.float32)
+        assert float((y[0] - F.gelu(b)).abs().max()) < 1e-4
+        outs.append(y[0])
+    assert torch.isfinite(torch.cat(outs)).all()
+
+
+@pytest.mark.parametrize('fmt', [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize('M,grouped', [(4416, True), (2304, False), (300, False), (9024, True), (1, False)])
+@pytest.mark.parametrize('eps', [1e-12, 1e-5])
+def test_gemm_layernorm_folding(ops, fmt, M, grouped, eps):
+    """producer (dense + residual, writes raw sums + per-chunk row statistics + a 16-bit copy), consumer with the LayerNorm
+    folded into its weights (VI_LN_FOLD, also with GELU), consumer with the LayerNorm applied to its residual operand
+    (VI_LN_RESIDUAL): against F.linear / F.layer_norm in fp32 on the same rounded operands"""
+    from vln_imagine_b200 import _lib
+    G = 2 if grouped else 1
+    ends = [2048 if M == 4416 else 5632, M] if grouped else None
     bounds = [0] + (ends or [M])
-    ref_pre, ref = [], []
-    for i in range(n_groups):
-        r0, r1 = bounds[i], bounds[i + 1]
-        t = F.linear(x16[r0:r1].float(), w16[i * 768:(i + 1) * 768].float(), b[i * 768:(i + 1) * 768])
-        if res is not None:
-            t = t + res[r0:r1]
-        ref_pre.append(t)
-        ref.append(F.layer_norm(t, (768,), g[i * 768:(i + 1) * 768], be[i * 768:(i + 1) * 768], eps))
-    ref_pre, ref = torch.cat(ref_pre), torch.cat(ref)
-    if pre is not None:
-        assert relerr(pre, ref_pre) < 2e-3
-    if y32 is not None:
-        assert relerr(y32, ref) < 2e-3
-        assert relerr(y16, y32) < 5e-3
-    else:
-        assert relerr(y16, ref) < 1e-2
-    # the fused kernel against the two-kernel path it replaces (same operands): fp32 outputs agree closely
-    ao = ops.gemm(x16, w16, b, residual=res, out_dtype=torch.float32, group_row_end=ends)
-    z32, z16 = ops.add_ln(ao, None, g.view(n_groups, 768), be.view(n_groups, 768), eps, want16=True, group_row_end=ends)
-    if y32 is not None:
-        assert relerr(y32, z32) < 1e-4
+    x16 = _rand(M, 768, seed=11).to(fmt)
+    wo = _rand(G * 768, 768, scale=0.05, seed=12)
+    bo = _rand(G * 768, scale=0.1, seed=13)
+    res = _rand(M, 768, seed=14) * 2.0 + 0.3
+    gamma = 1 + _rand(G, 768, scale=0.2, seed=15)
+    beta = _rand(G, 768, scale=0.2, seed=16)
+    w1 = _rand(G * 3072, 768, scale=0.05, seed=17)
+    b1 = _rand(G * 3072, scale=0.1, seed=18)
+
+    def per_group(fn):
+        return torch.cat([fn(g, slice(bounds[g], bounds[g + 1])) for g in range(G)])
+
+    # ---- producer
+    z32 = torch.empty((M, 768), device='cuda')
+    z16 = torch.empty((M, 768), device='cuda', dtype=fmt)
+    stats = torch.full((24, M, 2), float('nan'), device='cuda')
+    ops.gemm(x16, wo.to(fmt), bo, residual=res, out=z32, out16=z16, group_row_end=ends, stats_out=stats)
+    z_ref = per_group(lambda g, r: F.linear(x16[r].float(), wo[g * 768:(g + 1) * 768].to(fmt).float(), bo[g * 768:(g + 1) * 768]) + res[r])
+    assert relerr(z32, z_ref) < 1e-4
+    assert torch.equal(z16, z32.to(fmt))
+    ch = z32.view(M, 24, 32)
+    assert relerr(stats[:, :, 0].t(), ch.mean(-1)) < 1e-5
+    assert relerr(stats[:, :, 1].t(), ((ch - ch.mean(-1, keepdim=True)) ** 2).sum(-1)) < 1e-4
+    ln_ref = per_group(lambda g, r: F.layer_norm(z32[r], (768,), gamma[g], beta[g], eps))
+
+    # ---- VI_LN_FOLD consumer (with GELU): weights W * gamma, s = row sums of the ROUNDED product, c = W beta + b
+    wg = (w1.view(G, 3072, 768) * gamma[:, None, :]).reshape(G * 3072, 768).to(fmt)
+    s = wg.double().sum(1).float()
+    c = (torch.einsum('gnk,gk->gn', w1.view(G, 3072, 768).double(), beta.double()).reshape(-1) + b1.double()).float()
+    for epi in (0, 1):
+        y = ops.gemm(z16, wg, c, epilogue=epi, out_dtype=torch.float32, group_row_end=ends, ln=(_lib.LN_FOLD, s, stats, eps))
+        ref = per_group(lambda g, r: F.linear(ln_ref[r], w1[g * 3072:(g + 1) * 3072], b1[g * 3072:(g + 1) * 3072]))
+        ref = F.gelu(ref) if epi else ref
+        assert relerr(y, ref) < (3e-3 if fmt == torch.float16 else 2e-2), epi
+
+    # ---- VI_LN_RESIDUAL consumer: out = x W^T + b + LayerNorm(z)
+    h16 = _rand(M, 768, seed=19).to(fmt)
+    w2 = _rand(G * 768, 768, scale=0.05, seed=20)
+    b2 = _rand(G * 768, scale=0.1, seed=21)
+    out = ops.gemm(h16, w2.to(fmt), (beta.reshape(-1) + b2).contiguous(), residual=z32, out_dtype=torch.float32, group_row_end=ends,
+                   ln=(_lib.LN_RESIDUAL, gamma.reshape(-1).contiguous(), stats, eps))
+    ref = per_group(lambda g, r: F.linear(h16[r].float(), w2[g * 768:(g + 1) * 768].to(fmt).float(), b2[g * 768:(g + 1) * 768])) + ln_ref
+    assert relerr(out, ref) < 1e-4
+
+
+def test_embed_compose_chained_layernorm(ops):
+    """y32 = LN_out(sum), y16 = LN2(y32) from one launch (first pre-norm layer of the panorama encoder)"""
+    rows = 777
+    a = _rand(rows, 768, seed=31)
+    g1, b1 = 1 + _rand(768, scale=0.1, seed=32), _rand(768, scale=0.1, seed=33)
+    g2, b2 = 1 + _rand(768, scale=0.1, seed=34), _rand(768, scale=0.1, seed=35)
+    with ops.half_format(torch.float16):
+        y32, y16 = ops.embed_compose(rows, a.device, a=a, out_ln=(g1, b1), eps=1e-12, want16=True, want32=True, ln2=(g2, b2), ln2_eps=1e-5)
+    r32 = F.layer_norm(a, (768,), g1, b1, 1e-12)
+    assert relerr(y32, r32) < 1e-5
+    assert y16.dtype == torch.float16 and relerr(y16, F.layer_norm(r32, (768,), g2, b2, 1e-5)) < 2e-3

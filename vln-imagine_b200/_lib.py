@@ -19,7 +19,8 @@ if not os.path.exists(LIB_PATH):
 lib = C.CDLL(LIB_PATH)
 
 VI_OK = 0
-DT_BF16, DT_F32 = 0, 1
+DT_BF16, DT_F32, DT_F16 = 0, 1, 2
+LN_NONE, LN_FOLD, LN_RESIDUAL = 0, 1, 2
 EPI_NONE, EPI_GELU, EPI_RELU = 0, 1, 2
 MASK_ADD_NEG10000, MASK_NEG_INF = 0, 1
 
@@ -34,7 +35,16 @@ class EmbedArgs(C.Structure):
         ('idx', _p), ('table', _p), ('pos_table', _p), ('pos_period', C.c_int32),
         ('const_row', _p), ('const_row2', _p), ('out_gamma', _p), ('out_beta', _p),
         ('eps', _f), ('y32', _p), ('y16', _p), ('rows', _l), ('a2', _p), ('a3', _p),
+        ('y16_dtype', C.c_int32), ('ln2_gamma', _p), ('ln2_beta', _p), ('ln2_eps', _f),
     ]
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [('x', _p), ('ldx', _l), ('w', _p), ('in_dtype', _i), ('bias', _p), ('residual', _p), ('ldr', _l),
+                ('y', _p), ('ldy', _l), ('y_dtype', _i), ('y16', _p), ('ldy16', _l),
+                ('M', _i), ('N', _i), ('K', _i), ('epilogue', _i), ('n_groups', _i), ('group_row_end', _ip), ('tile', _i),
+                ('ln_mode', _i), ('ln_vec_a', _p), ('ln_stats', _p), ('ln_chunks', _i), ('ln_eps', _f),
+                ('stats_out', _p), ('stats_ld', _l)]
 
 
 class AttnProblem(C.Structure):
@@ -50,24 +60,24 @@ PROTOTYPES = {
     'vi_init': [_i],
     'vi_gemm_bf16': [_p, _l, _p, _p, _p, _l, _p, _l, _i, _i, _i, _i, _i, _i, _ip, _p],
     'vi_gemm_bf16_tiled': [_p, _l, _p, _p, _p, _l, _p, _l, _i, _i, _i, _i, _i, _i, _ip, _i, _p],
-    'vi_gemm_bf16_mc': [_p, _l, _p, _p, _p, _l, _p, _l, _i, _i, _i, _i, _i, _i, _ip, _i, _p],
-    'vi_gemm_ln_bf16': [_p, _l, _p, _p, _p, _l, _p, _p, _f, _p, _p, _p, _i, _i, _i, _ip, _p],
+    'vi_gemm16': [C.POINTER(GemmArgs), _p],
     'vi_gemm_f32': [_p, _l, _p, _p, _p, _l, _p, _l, _i, _i, _i, _i, _i, _ip, _p],
     'vi_attn_fwd': [_p, _l, _p, _l, _p, _l, _p, _l, _i, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
     'vi_attn_fwd_multi': [C.POINTER(AttnProblem), _i, _i, _i, _i, _p],
-    'vi_add_ln': [_p, _p, _p, _p, _f, _p, _p, _l, _i, _ip, _p],
+    'vi_add_ln': [_p, _p, _p, _p, _f, _p, _p, _i, _l, _i, _ip, _p],
     'vi_embed_compose': [C.POINTER(EmbedArgs), _p],
     'vi_ln_dot': [_p, _p, _p, _f, _p, _p, _p, _l, _i, _ip, _p],
-    'vi_mul_bcast': [_p, _l, _p, _l, _p, _p, _l, _i, _p],
+    'vi_mul_bcast': [_p, _l, _p, _l, _p, _p, _i, _l, _i, _p],
     'vi_duet_fuse_logits': [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
     'vi_mask_logits_navtype': [_p, _p, _p, _l, _p],
-    'vi_gather_mean': [_p, _p, _p, _p, _p, _i, _p],
+    'vi_gather_mean': [_p, _p, _p, _p, _p, _i, _i, _p],
     'vi_scatter_rows': [_p, _p, _p, _i, _p],
     'vi_cosine_loss': [_p, _p, _p, _p, _i, _p],
     'vi_infonce_loss': [_p, _p, _p, _p, _p, _f, _p, _p, _i, _i, _p],
     'vi_margin_loss': [_p, _p, _p, _p, _p, _f, _p, _p, _i, _i, _p],
-    'vi_copy_rows': [_p, _l, _l, _p, _p, _l, _l, _l, _i, _p],
+    'vi_copy_rows': [_p, _l, _l, _p, _p, _i, _l, _l, _l, _i, _p],
     'vi_cast_bf16': [_p, _p, _l, _p],
+    'vi_cast_h16': [_p, _p, _i, _l, _p],
     'vi_transpose': [_p, _l, _p, _l, _i, _i, _i, _i, _p],
     'vi_colsum': [_p, _l, _i, _p, _l, _i, _p, _l, _p],
     'vi_reduce_scratch_elems': [_l, _i, _i],

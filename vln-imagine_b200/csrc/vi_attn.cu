@@ -40,11 +40,19 @@ struct AttnParams {
 constexpr int DH = 64;
 constexpr int ROW = 72;            // bf16 elements per staged row (64 + 8): 144-byte pitch keeps ldmatrix conflict-free
 
+template <bool F16>
 __device__ __forceinline__ void mma_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  if constexpr (F16) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  } else {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  }
 }
 __device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
@@ -72,6 +80,8 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 // no warp of a CTA idles on registers another CTA could use): warp w owns query rows [qrows*bx + 16w, +16).
 // K, V (whole head) and the Q tile are staged with cp.async; fragments come from ldmatrix (V through .trans, so no
 // explicit transpose); scores stay in registers with an fp32 online softmax over 64-key chunks.
+// F16: the 16-bit operands / output are fp16 (inference on range-bounded tensors) instead of bf16.
+template <bool F16>
 __global__ void __launch_bounds__(128, 5) attn_fwd_bf16_kernel(const AttnParams p) {
   pdl_enter();
   extern __shared__ __align__(16) uint8_t smem[];
@@ -174,8 +184,8 @@ __global__ void __launch_bounds__(128, 5) attn_fwd_bf16_kernel(const AttnParams 
         if (np < npairs) {
           uint32_t kb[4];     // (keys 0-7, d 0-7) (keys 0-7, d 8-15) (keys 8-15, d 0-7) (keys 8-15, d 8-15)
           ldsm_x4(kb, ks_u + (uint32_t)((kc + np * 16 + (lm >> 1) * 8 + lr) * ROW + ks * 16 + (lm & 1) * 8) * 2);
-          mma_16816(s[2 * np], qa, kb[0], kb[1]);
-          mma_16816(s[2 * np + 1], qa, kb[2], kb[3]);
+          mma_16816<F16>(s[2 * np], qa, kb[0], kb[1]);
+          mma_16816<F16>(s[2 * np + 1], qa, kb[2], kb[3]);
         }
       }
     }
@@ -233,16 +243,16 @@ __global__ void __launch_bounds__(128, 5) attn_fwd_bf16_kernel(const AttnParams 
     for (int kk = 0; kk < 4; ++kk) {
       if (kk < npairs) {
         uint32_t pa[4];
-        pa[0] = pack_bf16x2(s[2 * kk][0], s[2 * kk][1]);
-        pa[1] = pack_bf16x2(s[2 * kk][2], s[2 * kk][3]);
-        pa[2] = pack_bf16x2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
-        pa[3] = pack_bf16x2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+        pa[0] = pack_h16x2(s[2 * kk][0], s[2 * kk][1], F16);
+        pa[1] = pack_h16x2(s[2 * kk][2], s[2 * kk][3], F16);
+        pa[2] = pack_h16x2(s[2 * kk + 1][0], s[2 * kk + 1][1], F16);
+        pa[3] = pack_h16x2(s[2 * kk + 1][2], s[2 * kk + 1][3], F16);
 #pragma unroll
         for (int d2 = 0; d2 < 4; ++d2) {
           uint32_t vb[4];     // (keys 0-7, d 0-7)^T (keys 8-15, d 0-7)^T (keys 0-7, d 8-15)^T (keys 8-15, d 8-15)^T
           ldsm_x4_trans(vb, vs_u + (uint32_t)((kc + kk * 16 + (lm & 1) * 8 + lr) * ROW + d2 * 16 + (lm >> 1) * 8) * 2);
-          mma_16816(o[2 * d2], pa, vb[0], vb[1]);
-          mma_16816(o[2 * d2 + 1], pa, vb[2], vb[3]);
+          mma_16816<F16>(o[2 * d2], pa, vb[0], vb[1]);
+          mma_16816<F16>(o[2 * d2 + 1], pa, vb[2], vb[3]);
         }
       }
     }
@@ -256,8 +266,8 @@ __global__ void __launch_bounds__(128, 5) attn_fwd_bf16_kernel(const AttnParams 
 #pragma unroll
   for (int dt = 0; dt < 8; ++dt) {
     const int c = dt * 8 + 2 * tg;
-    if (r0 < pr.Lq) *reinterpret_cast<uint32_t*>(og + (long long)r0 * pr.ldo + c) = pack_bf16x2(o[dt][0] * i0, o[dt][1] * i0);
-    if (r1 < pr.Lq) *reinterpret_cast<uint32_t*>(og + (long long)r1 * pr.ldo + c) = pack_bf16x2(o[dt][2] * i1, o[dt][3] * i1);
+    if (r0 < pr.Lq) *reinterpret_cast<uint32_t*>(og + (long long)r0 * pr.ldo + c) = pack_h16x2(o[dt][0] * i0, o[dt][1] * i0, F16);
+    if (r1 < pr.Lq) *reinterpret_cast<uint32_t*>(og + (long long)r1 * pr.ldo + c) = pack_h16x2(o[dt][2] * i1, o[dt][3] * i1, F16);
   }
   if (pr.lse && tg == 0) {
     float* lg = pr.lse + ((long long)b * p.H + h) * pr.Lq;
@@ -347,7 +357,7 @@ static int check_problem(const vi_attn_problem& a, int H, int dtype, AttnProblem
   VI_CHECK_ARG(!a.pair_dist || a.bias_affine, "vi_attn_fwd: pair_dist needs bias_affine {w,b}");
   const int64_t hd = (int64_t)H * DH;
   VI_CHECK_ARG(a.ldq >= hd && a.ldk >= hd && a.ldv >= hd && a.ldo >= hd, "vi_attn_fwd: leading dimensions smaller than H*64");
-  if (dtype == VI_DT_BF16) {
+  if (dtype != VI_DT_F32) {
     VI_CHECK_ARG(a.ldq % 8 == 0 && a.ldk % 8 == 0 && a.ldv % 8 == 0 && a.ldo % 2 == 0,
                  "vi_attn_fwd: bf16 leading dims must be multiples of 8");
     VI_CHECK_ARG((((uintptr_t)a.q | (uintptr_t)a.k | (uintptr_t)a.v) & 15) == 0 && ((uintptr_t)a.o & 3) == 0,
@@ -356,7 +366,7 @@ static int check_problem(const vi_attn_problem& a, int H, int dtype, AttnProblem
   o.q = a.q; o.ldq = a.ldq; o.k = a.k; o.ldk = a.ldk; o.v = a.v; o.ldv = a.ldv; o.o = a.o; o.ldo = a.ldo;
   o.key_mask = a.key_mask; o.pair_dist = a.pair_dist; o.bias_affine = a.bias_affine; o.lse = a.lse;
   o.B = a.B; o.Lq = a.Lq; o.Lk = a.Lk; o.LkP = (a.Lk + 15) & ~15;
-  VI_CHECK_ARG(a.drop_p >= 0.f && a.drop_p < 1.f && (a.drop_p == 0.f || (a.drop_seed && dtype == VI_DT_BF16)),
+  VI_CHECK_ARG(a.drop_p >= 0.f && a.drop_p < 1.f && (a.drop_p == 0.f || (a.drop_seed && dtype != VI_DT_F32)),
                "vi_attn_fwd: attention dropout needs 0 <= p < 1, a device seed pointer and the bf16 kernel");
   o.drop_thresh = a.drop_p > 0.f ? vi_drop_threshold(a.drop_p) : 0u;
   if (a.drop_p > 0.f && o.drop_thresh == 0u) o.drop_thresh = 1u;
@@ -371,7 +381,7 @@ extern "C" int vi_attn_fwd_multi(const vi_attn_problem* problems, int n_problems
                VI_ATTN_MAX_PROBLEMS);
   VI_CHECK_ARG(H > 0, "vi_attn_fwd_multi: H must be positive");
   VI_CHECK_ARG(mask_mode == VI_MASK_ADD_NEG10000 || mask_mode == VI_MASK_NEG_INF, "vi_attn_fwd: bad mask_mode");
-  VI_CHECK_ARG(dtype == VI_DT_BF16 || dtype == VI_DT_F32, "vi_attn_fwd: bad dtype %d", dtype);
+  VI_CHECK_ARG(dtype == VI_DT_BF16 || dtype == VI_DT_F32 || dtype == VI_DT_F16, "vi_attn_fwd: bad dtype %d", dtype);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   AttnParams p;
   memset(&p, 0, sizeof(p));
@@ -383,13 +393,14 @@ extern "C" int vi_attn_fwd_multi(const vi_attn_problem* problems, int n_problems
     max_lq = p.pr[i].Lq > max_lq ? p.pr[i].Lq : max_lq;
     max_lkp = p.pr[i].LkP > max_lkp ? p.pr[i].LkP : max_lkp;
   }
-  if (dtype == VI_DT_BF16) {
+  if (dtype != VI_DT_F32) {
     const int q_tiles = (max_lq + 15) / 16;
     const int nwarp = q_tiles < 4 ? q_tiles : 4;
     const int qrows = nwarp * 16;
     const size_t smem = (size_t)max_lkp * ROW * 2 * 2 + (size_t)qrows * ROW * 2 + (size_t)max_lkp * 4;
     dim3 grid((max_lq + qrows - 1) / qrows, H, total_b);
-    VI_CUDA(vi_launch(attn_fwd_bf16_kernel, dim3(grid), dim3(nwarp * 32), (size_t)(smem), st, p));
+    if (dtype == VI_DT_F16) VI_CUDA(vi_launch(attn_fwd_bf16_kernel<true>, dim3(grid), dim3(nwarp * 32), (size_t)(smem), st, p));
+    else VI_CUDA(vi_launch(attn_fwd_bf16_kernel<false>, dim3(grid), dim3(nwarp * 32), (size_t)(smem), st, p));
     VI_LAUNCH_CHECK();
   } else {
     for (int i = 0; i < n_problems; ++i) {
@@ -416,8 +427,10 @@ extern "C" int vi_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ld
 }
 
 int vi_attn_init() {
-  VI_CUDA(cudaFuncSetAttribute(attn_fwd_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 176 * 1024));
-  VI_CUDA(cudaFuncSetAttribute(attn_fwd_bf16_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  VI_CUDA(cudaFuncSetAttribute(attn_fwd_bf16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 176 * 1024));
+  VI_CUDA(cudaFuncSetAttribute(attn_fwd_bf16_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  VI_CUDA(cudaFuncSetAttribute(attn_fwd_bf16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 176 * 1024));
+  VI_CUDA(cudaFuncSetAttribute(attn_fwd_bf16_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   VI_CUDA(cudaFuncSetAttribute(attn_fwd_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   return VI_OK;
 }

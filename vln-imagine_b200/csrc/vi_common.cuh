@@ -117,6 +117,14 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&t);
 }
 
+// 16-bit operand formats of the forward kernels: bf16, or fp16 with saturation (+-65504 instead of inf) - see vi_gemm16
+__device__ __forceinline__ uint32_t pack_f16x2_sat(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+__device__ __forceinline__ uint32_t pack_h16x2(float lo, float hi, bool f16) { return f16 ? pack_f16x2_sat(lo, hi) : pack_bf16x2(lo, hi); }
+
 template <typename T> __device__ __forceinline__ float to_f32(T v);
 template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
 template <> __device__ __forceinline__ float to_f32<bf16>(bf16 v) { return __bfloat162float(v); }

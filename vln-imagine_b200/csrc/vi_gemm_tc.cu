@@ -32,14 +32,28 @@ constexpr int MAX_GROUPS = 4;
 constexpr int EPI_WARPS = 8;
 constexpr int NUM_THREADS = 128 + EPI_WARPS * 32;
 constexpr int MAX_CPW = 4;                             // 32-column chunks per epilogue warp per tile (BN <= 256)
-constexpr int BIAS_BYTES = EPI_WARPS * 2 * 32 * 4;     // per epilogue warp: the bias slice of the current and the next chunk
-// staging per epilogue warp: two buffers of 32 rows x 32 columns (fp32: 128-byte rows, bf16: 64-byte rows)
-__host__ __device__ constexpr int epi_buf_bytes(bool f32out) { return f32out ? 4096 : 2048; }
-__host__ __device__ constexpr int epi_bytes(bool f32out) { return EPI_WARPS * 2 * epi_buf_bytes(f32out); }
+// per epilogue warp: the two per-column vectors of the current chunk (bias | folded constant, LayerNorm vector), 32 floats
+// each; the next chunk's slices wait in registers until the current ones have been read
+constexpr int VEC_BYTES = EPI_WARPS * 2 * 32 * 4;
+// what the epilogue writes: a 16-bit tile (bf16 / fp16), an fp32 tile, or both (fp32 residual stream + 16-bit operand copy)
+enum { OUT_H16 = 0, OUT_F32 = 1, OUT_DUAL = 2 };
+// staging per epilogue warp: two buffers of 32 rows x 32 columns (fp32: 128-byte rows; 16-bit: 64-byte rows; dual: both, fp32 first)
+__host__ __device__ constexpr int epi_buf_bytes(int om) { return om == OUT_H16 ? 2048 : (om == OUT_F32 ? 4096 : 6144); }
+__host__ __device__ constexpr int epi_bytes(int om) { return EPI_WARPS * 2 * epi_buf_bytes(om); }
 constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;            // clears the CTA-rank bit of a shared::cluster address (pair leader)
 
+enum { LN_NONE = 0, LN_FOLD = 1, LN_RESIDUAL = 2 };
+
 struct GemmParams {
-  const float* bias;
+  const float* bias;               // [n_groups * N]; LN_FOLD: the folded constant c = W beta + b; LN_RESIDUAL: beta + b
+  const float* vec_a;              // LN_FOLD: s = row sums of the folded weight; LN_RESIDUAL: gamma   ([n_groups * N])
+  const float2* stats_in;          // [stats_chunks][stats_ld] (mean, M2) of every 32-column chunk of the rows to normalise
+  float2* stats_out;               // [N / 32][stats_ld] (mean, M2) of every 32-column chunk of the output rows, or NULL
+  long long stats_ld;
+  int stats_chunks;
+  int ln_mode;
+  float ln_eps;
+  int fmt_f16;                     // 16-bit operands / outputs are fp16 (else bf16)
   int has_residual;
   int y_f32;
   int M, N, K;
@@ -63,27 +77,47 @@ __device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t saddr) {
   return d;
 }
 
-__host__ __device__ constexpr uint32_t make_idesc(int mma_m, int mma_n) {
-  // kind::f16 instruction descriptor: D=f32 (bits 4-5 = 1), A=B=bf16 (bits 7-9, 10-12 = 1), both operands
-  // K-major (bits 15,16 = 0), N>>3 at bits 17-22, M>>4 at bits 24-28.
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(mma_n >> 3) << 17) | ((uint32_t)(mma_m >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc(int mma_m, int mma_n, bool f16) {
+  // kind::f16 instruction descriptor: D=f32 (bits 4-5 = 1), A / B format at bits 7-9 / 10-12 (0 = fp16, 1 = bf16),
+  // both operands K-major (bits 15,16 = 0), N>>3 at bits 17-22, M>>4 at bits 24-28.
+  return (1u << 4) | (f16 ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(mma_n >> 3) << 17) | ((uint32_t)(mma_m >> 4) << 24);
 }
 
-// erf by Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7): two MUFU ops instead of erff's branchy polynomial.  The
-// GELU output of this kernel is rounded to bf16 (relative step 4e-3), so the approximation is invisible.
-__device__ __forceinline__ float gelu_fast(float x) {
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  float t;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));      // MUFU.RCP, 1 ulp
-  float poly = fmaf(t, 1.061405429f, -1.453152027f);
-  poly = fmaf(t, poly, 1.421413741f);
-  poly = fmaf(t, poly, -0.284496736f);
-  poly = fmaf(t, poly, 0.254829592f);
-  poly *= t;
-  const float erf_abs = fmaf(-poly, __expf(-z * z), 1.0f);
-  return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+// Packed fp32 pair arithmetic (FFMA2 on sm_100): one instruction for two elements.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
 }
+__device__ __forceinline__ float2 bcast2(float v) { return make_float2(v, v); }
 
+// erf-form GELU (D/models/vilmodel.py:32-38) of two elements without any MUFU op: erf(x / sqrt 2) is an odd degree-19
+// polynomial in t = clamp(x, +-4.5) / 4.5 (least-squares fit on Chebyshev nodes; |erf error| < 8e-6 on the interval,
+// erfc(4.5 / sqrt 2) = 6.8e-6 beyond it), evaluated with packed FFMA2: 13 packed + 4 scalar instructions per PAIR.
+// Measured against the exact form over x ~ N(0, 1): RMS error = 0.3 % of the bf16 rounding error of the result.
+// The A&S 7.1.26 form it replaces cost two MUFU ops and ~14 FMAs per ELEMENT and was the exposed part of the FFN1 epilogue.
+__device__ __forceinline__ void gelu_pair(float& x0, float& x1) {
+  const float2 x = make_float2(x0, x1);
+  const float2 xc = make_float2(fminf(fmaxf(x0, -4.5f), 4.5f), fminf(fmaxf(x1, -4.5f), 4.5f));
+  const float2 t = ffma2(xc, bcast2(1.0f / 4.5f), bcast2(0.f));
+  const float2 u = ffma2(t, t, bcast2(0.f));
+  float2 p = bcast2(-8.882999948e+00f);
+  p = ffma2(p, u, bcast2(5.144924412e+01f));
+  p = ffma2(p, u, bcast2(-1.328671530e+02f));
+  p = ffma2(p, u, bcast2(2.037066147e+02f));
+  p = ffma2(p, u, bcast2(-2.090744719e+02f));
+  p = ffma2(p, u, bcast2(1.541237008e+02f));
+  p = ffma2(p, u, bcast2(-8.545582162e+01f));
+  p = ffma2(p, u, bcast2(3.651658807e+01f));
+  p = ffma2(p, u, bcast2(-1.210606152e+01f));
+  p = ffma2(p, u, bcast2(3.590346739e+00f));
+  const float2 e = ffma2(p, t, bcast2(0.f));                 // erf(x / sqrt 2)
+  const float2 hx = ffma2(x, bcast2(0.5f), bcast2(0.f));
+  const float2 r = ffma2(hx, e, hx);
+  x0 = r.x; x1 = r.y;
+}
 // ---- PTX helpers that exist only for this kernel ---------------------------------------------------------------
 __device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
@@ -157,18 +191,21 @@ template <bool PAIR> __device__ __forceinline__ void tmem_dealloc_t(uint32_t tad
 
 __host__ __device__ constexpr uint32_t tmem_cols_for(int bn) { return 2 * bn <= 128 ? 128u : (2 * bn <= 256 ? 256u : 512u); }
 
-template <int BN, int STAGES, bool PAIR, bool F32OUT>
+template <int BN, int STAGES, bool PAIR, int OUTMODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR,
-                    const GemmParams p) {
+                    const __grid_constant__ CUtensorMap tmY2, const GemmParams p) {
   constexpr int BN_CTA = PAIR ? BN / 2 : BN;         // rows of the W tile this CTA stages
   constexpr int A_BYTES = BM * BK * 2;
   constexpr int B_BYTES = BN_CTA * BK * 2;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr uint32_t TMEM_COLS = tmem_cols_for(BN);
   constexpr int NCHUNK = BN / 32;                    // 32-column epilogue chunks per tile
-  constexpr int EPI_BUF = epi_buf_bytes(F32OUT);
+  constexpr int EPI_BUF = epi_buf_bytes(OUTMODE);
+  constexpr bool HAS_F32 = OUTMODE != OUT_H16;       // fp32 tile staged at offset 0 of a buffer
+  constexpr bool HAS_H16 = OUTMODE != OUT_F32;       // 16-bit tile staged at offset 0 (OUT_H16) or 4096 (OUT_DUAL)
+  constexpr uint32_t H16_OFF = OUTMODE == OUT_DUAL ? 4096u : 0u;
   constexpr int TILES_PER_M = PAIR ? 2 : 1;          // 128-row tiles per m index
   static_assert(BN % 32 == 0 && BN >= 64 && BN <= 256, "tile N");
   static_assert(A_BYTES % 1024 == 0 && B_BYTES % 1024 == 0, "operand tiles must keep the 1024-byte swizzle alignment");
@@ -177,8 +214,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   // and is 1024-byte aligned, which the 128B-swizzled tiles need (checked below: a misaligned base traps).
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* epi_smem = smem + STAGES * STAGE_BYTES;
-  float* bias_smem = reinterpret_cast<float*>(epi_smem + epi_bytes(F32OUT));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + epi_bytes(F32OUT) + BIAS_BYTES);
+  float* vec_smem = reinterpret_cast<float*>(epi_smem + epi_bytes(OUTMODE));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + epi_bytes(OUTMODE) + VEC_BYTES);
   // barrier slots: full[S], empty[S], tfull[2], tempty[2], rbar[EPI_WARPS][2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4 + 2 * EPI_WARPS);
 
@@ -206,6 +243,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmY);
     if (p.has_residual) tma_prefetch_desc(&tmR);
+    if (OUTMODE == OUT_DUAL) tma_prefetch_desc(&tmY2);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -266,7 +304,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   } else if (warp == 1) {
     // ------------------------------- MMA issuer (pair: leader only; warp converged, elected lane issues) ----
     if (rank == 0) {
-      constexpr uint32_t idesc = make_idesc(PAIR ? 256 : 128, BN);
+      const uint32_t idesc = make_idesc(PAIR ? 256 : 128, BN, p.fmt_f16 != 0);
       int s = 0, it = 0;
       uint32_t ph = 0;
       for (int t = worker; t < total_tiles; t += n_workers, ++it) {
@@ -302,22 +340,37 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     constexpr int CPW0 = (NCHUNK + 1) / 2, CPW1 = NCHUNK / 2;
     const int cpw = half ? CPW1 : CPW0;               // chunks per tile for this warp: half, half+2, ...
     const uint32_t my_buf = epi_base + (uint32_t)(ew * 2 * EPI_BUF);
-    float* my_bias = bias_smem + ew * 2 * 32;         // [2][32]: bias slice of chunk n in buffer n & 1
-    const uint32_t my_bias_u = smem_u32(my_bias);
+    float* my_vec = vec_smem + ew * 64;               // [2][32]: per-column vectors of the current chunk
+    const uint32_t my_vec_u = smem_u32(my_vec);
     const bool res = p.has_residual != 0;
+    const int ln_mode = p.ln_mode;
     const int row_in_tile = (int)rank * BM + quarter * 32;
+    const bool has_v0 = p.bias != nullptr, has_v1 = p.vec_a != nullptr;
 
     auto issue_residual = [&](int n, int row0, int col0) {          // lane 0 only
       const uint32_t bar = res_bar(ew, n & 1);
       mbar_expect_tx(bar, 4096);
       tma_load_2d(my_buf + (uint32_t)((n & 1) * EPI_BUF), &tmR, bar, col0, row0);
     };
+    // this lane's elements of the per-column vectors for (group g, column c)
+    auto load_vecs = [&](int g, int c, float& a0, float& a1) {
+      const long long o = (long long)g * p.N + c + lane;
+      a0 = has_v0 ? *(p.bias + o) : 0.f;
+      a1 = has_v1 ? *(p.vec_a + o) : 0.f;
+    };
+    auto park_vecs = [&](float a0, float a1) {
+      float* d = my_vec + lane;
+      if (has_v0) d[0] = a0;
+      if (has_v1) d[32] = a1;
+    };
 
     int n = 0, it = 0;
     if (worker < total_tiles) {
       const int mt = worker / p.num_n_tiles, nt = worker - mt * p.num_n_tiles;
       if (res && lane == 0) issue_residual(0, mt * TILES_PER_M * BM + row_in_tile, nt * BN + half * 32);
-      if (p.bias) my_bias[lane] = (*(p.bias + (long long)group_of(mt * TILES_PER_M) * p.N + nt * BN + half * 32 + lane));
+      float a0, a1;
+      load_vecs(group_of(mt * TILES_PER_M), nt * BN + half * 32, a0, a1);
+      park_vecs(a0, a1);
       __syncwarp();
     }
     for (int t = worker; t < total_tiles; t += n_workers, ++it) {
@@ -329,10 +382,32 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int tn = t + n_workers;
       const int mtn = tn / p.num_n_tiles, ntn = tn - mtn * p.num_n_tiles;
       const int row0n = mtn * TILES_PER_M * BM + row_in_tile, tcol0n = ntn * BN + half * 32;
+      const int gn = tn < total_tiles ? group_of(mtn * TILES_PER_M) : g;
       const int acc = it & 1;
       const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
-      const float* bias_g = p.bias ? p.bias + (long long)g * p.N : nullptr;
-      const float* bias_gn = (p.bias && tn < total_tiles) ? p.bias + (long long)group_of(mtn * TILES_PER_M) * p.N : nullptr;
+      const long long grow = (long long)row0 + lane;  // this thread's output row
+      const bool row_ok = grow < p.M;
+
+      // LayerNorm statistics of this thread's row from the producer's per-chunk (mean, M2) partials (Chan's combination
+      // of equal-sized groups), fetched while the main loop of the tile is still running
+      float rstd = 1.f, rm = 0.f;                     // 1 / sigma and mu / sigma
+      if (ln_mode != LN_NONE) {
+        float sm = 0.f, sq = 0.f, m2 = 0.f;
+        if (row_ok) {
+          const float2* sp = p.stats_in + grow;
+#pragma unroll 8
+          for (int c = 0; c < p.stats_chunks; ++c) {
+            const float2 pr = *(sp + (long long)c * p.stats_ld);
+            sm += pr.x; sq = fmaf(pr.x, pr.x, sq); m2 += pr.y;
+          }
+        }
+        const float inv_c = 1.0f / (float)p.stats_chunks;
+        const float mean = sm * inv_c;
+        const float var = fmaxf((m2 + 32.0f * (sq - sm * mean)) * inv_c * (1.0f / 32.0f), 0.f);
+        rstd = rsqrtf(var + p.ln_eps);
+        rm = rstd * mean;
+      }
+
       mbar_wait(tfull_bar(acc), acc_ph);
       tc_fence_after();
       const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + half * 32);
@@ -342,10 +417,11 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       for (int k = 0; k < MAX_CPW; ++k) {
         if (k < cpw) {
           const uint32_t buf = my_buf + (uint32_t)((n & 1) * EPI_BUF);
+          const uint32_t vec_u = my_vec_u;
           const int col0 = tcol0 + k * 64;
+          const bool last = k == cpw - 1;
           if (lane == 0) {
             if (res) {
-              const bool last = k == cpw - 1;
               if (!last || tn < total_tiles) {
                 bulk_wait_read<0>();                  // the store that last used the other buffer has read it
                 issue_residual(n + 1, last ? row0n : row0, last ? tcol0n : col0 + 64);
@@ -354,12 +430,12 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               bulk_wait_read<1>();                    // the store issued two chunks ago has read this buffer
             }
           }
-          // bias slice of the NEXT chunk (possibly the first one of the next tile): loaded now, parked at the end
-          float bias_next = 0.f;
-          if (k + 1 < cpw) { if (bias_g) bias_next = (*(bias_g + col0 + 64 + lane)); }
-          else if (bias_gn) bias_next = (*(bias_gn + tcol0n + lane));
+          // per-column vectors of the NEXT chunk (possibly the first one of the next tile): loaded now, parked at the end
+          float nv0 = 0.f, nv1 = 0.f;
+          if (!last) load_vecs(g, col0 + 64, nv0, nv1);
+          else if (tn < total_tiles) load_vecs(gn, tcol0n, nv0, nv1);
           tmem_ld_wait();
-          if (k + 1 < cpw) {
+          if (!last) {
             tmem_ld_32x32(tbase + (uint32_t)((k + 1) * 64), r[(k + 1) & 1]);   // next chunk in flight during the math
           } else {                                    // accumulator fully read by this warp: hand it back early
             tc_fence_before();
@@ -371,18 +447,30 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[k & 1][j]);
-          if (p.bias) {
+          if (ln_mode == LN_FOLD) {
+            // LayerNorm folded into the weights: y = (acc - mu * s_n) / sigma + c_n   (W gamma in the operand, s = its row sums)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 c4, s4;
+              asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(c4.x), "=f"(c4.y), "=f"(c4.z), "=f"(c4.w) : "r"(vec_u + (uint32_t)(j * 16)));
+              asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(s4.x), "=f"(s4.y), "=f"(s4.z), "=f"(s4.w) : "r"(vec_u + (uint32_t)(128 + j * 16)));
+              v[4 * j] = fmaf(rstd, v[4 * j], fmaf(-rm, s4.x, c4.x));
+              v[4 * j + 1] = fmaf(rstd, v[4 * j + 1], fmaf(-rm, s4.y, c4.y));
+              v[4 * j + 2] = fmaf(rstd, v[4 * j + 2], fmaf(-rm, s4.z, c4.z));
+              v[4 * j + 3] = fmaf(rstd, v[4 * j + 3], fmaf(-rm, s4.w, c4.w));
+            }
+          } else if (has_v0 && ln_mode != LN_RESIDUAL) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               float4 b;
               asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
-                           : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "r"(my_bias_u + (uint32_t)((n & 1) * 128 + j * 16)));
+                           : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "r"(vec_u + (uint32_t)(j * 16)));
               v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
             }
           }
           if (p.epilogue == VI_EPI_GELU) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
+            for (int j = 0; j < 16; ++j) gelu_pair(v[2 * j], v[2 * j + 1]);
           } else if (p.epilogue == VI_EPI_RELU) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
@@ -397,31 +485,63 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               float4 q;
               asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
                            : "=f"(q.x), "=f"(q.y), "=f"(q.z), "=f"(q.w) : "r"(rowb + (uint32_t)((j ^ (lane & 7)) << 4)));
+              if (ln_mode == LN_RESIDUAL) {
+                // the residual is LayerNorm(raw) of the producer: (raw - mu) / sigma * gamma + beta, from the raw fp32 rows
+                // (the vector in slot 0 is beta + this layer's bias)
+                float4 g4, b4;
+                asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(g4.x), "=f"(g4.y), "=f"(g4.z), "=f"(g4.w) : "r"(vec_u + (uint32_t)(128 + j * 16)));
+                asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b4.x), "=f"(b4.y), "=f"(b4.z), "=f"(b4.w) : "r"(vec_u + (uint32_t)(j * 16)));
+                q.x = fmaf(fmaf(q.x, rstd, -rm), g4.x, b4.x);
+                q.y = fmaf(fmaf(q.y, rstd, -rm), g4.y, b4.y);
+                q.z = fmaf(fmaf(q.z, rstd, -rm), g4.z, b4.z);
+                q.w = fmaf(fmaf(q.w, rstd, -rm), g4.w, b4.w);
+              }
               v[4 * j] += q.x; v[4 * j + 1] += q.y; v[4 * j + 2] += q.z; v[4 * j + 3] += q.w;
             }
           }
-          if constexpr (F32OUT) {
+          if (p.stats_out) {
+            // (mean, M2) of this row's 32 columns: the consumer of the LayerNorm that follows combines the chunks
+            float sm = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sm += v[j];
+            const float mean = sm * (1.0f / 32.0f);
+            float m2 = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { const float d = v[j] - mean; m2 = fmaf(d, d, m2); }
+            if (row_ok) *(p.stats_out + (long long)(col0 >> 5) * p.stats_ld + grow) = make_float2(mean, m2);
+          }
+          if constexpr (HAS_F32) {
             const uint32_t rowb = buf + (uint32_t)(lane * 128);
 #pragma unroll
             for (int j = 0; j < 8; ++j)
               asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};"
                            ::"r"(rowb + (uint32_t)((j ^ (lane & 7)) << 4)), "f"(v[4 * j]), "f"(v[4 * j + 1]), "f"(v[4 * j + 2]),
                            "f"(v[4 * j + 3]) : "memory");
-          } else {
-            // bf16 rows are 64 B, 64B-swizzled: chunk j of row r sits at j ^ ((r >> 1) & 3)
-            const uint32_t rowb = buf + (uint32_t)(lane * 64);
+          }
+          if constexpr (HAS_H16) {
+            // 16-bit rows are 64 B, 64B-swizzled: chunk j of row r sits at j ^ ((r >> 1) & 3)
+            const uint32_t rowb = buf + H16_OFF + (uint32_t)(lane * 64);
+            uint32_t h[16];
+            if (p.fmt_f16) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) h[j] = pack_f16x2_sat(v[2 * j], v[2 * j + 1]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) h[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+            }
 #pragma unroll
             for (int j = 0; j < 4; ++j)
               asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};"
-                           ::"r"(rowb + (uint32_t)((j ^ ((lane >> 1) & 3)) << 4)), "r"(pack_bf16x2(v[8 * j], v[8 * j + 1])),
-                           "r"(pack_bf16x2(v[8 * j + 2], v[8 * j + 3])), "r"(pack_bf16x2(v[8 * j + 4], v[8 * j + 5])),
-                           "r"(pack_bf16x2(v[8 * j + 6], v[8 * j + 7])) : "memory");
+                           ::"r"(rowb + (uint32_t)((j ^ ((lane >> 1) & 3)) << 4)), "r"(h[4 * j]), "r"(h[4 * j + 1]),
+                           "r"(h[4 * j + 2]), "r"(h[4 * j + 3]) : "memory");
           }
-          if (p.bias) my_bias[((n + 1) & 1) * 32 + lane] = bias_next;
+          __syncwarp();                               // every lane has read the current vectors
+          park_vecs(nv0, nv1);
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) {
             tma_store_2d(&tmY, buf, col0, row0);      // rows beyond M are clipped by the tensor map
+            if constexpr (OUTMODE == OUT_DUAL) tma_store_2d(&tmY2, buf + H16_OFF, col0, row0);
             bulk_commit();
           }
           ++n;
@@ -481,27 +601,28 @@ int make_map(CUtensorMap* map, const void* ptr, CUtensorMapDataType dt, int elem
   return VI_OK;
 }
 
-template <int BN, int STAGES, bool PAIR, bool F32OUT>
+template <int BN, int STAGES, bool PAIR, int OUTMODE>
 constexpr int smem_bytes() {
-  return STAGES * (BM * BK * 2 + (PAIR ? BN / 2 : BN) * BK * 2) + epi_bytes(F32OUT) + BIAS_BYTES +
+  return STAGES * (BM * BK * 2 + (PAIR ? BN / 2 : BN) * BK * 2) + epi_bytes(OUTMODE) + VEC_BYTES +
          (2 * STAGES + 4 + 2 * EPI_WARPS) * 8 + 16;
 }
 
-template <int BN, int STAGES, bool PAIR, bool F32OUT>
-int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY, const CUtensorMap& tmR,
-           const GemmParams& p, int grid, cudaStream_t st) {
-  static_assert(smem_bytes<BN, STAGES, PAIR, F32OUT>() <= 232448, "shared memory budget");
+struct Maps { CUtensorMap a, b, y, r, y2; };
+
+template <int BN, int STAGES, bool PAIR, int OUTMODE>
+int launch(const Maps& m, const GemmParams& p, int grid, cudaStream_t st) {
+  static_assert(smem_bytes<BN, STAGES, PAIR, OUTMODE>() <= 232448, "shared memory budget");
   static bool attr_set = false;          // idempotent; races only repeat the same call
-  auto kern = gemm_bf16_tc_kernel<BN, STAGES, PAIR, F32OUT>;
+  auto kern = gemm_bf16_tc_kernel<BN, STAGES, PAIR, OUTMODE>;
   if (!attr_set) {
-    VI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<BN, STAGES, PAIR, F32OUT>()));
+    VI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<BN, STAGES, PAIR, OUTMODE>()));
     attr_set = true;
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(NUM_THREADS);
-  cfg.dynamicSmemBytes = smem_bytes<BN, STAGES, PAIR, F32OUT>();
+  cfg.dynamicSmemBytes = smem_bytes<BN, STAGES, PAIR, OUTMODE>();
   cfg.stream = st;
   cudaLaunchAttribute attr[2];
   int nattr = 0;
@@ -519,7 +640,7 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tm
   }
   cfg.attrs = attr;
   cfg.numAttrs = nattr;
-  VI_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmY, tmR, p));
+  VI_CUDA(cudaLaunchKernelEx(&cfg, kern, m.a, m.b, m.y, m.r, m.y2, p));
   return VI_OK;
 }
 
@@ -572,49 +693,79 @@ extern "C" int vi_gemm_bf16(const void* x, int64_t ldx, const void* w, const flo
 extern "C" int vi_gemm_bf16_tiled(const void* x, int64_t ldx, const void* w, const float* bias, const float* residual,
                                   int64_t ldr, void* y, int64_t ldy, int y_dtype, int M, int N, int K, int epilogue,
                                   int n_groups, const int32_t* group_row_end, int tile, vi_stream_t stream) {
-  VI_CHECK_ARG(x && w && y, "vi_gemm_bf16: null operand");
-  VI_CHECK_ARG(M > 0 && N > 0 && K > 0, "vi_gemm_bf16: empty problem M=%d N=%d K=%d", M, N, K);
-  VI_CHECK_ARG(K % BK == 0, "vi_gemm_bf16: K=%d must be a multiple of %d", K, BK);
-  VI_CHECK_ARG(N % 64 == 0, "vi_gemm_bf16: N=%d must be a multiple of 64", N);
-  VI_CHECK_ARG(ldx % 8 == 0 && ldx >= K, "vi_gemm_bf16: ldx=%lld must be >= K and a multiple of 8", (long long)ldx);
-  VI_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)w & 15) == 0 && ((uintptr_t)y & 15) == 0,
-               "vi_gemm_bf16: operands must be 16-byte aligned");
-  VI_CHECK_ARG(ldy >= N && ldy % 8 == 0, "vi_gemm_bf16: ldy=%lld must be >= N and a multiple of 8", (long long)ldy);
-  VI_CHECK_ARG(!residual || (ldr >= N && ldr % 4 == 0 && ((uintptr_t)residual & 15) == 0),
-               "vi_gemm_bf16: residual must be 16-byte aligned with ldr >= N, ldr %% 4 == 0");
-  VI_CHECK_ARG(!bias || ((uintptr_t)bias & 15) == 0, "vi_gemm_bf16: bias must be 16-byte aligned");
-  VI_CHECK_ARG(!residual || y_dtype == VI_DT_F32,
-               "vi_gemm_bf16: a residual needs an fp32 output (the residual stream of the model is fp32)");
-  VI_CHECK_ARG(y_dtype == VI_DT_BF16 || y_dtype == VI_DT_F32, "vi_gemm_bf16: bad y_dtype %d", y_dtype);
-  VI_CHECK_ARG(epilogue >= VI_EPI_NONE && epilogue <= VI_EPI_RELU, "vi_gemm_bf16: bad epilogue %d", epilogue);
-  VI_CHECK_ARG(n_groups >= 1 && n_groups <= MAX_GROUPS, "vi_gemm_bf16: n_groups=%d out of range", n_groups);
-  VI_CHECK_ARG(n_groups == 1 || group_row_end, "vi_gemm_bf16: grouped call without group_row_end");
+  vi_gemm_args a;
+  memset(&a, 0, sizeof(a));
+  a.x = x; a.ldx = ldx; a.w = w; a.in_dtype = VI_DT_BF16; a.bias = bias; a.residual = residual; a.ldr = ldr;
+  a.y = y; a.ldy = ldy; a.y_dtype = y_dtype; a.M = M; a.N = N; a.K = K; a.epilogue = epilogue; a.n_groups = n_groups;
+  a.group_row_end = group_row_end; a.tile = tile;
+  return vi_gemm16(&a, stream);
+}
+
+extern "C" int vi_gemm16(const vi_gemm_args* args, vi_stream_t stream) {
+  VI_CHECK_ARG(args, "vi_gemm16: null args");
+  const vi_gemm_args& a = *args;
+  const int M = a.M, N = a.N, K = a.K, n_groups = a.n_groups;
+  VI_CHECK_ARG(a.x && a.w && a.y, "vi_gemm16: null operand");
+  VI_CHECK_ARG(M > 0 && N > 0 && K > 0, "vi_gemm16: empty problem M=%d N=%d K=%d", M, N, K);
+  VI_CHECK_ARG(K % BK == 0, "vi_gemm16: K=%d must be a multiple of %d", K, BK);
+  VI_CHECK_ARG(N % 64 == 0, "vi_gemm16: N=%d must be a multiple of 64", N);
+  VI_CHECK_ARG(a.in_dtype == VI_DT_BF16 || a.in_dtype == VI_DT_F16, "vi_gemm16: operands must be bf16 or fp16 (in_dtype %d)", a.in_dtype);
+  VI_CHECK_ARG(a.ldx % 8 == 0 && a.ldx >= K, "vi_gemm16: ldx=%lld must be >= K and a multiple of 8", (long long)a.ldx);
+  VI_CHECK_ARG(((uintptr_t)a.x & 15) == 0 && ((uintptr_t)a.w & 15) == 0 && ((uintptr_t)a.y & 15) == 0,
+               "vi_gemm16: operands must be 16-byte aligned");
+  VI_CHECK_ARG(a.ldy >= N && a.ldy % 8 == 0, "vi_gemm16: ldy=%lld must be >= N and a multiple of 8", (long long)a.ldy);
+  VI_CHECK_ARG(!a.residual || (a.ldr >= N && a.ldr % 4 == 0 && ((uintptr_t)a.residual & 15) == 0),
+               "vi_gemm16: residual must be 16-byte aligned with ldr >= N, ldr %% 4 == 0");
+  VI_CHECK_ARG(!a.bias || ((uintptr_t)a.bias & 15) == 0, "vi_gemm16: bias must be 16-byte aligned");
+  VI_CHECK_ARG(a.y_dtype == a.in_dtype || a.y_dtype == VI_DT_F32, "vi_gemm16: y_dtype %d must be fp32 or the operand type", a.y_dtype);
+  VI_CHECK_ARG(!a.residual || a.y_dtype == VI_DT_F32,
+               "vi_gemm16: a residual needs an fp32 output (the residual stream of the model is fp32)");
+  VI_CHECK_ARG(!a.y16 || (a.y_dtype == VI_DT_F32 && a.ldy16 >= N && a.ldy16 % 8 == 0 && ((uintptr_t)a.y16 & 15) == 0),
+               "vi_gemm16: the 16-bit copy needs an fp32 primary output, ldy16 >= N, ldy16 %% 8 == 0, 16-byte alignment");
+  VI_CHECK_ARG(a.epilogue >= VI_EPI_NONE && a.epilogue <= VI_EPI_RELU, "vi_gemm16: bad epilogue %d", a.epilogue);
+  VI_CHECK_ARG(n_groups >= 1 && n_groups <= MAX_GROUPS, "vi_gemm16: n_groups=%d out of range", n_groups);
+  VI_CHECK_ARG(n_groups == 1 || a.group_row_end, "vi_gemm16: grouped call without group_row_end");
+  VI_CHECK_ARG(a.ln_mode >= VI_LN_NONE && a.ln_mode <= VI_LN_RESIDUAL, "vi_gemm16: bad ln_mode %d", a.ln_mode);
+  if (a.ln_mode != VI_LN_NONE) {
+    VI_CHECK_ARG(a.ln_stats && a.ln_chunks > 0 && a.ln_chunks <= 256 && a.stats_ld >= M,
+                 "vi_gemm16: LayerNorm modes need ln_stats, ln_chunks and stats_ld >= M");
+    VI_CHECK_ARG(a.ln_mode != VI_LN_FOLD || (a.bias && a.ln_vec_a), "vi_gemm16: VI_LN_FOLD needs bias (= W beta + b) and ln_vec_a (row sums)");
+    VI_CHECK_ARG(a.ln_mode != VI_LN_RESIDUAL || (a.residual && a.bias && a.ln_vec_a && a.ln_chunks * 32 == N && a.epilogue == VI_EPI_NONE),
+                 "vi_gemm16: VI_LN_RESIDUAL needs residual, bias (= beta + b), gamma, N == 32 * ln_chunks and no activation");
+  }
+  VI_CHECK_ARG(!a.stats_out || a.stats_ld >= M, "vi_gemm16: stats_out needs stats_ld >= M");
+  VI_CHECK_ARG(((uintptr_t)a.ln_stats & 7) == 0 && ((uintptr_t)a.stats_out & 7) == 0, "vi_gemm16: statistics must be 8-byte aligned");
   if (int rc = resolve_encode()) return rc;
 
   GemmParams p;
   memset(&p, 0, sizeof(p));
-  p.bias = bias; p.has_residual = residual != nullptr; p.y_f32 = (y_dtype == VI_DT_F32);
-  p.M = M; p.N = N; p.K = K; p.epilogue = epilogue; p.n_groups = n_groups;
+  p.bias = a.bias; p.has_residual = a.residual != nullptr; p.y_f32 = (a.y_dtype == VI_DT_F32);
+  p.M = M; p.N = N; p.K = K; p.epilogue = a.epilogue; p.n_groups = n_groups;
+  p.vec_a = a.ln_mode != VI_LN_NONE ? a.ln_vec_a : nullptr;
+  p.stats_in = reinterpret_cast<const float2*>(a.ln_stats);
+  p.stats_out = reinterpret_cast<float2*>(a.stats_out);
+  p.stats_ld = a.stats_ld; p.stats_chunks = a.ln_chunks; p.ln_mode = a.ln_mode; p.ln_eps = a.ln_eps;
+  p.fmt_f16 = a.in_dtype == VI_DT_F16;
   bool pair_ok = true;                   // a 256-row pair tile must not straddle two weight groups
   const int m_tiles128 = (M + BM - 1) / BM;
   for (int g = 0; g < n_groups; ++g) {
     if (n_groups == 1) { p.group_tile_end[g] = m_tiles128; break; }
-    const int e = group_row_end[g];
-    VI_CHECK_ARG(e > 0 && e <= M && (g == 0 || e > group_row_end[g - 1]), "vi_gemm_bf16: bad group_row_end[%d]=%d", g, e);
-    VI_CHECK_ARG(g == n_groups - 1 || e % BM == 0, "vi_gemm_bf16: group %d must end on a multiple of %d rows (got %d)", g, BM, e);
+    const int e = a.group_row_end[g];
+    VI_CHECK_ARG(e > 0 && e <= M && (g == 0 || e > a.group_row_end[g - 1]), "vi_gemm16: bad group_row_end[%d]=%d", g, e);
+    VI_CHECK_ARG(g == n_groups - 1 || e % BM == 0, "vi_gemm16: group %d must end on a multiple of %d rows (got %d)", g, BM, e);
     if (g < n_groups - 1 && e % (2 * BM) != 0) pair_ok = false;
     p.group_tile_end[g] = (e + BM - 1) / BM;
   }
-  VI_CHECK_ARG(n_groups == 1 || group_row_end[n_groups - 1] == M, "vi_gemm_bf16: last group must end at M");
+  VI_CHECK_ARG(n_groups == 1 || a.group_row_end[n_groups - 1] == M, "vi_gemm16: last group must end at M");
 
   const int nsm = vi_num_sms();
   Choice c = pick_tile(M, N, K, nsm, pair_ok);
-  if (tile != 0) {                       // caller-selected tile (the Python host autotunes per shape)
-    const int bn = tile & 0xFFF;
-    const bool pr = (tile & VI_TILE_PAIR) != 0;
+  if (a.tile != 0) {                     // caller-selected tile (the Python host keeps a measured table per shape)
+    const int bn = a.tile & 0xFFF;
+    const bool pr = (a.tile & VI_TILE_PAIR) != 0;
     VI_CHECK_ARG((bn == 64 || bn == 96 || bn == 128 || bn == 192 || bn == 256) && N % bn == 0,
-                 "vi_gemm_bf16_tiled: tile width %d does not divide N=%d", bn, N);
-    VI_CHECK_ARG(!pr || (pair_ok && bn >= 128), "vi_gemm_bf16_tiled: CTA-pair tiles need width >= 128 and 256-row group ends");
+                 "vi_gemm16: tile width %d does not divide N=%d", bn, N);
+    VI_CHECK_ARG(!pr || (pair_ok && bn >= 128), "vi_gemm16: CTA-pair tiles need width >= 128 and 256-row group ends");
     c = Choice{bn, pr};
   }
   const int tm = c.pair ? 2 * BM : BM;
@@ -629,44 +780,50 @@ extern "C" int vi_gemm_bf16_tiled(const void* x, int64_t ldx, const void* w, con
     grid = (int)(tiles < nsm ? tiles : nsm);
   }
 
-  CUtensorMap tmA, tmB, tmY, tmR;
-  memset(&tmR, 0, sizeof(tmR));
-  if (int rc = make_map(&tmA, x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)K, (uint64_t)M, (uint64_t)ldx, BK, BM,
-                        CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
-  if (int rc = make_map(&tmB, w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)K, (uint64_t)n_groups * N, (uint64_t)K, BK,
+  const CUtensorMapDataType dt16 = p.fmt_f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  Maps m;
+  memset(&m, 0, sizeof(m));
+  if (int rc = make_map(&m.a, a.x, dt16, 2, (uint64_t)K, (uint64_t)M, (uint64_t)a.ldx, BK, BM, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+  if (int rc = make_map(&m.b, a.w, dt16, 2, (uint64_t)K, (uint64_t)n_groups * N, (uint64_t)K, BK,
                         (uint32_t)(c.pair ? c.bn / 2 : c.bn), CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
   if (p.y_f32) {
-    if (int rc = make_map(&tmY, y, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (uint64_t)N, (uint64_t)M, (uint64_t)ldy, 32, 32,
+    if (int rc = make_map(&m.y, a.y, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (uint64_t)N, (uint64_t)M, (uint64_t)a.ldy, 32, 32,
                           CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
   } else {
-    if (int rc = make_map(&tmY, y, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)N, (uint64_t)M, (uint64_t)ldy, 32, 32,
-                          CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
+    if (int rc = make_map(&m.y, a.y, dt16, 2, (uint64_t)N, (uint64_t)M, (uint64_t)a.ldy, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
   }
-  if (residual) {
-    if (int rc = make_map(&tmR, residual, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (uint64_t)N, (uint64_t)M, (uint64_t)ldr, 32, 32,
+  if (a.residual) {
+    if (int rc = make_map(&m.r, a.residual, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (uint64_t)N, (uint64_t)M, (uint64_t)a.ldr, 32, 32,
                           CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
   } else {
-    tmR = tmY;
+    m.r = m.y;
+  }
+  if (a.y16) {
+    if (int rc = make_map(&m.y2, a.y16, dt16, 2, (uint64_t)N, (uint64_t)M, (uint64_t)a.ldy16, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
+  } else {
+    m.y2 = m.y;
   }
 
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-#define VI_LAUNCH(BN_, SB_, SF_, PAIR_)                                                          \
-  (p.y_f32 ? launch<BN_, SF_, PAIR_, true>(tmA, tmB, tmY, tmR, p, grid, st)                      \
-           : launch<BN_, SB_, PAIR_, false>(tmA, tmB, tmY, tmR, p, grid, st))
-  // ring depth = what fits beside the epilogue staging (bf16 out: 32 KB, fp32 out: 64 KB) in 227 KB
+  const int om = a.y16 ? OUT_DUAL : (p.y_f32 ? OUT_F32 : OUT_H16);
+  // ring depth = what fits beside the epilogue staging (16-bit out: 32 KB, fp32 out: 64 KB, both: 96 KB) in 227 KB
+#define VI_LAUNCH(BN_, SH_, SF_, SD_, PAIR_)                                                     \
+  (om == OUT_DUAL ? launch<BN_, SD_, PAIR_, OUT_DUAL>(m, p, grid, st)                            \
+   : om == OUT_F32 ? launch<BN_, SF_, PAIR_, OUT_F32>(m, p, grid, st)                            \
+                   : launch<BN_, SH_, PAIR_, OUT_H16>(m, p, grid, st))
   if (c.pair) {
     switch (c.bn) {
-      case 256: return VI_LAUNCH(256, 6, 5, true);
-      case 192: return VI_LAUNCH(192, 6, 5, true);
-      default:  return VI_LAUNCH(128, 8, 6, true);
+      case 256: return VI_LAUNCH(256, 6, 5, 3, true);
+      case 192: return VI_LAUNCH(192, 6, 5, 4, true);
+      default:  return VI_LAUNCH(128, 8, 6, 5, true);
     }
   }
   switch (c.bn) {
-    case 256: return VI_LAUNCH(256, 4, 3, false);
-    case 192: return VI_LAUNCH(192, 4, 4, false);
-    case 128: return VI_LAUNCH(128, 6, 5, false);
-    case 96:  return VI_LAUNCH(96, 6, 5, false);
-    default:  return VI_LAUNCH(64, 8, 6, false);
+    case 256: return VI_LAUNCH(256, 4, 3, 2, false);
+    case 192: return VI_LAUNCH(192, 4, 4, 3, false);
+    case 128: return VI_LAUNCH(128, 6, 5, 3, false);
+    case 96:  return VI_LAUNCH(96, 6, 5, 4, false);
+    default:  return VI_LAUNCH(64, 8, 6, 5, false);
   }
 #undef VI_LAUNCH
 }

@@ -62,7 +62,7 @@ __device__ __forceinline__ void row_layernorm(Row& r, const float* gamma, const 
     r.v[4 * j + 3] = (r.v[4 * j + 3] - mean) * rstd * g.w + b.w;
   }
 }
-__device__ __forceinline__ void row_store(const Row& r, float* y32, bf16* y16, long long row, int lane) {
+__device__ __forceinline__ void row_store(const Row& r, float* y32, bf16* y16, long long row, int lane, bool f16 = false) {
   if (y32) {
     float4* o = reinterpret_cast<float4*>(y32 + row * D);
 #pragma unroll
@@ -72,7 +72,7 @@ __device__ __forceinline__ void row_store(const Row& r, float* y32, bf16* y16, l
     uint2* o = reinterpret_cast<uint2*>(y16 + row * D);
 #pragma unroll
     for (int j = 0; j < V4; ++j)
-      o[lane + 32 * j] = make_uint2(pack_bf16x2(r.v[4 * j], r.v[4 * j + 1]), pack_bf16x2(r.v[4 * j + 2], r.v[4 * j + 3]));
+      o[lane + 32 * j] = make_uint2(pack_h16x2(r.v[4 * j], r.v[4 * j + 1], f16), pack_h16x2(r.v[4 * j + 2], r.v[4 * j + 3], f16));
   }
 }
 __device__ __forceinline__ float row_dot(const Row& a, const Row& b) {
@@ -99,7 +99,7 @@ __device__ __forceinline__ int group_of_row(const RowGroups& g, long long row) {
 
 __global__ void __launch_bounds__(128) add_ln_kernel(const float* a, const float* b,
                                                      const float* gamma, const float* beta,
-                                                     float eps, float* y32, bf16* y16, long long rows, const RowGroups grp) {
+                                                     float eps, float* y32, bf16* y16, int f16, long long rows, const RowGroups grp) {
   pdl_enter();
   ROW_INDEX();
   if (row >= rows) return;
@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(128) add_ln_kernel(const float* a, const float
   row_load(r, a + row * D, lane);
   if (b) row_add(r, b + row * D, lane);
   row_layernorm(r, gamma, beta, eps, lane);
-  row_store(r, y32, y16, row, lane);
+  row_store(r, y32, y16, row, lane, f16 != 0);
 }
 
 // 8 warps per CTA, one row per warp per iteration, CTAs stride over the rows.  The small feature projection
@@ -165,7 +165,15 @@ __global__ void __launch_bounds__(EMBED_WARPS * 32) embed_compose_kernel(const v
     if (p.const_row) row_add(acc, p.const_row, lane);
     if (p.const_row2) row_add(acc, p.const_row2, lane);
     if (p.out_gamma) row_layernorm(acc, p.out_gamma, p.out_beta, p.eps, lane);
-    row_store(acc, p.y32, reinterpret_cast<bf16*>(p.y16), row, lane);
+    if (p.ln2_gamma) {
+      // a second LayerNorm chained on the result (norm1 of the first panorama layer, D/models/transformer.py:171): the fp32
+      // output keeps the first result (the residual stream), the 16-bit output is the operand of the next contraction
+      if (p.y32) row_store(acc, p.y32, nullptr, row, lane);
+      row_layernorm(acc, p.ln2_gamma, p.ln2_beta, p.ln2_eps, lane);
+      row_store(acc, nullptr, reinterpret_cast<bf16*>(p.y16), row, lane, p.y16_dtype == VI_DT_F16);
+      continue;
+    }
+    row_store(acc, p.y32, reinterpret_cast<bf16*>(p.y16), row, lane, p.y16_dtype == VI_DT_F16);
   }
 }
 
@@ -191,7 +199,7 @@ __global__ void __launch_bounds__(128) ln_dot_kernel(const float* h, const float
 
 __global__ void __launch_bounds__(128) mul_bcast_kernel(const float* x, long long x_bs,
                                                         const float* s, long long lds, float* y32,
-                                                        bf16* y16, long long rows, int rows_per_batch) {
+                                                        bf16* y16, int f16, long long rows, int rows_per_batch) {
   pdl_enter();
   ROW_INDEX();
   if (row >= rows) return;
@@ -201,7 +209,7 @@ __global__ void __launch_bounds__(128) mul_bcast_kernel(const float* x, long lon
   row_load(m, s + b * lds, lane);
 #pragma unroll
   for (int i = 0; i < V4 * 4; ++i) r.v[i] *= m.v[i];
-  row_store(r, y32, y16, row, lane);
+  row_store(r, y32, y16, row, lane, f16 != 0);
 }
 
 // One warp per episode.  Viewpoint-id strings are interned to int32 on the host (gmap_ids: -1 = padding,
@@ -282,7 +290,7 @@ __global__ void mask_logits_navtype_kernel(const float* raw, const int64_t* nav_
 }
 
 __global__ void __launch_bounds__(128) gather_mean_kernel(const float* src, const int32_t* offsets,
-                                                          const int32_t* row_idx, float* out32, bf16* out16,
+                                                          const int32_t* row_idx, float* out32, bf16* out16, int f16,
                                                           long long rows) {
   pdl_enter();
   ROW_INDEX();
@@ -295,7 +303,7 @@ __global__ void __launch_bounds__(128) gather_mean_kernel(const float* src, cons
   const float n = (float)(e - s);
 #pragma unroll
   for (int i = 0; i < V4 * 4; ++i) acc.v[i] = acc.v[i] / n;
-  row_store(acc, out32, out16, row, lane);
+  row_store(acc, out32, out16, row, lane, f16 != 0);
 }
 
 __global__ void __launch_bounds__(128) scatter_rows_kernel(const float* src, const int32_t* dst_rows,
@@ -394,21 +402,23 @@ __global__ void __launch_bounds__(128) margin_rows_kernel(const float* sims, con
   if (lane == 0) loss_rows[row] = (1.0f - pos) + sum / cnt;
 }
 
-__global__ void cast_bf16_kernel(const float* src, bf16* dst, long long n4, long long n) {
+__global__ void cast_bf16_kernel(const float* src, bf16* dst, int f16, long long n4, long long n) {
   pdl_enter();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n4) {
     const float4 t = (*(reinterpret_cast<const float4*>(src) + i));
-    reinterpret_cast<uint2*>(dst)[i] = make_uint2(pack_bf16x2(t.x, t.y), pack_bf16x2(t.z, t.w));
+    reinterpret_cast<uint2*>(dst)[i] = make_uint2(pack_h16x2(t.x, t.y, f16 != 0), pack_h16x2(t.z, t.w, f16 != 0));
   }
-  if (i == 0) for (long long j = n4 * 4; j < n; ++j) dst[j] = __float2bfloat16_rn(src[j]);
+  if (i == 0)
+    for (long long j = n4 * 4; j < n; ++j)
+      reinterpret_cast<uint16_t*>(dst)[j] = (uint16_t)(pack_h16x2(src[j], 0.f, f16 != 0) & 0xFFFFu);
 }
 
 
 // dst[b, r, :] = src[b, r, :] for nb batches of `rpb` 768-wide rows with independent batch / row strides
 // (token concatenation [txt; imagine], token-0 gathers, fp32 -> bf16 operand copies)
 __global__ void __launch_bounds__(128) copy_rows_kernel(const float* src, long long src_bs, long long src_rs,
-                                                        float* dst32, bf16* dst16, long long dst_bs, long long dst_rs,
+                                                        float* dst32, bf16* dst16, int f16, long long dst_bs, long long dst_rs,
                                                         long long rows, int rpb) {
   pdl_enter();
   ROW_INDEX();
@@ -426,7 +436,7 @@ __global__ void __launch_bounds__(128) copy_rows_kernel(const float* src, long l
     uint2* o = reinterpret_cast<uint2*>(dst16 + off);
 #pragma unroll
     for (int j = 0; j < V4; ++j)
-      o[lane + 32 * j] = make_uint2(pack_bf16x2(v.v[4 * j], v.v[4 * j + 1]), pack_bf16x2(v.v[4 * j + 2], v.v[4 * j + 3]));
+      o[lane + 32 * j] = make_uint2(pack_h16x2(v.v[4 * j], v.v[4 * j + 1], f16 != 0), pack_h16x2(v.v[4 * j + 2], v.v[4 * j + 3], f16 != 0));
   }
 }
 
@@ -448,15 +458,18 @@ inline bool make_groups(RowGroups& g, int n_groups, const int32_t* ends, long lo
 
 #define ST(s) reinterpret_cast<cudaStream_t>(s)
 
+inline bool dt16_ok(int dt) { return dt == VI_DT_BF16 || dt == VI_DT_F16; }
+
 extern "C" int vi_add_ln(const float* a, const float* b, const float* gamma, const float* beta, float eps, float* y32,
-                         void* y16, int64_t rows, int n_groups, const int32_t* group_row_end, vi_stream_t stream) {
+                         void* y16, int y16_dtype, int64_t rows, int n_groups, const int32_t* group_row_end, vi_stream_t stream) {
   RowGroups grp;
+  VI_CHECK_ARG(dt16_ok(y16_dtype), "vi_add_ln: y16_dtype must be VI_DT_BF16 or VI_DT_F16");
   VI_CHECK_ARG(make_groups(grp, n_groups, group_row_end, rows), "vi_add_ln: bad row groups");
   VI_CHECK_ARG(a && gamma && beta && (y32 || y16), "vi_add_ln: null operand");
   VI_CHECK_ARG(aligned16(a) && aligned16(b) && aligned16(gamma) && aligned16(beta) && aligned16(y32) && ((uintptr_t)y16 & 7) == 0,
                "vi_add_ln: operands must be 16-byte aligned");
   if (rows <= 0) return VI_OK;
-  VI_CUDA(vi_launch(add_ln_kernel, dim3(row_grid(rows)), dim3(128), (size_t)(0), ST(stream), a, b, gamma, beta, eps, y32, reinterpret_cast<bf16*>(y16), rows, grp));
+  VI_CUDA(vi_launch(add_ln_kernel, dim3(row_grid(rows)), dim3(128), (size_t)(0), ST(stream), a, b, gamma, beta, eps, y32, reinterpret_cast<bf16*>(y16), (int)(y16_dtype == VI_DT_F16), rows, grp));
   VI_LAUNCH_CHECK();
   return VI_OK;
 }
@@ -471,6 +484,8 @@ extern "C" int vi_embed_compose(const vi_embed_args* args, vi_stream_t stream) {
   VI_CHECK_ARG(!p.a_gamma || p.a_beta, "vi_embed_compose: a_gamma without a_beta");
   VI_CHECK_ARG(!p.feat_gamma || p.feat_beta, "vi_embed_compose: feat_gamma without feat_beta");
   VI_CHECK_ARG(!p.out_gamma || p.out_beta, "vi_embed_compose: out_gamma without out_beta");
+  VI_CHECK_ARG(!p.ln2_gamma || (p.ln2_beta && p.y16), "vi_embed_compose: the chained LayerNorm needs ln2_beta and a 16-bit output");
+  VI_CHECK_ARG(dt16_ok(p.y16_dtype), "vi_embed_compose: y16_dtype must be VI_DT_BF16 or VI_DT_F16");
   VI_CHECK_ARG(aligned16(p.a2) && aligned16(p.a3), "vi_embed_compose: a2 / a3 must be 16-byte aligned");
   VI_CHECK_ARG(aligned16(p.a) && aligned16(p.table) && aligned16(p.pos_table) && aligned16(p.const_row) &&
                    aligned16(p.const_row2) && aligned16(p.y32) && ((uintptr_t)p.y16 & 7) == 0,
@@ -499,12 +514,13 @@ extern "C" int vi_ln_dot(const float* h, const float* gamma, const float* beta, 
 }
 
 extern "C" int vi_mul_bcast(const float* x, int64_t x_batch_stride, const float* s, int64_t lds, float* y32, void* y16,
-                            int64_t rows, int rows_per_batch, vi_stream_t stream) {
+                            int y16_dtype, int64_t rows, int rows_per_batch, vi_stream_t stream) {
+  VI_CHECK_ARG(dt16_ok(y16_dtype), "vi_mul_bcast: y16_dtype must be VI_DT_BF16 or VI_DT_F16");
   VI_CHECK_ARG(x && s && (y32 || y16) && rows_per_batch > 0, "vi_mul_bcast: bad operands");
   VI_CHECK_ARG(aligned16(x) && aligned16(s) && lds % 4 == 0 && x_batch_stride % 4 == 0 && aligned16(y32) &&
                    ((uintptr_t)y16 & 7) == 0, "vi_mul_bcast: misaligned operands");
   if (rows <= 0) return VI_OK;
-  VI_CUDA(vi_launch(mul_bcast_kernel, dim3(row_grid(rows)), dim3(128), (size_t)(0), ST(stream), x, x_batch_stride, s, lds, y32, reinterpret_cast<bf16*>(y16), rows,
+  VI_CUDA(vi_launch(mul_bcast_kernel, dim3(row_grid(rows)), dim3(128), (size_t)(0), ST(stream), x, x_batch_stride, s, lds, y32, reinterpret_cast<bf16*>(y16), (int)(y16_dtype == VI_DT_F16), rows,
                                                           rows_per_batch));
   VI_LAUNCH_CHECK();
   return VI_OK;
@@ -533,11 +549,12 @@ extern "C" int vi_mask_logits_navtype(const float* raw, const int64_t* nav_types
 }
 
 extern "C" int vi_gather_mean(const float* src, const int32_t* offsets, const int32_t* row_idx, float* out32, void* out16,
-                              int R, vi_stream_t stream) {
+                              int out16_dtype, int R, vi_stream_t stream) {
+  VI_CHECK_ARG(dt16_ok(out16_dtype), "vi_gather_mean: out16_dtype must be VI_DT_BF16 or VI_DT_F16");
   VI_CHECK_ARG(src && offsets && row_idx && (out32 || out16), "vi_gather_mean: null operand");
   VI_CHECK_ARG(aligned16(src) && aligned16(out32) && ((uintptr_t)out16 & 7) == 0, "vi_gather_mean: misaligned operands");
   if (R <= 0) return VI_OK;
-  VI_CUDA(vi_launch(gather_mean_kernel, dim3(row_grid(R)), dim3(128), (size_t)(0), ST(stream), src, offsets, row_idx, out32, reinterpret_cast<bf16*>(out16), R));
+  VI_CUDA(vi_launch(gather_mean_kernel, dim3(row_grid(R)), dim3(128), (size_t)(0), ST(stream), src, offsets, row_idx, out32, reinterpret_cast<bf16*>(out16), (int)(out16_dtype == VI_DT_F16), (long long)R));
   VI_LAUNCH_CHECK();
   return VI_OK;
 }
@@ -600,8 +617,9 @@ extern "C" int vi_margin_loss(const float* proj, const float* tgt, const float* 
 }
 
 extern "C" int vi_copy_rows(const float* src, int64_t src_batch_stride, int64_t src_row_stride, float* dst32, void* dst16,
-                            int64_t dst_batch_stride, int64_t dst_row_stride, int64_t n_batches, int rows_per_batch,
-                            vi_stream_t stream) {
+                            int dst16_dtype, int64_t dst_batch_stride, int64_t dst_row_stride, int64_t n_batches,
+                            int rows_per_batch, vi_stream_t stream) {
+  VI_CHECK_ARG(dt16_ok(dst16_dtype), "vi_copy_rows: dst16_dtype must be VI_DT_BF16 or VI_DT_F16");
   VI_CHECK_ARG(src && (dst32 || dst16) && rows_per_batch > 0, "vi_copy_rows: bad operands");
   VI_CHECK_ARG(aligned16(src) && aligned16(dst32) && ((uintptr_t)dst16 & 7) == 0 && src_batch_stride % 4 == 0 &&
                    src_row_stride % 4 == 0 && dst_batch_stride % 4 == 0 && dst_row_stride % 4 == 0,
@@ -609,19 +627,24 @@ extern "C" int vi_copy_rows(const float* src, int64_t src_batch_stride, int64_t 
   const long long rows = (long long)n_batches * rows_per_batch;
   if (rows <= 0) return VI_OK;
   VI_CUDA(vi_launch(copy_rows_kernel, dim3(row_grid(rows)), dim3(128), (size_t)(0), ST(stream), src, src_batch_stride, src_row_stride, dst32,
-                                                          reinterpret_cast<bf16*>(dst16), dst_batch_stride, dst_row_stride,
-                                                          rows, rows_per_batch));
+                                                          reinterpret_cast<bf16*>(dst16), (int)(dst16_dtype == VI_DT_F16), dst_batch_stride,
+                                                          dst_row_stride, rows, rows_per_batch));
   VI_LAUNCH_CHECK();
   return VI_OK;
 }
 
 extern "C" int vi_cast_bf16(const float* src, void* dst, int64_t n, vi_stream_t stream) {
-  VI_CHECK_ARG(src && dst, "vi_cast_bf16: null operand");
-  VI_CHECK_ARG(aligned16(src) && ((uintptr_t)dst & 7) == 0, "vi_cast_bf16: misaligned operands");
+  return vi_cast_h16(src, dst, VI_DT_BF16, n, stream);
+}
+
+extern "C" int vi_cast_h16(const float* src, void* dst, int dst_dtype, int64_t n, vi_stream_t stream) {
+  VI_CHECK_ARG(src && dst, "vi_cast_h16: null operand");
+  VI_CHECK_ARG(dt16_ok(dst_dtype), "vi_cast_h16: dst_dtype must be VI_DT_BF16 or VI_DT_F16");
+  VI_CHECK_ARG(aligned16(src) && ((uintptr_t)dst & 7) == 0, "vi_cast_h16: misaligned operands");
   if (n <= 0) return VI_OK;
   const long long n4 = n / 4;
   const long long threads = n4 > 0 ? n4 : 1;
-  VI_CUDA(vi_launch(cast_bf16_kernel, dim3((unsigned)((threads + 255) / 256)), dim3(256), (size_t)(0), ST(stream), src, reinterpret_cast<bf16*>(dst), n4, n));
+  VI_CUDA(vi_launch(cast_bf16_kernel, dim3((unsigned)((threads + 255) / 256)), dim3(256), (size_t)(0), ST(stream), src, reinterpret_cast<bf16*>(dst), (int)(dst_dtype == VI_DT_F16), n4, n));
   VI_LAUNCH_CHECK();
   return VI_OK;
 }

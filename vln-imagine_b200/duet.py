@@ -163,7 +163,7 @@ def align_forward(model, align_txt_embeds, align_imagine_embeds, flags, noun_phr
     for j, lp in enumerate(pk):
         w, _ = lp.get(lowp)
         last = j == len(pk) - 1
-        x = ops.gemm(x, w, None, epilogue=ops.EPI_NONE if last else ops.EPI_RELU, out_dtype=F32 if (last or not lowp) else BF16)
+        x = ops.gemm(x, w, None, epilogue=ops.EPI_NONE if last else ops.EPI_RELU, out_dtype=F32 if (last or not lowp) else x.dtype)
     proj = x
     tgt, _ = ops.gather_mean(txt, rows.tok_off, rows.tok_rows, rows.R, want16=False)
     if cfg.aux_loss_type == 'cosine':
@@ -256,6 +256,10 @@ class GlocalTextPathNavCMT(nn.Module):
                 for p in m.parameters():
                     p.requires_grad = False
         self.precision = os.environ.get('VLN_IMAGINE_PRECISION', 'bf16')
+        # 16-bit operand format of inference calls in the 'bf16' (= 16-bit tensor-core) mode: 'auto' picks fp16 when the weights
+        # prove it safe (blocks.operand_format), 'bf16' / 'f16' force one
+        self.operand16 = os.environ.get('VLN_IMAGINE_OPERAND16', 'auto')
+        self._fmt_cache = {}
         self._packs = None
         self._ids = _IdTable()
         self.context_cache = os.environ.get('VLN_IMAGINE_CONTEXT_CACHE', '1') != '0'
@@ -338,7 +342,8 @@ class GlocalTextPathNavCMT(nn.Module):
                              const_rows=(e.token_type_embeddings.weight[0],), out_ln=e.LayerNorm, lowp=lowp, dropout=True)
             s = [Stream(0, B, L, blocks.mask_u8(txt_masks))]
             for pk in self._pk()['lang']:
-                x = blocks.self_attn_ffn(x, pk, s, None, lowp)
+                x = blocks.self_attn_ffn(x, pk, s, None, lowp, defer=True)
+            x = blocks.materialize(x, lowp, want16=False)
         out = x.f32.view(B, L, HIDDEN)
         if self.config.fix_lang_embedding:
             out = out.detach()
@@ -368,13 +373,18 @@ class GlocalTextPathNavCMT(nn.Module):
         km = blocks.mask_u8(pano_masks)
         with blocks.grad_mode(self._recording(view_img_fts) and not self.config.fix_pano_embedding, self._drop()):
             a = blocks.linear(blocks.operand(v32, lowp), pk['img_linear'], lowp, out_dtype=F32)
-            x32 = blocks.embed(B * V, dev, a=a, a_ln=ie.img_layer_norm, feat=_f32c(loc_fts).view(B * V, -1),
-                               feat_lin=ie.loc_linear, feat_ln=ie.loc_layer_norm,
-                               idx=nav_types.long().contiguous().view(-1), table=ie.nav_type_embedding.weight,
-                               const_rows=(self.embeddings.token_type_embeddings.weight[1],), out_ln=ie.layer_norm,
-                               dropout=True).f32
-            for lp in pk['pano']:
-                x32 = blocks.pano_layer(x32, lp, B, V, km, lowp)
+            folded = lowp and blocks.fold_enabled() and not blocks.training() and len(pk['pano']) > 0
+            x = blocks.embed(B * V, dev, a=a, a_ln=ie.img_layer_norm, feat=_f32c(loc_fts).view(B * V, -1),
+                             feat_lin=ie.loc_linear, feat_ln=ie.loc_layer_norm,
+                             idx=nav_types.long().contiguous().view(-1), table=ie.nav_type_embedding.weight,
+                             const_rows=(self.embeddings.token_type_embeddings.weight[1],), out_ln=ie.layer_norm,
+                             dropout=True, chain_ln=ie.pano_encoder.layers[0].norm1 if folded else None)
+            if folded:
+                x32 = blocks.pano_encoder_folded(x, pk['pano'], B, V, km)
+            else:
+                x32 = x.f32
+                for lp in pk['pano']:
+                    x32 = blocks.pano_layer(x32, lp, B, V, km, lowp)
             y32 = blocks.layer_norm(x32, None, pk['pano_norm'], 1e-12, False).f32
         out = y32.view(B, V, HIDDEN)
         if self.config.fix_pano_embedding:
@@ -400,14 +410,14 @@ class GlocalTextPathNavCMT(nn.Module):
         v32 = _f32c(view_img_fts).view(B * V, -1)
         o32 = _f32c(obj_img_fts).view(B * O, -1)
         w, b = pk['img_linear'].get(lowp)
-        nv, _ = ops.add_ln(ops.gemm(ops.cast_bf16(v32) if lowp else v32, w, b, out_dtype=F32), None, ie.img_layer_norm.weight,
+        nv, _ = ops.add_ln(ops.gemm(ops.cast_h16(v32) if lowp else v32, w, b, out_dtype=F32), None, ie.img_layer_norm.weight,
                            ie.img_layer_norm.bias, 1e-12, want16=False)
         if ie.obj_linear is not None:                          # obj_feat_size != image_feat_size (:464-468)
             w, b = pk['obj_linear'].get(lowp)
             oln = ie.obj_layer_norm
         else:
             oln = ie.img_layer_norm
-        no, _ = ops.add_ln(ops.gemm(ops.cast_bf16(o32) if lowp else o32, w, b, out_dtype=F32), None, oln.weight, oln.bias, 1e-12,
+        no, _ = ops.add_ln(ops.gemm(ops.cast_h16(o32) if lowp else o32, w, b, out_dtype=F32), None, oln.weight, oln.bias, 1e-12,
                            want16=False)
         src = torch.cat([nv, no, torch.zeros((1, HIDDEN), dtype=F32, device=dev)], 0)
         zero_row = B * V + B * O
@@ -457,7 +467,7 @@ class GlocalTextPathNavCMT(nn.Module):
         # ---- input embeddings of both branches into one row-stacked activation (:1141-1152)
         (r_g, r_l), ends, R = blocks.stack_layout([B * G, B * P])
         x32 = torch.empty((R, HIDDEN), dtype=F32, device=dev)
-        x16 = torch.empty((R, HIDDEN), dtype=BF16, device=dev) if lowp else None
+        x16 = torch.empty((R, HIDDEN), dtype=ops.h16(), device=dev) if lowp else None
         if ends[0] > B * G:
             x32[B * G:ends[0]].zero_()
             if lowp:
@@ -490,8 +500,9 @@ class GlocalTextPathNavCMT(nn.Module):
 
         # ---- 4 graph-aware cross-modal layers, both branches per launch (:384-399, :444-453)
         for cp, sp, kv in zip(pk['x_cross'], pk['x_self'], kvs):
-            x = blocks.cross_attn(x, kv, [0, 2 * HIDDEN], C, ctx_mask, cp, streams, ends, lowp)
-            x = blocks.self_attn_ffn(x, sp, streams, ends, lowp)
+            x = blocks.cross_attn(x, kv, [0, 2 * HIDDEN], C, ctx_mask, cp, streams, ends, lowp, defer=True)
+            x = blocks.self_attn_ffn(x, sp, streams, ends, lowp, defer=True)
+        x = blocks.materialize(x, lowp, ends)
 
         gmap_out = x.f32[r_g:r_g + B * G].view(B, G, HIDDEN)
         vp_out = x.f32[r_l:r_l + B * P].view(B, P, HIDDEN)
@@ -499,7 +510,7 @@ class GlocalTextPathNavCMT(nn.Module):
         # ---- heads (:1182-1196) and global/local fusion (:1198-1217)
         fuse_raw = None
         if self.sap_fuse_linear is not None:
-            cat = torch.empty((B, 2 * HIDDEN), dtype=BF16 if lowp else F32, device=dev)
+            cat = torch.empty((B, 2 * HIDDEN), dtype=ops.h16() if lowp else F32, device=dev)
             c32, c16 = (None, cat) if lowp else (cat, None)
             ops.copy_rows(x.f32[r_g:], G * HIDDEN, HIDDEN, B, 1, c32, c16, 2 * HIDDEN, HIDDEN)
             ops.copy_rows(x.f32[r_l:], P * HIDDEN, HIDDEN, B, 1, c32[:, HIDDEN:] if c32 is not None else None,
@@ -565,7 +576,7 @@ class GlocalTextPathNavCMT(nn.Module):
         I = imagine_embeds.shape[1] if with_img else 0
         C = L + I
         dev = self.embeddings.LayerNorm.weight.device
-        slot_key = (B, L, I, lowp)
+        slot_key = (B, L, I, lowp, ops.h16())
         slot = self._ctx_slots.get(slot_key)
         wtok = tuple(cp.kv.get_token() for cp in pk['x_cross'])
         ident = (id(txt_embeds), txt_embeds._version, txt_embeds.data_ptr(),
@@ -575,8 +586,8 @@ class GlocalTextPathNavCMT(nn.Module):
             self.context_hits += 1
             return slot['kv']
         if slot is None:
-            slot = {'ctx': torch.empty((B * C, HIDDEN), dtype=BF16 if lowp else F32, device=dev),
-                    'kv': [torch.empty((B * C, 4 * HIDDEN), dtype=BF16 if lowp else F32, device=dev) for _ in pk['x_cross']]}
+            slot = {'ctx': torch.empty((B * C, HIDDEN), dtype=ops.h16() if lowp else F32, device=dev),
+                    'kv': [torch.empty((B * C, 4 * HIDDEN), dtype=ops.h16() if lowp else F32, device=dev) for _ in pk['x_cross']]}
             self._ctx_slots[slot_key] = slot
         ctx = slot['ctx']
         c32, c16 = (None, ctx) if lowp else (ctx, None)
@@ -587,7 +598,7 @@ class GlocalTextPathNavCMT(nn.Module):
             ops.copy_rows(img, I * HIDDEN, HIDDEN, B, I, c32[L:] if c32 is not None else None,
                           c16[L:] if c16 is not None else None, C * HIDDEN, HIDDEN)
         elif lowp:
-            ops.cast_bf16(txt.view(B * L, HIDDEN), ctx)
+            ops.cast_h16(txt.view(B * L, HIDDEN), ctx)
         else:
             ctx.copy_(txt.view(B * L, HIDDEN))
         for cp, kv in zip(pk['x_cross'], slot['kv']):
@@ -694,7 +705,15 @@ class GlocalTextPathNavCMT(nn.Module):
             return align_forward(self, txt, batch['align_imagine_embeds'], batch['sub_instr_imag_flag'],
                                  batch['noun_phrase_segs'], self.lowp)
 
+    def h16_format(self):
+        """16-bit operand format of this call (blocks.operand_format)"""
+        return blocks.operand_format(self, self._fmt_cache, self.operand16)
+
     def forward(self, mode, batch, **kwargs):
+        with ops.half_format(self.h16_format()):
+            return self._forward(mode, batch, **kwargs)
+
+    def _forward(self, mode, batch, **kwargs):
         """Mode dispatch, :1237-1288."""
         if mode == 'language':
             return self.forward_text(batch['txt_ids'], batch['txt_masks'])
@@ -769,6 +788,10 @@ class VLNBert(nn.Module):
         return self.use_cuda_graphs and not self.training and not torch.is_grad_enabled()
 
     def forward(self, mode, batch):
+        with ops.half_format(self.vln_bert.h16_format()):
+            return self._forward(mode, batch)
+
+    def _forward(self, mode, batch):
         batch = collections.defaultdict(lambda: None, batch)
         m = self.vln_bert
         if mode == 'panorama':
@@ -783,7 +806,7 @@ class VLNBert(nn.Module):
                 dev = m.embeddings.LayerNorm.weight.device
                 tok = graphs.weights_token(m, self._wt_cache)
                 out = self._g_pano({k: batch[k] for k in ('view_img_fts', 'loc_fts', 'nav_types', 'view_lens')}, dev,
-                                   extra_key=(m.precision,), weights_token=tok)
+                                   extra_key=(m.precision, ops.h16(), blocks.fold_enabled()), weights_token=tok)
                 return out['pano_embeds'], out['pano_masks']
             return m(mode, batch)
         if mode == 'navigation':
@@ -798,7 +821,7 @@ class VLNBert(nn.Module):
                 # The graph stops before the global / local fusion: the ~1700 viewpoint-id strings of a batch are
                 # interned on the host AFTER the encoder has been queued (the GPU would otherwise idle for that long),
                 # then the one fusion kernel is launched eagerly on the graph's outputs.
-                pre = self._g_nav(t, dev, extra_key=(m.precision, cfg.imagine_enc_pano, cfg.concat_imagine_with if
+                pre = self._g_nav(t, dev, extra_key=(m.precision, ops.h16(), blocks.fold_enabled(), cfg.imagine_enc_pano, cfg.concat_imagine_with if
                                                      cfg.imagine_enc_pano else None), weights_token=tok,
                                   borrowed={'ctx_kv%d' % i: x for i, x in enumerate(kv)}, no_clone_prefix='_')
                 return m.fuse_logits(pre, batch['gmap_vpids'], batch['vp_cand_vpids'], G, P)

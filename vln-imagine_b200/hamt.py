@@ -68,6 +68,10 @@ class NavCMT(nn.Module):
         if c.imagine_enc_pano:
             self.fix_imagine_embeds = c.fix_imagine_embeds
         self.precision = os.environ.get('VLN_IMAGINE_PRECISION', 'bf16')
+        # 16-bit operand format of inference calls in the 'bf16' (= 16-bit tensor-core) mode: 'auto' picks fp16 when the weights
+        # prove it safe (blocks.operand_format), 'bf16' / 'f16' force one
+        self.operand16 = os.environ.get('VLN_IMAGINE_OPERAND16', 'auto')
+        self._fmt_cache = {}
         self._packs = None
         self._mean_idx = {}
 
@@ -146,7 +150,8 @@ class NavCMT(nn.Module):
                              const_rows=(e.token_type_embeddings.weight[0],), out_ln=e.LayerNorm, lowp=lowp, dropout=True)
             s = [Stream(0, B, L, blocks.mask_u8(txt_masks))]
             for pk in self._pk()['lang']:
-                x = blocks.self_attn_ffn(x, pk, s, None, lowp)
+                x = blocks.self_attn_ffn(x, pk, s, None, lowp, defer=True)
+            x = blocks.materialize(x, lowp, want16=False)
         out = x.f32.view(B, L, HIDDEN)
         return out.detach() if frozen else out
 
@@ -168,7 +173,7 @@ class NavCMT(nn.Module):
         pk = self._pk()
         f32 = _f32c(hist_img_feats)
         w, b = pk['hist_img'].get(lowp)
-        a = ops.gemm(ops.cast_bf16(f32) if lowp else f32, w, b, out_dtype=F32)
+        a = ops.gemm(ops.cast_h16(f32) if lowp else f32, w, b, out_dtype=F32)
         # position embedding of the current step: a [B] index tensor (the same id for every episode, :597), so the
         # step never becomes a pointer baked into a captured graph
         if torch.is_tensor(ob_step_ids) and ob_step_ids.numel() == B:
@@ -185,7 +190,7 @@ class NavCMT(nn.Module):
             V = hist_pano_img_feats.shape[1]
             p32 = _f32c(hist_pano_img_feats).view(B * V, -1)
             w, b = pk['hist_pano_img'].get(lowp)
-            pa = ops.gemm(ops.cast_bf16(p32) if lowp else p32, w, b, out_dtype=F32)
+            pa = ops.gemm(ops.cast_h16(p32) if lowp else p32, w, b, out_dtype=F32)
             y32, y16 = ops.embed_compose(B * V, dev, a=pa, a_ln=(he.pano_img_layer_norm.weight, he.pano_img_layer_norm.bias),
                                          feat=_f32c(hist_pano_ang_feats).view(B * V, -1), feat_w=he.pano_ang_linear.weight,
                                          feat_b=he.pano_ang_linear.bias,
@@ -266,7 +271,7 @@ class NavCMT(nn.Module):
                                           ob_nav_types, ob_masks, imagine_embeds, imagine_masks)
         (r_l, r_v), ends, R = blocks.stack_layout([B * C, B * Nv])
         x32 = torch.empty((R, HIDDEN), dtype=F32, device=dev)
-        x16 = torch.empty((R, HIDDEN), dtype=BF16, device=dev) if lowp else None
+        x16 = torch.empty((R, HIDDEN), dtype=ops.h16(), device=dev) if lowp else None
         if ends[0] > B * C:
             x32[B * C:ends[0]].zero_()
             if lowp:
@@ -283,7 +288,7 @@ class NavCMT(nn.Module):
         ie = self.img_embeddings
         o32 = _f32c(ob_img_feats).view(B * O, -1)
         w, b = pk['ob_img'].get(lowp)
-        a = ops.gemm(ops.cast_bf16(o32) if lowp else o32, w, b, out_dtype=F32)
+        a = ops.gemm(ops.cast_h16(o32) if lowp else o32, w, b, out_dtype=F32)
         ob32, _ = ops.embed_compose(B * O, dev, a=a, a_ln=(ie.img_layer_norm.weight, ie.img_layer_norm.bias),
                                     feat=_f32c(ob_ang_feats).view(B * O, -1), feat_w=ie.ang_linear.weight, feat_b=ie.ang_linear.bias,
                                     feat_ln=(ie.ang_layer_norm.weight, ie.ang_layer_norm.bias),
@@ -302,18 +307,17 @@ class NavCMT(nn.Module):
 
         for cp, sp in zip(pk['x_cross'], pk['x_self']):
             # bidirectional cross-attention with shared weights, both directions read the layer inputs (:385-397)
-            xin = x.operand(lowp)
-            w, b = cp['qkv'].get(lowp)
-            qkv = ops.gemm(xin, w, b)                          # all rows: Q | K | V
-            ctx = blocks._ctx_buffer(R, xin, streams)
+            qkv = blocks.gemm_act(x, cp['qkv'], lowp, ends)    # all rows: Q | K | V
+            ctx = blocks._ctx_buffer(R, qkv, streams)
             ql, qv = qkv[r_l:r_l + B * C], qkv[r_v:r_v + B * Nv]
             ops.attention_multi([
                 dict(q=ql[:, :HIDDEN], k=qv[:, HIDDEN:2 * HIDDEN], v=qv[:, 2 * HIDDEN:], out=ctx[r_l:r_l + B * C],
                      B=B, Lq=C, Lk=Nv, key_mask=visn_mask),
                 dict(q=qv[:, :HIDDEN], k=ql[:, HIDDEN:2 * HIDDEN], v=ql[:, 2 * HIDDEN:], out=ctx[r_v:r_v + B * Nv],
                      B=B, Lq=Nv, Lk=C, key_mask=lang_mask)])
-            x = blocks.linear_residual_ln(ctx, cp['o'], x.f32, cp['ln'], 1e-12, lowp)
-            x = blocks.self_attn_ffn(x, sp, streams, ends, lowp)
+            x = blocks.linear_residual_ln(ctx, cp['o'], x, cp['ln'], 1e-12, lowp, ends, defer=True)
+            x = blocks.self_attn_ffn(x, sp, streams, ends, lowp, defer=True)
+        x = blocks.materialize(x, lowp, ends, want16=False)
 
         lang_out = x.f32[r_l:r_l + B * C].view(B, C, HIDDEN)
         visn_out = x.f32[r_v:r_v + B * Nv].view(B, Nv, HIDDEN)
@@ -341,7 +345,7 @@ class NavCMT(nn.Module):
             h32, h16 = ops.mul_bcast(ob_out, Nv * HIDDEN, gate, HIDDEN, B, O, want16=lowp, want32=not lowp)
         else:                                                  # 'ob'
             h32 = torch.empty((B * O, HIDDEN), dtype=F32, device=dev) if not lowp else None
-            h16 = torch.empty((B * O, HIDDEN), dtype=BF16, device=dev) if lowp else None
+            h16 = torch.empty((B * O, HIDDEN), dtype=ops.h16(), device=dev) if lowp else None
             ops.copy_rows(ob_out, Nv * HIDDEN, HIDDEN, B, O, h32, h16, O * HIDDEN, HIDDEN)
         raw = blocks.cls_head(h16 if lowp else h32, pk['act'], lowp)
         act_logits = ops.mask_logits_navtype(raw, ob_nav_types.long().contiguous().view(-1)).view(B, O)
@@ -397,7 +401,15 @@ class NavCMT(nn.Module):
         act_logits = raw.view(B, O).masked_fill(ob_nav_types.view(B, O) == 0, float('-inf'))
         return act_logits, txt_out, hist_out, ob_out
 
-    def forward(self, mode, txt_ids=None, txt_embeds=None, txt_masks=None, hist_img_feats=None, hist_ang_feats=None,
+    def h16_format(self):
+        """16-bit operand format of this call (blocks.operand_format)"""
+        return blocks.operand_format(self, self._fmt_cache, self.operand16)
+
+    def forward(self, mode, **kw):
+        with ops.half_format(self.h16_format()):
+            return self._forward(mode, **kw)
+
+    def _forward(self, mode, txt_ids=None, txt_embeds=None, txt_masks=None, hist_img_feats=None, hist_ang_feats=None,
                 hist_pano_img_feats=None, hist_pano_ang_feats=None, hist_embeds=None, ob_step_ids=None, hist_masks=None,
                 ob_img_feats=None, ob_ang_feats=None, ob_nav_types=None, ob_masks=None, imagine_pano_img_feats=None,
                 imagine_masks=None, imagine_embeds=None, align_txt_embeds=None, align_imagine_embeds=None,
@@ -486,8 +498,12 @@ class VLNBertCMT(nn.Module):
     def _graphable(self):
         return self.use_cuda_graphs and not self.training and not torch.is_grad_enabled()
 
-    def forward(self, mode, txt_ids=None, txt_masks=None, txt_embeds=None, hist_img_feats=None, hist_ang_feats=None,
-                hist_pano_img_feats=None, hist_pano_ang_feats=None, hist_embeds=None, hist_lens=None, ob_step=None,
+    def forward(self, mode, **kw):
+        with ops.half_format(self.vln_bert.h16_format()):
+            return self._forward(mode, **kw)
+
+    def _forward(self, mode, txt_ids=None, txt_masks=None, txt_embeds=None, hist_img_feats=None, hist_ang_feats=None,
+                 hist_pano_img_feats=None, hist_pano_ang_feats=None, hist_embeds=None, hist_lens=None, ob_step=None,
                 ob_img_feats=None, ob_ang_feats=None, ob_nav_types=None, ob_masks=None, imagine_pano_img_feats=None,
                 imagine_masks=None, imagine_embeds=None, align_txt_embeds=None, align_imagine_embeds=None,
                 sub_instr_segs=None, sub_instr_imag_flag=None, noun_phrase_segs=None, obs_instr_ids=None,
@@ -508,7 +524,7 @@ class VLNBertCMT(nn.Module):
                            hist_pano_img_feats=hist_pano_img_feats, hist_pano_ang_feats=hist_pano_ang_feats)
                 t = {k: loc[k] for k in self.HIST_TENSORS if loc[k] is not None}
                 t['ob_step_ids'] = torch.full((hist_img_feats.shape[0],), int(ob_step), dtype=torch.int64)
-                return self._g_hist(t, dev, extra_key=(m.precision,), weights_token=graphs.weights_token(m, self._wt_cache))['hist']
+                return self._g_hist(t, dev, extra_key=(m.precision, ops.h16(), blocks.fold_enabled()), weights_token=graphs.weights_token(m, self._wt_cache))['hist']
             return m('history', hist_img_feats=self._env_dropout(hist_img_feats), hist_ang_feats=hist_ang_feats,
                      ob_step_ids=ob_step, hist_pano_img_feats=self._env_dropout(hist_pano_img_feats),
                      hist_pano_ang_feats=hist_pano_ang_feats)
@@ -523,7 +539,7 @@ class VLNBertCMT(nn.Module):
                 t = {k: loc[k] for k in self.VIS_TENSORS if loc[k] is not None}
                 t['hist_embeds'] = hist
                 t['hist_masks'] = length2mask(hist_lens, hist.size(1), 'cpu').logical_not()
-                out = self._g_vis(t, dev, extra_key=(m.precision, m.config.imagine_enc_pano),
+                out = self._g_vis(t, dev, extra_key=(m.precision, ops.h16(), blocks.fold_enabled(), m.config.imagine_enc_pano),
                                   weights_token=graphs.weights_token(m, self._wt_cache))
                 return (out['act_logits'], out['states']) if return_states else (out['act_logits'],)
             hist_masks = length2mask(hist_lens, hist.size(1), hist.device).logical_not()

@@ -12,11 +12,42 @@ from typing import Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import check, EPI_NONE, EPI_GELU, EPI_RELU, MASK_ADD_NEG10000, MASK_NEG_INF  # noqa: F401
+from ._lib import check, EPI_NONE, EPI_GELU, EPI_RELU, MASK_ADD_NEG10000, MASK_NEG_INF, LN_FOLD, LN_RESIDUAL  # noqa: F401
 
 HIDDEN = 768
 HEADS = 12
-BF16, F32 = torch.bfloat16, torch.float32
+BF16, F16, F32 = torch.bfloat16, torch.float16, torch.float32
+_DT = {BF16: _lib.DT_BF16, F16: _lib.DT_F16, F32: _lib.DT_F32}
+
+
+class _Half:
+    """The 16-bit operand format new activations / weight shadows are created in: bf16, or fp16 for inference on tensors
+    whose range the host has bounded (blocks.half_format_for).  Training always runs bf16."""
+    dtype = BF16
+
+
+class half_format:
+    """with ops.half_format(torch.float16): ...   (set by the host modules once per mode call)"""
+
+    def __init__(self, dtype):
+        if dtype not in (BF16, F16):
+            raise _lib.VlnImagineError('the 16-bit operand format must be torch.bfloat16 or torch.float16')
+        self.dtype = dtype
+
+    def __enter__(self):
+        self.prev = _Half.dtype
+        _Half.dtype = self.dtype
+
+    def __exit__(self, *a):
+        _Half.dtype = self.prev
+
+
+def h16():
+    return _Half.dtype
+
+
+def is16(dtype) -> bool:
+    return dtype in (BF16, F16)
 
 
 class _Counters:
@@ -115,7 +146,19 @@ _TILE_TABLE = load_tile_table()
 
 
 def autotune_enabled() -> bool:
-    return os.environ.get('VLN_IMAGINE_AUTOTUNE', '1') != '0' and not os.environ.get('VI_GEMM_TILE')
+    """Timing tile candidates on first use is OFF by default: shapes missing from tile_table.json use the library's cost
+    model, so results and timings are reproducible from process to process and a rollout never stalls on a tuning pass.
+    tools/tune_tiles.py (VLN_IMAGINE_AUTOTUNE=1) measures new shapes and rewrites the table."""
+    return os.environ.get('VLN_IMAGINE_AUTOTUNE', '0') == '1' and not os.environ.get('VI_GEMM_TILE')
+
+
+def _table_tile(key) -> int:
+    """tile from the measured table: the exact signature, else the same shape without the LayerNorm / dual-output flags"""
+    for k in (key, key[:8] + key[-1:]):
+        ks = _key_str(k)
+        if ks in _TILE_TABLE:
+            return int(_TILE_TABLE[ks])
+    return 0
 
 
 def _tune_tile(key, launch, N: int, pair_ok: bool) -> int:
@@ -123,10 +166,11 @@ def _tune_tile(key, launch, N: int, pair_ok: bool) -> int:
     the fastest.  Skipped (library cost model) while a CUDA graph is being captured."""
     if key in _TILE_CACHE:
         return _TILE_CACHE[key]
-    ks = _key_str(key)
-    if ks in _TILE_TABLE and os.environ.get('VLN_IMAGINE_RETUNE', '0') == '0':
-        _TILE_CACHE[key] = int(_TILE_TABLE[ks])
-        return _TILE_CACHE[key]
+    if os.environ.get('VLN_IMAGINE_RETUNE', '0') == '0':
+        t = _table_tile(key)
+        if t or not autotune_enabled():
+            _TILE_CACHE[key] = t
+            return t
     if torch.cuda.is_current_stream_capturing():
         return 0
     best, best_t = 0, float('inf')
@@ -153,10 +197,14 @@ def _tune_tile(key, launch, N: int, pair_ok: bool) -> int:
 
 def gemm(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None,
          residual: Optional[torch.Tensor] = None, epilogue: int = EPI_NONE,
-         out_dtype: torch.dtype = BF16, group_row_end: Optional[Sequence[int]] = None,
-         out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Y = epi(X W^T + bias) + residual.  x bf16 -> tcgen05 kernel; x fp32 -> fp32 check-mode kernel.
-    w is [n_groups*N, K]; group_row_end (python ints) splits the rows of x between the weight blocks."""
+         out_dtype: Optional[torch.dtype] = None, group_row_end: Optional[Sequence[int]] = None,
+         out: Optional[torch.Tensor] = None, out16: Optional[torch.Tensor] = None, ln=None,
+         stats_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Y = epi(X W^T + bias) + residual.  x bf16 / fp16 -> tcgen05 kernel (vi_gemm16); x fp32 -> fp32 check-mode kernel.
+    w is [n_groups*N, K]; group_row_end (python ints) splits the rows of x between the weight blocks.
+    out16: a 16-bit tensor that receives a copy of an fp32 output.  ln = (mode, vec_a, stats, eps): LayerNorm folded into
+    this contraction (_lib.LN_FOLD / LN_RESIDUAL, see include/vlnimagine.h); stats_out: float32 [N/32, M, 2] that receives
+    the per-chunk row statistics of the output."""
     M, K, ldx = _rows2d(x, 'x')
     n_groups = 1 if group_row_end is None else len(group_row_end)
     if w.dim() != 2 or not w.is_contiguous() or w.shape[1] != K or w.shape[0] % n_groups:
@@ -164,22 +212,42 @@ def gemm(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None,
     N = w.shape[0] // n_groups
     ends = _lib.int_array(list(group_row_end)) if group_row_end is not None else None
     ldr = residual.stride(0) if residual is not None else 0
-    if x.dtype == BF16:
-        if w.dtype != BF16:
-            raise _lib.VlnImagineError('bf16 GEMM needs a bf16 weight')
+    if is16(x.dtype):
+        if w.dtype != x.dtype:
+            raise _lib.VlnImagineError('%s GEMM needs a weight of the same type (got %s)' % (x.dtype, w.dtype))
         if out is None:
-            out = torch.empty((M, N), dtype=out_dtype, device=x.device)
-        ydt = _lib.DT_F32 if out.dtype == F32 else _lib.DT_BF16
+            out = torch.empty((M, N), dtype=out_dtype or x.dtype, device=x.device)
+        if out.dtype != F32 and out.dtype != x.dtype:
+            raise _lib.VlnImagineError('GEMM output must be fp32 or the operand type')
+        a = _lib.GemmArgs()
+        a.x, a.ldx, a.w, a.in_dtype = x.data_ptr(), ldx, w.data_ptr(), _DT[x.dtype]
+        a.bias, a.residual, a.ldr = _ptr(bias), _ptr(residual), ldr
+        a.y, a.ldy, a.y_dtype = out.data_ptr(), out.stride(0), _DT[out.dtype]
+        if out16 is not None:
+            if out16.dtype != x.dtype:
+                raise _lib.VlnImagineError('the 16-bit output copy must have the operand type')
+            a.y16, a.ldy16 = out16.data_ptr(), out16.stride(0)
+        a.M, a.N, a.K, a.epilogue, a.n_groups, a.group_row_end = M, N, K, epilogue, n_groups, ends
+        ln_mode = 0
+        if ln is not None:
+            ln_mode, vec_a, stats, eps = ln
+            a.ln_mode, a.ln_vec_a, a.ln_stats, a.ln_chunks, a.ln_eps = ln_mode, vec_a.data_ptr(), stats.data_ptr(), stats.shape[0], eps
+            a.stats_ld = stats.shape[1]
+        if stats_out is not None:
+            if stats_out.shape[0] * 32 != N or stats_out.shape[1] < M or (ln is not None and ln[2].shape[1] != stats_out.shape[1]):
+                raise _lib.VlnImagineError('stats_out must be [N/32, >=M, 2] with the row stride of the input statistics')
+            a.stats_out, a.stats_ld = stats_out.data_ptr(), stats_out.shape[1]
+        ge = tuple(group_row_end) if group_row_end is not None else None
+        key = (M, N, K, ge, epilogue, bias is not None, residual is not None, 1 if out.dtype == F32 else 0,
+               ln_mode, out16 is not None, stats_out is not None, x.device.index)
 
         def launch(tile):
-            check(lib.vi_gemm_bf16_tiled(x.data_ptr(), ldx, w.data_ptr(), _ptr(bias), _ptr(residual), ldr, out.data_ptr(),
-                                         out.stride(0), ydt, M, N, K, epilogue, n_groups, ends, tile, _stream()),
-                  'vi_gemm_bf16_tiled')
-        tile = 0
-        if autotune_enabled():
-            ge = tuple(group_row_end) if group_row_end is not None else None
+            a.tile = tile
+            check(lib.vi_gemm16(a, _stream()), 'vi_gemm16')
+        if os.environ.get('VI_GEMM_TILE'):
+            tile = 0
+        else:
             pair_ok = ge is None or all(e % 256 == 0 for e in ge[:-1])
-            key = (M, N, K, ge, epilogue, bias is not None, residual is not None, ydt, x.device.index)
             tile = _tune_tile(key, launch, N, pair_ok)
         tr = _Counters.gemm_trace
         if tr is not None:
@@ -193,6 +261,8 @@ def gemm(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None,
     elif x.dtype == F32:
         if w.dtype != F32:
             raise _lib.VlnImagineError('fp32 GEMM needs an fp32 weight')
+        if ln is not None or out16 is not None or stats_out is not None:
+            raise _lib.VlnImagineError('LayerNorm folding exists in the tensor-core kernel only')
         if out is None:
             out = torch.empty((M, N), dtype=F32, device=x.device)
         check(lib.vi_gemm_f32(x.data_ptr(), ldx, w.data_ptr(), _ptr(bias), _ptr(residual), ldr, out.data_ptr(),
@@ -201,59 +271,6 @@ def gemm(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None,
     else:
         raise _lib.VlnImagineError('unsupported GEMM dtype %s' % x.dtype)
     return out
-
-
-def gemm_mc(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
-            epilogue: int = EPI_NONE, out_dtype: torch.dtype = BF16, group_row_end: Optional[Sequence[int]] = None,
-            tile: int = 256) -> torch.Tensor:
-    """EXPERIMENTAL: ``gemm`` through vi_gemm_bf16_mc (W tile multicast across a 2-CTA cluster).  Not used by the model code;
-    tools/gemm_mc_check.py compares it with ``gemm`` and times both."""
-    M, K, ldx = _rows2d(x, 'x')
-    n_groups = 1 if group_row_end is None else len(group_row_end)
-    N = w.shape[0] // n_groups
-    out = torch.empty((M, N), dtype=out_dtype, device=x.device)
-    ends = _lib.int_array(list(group_row_end)) if group_row_end is not None else None
-    check(lib.vi_gemm_bf16_mc(x.data_ptr(), ldx, w.data_ptr(), _ptr(bias), _ptr(residual), residual.stride(0) if residual is not None else 0,
-                              out.data_ptr(), out.stride(0), _lib.DT_F32 if out_dtype == F32 else _lib.DT_BF16, M, N, K, epilogue,
-                              n_groups, ends, tile, _stream()), 'vi_gemm_bf16_mc')
-    _launched(1)
-    return out
-
-
-def fused_ln_enabled() -> bool:
-    """vi_gemm_ln_bf16 (cluster GEMM with residual + LayerNorm in the epilogue) is correct (tests/test_kernels_gpu.py::
-    test_gemm_ln_rowblock) but not yet faster than the tuned GEMM + row kernel it replaces (B200, M = 4416: 44.9 vs 17.1 us
-    at K = 768, 66.8 vs 29.2 us at K = 3072; 14.9 / 35.6 us with its epilogue I/O switched off - DESIGN.md section 5), so
-    it is opt-in: VLN_IMAGINE_FUSED_LN=1."""
-    return os.environ.get('VLN_IMAGINE_FUSED_LN', '0') == '1'
-
-
-def gemm_ln(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], residual: Optional[torch.Tensor],
-            gamma: torch.Tensor, beta: torch.Tensor, eps: float, want32: bool = True, want16: bool = True,
-            want_pre: bool = False, group_row_end: Optional[Sequence[int]] = None):
-    """(pre32 or None, y32 or None, y16 or None) with y = LayerNorm(x w^T + bias + residual) * gamma + beta over 768
-    columns (vi_gemm_ln_bf16: cluster GEMM with the LayerNorm in its epilogue).  x bf16 [M, K], w bf16 [n_groups*768, K]."""
-    M, K, ldx = _rows2d(x, 'x')
-    n_groups = 1 if group_row_end is None else len(group_row_end)
-    if x.dtype != BF16 or w.dtype != BF16 or not w.is_contiguous() or w.shape != (n_groups * HIDDEN, K):
-        raise _lib.VlnImagineError('gemm_ln: x / w must be bf16 with w of shape [%d, %d] (got %s)' % (n_groups * HIDDEN, K, tuple(w.shape)))
-    dev = x.device
-    pre = torch.empty((M, HIDDEN), dtype=F32, device=dev) if want_pre else None
-    y32 = torch.empty((M, HIDDEN), dtype=F32, device=dev) if want32 else None
-    y16 = torch.empty((M, HIDDEN), dtype=BF16, device=dev) if want16 else None
-    ends = _lib.int_array(list(group_row_end)) if group_row_end is not None else None
-    ldr = residual.stride(0) if residual is not None else 0
-    tr = _Counters.gemm_trace
-    if tr is not None:
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-    check(lib.vi_gemm_ln_bf16(x.data_ptr(), ldx, w.data_ptr(), _ptr(bias), _ptr(residual), ldr, gamma.data_ptr(), beta.data_ptr(),
-                              eps, _ptr(pre), _ptr(y32), _ptr(y16), M, K, n_groups, ends, _stream()), 'vi_gemm_ln_bf16')
-    _launched(1)
-    if tr is not None:
-        e1.record()
-        tr.append((M, HIDDEN, K, e0, e1))
-    return pre, y32, y16
 
 
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, B: int, Lq: int, Lk: int,
@@ -269,7 +286,7 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, B: int, Lq: int
     if key_mask is not None and (key_mask.dtype != torch.uint8 or not key_mask.is_contiguous()):
         raise _lib.VlnImagineError('key_mask must be a contiguous uint8 tensor')
     check(lib.vi_attn_fwd(q.data_ptr(), ldq, k.data_ptr(), ldk, v.data_ptr(), ldv, out.data_ptr(), out.stride(0),
-                          _lib.DT_BF16 if q.dtype == BF16 else _lib.DT_F32, _ptr(key_mask), _ptr(pair_dist),
+                          _DT[q.dtype], _ptr(key_mask), _ptr(pair_dist),
                           _ptr(bias_affine), _ptr(lse), B, HEADS, Lq, Lk, mask_mode, _stream()), 'vi_attn_fwd')
     _launched(1)
     return out
@@ -299,9 +316,13 @@ def attention_multi(problems, mask_mode: int = MASK_ADD_NEG10000):
             dtype = q.dtype
         elif dtype != q.dtype:
             raise _lib.VlnImagineError('attention problems of one launch must share a dtype')
-    check(lib.vi_attn_fwd_multi(arr, n, HEADS, _lib.DT_BF16 if dtype == BF16 else _lib.DT_F32, mask_mode, _stream()),
+    check(lib.vi_attn_fwd_multi(arr, n, HEADS, _DT[dtype], mask_mode, _stream()),
           'vi_attn_fwd_multi')
-    _launched(1 if dtype == BF16 else n)
+    _launched(1 if is16(dtype) else n)
+
+
+def _dt16(t: Optional[torch.Tensor]) -> int:
+    return _DT[t.dtype] if t is not None else _lib.DT_BF16
 
 
 def add_ln(a: torch.Tensor, b: Optional[torch.Tensor], gamma: torch.Tensor, beta: torch.Tensor, eps: float,
@@ -309,10 +330,10 @@ def add_ln(a: torch.Tensor, b: Optional[torch.Tensor], gamma: torch.Tensor, beta
     """LayerNorm(a [+ b]); returns (y32 or None, y16 or None)."""
     rows = a.shape[0]
     y32 = torch.empty((rows, HIDDEN), dtype=F32, device=a.device) if want32 else None
-    y16 = torch.empty((rows, HIDDEN), dtype=BF16, device=a.device) if want16 else None
+    y16 = torch.empty((rows, HIDDEN), dtype=h16(), device=a.device) if want16 else None
     n_groups = 1 if group_row_end is None else len(group_row_end)
     ends = _lib.int_array(list(group_row_end)) if group_row_end is not None else None
-    check(lib.vi_add_ln(a.data_ptr(), _ptr(b), gamma.data_ptr(), beta.data_ptr(), eps, _ptr(y32), _ptr(y16), rows,
+    check(lib.vi_add_ln(a.data_ptr(), _ptr(b), gamma.data_ptr(), beta.data_ptr(), eps, _ptr(y32), _ptr(y16), _dt16(y16), rows,
                         n_groups, ends, _stream()), 'vi_add_ln')
     _launched(1)
     return y32, y16
@@ -320,12 +341,12 @@ def add_ln(a: torch.Tensor, b: Optional[torch.Tensor], gamma: torch.Tensor, beta
 
 def embed_compose(rows: int, device, *, a=None, a2=None, a3=None, a_ln=None, feat=None, feat_w=None, feat_b=None, feat_ln=None,
                   idx=None, table=None, pos_table=None, pos_period=0, const_row=None, const_row2=None,
-                  out_ln=None, eps=1e-12, y32=None, y16=None, want16=False, want32=True):
+                  out_ln=None, eps=1e-12, y32=None, y16=None, want16=False, want32=True, ln2=None, ln2_eps=1e-5):
     """See vi_embed_compose.  *_ln are (gamma, beta) pairs.  y32 / y16 may be preallocated row views."""
     if y32 is None and want32:
         y32 = torch.empty((rows, HIDDEN), dtype=F32, device=device)
     if y16 is None and want16:
-        y16 = torch.empty((rows, HIDDEN), dtype=BF16, device=device)
+        y16 = torch.empty((rows, HIDDEN), dtype=h16(), device=device)
     args = _lib.EmbedArgs()
     args.a, args.a2, args.a3 = _ptr(a), _ptr(a2), _ptr(a3)
     if a_ln is not None:
@@ -343,7 +364,9 @@ def embed_compose(rows: int, device, *, a=None, a2=None, a3=None, a_ln=None, fea
     if out_ln is not None:
         args.out_gamma, args.out_beta = out_ln[0].data_ptr(), out_ln[1].data_ptr()
     args.eps = eps
-    args.y32, args.y16, args.rows = _ptr(y32), _ptr(y16), rows
+    args.y32, args.y16, args.rows, args.y16_dtype = _ptr(y32), _ptr(y16), rows, _dt16(y16)
+    if ln2 is not None:                               # a second LayerNorm chained on the result: y16 = LN2(y32)
+        args.ln2_gamma, args.ln2_beta, args.ln2_eps = ln2[0].data_ptr(), ln2[1].data_ptr(), ln2_eps
     check(lib.vi_embed_compose(args, _stream()), 'vi_embed_compose')
     _launched(1)
     return y32, y16
@@ -365,8 +388,8 @@ def mul_bcast(x: torch.Tensor, x_batch_stride: int, s: torch.Tensor, s_batch_str
     """y[b, r] = x[b, r] * s[b] over 768-wide rows; x / s are base views with element batch strides."""
     rows = n_batches * rows_per_batch
     y32 = torch.empty((rows, HIDDEN), dtype=F32, device=x.device) if want32 else None
-    y16 = torch.empty((rows, HIDDEN), dtype=BF16, device=x.device) if want16 else None
-    check(lib.vi_mul_bcast(x.data_ptr(), x_batch_stride, s.data_ptr(), s_batch_stride, _ptr(y32), _ptr(y16), rows,
+    y16 = torch.empty((rows, HIDDEN), dtype=h16(), device=x.device) if want16 else None
+    check(lib.vi_mul_bcast(x.data_ptr(), x_batch_stride, s.data_ptr(), s_batch_stride, _ptr(y32), _ptr(y16), _dt16(y16), rows,
                            rows_per_batch, _stream()), 'vi_mul_bcast')
     _launched(1)
     return y32, y16
@@ -396,8 +419,8 @@ def mask_logits_navtype(raw: torch.Tensor, nav_types: torch.Tensor):
 
 def gather_mean(src: torch.Tensor, offsets: torch.Tensor, row_idx: torch.Tensor, R: int, want16: bool, want32: bool = True):
     y32 = torch.empty((R, HIDDEN), dtype=F32, device=src.device) if want32 else None
-    y16 = torch.empty((R, HIDDEN), dtype=BF16, device=src.device) if want16 else None
-    check(lib.vi_gather_mean(src.data_ptr(), offsets.data_ptr(), row_idx.data_ptr(), _ptr(y32), _ptr(y16), R, _stream()),
+    y16 = torch.empty((R, HIDDEN), dtype=h16(), device=src.device) if want16 else None
+    check(lib.vi_gather_mean(src.data_ptr(), offsets.data_ptr(), row_idx.data_ptr(), _ptr(y32), _ptr(y16), _dt16(y16), R, _stream()),
           'vi_gather_mean')
     _launched(1)
     return y32, y16
@@ -449,15 +472,21 @@ def infonce_loss_with_sims(proj, tgt, negs, row_episode, neg_episode, temperatur
 def copy_rows(src: torch.Tensor, src_bs: int, src_rs: int, n_batches: int, rows_per_batch: int,
               dst32: Optional[torch.Tensor], dst16: Optional[torch.Tensor], dst_bs: int, dst_rs: int):
     """dst[b, r] = src[b, r] over 768-wide rows with element strides (see vi_copy_rows)."""
-    check(lib.vi_copy_rows(src.data_ptr(), src_bs, src_rs, _ptr(dst32), _ptr(dst16), dst_bs, dst_rs, n_batches,
+    check(lib.vi_copy_rows(src.data_ptr(), src_bs, src_rs, _ptr(dst32), _ptr(dst16), _dt16(dst16), dst_bs, dst_rs, n_batches,
                            rows_per_batch, _stream()), 'vi_copy_rows')
     _launched(1)
 
 
 def cast_bf16(src: torch.Tensor, dst: Optional[torch.Tensor] = None):
+    """fp32 -> bf16 (the training path and weight shadows of it)"""
+    return cast_h16(src, dst, BF16)
+
+
+def cast_h16(src: torch.Tensor, dst: Optional[torch.Tensor] = None, dtype=None):
+    """fp32 -> the current 16-bit operand format (or ``dtype`` / the type of ``dst``)"""
     src = src.contiguous()
     if dst is None:
-        dst = torch.empty(src.shape, dtype=BF16, device=src.device)
-    check(lib.vi_cast_bf16(src.data_ptr(), dst.data_ptr(), src.numel(), _stream()), 'vi_cast_bf16')
+        dst = torch.empty(src.shape, dtype=dtype or h16(), device=src.device)
+    check(lib.vi_cast_h16(src.data_ptr(), dst.data_ptr(), _DT[dst.dtype], src.numel(), _stream()), 'vi_cast_h16')
     _launched(1)
     return dst
