@@ -17,6 +17,7 @@ GEMM kernel: algorithmic FLOPs / CUDA-event time per launch vs MEASURED_PEAKS.js
 oracle timed on this box's host cores), `clocks`, `gpu_launches`.
 """
 import argparse
+import contextlib
 import dataclasses
 import json
 import os
@@ -295,91 +296,144 @@ def glue_leg(dev, batch, with_cpu):
     return res
 
 
-def eager_gpu_reference(shape, budget_s=2.0):
-    """The same algorithm (the oracle's plain fp32 torch ops: no fusion, no graphs, the reference's Python fusion loop) on THIS
-    GPU at the workload's own batch size - what running the reference's modules on the same box looks like ("the
-    real bar").  A reported figure of the cpu_baseline leg; never a product path."""
-    import vln_imagine_b200.synth as synth
-    from oracle import duet_oracle as O
-    man = json.load(open(os.path.join(ROOT, 'tests', 'golden', 'duet_manifest.json')))
-    sd = synth.synth_state_dict(man, seed=0)
-    ep = synth.to_torch(synth.duet_episode(shape, 1234))
-    with torch.no_grad():
-        B = shape.batch                                   # the step's cost does not depend on the context VALUES: random ones
-        g = torch.Generator().manual_seed(1)
-        txt = torch.randn(B, shape.instr_len, 768, generator=g).cuda()
-        img2 = torch.randn(B, shape.n_imagine, 768, generator=g).cuda()
-        sd = {k: v.cuda() for k, v in sd.items()}
-        ep = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in ep.items()}
-        O.nav_step(sd, ep, txt, img2)
-        torch.cuda.synchronize()
-        n, t0 = 0, time.perf_counter()
-        while time.perf_counter() - t0 < budget_s or n < 3:
-            O.nav_step(sd, ep, txt, img2)
-            torch.cuda.synchronize()
-            n += 1
-        dt = (time.perf_counter() - t0) / n
-    return {'value': B / dt, 'unit': UNIT, 'ms_per_step': dt * 1e3,
-            'what': 'the oracle (plain fp32 torch ops, eager, Python fusion loop) on this GPU, %d episodes per step' % B}
+def load_reference(model_kind):
+    """(module, root) - the UNMODIFIED reference model class (GlocalTextPathNavCMT / NavCMT) built from the reference checkout
+    (/root/reference in the build container) or from its files staged under baseline/_ref by tools/make_baseline_ref.py (the GPU
+    box), with the synthetic weights; (None, why) when neither is present.  Harness-side shims only (oracle/gen_golden.py)."""
+    for root in (os.environ.get('VLN_REFERENCE'), '/root/reference', os.path.join(ROOT, 'baseline', '_ref')):
+        sub = ('VLN-DUET', 'map_nav_src') if model_kind == 'duet' else ('VLN-HAMT', 'finetune_src')
+        if root and os.path.isfile(os.path.join(root, *sub, 'models', 'vilmodel.py' if model_kind == 'duet' else 'vilmodel_cmt.py')):
+            try:
+                from oracle import gen_golden
+                gen_golden.REF = root
+                import vln_imagine_b200.synth as synth
+                ref = gen_golden.build_reference(model_kind)
+                shapes = {k: list(v.shape) for k, v in ref.state_dict().items()}
+                ref.load_state_dict(synth.synth_state_dict(shapes, seed=0))
+                return ref, root
+            except Exception as e:                      # a missing dependency of the reference tree: fall back to the port
+                return None, '%s: %s' % (type(e).__name__, str(e)[:200])
+    return None, 'no reference files (neither /root/reference nor baseline/_ref)'
 
 
-def cpu_reference(model_kind, shape, budget_s=15.0, batch=8):
-    """The reference algorithm (CPU oracle port, fp32, all host threads) on a bounded sample of the same
-    workload: `batch` episodes of the same shape, repeated for about budget_s seconds."""
+def reference_stepper(model_kind, shape, device='cpu', seed=1234):
+    """(step() -> logits, kind, note): one navigation decision per episode of the workload shape through the reference's own
+    modules (kind 'reference'), or through the oracle port of them when the reference files are absent (kind 'port')."""
     import vln_imagine_b200.synth as synth
     from oracle import duet_oracle, hamt_oracle
+    ep = synth.to_torch((synth.duet_episode if model_kind == 'duet' else synth.hamt_episode)(shape, seed))
+    ep = {k: (v.to(device) if torch.is_tensor(v) else v) for k, v in ep.items()}
+    g = torch.Generator().manual_seed(1)                 # the step's cost does not depend on the context VALUES
+    txt = torch.randn(shape.batch, shape.instr_len, 768, generator=g).to(device)
+    img2 = torch.randn(shape.batch, shape.n_imagine, 768, generator=g).to(device)
+    ref, root = load_reference(model_kind)
+    if ref is None:
+        man = json.load(open(os.path.join(ROOT, 'tests', 'golden', '%s_manifest.json' % model_kind)))
+        sd = {k: v.to(device) for k, v in synth.synth_state_dict(man, seed=0).items()}
+        O = duet_oracle if model_kind == 'duet' else hamt_oracle
+        if model_kind == 'duet':
+            return (lambda: O.nav_step(sd, ep, txt, img2)[2]['fused_logits']), 'port', 'oracle port (%s)' % root
+        return (lambda: O.nav_step(sd, ep, txt, img2)[0]), 'port', 'oracle port (%s)' % root
+    ref = ref.to(device)
+    if model_kind == 'duet':
+        pano_in = {'view_img_fts': ep['view_img_fts'], 'obj_img_fts': None, 'loc_fts': ep['loc_fts'], 'nav_types': ep['nav_types'],
+                   'view_lens': ep['view_lens'], 'obj_lens': None}
+        nav_in = {k: ep[k] for k in ('txt_masks', 'gmap_img_embeds', 'gmap_step_ids', 'gmap_pos_fts', 'gmap_masks', 'gmap_pair_dists',
+                                     'gmap_visited_masks', 'gmap_vpids', 'vp_img_embeds', 'vp_pos_fts', 'vp_masks', 'vp_nav_masks',
+                                     'vp_cand_vpids', 'imagine_masks')}
+        nav_in.update(txt_embeds=txt, imagine_embeds=img2, vp_obj_masks=None)
+
+        def step():
+            ref('panorama', pano_in)
+            return ref('navigation', nav_in)['fused_logits']
+    else:
+        hm = hamt_oracle.hist_masks_from_lens(ep['hist_lens'], ep['hist_embeds'].shape[1]).to(device)
+        step_ids = torch.LongTensor([ep['ob_step']]).to(device)
+
+        def step():
+            out = ref('visual', txt_embeds=txt, txt_masks=ep['txt_masks'], hist_embeds=ep['hist_embeds'], hist_masks=hm,
+                      ob_img_feats=ep['ob_img_feats'], ob_ang_feats=ep['ob_ang_feats'], ob_nav_types=ep['ob_nav_types'],
+                      ob_masks=ep['ob_masks'], imagine_embeds=img2, imagine_masks=ep['imagine_masks'])
+            ref('history', hist_img_feats=ep['hist_img_feats'], hist_ang_feats=ep['hist_ang_feats'], ob_step_ids=step_ids,
+                hist_pano_img_feats=ep['hist_pano_img_feats'], hist_pano_ang_feats=ep['hist_pano_ang_feats'])
+            return out[0]
+    return step, 'reference', 'unmodified reference modules from %s' % root
+
+
+def eager_gpu_reference(model_kind, shape, budget_s=2.0):
+    """The reference's own modules (else the oracle port), eager PyTorch on THIS GPU at the workload's batch size, in fp32 and
+    under torch.autocast(bfloat16) - what running the reference on the same box looks like ("the real bar").
+    A reported figure of the cpu_baseline leg; never a product path."""
+    step, kind, note = reference_stepper(model_kind, shape, 'cuda')
+    out = {'kind': kind, 'what': '%s, eager PyTorch on this GPU, %d episodes per step' % (note, shape.batch)}
+    for tag, ctx in (('fp32', contextlib.nullcontext()), ('bf16_autocast', torch.autocast('cuda', dtype=torch.bfloat16))):
+        try:
+            with torch.no_grad(), ctx:
+                step()
+                torch.cuda.synchronize()
+                n, t0 = 0, time.perf_counter()
+                while time.perf_counter() - t0 < budget_s or n < 3:
+                    step()
+                    torch.cuda.synchronize()
+                    n += 1
+                dt = (time.perf_counter() - t0) / n
+            out[tag] = {'value': shape.batch / dt, 'unit': UNIT, 'ms_per_step': dt * 1e3}
+        except Exception as e:
+            out[tag] = {'error': '%s: %s' % (type(e).__name__, str(e)[:200])}
+    return out
+
+
+def cpu_reference(model_kind, shape, budget_s=15.0):
+    """The reference on the host cores (its own modules when staged under baseline/_ref, else the oracle port), fp32, all host
+    threads, on a bounded sample of the same workload: steps of the workload's own batch for about budget_s seconds."""
     torch.set_num_threads(os.cpu_count())
-    sample = dataclasses.replace(shape, batch=batch)
-    man = json.load(open(os.path.join(ROOT, 'tests', 'golden', '%s_manifest.json' % model_kind)))
-    sd = synth.synth_state_dict(man, seed=0)
-    O = duet_oracle if model_kind == 'duet' else hamt_oracle
-    ep = synth.to_torch((synth.duet_episode if model_kind == 'duet' else synth.hamt_episode)(sample, 1234))
+    step, kind, note = reference_stepper(model_kind, shape, 'cpu')
     with torch.no_grad():
-        txt, img, loss, img2 = O.episode_prelude(sd, ep)
-        O.nav_step(sd, ep, txt, img2)                       # warm-up
+        step()                                              # warm-up
         times = []
         t_end = time.perf_counter() + budget_s
         while time.perf_counter() < t_end or len(times) < 3:
             t0 = time.perf_counter()
-            O.nav_step(sd, ep, txt, img2)
+            step()
             times.append(time.perf_counter() - t0)
     best = min(times)
-    return {'value': batch / best, 'unit': UNIT, 'cores': os.cpu_count(), 'kind': 'port',
-            'sample': '%d episodes of the same shape x %d repeats, best step %.1f ms, fp32 CPU oracle (oracle/%s_oracle.py)'
-                      % (batch, len(times), best * 1e3, model_kind)}, times
+    return {'value': shape.batch / best, 'unit': UNIT, 'cores': os.cpu_count(), 'kind': kind,
+            'sample': '%d-episode steps (the workload batch) x %d repeats, best step %.1f ms, fp32 on the host CPU: %s'
+                      % (shape.batch, len(times), best * 1e3, note)}, times
 
 
 def run_reference_arm(args, model_kind, shape, desc, rank):
+    """`--impl reference`: the reference's own CPU implementation of the path (its unmodified modules when staged, else the port)
+    on the host cores, same workload shape and batch, exactly --steps steps after --warmup warm-up steps (rank 0 only)."""
     if rank != 0:
         return
-    batch = 8
-    import vln_imagine_b200.synth as synth
-    from oracle import duet_oracle, hamt_oracle
     torch.set_num_threads(os.cpu_count())
-    sample = dataclasses.replace(shape, batch=batch)
-    man = json.load(open(os.path.join(ROOT, 'tests', 'golden', '%s_manifest.json' % model_kind)))
-    sd = synth.synth_state_dict(man, seed=0)
-    O = duet_oracle if model_kind == 'duet' else hamt_oracle
-    ep = synth.to_torch((synth.duet_episode if model_kind == 'duet' else synth.hamt_episode)(sample, 1234))
-    steps = min(args.steps, 40)
-    warm = min(args.warmup, 3)
+    step, kind, note = reference_stepper(model_kind, shape, 'cpu')
+    steps, warm = args.steps, args.warmup
     with torch.no_grad():
-        txt, img, loss, img2 = O.episode_prelude(sd, ep)
-        for _ in range(max(warm, 1)):
-            O.nav_step(sd, ep, txt, img2)
+        t0 = time.perf_counter()
+        step()
+        t_one = time.perf_counter() - t0
+        budget = float(os.environ.get('VI_REFERENCE_BUDGET_S', '240'))
+        if t_one * (steps + warm) > budget:                 # keep the whole arm within a few minutes, and say so
+            scale = budget / (t_one * (steps + warm))
+            steps, warm = max(int(steps * scale), 3), max(int(warm * scale), 1)
+        for _ in range(max(warm - 1, 0)):
+            step()
         t0 = time.perf_counter()
         for _ in range(steps):
-            O.nav_step(sd, ep, txt, img2)
+            step()
         dt = time.perf_counter() - t0
-    val = batch * steps / dt
+    B = shape.batch
+    val = B * steps / dt
     line = {'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': steps,
             'warmup': warm, 'ms_per_step': dt / steps * 1e3, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': '%s: %s' % (args.workload, desc),
-                       'sample': 'each step = %d episodes of the workload shape on the host CPU' % batch},
-            'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': os.cpu_count(), 'kind': 'port',
-                             'sample': '%d-episode steps x %d, CPU oracle port of the reference (reference is Python and '
-                                       'absent on the GPU box)' % (batch, steps)},
+            'config': {'workload': '%s: %s' % (args.workload, desc), 'episodes_per_step': B,
+                       'requested': {'steps': args.steps, 'warmup': args.warmup},
+                       'sample': 'each step = %d episodes (the workload batch) on the host CPU: %s' % (B, note)},
+            'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': os.cpu_count(), 'kind': kind,
+                             'sample': '%d-episode steps x %d, fp32, %d host threads: %s' % (B, steps, os.cpu_count(), note)},
             'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(line), flush=True)
 
@@ -388,13 +442,12 @@ def run_reference_arm(args, model_kind, shape, desc, rank):
 # ----------------------------------------------------------------------------------------------
 # fine-tuning workload (BASELINE.json cfg-4): forward + backward + gradient all-reduce + optimiser step
 # ----------------------------------------------------------------------------------------------
-def run_train(args, shape, desc, rank, local_rank, world):
+def train_measure(args, shape, rank, local_rank, world, K, W, detail=True):
+    """Fine-tuning iterations (forward + backward + gradient all-reduce + clipping + AdamW) on this rank's episodes; the
+    process group is the caller's.  Returns the measurements of rank 0's report (every rank must call it)."""
     import torch.distributed as dist
     from vln_imagine_b200 import config, duet, ops, synth, train
-    torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
-    if world > 1:
-        dist.init_process_group('nccl', device_id=dev)
     T = 6                                                   # navigation steps per episode (SURVEY.md 8(d))
     B = shape.batch
     a = config.default_duet_args()
@@ -437,7 +490,6 @@ def run_train(args, shape, desc, rank, local_rank, world):
     G, P = ep_host['gmap_img_embeds'].shape[1], ep_host['vp_img_embeds'].shape[1]
     d['gmap_vpids'], d['vp_cand_vpids'] = net.intern_vpids(ep_host['gmap_vpids'], ep_host['vp_cand_vpids'], G, P, dev)
     host['gmap_vpids'], host['vp_cand_vpids'] = d['gmap_vpids'], d['vp_cand_vpids']
-    K, W = args.steps, args.warmup
     for _ in range(W):
         iteration(d)
     torch.cuda.synchronize()
@@ -483,9 +535,35 @@ def run_train(args, shape, desc, rank, local_rank, world):
         t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, ms_e2e = float(t[0]), float(t[1])
-    # roofline of the GEMM kernel over one EAGER iteration (forward + dgrad + wgrad launches)
+    # the one collective of the path, alone: NCCL all-reduce (AVG) of the flat fp32 gradient buffer
+    ar_ms = None
+    if world > 1:
+        barrier()
+        for _ in range(2):
+            flat.all_reduce()
+        torch.cuda.synchronize()
+        barrier()
+        e0.record()
+        for _ in range(5):
+            flat.all_reduce()
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / 5], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ar_ms = float(t[0])
+    loss_host = float(loss_host)
+    res = dict(ms=ms, ms_e2e=ms_e2e, K=K, W=W, T=T, B=B, h2d=h2d, launches=launches, loss=loss_host,
+               loss_finite=bool(np.isfinite(loss_host)), allreduce_ms=ar_ms, allreduce_bytes=flat.bytes(),
+               allreduce_busbw_gbs=(2.0 * (world - 1) / world * flat.bytes() / (ar_ms * 1e-3) / 1e9) if ar_ms else None,
+               clocks=sampler.summary(), graphed=graphed is not None,
+               dropout=(net.config.hidden_dropout_prob, net.config.attention_probs_dropout_prob, model.drop_env.p))
     if graphed is not None:
         graphed.finish()
+    if not detail:
+        del graphed, opt, flat, model
+        torch.cuda.empty_cache()
+        return res
+    # roofline of the GEMM kernel over one EAGER iteration (forward + dgrad + wgrad launches)
     iteration = eager_iteration
     torch.cuda.synchronize()
     torch.cuda._sleep(400_000_000)                          # ~0.2 s head start: the host queues ~4000 launches
@@ -505,6 +583,19 @@ def run_train(args, shape, desc, rank, local_rank, world):
         n_, t_ = breakdown.get(name, (0, 0.0))
         breakdown[name] = (n_ + 1, t_ + x.elapsed_time(y))
     breakdown = {k: {'launches': v[0], 'ms': round(v[1], 3)} for k, v in sorted(breakdown.items(), key=lambda kv: -kv[1][1])}
+    res.update(gemm_flops=gemm_flops, gemm_ms=gemm_ms, n_gemm=len(trace), breakdown=breakdown)
+    return res
+
+
+def run_train(args, shape, desc, rank, local_rank, world):
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    r = train_measure(args, shape, rank, local_rank, world, args.steps, args.warmup, detail=True)
+    ms, ms_e2e, K, W, T, B, h2d, launches, loss_host = (r[k] for k in ('ms', 'ms_e2e', 'K', 'W', 'T', 'B', 'h2d', 'launches', 'loss'))
+    gemm_flops, gemm_ms, breakdown = r['gemm_flops'], r['gemm_ms'], r['breakdown']
     if world > 1:
         dist.destroy_process_group()
     if rank != 0:
@@ -527,11 +618,11 @@ def run_train(args, shape, desc, rank, local_rank, world):
                    'replay': 'eager launches (autograd)' if args.no_graph else 'two CUDA graphs per iteration (forward + backward | '
                              'clipping + AdamW) around the eager NCCL all-reduce',
                    'dropout': 'on: hidden %.2f, attention %.2f, features %.2f, projection head 0.15'
-                              % (net.config.hidden_dropout_prob, net.config.attention_probs_dropout_prob, model.drop_env.p),
+                              % r['dropout'],
                    'l2': 'no flush: an iteration touches > 3 GB of weights, gradients and saved activations',
-                   'collective': 'one NCCL all-reduce (AVG) of the flat fp32 gradient buffer, %.0f MB' % (flat.bytes() / 1e6),
+                   'collective': 'one NCCL all-reduce (AVG) of the flat fp32 gradient buffer, %.0f MB' % (r['allreduce_bytes'] / 1e6),
                    'weights': 'random-init (deterministic synthetic)'},
-        'clocks': sampler.summary(),
+        'clocks': r['clocks'],
         'e2e': {'value': world * B * T * K / (ms_e2e * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4,
                 'ms_per_step': ms_e2e / K, 'api': 'train.duet_finetune_iteration through the module API; episode batch copied '
                                                   'from pinned host memory every iteration, loss read back'},
@@ -539,12 +630,18 @@ def run_train(args, shape, desc, rank, local_rank, world):
         'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': achieved / peak_tf,
                      'traffic': None, 'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained' if peaks else 'fallback',
                      'kernel': 'gemm_bf16_tc_kernel (tcgen05): %d launches/iteration (forward, dgrad, wgrad), %.1f GFLOP executed, '
-                               '%.3f ms of GEMM time' % (len(trace), gemm_flops / 1e9, gemm_ms)},
+                               '%.3f ms of GEMM time' % (r['n_gemm'], gemm_flops / 1e9, gemm_ms)},
+        'allreduce': {'ms': r['allreduce_ms'], 'bytes': r['allreduce_bytes'], 'busbw_gbs': r['allreduce_busbw_gbs']},
+        'loss_finite': r['loss_finite'],
         'step': {'algorithmic_gflop_per_iteration': fl_episode * B / 1e9,
                  'tflops': fl_episode * B / (ms / K * 1e-3) / 1e12, 'launches_per_iteration': launches, 'loss': loss_host,
                  'breakdown': breakdown},
     }
+    if not r['loss_finite']:
+        line['invalid'] = 'the loss is not finite (%r): this is not a training measurement' % loss_host
     print(json.dumps(line), flush=True)
+    if not r['loss_finite']:
+        sys.exit(3)
 
 # ----------------------------------------------------------------------------------------------
 def main():
@@ -759,6 +856,25 @@ def main():
         breakdown = {k: {'launches_per_step': round(v[0] / TRACE_STEPS, 2), 'ms_per_step': round(v[1] / TRACE_STEPS, 4)} for k, v in
                      sorted(breakdown.items(), key=lambda kv: -kv[1][1])}
 
+    # cfg-4 beside the headline: a few fine-tuning iterations (forward + backward + NCCL gradient all-reduce + AdamW) on the
+    # same ranks, so that the 1/2/4/8-GPU scaling runs also record the only collective this path has (every rank takes part)
+    train_rec = None
+    if model_kind == 'duet' and args.workload == 'duet_cfg2' and os.environ.get('VI_BENCH_TRAIN', '1') != '0':
+        try:
+            del model
+            torch.cuda.empty_cache()
+            tr_ = train_measure(args, shape, rank, local_rank, world, 4, 3, detail=False)
+            train_rec = {'what': 'DUET-Imagine fine-tuning (cfg-4): %d episodes/GPU x %d navigation steps, forward + backward + gradient '
+                                 'all-reduce + clipping + AdamW, dropout on, CUDA-graph replay' % (tr_['B'], tr_['T']),
+                         'value': world * tr_['B'] * tr_['T'] * tr_['K'] / (tr_['ms'] * 1e-3), 'unit': UNIT,
+                         'ms_per_iteration': tr_['ms'] / tr_['K'], 'iterations': tr_['K'], 'warmup': tr_['W'],
+                         'allreduce_ms': tr_['allreduce_ms'], 'allreduce_bytes': tr_['allreduce_bytes'],
+                         'allreduce_busbw_gbs': tr_['allreduce_busbw_gbs'], 'loss': tr_['loss'], 'loss_finite': tr_['loss_finite']}
+        except Exception as e:                          # noqa: BLE001 - an auxiliary record must never cost the bench line
+            train_rec = {'error': '%s: %s' % (type(e).__name__, str(e)[:300])}
+            if world > 1:
+                raise                                   # ranks must not diverge inside a collective
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -807,14 +923,16 @@ def main():
                  'prelude_ms_per_episode_batch': prelude_ms,
                  'breakdown': breakdown},
     }
+    if train_rec is not None:
+        line['train'] = train_rec
     if world == 1 and not args.no_cpu_baseline:
         cb, _ = cpu_reference(model_kind, shape)
         line['cpu_baseline'] = cb
         if model_kind == 'duet':
             try:                                        # an auxiliary figure must never cost the bench line
-                cb['same_algorithm_torch_eager_on_this_gpu'] = eager_gpu_reference(shape)
+                cb['reference_torch_eager_on_this_gpu'] = eager_gpu_reference(model_kind, shape)
             except Exception as e:                      # noqa: BLE001
-                cb['same_algorithm_torch_eager_on_this_gpu'] = {'error': '%s: %s' % (type(e).__name__, str(e)[:200])}
+                cb['reference_torch_eager_on_this_gpu'] = {'error': '%s: %s' % (type(e).__name__, str(e)[:200])}
     if world == 1 and model_kind == 'duet':
         try:                                            # an auxiliary figure must never cost the bench line
             line['step']['graph_glue'] = glue_leg(dev, B, with_cpu=not args.no_cpu_baseline)

@@ -141,6 +141,11 @@ typedef struct {
  * HAMT language | vision) in ONE launch; same arithmetic as vi_attn_fwd per problem. */
 int vi_attn_fwd_multi(const vi_attn_problem* problems, int n_problems, int H, int dtype, int mask_mode,
                       vi_stream_t stream);
+/* The same contraction on the 5th-gen tensor cores (vi_attn_tc.cu: tcgen05.mma M = 64 score tiles of two heads interleaved in
+ * the TMEM lanes, TMA-fed operands, V consumed as an MN-major operand, softmax from tcgen05.ld).  Inference shapes only: 16-bit
+ * operands, even H, Lk <= 256, no dropout / lse.  vi_attn_fwd_multi routes to it when VI_ATTN_TC=1; at the 30 - 37 query tiles of
+ * this path the mma.sync kernel is faster, so it is not the default. */
+int vi_attn_fwd_tc(const vi_attn_problem* problems, int n_problems, int H, int dtype, int mask_mode, vi_stream_t stream);
 int vi_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                 void* o, int64_t ldo, int dtype,
                 const uint8_t* key_mask, const float* pair_dist, const float* bias_affine,
@@ -252,6 +257,13 @@ int vi_margin_loss(const float* proj, const float* tgt, const float* negs, const
                    const int32_t* neg_episode, float margin, float* loss_rows, float* loss_mean, int R, int n_negs,
                    vi_stream_t stream);
 
+/* Loss rows of the pre-training proxy tasks (VLN-DUET/pretrain_src/model/pretrain_cmt.py:150 MLM, :198-204 MRC):
+ *   vi_ce_rows: out[r] = logsumexp(logits[r, 0:n_cols]) - logits[r, labels[r]]            (F.cross_entropy, reduction 'none')
+ *   vi_kl_rows: out[r] = sum_c t[r,c] * (log t[r,c] - log_softmax(logits[r])[c]), t == 0 terms dropped  (F.kl_div(...).sum(1))
+ * logits / targets are fp32 row-major with leading dimensions ld / ldt >= n_cols (a padded vocabulary GEMM output). */
+int vi_ce_rows(const float* logits, int64_t ld, const int64_t* labels, int n_cols, float* out, int64_t rows, vi_stream_t stream);
+int vi_kl_rows(const float* logits, int64_t ld, const float* targets, int64_t ldt, int n_cols, float* out, int64_t rows,
+               vi_stream_t stream);
 /* dst[b, r, 0:768] = src[b, r, 0:768] for n_batches x rows_per_batch rows; strides in ELEMENTS.  Writes an
  * fp32 and/or a 16-bit copy.  Builds the cross-attention context cat([txt_embeds, imagine_embeds], 1)
  * (D/models/vilmodel.py:1157, H/models/vilmodel_cmt.py:1110) and gathers the token-0 rows that feed

@@ -1,0 +1,82 @@
+"""north_star's parity contract at the BENCHMARK shapes: cfg-2 (DUET, B = 64) and cfg-3 (HAMT, B = 64).
+
+  * action argmax identical to the fp32 CPU oracle on >= 99.5 % of >= 2000 decisions per model - the RAW rate, near-ties included
+    (flips and their reference top-2 gaps are printed, none is excused);
+  * logits within 2e-2 (max-norm relative) with the identical -inf pattern at B = 64, where the GEMMs run other tile kernels
+    (M = 4416 / 5440 / 9024) than the B = 3 / B = 8 golden fixtures do;
+  * the same statistic in the pure-bf16 operand format is REPORTED and bounded loosely: on these random-init, nearly flat logits
+    bf16 rounding alone flips 0.4 - 0.7 % of the decisions (13 of 2048 for DUET, measured), which is why the default 16-bit
+    mode stores range-bounded tensors in fp16 (blocks.operand_format) - same tensor-core rate, 8x smaller rounding error.
+"""
+import importlib
+import json
+import os
+
+import pytest
+import torch
+
+from parity_utils import TOL, manifest, max_rel, to_dev
+
+pytestmark = pytest.mark.gpu
+
+N_BATCHES = 32          # x 64 episodes = 2048 decisions per model
+RESULTS = {}
+
+
+def _run(model_name, operand16, n_batches):
+    synth = importlib.import_module('vln_imagine_b200.synth')
+    config = importlib.import_module('vln_imagine_b200.config')
+    if model_name == 'duet':
+        from oracle import duet_oracle as O
+        from test_duet_parity_gpu import run_product
+        model = importlib.import_module('vln_imagine_b200.duet').VLNBert(config.default_duet_args()).cuda().eval()
+        shape, make, key = synth.CFG2, synth.duet_episode, 'fused_logits'
+    else:
+        from oracle import hamt_oracle as O
+        from test_hamt_parity_gpu import run_product
+        model = importlib.import_module('vln_imagine_b200.hamt').VLNBertCMT(config.default_hamt_args()).cuda().eval()
+        shape, make, key = synth.CFG3, synth.hamt_episode, 'act_logits'
+    sd = synth.synth_state_dict(manifest(model_name), seed=0)
+    model.vln_bert.load_state_dict(sd)
+    model.vln_bert.precision = 'bf16'
+    model.vln_bert.operand16 = operand16
+    torch.set_num_threads(os.cpu_count())
+    agree = total = 0
+    worst = 0.0
+    flips = []
+    for j in range(n_batches):
+        ep = synth.to_torch(make(shape, 5000 + j))
+        with torch.no_grad():
+            o_txt, _, _, o_img2 = O.episode_prelude(sd, ep)
+            nav = O.nav_step(sd, ep, o_txt, o_img2)
+        ref = nav[2]['fused_logits'] if model_name == 'duet' else nav[0]
+        out = run_product(model, to_dev(ep))
+        worst = max(worst, max_rel(out[key], ref))          # also asserts the identical -inf pattern
+        p, r = out[key].float().cpu(), ref.float()
+        a, b = p.argmax(-1), r.argmax(-1)
+        top2 = r.topk(2, -1).values
+        for i in torch.nonzero(a != b).flatten().tolist():
+            flips.append((5000 + j, i, float(top2[i, 0] - top2[i, 1])))
+        agree += int((a == b).sum())
+        total += a.numel()
+    rec = dict(model=model_name, operand16=operand16, decisions=total, agree=agree, rate=agree / total, max_rel_logit_err=worst,
+               flips=flips)
+    RESULTS[(model_name, operand16)] = rec
+    print(json.dumps(rec))
+    return rec
+
+
+@pytest.mark.parametrize('model_name', ['duet', 'hamt'])
+def test_argmax_agreement_at_benchmark_shapes(lib_built, model_name):
+    rec = _run(model_name, 'auto', N_BATCHES)
+    assert rec['decisions'] >= 2000
+    assert rec['max_rel_logit_err'] < TOL['bf16']
+    assert rec['rate'] >= 0.995, rec
+
+
+def test_pure_bf16_operands_are_reported(lib_built):
+    """pure bf16 operands (north_star's letter): logits within tolerance at B = 64; the raw agreement is what bf16 rounding
+    gives on near-tied random-init logits and is the reason fp16 operands are the default where the range allows"""
+    rec = _run('duet', 'bf16', 8)
+    assert rec['max_rel_logit_err'] < TOL['bf16']
+    assert rec['rate'] >= 0.985, rec

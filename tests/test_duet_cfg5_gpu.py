@@ -97,4 +97,4 @@ def test_cfg5_full_batch_properties(env):
     for k in KEYS:
         assert max_rel(full[k], f32[k]) < TOL['bf16'], k
     agree, total, decisive_bad = argmax_report(full['fused_logits'], f32['fused_logits'], TOL['bf16'])
-    assert decisive_bad == 0 and agree >= 0.9 * total
+    assert decisive_bad == 0 and agree >= 0.97 * total          # 32 decisions: at most one near-tie may differ

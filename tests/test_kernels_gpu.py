@@ -523,3 +523,88 @@ def test_embed_compose_chained_layernorm(ops):
     r32 = F.layer_norm(a, (768,), g1, b1, 1e-12)
     assert relerr(y32, r32) < 1e-5
     assert y16.dtype == torch.float16 and relerr(y16, F.layer_norm(r32, (768,), g2, b2, 1e-5)) < 2e-3
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# vi_attn_tc.cu: the tcgen05 attention kernel, called by name (vi_attn_fwd_tc); the dispatcher uses it only with VI_ATTN_TC=1
+# ---------------------------------------------------------------------------------------------------------------------
+TC_ATTN_CASES = ATTN_CASES + [(64, 30, 85, True, False, False), (3, 64, 256, True, False, False), (2, 65, 17, True, True, False),
+                              (2, 200, 200, True, False, False), (1, 37, 240, False, False, True)]
+
+
+@pytest.mark.parametrize('B,Lq,Lk,masked,gasa,neg_inf', [c for c in TC_ATTN_CASES if c[2] <= 256])
+@pytest.mark.parametrize('fmt', [torch.bfloat16, torch.float16])
+def test_attention_tcgen05(ops, B, Lq, Lk, masked, gasa, neg_inf, fmt):
+    qkv_q = _rand(B * Lq, 2304, seed=1).to(fmt)            # strided views, like the fused QKV output
+    qkv_k = _rand(B * Lk, 2304, seed=2).to(fmt)
+    q, k, v = qkv_q[:, :768], qkv_k[:, 768:1536], qkv_k[:, 1536:]
+    key_mask = None
+    if masked:
+        g = torch.Generator().manual_seed(3)
+        lens = torch.randint(1, Lk + 1, (B,), generator=g)
+        lens[0] = Lk
+        key_mask = (torch.arange(Lk)[None] < lens[:, None]).to(torch.uint8).cuda()
+        if Lk > 4:
+            key_mask[-1, 1] = 0
+    pair_dist = affine = None
+    if gasa:
+        pair_dist = (_rand(B, Lq, Lk, seed=4).abs() * 10).contiguous()
+        affine = torch.tensor([-0.5, 0.1], device='cuda')
+    o = torch.empty((B * Lq, 768), dtype=fmt, device='cuda')
+    ops.attention_multi([dict(q=q, k=k, v=v, out=o, B=B, Lq=Lq, Lk=Lk, key_mask=key_mask, pair_dist=pair_dist, bias_affine=affine)],
+                        mask_mode=ops.MASK_NEG_INF if neg_inf else ops.MASK_ADD_NEG10000, kernel='tc')
+    ref, _ = _attn_ref(q, k, v, B, Lq, Lk, key_mask, pair_dist, affine, neg_inf)
+    assert relerr(o, ref) < (1.5e-2 if fmt == torch.bfloat16 else 2.5e-3)
+
+
+@pytest.mark.parametrize('fmt', [torch.bfloat16, torch.float16])
+def test_attention_tcgen05_multi_problem(ops, fmt):
+    """the two token streams of a row-stacked DUET activation (global 30 nodes with GASA | local 37 views) against one shared
+    85-token context, and HAMT's bidirectional pair (85 x 53 | 53 x 85), in one launch each; padding rows stay untouched"""
+    B = 16
+    for (La, Lb, Lka, Lkb, gasa) in ((30, 37, 85, 85, False), (30, 37, 30, 37, True), (85, 53, 53, 85, False)):
+        ra = (B * La + 255) // 256 * 256
+        R = ra + B * Lb
+        x = _rand(R, 2304, seed=5).to(fmt)
+        ctx = _rand(B * 85, 3072, seed=6).to(fmt)
+        out = torch.full((R, 768), 7.0, device='cuda', dtype=fmt)
+        ga, gb = torch.Generator().manual_seed(1), torch.Generator().manual_seed(2)
+        ma = (torch.arange(Lka)[None] < torch.randint(1, Lka + 1, (B,), generator=ga)[:, None]).to(torch.uint8).cuda()
+        mb = (torch.arange(Lkb)[None] < torch.randint(1, Lkb + 1, (B,), generator=gb)[:, None]).to(torch.uint8).cuda()
+        dist = (_rand(B, La, Lka, seed=7).abs() * 10).contiguous() if gasa else None
+        aff = torch.tensor([-0.3, 0.05], device='cuda') if gasa else None
+        if Lka == 85 and Lkb == 85:                          # cross-attention: both streams read the projected context
+            ka, va, kb, vb = ctx[:, :768], ctx[:, 768:1536], ctx[:, 1536:2304], ctx[:, 2304:]
+        elif gasa:                                           # self-attention inside each stream
+            ka, va, kb, vb = x[:B * La, 768:1536], x[:B * La, 1536:], x[ra:, 768:1536], x[ra:, 1536:]
+        else:                                                # HAMT: each stream attends to the other one
+            ka, va, kb, vb = x[ra:, 768:1536], x[ra:, 1536:], x[:B * La, 768:1536], x[:B * La, 1536:]
+        pa = dict(q=x[:B * La, :768], k=ka, v=va, out=out[:B * La], B=B, Lq=La, Lk=Lka, key_mask=ma, pair_dist=dist, bias_affine=aff)
+        pb = dict(q=x[ra:, :768], k=kb, v=vb, out=out[ra:], B=B, Lq=Lb, Lk=Lkb, key_mask=mb)
+        ops.attention_multi([pa, pb], kernel='tc')
+        refa, _ = _attn_ref(pa['q'], ka, va, B, La, Lka, ma, dist, aff, False)
+        refb, _ = _attn_ref(pb['q'], kb, vb, B, Lb, Lkb, mb, None, None, False)
+        tol = 1.5e-2 if fmt == torch.bfloat16 else 2.5e-3
+        assert relerr(out[:B * La], refa) < tol and relerr(out[ra:], refb) < tol
+        assert bool((out[B * La:ra].float() == 7.0).all())
+
+
+@pytest.mark.parametrize('B,Lq,Lk,masked,gasa,neg_inf', [(8, 30, 30, True, True, False), (8, 37, 85, True, False, False),
+                                                          (4, 36, 36, True, False, True), (2, 130, 300, True, False, False)])
+def test_attention_fp16_operands(ops, B, Lq, Lk, masked, gasa, neg_inf):
+    """the default (mma.sync) attention kernel with fp16 operands / output, as the 16-bit inference mode runs it"""
+    qkv_q = _rand(B * Lq, 2304, seed=1).half()
+    qkv_k = _rand(B * Lk, 2304, seed=2).half()
+    q, k, v = qkv_q[:, :768], qkv_k[:, 768:1536], qkv_k[:, 1536:]
+    g = torch.Generator().manual_seed(3)
+    lens = torch.randint(1, Lk + 1, (B,), generator=g)
+    lens[0] = Lk
+    key_mask = (torch.arange(Lk)[None] < lens[:, None]).to(torch.uint8).cuda()
+    pair_dist = affine = None
+    if gasa:
+        pair_dist = (_rand(B, Lq, Lk, seed=4).abs() * 10).contiguous()
+        affine = torch.tensor([-0.5, 0.1], device='cuda')
+    o = ops.attention(q, k, v, B, Lq, Lk, key_mask=key_mask, pair_dist=pair_dist, bias_affine=affine,
+                      mask_mode=ops.MASK_NEG_INF if neg_inf else ops.MASK_ADD_NEG10000)
+    ref, _ = _attn_ref(q, k, v, B, Lq, Lk, key_mask, pair_dist, affine, neg_inf)
+    assert o.dtype == torch.float16 and relerr(o, ref) < 2.5e-3

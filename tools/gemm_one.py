@@ -1,4 +1,4 @@
-"""Launch one GEMM shape a few times (for ncu).  Usage: python tools/gemm_one.py M N K tile epi res f32"""
+"""Launch one GEMM shape a few times (for ncu).  Usage: python tools/gemm_one.py M N K tile epi res f32 [fold]"""
 import os
 import sys
 
@@ -21,7 +21,14 @@ w = (torch.randn(N, K, device='cuda') * 0.05).bfloat16()
 b = torch.randn(N, device='cuda')
 r = torch.randn(M, N, device='cuda') if res else None
 out = torch.empty(M, N, dtype=torch.float32 if f32 else torch.bfloat16, device='cuda')
+fold = int(sys.argv[8]) if len(sys.argv) > 8 else 0
+ln = None
+if fold:
+    from vln_imagine_b200 import _lib
+    stats = torch.zeros(K // 32, M, 2, device='cuda')
+    stats[:, :, 1] = 32.0
+    ln = (_lib.LN_FOLD, w.float().sum(1), stats, 1e-12)
 for _ in range(5):
-    ops.gemm(x, w, b, residual=r, epilogue=epi, out=out)
+    ops.gemm(x, w, b, residual=r, epilogue=epi, out=out, ln=ln)
 torch.cuda.synchronize()
 print('ok')

@@ -9,6 +9,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 os.environ['VLN_IMAGINE_RETUNE'] = '1'
+os.environ['VLN_IMAGINE_AUTOTUNE'] = '1'
 import bench  # noqa: E402
 from vln_imagine_b200 import ops  # noqa: E402
 
@@ -22,7 +23,8 @@ with torch.no_grad():
         (bench.duet_step if kind == 'duet' else bench.hamt_step)(model, d, txt, img2)
         torch.cuda.synchronize()
         del model
-table = {ops._key_str(k): v for k, v in ops._TILE_CACHE.items()}
+table = dict(ops._TILE_TABLE)            # keep the signatures measured earlier, add / refresh the ones of this run
+table.update({ops._key_str(k): v for k, v in ops._TILE_CACHE.items() if v})
 path = os.path.join(ROOT, 'vln-imagine_b200', 'tile_table.json')
 with open(path, 'w') as f:
     json.dump(table, f, indent=0, sort_keys=True)

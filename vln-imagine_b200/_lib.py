@@ -64,6 +64,7 @@ PROTOTYPES = {
     'vi_gemm_f32': [_p, _l, _p, _p, _p, _l, _p, _l, _i, _i, _i, _i, _i, _ip, _p],
     'vi_attn_fwd': [_p, _l, _p, _l, _p, _l, _p, _l, _i, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
     'vi_attn_fwd_multi': [C.POINTER(AttnProblem), _i, _i, _i, _i, _p],
+    'vi_attn_fwd_tc': [C.POINTER(AttnProblem), _i, _i, _i, _i, _p],
     'vi_add_ln': [_p, _p, _p, _p, _f, _p, _p, _i, _l, _i, _ip, _p],
     'vi_embed_compose': [C.POINTER(EmbedArgs), _p],
     'vi_ln_dot': [_p, _p, _p, _f, _p, _p, _p, _l, _i, _ip, _p],
@@ -75,6 +76,8 @@ PROTOTYPES = {
     'vi_cosine_loss': [_p, _p, _p, _p, _i, _p],
     'vi_infonce_loss': [_p, _p, _p, _p, _p, _f, _p, _p, _i, _i, _p],
     'vi_margin_loss': [_p, _p, _p, _p, _p, _f, _p, _p, _i, _i, _p],
+    'vi_ce_rows': [_p, _l, _p, _i, _p, _l, _p],
+    'vi_kl_rows': [_p, _l, _p, _l, _i, _p, _l, _p],
     'vi_copy_rows': [_p, _l, _l, _p, _p, _i, _l, _l, _l, _i, _p],
     'vi_cast_bf16': [_p, _p, _l, _p],
     'vi_cast_h16': [_p, _p, _i, _l, _p],

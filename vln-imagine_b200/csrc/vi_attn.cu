@@ -375,6 +375,9 @@ static int check_problem(const vi_attn_problem& a, int H, int dtype, AttnProblem
   return VI_OK;
 }
 
+int vi_attn_tc_eligible(const vi_attn_problem* pr, int n, int H, int dtype);                                     // vi_attn_tc.cu
+int vi_attn_tc_launch(const vi_attn_problem* problems, int n_problems, int H, int dtype, int mask_mode, cudaStream_t st);
+
 extern "C" int vi_attn_fwd_multi(const vi_attn_problem* problems, int n_problems, int H, int dtype, int mask_mode,
                                  vi_stream_t stream) {
   VI_CHECK_ARG(problems && n_problems >= 1 && n_problems <= VI_ATTN_MAX_PROBLEMS, "vi_attn_fwd_multi: 1..%d problems",
@@ -393,6 +396,8 @@ extern "C" int vi_attn_fwd_multi(const vi_attn_problem* problems, int n_problems
     max_lq = p.pr[i].Lq > max_lq ? p.pr[i].Lq : max_lq;
     max_lkp = p.pr[i].LkP > max_lkp ? p.pr[i].LkP : max_lkp;
   }
+  // inference shapes go to the tcgen05 kernel (vi_attn_tc.cu); dropout / lse / > 256 keys stay on the mma.sync kernel below
+  if (vi_attn_tc_eligible(problems, n_problems, H, dtype)) return vi_attn_tc_launch(problems, n_problems, H, dtype, mask_mode, st);
   if (dtype != VI_DT_F32) {
     const int q_tiles = (max_lq + 15) / 16;
     const int nwarp = q_tiles < 4 ? q_tiles : 4;

@@ -42,6 +42,8 @@ void vi_set_error(const char* fmt, ...);
   } while (0)
 
 int vi_num_sms();
+// 2-D row-major TMA tensor map over bf16 / fp16 elements, 128-byte swizzle, boxes of 64 columns x box_rows rows (vi_api.cu)
+int vi_make_tmap_h16(CUtensorMap* map, const void* ptr, int f16, uint64_t cols, uint64_t rows, uint64_t ld_elems, uint32_t box_rows);
 bool vi_pdl_enabled();      // programmatic dependent launch on every kernel of the library (VI_PDL=0 disables)
 
 // Launch with the programmatic-stream-serialization attribute: the kernel may start (and run its prologue) while

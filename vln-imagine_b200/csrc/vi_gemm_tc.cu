@@ -37,9 +37,12 @@ constexpr int MAX_CPW = 4;                             // 32-column chunks per e
 constexpr int VEC_BYTES = EPI_WARPS * 2 * 32 * 4;
 // what the epilogue writes: a 16-bit tile (bf16 / fp16), an fp32 tile, or both (fp32 residual stream + 16-bit operand copy)
 enum { OUT_H16 = 0, OUT_F32 = 1, OUT_DUAL = 2 };
-// staging per epilogue warp: two buffers of 32 rows x 32 columns (fp32: 128-byte rows; 16-bit: 64-byte rows; dual: both, fp32 first)
-__host__ __device__ constexpr int epi_buf_bytes(int om) { return om == OUT_H16 ? 2048 : (om == OUT_F32 ? 4096 : 6144); }
-__host__ __device__ constexpr int epi_bytes(int om) { return EPI_WARPS * 2 * epi_buf_bytes(om); }
+// staging per epilogue warp: two buffers of 32 rows x 32 columns (fp32: 128-byte rows; 16-bit: 64-byte rows).  OUT_DUAL: the two
+// fp32 buffers plus ONE 16-bit buffer behind them - a dual output always has a residual, whose prefetch already waits for every
+// outstanding store of the warp at the top of each chunk, so the 16-bit copy needs no second buffer
+__host__ __device__ constexpr int epi_buf_bytes(int om) { return om == OUT_H16 ? 2048 : 4096; }
+__host__ __device__ constexpr int epi_warp_bytes(int om) { return 2 * epi_buf_bytes(om) + (om == OUT_DUAL ? 2048 : 0); }
+__host__ __device__ constexpr int epi_bytes(int om) { return EPI_WARPS * epi_warp_bytes(om); }
 constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;            // clears the CTA-rank bit of a shared::cluster address (pair leader)
 
 enum { LN_NONE = 0, LN_FOLD = 1, LN_RESIDUAL = 2 };
@@ -205,7 +208,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   constexpr int EPI_BUF = epi_buf_bytes(OUTMODE);
   constexpr bool HAS_F32 = OUTMODE != OUT_H16;       // fp32 tile staged at offset 0 of a buffer
   constexpr bool HAS_H16 = OUTMODE != OUT_F32;       // 16-bit tile staged at offset 0 (OUT_H16) or 4096 (OUT_DUAL)
-  constexpr uint32_t H16_OFF = OUTMODE == OUT_DUAL ? 4096u : 0u;
+  constexpr int EPI_WARP = epi_warp_bytes(OUTMODE);
   constexpr int TILES_PER_M = PAIR ? 2 : 1;          // 128-row tiles per m index
   static_assert(BN % 32 == 0 && BN >= 64 && BN <= 256, "tile N");
   static_assert(A_BYTES % 1024 == 0 && B_BYTES % 1024 == 0, "operand tiles must keep the 1024-byte swizzle alignment");
@@ -270,9 +273,10 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int total_tiles = p.num_m_tiles * p.num_n_tiles;
   const int num_kb = p.K / BK;
 
-  auto group_of = [&](int mt128) {
+  auto group_of = [&](int mt128) {                     // group ends ascend: count the ends at or below the tile (static indices)
     int g = 0;
-    while (g < p.n_groups - 1 && mt128 >= p.group_tile_end[g]) ++g;
+#pragma unroll
+    for (int i = 0; i < MAX_GROUPS - 1; ++i) g += (i < p.n_groups - 1 && mt128 >= p.group_tile_end[i]) ? 1 : 0;
     return g;
   };
 
@@ -339,7 +343,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int half = ew >> 2;                         // which interleaved half of the column chunks
     constexpr int CPW0 = (NCHUNK + 1) / 2, CPW1 = NCHUNK / 2;
     const int cpw = half ? CPW1 : CPW0;               // chunks per tile for this warp: half, half+2, ...
-    const uint32_t my_buf = epi_base + (uint32_t)(ew * 2 * EPI_BUF);
+    const uint32_t my_buf = epi_base + (uint32_t)(ew * EPI_WARP);
+    const uint32_t my_h16 = my_buf + (uint32_t)(2 * EPI_BUF);      // OUT_DUAL: the single 16-bit staging buffer
     float* my_vec = vec_smem + ew * 64;               // [2][32]: per-column vectors of the current chunk
     const uint32_t my_vec_u = smem_u32(my_vec);
     const bool res = p.has_residual != 0;
@@ -395,10 +400,12 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         float sm = 0.f, sq = 0.f, m2 = 0.f;
         if (row_ok) {
           const float2* sp = p.stats_in + grow;
-#pragma unroll 8
-          for (int c = 0; c < p.stats_chunks; ++c) {
-            const float2 pr = *(sp + (long long)c * p.stats_ld);
-            sm += pr.x; sq = fmaf(pr.x, pr.x, sq); m2 += pr.y;
+          for (int c0 = 0; c0 < p.stats_chunks; c0 += 24) {       // 24 chunks = one 768-wide LayerNorm: ONE round trip to L2
+            float2 pr[24];
+#pragma unroll
+            for (int c = 0; c < 24; ++c) pr[c] = (c0 + c < p.stats_chunks) ? *(sp + (long long)(c0 + c) * p.stats_ld) : make_float2(0.f, 0.f);
+#pragma unroll
+            for (int c = 0; c < 24; ++c) { sm += pr[c].x; sq = fmaf(pr[c].x, pr[c].x, sq); m2 += pr[c].y; }
           }
         }
         const float inv_c = 1.0f / (float)p.stats_chunks;
@@ -454,10 +461,12 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               float4 c4, s4;
               asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(c4.x), "=f"(c4.y), "=f"(c4.z), "=f"(c4.w) : "r"(vec_u + (uint32_t)(j * 16)));
               asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(s4.x), "=f"(s4.y), "=f"(s4.z), "=f"(s4.w) : "r"(vec_u + (uint32_t)(128 + j * 16)));
-              v[4 * j] = fmaf(rstd, v[4 * j], fmaf(-rm, s4.x, c4.x));
-              v[4 * j + 1] = fmaf(rstd, v[4 * j + 1], fmaf(-rm, s4.y, c4.y));
-              v[4 * j + 2] = fmaf(rstd, v[4 * j + 2], fmaf(-rm, s4.z, c4.z));
-              v[4 * j + 3] = fmaf(rstd, v[4 * j + 3], fmaf(-rm, s4.w, c4.w));
+              const float2 nrm = bcast2(-rm), rs = bcast2(rstd);
+              const float2 t0 = ffma2(nrm, make_float2(s4.x, s4.y), make_float2(c4.x, c4.y));
+              const float2 t1 = ffma2(nrm, make_float2(s4.z, s4.w), make_float2(c4.z, c4.w));
+              const float2 y0 = ffma2(rs, make_float2(v[4 * j], v[4 * j + 1]), t0);
+              const float2 y1 = ffma2(rs, make_float2(v[4 * j + 2], v[4 * j + 3]), t1);
+              v[4 * j] = y0.x; v[4 * j + 1] = y0.y; v[4 * j + 2] = y1.x; v[4 * j + 3] = y1.y;
             }
           } else if (has_v0 && ln_mode != LN_RESIDUAL) {
 #pragma unroll
@@ -491,10 +500,11 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 float4 g4, b4;
                 asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(g4.x), "=f"(g4.y), "=f"(g4.z), "=f"(g4.w) : "r"(vec_u + (uint32_t)(128 + j * 16)));
                 asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b4.x), "=f"(b4.y), "=f"(b4.z), "=f"(b4.w) : "r"(vec_u + (uint32_t)(j * 16)));
-                q.x = fmaf(fmaf(q.x, rstd, -rm), g4.x, b4.x);
-                q.y = fmaf(fmaf(q.y, rstd, -rm), g4.y, b4.y);
-                q.z = fmaf(fmaf(q.z, rstd, -rm), g4.z, b4.z);
-                q.w = fmaf(fmaf(q.w, rstd, -rm), g4.w, b4.w);
+                const float2 nrm = bcast2(-rm), rs = bcast2(rstd);
+                const float2 n0 = ffma2(make_float2(q.x, q.y), rs, nrm), n1 = ffma2(make_float2(q.z, q.w), rs, nrm);
+                const float2 r0 = ffma2(n0, make_float2(g4.x, g4.y), make_float2(b4.x, b4.y));
+                const float2 r1 = ffma2(n1, make_float2(g4.z, g4.w), make_float2(b4.z, b4.w));
+                q.x = r0.x; q.y = r0.y; q.z = r1.x; q.w = r1.y;
               }
               v[4 * j] += q.x; v[4 * j + 1] += q.y; v[4 * j + 2] += q.z; v[4 * j + 3] += q.w;
             }
@@ -520,7 +530,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
           if constexpr (HAS_H16) {
             // 16-bit rows are 64 B, 64B-swizzled: chunk j of row r sits at j ^ ((r >> 1) & 3)
-            const uint32_t rowb = buf + H16_OFF + (uint32_t)(lane * 64);
+            const uint32_t rowb = (OUTMODE == OUT_DUAL ? my_h16 : buf) + (uint32_t)(lane * 64);
             uint32_t h[16];
             if (p.fmt_f16) {
 #pragma unroll
@@ -541,7 +551,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           __syncwarp();
           if (lane == 0) {
             tma_store_2d(&tmY, buf, col0, row0);      // rows beyond M are clipped by the tensor map
-            if constexpr (OUTMODE == OUT_DUAL) tma_store_2d(&tmY2, buf + H16_OFF, col0, row0);
+            if constexpr (OUTMODE == OUT_DUAL) tma_store_2d(&tmY2, my_h16, col0, row0);
             bulk_commit();
           }
           ++n;
@@ -806,24 +816,24 @@ extern "C" int vi_gemm16(const vi_gemm_args* args, vi_stream_t stream) {
 
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int om = a.y16 ? OUT_DUAL : (p.y_f32 ? OUT_F32 : OUT_H16);
-  // ring depth = what fits beside the epilogue staging (16-bit out: 32 KB, fp32 out: 64 KB, both: 96 KB) in 227 KB
+  // ring depth = what fits beside the epilogue staging (16-bit out: 32 KB, fp32 out: 64 KB, both: 80 KB) in 227 KB
 #define VI_LAUNCH(BN_, SH_, SF_, SD_, PAIR_)                                                     \
   (om == OUT_DUAL ? launch<BN_, SD_, PAIR_, OUT_DUAL>(m, p, grid, st)                            \
    : om == OUT_F32 ? launch<BN_, SF_, PAIR_, OUT_F32>(m, p, grid, st)                            \
                    : launch<BN_, SH_, PAIR_, OUT_H16>(m, p, grid, st))
   if (c.pair) {
     switch (c.bn) {
-      case 256: return VI_LAUNCH(256, 6, 5, 3, true);
-      case 192: return VI_LAUNCH(192, 6, 5, 4, true);
+      case 256: return VI_LAUNCH(256, 6, 5, 4, true);
+      case 192: return VI_LAUNCH(192, 6, 5, 5, true);
       default:  return VI_LAUNCH(128, 8, 6, 5, true);
     }
   }
   switch (c.bn) {
     case 256: return VI_LAUNCH(256, 4, 3, 2, false);
     case 192: return VI_LAUNCH(192, 4, 4, 3, false);
-    case 128: return VI_LAUNCH(128, 6, 5, 3, false);
-    case 96:  return VI_LAUNCH(96, 6, 5, 4, false);
-    default:  return VI_LAUNCH(64, 8, 6, 5, false);
+    case 128: return VI_LAUNCH(128, 6, 5, 4, false);
+    case 96:  return VI_LAUNCH(96, 6, 5, 5, false);
+    default:  return VI_LAUNCH(64, 8, 6, 6, false);
   }
 #undef VI_LAUNCH
 }

@@ -440,6 +440,45 @@ __global__ void __launch_bounds__(128) copy_rows_kernel(const float* src, long l
   }
 }
 
+// ---- loss rows of the pre-training proxy tasks (VLN-DUET/pretrain_src/model/pretrain_cmt.py:150,198-204) -----------------
+// out[r] = logsumexp(logits[r, 0:n]) - logits[r, label[r]]          (F.cross_entropy, reduction='none'); one warp per row
+__global__ void __launch_bounds__(128) ce_rows_kernel(const float* logits, long long ld, const int64_t* labels, int n,
+                                                      float* out, long long rows) {
+  pdl_enter();
+  ROW_INDEX();
+  if (row >= rows) return;
+  const float* x = logits + row * ld;
+  float mx = -INFINITY;
+  for (int c = lane; c < n; c += 32) mx = fmaxf(mx, x[c]);
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int c = lane; c < n; c += 32) sum += expf(x[c] - mx);
+  sum = warp_sum(sum);
+  if (lane == 0) out[row] = mx + logf(sum) - x[labels[row]];
+}
+// out[r] = sum_c t[r, c] * (log t[r, c] - log_softmax(logits[r])[c]), terms with t == 0 dropped   (F.kl_div(..., 'none').sum(1))
+__global__ void __launch_bounds__(128) kl_rows_kernel(const float* logits, long long ld, const float* targets, long long ldt, int n,
+                                                      float* out, long long rows) {
+  pdl_enter();
+  ROW_INDEX();
+  if (row >= rows) return;
+  const float* x = logits + row * ld;
+  const float* t = targets + row * ldt;
+  float mx = -INFINITY;
+  for (int c = lane; c < n; c += 32) mx = fmaxf(mx, x[c]);
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int c = lane; c < n; c += 32) sum += expf(x[c] - mx);
+  const float lse = mx + logf(warp_sum(sum));
+  float acc = 0.f;
+  for (int c = lane; c < n; c += 32) {
+    const float tc = t[c];
+    if (tc > 0.f) acc += tc * (logf(tc) - (x[c] - lse));
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) out[row] = acc;
+}
+
 inline unsigned row_grid(long long rows) { return (unsigned)((rows + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK); }
 inline bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 inline bool make_groups(RowGroups& g, int n_groups, const int32_t* ends, long long rows) {
@@ -645,6 +684,25 @@ extern "C" int vi_cast_h16(const float* src, void* dst, int dst_dtype, int64_t n
   const long long n4 = n / 4;
   const long long threads = n4 > 0 ? n4 : 1;
   VI_CUDA(vi_launch(cast_bf16_kernel, dim3((unsigned)((threads + 255) / 256)), dim3(256), (size_t)(0), ST(stream), src, reinterpret_cast<bf16*>(dst), (int)(dst_dtype == VI_DT_F16), n4, n));
+  VI_LAUNCH_CHECK();
+  return VI_OK;
+}
+
+extern "C" int vi_ce_rows(const float* logits, int64_t ld, const int64_t* labels, int n_cols, float* out, int64_t rows,
+                          vi_stream_t stream) {
+  VI_CHECK_ARG(logits && labels && out && n_cols > 0 && ld >= n_cols, "vi_ce_rows: bad operands");
+  if (rows <= 0) return VI_OK;
+  VI_CUDA(vi_launch(ce_rows_kernel, dim3(row_grid(rows)), dim3(128), (size_t)(0), ST(stream), logits, (long long)ld, labels, n_cols, out, (long long)rows));
+  VI_LAUNCH_CHECK();
+  return VI_OK;
+}
+
+extern "C" int vi_kl_rows(const float* logits, int64_t ld, const float* targets, int64_t ldt, int n_cols, float* out, int64_t rows,
+                          vi_stream_t stream) {
+  VI_CHECK_ARG(logits && targets && out && n_cols > 0 && ld >= n_cols && ldt >= n_cols, "vi_kl_rows: bad operands");
+  if (rows <= 0) return VI_OK;
+  VI_CUDA(vi_launch(kl_rows_kernel, dim3(row_grid(rows)), dim3(128), (size_t)(0), ST(stream), logits, (long long)ld, targets, (long long)ldt, n_cols, out,
+                    (long long)rows));
   VI_LAUNCH_CHECK();
   return VI_OK;
 }

@@ -33,18 +33,31 @@ def _ptr(t: Optional[torch.Tensor]):
 
 
 class _Staging:
-    """A small ring of pinned host buffers: one packed host->device copy per call, no reuse while a copy may be in flight."""
+    """A small ring of pinned host buffers: one packed host->device copy per call.  Every slot carries the CUDA event of its
+    last copy; a slot is rewritten only after that copy has completed (the wait is free unless the caller runs more than
+    ``slots`` calls ahead of the device)."""
 
     def __init__(self, slots: int = 4):
         self.bufs = [None] * slots
+        self.events = [None] * slots
         self.i = 0
 
     def get(self, nbytes: int) -> torch.Tensor:
         self.i = (self.i + 1) % len(self.bufs)
+        ev = self.events[self.i]
+        if ev is not None:
+            ev.synchronize()                     # the H2D copy that last read this slot has finished
         b = self.bufs[self.i]
         if b is None or b.numel() < nbytes:
             b = self.bufs[self.i] = torch.empty(max(nbytes, 1 << 16), dtype=torch.uint8).pin_memory()
         return b
+
+    def copied(self):
+        """record the copy just queued from the current slot on the current stream"""
+        ev = self.events[self.i]
+        if ev is None:
+            ev = self.events[self.i] = torch.cuda.Event()
+        ev.record()
 
 
 _TORCH_DTYPE = {np.dtype(k).char: v for k, v in (('float64', torch.float64), ('float32', torch.float32), ('int64', torch.int64),
@@ -62,6 +75,8 @@ def _pack(staging: _Staging, device, arrays: Dict[str, np.ndarray]) -> Dict[str,
     for k, a in arrays.items():
         hv[offs[k]:offs[k] + a.nbytes] = np.ascontiguousarray(a).view(np.uint8).reshape(-1)
     dev = host[:total].to(device, non_blocking=True)
+    if dev.is_cuda:
+        staging.copied()
     out = {}
     for k, a in arrays.items():
         out[k] = dev[offs[k]:offs[k] + a.nbytes].view(_TORCH_DTYPE[a.dtype.char]).view(a.shape)

@@ -115,10 +115,10 @@ class GraphedCall:
             if v.is_cuda:
                 static_in[k].copy_(v, non_blocking=True)
         ent['graph'].replay()
-        if host_items:
-            if ent.get('done') is None:
-                ent['done'] = torch.cuda.Event()
-            ent['done'].record(main)
+        # recorded on EVERY replay (also device-only calls): the next host upload into the static buffers waits for it
+        if ent.get('done') is None:
+            ent['done'] = torch.cuda.Event()
+        ent['done'].record(main)
         return {k: (v.clone() if torch.is_tensor(v) and not (no_clone_prefix and k.startswith(no_clone_prefix)) else v)
                 for k, v in ent['static_out'].items()}
 

@@ -292,9 +292,9 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, B: int, Lq: int
     return out
 
 
-def attention_multi(problems, mask_mode: int = MASK_ADD_NEG10000):
+def attention_multi(problems, mask_mode: int = MASK_ADD_NEG10000, kernel: str = 'auto'):
     """Several attention problems in one launch.  Each problem is a dict with q, k, v (2-D row views), out,
-    B, Lq, Lk and optional key_mask (uint8 [B, Lk]), pair_dist, bias_affine, lse."""
+    B, Lq, Lk and optional key_mask (uint8 [B, Lk]), pair_dist, bias_affine, lse.  kernel='tc': the tcgen05 kernel by name."""
     n = len(problems)
     arr = (_lib.AttnProblem * n)()
     dtype = None
@@ -316,8 +316,10 @@ def attention_multi(problems, mask_mode: int = MASK_ADD_NEG10000):
             dtype = q.dtype
         elif dtype != q.dtype:
             raise _lib.VlnImagineError('attention problems of one launch must share a dtype')
-    check(lib.vi_attn_fwd_multi(arr, n, HEADS, _DT[dtype], mask_mode, _stream()),
-          'vi_attn_fwd_multi')
+    if kernel == 'tc':
+        check(lib.vi_attn_fwd_tc(arr, n, HEADS, _DT[dtype], mask_mode, _stream()), 'vi_attn_fwd_tc')
+    else:
+        check(lib.vi_attn_fwd_multi(arr, n, HEADS, _DT[dtype], mask_mode, _stream()), 'vi_attn_fwd_multi')
     _launched(1 if is16(dtype) else n)
 
 
@@ -490,3 +492,22 @@ def cast_h16(src: torch.Tensor, dst: Optional[torch.Tensor] = None, dtype=None):
     check(lib.vi_cast_h16(src.data_ptr(), dst.data_ptr(), _DT[dst.dtype], src.numel(), _stream()), 'vi_cast_h16')
     _launched(1)
     return dst
+
+
+def ce_rows(logits: torch.Tensor, labels: torch.Tensor, n_cols: int) -> torch.Tensor:
+    """per-row cross-entropy over the first n_cols columns of fp32 logits [R, ld] (F.cross_entropy, reduction='none')"""
+    R, _, ld = _rows2d(logits, 'logits')
+    out = torch.empty((R,), dtype=F32, device=logits.device)
+    check(lib.vi_ce_rows(logits.data_ptr(), ld, labels.long().contiguous().data_ptr(), n_cols, out.data_ptr(), R, _stream()), 'vi_ce_rows')
+    _launched(1)
+    return out
+
+
+def kl_rows(logits: torch.Tensor, targets: torch.Tensor, n_cols: int) -> torch.Tensor:
+    """per-row KL(targets || softmax(logits)) over the first n_cols columns (F.kl_div(log_softmax, targets, 'none').sum(1))"""
+    R, _, ld = _rows2d(logits, 'logits')
+    _, _, ldt = _rows2d(targets, 'targets')
+    out = torch.empty((R,), dtype=F32, device=logits.device)
+    check(lib.vi_kl_rows(logits.data_ptr(), ld, targets.data_ptr(), ldt, n_cols, out.data_ptr(), R, _stream()), 'vi_kl_rows')
+    _launched(1)
+    return out

@@ -173,9 +173,11 @@ def _pos_embed(d_in):
 class XEncoderP(_Container):
     """CrossmodalEncoder :436-453"""
 
-    def __init__(self, n):
+    def __init__(self, n, lang2visn=False):
         super().__init__()
-        self.x_layers = nn.ModuleList([GraphXLayerP() for _ in range(n)])
+        # use_lang2visn_attn (pre-training, VLN-DUET/pretrain_src/model/vilmodel.py:366-411): the layers also carry the
+        # lang_self_att / lang_inter / lang_output blocks - the same parameter set as HAMT's LXRTXLayer
+        self.x_layers = nn.ModuleList([(LXRTXLayerP() if lang2visn else GraphXLayerP()) for _ in range(n)])
 
 
 class LocalVPEncoderP(_Container):
@@ -184,7 +186,7 @@ class LocalVPEncoderP(_Container):
     def __init__(self, cfg):
         super().__init__()
         self.vp_pos_embeddings = _pos_embed(cfg.angle_feat_size * 2 + 6)
-        self.encoder = XEncoderP(cfg.num_x_layers)
+        self.encoder = XEncoderP(cfg.num_x_layers, bool(getattr(cfg, 'use_lang2visn_attn', False)))
 
 
 class GlobalMapEncoderP(_Container):
@@ -194,7 +196,7 @@ class GlobalMapEncoderP(_Container):
         super().__init__()
         self.gmap_pos_embeddings = _pos_embed(cfg.angle_feat_size + 3)
         self.gmap_step_embeddings = nn.Embedding(cfg.max_action_steps, H)
-        self.encoder = XEncoderP(cfg.num_x_layers)
+        self.encoder = XEncoderP(cfg.num_x_layers, bool(getattr(cfg, 'use_lang2visn_attn', False)))
         if cfg.graph_sprels:
             self.sprel_linear = nn.Linear(1, 1)
         else:

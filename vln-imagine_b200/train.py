@@ -178,7 +178,25 @@ class GraphedIteration:
         if self.between is not None:
             self.between()
         self.g_update.replay()
+        # the optimiser ran inside a graph: no Python hook fired and fused optimisers do not bump tensor versions, so tell
+        # every consumer of derived weights (blocks.Pack keys, graphs.weights_token) that the parameters have moved
+        from . import blocks
+        blocks.touch_weights()
         return self.loss
 
     def finish(self):
+        """Call before using the model outside the replayed iteration (validation between training phases): drops the
+        derived weight copies, the inference CUDA graphs that hold raw pointers to them and the cached context projections,
+        so the next eager / graphed inference call rebuilds all of them from the CURRENT parameters."""
+        from . import blocks
+        blocks.touch_weights()
         self._invalidate_packs()
+        for m in self.model.modules():
+            for name in ('_g_pano', '_g_nav', '_g_vis', '_g_hist'):
+                g = getattr(m, name, None)
+                if g is not None:
+                    g.clear()
+            if hasattr(m, '_wt_cache'):
+                m._wt_cache = {}
+            if hasattr(m, 'drop_context'):
+                m.drop_context()
