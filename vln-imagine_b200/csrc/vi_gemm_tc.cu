@@ -432,7 +432,11 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               if (!last || tn < total_tiles) {
                 bulk_wait_read<0>();                  // the store that last used the other buffer has read it
                 issue_residual(n + 1, last ? row0n : row0, last ? tcol0n : col0 + 64);
+              } else if (OUTMODE == OUT_DUAL) {
+                bulk_wait_read<0>();                  // the single 16-bit staging buffer: the previous chunk's copy has been read
               }
+            } else if (OUTMODE == OUT_DUAL) {
+              bulk_wait_read<0>();                    // single 16-bit staging buffer: wait for the previous chunk's stores
             } else {
               bulk_wait_read<1>();                    // the store issued two chunks ago has read this buffer
             }
