@@ -23,7 +23,7 @@ def test_reference_arm_prints_one_contract_line():
     assert d['value'] > 0 and d['higher_is_better'] is True and d['vs_baseline'] is None
     assert d['e2e'] == {'value': d['value'], 'unit': d['unit'], 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
     cb = d['cpu_baseline']
-    assert cb['kind'] == 'port' and cb['cores'] >= 1 and cb['value'] == d['value'] and 'sample' in cb
+    assert cb['kind'] in ('reference', 'port') and cb['cores'] >= 1 and cb['value'] == d['value'] and 'sample' in cb
     assert 'workload' in d['config'] and 'model' not in d['config']
 
 
