@@ -468,7 +468,7 @@ def train_measure(args, shape, rank, local_rank, world, K, W, detail=True):
 
     def grad_fn(ep):
         flat.zero()
-        loss, ce, aux, _ = train.duet_finetune_iteration(model, ep, n_steps=T)
+        loss, ce, aux, _ = train.duet_finetune_iteration(model, ep, n_steps=T, fused_accumulation=os.environ.get('VI_TRAIN_FUSED_ACC', '1') != '0')
         return loss.detach()
 
     def update_fn():

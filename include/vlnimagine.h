@@ -203,7 +203,8 @@ int vi_embed_compose(const vi_embed_args* args, vi_stream_t stream);
 
 /* out[row] = LayerNorm(h[row]) . w + b   (tail of ClsPrediction / NextActionPrediction:
  * D/models/vilmodel.py:1009-1020, H/models/vilmodel_cmt.py:953-963).  Grouped like vi_add_ln:
- * gamma/beta/w are [n_groups, 768] stacks and b is [n_groups]. */
+ * gamma/beta/w are [n_groups, 768] stacks and b is [n_groups].  gamma == beta == NULL: no LayerNorm, out[row] = h[row] . w + b
+ * (the training forward keeps the normalised rows and applies the dot product on its own). */
 int vi_ln_dot(const float* h, const float* gamma, const float* beta, float eps,
               const float* w, const float* b, float* out, int64_t rows,
               int n_groups, const int32_t* group_row_end, vi_stream_t stream);
@@ -281,6 +282,20 @@ int vi_copy_rows(const float* src, int64_t src_batch_stride, int64_t src_row_str
 /* dst[c, r] = src[r, c]; dst is [cols, ldd] with columns rows..pad_rows-1 zero-filled (pad_rows <= ldd) */
 int vi_transpose(const void* src, int64_t ld, void* dst, int64_t ldd, int rows, int cols, int pad_rows, int dtype,
                  vi_stream_t stream);
+/* Weight and bias gradients of a (grouped) dense layer WITHOUT transposes (vi_wgrad.cu):
+ *   dw[g] = dY[g]^T X[g]  ([N, K] fp32, groups stacked: dw is [n_groups * N, K]),   db[g] = column sums of dY[g]  (or NULL)
+ * dY [rows, N] and X [rows, K] are row-major 16-bit tensors (dtype VI_DT_BF16 / VI_DT_F16), N % 128 == 0, K % 64 == 0; group g
+ * covers rows group_row_end[g-1] .. group_row_end[g].  Both operands reach tcgen05.mma as MN-major tiles exactly as they lie in
+ * memory; the contraction (over rows) is split over `splits` work units per output tile (0: the library's choice,
+ * vi_wgrad16_splits), whose fp32 partials go through `workspace` (vi_wgrad16_workspace floats) and are summed in a fixed order.
+ * accumulate != 0: dw / db are added to (gradient accumulation over the steps of an iteration; one writer per element, so the
+ * result does not depend on scheduling).
+ * What loss.backward() computes for nn.Linear: grad_weight = grad_output^T input, grad_bias = grad_output.sum(0). */
+int vi_wgrad16_splits(int N, int K, int n_groups, const int32_t* group_rows);
+int64_t vi_wgrad16_workspace(int N, int K, int n_groups, const int32_t* group_rows, int splits);
+int vi_wgrad16(const void* dy, int64_t lddy, const void* x, int64_t ldx, int dtype, int N, int K, int n_groups,
+               const int32_t* group_row_end, float* dw, float* db, float* workspace, int64_t workspace_floats, int splits,
+               int accumulate, vi_stream_t stream);
 /* Column reductions over rows run in two deterministic stages (128-row chunks -> a caller-provided fp32 scratch ->
  * fixed-order sum).  vi_reduce_scratch_elems gives the scratch size for n_out reduced quantities per column. */
 int64_t vi_reduce_scratch_elems(int64_t rows, int cols, int n_out);
@@ -296,6 +311,11 @@ int vi_act_bwd(const void* x, const void* dy, void* dx, int64_t n, int act, int 
 int vi_add_ln_bwd(const float* a, const float* b, const float* gamma, float eps, const float* dy32, const void* dy16,
                   float* dx32, void* dx16, float* dgamma, float* dbeta, float* stats, int64_t rows,
                   int n_groups, const int32_t* group_row_end, float* scratch, int64_t scratch_elems, vi_stream_t stream);
+/* the same with dgamma / dbeta ADDED to (accumulate != 0) instead of overwritten */
+int vi_add_ln_bwd_acc(const float* a, const float* b, const float* gamma, float eps, const float* dy32, const void* dy16,
+                      float* dx32, void* dx16, float* dgamma, float* dbeta, float* stats, int64_t rows,
+                      int n_groups, const int32_t* group_row_end, float* scratch, int64_t scratch_elems, int accumulate,
+                      vi_stream_t stream);
 /* small-feature linear of vi_embed_compose: dW[768, feat_dim] = dt^T feat, db[768] = colsum(dt) */
 int vi_feat_wgrad(const float* dt, const float* feat, int feat_dim, float* dW, float* db, int64_t rows, float* scratch,
                   int64_t scratch_elems, vi_stream_t stream);
@@ -328,6 +348,11 @@ int vi_cosine_loss_bwd(const float* proj, const float* tgt, const float* dloss, 
 int vi_infonce_loss_bwd(const float* proj, const float* tgt, const float* negs, const int32_t* row_episode,
                         const int32_t* neg_episode, float temperature, const float* sims, const float* dloss,
                         float* dproj, int R, int n_negs, vi_stream_t stream);
+/* adjoint of vi_margin_loss w.r.t. proj (H/models/vilmodel_cmt.py:825-856); `sims` = the cosines the forward call left in its
+ * loss_rows scratch */
+int vi_margin_loss_bwd(const float* proj, const float* tgt, const float* negs, const int32_t* row_episode,
+                       const int32_t* neg_episode, float margin, const float* sims, const float* dloss,
+                       float* dproj, int R, int n_negs, vi_stream_t stream);
 
 /* Dropout (training only): y = x * keep / (1 - p) with keep(i) = hash(i, *seed, site) >= p * 2^32; the backward pass is the
  * same call on the gradient.  `seed` is a device pointer (the host module advances it once per optimiser step, also inside

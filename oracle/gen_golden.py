@@ -238,10 +238,14 @@ def run_duet_grads(args):
             samples.append(g[torch.from_numpy(grad_sample_index(name, g.numel()))].float().numpy())
         out['grad_norms'] = np.asarray(norms, np.float64)
         out['grad_samples'] = np.stack(samples)
+        full = {name: dict(ref.named_parameters())[name].grad.detach().clone() for name in (
+            'global_encoder.sprel_linear.weight', 'global_encoder.sprel_linear.bias', 'imagine_embeddings.type_embedding.weight',
+            'embeddings.LayerNorm.weight', 'sap_fuse_linear.net.3.weight', 'local_encoder.vp_pos_embeddings.0.weight')}
+        autocast_noise(ref, lambda: duet_train_step(ref, ep, lambda mode, batch: ref(mode, batch))[0], out)
         for name in ('global_encoder.sprel_linear.weight', 'global_encoder.sprel_linear.bias',
                      'imagine_embeddings.type_embedding.weight', 'embeddings.LayerNorm.weight',
                      'sap_fuse_linear.net.3.weight', 'local_encoder.vp_pos_embeddings.0.weight'):
-            out['full::' + name] = dict(ref.named_parameters())[name].grad.detach()
+            out['full::' + name] = full[name]
         np.savez(os.path.join(GOLD, 'duet_grads_%s.npz' % tag), **_np(out))
         with open(os.path.join(GOLD, 'duet_grads_names.json'), 'w') as f:
             json.dump(names, f, indent=0)
@@ -300,11 +304,171 @@ def run_hamt_grads(args):
             samples.append(g[torch.from_numpy(grad_sample_index(name, g.numel()))].float().numpy())
         out['grad_norms'] = np.asarray(norms, np.float64)
         out['grad_samples'] = np.stack(samples)
+        autocast_noise(ref, lambda: hamt_train_step(lambda mode, **kw: ref(mode, **kw), ep, hm)[0], out)
         np.savez(os.path.join(GOLD, 'hamt_grads_%s.npz' % tag), **_np(out))
         with open(os.path.join(GOLD, 'hamt_grads_names.json'), 'w') as f:
             json.dump(names, f, indent=0)
         print(tag, 'loss', float(loss.detach()), 'ce', float(ce.detach()), 'aux', float(aux.detach()), 'params with grad', len(names),
               'of', len(list(ref.named_parameters())))
+
+
+# HAMT-Imagine fine-tuning variants beyond the released recipe: the flags each one overrides
+HAMT_GRAD_VARIANTS = {
+    # the PARSER defaults (r2r/parser.py:109,122): ImagineEmbeddings encoder trained, imagination tokens on the vision stream
+    'encvis_imgtxt': dict(bypass_imag_encoder=False, concat_imagine_with='visual', act_pred_token='ob_imagine_text'),
+    # margin form of the alignment loss (models/vilmodel_cmt.py:825-856) + the 'ob_txt_hist' action token (:1195-1196)
+    'margin_txthist': dict(aux_loss_type='constrastive-margin', contrastive_margin_value=0.5, act_pred_token='ob_txt_hist'),
+    # history embeddings trained (fix_hist_embedding off, the parser default, r2r/parser.py:57; models/vilmodel_cmt.py:576-618,1036)
+    'hist_obhist': dict(fix_hist_embedding=False, act_pred_token='ob_hist'),
+}
+
+
+def hamt_variant_train_step(call, ep, hist_masks, over):
+    """hamt_train_step for the variants: 'imagine' gets the masks when the encoder runs (r2r/agent_cmt.py:413-417); with trainable
+    history embeddings the history tokens are [cls ; one step] from two 'history' calls (r2r/agent_cmt.py:424,596-603)."""
+    txt = call('language', txt_ids=ep['txt_ids'], txt_masks=ep['txt_masks'])
+    enc = not over.get('bypass_imag_encoder', True)
+    img = call('imagine', imagine_pano_img_feats=ep['imagine_feats'], imagine_masks=ep['imagine_masks'] if enc else None)
+    aux, img2 = call('align_with_contrastive_loss', align_txt_embeds=txt, txt_masks=ep['txt_masks'],
+                     align_imagine_embeds=img, imagine_masks=ep['imagine_masks'], sub_instr_segs=ep['sub_instr_segs'],
+                     sub_instr_imag_flag=ep['sub_instr_imag_flag'], noun_phrase_segs=ep['noun_phrase_segs'],
+                     obs_instr_ids=ep['obs_instr_ids'])
+    hist_embeds = ep['hist_embeds']
+    if not over.get('fix_hist_embedding', True):
+        B = ep['txt_ids'].shape[0]
+        cls = call('history').reshape(1, -1).expand(B, -1)
+        step = call('history', hist_img_feats=ep['hist_img_feats'], hist_ang_feats=ep['hist_ang_feats'],
+                    ob_step_ids=torch.full((1,), int(ep['ob_step']), dtype=torch.long, device=ep['txt_ids'].device),
+                    hist_pano_img_feats=ep['hist_pano_img_feats'], hist_pano_ang_feats=ep['hist_pano_ang_feats'])
+        hist_embeds = torch.stack([cls, step], 1)
+        hist_masks = torch.ones((B, 2), dtype=torch.bool, device=hist_embeds.device)
+    logits = call('visual', txt_embeds=txt, txt_masks=ep['txt_masks'], hist_embeds=hist_embeds, hist_masks=hist_masks,
+                  ob_img_feats=ep['ob_img_feats'], ob_ang_feats=ep['ob_ang_feats'], ob_nav_types=ep['ob_nav_types'],
+                  ob_masks=ep['ob_masks'], imagine_embeds=img2, imagine_masks=ep['imagine_masks'])[0]
+    tgt = hamt_targets_of(ep)
+    ce = torch.nn.functional.cross_entropy(logits, tgt, reduction='sum') / tgt.shape[0]
+    return ce + 0.5 * aux, ce, aux, logits
+
+
+def autocast_noise(ref, run_step, out):
+    """What ANY bf16 evaluation of this step does to the gradients: the unmodified reference under torch.autocast(bfloat16) against
+    its own fp32 gradients (already in .grad), measured exactly as the GPU tests measure the product (sampled elements scaled by
+    max(|ref sample|, 3 rms), per-parameter norms, per-parameter cosine).  Stored in the fixture: the bf16-mode bounds of the tests
+    are multiples of these numbers, not free constants."""
+    fp32 = {n: p.grad.detach().clone() for n, p in ref.named_parameters() if p.grad is not None}
+    ref.zero_grad(set_to_none=True)
+    with torch.autocast('cpu', dtype=torch.bfloat16):
+        loss = run_step()
+    loss.float().backward()
+    top = max(float(g.double().norm()) for g in fp32.values())
+    elem, nerr, dots = [], [], []
+    for n, g32 in fp32.items():
+        g = dict(ref.named_parameters())[n].grad
+        ref_norm = float(g32.double().norm())
+        if g is None or ref_norm < 1e-7 * top:
+            continue
+        idx = torch.from_numpy(grad_sample_index(n, g32.numel()))
+        got, want = g.reshape(-1)[idx].float(), g32.reshape(-1)[idx].float()
+        scale = max(float(want.abs().max()), 3.0 * ref_norm / np.sqrt(g32.numel()))
+        elem.append(float((got - want).abs().max()) / scale)
+        nerr.append(abs(float(g.double().norm()) - ref_norm) / ref_norm)
+        if g32.numel() >= 32:
+            dots.append(float((got * want).sum() / (got.norm() * want.norm()).clamp_min(1e-30)))
+    out['autocast_elem_median'] = np.float64(np.median(elem))
+    out['autocast_elem_max'] = np.float64(np.max(elem))
+    out['autocast_norm_median'] = np.float64(np.median(nerr))
+    out['autocast_norm_max'] = np.float64(np.max(nerr))
+    out['autocast_cosine'] = np.float64(np.mean(dots))
+    out['autocast_loss'] = loss.detach().float()
+    for n, g32 in fp32.items():                                  # leave the fp32 gradients in place
+        dict(ref.named_parameters())[n].grad = g32
+    print('   reference under autocast(bf16): element err median %.3f max %.3f, norm err median %.4f max %.3f, cosine %.5f'
+          % (out['autocast_elem_median'], out['autocast_elem_max'], out['autocast_norm_median'], out['autocast_norm_max'],
+             out['autocast_cosine']))
+
+
+def _grad_fixture(ref, out):
+    names, norms, samples = [], [], []
+    for name, p in ref.named_parameters():
+        if p.grad is None:
+            continue
+        names.append(name)
+        g = p.grad.detach().double().reshape(-1)
+        norms.append(float(g.norm()))
+        samples.append(g[torch.from_numpy(grad_sample_index(name, g.numel()))].float().numpy())
+    out['grad_norms'] = np.asarray(norms, np.float64)
+    out['grad_samples'] = np.stack(samples)
+    return names
+
+
+def run_hamt_variant_grads(args):
+    """Gradient fixtures of the HAMT fine-tuning variants from the REAL reference (TINY episodes)."""
+    from importlib import import_module
+    synth = import_module('vln_imagine_b200.synth')
+    from oracle import hamt_oracle as O
+    all_names = {}
+    for tag, over in HAMT_GRAD_VARIANTS.items():
+        ref = build_reference('hamt', over)
+        ref.contrastive_alignment_model.image_proj.dropout = _Clone()
+        manifest = {k: list(v.shape) for k, v in ref.state_dict().items()}
+        ref.load_state_dict(synth.synth_state_dict(manifest, seed=0))
+        ref.zero_grad(set_to_none=True)
+        ep = synth.to_torch(synth.hamt_episode(synth.TINY, 7))
+        hm = O.hist_masks_from_lens(ep['hist_lens'], ep['hist_embeds'].shape[1])
+        loss, ce, aux, logits = hamt_variant_train_step(lambda mode='history', **kw: ref(mode, **kw), ep, hm, over)
+        loss.backward()
+        out = {'loss': loss.detach(), 'ce': ce.detach(), 'aux': aux.detach(), 'act_logits': logits.detach()}
+        all_names[tag] = _grad_fixture(ref, out)
+        autocast_noise(ref, lambda: hamt_variant_train_step(lambda mode='history', **kw: ref(mode, **kw), ep, hm, over)[0], out)
+        np.savez(os.path.join(GOLD, 'hamt_grads_%s.npz' % tag), **_np(out))
+        print(tag, 'loss', float(loss.detach()), 'ce', float(ce.detach()), 'aux', float(aux.detach()), 'params with grad', len(all_names[tag]))
+    with open(os.path.join(GOLD, 'hamt_grads_variant_names.json'), 'w') as f:
+        json.dump(all_names, f, indent=0)
+
+
+def duet_reverie_train_step(call, ep):
+    """One fine-tuning step of the REVERIE agent (reverie/agent_obj.py:373-463,544-546): navigation cross-entropy + object-grounding
+    cross-entropy over the episodes that see an object (the first box is the teacher's) + 0.5 * aux."""
+    txt = call('language', {'txt_ids': ep['txt_ids'], 'txt_masks': ep['txt_masks']})
+    img = call('imagine', {'imagine_feats': ep['imagine_feats'], 'imagine_masks': None})
+    aux, img2 = call('align_with_contrastive_loss', {
+        'align_txt_embeds': txt, 'txt_masks': ep['txt_masks'], 'align_imagine_embeds': img,
+        'imagine_masks': ep['imagine_masks'], 'obs_instr_ids': ep['obs_instr_ids']})
+    pano, pano_masks = call('panorama', {k: ep[k] for k in ('view_img_fts', 'obj_img_fts', 'loc_fts', 'nav_types', 'view_lens', 'obj_lens')})
+    vp_img = torch.cat([torch.zeros_like(pano[:, :1]), pano], 1)
+    nav = call('navigation', {**{k: ep[k] for k in (
+        'txt_masks', 'gmap_img_embeds', 'gmap_step_ids', 'gmap_pos_fts', 'gmap_masks', 'gmap_pair_dists', 'gmap_visited_masks',
+        'gmap_vpids', 'vp_pos_fts', 'vp_masks', 'vp_nav_masks', 'vp_obj_masks', 'vp_cand_vpids', 'imagine_masks')},
+        'txt_embeds': txt, 'imagine_embeds': img2, 'vp_img_embeds': vp_img})
+    tgt = nav_targets_of(ep).to(nav['fused_logits'].device)
+    B = tgt.shape[0]
+    ce = torch.nn.functional.cross_entropy(nav['fused_logits'], tgt, reduction='sum') / B
+    has = torch.nonzero(ep['obj_lens'].to(tgt.device) > 0).view(-1)
+    og_t = (ep['view_lens'].to(tgt.device) + 1)[has]                      # first object token of the local stream
+    og = torch.nn.functional.cross_entropy(nav['obj_logits'][has], og_t, reduction='sum') / B
+    return ce + og + 0.5 * aux, ce, og, aux, nav
+
+
+def run_duet_reverie_grads(args):
+    from importlib import import_module
+    synth = import_module('vln_imagine_b200.synth')
+    ref = build_reference('duet', dict(dataset='reverie', obj_feat_size=768, aux_loss_type='cosine'))
+    ref.contrastive_alignment_model.image_proj.dropout = _Clone()
+    manifest = {k: list(v.shape) for k, v in ref.state_dict().items()}
+    ref.load_state_dict(synth.synth_state_dict(manifest, seed=0, gasa_stress=True))
+    ref.zero_grad(set_to_none=True)
+    ep = synth.to_torch(synth.duet_reverie_episode(synth.TINY, 7))
+    loss, ce, og, aux, nav = duet_reverie_train_step(lambda mode, batch: ref(mode, batch), ep)
+    loss.backward()
+    out = {'loss': loss.detach(), 'ce': ce.detach(), 'og': og.detach(), 'aux': aux.detach(), 'fused_logits': nav['fused_logits'].detach(),
+           'obj_logits': nav['obj_logits'].detach()}
+    names = _grad_fixture(ref, out)
+    autocast_noise(ref, lambda: duet_reverie_train_step(lambda mode, batch: ref(mode, batch), ep)[0], out)
+    np.savez(os.path.join(GOLD, 'duet_reverie_grads_tiny.npz'), **_np(out))
+    with open(os.path.join(GOLD, 'duet_reverie_grads_names.json'), 'w') as f:
+        json.dump(names, f, indent=0)
+    print('reverie loss', float(loss.detach()), 'ce', float(ce.detach()), 'og', float(og.detach()), 'aux', float(aux.detach()),
+          'params with grad', len(names), 'of', len(manifest))
 
 
 def run_hamt(args):
@@ -623,12 +787,13 @@ def run_hamt_margin(args):
 
 if __name__ == '__main__':
     ap = argparse.ArgumentParser()
-    ap.add_argument('--model', choices=['duet', 'hamt', 'hamt_encvis', 'hamt_margin', 'hamt_actpred', 'duet_reverie', 'duet_soon', 'duet_pretrain'], required=True)
+    ap.add_argument('--model', choices=['duet', 'hamt', 'hamt_variants', 'hamt_encvis', 'hamt_margin', 'hamt_actpred', 'duet_reverie', 'duet_soon', 'duet_pretrain'], required=True)
     ap.add_argument('--grads', action='store_true', help='write the gradient fixtures (cfg-4) instead')
     a = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
     if a.grads:
-        (run_duet_grads if a.model == 'duet' else run_hamt_grads)(a)
+        {'duet': run_duet_grads, 'hamt': run_hamt_grads, 'hamt_variants': run_hamt_variant_grads,
+         'duet_reverie': run_duet_reverie_grads}[a.model](a)
     else:
         {'duet': run_duet, 'hamt': run_hamt, 'hamt_encvis': run_hamt_encvis, 'hamt_margin': run_hamt_margin, 'hamt_actpred': run_hamt_actpred, 'duet_reverie': run_duet_reverie, 'duet_soon': run_duet_soon, 'duet_pretrain': run_duet_pretrain}[a.model](a)

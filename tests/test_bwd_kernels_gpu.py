@@ -322,6 +322,66 @@ def test_infonce_loss_bwd(ag, T):
     assert abs(float(l2)) < 1e-6 and float(p2.grad.abs().max()) < 1e-6
 
 
+@pytest.mark.parametrize('dtype', [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize('M,N,K,ends', [
+    (300, 128, 64, None),                 # one unit, rows not a multiple of 64 (TMA zero fill), 64-wide tile
+    (4416, 768, 768, [2048, 4416]),       # cfg-2 grouped projection: 36 tiles x 4 splits
+    (2304, 2304, 768, None),              # panorama QKV
+    (4416, 768, 3072, [2048, 4416]),      # FFN2 weight gradient (256-wide tiles, no split)
+    (2304, 3072, 768, None),              # FFN1
+    (520, 512, 768, None),                # projection head
+    (1000, 256, 192, [256, 1000]),        # 64-wide tiles, uneven groups
+])
+def test_wgrad16_vs_torch(ag, M, N, K, ends, dtype):
+    """vi_wgrad16 (MN-major tcgen05 operands, split rows, ones-tile bias gradient) against dY^T X / dY.sum(0) in fp32 of the
+    same 16-bit values; two calls are bit-identical (fixed-order reduction of the split partials)"""
+    dy = (_rand(M, N, seed=51) * 0.5).to(dtype)
+    x = _rand(M, K, seed=52).to(dtype)
+    assert ag.wgrad16_ok(dy, x)
+    dW, db = ag.wgrad16(dy, x, ends, True)
+    dW2, db2 = ag.wgrad16(dy, x, ends, True)
+    torch.cuda.synchronize()
+    assert torch.equal(dW, dW2) and torch.equal(db, db2)
+    bounds = [0] + (ends or [M])
+    for g in range(len(bounds) - 1):
+        r0, r1 = bounds[g], bounds[g + 1]
+        ref_w = dy[r0:r1].float().t() @ x[r0:r1].float()
+        ref_b = dy[r0:r1].float().sum(0)
+        assert relerr(dW[g * N:(g + 1) * N], ref_w) < 2e-3, (g, relerr(dW[g * N:(g + 1) * N], ref_w))
+        assert relerr(db[g * N:(g + 1) * N], ref_b) < 2e-3, (g, relerr(db[g * N:(g + 1) * N], ref_b))
+    dW3, db3 = ag.wgrad16(dy, x, ends, False)
+    assert db3 is None and torch.equal(dW3, dW)
+
+
+@pytest.mark.parametrize('margin', [0.1, 0.5])
+def test_margin_loss_bwd(ag, margin):
+    """margin form of the alignment loss (H/models/vilmodel_cmt.py:825-856): (1 - cos_pos) + mean relu(margin + cos_neg - cos_pos)
+    over the noun-phrase means of OTHER episodes; gradient w.r.t. the projected rows against torch autograd"""
+    R, Nn = 37, 45
+    p = _rand(R, 768, seed=41).requires_grad_()
+    t, negs = _rand(R, 768, seed=42), _rand(Nn, 768, seed=43)
+    with torch.no_grad():                                # some negatives close to the row, so both hinge states occur
+        negs[::3] = p.detach()[: negs[::3].shape[0]] + 0.3 * negs[::3]
+    g = torch.Generator().manual_seed(6)
+    row_ep = torch.sort(torch.randint(0, 8, (R,), generator=g)).values.int().cuda()
+    neg_ep = torch.sort(torch.randint(0, 8, (Nn,), generator=g)).values.int().cuda()
+    loss = ag.MarginLossFn.apply(p, t, negs, row_ep, neg_ep, margin, R, Nn)
+    (loss * 0.7).backward()
+    pr = p.detach().clone().requires_grad_()
+    ref, active = [], 0
+    for r in range(R):
+        ng = negs[neg_ep != row_ep[r]]
+        pos = F.cosine_similarity(pr[r:r + 1], t[r:r + 1]).squeeze()
+        hinge = F.relu(margin + F.cosine_similarity(pr[r:r + 1], ng) - pos)
+        active += int((hinge > 0).sum())
+        ref.append((1 - pos) + hinge.mean())
+    ref = torch.stack(ref).mean()
+    (ref * 0.7).backward()
+    assert 0 < active < R * Nn
+    assert abs(float(loss) - float(ref)) < 1e-4 * max(1.0, abs(float(ref)))
+    assert relerr(p.grad, pr.grad) < 1e-4
+
+
 def test_slot_gather_scatter_bwd(ag):
     n, R = 40, 9
     src = _rand(n, 768, seed=26).requires_grad_()

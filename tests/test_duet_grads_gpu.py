@@ -3,14 +3,13 @@ kernels against gradient fixtures of the REAL reference (tests/golden/duet_grads
 ``oracle/gen_golden.py --model duet --grads``): every one of the 427 parameters is pinned by its gradient L2 norm
 and 32 seeded element values, a few small ones in full.
 
-Tolerances.  fp32 check mode: every parameter within 1e-3 (max-norm relative over the sampled elements, and on the
-L2 norm); measured on B200: <= 2e-5.  Loss terms within 1e-4.
-bf16 mode: loss terms and logits within 2e-2; per-parameter gradient NORMS within 5e-2 (the scalar GASA slope, a sum
-with heavy cancellation, within 0.35); individual gradient ELEMENTS of a deep post-LN stack are noisy in ANY bf16
-evaluation - the reference itself under torch.autocast(bfloat16) on these inputs (CPU, build container) shows
-per-parameter sampled-element errors of median 6-7 %, p90 10-11 %, max 22 % and norm errors of median 0.6 %, max
-3-8 % against its own fp32 gradients - so elements are held to: median over parameters < 0.10, every parameter < 0.40,
-and the cosine between all sampled product and reference gradient elements (each parameter normalised) > 0.99.
+Tolerances (tests/parity_utils.py).  fp32 check mode: every parameter within 1e-3 (max-norm relative over the sampled elements,
+and on the L2 norm); measured on B200: <= 2e-5.  Loss terms within 1e-4.
+bf16 mode: loss terms and logits within 2e-2; individual gradient ELEMENTS of a deep post-LN stack are noisy in ANY bf16 evaluation,
+so the fixture also records what the unmodified reference itself shows under torch.autocast(bfloat16) on this step against its own
+fp32 gradients (oracle/gen_golden.autocast_noise: DUET tiny / cfg-1 element error median 6.9 / 7.0 %, max 69 / 37 %, norm error
+max 7.7 / 3.0 %, mean per-parameter cosine 0.9936 / 0.9957) and the product is held to 1.5 x those figures on every one of them
+(the scalar GASA slope, a sum with heavy cancellation, to 0.35 on its norm).
 """
 import importlib
 import json
@@ -21,13 +20,11 @@ import pytest
 import torch
 
 from conftest import GOLDEN
-from parity_utils import golden, manifest, max_rel, to_dev
+from parity_utils import BF16_SCALAR_NORM, GRAD_TOL, LOSS_TOL, check_gradients, golden, manifest, max_rel, to_dev
 
 pytestmark = pytest.mark.gpu
 
-GRAD_TOL = {'fp32': 1e-3, 'bf16': 5e-2}
-BF16_ELEM_MAX, BF16_ELEM_MEDIAN, BF16_COSINE, BF16_SCALAR_NORM = 0.40, 0.10, 0.99, 0.35
-LOSS_TOL = {'fp32': 1e-4, 'bf16': 2e-2}
+BF16_COSINE = 0.99        # whole small tensors kept in full (full::*): cosine with the reference gradient
 
 
 @pytest.fixture(scope='module')
@@ -63,43 +60,7 @@ def test_duet_train_step_gradients(env, tag, shape, seed, stress, precision):
     assert list(params) == names
     tol = GRAD_TOL[precision]
     top = float(gold['grad_norms'].max())
-    worst = []
-    dots = []
-    for i, name in enumerate(names):
-        g = params[name].grad
-        assert g is not None, 'no gradient for ' + name
-        assert torch.isfinite(g).all(), name
-        ref_norm = float(gold['grad_norms'][i])
-        got_norm = float(g.double().norm())
-        if ref_norm < 1e-7 * top:
-            # analytically zero gradients (key biases: softmax is invariant to a per-query constant)
-            assert got_norm < 1e-4 * top, (name, got_norm)
-            continue
-        idx = torch.from_numpy(grad_sample_index(name, g.numel())).cuda()
-        got = g.reshape(-1)[idx].float().cpu()
-        want = gold['grad_samples'][i]
-        rms = ref_norm / np.sqrt(g.numel())
-        scale = max(float(want.abs().max()), 3.0 * rms)
-        err = float((got - want).abs().max()) / scale
-        nerr = abs(got_norm - ref_norm) / ref_norm
-        worst.append((max(err, nerr), name, err, nerr))
-        if g.numel() >= 32:
-            dots.append(float((got * want).sum() / (got.norm() * want.norm()).clamp_min(1e-30)))
-    worst.sort(reverse=True)
-    print('worst gradient errors (%s, %s):' % (tag, precision))
-    for w in worst[:int(os.environ.get('VI_GRAD_REPORT', '5'))]:
-        print('   %.3e  %s  (samples %.3e, norm %.3e)' % w)
-    if precision == 'fp32':
-        bad = [w for w in worst if w[0] >= tol]
-        assert not bad, '%d of %d parameters outside %.0e: %s' % (len(bad), len(worst), tol, bad[:8])
-    else:
-        elem = np.array([w[2] for w in worst if not w[1].endswith('sprel_linear.weight')])
-        cos = float(np.mean(dots))
-        print('   bf16: element error median %.3e max %.3e, mean per-parameter cosine %.5f' % (np.median(elem), elem.max(), cos))
-        assert np.median(elem) < BF16_ELEM_MEDIAN and elem.max() < BF16_ELEM_MAX
-        assert cos > BF16_COSINE
-        bad = [w for w in worst if w[3] >= (BF16_SCALAR_NORM if w[1].endswith('sprel_linear.weight') else tol)]
-        assert not bad, '%d of %d parameter norms outside tolerance: %s' % (len(bad), len(worst), bad[:8])
+    check_gradients(net, gold, names, precision, 'duet ' + tag)
     for key in gold:
         if key.startswith('full::'):
             ref = gold[key]
@@ -205,3 +166,38 @@ def test_duet_infonce_alignment_gradients(env, precision):
             nerr = abs(float(got.norm()) - float(want.norm())) / float(want.norm())
             cos = float((got * want).sum() / (got.norm() * want.norm()))
             assert nerr < tol and cos > 0.99, (n, nerr, cos)
+
+
+def test_fused_gradient_accumulation_matches_autograd(env):
+    """train.duet_finetune_iteration(fused_accumulation=True): the per-step parameter gradients summed inside vi_wgrad16 /
+    vi_add_ln_bwd_acc (autograd gets None, one multi-tensor add into .grad at the end of the backward pass) against the plain path
+    where autograd adds one gradient per parameter per step.  Same kernels, same operands: only the order of the fp32 additions
+    over the steps differs.  Three navigation steps so that every accumulator sees overwrite + add + add; run twice to check that
+    nothing leaks from one backward pass into the next."""
+    train = importlib.import_module('vln_imagine_b200.train')
+    synth, model = env
+    net = model.vln_bert
+    net.load_state_dict(synth.synth_state_dict(manifest('duet'), seed=0, gasa_stress=True))
+    net.precision = 'bf16'
+    ep = to_dev(synth.to_torch(synth.duet_episode(synth.CFG1, 1234)))
+
+    def run(fused):
+        net.zero_grad(set_to_none=True)
+        loss, _, _, _ = train.duet_finetune_iteration(model, ep, n_steps=3, fused_accumulation=fused)
+        torch.cuda.synchronize()
+        return float(loss), {n: p.grad.detach().clone() for n, p in net.named_parameters()}
+    l0, g0 = run(False)
+    for _ in range(2):
+        l1, g1 = run(True)
+        assert l1 == l0
+        assert set(g1) == set(g0)
+        worst = max((float((g1[n] - g0[n]).abs().max() / g0[n].abs().max().clamp_min(1e-20)), n) for n in g0)
+        assert worst[0] < 1e-4, worst
+    # with gradients that already exist (.grad views of a flat buffer) the sums are ADDED to them
+    flat = train.FlatGradients(net)
+    flat.buffer.fill_(1.0)
+    train.duet_finetune_iteration(model, ep, n_steps=3, fused_accumulation=True)
+    torch.cuda.synchronize()
+    for n, p in net.named_parameters():
+        assert float((p.grad - 1.0 - g0[n]).abs().max()) < 1e-4 * max(1.0, float(g0[n].abs().max())), n
+    net.zero_grad(set_to_none=True)

@@ -122,7 +122,7 @@ def test_graph_replayed_iteration_equals_the_eager_one(lib_built):
 
     def grad_fn(ep):
         flat.zero()
-        loss, _, _, _ = train.duet_finetune_iteration(model, ep, n_steps=2)
+        loss, _, _, _ = train.duet_finetune_iteration(model, ep, n_steps=2, fused_accumulation=True)
         return loss.detach()
 
     holder = {}

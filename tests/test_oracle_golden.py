@@ -5,6 +5,7 @@ import importlib
 import json
 import os
 
+import numpy as np
 import pytest
 import torch
 
@@ -207,3 +208,18 @@ def test_oracle_edge_cases_empty_alignment_and_single_admissible_action():
     l = torch.full((1, 3), float('-inf')); l[0, 0] = 0.2
     fused = O.fuse_logits(g, l, [[None, 'a', 'b', 'c']], torch.tensor([[False, True, False, False]]), [[None, 'b', 'c']])
     assert torch.isfinite(fused).sum() == 1 and abs(float(fused[0, 0]) - 0.5) < 1e-6
+
+
+def test_gradient_fixtures_record_the_reference_autocast_noise():
+    """every gradient fixture carries what the unmodified reference shows under torch.autocast(bfloat16) against its own fp32
+    gradients (oracle/gen_golden.autocast_noise): the bf16-mode bounds of the GPU gradient tests are 1.5 x these figures"""
+    import glob
+    files = sorted(glob.glob(os.path.join(GOLDEN, '*grads_*.npz')))
+    assert len(files) >= 8
+    for f in files:
+        z = np.load(f)
+        for k in ('autocast_elem_median', 'autocast_elem_max', 'autocast_norm_median', 'autocast_norm_max', 'autocast_cosine'):
+            assert k in z.files, (f, k)
+        # bf16 noise of a deep post-LN stack: per-parameter sampled-element errors of several percent, cosine ~0.99
+        assert 0.02 < float(z['autocast_elem_median']) < 0.2 and 0.98 < float(z['autocast_cosine']) < 1.0, f
+        assert abs(float(z['autocast_loss']) - float(z['loss'])) < 2e-2 * abs(float(z['loss'])), f

@@ -84,9 +84,13 @@ PROTOTYPES = {
     'vi_transpose': [_p, _l, _p, _l, _i, _i, _i, _i, _p],
     'vi_colsum': [_p, _l, _i, _p, _l, _i, _p, _l, _p],
     'vi_reduce_scratch_elems': [_l, _i, _i],
+    'vi_wgrad16_splits': [_i, _i, _i, _ip],
+    'vi_wgrad16_workspace': [_i, _i, _i, _ip, _i],
+    'vi_wgrad16': [_p, _l, _p, _l, _i, _i, _i, _i, _ip, _p, _p, _p, _l, _i, _i, _p],
     'vi_act_fwd': [_p, _p, _l, _i, _i, _p],
     'vi_act_bwd': [_p, _p, _p, _l, _i, _i, _p],
     'vi_add_ln_bwd': [_p, _p, _p, _f, _p, _p, _p, _p, _p, _p, _p, _l, _i, _ip, _p, _l, _p],
+    'vi_add_ln_bwd_acc': [_p, _p, _p, _f, _p, _p, _p, _p, _p, _p, _p, _l, _i, _ip, _p, _l, _i, _p],
     'vi_feat_wgrad': [_p, _p, _i, _p, _p, _l, _p, _l, _p],
     'vi_scatter_add_rows': [_p, _p, _i, _p, _l, _p],
     'vi_rowdot_bwd': [_p, _p, _p, _p, _p, _p, _l, _i, _ip, _p, _l, _p],
@@ -96,6 +100,7 @@ PROTOTYPES = {
     'vi_mul_bcast_bwd_s': [_p, _p, _p, _l, _i, _p],
     'vi_cosine_loss_bwd': [_p, _p, _p, _p, _p, _i, _p],
     'vi_infonce_loss_bwd': [_p, _p, _p, _p, _p, _f, _p, _p, _p, _i, _i, _p],
+    'vi_margin_loss_bwd': [_p, _p, _p, _p, _p, _f, _p, _p, _p, _i, _i, _p],
     'vi_graph_init': [_p, _p, _p, _p, _i, _i, _p],
     'vi_graph_update': [_p, _p, _p, _p, _i, _i, _p, _p, _p, _p, _i, _p, _p],
     'vi_graph_embed_step': [_p, _p, _i, _i, _i, _p, _p, _i, _p, _p, _p, _i, _p, _i, _p, _p, _p],
@@ -106,6 +111,7 @@ for _name, _args in PROTOTYPES.items():
     _fn.argtypes = _args
     _fn.restype = _i
 lib.vi_reduce_scratch_elems.restype = C.c_int64
+lib.vi_wgrad16_workspace.restype = C.c_int64
 lib.vi_last_error.argtypes = []
 lib.vi_last_error.restype = C.c_char_p
 

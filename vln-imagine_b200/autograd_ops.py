@@ -71,6 +71,118 @@ def colsum(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+_WGRAD_WS = {}
+
+
+class _GradAcc:
+    """Gradient accumulation fused into the kernels (opt-in, ``fused_grad_accumulation``).  A parameter of this path is used once
+    per navigation step, so autograd ends an iteration with one small ``add`` kernel per parameter per step (~1500 launches at 6
+    steps).  With the switch on, the dense-layer and LayerNorm backward nodes add their parameter gradients straight into one fp32
+    accumulator per weight pack (vi_wgrad16 / vi_add_ln_bwd_acc with accumulate = 1: TMA reduce-add or a read-modify-write with one
+    writer per element, in backward order - deterministic) and hand autograd ``None``; when the backward pass ends, ONE multi-tensor
+    add moves the accumulators into ``.grad`` (created if missing), which is what the optimiser / the flat all-reduce buffer see.
+    Not for modules whose parameters carry autograd hooks (DistributedDataParallel): those keep the plain path."""
+    enabled = False
+    buffers = {}            # key (ids of the pack's parameters) -> dict(tensors..., live=bool, params=[...])
+    live = []               # entries holding gradients of the backward pass in flight
+    queued = False
+
+
+class fused_grad_accumulation:
+    def __init__(self, on: bool = True):
+        self.on = on
+
+    def __enter__(self):
+        self.prev = _GradAcc.enabled
+        _GradAcc.enabled = self.on
+        if self.on:                                   # a backward pass that died half-way must not leak into this one
+            for e in _GradAcc.live:
+                e['live'] = False
+            _GradAcc.live, _GradAcc.queued = [], False
+        return self
+
+    def __exit__(self, *exc):
+        _GradAcc.enabled = self.prev
+        return False
+
+
+def _acc_entry(params, shapes, device):
+    """the accumulators of one pack: tensors of ``shapes`` + the parameter slices they feed"""
+    key = tuple(id(p) for p in params) + tuple(tuple(s) for s in shapes)
+    e = _GradAcc.buffers.get(key)
+    if e is None or e['t'][0].device != device:
+        e = {'t': [torch.empty(tuple(sh), dtype=F32, device=device) for sh in shapes], 'live': False, 'params': list(params)}
+        _GradAcc.buffers[key] = e
+    return e
+
+
+def _acc_begin(e) -> int:
+    """1 when the entry already holds gradients of this backward pass (the kernel must add), else 0 (overwrite)"""
+    beta = 1 if e['live'] else 0
+    if not e['live']:
+        e['live'] = True
+        _GradAcc.live.append(e)
+    if not _GradAcc.queued:
+        _GradAcc.queued = True
+        torch.autograd.Variable._execution_engine.queue_callback(_acc_flush)
+    return beta
+
+
+def _acc_flush():
+    """end of the backward pass: accumulators -> .grad (one multi-tensor add)"""
+    dsts, srcs = [], []
+    for e in _GradAcc.live:
+        for p, src in e['slices']:
+            if not p.requires_grad:
+                continue
+            if p.grad is None:
+                p.grad = src.reshape(p.shape).clone()
+            else:
+                dsts.append(p.grad)
+                srcs.append(src.reshape(p.shape))
+        e['live'] = False
+    _GradAcc.live = []
+    _GradAcc.queued = False
+    if dsts:
+        torch._foreach_add_(dsts, srcs)
+        _launched(1)
+
+
+def wgrad16(dy16: torch.Tensor, x16: torch.Tensor, ends, want_db: bool, out=None, accumulate: int = 0):
+    """(dW [n_groups * N, K] fp32, db [n_groups * N] fp32 or None) of a (grouped) dense layer from the 16-bit row-major dY [M, N]
+    and X [M, K] as they are (vi_wgrad16: MN-major tcgen05 operands, no transposed copies, bias gradient on the tensor cores).
+    out = (dW, db) preallocated; accumulate = 1 adds to them."""
+    M, N = dy16.shape
+    K = x16.shape[1]
+    bounds = [min(int(e), M) for e in ends] if ends is not None else [M]
+    G = len(bounds)
+    rows = _lib.int_array([b - (bounds[i - 1] if i else 0) for i, b in enumerate(bounds)])
+    S = int(lib.vi_wgrad16_splits(N, K, G, rows))
+    need = int(lib.vi_wgrad16_workspace(N, K, G, rows, S))
+    ws = None
+    if need > 0:
+        ws = _WGRAD_WS.get(dy16.device)
+        if ws is None or ws.numel() < need:
+            ws = torch.empty((max(need, 1 << 23),), dtype=F32, device=dy16.device)
+            _WGRAD_WS[dy16.device] = ws
+    if out is not None:
+        dW, db = out
+    else:
+        dW = torch.empty((G * N, K), dtype=F32, device=dy16.device)
+        db = torch.empty((G * N,), dtype=F32, device=dy16.device) if want_db else None
+    check(lib.vi_wgrad16(dy16.data_ptr(), dy16.stride(0), x16.data_ptr(), x16.stride(0), ops._DT[dy16.dtype], N, K, G,
+                         _lib.int_array(bounds), dW.data_ptr(), _ptr(db), _ptr(ws), ws.numel() if ws is not None else 0, S,
+                         int(accumulate), _stream()), 'vi_wgrad16')
+    _launched(2 if S > 1 else 1)
+    return dW, db
+
+
+def wgrad16_ok(dy16: torch.Tensor, x16: torch.Tensor) -> bool:
+    return (ops.is16(dy16.dtype) and x16.dtype == dy16.dtype and dy16.shape[1] % 128 == 0 and x16.shape[1] % 64 == 0
+            and dy16.stride(1) == 1 and x16.stride(1) == 1 and dy16.stride(0) % 8 == 0 and x16.stride(0) % 8 == 0
+            and dy16.data_ptr() % 16 == 0 and x16.data_ptr() % 16 == 0)
+
+
 def to_operand(t: torch.Tensor, lowp: bool) -> torch.Tensor:
     """gradient tensor -> GEMM operand dtype of the current precision mode (contiguous)"""
     t = t.contiguous()
@@ -172,17 +284,39 @@ class LinearFn(Function):
         if ctx.needs_input_grad[0]:
             wt = pack.get_t(lowp, n_groups)                             # [n_groups*K, N]
             dx = ops.gemm(dyo, wt, None, out_dtype=x.dtype, group_row_end=ends)
-        dW = torch.empty((n_groups * N, K), dtype=F32, device=x.device)
-        db = torch.empty((n_groups * N,), dtype=F32, device=x.device) if pack.biases is not None else None
-        bounds = [0] + (list(ends) if ends is not None else [M])
-        for g in range(n_groups):
-            r0, r1 = bounds[g], min(bounds[g + 1], M)
-            rp = pad64(r1 - r0) if lowp else r1 - r0
-            dyT = transpose(dyo[r0:r1], rp)                             # [N, rp]
-            xT = transpose(x[r0:r1], rp)                                # [K, rp]
-            ops.gemm(dyT, xT, None, out_dtype=F32, out=dW[g * N:(g + 1) * N])
-            if db is not None:
-                db[g * N:(g + 1) * N] = colsum(dyo[r0:r1])
+        if lowp and wgrad16_ok(dyo, x) and _GradAcc.enabled and dyo.shape[1] * n_groups == sum(w.shape[0] for w in pack.weights):
+            # gradient accumulation inside the kernel: autograd gets None, _acc_flush moves the sums into .grad
+            has_b = pack.biases is not None
+            bs = [b for b in pack.biases if b is not None] if has_b else []
+            e = _acc_entry(pack.weights + bs, [(n_groups * N, K)] + ([(n_groups * N,)] if has_b else []), x.device)
+            if 'slices' not in e:
+                sl, off = [], 0
+                for wsrc in pack.weights:
+                    sl.append((wsrc, e['t'][0][off:off + wsrc.shape[0]]))
+                    off += wsrc.shape[0]
+                off = 0
+                for bsrc, wsrc in zip(pack.biases or [], pack.weights):
+                    if bsrc is not None:
+                        sl.append((bsrc, e['t'][1][off:off + wsrc.shape[0]]))
+                    off += wsrc.shape[0]
+                e['slices'] = sl
+            beta = _acc_begin(e)
+            wgrad16(dyo, x, ends, has_b, out=(e['t'][0], e['t'][1] if has_b else None), accumulate=beta)
+            return (dx, dy if ctx.has_res else None, None, None, None, None, *([None] * len(pack.grad_sources())))
+        if lowp and wgrad16_ok(dyo, x):
+            dW, db = wgrad16(dyo, x, ends, pack.biases is not None)
+        else:                                                           # fp32 check mode / odd shapes: transposed copies
+            dW = torch.empty((n_groups * N, K), dtype=F32, device=x.device)
+            db = torch.empty((n_groups * N,), dtype=F32, device=x.device) if pack.biases is not None else None
+            bounds = [0] + (list(ends) if ends is not None else [M])
+            for g in range(n_groups):
+                r0, r1 = bounds[g], min(bounds[g + 1], M)
+                rp = pad64(r1 - r0) if lowp else r1 - r0
+                dyT = transpose(dyo[r0:r1], rp)                             # [N, rp]
+                xT = transpose(x[r0:r1], rp)                                # [K, rp]
+                ops.gemm(dyT, xT, None, out_dtype=F32, out=dW[g * N:(g + 1) * N])
+                if db is not None:
+                    db[g * N:(g + 1) * N] = colsum(dyo[r0:r1])
         grads, off = [], 0
         for wsrc in pack.weights:
             n = wsrc.shape[0]
@@ -239,6 +373,7 @@ class LayerNormFn(Function):
         ctx.b_needs = b is not None and b.requires_grad
         ctx.a_needs = a.requires_grad
         ctx.param_needs = [p.requires_grad for p in params]
+        ctx.param_srcs = list(params) if params else None
         if y16 is None:
             y16 = a.new_empty(0)
             ctx.mark_non_differentiable(y16)
@@ -260,16 +395,29 @@ class LayerNormFn(Function):
         if dy16 is not None:
             dy16 = dy16.contiguous()
         dx = torch.empty_like(a)
-        dg = torch.empty((n_groups, HIDDEN), dtype=F32, device=a.device)
-        dbt = torch.empty((n_groups, HIDDEN), dtype=F32, device=a.device)
-        stats = torch.empty((rows, 2), dtype=F32, device=a.device)
-        sc = reduce_scratch(a.device, rows, HIDDEN, 2)
-        check(lib.vi_add_ln_bwd(a.data_ptr(), _ptr(b), gamma.data_ptr(), ctx.eps, _ptr(dy32), _ptr(dy16), dx.data_ptr(), None,
-                                dg.data_ptr(), dbt.data_ptr(), stats.data_ptr(), rows, n_groups,
-                                _lib.int_array(list(ends)) if ends is not None else None, sc.data_ptr(), sc.numel(), _stream()),
-              'vi_add_ln_bwd')
-        _launched(4)
         half = ctx.n_params // 2
+        srcs = ctx.param_srcs
+        fused = _GradAcc.enabled and srcs is not None and half == n_groups
+        beta = 0
+        if fused:
+            e = _acc_entry(srcs, [(n_groups, HIDDEN), (n_groups, HIDDEN)], a.device)
+            if 'slices' not in e:
+                e['slices'] = [(srcs[i], e['t'][0][i]) for i in range(half)] + [(srcs[half + i], e['t'][1][i]) for i in range(half)]
+            beta = _acc_begin(e)
+            dg, dbt = e['t']
+        else:
+            dg = torch.empty((n_groups, HIDDEN), dtype=F32, device=a.device)
+            dbt = torch.empty((n_groups, HIDDEN), dtype=F32, device=a.device)
+        stats = torch.empty((rows, 2), dtype=F32, device=a.device)
+        sc = reduce_scratch(a.device, 4 * rows, HIDDEN, 2)            # the fused pass reduces 32-row chunks (RED_CHUNK / 4)
+        check(lib.vi_add_ln_bwd_acc(a.data_ptr(), _ptr(b), gamma.data_ptr(), ctx.eps, _ptr(dy32), _ptr(dy16), dx.data_ptr(), None,
+                                    dg.data_ptr(), dbt.data_ptr(), stats.data_ptr(), rows, n_groups,
+                                    _lib.int_array(list(ends)) if ends is not None else None, sc.data_ptr(), sc.numel(), beta,
+                                    _stream()), 'vi_add_ln_bwd')
+        _launched(2)
+        if fused:
+            return (dx if ctx.a_needs else None, dx if ctx.b_needs else None, None, None, None, None, None, None,
+                    *([None] * ctx.n_params))
         pg = [dg[i] if ctx.param_needs[i] else None for i in range(half)] + \
              [dbt[i] if ctx.param_needs[half + i] else None for i in range(half)]
         return (dx if ctx.a_needs else None, dx if ctx.b_needs else None, None, None, None, None, None, None, *pg)
@@ -437,13 +585,11 @@ class RowDotFn(Function):
         x = x.contiguous()
         rows = x.shape[0]
         out = torch.empty((rows,), dtype=F32, device=x.device)
-        # LayerNorm-free dot: reuse vi_ln_dot's kernel is not possible (it normalises), so run the dot through the
-        # fp32 GEMM entry point per group (N = 1)
-        bounds = [0] + (list(ends) if ends is not None else [rows])
-        for g in range(len(bounds) - 1):
-            r0, r1 = bounds[g], min(bounds[g + 1], rows)
-            ops.gemm(x[r0:r1], wstack[g:g + 1] if wstack.dim() == 2 else wstack.view(1, -1), bstack.view(-1)[g:g + 1],
-                     out=out[r0:r1].view(-1, 1))
+        # the dot-product tail of vi_ln_dot without its LayerNorm (gamma = beta = NULL): one warp per row, all groups in one launch
+        n_groups = 1 if ends is None else len(ends)
+        check(lib.vi_ln_dot(x.data_ptr(), None, None, 0.0, wstack.data_ptr(), bstack.data_ptr(), out.data_ptr(), rows, n_groups,
+                            _lib.int_array([min(int(e), rows) for e in ends]) if ends is not None else None, _stream()), 'vi_ln_dot')
+        _launched(1)
         ctx.save_for_backward(x, wstack)
         ctx.ends, ctx.n_heads = ends, n_heads
         return out
@@ -578,6 +724,30 @@ class InfoNCELossFn(Function):
         return dp, None, None, None, None, None, None, None
 
 
+class MarginLossFn(Function):
+    """compute_contrastive_loss_margin (H/models/vilmodel_cmt.py:825-856) with constant noun-phrase means; grad w.r.t. proj"""
+
+    @staticmethod
+    def forward(ctx, proj, tgt, negs, row_ep, neg_ep, margin, R, n_negs):
+        proj = proj.contiguous()
+        loss, scratch = ops.margin_loss_with_sims(proj, tgt, negs, row_ep, neg_ep, margin, R, n_negs, proj.device)
+        ctx.save_for_backward(proj, tgt, scratch)
+        ctx.extra = (negs, row_ep, neg_ep, float(margin), R, n_negs)
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        proj, tgt, scratch = ctx.saved_tensors
+        negs, row_ep, neg_ep, margin, R, n_negs = ctx.extra
+        dloss = dloss.contiguous().float().view(1)
+        dp = torch.empty_like(proj)
+        check(lib.vi_margin_loss_bwd(proj.data_ptr(), tgt.data_ptr(), _ptr(negs), row_ep.data_ptr(), _ptr(neg_ep), margin,
+                                     scratch.data_ptr(), dloss.data_ptr(), dp.data_ptr(), R, n_negs, _stream()),
+              'vi_margin_loss_bwd')
+        _launched(1)
+        return dp, None, None, None, None, None, None, None
+
+
 class MulBcastFn(Function):
     """y[b, r, :] = x[b, r, :] * s[b, :]   (x [B, R, 768], s [B, 768], both contiguous fp32) -> bf16 or fp32 rows [B*R, 768]"""
 
@@ -599,3 +769,31 @@ class MulBcastFn(Function):
         check(lib.vi_mul_bcast_bwd_s(dy.data_ptr(), x.data_ptr(), ds.data_ptr(), B, R, _stream()), 'vi_mul_bcast_bwd_s')
         _launched(1)
         return dx.view(B, R, HIDDEN), ds, None
+
+
+class SegmentMeanFn(Function):
+    """y[r] = mean of src[row_idx[offsets[r]:offsets[r+1]]] (equal-sized segments of ``seg`` rows, every source row in at most one
+    segment): torch.mean over a token axis (HistoryEmbeddings' panorama mean, H/models/vilmodel_cmt.py:610; the imagination mean of
+    act_pred_token 'ob_imagine_text', :1199).  Adjoint: every source row of segment r receives dy[r] / seg."""
+
+    @staticmethod
+    def forward(ctx, src, offsets, row_idx, R, seg):
+        src = src.contiguous()
+        y32, _ = ops.gather_mean(src, offsets, row_idx, R, want16=False)
+        ctx.save_for_backward(row_idx)
+        ctx.shape, ctx.R, ctx.seg = src.shape, R, seg
+        return y32
+
+    @staticmethod
+    def backward(ctx, dy):
+        (row_idx,) = ctx.saved_tensors
+        dy = dy.contiguous()
+        dev = dy.device
+        R, seg = ctx.R, ctx.seg
+        inv = torch.full((HIDDEN,), 1.0 / seg, dtype=F32, device=dev)
+        g, _ = ops.mul_bcast(dy, HIDDEN, inv, 0, R, 1, want16=False)                  # dy / seg
+        seg_of = torch.arange(R, device=dev, dtype=torch.int64).repeat_interleave(seg)
+        rows, _ = ops.embed_compose(R * seg, dev, idx=seg_of, table=g)                # one copy per member row
+        d = torch.zeros(ctx.shape, dtype=F32, device=dev)
+        ops.scatter_rows(rows, row_idx, d)
+        return d, None, None, None, None

@@ -320,6 +320,123 @@ __global__ void __launch_bounds__(256) ln_bwd_param_partial_kernel(const float* 
   }
 }
 
+// dx AND the parameter-gradient partials in ONE pass over the rows (the two-kernel form above reads a, b and dy twice): a CTA of
+// 8 warps owns LN_CHUNK = 32 consecutive rows (4 per warp), every lane keeps the dgamma / dbeta contributions of its 24 columns in
+// registers, the 8 warps are summed through shared memory in a fixed order and the chunk's partial row goes to
+// part[2][n_chunks][768]; ln_param_sum_kernel then adds the chunks of each row group (fixed order: deterministic).
+constexpr int LN_CHUNK = 32;
+__global__ void __launch_bounds__(256) ln_bwd_fused_kernel(const float* a, const float* b, const float* gamma, float eps,
+                                                           const float* dy32, const bf16* dy16, float* __restrict__ dx32,
+                                                           bf16* __restrict__ dx16, float* __restrict__ stats,
+                                                           float* __restrict__ part, long long rows, int n_chunks,
+                                                           const RowGroups grp) {
+  pdl_enter();
+  __shared__ float red[8][D];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long r0 = (long long)blockIdx.x * LN_CHUNK;
+  float ag[24], ab[24];
+#pragma unroll
+  for (int i = 0; i < 24; ++i) { ag[i] = 0.f; ab[i] = 0.f; }
+  const float* gm_base = gamma + group_of_row(grp, r0) * D;         // a chunk never straddles two row groups
+  for (int it = 0; it < LN_CHUNK / 8; ++it) {
+    const long long row = r0 + it * 8 + warp;
+    if (row >= rows) break;
+    float x[24], g[24], dv[24];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      const int c = (lane + 32 * j) * 4;
+      float4 t = *reinterpret_cast<const float4*>(a + row * D + c);
+      if (b) {
+        const float4 u = *reinterpret_cast<const float4*>(b + row * D + c);
+        t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+      }
+      x[4 * j] = t.x; x[4 * j + 1] = t.y; x[4 * j + 2] = t.z; x[4 * j + 3] = t.w;
+      s += t.x + t.y + t.z + t.w;
+      float4 d4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (dy32) d4 = *reinterpret_cast<const float4*>(dy32 + row * D + c);
+      if (dy16) {
+        const uint2 h = *reinterpret_cast<const uint2*>(dy16 + row * D + c);
+        const float2 h0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&h.x));
+        const float2 h1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&h.y));
+        d4.x += h0.x; d4.y += h0.y; d4.z += h1.x; d4.w += h1.y;
+      }
+      dv[4 * j] = d4.x; dv[4 * j + 1] = d4.y; dv[4 * j + 2] = d4.z; dv[4 * j + 3] = d4.w;
+    }
+    const float mean = warp_sum(s) * (1.0f / D);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 24; ++i) { const float d = x[i] - mean; q = fmaf(d, d, q); }
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + eps);
+    float sg = 0.f, sgx = 0.f;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      const float4 gm = *reinterpret_cast<const float4*>(gm_base + (lane + 32 * j) * 4);
+      const float gmv[4] = {gm.x, gm.y, gm.z, gm.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float xh = (x[4 * j + e] - mean) * rstd;
+        const float gg = dv[4 * j + e] * gmv[e];
+        x[4 * j + e] = xh;
+        g[4 * j + e] = gg;
+        sg += gg;
+        sgx = fmaf(gg, xh, sgx);
+        ag[4 * j + e] = fmaf(dv[4 * j + e], xh, ag[4 * j + e]);
+        ab[4 * j + e] += dv[4 * j + e];
+      }
+    }
+    const float mg = warp_sum(sg) * (1.0f / D), mgx = warp_sum(sgx) * (1.0f / D);
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      const int c = (lane + 32 * j) * 4;
+      float o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o[e] = rstd * (g[4 * j + e] - mg - x[4 * j + e] * mgx);
+      if (dx32) *reinterpret_cast<float4*>(dx32 + row * D + c) = make_float4(o[0], o[1], o[2], o[3]);
+      if (dx16) *reinterpret_cast<uint2*>(dx16 + row * D + c) = make_uint2(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]));
+    }
+    if (lane == 0) { stats[2 * row] = mean; stats[2 * row + 1] = rstd; }
+  }
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      const int c = (lane + 32 * j) * 4;
+      const float* v = pass ? ab : ag;
+      *reinterpret_cast<float4*>(&red[warp][c]) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < D; c += 256) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += red[w][c];
+      part[((long long)pass * n_chunks + blockIdx.x) * D + c] = t;
+    }
+  }
+}
+// dgamma[g][c] / dbeta[g][c] = sum over the LN_CHUNK-row chunks of group g; grid (768 / 256, n_groups, 2)
+__global__ void __launch_bounds__(256) ln_param_sum_kernel(const float* part, float* dgamma, float* dbeta,
+                                                           int n_chunks, long long rows, const RowGroups grp, int accumulate) {
+  pdl_enter();
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  const int gi = blockIdx.y, o = blockIdx.z;
+  const long long g0 = gi == 0 ? 0 : grp.end[gi - 1];
+  long long g1 = gi == grp.n - 1 ? rows : grp.end[gi];
+  if (g1 > rows) g1 = rows;
+  const int k0 = (int)(g0 / LN_CHUNK), k1 = (int)((g1 + LN_CHUNK - 1) / LN_CHUNK);
+  const float* pp = part + ((long long)o * n_chunks) * D + c;
+  float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+  int k = k0;
+  for (; k + 3 < k1; k += 4) {
+    t0 += pp[(long long)k * D]; t1 += pp[(long long)(k + 1) * D]; t2 += pp[(long long)(k + 2) * D]; t3 += pp[(long long)(k + 3) * D];
+  }
+  for (; k < k1; ++k) t0 += pp[(long long)k * D];
+  float* dst = (o ? dbeta : dgamma) + (long long)gi * D + c;
+  const float t = (t0 + t1) + (t2 + t3);
+  *dst = accumulate ? *dst + t : t;
+}
+
 // ---------------------------------------------------------------------------------------------
 // small-feature linear  t = feat W^T + b  (feat_dim <= 16):  dW[c, k] = sum_r dt[r, c] feat[r, k], db[c] = sum_r dt[r, c]
 // stage 1: part[17][n_chunks][768] (k = 16 is the bias), grid (768 / 32, n_chunks), 256 threads; stage 2 sums the chunks
@@ -695,7 +812,8 @@ __global__ void __launch_bounds__(128) cosine_loss_bwd_kernel(const float* proj,
 __global__ void __launch_bounds__(128) infonce_loss_bwd_kernel(const float* proj, const float* tgt, const float* negs,
                                                                const int32_t* row_ep, const int32_t* neg_ep, float inv_t,
                                                                const float* sims, const float* dloss,
-                                                               float* __restrict__ dproj, int R, int n_negs) {
+                                                               float* __restrict__ dproj, int R, int n_negs, int margin_mode,
+                                                               float margin) {
   pdl_enter();
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
@@ -703,14 +821,22 @@ __global__ void __launch_bounds__(128) infonce_loss_bwd_kernel(const float* proj
   const int cols = n_negs + 1;
   const float* s = sims + row * cols;
   const int ep = row_ep[row];
+  // margin form (H/models/vilmodel_cmt.py:825-856): loss_r = (1 - cos_0) + mean_c relu(margin + cos_c - cos_0) over the admissible
+  // negatives, so w_rc = [hinge c active] / count for c >= 1 and w_r0 = -1 - (active hinges) / count   (sims hold plain cosines)
   float mx = s[0];
-  for (int c = 1 + lane; c < cols; c += 32)
-    if (neg_ep[c - 1] != ep) mx = fmaxf(mx, s[c]);
-  mx = warp_max(mx);
-  float sum = 0.f;
-  for (int c = 1 + lane; c < cols; c += 32)
-    if (neg_ep[c - 1] != ep) sum += expf(s[c] - mx);
-  sum = warp_sum(sum) + expf(s[0] - mx);
+  float sum = 0.f, cnt = 0.f, nact = 0.f;
+  if (margin_mode) {
+    for (int c = 1 + lane; c < cols; c += 32)
+      if (neg_ep[c - 1] != ep) { cnt += 1.f; nact += (margin + s[c] - s[0] > 0.f) ? 1.f : 0.f; }
+    cnt = warp_sum(cnt); nact = warp_sum(nact);
+  } else {
+    for (int c = 1 + lane; c < cols; c += 32)
+      if (neg_ep[c - 1] != ep) mx = fmaxf(mx, s[c]);
+    mx = warp_max(mx);
+    for (int c = 1 + lane; c < cols; c += 32)
+      if (neg_ep[c - 1] != ep) sum += expf(s[c] - mx);
+    sum = warp_sum(sum) + expf(s[0] - mx);
+  }
   const float inv_sum = 1.0f / sum;
   float a[24], acc[24];
   float aa = 0.f;
@@ -721,7 +847,13 @@ __global__ void __launch_bounds__(128) infonce_loss_bwd_kernel(const float* proj
   float wcos = 0.f;                                    // sum_c w_rc cos_rc
   for (int c = 0; c < cols; ++c) {
     if (c > 0 && neg_ep[c - 1] == ep) continue;        // warp-uniform
-    const float w = expf(s[c] - mx) * inv_sum - (c == 0 ? 1.f : 0.f);
+    float w;
+    if (margin_mode) {
+      w = c == 0 ? -1.f - nact / cnt : ((margin + s[c] - s[0] > 0.f) ? 1.f / cnt : 0.f);
+      if (w == 0.f) continue;                          // warp-uniform
+    } else {
+      w = expf(s[c] - mx) * inv_sum - (c == 0 ? 1.f : 0.f);
+    }
     const float* t = c == 0 ? tgt + row * D : negs + (long long)(c - 1) * D;
     float tv[24];
     float bb = 0.f;
@@ -853,6 +985,14 @@ extern "C" int vi_act_bwd(const void* x, const void* dy, void* dx, int64_t n, in
 extern "C" int vi_add_ln_bwd(const float* a, const float* b, const float* gamma, float eps, const float* dy32, const void* dy16,
                              float* dx32, void* dx16, float* dgamma, float* dbeta, float* stats, int64_t rows, int n_groups,
                              const int32_t* group_row_end, float* scratch, int64_t scratch_elems, vi_stream_t stream) {
+  return vi_add_ln_bwd_acc(a, b, gamma, eps, dy32, dy16, dx32, dx16, dgamma, dbeta, stats, rows, n_groups, group_row_end, scratch,
+                           scratch_elems, 0, stream);
+}
+
+extern "C" int vi_add_ln_bwd_acc(const float* a, const float* b, const float* gamma, float eps, const float* dy32, const void* dy16,
+                                 float* dx32, void* dx16, float* dgamma, float* dbeta, float* stats, int64_t rows, int n_groups,
+                                 const int32_t* group_row_end, float* scratch, int64_t scratch_elems, int accumulate,
+                                 vi_stream_t stream) {
   RowGroups grp;
   VI_CHECK_ARG(make_groups(grp, n_groups, group_row_end), "vi_add_ln_bwd: bad row groups");
   for (int g = 0; g + 1 < n_groups; ++g)
@@ -861,18 +1001,18 @@ extern "C" int vi_add_ln_bwd(const float* a, const float* b, const float* gamma,
   VI_CHECK_ARG(aligned16(a) && aligned16(b) && aligned16(gamma) && aligned16(dy32) && aligned16(dx32) &&
                    ((uintptr_t)dx16 & 7) == 0, "vi_add_ln_bwd: misaligned operands");
   if (rows <= 0) return VI_OK;
-  VI_CUDA(vi_launch(ln_bwd_dx_kernel, dim3((unsigned)((rows + 3) / 4)), dim3(128), 0, ST(stream), a, b, gamma, eps, dy32,
-                    reinterpret_cast<const bf16*>(dy16), dx32, reinterpret_cast<bf16*>(dx16), stats, (long long)rows, grp));
   if (dgamma && dbeta) {
-    const int nch = red_chunks(rows);
-    VI_CHECK_ARG(scratch && scratch_elems >= (int64_t)2 * nch * D, "vi_add_ln_bwd: scratch too small");
-    VI_CUDA(vi_launch(ln_bwd_param_partial_kernel, dim3(D / 64, nch), dim3(256), 0, ST(stream), a, b, dy32,
-                      reinterpret_cast<const bf16*>(dy16), (const float*)stats, scratch, (long long)rows, nch));
-    // output 0 -> dgamma[n_groups, 768], output 1 -> dbeta[n_groups, 768]
-    VI_CUDA(vi_launch(chunk_sum_kernel, dim3(D / 256, n_groups, 1), dim3(256), 0, ST(stream), (const float*)scratch, dgamma, nch, D,
-                      (long long)rows, grp, (long long)0));
-    VI_CUDA(vi_launch(chunk_sum_kernel, dim3(D / 256, n_groups, 1), dim3(256), 0, ST(stream),
-                      (const float*)(scratch + (long long)nch * D), dbeta, nch, D, (long long)rows, grp, (long long)0));
+    // one pass: dx + per-chunk partials of dgamma / dbeta, then the fixed-order sum of the chunks of every row group
+    const int nch = (int)((rows + LN_CHUNK - 1) / LN_CHUNK);
+    VI_CHECK_ARG(scratch && scratch_elems >= (int64_t)2 * nch * D, "vi_add_ln_bwd: scratch too small (need 2 x ceil(rows / %d) x %d floats)",
+                 LN_CHUNK, D);
+    VI_CUDA(vi_launch(ln_bwd_fused_kernel, dim3((unsigned)nch), dim3(256), 0, ST(stream), a, b, gamma, eps, dy32,
+                      reinterpret_cast<const bf16*>(dy16), dx32, reinterpret_cast<bf16*>(dx16), stats, scratch, (long long)rows, nch, grp));
+    VI_CUDA(vi_launch(ln_param_sum_kernel, dim3(D / 256, n_groups, 2), dim3(256), 0, ST(stream), (const float*)scratch, dgamma, dbeta, nch,
+                      (long long)rows, grp, (int)(accumulate != 0)));
+  } else {
+    VI_CUDA(vi_launch(ln_bwd_dx_kernel, dim3((unsigned)((rows + 3) / 4)), dim3(128), 0, ST(stream), a, b, gamma, eps, dy32,
+                      reinterpret_cast<const bf16*>(dy16), dx32, reinterpret_cast<bf16*>(dx16), stats, (long long)rows, grp));
   }
   return VI_OK;
 }
@@ -990,6 +1130,17 @@ extern "C" int vi_infonce_loss_bwd(const float* proj, const float* tgt, const fl
   VI_CHECK_ARG(temperature > 0.f, "vi_infonce_loss_bwd: temperature must be positive");
   if (R <= 0) return VI_OK;
   VI_CUDA(vi_launch(infonce_loss_bwd_kernel, dim3((unsigned)((R + 3) / 4)), dim3(128), 0, ST(stream), proj, tgt, negs, row_episode,
-                    neg_episode, 1.0f / temperature, sims, dloss, dproj, R, n_negs));
+                    neg_episode, 1.0f / temperature, sims, dloss, dproj, R, n_negs, 0, 0.f));
+  return VI_OK;
+}
+
+extern "C" int vi_margin_loss_bwd(const float* proj, const float* tgt, const float* negs, const int32_t* row_episode,
+                                  const int32_t* neg_episode, float margin, const float* sims, const float* dloss,
+                                  float* dproj, int R, int n_negs, vi_stream_t stream) {
+  VI_CHECK_ARG(proj && tgt && row_episode && sims && dloss && dproj, "vi_margin_loss_bwd: null operand");
+  VI_CHECK_ARG(n_negs == 0 || (negs && neg_episode), "vi_margin_loss_bwd: negatives missing");
+  if (R <= 0) return VI_OK;
+  VI_CUDA(vi_launch(infonce_loss_bwd_kernel, dim3((unsigned)((R + 3) / 4)), dim3(128), 0, ST(stream), proj, tgt, negs, row_episode,
+                    neg_episode, 1.0f, sims, dloss, dproj, R, n_negs, 1, margin));
   return VI_OK;
 }

@@ -185,13 +185,11 @@ __global__ void __launch_bounds__(128) ln_dot_kernel(const float* h, const float
   ROW_INDEX();
   if (row >= rows) return;
   const int gi = group_of_row(grp, row);
-  gamma += gi * D;
-  beta += gi * D;
   w += gi * D;
   if (bias) bias += gi;
   Row r, wv;
   row_load(r, h + row * D, lane);
-  row_layernorm(r, gamma, beta, eps, lane);
+  if (gamma) row_layernorm(r, gamma + gi * D, beta + gi * D, eps, lane);       // gamma == NULL: plain dot product of the rows
   row_load(wv, w, lane);
   const float d = row_dot(r, wv);
   if (lane == 0) out[row] = d + (bias ? (*(bias)) : 0.f);
@@ -544,7 +542,7 @@ extern "C" int vi_ln_dot(const float* h, const float* gamma, const float* beta, 
                          float* out, int64_t rows, int n_groups, const int32_t* group_row_end, vi_stream_t stream) {
   RowGroups grp;
   VI_CHECK_ARG(make_groups(grp, n_groups, group_row_end, rows), "vi_ln_dot: bad row groups");
-  VI_CHECK_ARG(h && gamma && beta && w && out, "vi_ln_dot: null operand");
+  VI_CHECK_ARG(h && w && out && ((gamma != nullptr) == (beta != nullptr)), "vi_ln_dot: null operand");
   VI_CHECK_ARG(aligned16(h) && aligned16(gamma) && aligned16(beta) && aligned16(w), "vi_ln_dot: operands must be 16-byte aligned");
   if (rows <= 0) return VI_OK;
   VI_CUDA(vi_launch(ln_dot_kernel, dim3(row_grid(rows)), dim3(128), (size_t)(0), ST(stream), h, gamma, beta, eps, w, b, out, rows, grp));

@@ -194,7 +194,7 @@ def _align_forward_train(model, txt, img, rows, pk, lowp, shape):
     if txt.requires_grad:
         raise NotImplementedError('training the text encoder through the alignment loss '
                                   '(fix_lang_inside_cosine_model=False) is not on the released path')
-    if cfg.aux_loss_type not in ('cosine', 'contrastive-InfoNCE'):
+    if cfg.aux_loss_type not in ('cosine', 'contrastive-InfoNCE', 'constrastive-margin'):
         raise NotImplementedError('backward of aux_loss_type %r' % cfg.aux_loss_type)
     B, I = shape
     x = ag.GatherSlotsFn.apply(img, rows.unit, rows.slot, rows.R, lowp)
@@ -212,8 +212,12 @@ def _align_forward_train(model, txt, img, rows, pk, lowp, shape):
         negs = None
         if rows.n_negs:
             negs, _ = ops.gather_mean(txt, rows.np_off, rows.np_rows, rows.n_negs, want16=False)
-        loss = ag.InfoNCELossFn.apply(x, tgt, negs, rows.ep, rows.np_ep if rows.n_negs else None,
-                                      float(cfg.infonce_temperature), rows.R, rows.n_negs)
+        if cfg.aux_loss_type == 'constrastive-margin':        # (sic) H/models/vilmodel_cmt.py:825-856
+            loss = ag.MarginLossFn.apply(x, tgt, negs, rows.ep, rows.np_ep if rows.n_negs else None,
+                                         float(cfg.contrastive_margin_value), rows.R, rows.n_negs)
+        else:
+            loss = ag.InfoNCELossFn.apply(x, tgt, negs, rows.ep, rows.np_ep if rows.n_negs else None,
+                                          float(cfg.infonce_temperature), rows.R, rows.n_negs)
     out = ag.ScatterSlotsFn.apply(img, x, rows.slot, rows.unit)
     return loss, out.view(B, I, HIDDEN)
 
@@ -396,9 +400,9 @@ class GlocalTextPathNavCMT(nn.Module):
         LayerNorm-ed view embeddings, zero padded to the longest; everything after that is the R2R path over P = max(view_len
         + obj_len) tokens.  The ragged concatenation is one row gather over [views ; objects ; a zero row].  Inference only."""
         self._guard(view_img_fts)
-        if self._recording(view_img_fts, obj_img_fts) and not self.config.fix_pano_embedding:
-            raise NotImplementedError('fine-tuning the panorama encoder with object features (REVERIE) is not built')
         lowp, pk, ie = self.lowp, self._pk(), self.img_embeddings
+        if self._recording(view_img_fts, obj_img_fts) and not self.config.fix_pano_embedding:
+            return self._panorama_with_objects_train(view_img_fts, obj_img_fts, loc_fts, nav_types, view_lens, obj_lens)
         B, V, _ = view_img_fts.shape
         O = obj_img_fts.shape[1]
         dev = view_img_fts.device
@@ -440,6 +444,48 @@ class GlocalTextPathNavCMT(nn.Module):
             y32 = blocks.layer_norm(x32, None, pk['pano_norm'], 1e-12, False).f32
         return y32.view(B, P, HIDDEN).detach(), pano_masks
 
+    def _panorama_with_objects_train(self, view_img_fts, obj_img_fts, loc_fts, nav_types, view_lens, obj_lens):
+        """'panorama' with object boxes and autograd recording (REVERIE / SOON fine-tuning, :1096-1131): the same sequence from the
+        differentiable blocks; the ragged [views ; objects] concatenation is a row gather whose adjoint is a scatter-add."""
+        lowp, pk, ie = self.lowp, self._pk(), self.img_embeddings
+        B, V, _ = view_img_fts.shape
+        O = obj_img_fts.shape[1]
+        dev = view_img_fts.device
+        vl = [int(x) for x in view_lens.tolist()]
+        ol = [int(x) for x in obj_lens.tolist()]
+        P = max(a + b for a, b in zip(vl, ol))
+        if loc_fts.shape[1] != P or nav_types.shape[1] != P:
+            raise ValueError('loc_fts / nav_types must cover max(view_len + obj_len) = %d tokens' % P)
+        zero_row = B * V + B * O
+        idx = np.full((B, P), zero_row, np.int64)
+        for i in range(B):
+            idx[i, :vl[i]] = i * V + np.arange(vl[i])
+            idx[i, vl[i]:vl[i] + ol[i]] = B * V + i * O + np.arange(ol[i])
+        idx_d = torch.from_numpy(idx.reshape(-1)).to(dev, non_blocking=True)
+        pano_lens = (view_lens + obj_lens).to(dev)
+        pano_masks = torch.arange(P, device=dev)[None, :] < pano_lens[:, None]
+        km = blocks.mask_u8(pano_masks)
+        with blocks.grad_mode(True, self._drop()):
+            v32 = _f32c(view_img_fts).view(B * V, -1)
+            o32 = _f32c(obj_img_fts).view(B * O, -1)
+            nv = blocks.layer_norm(blocks.linear(blocks.operand(v32, lowp), pk['img_linear'], lowp, out_dtype=F32), None,
+                                   blocks.LNPack([ie.img_layer_norm]), 1e-12, False).f32
+            if ie.obj_linear is not None:                      # obj_feat_size != image_feat_size (:464-468)
+                olin, oln = pk['obj_linear'], ie.obj_layer_norm
+            else:
+                olin, oln = pk['img_linear'], ie.img_layer_norm
+            no = blocks.layer_norm(blocks.linear(blocks.operand(o32, lowp), olin, lowp, out_dtype=F32), None, blocks.LNPack([oln]),
+                                   1e-12, False).f32
+            src = torch.cat([nv, no, torch.zeros((1, HIDDEN), dtype=F32, device=dev)], 0)
+            a = ag.GatherRowsFn.apply(src, idx_d, 0, B * P)
+            x32 = blocks.embed(B * P, dev, a=a, feat=_f32c(loc_fts).view(B * P, -1), feat_lin=ie.loc_linear, feat_ln=ie.loc_layer_norm,
+                               idx=nav_types.long().contiguous().view(-1), table=ie.nav_type_embedding.weight,
+                               const_rows=(self.embeddings.token_type_embeddings.weight[1],), out_ln=ie.layer_norm, dropout=True).f32
+            for lp in pk['pano']:
+                x32 = blocks.pano_layer(x32, lp, B, P, km, lowp)
+            y32 = blocks.layer_norm(x32, None, pk['pano_norm'], 1e-12, False).f32
+        return y32.view(B, P, HIDDEN), pano_masks
+
     def forward_navigation_per_step(self, txt_embeds, txt_masks, gmap_img_embeds, gmap_step_ids, gmap_pos_fts,
                                     gmap_masks, gmap_pair_dists, gmap_visited_masks, gmap_vpids,
                                     vp_img_embeds, vp_pos_fts, vp_masks, vp_nav_masks, vp_obj_masks, vp_cand_vpids,
@@ -457,12 +503,10 @@ class GlocalTextPathNavCMT(nn.Module):
         ge, le = self.global_encoder, self.local_encoder
 
         if ctx_kv is None and self._recording(txt_embeds, gmap_img_embeds, vp_img_embeds, imagine_embeds):
-            if vp_obj_masks is not None:
-                raise NotImplementedError('fine-tuning with the object-grounding head (REVERIE) is not built')
             with blocks.grad_mode(True, self._drop()):
                 return self._navigation_train(txt_embeds, txt_masks, gmap_img_embeds, gmap_step_ids, gmap_pos_fts, gmap_masks,
                                               gmap_pair_dists, gmap_visited_masks, gmap_vpids, vp_img_embeds, vp_pos_fts,
-                                              vp_masks, vp_nav_masks, vp_cand_vpids, imagine_embeds, imagine_masks)
+                                              vp_masks, vp_nav_masks, vp_cand_vpids, imagine_embeds, imagine_masks, vp_obj_masks)
 
         # ---- input embeddings of both branches into one row-stacked activation (:1141-1152)
         (r_g, r_l), ends, R = blocks.stack_layout([B * G, B * P])
@@ -616,7 +660,7 @@ class GlocalTextPathNavCMT(nn.Module):
 
     def _navigation_train(self, txt_embeds, txt_masks, gmap_img_embeds, gmap_step_ids, gmap_pos_fts, gmap_masks,
                           gmap_pair_dists, gmap_visited_masks, gmap_vpids, vp_img_embeds, vp_pos_fts, vp_masks,
-                          vp_nav_masks, vp_cand_vpids, imagine_embeds, imagine_masks):
+                          vp_nav_masks, vp_cand_vpids, imagine_embeds, imagine_masks, vp_obj_masks=None):
         """'navigation' with autograd recording (fine-tuning, BASELINE.json cfg-4): the same layer sequence as
         forward_navigation_per_step built from the differentiable blocks; torch only concatenates / slices rows."""
         cfg, lowp, pk = self.config, self.lowp, self._pk()
@@ -671,8 +715,12 @@ class GlocalTextPathNavCMT(nn.Module):
         gl, ll, fl = ag.FuseLogitsFn.apply(raw[r_g:r_g + B * G], raw[r_l:r_l + B * P], fuse_raw, blocks.mask_u8(gmap_masks),
                                            blocks.mask_u8(gmap_visited_masks), blocks.mask_u8(vp_nav_masks), gmap_ids,
                                            cand_ids, B, G, P)
+        obj_logits = None
+        if vp_obj_masks is not None:                           # object grounding head (:1220-1225)
+            og_raw = blocks.cls_head(x.operand(lowp)[r_l:r_l + B * P], pk['og'], lowp)
+            obj_logits = og_raw.view(B, P).masked_fill(vp_obj_masks.logical_not(), float('-inf'))
         return {'gmap_embeds': gmap_out, 'vp_embeds': vp_out, 'global_logits': gl, 'local_logits': ll,
-                'fused_logits': fl, 'obj_logits': None}
+                'fused_logits': fl, 'obj_logits': obj_logits}
 
     def intern_vpids(self, gmap_vpids, vp_cand_vpids, G, P, dev):
         """Viewpoint-id strings -> int32 tensors on ``dev`` (gmap padding -1, candidate padding -2).  Callers that

@@ -100,6 +100,8 @@ class NavCMT(nn.Module):
                 im = self.imagine_embeddings
                 pk['imag_img'] = blocks.LinearPack([im.pano_img_linear.weight], [im.pano_img_linear.bias])
                 pk['imag_enc'] = [blocks.SelfFFNPack([l.attention], [l.intermediate], [l.output]) for l in im.pano_encoder.layer]
+                pk['imag_ln0'] = blocks.LNPack([im.pano_img_layer_norm])
+                pk['imag_ln1'] = blocks.LNPack([im.layer_norm])
             pk['act'] = blocks.ClsHeadPack([self.next_action], last_index=4)
             if hasattr(self, 'contrastive_alignment_model'):
                 ip = self.contrastive_alignment_model.image_proj
@@ -160,7 +162,7 @@ class NavCMT(nn.Module):
         he = self.hist_embeddings
         lowp = self.lowp
         if not self.fix_hist_embedding and self._recording(hist_img_feats) and any(p.requires_grad for p in he.parameters()):
-            raise NotImplementedError('training the history embeddings (fix_hist_embedding=False) is not on the released path')
+            return self._history_train(hist_img_feats, hist_ang_feats, ob_step_ids, hist_pano_img_feats, hist_pano_ang_feats)
         type_row = he.type_embedding.weight[0]
         ln = (he.layer_norm.weight, he.layer_norm.bias)
         if hist_img_feats is None:
@@ -208,6 +210,45 @@ class NavCMT(nn.Module):
         y32, _ = ops.add_ln(e32, pano_mean, ln[0], ln[1], 1e-12, want16=False)
         return y32.detach() if self.fix_hist_embedding else y32
 
+    def _history_train(self, hist_img_feats, hist_ang_feats, ob_step_ids, hist_pano_img_feats, hist_pano_ang_feats):
+        """'history' with autograd recording (fix_hist_embedding=False, :576-618): the same sum from the differentiable blocks;
+        nn.Dropout after the final LayerNorm (:616)."""
+        he, lowp, pk = self.hist_embeddings, self.lowp, self._pk()
+        type_row = he.type_embedding.weight[0]
+        with blocks.grad_mode(True, self._drop()):
+            if hist_img_feats is None:
+                ops.ensure_init(he.cls_token)
+                y = blocks.embed(1, he.cls_token.device, a=he.cls_token.view(1, HIDDEN), const_rows=(type_row,), out_ln=he.layer_norm,
+                                 dropout=True)
+                return y.f32
+            ops.ensure_init(hist_img_feats)
+            dev = hist_img_feats.device
+            B = hist_img_feats.shape[0]
+            a = blocks.linear(blocks.operand(_f32c(hist_img_feats), lowp), pk['hist_img'], lowp, out_dtype=F32)
+            if torch.is_tensor(ob_step_ids) and ob_step_ids.numel() == B:
+                step_idx = ob_step_ids.long().contiguous().view(-1)
+            else:
+                step = int(ob_step_ids.view(-1)[0]) if torch.is_tensor(ob_step_ids) else int(ob_step_ids)
+                step_idx = torch.full((B,), step, dtype=torch.int64, device=dev)
+            e32 = blocks.embed(B, dev, a=a, a_ln=he.img_layer_norm, feat=_f32c(hist_ang_feats), feat_lin=he.ang_linear,
+                               feat_ln=he.ang_layer_norm, idx=step_idx, table=he.position_embeddings.weight, const_rows=(type_row,)).f32
+            pano_mean = None
+            if he.pano_encoder is not None:
+                V = hist_pano_img_feats.shape[1]
+                pa = blocks.linear(blocks.operand(_f32c(hist_pano_img_feats).view(B * V, -1), lowp), pk['hist_pano_img'], lowp, out_dtype=F32)
+                x = blocks.embed(B * V, dev, a=pa, a_ln=he.pano_img_layer_norm, feat=_f32c(hist_pano_ang_feats).view(B * V, -1),
+                                 feat_lin=he.pano_ang_linear, feat_ln=he.pano_ang_layer_norm, lowp=lowp, dropout=True)
+                st = [Stream(0, B, V, None)]                  # the reference's mask is all ones (:606-607)
+                for lp in pk['hist_pano']:
+                    x = blocks.self_attn_ffn(x, lp, st, None, lowp)
+                off = torch.arange(0, B * V + 1, V, dtype=torch.int32, device=dev)
+                idx = torch.arange(B * V, dtype=torch.int32, device=dev)
+                pano_mean = ag.SegmentMeanFn.apply(x.f32, off, idx, B, V)
+            y = blocks.layer_norm(e32, pano_mean, blocks.LNPack([he.layer_norm]), 1e-12, False).f32
+            if blocks._Mode.p_hidden > 0:
+                y = ag.dropout(y, blocks._Mode.p_hidden)
+        return y
+
     def forward_imagination(self, imagine_pano_img_feats, imagine_masks=None):
         """'imagine', :1040-1048: the bypass embedding (:620-631) or the ImagineEmbeddings encoder (:634-703)."""
         ops.ensure_init(imagine_pano_img_feats)
@@ -222,16 +263,30 @@ class NavCMT(nn.Module):
 
     def _imagination_encoder(self, feats, imagine_masks):
         """ImagineEmbeddings.forward, :634-703: features + position + type embedding -> Linear + LN -> post-LN BertEncoder over
-        the imaginations of an episode (additive -10000 mask) -> LN.  Inference only."""
+        the imaginations of an episode (additive -10000 mask) -> LN."""
         im, lowp, pk = self.imagine_embeddings, self.lowp, self._pk()
         if imagine_masks is None:
             raise ValueError("mode 'imagine' needs imagine_masks when bypass_imag_encoder is off (r2r/agent_cmt.py:413-417)")
-        if self._recording(feats) and any(p.requires_grad for p in im.parameters()) and not self.fix_imagine_embeds:
-            raise NotImplementedError('fine-tuning the ImagineEmbeddings encoder (bypass_imag_encoder=False) is not built')
         B, I, _ = feats.shape
         if I >= im.position_embeddings.weight.shape[0]:
             raise ValueError('imagination length %d out of bounds (max_imagination_len %d, :683)' % (I, im.position_embeddings.weight.shape[0]))
         dev = feats.device
+        if self._recording(feats) and any(p.requires_grad for p in im.parameters()) and not self.fix_imagine_embeds:
+            # fine-tuning: the same sequence from the differentiable blocks; nn.Dropout after both LayerNorms (:686, :701)
+            with blocks.grad_mode(True, self._drop()):
+                x = blocks.embed(B * I, dev, a=_f32c(feats).view(B * I, -1), pos_table=im.position_embeddings.weight, pos_period=I,
+                                 const_rows=(im.type_embedding.weight[0],), lowp=lowp)
+                a = blocks.linear(x.operand(lowp), pk['imag_img'], lowp, out_dtype=F32)
+                x = blocks.layer_norm(a, None, pk['imag_ln0'], 1e-12, lowp)
+                if blocks._Mode.p_hidden > 0:
+                    x = blocks.as_act(ag.dropout(x.f32, blocks._Mode.p_hidden), lowp)
+                st = [Stream(0, B, I, blocks.mask_u8(imagine_masks))]
+                for lp in pk['imag_enc']:
+                    x = blocks.self_attn_ffn(x, lp, st, None, lowp)
+                out = blocks.layer_norm(x.f32, None, pk['imag_ln1'], 1e-12, False).f32
+                if blocks._Mode.p_hidden > 0:
+                    out = ag.dropout(out, blocks._Mode.p_hidden)
+            return out.view(B, I, HIDDEN)
         x32, x16 = ops.embed_compose(B * I, dev, a=_f32c(feats).view(B * I, -1), pos_table=im.position_embeddings.weight, pos_period=I,
                                      const_row=im.type_embedding.weight[0], want16=lowp, want32=not lowp)
         w, b = pk['imag_img'].get(lowp)
@@ -263,9 +318,6 @@ class NavCMT(nn.Module):
         Il, Iv = (0, I) if on_visn else (I, 0)
         C, Nv = L + Il, T + O + Iv
         if self._recording(txt_embeds, hist_embeds, ob_img_feats, imagine_embeds):
-            if on_visn or cfg.act_pred_token not in ('ob_txt', 'ob'):
-                raise NotImplementedError("fine-tuning with concat_imagine_with='visual' or act_pred_token=%r is not built"
-                                          % cfg.act_pred_token)
             with blocks.grad_mode(True, self._drop()):
                 return self._visual_train(txt_embeds, txt_masks, hist_embeds, hist_masks, ob_img_feats, ob_ang_feats,
                                           ob_nav_types, ob_masks, imagine_embeds, imagine_masks)
@@ -359,9 +411,10 @@ class NavCMT(nn.Module):
         dev = txt_embeds.device
         B, L, _ = txt_embeds.shape
         T, O = hist_embeds.shape[1], ob_img_feats.shape[1]
-        Nv = T + O
         I = imagine_embeds.shape[1] if cfg.imagine_enc_pano else 0
-        C = L + I
+        on_visn = bool(I) and cfg.concat_imagine_with == 'visual'      # :1106-1112
+        Il, Iv = (0, I) if on_visn else (I, 0)
+        C, Nv = L + Il, T + O + Iv
         (r_l, r_v), ends, R = blocks.stack_layout([B * C, B * Nv])
         ie = self.img_embeddings
         o32 = _f32c(ob_img_feats).view(B * O, -1)
@@ -371,14 +424,14 @@ class NavCMT(nn.Module):
                           const_rows=(self.embeddings.token_type_embeddings.weight[1],), out_ln=ie.layer_norm, dropout=True).f32
         if self.fix_obs_embedding:
             ob = ob.detach()
-        lang = torch.cat([_f32c(txt_embeds), _f32c(imagine_embeds)], 1) if I else _f32c(txt_embeds)
-        visn = torch.cat([_f32c(hist_embeds), ob.view(B, O, HIDDEN)], 1)
+        lang = torch.cat([_f32c(txt_embeds), _f32c(imagine_embeds)], 1) if Il else _f32c(txt_embeds)
+        visn = torch.cat([_f32c(hist_embeds), ob.view(B, O, HIDDEN)] + ([_f32c(imagine_embeds)] if Iv else []), 1)
         parts = [lang.reshape(B * C, HIDDEN)]
         if ends[0] > B * C:
             parts.append(torch.zeros((ends[0] - B * C, HIDDEN), dtype=F32, device=dev))
         x = blocks.as_act(torch.cat(parts + [visn.reshape(B * Nv, HIDDEN)], 0), lowp)
-        lang_mask = blocks.mask_u8(torch.cat([txt_masks.bool(), imagine_masks.bool()], 1) if I else txt_masks)
-        visn_mask = blocks.mask_u8(torch.cat([hist_masks.bool(), ob_masks.bool()], 1))
+        lang_mask = blocks.mask_u8(torch.cat([txt_masks.bool(), imagine_masks.bool()], 1) if Il else txt_masks)
+        visn_mask = blocks.mask_u8(torch.cat([hist_masks.bool(), ob_masks.bool()] + ([imagine_masks.bool()] if Iv else []), 1))
         streams = [Stream(r_l, B, C, lang_mask, 0), Stream(r_v, B, Nv, visn_mask, 1)]
         for cp, sp in zip(pk['x_cross'], pk['x_self']):
             # bidirectional cross-attention with shared weights, both directions read the layer inputs (:385-397)
@@ -392,11 +445,26 @@ class NavCMT(nn.Module):
             x = blocks.self_attn_ffn(x, sp, streams, ends, lowp)
         lang_out = x.f32[r_l:r_l + B * C].view(B, C, HIDDEN)
         visn_out = x.f32[r_v:r_v + B * Nv].view(B, Nv, HIDDEN)
-        txt_out, hist_out, ob_out = lang_out[:, :L], visn_out[:, :T], visn_out[:, T:]
-        if cfg.act_pred_token == 'ob_txt':                     # :1191
-            h = ag.MulBcastFn.apply(ob_out, lang_out[:, 0], lowp)
-        else:
+        txt_out, hist_out, ob_out = lang_out[:, :L], visn_out[:, :T], visn_out[:, T:T + O]      # :1173-1182
+        tok = cfg.act_pred_token                               # :1189-1199
+        if tok == 'ob':
             h = blocks.operand(ob_out.reshape(B * O, HIDDEN), lowp)
+        else:
+            if tok == 'ob_txt':
+                gate = lang_out[:, 0]
+            elif tok == 'ob_hist':
+                gate = visn_out[:, 0]
+            elif tok == 'ob_txt_hist':
+                gate = ag.SumRowsFn.apply(2, lang_out[:, 0].contiguous(), visn_out[:, 0].contiguous())
+            elif tok == 'ob_imagine_text':                     # txt[:, :1] + mean over ALL imagination output tokens (unmasked)
+                row0, per = (r_v + T + O, Nv) if on_visn else (r_l + L, C)
+                idx = (row0 + torch.arange(B, device=dev)[:, None] * per + torch.arange(I, device=dev)[None, :]).reshape(-1).to(torch.int32)
+                off = torch.arange(0, B * I + 1, I, dtype=torch.int32, device=dev)
+                mean = ag.SegmentMeanFn.apply(x.f32, off, idx, B, I)
+                gate = ag.SumRowsFn.apply(2, lang_out[:, 0].contiguous(), mean)
+            else:
+                raise NotImplementedError('act_pred_token %r' % tok)
+            h = ag.MulBcastFn.apply(ob_out, gate, lowp)
         raw = blocks.cls_head(h, pk['act'], lowp)
         act_logits = raw.view(B, O).masked_fill(ob_nav_types.view(B, O) == 0, float('-inf'))
         return act_logits, txt_out, hist_out, ob_out

@@ -471,6 +471,16 @@ def infonce_loss_with_sims(proj, tgt, negs, row_episode, neg_episode, temperatur
     return loss, scratch
 
 
+def margin_loss_with_sims(proj, tgt, negs, row_episode, neg_episode, margin: float, R: int, n_negs: int, device):
+    """margin_loss that also hands back the forward scratch (its first R * (n_negs + 1) floats are the cosines)."""
+    loss = torch.empty((), dtype=F32, device=device)
+    scratch = torch.empty((max(R, 1) * (n_negs + 2),), dtype=F32, device=device)
+    check(lib.vi_margin_loss(_ptr(proj), _ptr(tgt), _ptr(negs), _ptr(row_episode), _ptr(neg_episode), margin,
+                             scratch.data_ptr(), loss.data_ptr(), R, n_negs, _stream()), 'vi_margin_loss')
+    _launched(3)
+    return loss, scratch
+
+
 def copy_rows(src: torch.Tensor, src_bs: int, src_rs: int, n_batches: int, rows_per_batch: int,
               dst32: Optional[torch.Tensor], dst16: Optional[torch.Tensor], dst_bs: int, dst_rs: int):
     """dst[b, r] = src[b, r] over 768-wide rows with element strides (see vi_copy_rows)."""

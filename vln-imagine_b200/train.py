@@ -80,11 +80,13 @@ def teacher_targets(gmap_masks: torch.Tensor, gmap_visited_masks: torch.Tensor) 
 
 
 def duet_finetune_iteration(model, ep: dict, n_steps: int = 1, cosine_weight: float = 0.5, ml_weight: float = 1.0,
-                            backward: bool = True):
+                            backward: bool = True, fused_accumulation: bool = False):
     """One imitation-learning iteration of the reference agent on a batch of episodes (r2r/agent.py:384-623):
     language + imagine + align once, then ``n_steps`` navigation steps (panorama -> navigation -> summed
     cross-entropy on the fused logits), loss = ml_weight * CE / B + cosine_weight * aux.  ``model`` is the drop-in
-    VLNBert; ``ep`` holds device tensors (vln-imagine_b200/synth.py layout).  Returns (loss, ce, aux, last nav dict)."""
+    VLNBert; ``ep`` holds device tensors (vln-imagine_b200/synth.py layout).  Returns (loss, ce, aux, last nav dict).
+    ``fused_accumulation``: the per-step parameter gradients are summed inside the backward kernels instead of by one autograd
+    ``add`` per parameter per step (autograd_ops.fused_grad_accumulation); same .grad at the end, not for DDP-wrapped modules."""
     B = ep['txt_ids'].shape[0]
     txt = model('language', {'txt_ids': ep['txt_ids'], 'txt_masks': ep['txt_masks']})
     img = model('imagine', {'imagine_feats': ep['imagine_feats'], 'imagine_masks': None})
@@ -108,7 +110,9 @@ def duet_finetune_iteration(model, ep: dict, n_steps: int = 1, cosine_weight: fl
         ce = step_ce if ce is None else ce + step_ce
     loss = ce * (ml_weight / B) + cosine_weight * aux
     if backward:
-        loss.backward()
+        from . import autograd_ops as ag
+        with ag.fused_grad_accumulation(fused_accumulation):
+            loss.backward()
     return loss, ce / B, aux, nav
 
 
