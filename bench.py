@@ -629,7 +629,7 @@ def run_train(args, shape, desc, rank, local_rank, world):
         'gpu_launches': launches * K,
         'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': achieved / peak_tf,
                      'traffic': None, 'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained' if peaks else 'fallback',
-                     'kernel': 'gemm_bf16_tc_kernel (tcgen05): %d launches/iteration (forward, dgrad, wgrad), %.1f GFLOP executed, '
+                     'kernel': 'gemm_bf16_tc_kernel + wgrad_tc_kernel (tcgen05): %d launches/iteration (forward, dgrad | wgrad incl. its split reduction), %.1f GFLOP executed, '
                                '%.3f ms of GEMM time' % (r['n_gemm'], gemm_flops / 1e9, gemm_ms)},
         'allreduce': {'ms': r['allreduce_ms'], 'bytes': r['allreduce_bytes'], 'busbw_gbs': r['allreduce_busbw_gbs']},
         'loss_finite': r['loss_finite'],

@@ -589,6 +589,76 @@ def test_attention_tcgen05_multi_problem(ops, fmt):
         assert bool((out[B * La:ra].float() == 7.0).all())
 
 
+SP_ATTN_CASES = [c for c in TC_ATTN_CASES if c[2] <= 96] + [(64, 37, 85, True, False, False), (3, 50, 96, True, True, False),
+                                                            (2, 40, 81, True, True, True), (2, 17, 1, False, False, False)]
+
+
+@pytest.mark.parametrize('B,Lq,Lk,masked,gasa,neg_inf', SP_ATTN_CASES)
+@pytest.mark.parametrize('fmt', [torch.bfloat16, torch.float16])
+def test_attention_single_pass(ops, B, Lq, Lk, masked, gasa, neg_inf, fmt, monkeypatch):
+    """attn_fwd_sp_kernel (the default for <= 96 keys without dropout / lse: exactly unrolled key blocks, one softmax pass in the
+    log2 domain) against the fp32 reference and against the generic kernel (VI_ATTN_SP=0) on the same inputs"""
+    qkv_q = _rand(B * Lq, 2304, seed=1).to(fmt)
+    qkv_k = _rand(B * Lk, 2304, seed=2).to(fmt)
+    q, k, v = qkv_q[:, :768], qkv_k[:, 768:1536], qkv_k[:, 1536:]
+    key_mask = None
+    if masked:
+        g = torch.Generator().manual_seed(3)
+        lens = torch.randint(1, Lk + 1, (B,), generator=g)
+        lens[0] = Lk
+        key_mask = (torch.arange(Lk)[None] < lens[:, None]).to(torch.uint8).cuda()
+        if Lk > 4:
+            key_mask[-1, 1] = 0
+    pair_dist = affine = None
+    if gasa:
+        pair_dist = (_rand(B, Lq, Lk, seed=4).abs() * 10).contiguous()
+        affine = torch.tensor([-0.5, 0.1], device='cuda')
+    mode = ops.MASK_NEG_INF if neg_inf else ops.MASK_ADD_NEG10000
+    prob = dict(q=q, k=k, v=v, B=B, Lq=Lq, Lk=Lk, key_mask=key_mask, pair_dist=pair_dist, bias_affine=affine)
+    o = torch.full((B * Lq + 3, 768), 7.0, dtype=fmt, device='cuda')
+    ops.attention_multi([dict(prob, out=o[:B * Lq])], mask_mode=mode)
+    monkeypatch.setenv('VI_ATTN_SP', '0')
+    o_gen = torch.empty((B * Lq, 768), dtype=fmt, device='cuda')
+    ops.attention_multi([dict(prob, out=o_gen)], mask_mode=mode)
+    ref, _ = _attn_ref(q, k, v, B, Lq, Lk, key_mask, pair_dist, affine, neg_inf)
+    tol = 1.5e-2 if fmt == torch.bfloat16 else 2.5e-3
+    assert relerr(o[:B * Lq], ref) < tol
+    assert relerr(o[:B * Lq], o_gen) < tol / 3            # the two kernels differ in fp32 association only
+    assert bool((o[B * Lq:].float() == 7.0).all())
+
+
+@pytest.mark.parametrize('fmt', [torch.bfloat16, torch.float16])
+def test_attention_single_pass_multi_problem(ops, fmt):
+    """both token streams of a row-stacked activation in one launch through the default dispatcher (single-pass kernel): key-block
+    counts differ per problem (30 -> 2 blocks, 37 -> 3, 85 -> 6); padding rows stay untouched"""
+    B = 16
+    for (La, Lb, Lka, Lkb, gasa) in ((30, 37, 85, 85, False), (30, 37, 30, 37, True), (85, 53, 53, 85, False)):
+        ra = (B * La + 255) // 256 * 256
+        R = ra + B * Lb
+        x = _rand(R, 2304, seed=5).to(fmt)
+        ctx = _rand(B * 85, 3072, seed=6).to(fmt)
+        out = torch.full((R, 768), 7.0, device='cuda', dtype=fmt)
+        ga, gb = torch.Generator().manual_seed(1), torch.Generator().manual_seed(2)
+        ma = (torch.arange(Lka)[None] < torch.randint(1, Lka + 1, (B,), generator=ga)[:, None]).to(torch.uint8).cuda()
+        mb = (torch.arange(Lkb)[None] < torch.randint(1, Lkb + 1, (B,), generator=gb)[:, None]).to(torch.uint8).cuda()
+        dist = (_rand(B, La, Lka, seed=7).abs() * 10).contiguous() if gasa else None
+        aff = torch.tensor([-0.3, 0.05], device='cuda') if gasa else None
+        if Lka == 85 and Lkb == 85:
+            ka, va, kb, vb = ctx[:, :768], ctx[:, 768:1536], ctx[:, 1536:2304], ctx[:, 2304:]
+        elif gasa:
+            ka, va, kb, vb = x[:B * La, 768:1536], x[:B * La, 1536:], x[ra:, 768:1536], x[ra:, 1536:]
+        else:
+            ka, va, kb, vb = x[ra:, 768:1536], x[ra:, 1536:], x[:B * La, 768:1536], x[:B * La, 1536:]
+        pa = dict(q=x[:B * La, :768], k=ka, v=va, out=out[:B * La], B=B, Lq=La, Lk=Lka, key_mask=ma, pair_dist=dist, bias_affine=aff)
+        pb = dict(q=x[ra:, :768], k=kb, v=vb, out=out[ra:], B=B, Lq=Lb, Lk=Lkb, key_mask=mb)
+        ops.attention_multi([pa, pb])
+        refa, _ = _attn_ref(pa['q'], ka, va, B, La, Lka, ma, dist, aff, False)
+        refb, _ = _attn_ref(pb['q'], kb, vb, B, Lb, Lkb, mb, None, None, False)
+        tol = 1.5e-2 if fmt == torch.bfloat16 else 2.5e-3
+        assert relerr(out[:B * La], refa) < tol and relerr(out[ra:], refb) < tol
+        assert bool((out[B * La:ra].float() == 7.0).all())
+
+
 @pytest.mark.parametrize('B,Lq,Lk,masked,gasa,neg_inf', [(8, 30, 30, True, True, False), (8, 37, 85, True, False, False),
                                                           (4, 36, 36, True, False, True), (2, 130, 300, True, False, False)])
 def test_attention_fp16_operands(ops, B, Lq, Lk, masked, gasa, neg_inf):

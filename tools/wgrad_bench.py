@@ -49,7 +49,7 @@ for name, M, ends, N, K in (('nav proj 768x768', 4416, [2048, 4416], 768, 768), 
     bounds = ends or [M]
     G = len(bounds)
     rows = _lib.int_array([b - (bounds[i - 1] if i else 0) for i, b in enumerate(bounds)])
-    S0 = int(lib.vi_wgrad16_splits(N, K, G, rows))
+    S0 = int(_lib.lib.vi_wgrad16_splits(N, K, G, rows))
     dW, db = torch.empty(G * N, K, device=dev), torch.empty(G * N, device=dev)
     rec = {'gflop': round(2e-9 * M * N * K, 1), 'auto_splits': S0}
     cand = sorted({S0, 1, 2, 3, 4, 6, 8, 12}) if '--splits' in sys.argv else [S0]

@@ -157,8 +157,8 @@ def wgrad16(dy16: torch.Tensor, x16: torch.Tensor, ends, want_db: bool, out=None
     bounds = [min(int(e), M) for e in ends] if ends is not None else [M]
     G = len(bounds)
     rows = _lib.int_array([b - (bounds[i - 1] if i else 0) for i, b in enumerate(bounds)])
-    S = int(lib.vi_wgrad16_splits(N, K, G, rows))
-    need = int(lib.vi_wgrad16_workspace(N, K, G, rows, S))
+    S = int(_lib.lib.vi_wgrad16_splits(N, K, G, rows))               # host-side queries: not launches
+    need = int(_lib.lib.vi_wgrad16_workspace(N, K, G, rows, S))
     ws = None
     if need > 0:
         ws = _WGRAD_WS.get(dy16.device)
@@ -170,9 +170,16 @@ def wgrad16(dy16: torch.Tensor, x16: torch.Tensor, ends, want_db: bool, out=None
     else:
         dW = torch.empty((G * N, K), dtype=F32, device=dy16.device)
         db = torch.empty((G * N,), dtype=F32, device=dy16.device) if want_db else None
+    tr = ops._Counters.gemm_trace                                    # bench.py: tensor-core launches with their FLOPs
+    if tr is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     check(lib.vi_wgrad16(dy16.data_ptr(), dy16.stride(0), x16.data_ptr(), x16.stride(0), ops._DT[dy16.dtype], N, K, G,
                          _lib.int_array(bounds), dW.data_ptr(), _ptr(db), _ptr(ws), ws.numel() if ws is not None else 0, S,
                          int(accumulate), _stream()), 'vi_wgrad16')
+    if tr is not None:
+        e1.record()
+        tr.append((bounds[-1], N, K, e0, e1))
     _launched(2 if S > 1 else 1)
     return dW, db
 

@@ -113,40 +113,89 @@ __global__ void __launch_bounds__(128) add_ln_kernel(const float* a, const float
   row_store(r, y32, y16, row, lane, f16 != 0);
 }
 
-// 8 warps per CTA, one row per warp per iteration, CTAs stride over the rows.  The small feature projection
-// (feat_dim <= 16) reads its weight matrix from a transposed shared-memory copy [feat_dim][768] that the CTA
-// loads once, so a row costs feat_dim conflict-free float4 reads per 4 outputs instead of strided global loads.
+// 8 warps per CTA, one row per warp per iteration, CTAs stride over the rows.  Everything a row needs PER COLUMN - the
+// transposed weight of the small feature projection (feat_dim <= 16) and up to eleven 768-wide vectors (LayerNorm gains / biases,
+// the feature bias, constant rows) - is staged in shared memory once per CTA, so the only global loads of a row are the row
+// itself, its feature scalars and its table rows; they are all issued at the top of the row and the feature projection (shared
+// memory + FMAs) runs under their latency.  (Round 1 re-read every vector from global memory per row and staged the weight
+// with feat_dim-way bank conflicts: 14 - 19 us per launch at 2 % of the HBM roofline; ncu showed 1800 instructions per row and
+// long-scoreboard stalls.)
 constexpr int EMBED_WARPS = 8;
+enum { EV_A_G = 0, EV_A_B, EV_F_BIAS, EV_F_G, EV_F_B, EV_O_G, EV_O_B, EV_L2_G, EV_L2_B, EV_C1, EV_C2, EV_COUNT };
+
+__device__ __forceinline__ void row_load_s(Row& r, const float* s, int lane) {       // from shared memory
+  const float4* s4 = reinterpret_cast<const float4*>(s);
+#pragma unroll
+  for (int j = 0; j < V4; ++j) {
+    const float4 t = s4[lane + 32 * j];
+    r.v[4 * j] = t.x; r.v[4 * j + 1] = t.y; r.v[4 * j + 2] = t.z; r.v[4 * j + 3] = t.w;
+  }
+}
+// in-place LayerNorm with the gain / bias vectors in shared memory
+__device__ __forceinline__ void row_layernorm_s(Row& r, const float* gamma, const float* beta, float eps, int lane) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < V4 * 4; ++i) s += r.v[i];
+  const float mean = warp_sum(s) * (1.0f / D);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < V4 * 4; ++i) { const float d = r.v[i] - mean; q = fmaf(d, d, q); }
+  const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + eps);
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(beta);
+#pragma unroll
+  for (int j = 0; j < V4; ++j) {
+    const float4 g = g4[lane + 32 * j], b = b4[lane + 32 * j];
+    r.v[4 * j] = (r.v[4 * j] - mean) * rstd * g.x + b.x;
+    r.v[4 * j + 1] = (r.v[4 * j + 1] - mean) * rstd * g.y + b.y;
+    r.v[4 * j + 2] = (r.v[4 * j + 2] - mean) * rstd * g.z + b.z;
+    r.v[4 * j + 3] = (r.v[4 * j + 3] - mean) * rstd * g.w + b.w;
+  }
+}
+
 __global__ void __launch_bounds__(EMBED_WARPS * 32) embed_compose_kernel(const vi_embed_args p) {
   pdl_enter();
-  extern __shared__ __align__(16) float wT[];
+  extern __shared__ __align__(16) float esm[];
+  float* vec = esm;                                    // [EV_COUNT][768]
+  float* wT = esm + EV_COUNT * D;                      // [feat_dim][768]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (p.feat) {
-    const int n = D * p.feat_dim;
-    for (int i = threadIdx.x; i < n; i += EMBED_WARPS * 32) {
-      const int c = i / p.feat_dim, k = i - c * p.feat_dim;
-      wT[k * D + c] = (*(p.feat_w + i));
+  {
+    const float* src[EV_COUNT] = {p.a_gamma, p.a_beta, p.feat_b, p.feat_gamma, p.feat_beta, p.out_gamma, p.out_beta,
+                                  p.ln2_gamma, p.ln2_beta, p.const_row, p.const_row2};
+#pragma unroll
+    for (int v = 0; v < EV_COUNT; ++v) {
+      if (src[v]) {
+        for (int i = threadIdx.x; i < D / 4; i += EMBED_WARPS * 32)
+          reinterpret_cast<float4*>(vec + v * D)[i] = *(reinterpret_cast<const float4*>(src[v]) + i);
+      } else if (v == EV_F_BIAS) {
+        for (int i = threadIdx.x; i < D / 4; i += EMBED_WARPS * 32) reinterpret_cast<float4*>(vec + v * D)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    if (p.feat) {
+      // transposed copy: consecutive threads take consecutive columns of one k (conflict-free stores; the strided global
+      // reads of the 21 - 43 KB weight hit L1 / L2)
+      for (int i = threadIdx.x; i < D * p.feat_dim; i += EMBED_WARPS * 32) {
+        const int k = i / D, c = i - k * D;
+        wT[i] = *(p.feat_w + c * p.feat_dim + k);
+      }
     }
     __syncthreads();
   }
   for (long long row = (long long)blockIdx.x * EMBED_WARPS + warp; row < p.rows; row += (long long)gridDim.x * EMBED_WARPS) {
+    // ---- every global load of the row is issued here
+    Row a, tb;
+    float fv = 0.f;
+    if (p.feat && lane < p.feat_dim) fv = *(p.feat + row * p.feat_dim + lane);
+    if (p.a) row_load(a, p.a + row * D, lane);
+    if (p.idx) row_load(tb, p.table + p.idx[row] * D, lane);
     Row acc;
     row_zero(acc);
-    if (p.a) {
-      Row t;
-      row_load(t, p.a + row * D, lane);
-      if (p.a_gamma) row_layernorm(t, p.a_gamma, p.a_beta, p.eps, lane);
-      row_acc(acc, t);
-    }
-    if (p.a2) row_add(acc, p.a2 + row * D, lane);
-    if (p.a3) row_add(acc, p.a3 + row * D, lane);
+    // ---- feature projection from shared memory (runs under the loads above)
     if (p.feat) {
       Row t;
-      if (p.feat_b) row_load(t, p.feat_b, lane);
-      else row_zero(t);
-      const float* fr = p.feat + row * p.feat_dim;
+      row_load_s(t, vec + EV_F_BIAS * D, lane);
       for (int k = 0; k < p.feat_dim; ++k) {
-        const float f = (*(fr + k));
+        const float f = __shfl_sync(0xffffffffu, fv, k);
         const float4* w4 = reinterpret_cast<const float4*>(wT + k * D);
 #pragma unroll
         for (int j = 0; j < V4; ++j) {
@@ -157,19 +206,25 @@ __global__ void __launch_bounds__(EMBED_WARPS * 32) embed_compose_kernel(const v
           t.v[4 * j + 3] = fmaf(f, w.w, t.v[4 * j + 3]);
         }
       }
-      if (p.feat_gamma) row_layernorm(t, p.feat_gamma, p.feat_beta, p.eps, lane);
+      if (p.feat_gamma) row_layernorm_s(t, vec + EV_F_G * D, vec + EV_F_B * D, p.eps, lane);
       row_acc(acc, t);
     }
-    if (p.idx) row_add(acc, p.table + p.idx[row] * D, lane);
+    if (p.a) {
+      if (p.a_gamma) row_layernorm_s(a, vec + EV_A_G * D, vec + EV_A_B * D, p.eps, lane);
+      row_acc(acc, a);
+    }
+    if (p.a2) row_add(acc, p.a2 + row * D, lane);
+    if (p.a3) row_add(acc, p.a3 + row * D, lane);
+    if (p.idx) row_acc(acc, tb);
     if (p.pos_table) row_add(acc, p.pos_table + (row % p.pos_period) * D, lane);
-    if (p.const_row) row_add(acc, p.const_row, lane);
-    if (p.const_row2) row_add(acc, p.const_row2, lane);
-    if (p.out_gamma) row_layernorm(acc, p.out_gamma, p.out_beta, p.eps, lane);
+    if (p.const_row) { Row c; row_load_s(c, vec + EV_C1 * D, lane); row_acc(acc, c); }
+    if (p.const_row2) { Row c; row_load_s(c, vec + EV_C2 * D, lane); row_acc(acc, c); }
+    if (p.out_gamma) row_layernorm_s(acc, vec + EV_O_G * D, vec + EV_O_B * D, p.eps, lane);
     if (p.ln2_gamma) {
       // a second LayerNorm chained on the result (norm1 of the first panorama layer, D/models/transformer.py:171): the fp32
       // output keeps the first result (the residual stream), the 16-bit output is the operand of the next contraction
       if (p.y32) row_store(acc, p.y32, nullptr, row, lane);
-      row_layernorm(acc, p.ln2_gamma, p.ln2_beta, p.ln2_eps, lane);
+      row_layernorm_s(acc, vec + EV_L2_G * D, vec + EV_L2_B * D, p.ln2_eps, lane);
       row_store(acc, nullptr, reinterpret_cast<bf16*>(p.y16), row, lane, p.y16_dtype == VI_DT_F16);
       continue;
     }
@@ -531,8 +586,13 @@ extern "C" int vi_embed_compose(const vi_embed_args* args, vi_stream_t stream) {
   if (p.rows <= 0) return VI_OK;
   long long blocks = (p.rows + EMBED_WARPS - 1) / EMBED_WARPS;
   const long long cap = 2LL * vi_num_sms();
-  if (p.feat && blocks > cap) blocks = cap;          // amortise the weight staging over several rows per warp
-  const size_t smem = p.feat ? (size_t)p.feat_dim * D * sizeof(float) : 0;
+  if (blocks > cap) blocks = cap;                    // amortise the staging of the per-column vectors over several rows per warp
+  const size_t smem = ((size_t)EV_COUNT + (p.feat ? (size_t)p.feat_dim : 0)) * D * sizeof(float);
+  static bool attr_set = false;                      // idempotent; races only repeat the same call
+  if (!attr_set) {
+    VI_CUDA(cudaFuncSetAttribute(embed_compose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((EV_COUNT + 16) * D * sizeof(float))));
+    attr_set = true;
+  }
   VI_CUDA(vi_launch(embed_compose_kernel, dim3((unsigned)blocks), dim3(EMBED_WARPS * 32), (size_t)(smem), ST(stream), p));
   VI_LAUNCH_CHECK();
   return VI_OK;
