@@ -176,7 +176,7 @@ typedef struct {
   const float* a_beta;
   const float* feat;         /* [rows, feat_dim] small geometric features or NULL (feat_dim <= 16) */
   int32_t feat_dim;
-  const float* feat_w;       /* [768, feat_dim] */
+  const float* feat_w;       /* [feat_dim, 768]: the TRANSPOSE of nn.Linear(feat_dim, 768).weight (16-byte aligned) */
   const float* feat_b;       /* [768] */
   const float* feat_gamma;   /* LayerNorm over the projected features (NULL: none) */
   const float* feat_beta;
@@ -198,6 +198,8 @@ typedef struct {
   const float* ln2_gamma;    /* optional second LayerNorm chained on the result: y32 keeps the first result, y16 = LN2(y32) */
   const float* ln2_beta;     /* (norm1 of the first pre-norm panorama layer, D/models/transformer.py:171) */
   float ln2_eps;
+  int64_t zero_rows;         /* rows [rows, rows + zero_rows) of y32 / y16 are zero-filled (the padding up to the next stream of a
+                              * row-stacked activation: it flows through the following GEMMs and must stay finite) */
 } vi_embed_args;
 int vi_embed_compose(const vi_embed_args* args, vi_stream_t stream);
 
@@ -316,6 +318,17 @@ int vi_add_ln_bwd_acc(const float* a, const float* b, const float* gamma, float 
                       float* dx32, void* dx16, float* dgamma, float* dbeta, float* stats, int64_t rows,
                       int n_groups, const int32_t* group_row_end, float* scratch, int64_t scratch_elems, int accumulate,
                       vi_stream_t stream);
+/* LN(dropout(a) + b) and its adjoint: the hidden dropout of BertSelfOutput / BertOutput (D/models/vilmodel.py:151-155,190-194)
+ * applied inside the LayerNorm kernels (mask of vi_dropout for a [rows, 768] tensor at `site`).  Backward: dx32 / dx16 = gradient
+ * of b; dxa16 (optional, bf16) = dropout(dx) = gradient of a, the operand of the dense layer's gradient GEMMs - no separate
+ * dropout or cast pass.  p == 0: no dropout (dxa16 = the 16-bit copy of dx). */
+int vi_add_ln_drop(const float* a, const float* b, const float* gamma, const float* beta, float eps, float* y32, void* y16,
+                   int y16_dtype, int64_t rows, int n_groups, const int32_t* group_row_end, float p, const uint32_t* seed,
+                   uint32_t site, vi_stream_t stream);
+int vi_add_ln_drop_bwd(const float* a, const float* b, const float* gamma, float eps, const float* dy32, const void* dy16,
+                       float* dx32, void* dx16, void* dxa16, float* dgamma, float* dbeta, float* stats, int64_t rows,
+                       int n_groups, const int32_t* group_row_end, float* scratch, int64_t scratch_elems, int accumulate,
+                       float p, const uint32_t* seed, uint32_t site, vi_stream_t stream);
 /* small-feature linear of vi_embed_compose: dW[768, feat_dim] = dt^T feat, db[768] = colsum(dt) */
 int vi_feat_wgrad(const float* dt, const float* feat, int feat_dim, float* dW, float* db, int64_t rows, float* scratch,
                   int64_t scratch_elems, vi_stream_t stream);

@@ -127,7 +127,11 @@ def check_gradients(net, gold, names, precision, label):
         assert np.median(elem) < NOISE_MARGIN * ac['elem_median'] and elem.max() < NOISE_MARGIN * ac['elem_max']
         assert 1.0 - cos < NOISE_MARGIN * (1.0 - ac['cosine'])
         norm_tol = max(tol, NOISE_MARGIN * ac['norm_max'])
-        bad = [w for w in worst if w[3] >= (BF16_SCALAR_NORM if w[1].endswith('sprel_linear.weight') else norm_tol)]
+        # the scalar GASA slope: 0.35, or NOISE_MARGIN x the relative error the reference's own autocast run shows on it when that is
+        # larger (DUET cfg-1: the autocast run gets the SIGN wrong, relative error 2.1)
+        scalar_tol = {k[len('autocast_scalar::'):]: max(BF16_SCALAR_NORM, NOISE_MARGIN * float(v)) for k, v in gold.items()
+                      if k.startswith('autocast_scalar::')}
+        bad = [w for w in worst if w[3] >= (scalar_tol.get(w[1], BF16_SCALAR_NORM) if w[1].endswith('sprel_linear.weight') else norm_tol)]
         assert not bad, '%d of %d parameter norms outside tolerance: %s' % (len(bad), len(worst), bad[:8])
 
 

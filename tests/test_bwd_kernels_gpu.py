@@ -482,6 +482,54 @@ def test_dropout_mask_and_backward(ag, dtype):
     assert 0.3 < float(((y3 != 0) == (y.detach() != 0)).float().mean()) < 0.75
 
 
+@pytest.mark.parametrize('p', [0.0, 0.2])
+@pytest.mark.parametrize('grouped', [False, True])
+@pytest.mark.parametrize('fused_acc', [False, True])
+def test_dense_residual_layernorm_node(ag, blocks, p, grouped, fused_acc):
+    """DenseResLNFn: LN(dropout(x W^T + b) + res) as one autograd node with the dropout mask applied inside the LayerNorm kernels
+    (vi_add_ln_drop / vi_add_ln_drop_bwd emit dropout(dx) as the 16-bit operand of the gradient GEMMs) against torch autograd with
+    the SAME mask rebuilt from the hash; K = 768 and 3072, one and two row groups, with and without in-kernel accumulation"""
+    for K in (768, 3072):
+        ends = [256, 600] if grouped else None
+        rows, G = 600, (2 if grouped else 1)
+        lins = [_Lin(768, K, 70 + 2 * i) for i in range(G)]
+        lns = [_LN(80 + 2 * i) for i in range(G)]
+        pk = blocks.LinearPack([l.weight for l in lins], [l.bias for l in lins], n_groups=G)
+        lnp = blocks.LNPack(lns)
+        x = _rand(rows, K, seed=90).bfloat16().requires_grad_()
+        res = _rand(rows, 768, seed=91).requires_grad_()
+        for t in [x, res] + [q for l in lins for q in (l.weight, l.bias)] + [q for l in lns for q in (l.weight, l.bias)]:
+            t.grad = None
+        ag._DropState.site = 500
+        with ag.fused_grad_accumulation(fused_acc):
+            y32, y16 = ag.dense_res_ln(x, res, pk, lnp, 1e-12, ends, p)
+            site = ag._DropState.site
+            w32, w16 = _rand(rows, 768, seed=92), _rand(rows, 768, seed=93).bfloat16()
+            ((y32 * w32).sum() + (y16.float() * w16.float()).sum()).backward()
+        seed = int(ag.dropout_seed(x.device).item()) & M32
+        keep = _keep_mask(torch.arange(rows * 768, device='cuda', dtype=torch.int64), seed, site, p).view(rows, 768) if p > 0 else \
+            torch.ones(rows, 768, dtype=torch.bool, device='cuda')
+        xr, rr = x.detach().float().requires_grad_(), res.detach().clone().requires_grad_()
+        refs, outs = [], []
+        bounds = [0] + (ends or [rows])
+        for g in range(G):
+            r0, r1 = bounds[g], bounds[g + 1]
+            wr = lins[g].weight.detach().bfloat16().float().requires_grad_()
+            br, gr, ber = (t.detach().clone().requires_grad_() for t in (lins[g].bias, lns[g].weight, lns[g].bias))
+            d = F.linear(xr[r0:r1], wr, br)
+            d = torch.where(keep[r0:r1], d / (1 - p), torch.zeros_like(d))
+            outs.append(F.layer_norm(d + rr[r0:r1], (768,), gr, ber, 1e-12))
+            refs.append((wr, br, gr, ber))
+        yr = torch.cat(outs, 0)
+        ((yr * w32).sum() + (yr * w16.float()).sum()).backward()
+        assert relerr(y32, yr) < 2e-2 and relerr(y16, yr) < 2e-2
+        assert relerr(res.grad, rr.grad) < 2e-2 and relerr(x.grad, xr.grad) < 3e-2
+        for g in range(G):
+            wr, br, gr, ber = refs[g]
+            assert relerr(lins[g].weight.grad, wr.grad) < 3e-2, (K, g)
+            assert relerr(lins[g].bias.grad, br.grad) < 3e-2 and relerr(lns[g].weight.grad, gr.grad) < 3e-2 and relerr(lns[g].bias.grad, ber.grad) < 3e-2
+
+
 @pytest.mark.parametrize('case', ['self_gasa', 'cross'])
 def test_attention_dropout_fwd_bwd(ag, case):
     """attention-probability dropout inside the fused kernels against torch with the SAME mask (rebuilt from the hash)"""

@@ -239,6 +239,16 @@ def test_embed_compose_feature_terms(ops, fd):
     assert relerr(y32, ref) < 1e-5
     y32, _ = ops.embed_compose(rows, 'cuda', a=a, feat=feat, feat_w=fw, feat_b=fb, feat_ln=(gf, bf))   # vp / gmap form
     assert relerr(y32, a + F.layer_norm(F.linear(feat, fw, fb), (768,), gf, bf, 1e-12)) < 1e-5
+    # the padding rows behind a stream are zero-filled by the same launch (zero_rows), rows beyond them stay untouched; an updated
+    # weight is picked up (the transposed copy the kernel reads follows the weight version)
+    big32 = torch.full((rows + 60, 768), 7.0, device='cuda')
+    big16 = torch.full((rows + 60, 768), 7.0, device='cuda', dtype=torch.bfloat16)
+    fw.mul_(2.0)
+    ops.embed_compose(rows, 'cuda', a=a, feat=feat, feat_w=fw, feat_b=fb, feat_ln=(gf, bf), y32=big32[:rows + 51], y16=big16[:rows + 51],
+                      zero_rows=51)
+    assert relerr(big32[:rows], a + F.layer_norm(F.linear(feat, fw, fb), (768,), gf, bf, 1e-12)) < 1e-5
+    assert bool((big32[rows:rows + 51] == 0).all()) and bool((big16[rows:rows + 51].float() == 0).all())
+    assert bool((big32[rows + 51:] == 7.0).all()) and bool((big16[rows + 51:].float() == 7.0).all())
 
 
 def test_ln_dot_and_mul_bcast(ops):

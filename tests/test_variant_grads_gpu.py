@@ -82,3 +82,33 @@ def test_duet_reverie_gradients(lib_built, precision):
     for k, v in (('loss', loss), ('ce', ce), ('og', og), ('aux', aux)):
         assert abs(float(v) - float(gold[k])) < lt * abs(float(gold[k])), k
     check_gradients(net, gold, names, precision, 'duet reverie')
+
+
+@pytest.mark.parametrize('tag', ['unfixlang'])
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_duet_variant_gradients(lib_built, tag, precision):
+    """DUET-Imagine with the text encoder trained through the alignment loss as well (fix_lang_inside_cosine_model off, the parser
+    default; D/models/vilmodel.py:1256-1262): the noun-phrase token means carry gradients (ragged-mean adjoint = scatter-add of
+    dy / len), which changes the gradient of 149 language-encoder parameters against the released recipe"""
+    from oracle.gen_golden import DUET_GRAD_VARIANTS, duet_train_step
+    synth = importlib.import_module('vln_imagine_b200.synth')
+    duet = importlib.import_module('vln_imagine_b200.duet')
+    config = importlib.import_module('vln_imagine_b200.config')
+    from parity_utils import manifest
+    model = duet.VLNBert(config.default_duet_args(**DUET_GRAD_VARIANTS[tag])).cuda().eval()
+    net = model.vln_bert
+    net.load_state_dict(synth.synth_state_dict(manifest('duet'), seed=0, gasa_stress=True))
+    net.precision = precision
+    net.zero_grad(set_to_none=True)
+    ep = to_dev(synth.to_torch(synth.duet_episode(synth.TINY, 7)))
+    loss, ce, aux, nav = duet_train_step(net, ep, lambda mode, batch: model(mode, batch))
+    loss.backward()
+    torch.cuda.synchronize()
+    gold = golden('duet_grads_' + tag)
+    with open(os.path.join(GOLDEN, 'duet_grads_variant_names.json')) as f:
+        names = json.load(f)[tag]
+    lt = LOSS_TOL[precision]
+    assert max_rel(nav['fused_logits'], gold['fused_logits']) < lt
+    for k, v in (('loss', loss), ('ce', ce), ('aux', aux)):
+        assert abs(float(v) - float(gold[k])) < lt * abs(float(gold[k])), k
+    check_gradients(net, gold, names, precision, 'duet ' + tag)

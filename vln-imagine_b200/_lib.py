@@ -35,7 +35,7 @@ class EmbedArgs(C.Structure):
         ('idx', _p), ('table', _p), ('pos_table', _p), ('pos_period', C.c_int32),
         ('const_row', _p), ('const_row2', _p), ('out_gamma', _p), ('out_beta', _p),
         ('eps', _f), ('y32', _p), ('y16', _p), ('rows', _l), ('a2', _p), ('a3', _p),
-        ('y16_dtype', C.c_int32), ('ln2_gamma', _p), ('ln2_beta', _p), ('ln2_eps', _f),
+        ('y16_dtype', C.c_int32), ('ln2_gamma', _p), ('ln2_beta', _p), ('ln2_eps', _f), ('zero_rows', _l),
     ]
 
 
@@ -91,6 +91,8 @@ PROTOTYPES = {
     'vi_act_bwd': [_p, _p, _p, _l, _i, _i, _p],
     'vi_add_ln_bwd': [_p, _p, _p, _f, _p, _p, _p, _p, _p, _p, _p, _l, _i, _ip, _p, _l, _p],
     'vi_add_ln_bwd_acc': [_p, _p, _p, _f, _p, _p, _p, _p, _p, _p, _p, _l, _i, _ip, _p, _l, _i, _p],
+    'vi_add_ln_drop': [_p, _p, _p, _p, _f, _p, _p, _i, _l, _i, _ip, _f, _p, C.c_uint32, _p],
+    'vi_add_ln_drop_bwd': [_p, _p, _p, _f, _p, _p, _p, _p, _p, _p, _p, _p, _l, _i, _ip, _p, _l, _i, _f, _p, C.c_uint32, _p],
     'vi_feat_wgrad': [_p, _p, _i, _p, _p, _l, _p, _l, _p],
     'vi_scatter_add_rows': [_p, _p, _i, _p, _l, _p],
     'vi_rowdot_bwd': [_p, _p, _p, _p, _p, _p, _l, _i, _ip, _p, _l, _p],

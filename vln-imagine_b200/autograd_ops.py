@@ -430,6 +430,148 @@ class LayerNormFn(Function):
         return (dx if ctx.a_needs else None, dx if ctx.b_needs else None, None, None, None, None, None, None, *pg)
 
 
+class DenseResLNFn(Function):
+    """(y32, y16) = LN(dropout(x W^T + bias) + res) as ONE autograd node (BertSelfOutput / BertOutput, D/models/vilmodel.py:151-155,
+    190-194; 16-bit mode).  Chaining LinearFn -> DropoutFn -> LayerNormFn costs, per layer and direction, a dropout pass over the
+    fp32 rows and an fp32 -> bf16 cast of the gradient; here the mask is applied inside the LayerNorm kernels (vi_add_ln_drop,
+    vi_add_ln_drop_bwd) and the backward kernel emits dropout(dx) directly as the 16-bit operand of the weight / input gradient
+    GEMMs.  p == 0: the residual rides in the GEMM epilogue as before.  Parameter gradients: accumulated in the kernels when
+    fused_grad_accumulation is on, returned to autograd otherwise."""
+
+    @staticmethod
+    def forward(ctx, x, res32, pack, lnpack, eps, ends, p, site, n_lin, *params):
+        w, b = pack.get(True)
+        g, be = lnpack.get()
+        rows = x.shape[0]
+        n_groups = 1 if ends is None else len(ends)
+        ln_ends = ends if len(lnpack.g.tensors) > 1 else None
+        earr = _lib.int_array(list(ln_ends)) if ln_ends is not None else None
+        if p > 0:
+            y32 = torch.empty((rows, HIDDEN), dtype=F32, device=x.device)
+            y16 = torch.empty((rows, HIDDEN), dtype=x.dtype, device=x.device)
+            d = ops.gemm(x, w, b, out_dtype=F32, group_row_end=ends)
+            check(lib.vi_add_ln_drop(d.data_ptr(), res32.data_ptr(), g.data_ptr(), be.data_ptr(), eps, y32.data_ptr(), y16.data_ptr(),
+                                     ops._DT[y16.dtype], rows, 1 if ln_ends is None else len(ln_ends), earr, float(p),
+                                     dropout_seed(x.device).data_ptr(), site, _stream()), 'vi_add_ln_drop')
+            _launched(1)
+            ctx.save_for_backward(x, d, res32, g)
+        else:
+            d = ops.gemm(x, w, b, residual=res32, out_dtype=F32, group_row_end=ends)
+            y32, y16 = ops.add_ln(d, None, g, be, eps, want16=True, group_row_end=ln_ends)
+            ctx.save_for_backward(x, d, d.new_empty(0), g)
+        ctx.pack, ctx.lnpack, ctx.eps, ctx.ends, ctx.ln_ends, ctx.p, ctx.site, ctx.n_lin = pack, lnpack, eps, ends, ln_ends, p, site, n_lin
+        ctx.n_params = len(params)
+        ctx.res_needs = res32.requires_grad
+        return y32, y16
+
+    @staticmethod
+    def backward(ctx, dy32, dy16):
+        x, d, res32, g = ctx.saved_tensors
+        pack, lnpack, ends, ln_ends, p = ctx.pack, ctx.lnpack, ctx.ends, ctx.ln_ends, ctx.p
+        rows = d.shape[0]
+        dev = d.device
+        n_groups = 1 if ends is None else len(ends)
+        n_ln = 1 if ln_ends is None else len(ln_ends)
+        if dy16 is not None and dy16.numel() == 0:
+            dy16 = None
+        dy32 = dy32.contiguous() if dy32 is not None else None
+        dy16 = dy16.contiguous() if dy16 is not None else None
+        lin_srcs = pack.grad_sources()
+        ln_srcs = lnpack.grad_sources()
+        half = len(ln_srcs) // 2
+        fused = _GradAcc.enabled and half == n_ln
+        beta_ln = 0
+        if fused:
+            e = _acc_entry(ln_srcs, [(n_ln, HIDDEN), (n_ln, HIDDEN)], dev)
+            if 'slices' not in e:
+                e['slices'] = [(ln_srcs[i], e['t'][0][i]) for i in range(half)] + [(ln_srcs[half + i], e['t'][1][i]) for i in range(half)]
+            beta_ln = _acc_begin(e)
+            dg, dbt = e['t']
+        else:
+            dg = torch.empty((n_ln, HIDDEN), dtype=F32, device=dev)
+            dbt = torch.empty((n_ln, HIDDEN), dtype=F32, device=dev)
+        dres = torch.empty((rows, HIDDEN), dtype=F32, device=dev)
+        da16 = torch.empty((rows, HIDDEN), dtype=x.dtype, device=dev)
+        stats = torch.empty((rows, 2), dtype=F32, device=dev)
+        sc = reduce_scratch(dev, 4 * rows, HIDDEN, 2)
+        check(lib.vi_add_ln_drop_bwd(d.data_ptr(), res32.data_ptr() if p > 0 else None, g.data_ptr(), ctx.eps, _ptr(dy32), _ptr(dy16),
+                                     dres.data_ptr(), None, da16.data_ptr(), dg.data_ptr(), dbt.data_ptr(), stats.data_ptr(), rows, n_ln,
+                                     _lib.int_array(list(ln_ends)) if ln_ends is not None else None, sc.data_ptr(), sc.numel(), beta_ln,
+                                     float(p), dropout_seed(dev).data_ptr() if p > 0 else None, ctx.site, _stream()), 'vi_add_ln_drop_bwd')
+        _launched(2)
+        # dense layer: dX = dA W, dW = dA^T X, db = colsum(dA) with dA = da16
+        M, K = x.shape
+        N = da16.shape[1]
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = ops.gemm(da16, pack.get_t(True, n_groups), None, out_dtype=x.dtype, group_row_end=ends)
+        has_b = pack.biases is not None
+        lin_grads = [None] * len(lin_srcs)
+        if wgrad16_ok(da16, x) and N * n_groups == sum(w_.shape[0] for w_ in pack.weights):
+            if _GradAcc.enabled:
+                bs = [b_ for b_ in pack.biases if b_ is not None] if has_b else []
+                e = _acc_entry(pack.weights + bs, [(n_groups * N, K)] + ([(n_groups * N,)] if has_b else []), dev)
+                if 'slices' not in e:
+                    e['slices'] = _lin_slices(pack, e['t'])
+                beta = _acc_begin(e)
+                wgrad16(da16, x, ends, has_b, out=(e['t'][0], e['t'][1] if has_b else None), accumulate=beta)
+            else:
+                dW, db = wgrad16(da16, x, ends, has_b)
+                lin_grads = _lin_grads(pack, dW, db)
+        else:
+            raise _lib.VlnImagineError('DenseResLNFn: the dense layer must be a multiple of 128 x 64 (got N=%d, K=%d)' % (N, K))
+        ln_grads = [None] * len(ln_srcs)
+        if not fused:
+            needs = [s_.requires_grad for s_ in ln_srcs]
+            ln_grads = [dg[i] if needs[i] else None for i in range(half)] + [dbt[i] if needs[half + i] else None for i in range(half)]
+        return (dx, dres if ctx.res_needs else None, None, None, None, None, None, None, None, *lin_grads, *ln_grads)
+
+
+def _lin_slices(pack, tensors):
+    """(parameter, accumulator slice) pairs of a LinearPack's stacked weight / bias accumulators"""
+    sl, off = [], 0
+    for wsrc in pack.weights:
+        sl.append((wsrc, tensors[0][off:off + wsrc.shape[0]]))
+        off += wsrc.shape[0]
+    off = 0
+    for bsrc, wsrc in zip(pack.biases or [], pack.weights):
+        if bsrc is not None:
+            sl.append((bsrc, tensors[1][off:off + wsrc.shape[0]]))
+        off += wsrc.shape[0]
+    return sl
+
+
+def _lin_grads(pack, dW, db):
+    """gradients of a LinearPack's parameters in grad_sources() order from the stacked dW / db"""
+    grads, off = [], 0
+    for wsrc in pack.weights:
+        n = wsrc.shape[0]
+        grads.append(dW[off:off + n] if wsrc.requires_grad else None)
+        off += n
+    if pack.biases is not None:
+        off = 0
+        for bsrc, wsrc in zip(pack.biases, pack.weights):
+            n = wsrc.shape[0]
+            if bsrc is not None:
+                grads.append(db[off:off + n] if bsrc.requires_grad else None)
+            off += n
+    return grads
+
+
+def dense_res_ln(x, res32, pack, lnpack, eps, ends, p):
+    """differentiable LN(dropout(x W^T + b) + res) -> (y32, y16), 16-bit mode (see DenseResLNFn)"""
+    lin_srcs, ln_srcs = pack.grad_sources(), lnpack.grad_sources()
+    site = next_site() if p > 0 else 0
+    return DenseResLNFn.apply(x, res32, pack, lnpack, eps, ends, float(p), site, len(lin_srcs), *lin_srcs, *ln_srcs)
+
+
+def dense_res_ln_ok(x, pack, lnpack, ends) -> bool:
+    n_groups = 1 if ends is None else len(ends)
+    N = sum(w_.shape[0] for w_ in pack.weights)
+    return (ops.is16(x.dtype) and x.shape[1] % 64 == 0 and N % n_groups == 0 and (N // n_groups) == HIDDEN and x.stride(1) == 1
+            and x.stride(0) % 8 == 0 and len(lnpack.g.tensors) in (1, n_groups))
+
+
 def layer_norm(a, b, lnpack, eps, lowp, ends=None):
     """differentiable LayerNorm(a [+ b]) -> (y32, y16 or None); lnpack = blocks.LNPack"""
     g, be = lnpack.get()
@@ -776,6 +918,37 @@ class MulBcastFn(Function):
         check(lib.vi_mul_bcast_bwd_s(dy.data_ptr(), x.data_ptr(), ds.data_ptr(), B, R, _stream()), 'vi_mul_bcast_bwd_s')
         _launched(1)
         return dx.view(B, R, HIDDEN), ds, None
+
+
+class RaggedMeanFn(Function):
+    """y[r] = mean of src[row_idx[offsets[r]:offsets[r+1]]] over RAGGED segments whose rows may repeat across segments (the
+    noun-phrase / instruction token means of the alignment loss, D/models/vilmodel.py:617-641,781-806).  Adjoint: source row j
+    receives sum over the segments r that contain it of dy[r] / len_r (a scatter-add of scaled copies).  Used when the text encoder
+    trains through the alignment loss (fix_lang_inside_cosine_model off, :1256-1262)."""
+
+    @staticmethod
+    def forward(ctx, src, offsets, row_idx, R):
+        src = src.contiguous()
+        y32, _ = ops.gather_mean(src, offsets, row_idx, R, want16=False)
+        ctx.save_for_backward(offsets, row_idx)
+        ctx.shape, ctx.R = src.shape, R
+        return y32
+
+    @staticmethod
+    def backward(ctx, dy):
+        offsets, row_idx = ctx.saved_tensors
+        dy = dy.contiguous()
+        dev = dy.device
+        R, n = ctx.R, row_idx.shape[0]
+        lens = (offsets[1:R + 1] - offsets[:R]).long()
+        inv = (1.0 / lens.to(F32))[:, None].expand(R, HIDDEN).contiguous()            # per-segment scale as a 768-wide row
+        g, _ = ops.mul_bcast(dy, HIDDEN, inv, HIDDEN, R, 1, want16=False)              # dy[r] / len_r
+        seg_of = torch.repeat_interleave(torch.arange(R, device=dev, dtype=torch.int64), lens, output_size=n)
+        rows, _ = ops.embed_compose(n, dev, idx=seg_of, table=g)                       # one scaled copy per member row
+        d = torch.zeros(ctx.shape, dtype=F32, device=dev)
+        check(lib.vi_scatter_add_rows(rows.data_ptr(), row_idx.long().data_ptr(), 1, d.data_ptr(), n, _stream()), 'vi_scatter_add_rows')
+        _launched(1)
+        return d, None, None, None
 
 
 class SegmentMeanFn(Function):

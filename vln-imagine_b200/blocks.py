@@ -54,6 +54,9 @@ def _attn_drop(device, p=None):
 
 def _dense_res_ln(x, lin: 'LinearPack', res32, ln: 'LNPack', eps, lowp, ends):
     """training: LN(dropout(x W^T + b) + res)  (BertSelfOutput / BertOutput, D/models/vilmodel.py:151-155,190-194)"""
+    if lowp and ag.dense_res_ln_ok(x, lin, ln, ends) and os.environ.get('VLN_IMAGINE_FUSED_DENSE_LN', '1') != '0':
+        y32, y16 = ag.dense_res_ln(x, res32, lin, ln, eps, ends, _Mode.p_hidden)       # one autograd node, dropout inside the LN kernels
+        return Act(y32, y16)
     if _Mode.p_hidden > 0:
         d = ag.dropout(ag.linear(x, lin, lowp, out_dtype=F32, ends=ends), _Mode.p_hidden)
         return layer_norm(d, res32, ln, eps, lowp, ends)
@@ -117,6 +120,22 @@ class Pack:
                 self._val = self._build()
             self._key = key
         return self._val
+
+
+_FEAT_WT = {}
+
+
+def feat_wt(w: torch.Tensor) -> torch.Tensor:
+    """[feat_dim, 768] transposed fp32 copy of the weight of a small feature projection (nn.Linear(feat_dim, 768).weight), as
+    vi_embed_compose reads it; cached per parameter and rebuilt with the weight version like every derived tensor"""
+    e = _FEAT_WT.get(id(w))
+    if e is None or e[0] is not w:
+        e = (w, Pack([w], lambda: w.detach().t().contiguous().float()))
+        _FEAT_WT[id(w)] = e
+    return e[1].get()
+
+
+ops.set_feat_wt_provider(feat_wt)
 
 
 class LinearPack:

@@ -325,12 +325,17 @@ __global__ void __launch_bounds__(256) ln_bwd_param_partial_kernel(const float* 
 // registers, the 8 warps are summed through shared memory in a fixed order and the chunk's partial row goes to
 // part[2][n_chunks][768]; ln_param_sum_kernel then adds the chunks of each row group (fixed order: deterministic).
 constexpr int LN_CHUNK = 32;
+// DropArgs: the forward pass normalised dropout(a) + b (vi_add_ln_drop); then dxa16 receives dropout(dx) - the gradient of a - as the
+// 16-bit operand of the weight / input gradient GEMMs of the dense layer that produced a, and dx32 stays the gradient of b.
+struct DropArgs { uint32_t thresh; float scale; const uint32_t* seed; uint32_t site; bf16* dxa16; };
 __global__ void __launch_bounds__(256) ln_bwd_fused_kernel(const float* a, const float* b, const float* gamma, float eps,
                                                            const float* dy32, const bf16* dy16, float* __restrict__ dx32,
                                                            bf16* __restrict__ dx16, float* __restrict__ stats,
                                                            float* __restrict__ part, long long rows, int n_chunks,
-                                                           const RowGroups grp) {
+                                                           const RowGroups grp, const DropArgs dr) {
   pdl_enter();
+  const bool drop = dr.seed != nullptr;
+  const uint32_t dkey = drop ? vi_drop_key(dr.seed, dr.site) : 0u;
   __shared__ float red[8][D];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long r0 = (long long)blockIdx.x * LN_CHUNK;
@@ -347,6 +352,13 @@ __global__ void __launch_bounds__(256) ln_bwd_fused_kernel(const float* a, const
     for (int j = 0; j < 6; ++j) {
       const int c = (lane + 32 * j) * 4;
       float4 t = *reinterpret_cast<const float4*>(a + row * D + c);
+      if (drop) {
+        const uint32_t e0 = (uint32_t)(row * D) + (uint32_t)c;
+        t.x = vi_hash32(e0, dkey) >= dr.thresh ? t.x * dr.scale : 0.f;
+        t.y = vi_hash32(e0 + 1, dkey) >= dr.thresh ? t.y * dr.scale : 0.f;
+        t.z = vi_hash32(e0 + 2, dkey) >= dr.thresh ? t.z * dr.scale : 0.f;
+        t.w = vi_hash32(e0 + 3, dkey) >= dr.thresh ? t.w * dr.scale : 0.f;
+      }
       if (b) {
         const float4 u = *reinterpret_cast<const float4*>(b + row * D + c);
         t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
@@ -394,6 +406,14 @@ __global__ void __launch_bounds__(256) ln_bwd_fused_kernel(const float* a, const
       for (int e = 0; e < 4; ++e) o[e] = rstd * (g[4 * j + e] - mg - x[4 * j + e] * mgx);
       if (dx32) *reinterpret_cast<float4*>(dx32 + row * D + c) = make_float4(o[0], o[1], o[2], o[3]);
       if (dx16) *reinterpret_cast<uint2*>(dx16 + row * D + c) = make_uint2(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]));
+      if (dr.dxa16) {
+        if (drop) {
+          const uint32_t e0 = (uint32_t)(row * D) + (uint32_t)c;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) o[e] = vi_hash32(e0 + e, dkey) >= dr.thresh ? o[e] * dr.scale : 0.f;
+        }
+        *reinterpret_cast<uint2*>(dr.dxa16 + row * D + c) = make_uint2(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]));
+      }
     }
     if (lane == 0) { stats[2 * row] = mean; stats[2 * row + 1] = rstd; }
   }
@@ -993,6 +1013,20 @@ extern "C" int vi_add_ln_bwd_acc(const float* a, const float* b, const float* ga
                                  float* dx32, void* dx16, float* dgamma, float* dbeta, float* stats, int64_t rows, int n_groups,
                                  const int32_t* group_row_end, float* scratch, int64_t scratch_elems, int accumulate,
                                  vi_stream_t stream) {
+  return vi_add_ln_drop_bwd(a, b, gamma, eps, dy32, dy16, dx32, dx16, nullptr, dgamma, dbeta, stats, rows, n_groups, group_row_end,
+                            scratch, scratch_elems, accumulate, 0.f, nullptr, 0u, stream);
+}
+
+extern "C" int vi_add_ln_drop_bwd(const float* a, const float* b, const float* gamma, float eps, const float* dy32, const void* dy16,
+                                  float* dx32, void* dx16, void* dxa16, float* dgamma, float* dbeta, float* stats, int64_t rows,
+                                  int n_groups, const int32_t* group_row_end, float* scratch, int64_t scratch_elems, int accumulate,
+                                  float p, const uint32_t* seed, uint32_t site, vi_stream_t stream) {
+  VI_CHECK_ARG(p >= 0.f && p < 1.f && (p == 0.f || seed), "vi_add_ln_drop_bwd: 0 <= p < 1 and a device seed pointer");
+  VI_CHECK_ARG(!dxa16 || (dgamma && dbeta && ((uintptr_t)dxa16 & 7) == 0), "vi_add_ln_drop_bwd: dxa16 needs dgamma / dbeta and 8-byte alignment");
+  VI_CHECK_ARG(p == 0.f || (dgamma && dbeta && rows * D < (1LL << 32)), "vi_add_ln_drop_bwd: dropout needs the one-pass form and < 2^32 elements");
+  DropArgs dr;
+  dr.thresh = vi_drop_threshold(p); dr.scale = 1.0f / (1.0f - p); dr.seed = p > 0.f ? seed : nullptr; dr.site = site;
+  dr.dxa16 = reinterpret_cast<bf16*>(dxa16);
   RowGroups grp;
   VI_CHECK_ARG(make_groups(grp, n_groups, group_row_end), "vi_add_ln_bwd: bad row groups");
   for (int g = 0; g + 1 < n_groups; ++g)
@@ -1007,7 +1041,7 @@ extern "C" int vi_add_ln_bwd_acc(const float* a, const float* b, const float* ga
     VI_CHECK_ARG(scratch && scratch_elems >= (int64_t)2 * nch * D, "vi_add_ln_bwd: scratch too small (need 2 x ceil(rows / %d) x %d floats)",
                  LN_CHUNK, D);
     VI_CUDA(vi_launch(ln_bwd_fused_kernel, dim3((unsigned)nch), dim3(256), 0, ST(stream), a, b, gamma, eps, dy32,
-                      reinterpret_cast<const bf16*>(dy16), dx32, reinterpret_cast<bf16*>(dx16), stats, scratch, (long long)rows, nch, grp));
+                      reinterpret_cast<const bf16*>(dy16), dx32, reinterpret_cast<bf16*>(dx16), stats, scratch, (long long)rows, nch, grp, dr));
     VI_CUDA(vi_launch(ln_param_sum_kernel, dim3(D / 256, n_groups, 2), dim3(256), 0, ST(stream), (const float*)scratch, dgamma, dbeta, nch,
                       (long long)rows, grp, (int)(accumulate != 0)));
   } else {

@@ -113,123 +113,100 @@ __global__ void __launch_bounds__(128) add_ln_kernel(const float* a, const float
   row_store(r, y32, y16, row, lane, f16 != 0);
 }
 
-// 8 warps per CTA, one row per warp per iteration, CTAs stride over the rows.  Everything a row needs PER COLUMN - the
-// transposed weight of the small feature projection (feat_dim <= 16) and up to eleven 768-wide vectors (LayerNorm gains / biases,
-// the feature bias, constant rows) - is staged in shared memory once per CTA, so the only global loads of a row are the row
-// itself, its feature scalars and its table rows; they are all issued at the top of the row and the feature projection (shared
-// memory + FMAs) runs under their latency.  (Round 1 re-read every vector from global memory per row and staged the weight
-// with feat_dim-way bank conflicts: 14 - 19 us per launch at 2 % of the HBM roofline; ncu showed 1800 instructions per row and
-// long-scoreboard stalls.)
-constexpr int EMBED_WARPS = 8;
-enum { EV_A_G = 0, EV_A_B, EV_F_BIAS, EV_F_G, EV_F_B, EV_O_G, EV_O_B, EV_L2_G, EV_L2_B, EV_C1, EV_C2, EV_COUNT };
+// LN(dropout(a) + b): the hidden dropout of BertSelfOutput / BertOutput (D/models/vilmodel.py:151-155,190-194) applied on the fly -
+// keep(i) = hash(i, seed, site) >= threshold with i = row * 768 + column, the same mask vi_dropout produces for a [rows, 768] tensor
+__global__ void __launch_bounds__(128) add_ln_drop_kernel(const float* a, const float* b, const float* gamma, const float* beta,
+                                                          float eps, float* y32, bf16* y16, int f16, long long rows,
+                                                          const RowGroups grp, uint32_t thresh, float scale, const uint32_t* seed,
+                                                          uint32_t site) {
+  pdl_enter();
+  ROW_INDEX();
+  if (row >= rows) return;
+  const int gi = group_of_row(grp, row);
+  gamma += gi * D;
+  beta += gi * D;
+  const uint32_t key = vi_drop_key(seed, site);
+  Row r;
+  row_load(r, a + row * D, lane);
+#pragma unroll
+  for (int j = 0; j < V4; ++j) {
+    const uint32_t e0 = (uint32_t)(row * D) + (uint32_t)((lane + 32 * j) * 4);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) r.v[4 * j + e] = vi_hash32(e0 + e, key) >= thresh ? r.v[4 * j + e] * scale : 0.f;
+  }
+  if (b) row_add(r, b + row * D, lane);
+  row_layernorm(r, gamma, beta, eps, lane);
+  row_store(r, y32, y16, row, lane, f16 != 0);
+}
 
-__device__ __forceinline__ void row_load_s(Row& r, const float* s, int lane) {       // from shared memory
-  const float4* s4 = reinterpret_cast<const float4*>(s);
-#pragma unroll
-  for (int j = 0; j < V4; ++j) {
-    const float4 t = s4[lane + 32 * j];
-    r.v[4 * j] = t.x; r.v[4 * j + 1] = t.y; r.v[4 * j + 2] = t.z; r.v[4 * j + 3] = t.w;
-  }
-}
-// in-place LayerNorm with the gain / bias vectors in shared memory
-__device__ __forceinline__ void row_layernorm_s(Row& r, const float* gamma, const float* beta, float eps, int lane) {
-  float s = 0.f;
-#pragma unroll
-  for (int i = 0; i < V4 * 4; ++i) s += r.v[i];
-  const float mean = warp_sum(s) * (1.0f / D);
-  float q = 0.f;
-#pragma unroll
-  for (int i = 0; i < V4 * 4; ++i) { const float d = r.v[i] - mean; q = fmaf(d, d, q); }
-  const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + eps);
-  const float4* g4 = reinterpret_cast<const float4*>(gamma);
-  const float4* b4 = reinterpret_cast<const float4*>(beta);
-#pragma unroll
-  for (int j = 0; j < V4; ++j) {
-    const float4 g = g4[lane + 32 * j], b = b4[lane + 32 * j];
-    r.v[4 * j] = (r.v[4 * j] - mean) * rstd * g.x + b.x;
-    r.v[4 * j + 1] = (r.v[4 * j + 1] - mean) * rstd * g.y + b.y;
-    r.v[4 * j + 2] = (r.v[4 * j + 2] - mean) * rstd * g.z + b.z;
-    r.v[4 * j + 3] = (r.v[4 * j + 3] - mean) * rstd * g.w + b.w;
-  }
-}
+// One row per warp, 4 warps per CTA.  Everything a row needs PER COLUMN - the TRANSPOSED weight of the small feature
+// projection ([feat_dim][768], prepared by the caller once per weight version) and up to eleven 768-wide vectors (LayerNorm gains /
+// biases, the feature bias, constant rows) - is read with plain 16-byte loads that hit the SM's L1 after the first warp (33 - 76 KB
+// in all); the row's own loads (the row, its feature scalars, its table row) are issued first and the feature projection runs
+// under their latency.  History (ncu, cfg-2: 14 - 19 us per launch at 15 % of the HBM roofline): round 1 staged the weight in
+// shared memory with a load -> conflicted-store loop (30 - 50 serialised L2 round trips per CTA, for 8 rows each) and re-read the
+// vectors after the reductions that consume them; staging everything in shared memory cost 80 KB per 8 rows.
+constexpr int EMBED_WARPS = 4;
 
 __global__ void __launch_bounds__(EMBED_WARPS * 32) embed_compose_kernel(const vi_embed_args p) {
   pdl_enter();
-  extern __shared__ __align__(16) float esm[];
-  float* vec = esm;                                    // [EV_COUNT][768]
-  float* wT = esm + EV_COUNT * D;                      // [feat_dim][768]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  {
-    const float* src[EV_COUNT] = {p.a_gamma, p.a_beta, p.feat_b, p.feat_gamma, p.feat_beta, p.out_gamma, p.out_beta,
-                                  p.ln2_gamma, p.ln2_beta, p.const_row, p.const_row2};
-#pragma unroll
-    for (int v = 0; v < EV_COUNT; ++v) {
-      if (src[v]) {
-        for (int i = threadIdx.x; i < D / 4; i += EMBED_WARPS * 32)
-          reinterpret_cast<float4*>(vec + v * D)[i] = *(reinterpret_cast<const float4*>(src[v]) + i);
-      } else if (v == EV_F_BIAS) {
-        for (int i = threadIdx.x; i < D / 4; i += EMBED_WARPS * 32) reinterpret_cast<float4*>(vec + v * D)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    }
-    if (p.feat) {
-      // transposed copy: consecutive threads take consecutive columns of one k (conflict-free stores; the strided global
-      // reads of the 21 - 43 KB weight hit L1 / L2)
-      for (int i = threadIdx.x; i < D * p.feat_dim; i += EMBED_WARPS * 32) {
-        const int k = i / D, c = i - k * D;
-        wT[i] = *(p.feat_w + c * p.feat_dim + k);
-      }
-    }
-    __syncthreads();
+  const long long row = (long long)blockIdx.x * EMBED_WARPS + warp;
+  if (row >= p.rows + p.zero_rows) return;
+  if (row >= p.rows) {                                  // padding rows behind the stream (row-stacked activations): zeros
+    Row z;
+    row_zero(z);
+    row_store(z, p.y32, reinterpret_cast<bf16*>(p.y16), row, lane, p.y16_dtype == VI_DT_F16);
+    return;
   }
-  for (long long row = (long long)blockIdx.x * EMBED_WARPS + warp; row < p.rows; row += (long long)gridDim.x * EMBED_WARPS) {
-    // ---- every global load of the row is issued here
-    Row a, tb;
-    float fv = 0.f;
-    if (p.feat && lane < p.feat_dim) fv = *(p.feat + row * p.feat_dim + lane);
-    if (p.a) row_load(a, p.a + row * D, lane);
-    if (p.idx) row_load(tb, p.table + p.idx[row] * D, lane);
-    Row acc;
-    row_zero(acc);
-    // ---- feature projection from shared memory (runs under the loads above)
-    if (p.feat) {
-      Row t;
-      row_load_s(t, vec + EV_F_BIAS * D, lane);
-      for (int k = 0; k < p.feat_dim; ++k) {
-        const float f = __shfl_sync(0xffffffffu, fv, k);
-        const float4* w4 = reinterpret_cast<const float4*>(wT + k * D);
+  // ---- every global load that depends on the row is issued here
+  Row a, tb;
+  float fv = 0.f;
+  if (p.feat && lane < p.feat_dim) fv = *(p.feat + row * p.feat_dim + lane);
+  if (p.a) row_load(a, p.a + row * D, lane);
+  if (p.idx) row_load(tb, p.table + p.idx[row] * D, lane);
+  Row acc;
+  row_zero(acc);
+  // ---- feature projection (runs under the loads above)
+  if (p.feat) {
+    Row t;
+    if (p.feat_b) row_load(t, p.feat_b, lane);
+    else row_zero(t);
+    for (int k = 0; k < p.feat_dim; ++k) {
+      const float f = __shfl_sync(0xffffffffu, fv, k);
+      const float4* w4 = reinterpret_cast<const float4*>(p.feat_w + (long long)k * D);       // transposed: [feat_dim][768]
 #pragma unroll
-        for (int j = 0; j < V4; ++j) {
-          const float4 w = w4[lane + 32 * j];
-          t.v[4 * j] = fmaf(f, w.x, t.v[4 * j]);
-          t.v[4 * j + 1] = fmaf(f, w.y, t.v[4 * j + 1]);
-          t.v[4 * j + 2] = fmaf(f, w.z, t.v[4 * j + 2]);
-          t.v[4 * j + 3] = fmaf(f, w.w, t.v[4 * j + 3]);
-        }
+      for (int j = 0; j < V4; ++j) {
+        const float4 w = *(w4 + lane + 32 * j);
+        t.v[4 * j] = fmaf(f, w.x, t.v[4 * j]);
+        t.v[4 * j + 1] = fmaf(f, w.y, t.v[4 * j + 1]);
+        t.v[4 * j + 2] = fmaf(f, w.z, t.v[4 * j + 2]);
+        t.v[4 * j + 3] = fmaf(f, w.w, t.v[4 * j + 3]);
       }
-      if (p.feat_gamma) row_layernorm_s(t, vec + EV_F_G * D, vec + EV_F_B * D, p.eps, lane);
-      row_acc(acc, t);
     }
-    if (p.a) {
-      if (p.a_gamma) row_layernorm_s(a, vec + EV_A_G * D, vec + EV_A_B * D, p.eps, lane);
-      row_acc(acc, a);
-    }
-    if (p.a2) row_add(acc, p.a2 + row * D, lane);
-    if (p.a3) row_add(acc, p.a3 + row * D, lane);
-    if (p.idx) row_acc(acc, tb);
-    if (p.pos_table) row_add(acc, p.pos_table + (row % p.pos_period) * D, lane);
-    if (p.const_row) { Row c; row_load_s(c, vec + EV_C1 * D, lane); row_acc(acc, c); }
-    if (p.const_row2) { Row c; row_load_s(c, vec + EV_C2 * D, lane); row_acc(acc, c); }
-    if (p.out_gamma) row_layernorm_s(acc, vec + EV_O_G * D, vec + EV_O_B * D, p.eps, lane);
-    if (p.ln2_gamma) {
-      // a second LayerNorm chained on the result (norm1 of the first panorama layer, D/models/transformer.py:171): the fp32
-      // output keeps the first result (the residual stream), the 16-bit output is the operand of the next contraction
-      if (p.y32) row_store(acc, p.y32, nullptr, row, lane);
-      row_layernorm_s(acc, vec + EV_L2_G * D, vec + EV_L2_B * D, p.ln2_eps, lane);
-      row_store(acc, nullptr, reinterpret_cast<bf16*>(p.y16), row, lane, p.y16_dtype == VI_DT_F16);
-      continue;
-    }
-    row_store(acc, p.y32, reinterpret_cast<bf16*>(p.y16), row, lane, p.y16_dtype == VI_DT_F16);
+    if (p.feat_gamma) row_layernorm(t, p.feat_gamma, p.feat_beta, p.eps, lane);
+    row_acc(acc, t);
   }
+  if (p.a) {
+    if (p.a_gamma) row_layernorm(a, p.a_gamma, p.a_beta, p.eps, lane);
+    row_acc(acc, a);
+  }
+  if (p.a2) row_add(acc, p.a2 + row * D, lane);
+  if (p.a3) row_add(acc, p.a3 + row * D, lane);
+  if (p.idx) row_acc(acc, tb);
+  if (p.pos_table) row_add(acc, p.pos_table + (row % p.pos_period) * D, lane);
+  if (p.const_row) row_add(acc, p.const_row, lane);
+  if (p.const_row2) row_add(acc, p.const_row2, lane);
+  if (p.out_gamma) row_layernorm(acc, p.out_gamma, p.out_beta, p.eps, lane);
+  if (p.ln2_gamma) {
+    // a second LayerNorm chained on the result (norm1 of the first panorama layer, D/models/transformer.py:171): the fp32
+    // output keeps the first result (the residual stream), the 16-bit output is the operand of the next contraction
+    if (p.y32) row_store(acc, p.y32, nullptr, row, lane);
+    row_layernorm(acc, p.ln2_gamma, p.ln2_beta, p.ln2_eps, lane);
+    row_store(acc, nullptr, reinterpret_cast<bf16*>(p.y16), row, lane, p.y16_dtype == VI_DT_F16);
+    return;
+  }
+  row_store(acc, p.y32, reinterpret_cast<bf16*>(p.y16), row, lane, p.y16_dtype == VI_DT_F16);
 }
 
 __global__ void __launch_bounds__(128) ln_dot_kernel(const float* h, const float* gamma,
@@ -282,6 +259,7 @@ __global__ void __launch_bounds__(32) duet_fuse_logits_kernel(const float* g_raw
   __shared__ float ll[FUSE_MAX];
   __shared__ int gid[FUSE_MAX];
   __shared__ int cid[FUSE_MAX];
+  __shared__ int vid[FUSE_MAX];           // gid of the visited nodes, -1 elsewhere
   __shared__ uint8_t gvis[FUSE_MAX];      // node id is in the reference's `visited_nodes` set
   __shared__ uint8_t cvis[FUSE_MAX];      // candidate id is in `visited_nodes`
   __shared__ float bw_s;
@@ -295,18 +273,26 @@ __global__ void __launch_bounds__(32) duet_fuse_logits_kernel(const float* g_raw
     local_logits[i] = x;
     cid[v] = cand_ids[i];
   }
-  for (int j = lane; j < G; j += 32) gid[j] = gmap_ids[(long long)b * G + j];
+  // ids of the VISITED nodes only (-1 otherwise): the set look-ups below then run on shared memory alone (they used to read
+  // gmap_visited from global memory inside the inner loops: one latency chain per comparison hit)
+  for (int j = lane; j < G; j += 32) {
+    const int id = gmap_ids[(long long)b * G + j];
+    gid[j] = id;
+    vid[j] = (id != -1 && gmap_visited[(long long)b * G + j]) ? id : -1;
+  }
   __syncwarp();
   for (int j = lane; j < G; j += 32) {
     bool in_set = false;
-    if (gid[j] != -1)
-      for (int k = 0; k < G; ++k) in_set |= (gid[k] == gid[j]) && gid[k] != -1 && gmap_visited[(long long)b * G + k];
+    const int id = gid[j];
+    if (id != -1)
+      for (int k = 0; k < G; ++k) in_set |= vid[k] == id;
     gvis[j] = in_set;
   }
   for (int v = lane; v < P; v += 32) {
     bool in_set = false;
-    if (cid[v] != -2)
-      for (int k = 0; k < G; ++k) in_set |= (gid[k] == cid[v]) && gid[k] != -1 && gmap_visited[(long long)b * G + k];
+    const int id = cid[v];
+    if (id != -2 && id != -1)
+      for (int k = 0; k < G; ++k) in_set |= vid[k] == id;
     cvis[v] = in_set;
   }
   __syncwarp();
@@ -351,7 +337,19 @@ __global__ void __launch_bounds__(128) gather_mean_kernel(const float* src, cons
   Row acc;
   row_zero(acc);
   const int s = offsets[row], e = offsets[row + 1];
-  for (int t = s; t < e; ++t) row_add(acc, src + (long long)row_idx[t] * D, lane);
+  // four member rows in flight at a time (a segment of 36 views used to be 36 serialised DRAM round trips = 30 us for the
+  // history panorama mean of HAMT); they are still ADDED in member order, so the fp32 sum is unchanged
+  int t = s;
+  for (; t + 4 <= e; t += 4) {
+    Row r0, r1, r2, r3;
+    const long long i0 = row_idx[t], i1 = row_idx[t + 1], i2 = row_idx[t + 2], i3 = row_idx[t + 3];
+    row_load(r0, src + i0 * D, lane);
+    row_load(r1, src + i1 * D, lane);
+    row_load(r2, src + i2 * D, lane);
+    row_load(r3, src + i3 * D, lane);
+    row_acc(acc, r0); row_acc(acc, r1); row_acc(acc, r2); row_acc(acc, r3);
+  }
+  for (; t < e; ++t) row_add(acc, src + (long long)row_idx[t] * D, lane);
   // torch.mean = sum / n (true division); n == 0 never reaches the kernel (host filters empty rows)
   const float n = (float)(e - s);
 #pragma unroll
@@ -566,6 +564,23 @@ extern "C" int vi_add_ln(const float* a, const float* b, const float* gamma, con
   return VI_OK;
 }
 
+extern "C" int vi_add_ln_drop(const float* a, const float* b, const float* gamma, const float* beta, float eps, float* y32, void* y16,
+                              int y16_dtype, int64_t rows, int n_groups, const int32_t* group_row_end, float p, const uint32_t* seed,
+                              uint32_t site, vi_stream_t stream) {
+  RowGroups grp;
+  VI_CHECK_ARG(dt16_ok(y16_dtype), "vi_add_ln_drop: y16_dtype must be VI_DT_BF16 or VI_DT_F16");
+  VI_CHECK_ARG(make_groups(grp, n_groups, group_row_end, rows), "vi_add_ln_drop: bad row groups");
+  VI_CHECK_ARG(a && gamma && beta && (y32 || y16) && seed && p >= 0.f && p < 1.f, "vi_add_ln_drop: bad operands (0 <= p < 1, device seed)");
+  VI_CHECK_ARG(aligned16(a) && aligned16(b) && aligned16(gamma) && aligned16(beta) && aligned16(y32) && ((uintptr_t)y16 & 7) == 0,
+               "vi_add_ln_drop: operands must be 16-byte aligned");
+  VI_CHECK_ARG(rows * D < (1LL << 32), "vi_add_ln_drop: the dropout mask is indexed with 32 bits");
+  if (rows <= 0) return VI_OK;
+  VI_CUDA(vi_launch(add_ln_drop_kernel, dim3(row_grid(rows)), dim3(128), (size_t)(0), ST(stream), a, b, gamma, beta, eps, y32,
+                    reinterpret_cast<bf16*>(y16), (int)(y16_dtype == VI_DT_F16), rows, grp, vi_drop_threshold(p), 1.0f / (1.0f - p), seed, site));
+  VI_LAUNCH_CHECK();
+  return VI_OK;
+}
+
 extern "C" int vi_embed_compose(const vi_embed_args* args, vi_stream_t stream) {
   VI_CHECK_ARG(args, "vi_embed_compose: null args");
   const vi_embed_args& p = *args;
@@ -582,17 +597,11 @@ extern "C" int vi_embed_compose(const vi_embed_args* args, vi_stream_t stream) {
   VI_CHECK_ARG(aligned16(p.a) && aligned16(p.table) && aligned16(p.pos_table) && aligned16(p.const_row) &&
                    aligned16(p.const_row2) && aligned16(p.y32) && ((uintptr_t)p.y16 & 7) == 0,
                "vi_embed_compose: row operands must be 16-byte aligned");
-  VI_CHECK_ARG(aligned16(p.feat_b), "vi_embed_compose: feat_b must be 16-byte aligned");
+  VI_CHECK_ARG(aligned16(p.feat_b) && aligned16(p.feat_w), "vi_embed_compose: feat_b / feat_w must be 16-byte aligned");
+  VI_CHECK_ARG(p.zero_rows >= 0, "vi_embed_compose: negative zero_rows");
   if (p.rows <= 0) return VI_OK;
-  long long blocks = (p.rows + EMBED_WARPS - 1) / EMBED_WARPS;
-  const long long cap = 2LL * vi_num_sms();
-  if (blocks > cap) blocks = cap;                    // amortise the staging of the per-column vectors over several rows per warp
-  const size_t smem = ((size_t)EV_COUNT + (p.feat ? (size_t)p.feat_dim : 0)) * D * sizeof(float);
-  static bool attr_set = false;                      // idempotent; races only repeat the same call
-  if (!attr_set) {
-    VI_CUDA(cudaFuncSetAttribute(embed_compose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((EV_COUNT + 16) * D * sizeof(float))));
-    attr_set = true;
-  }
+  const long long blocks = (p.rows + p.zero_rows + EMBED_WARPS - 1) / EMBED_WARPS;
+  const size_t smem = 0;
   VI_CUDA(vi_launch(embed_compose_kernel, dim3((unsigned)blocks), dim3(EMBED_WARPS * 32), (size_t)(smem), ST(stream), p));
   VI_LAUNCH_CHECK();
   return VI_OK;

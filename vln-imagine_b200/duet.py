@@ -191,9 +191,9 @@ def _align_forward_train(model, txt, img, rows, pk, lowp, shape):
     projected rows (models/vilmodel.py:646) are differentiable; the noun-phrase text means are constants
     (``fix_lang_inside_cosine_model``, :1249-1255 - the released configuration)."""
     cfg = model.config
-    if txt.requires_grad:
-        raise NotImplementedError('training the text encoder through the alignment loss '
-                                  '(fix_lang_inside_cosine_model=False) is not on the released path')
+    if txt.requires_grad and cfg.aux_loss_type != 'cosine':
+        raise NotImplementedError('training the text encoder through the %r alignment loss (fix_lang_inside_cosine_model=False) '
+                                  'is not built: only the cosine form carries gradients to the text means' % cfg.aux_loss_type)
     if cfg.aux_loss_type not in ('cosine', 'contrastive-InfoNCE', 'constrastive-margin'):
         raise NotImplementedError('backward of aux_loss_type %r' % cfg.aux_loss_type)
     B, I = shape
@@ -205,7 +205,10 @@ def _align_forward_train(model, txt, img, rows, pk, lowp, shape):
         x = ag.linear(x, lp, lowp, out_dtype=F32 if (last or not lowp) else BF16)
         if not last:
             x = ag.ActFn.apply(x, ops.EPI_RELU)
-    tgt, _ = ops.gather_mean(txt, rows.tok_off, rows.tok_rows, rows.R, want16=False)
+    if txt.requires_grad:                                     # fix_lang_inside_cosine_model off (:1256-1262): the text means train too
+        tgt = ag.RaggedMeanFn.apply(txt, rows.tok_off, rows.tok_rows, rows.R)
+    else:
+        tgt, _ = ops.gather_mean(txt, rows.tok_off, rows.tok_rows, rows.R, want16=False)
     if cfg.aux_loss_type == 'cosine':
         loss = ag.CosineLossFn.apply(x, tgt, rows.R)
     else:                                                     # AlignWithContrastiveLossWithNegativeSamples (:689-779)
@@ -220,6 +223,21 @@ def _align_forward_train(model, txt, img, rows, pk, lowp, shape):
                                           float(cfg.infonce_temperature), rows.R, rows.n_negs)
     out = ag.ScatterSlotsFn.apply(img, x, rows.slot, rows.unit)
     return loss, out.view(B, I, HIDDEN)
+
+
+_ARANGE = {}
+
+
+def _arange(n: int, dev) -> torch.Tensor:
+    """0 .. n-1 on ``dev``, built once per length (one launch less per step; a constant, so it is safe inside captured graphs as
+    long as it was created outside of one - the first call of every mode runs eagerly)"""
+    key = (n, str(dev))
+    t = _ARANGE.get(key)
+    if t is None:
+        t = torch.arange(n, device=dev)
+        if not torch.cuda.is_current_stream_capturing():
+            _ARANGE[key] = t
+    return t
 
 
 class GlocalTextPathNavCMT(nn.Module):
@@ -373,7 +391,7 @@ class GlocalTextPathNavCMT(nn.Module):
         pk = self._pk()
         ie = self.img_embeddings
         v32 = _f32c(view_img_fts).view(B * V, Fd)
-        pano_masks = torch.arange(V, device=dev)[None, :] < view_lens.to(dev)[:, None]      # ops.py:36-44
+        pano_masks = _arange(V, dev)[None, :] < view_lens.to(dev)[:, None]                  # ops.py:36-44
         km = blocks.mask_u8(pano_masks)
         with blocks.grad_mode(self._recording(view_img_fts) and not self.config.fix_pano_embedding, self._drop()):
             a = blocks.linear(blocks.operand(v32, lowp), pk['img_linear'], lowp, out_dtype=F32)
@@ -512,16 +530,13 @@ class GlocalTextPathNavCMT(nn.Module):
         (r_g, r_l), ends, R = blocks.stack_layout([B * G, B * P])
         x32 = torch.empty((R, HIDDEN), dtype=F32, device=dev)
         x16 = torch.empty((R, HIDDEN), dtype=ops.h16(), device=dev) if lowp else None
-        if ends[0] > B * G:
-            x32[B * G:ends[0]].zero_()
-            if lowp:
-                x16[B * G:ends[0]].zero_()
+        # the padding rows between the two streams are zero-filled by the first composer launch
         ops.embed_compose(B * G, dev, a=_f32c(gmap_img_embeds).view(B * G, HIDDEN),
                           feat=_f32c(gmap_pos_fts).view(B * G, -1), feat_w=ge.gmap_pos_embeddings[0].weight,
                           feat_b=ge.gmap_pos_embeddings[0].bias,
                           feat_ln=(ge.gmap_pos_embeddings[1].weight, ge.gmap_pos_embeddings[1].bias),
                           idx=gmap_step_ids.long().contiguous().view(-1), table=ge.gmap_step_embeddings.weight,
-                          y32=x32[r_g:r_g + B * G], y16=x16[r_g:r_g + B * G] if lowp else None)
+                          y32=x32[r_g:ends[0]], y16=x16[r_g:ends[0]] if lowp else None, zero_rows=ends[0] - (r_g + B * G))
         ops.embed_compose(B * P, dev, a=_f32c(vp_img_embeds).view(B * P, HIDDEN),
                           feat=_f32c(vp_pos_fts).view(B * P, -1), feat_w=le.vp_pos_embeddings[0].weight,
                           feat_b=le.vp_pos_embeddings[0].bias,

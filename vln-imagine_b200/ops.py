@@ -341,9 +341,17 @@ def add_ln(a: torch.Tensor, b: Optional[torch.Tensor], gamma: torch.Tensor, beta
     return y32, y16
 
 
+_feat_wt_provider = None        # blocks installs a cache (transposed copies follow the weight versions like every derived tensor)
+
+
+def set_feat_wt_provider(fn):
+    global _feat_wt_provider
+    _feat_wt_provider = fn
+
+
 def embed_compose(rows: int, device, *, a=None, a2=None, a3=None, a_ln=None, feat=None, feat_w=None, feat_b=None, feat_ln=None,
                   idx=None, table=None, pos_table=None, pos_period=0, const_row=None, const_row2=None,
-                  out_ln=None, eps=1e-12, y32=None, y16=None, want16=False, want32=True, ln2=None, ln2_eps=1e-5):
+                  out_ln=None, eps=1e-12, y32=None, y16=None, want16=False, want32=True, ln2=None, ln2_eps=1e-5, zero_rows=0):
     """See vi_embed_compose.  *_ln are (gamma, beta) pairs.  y32 / y16 may be preallocated row views."""
     if y32 is None and want32:
         y32 = torch.empty((rows, HIDDEN), dtype=F32, device=device)
@@ -355,7 +363,9 @@ def embed_compose(rows: int, device, *, a=None, a2=None, a3=None, a_ln=None, fea
         args.a_gamma, args.a_beta = a_ln[0].data_ptr(), a_ln[1].data_ptr()
     if feat is not None:
         args.feat, args.feat_dim = feat.data_ptr(), feat.shape[-1]
-        args.feat_w, args.feat_b = feat_w.data_ptr(), _ptr(feat_b)
+        # the kernel reads the weight of the small projection TRANSPOSED ([feat_dim, 768]: coalesced, L1-resident rows per k)
+        wt = _feat_wt_provider(feat_w) if _feat_wt_provider is not None else feat_w.detach().t().contiguous().float()
+        args.feat_w, args.feat_b = wt.data_ptr(), _ptr(feat_b)
         if feat_ln is not None:
             args.feat_gamma, args.feat_beta = feat_ln[0].data_ptr(), feat_ln[1].data_ptr()
     if idx is not None:
@@ -369,6 +379,7 @@ def embed_compose(rows: int, device, *, a=None, a2=None, a3=None, a_ln=None, fea
     args.y32, args.y16, args.rows, args.y16_dtype = _ptr(y32), _ptr(y16), rows, _dt16(y16)
     if ln2 is not None:                               # a second LayerNorm chained on the result: y16 = LN2(y32)
         args.ln2_gamma, args.ln2_beta, args.ln2_eps = ln2[0].data_ptr(), ln2[1].data_ptr(), ln2_eps
+    args.zero_rows = int(zero_rows)                   # rows behind the last one that the same launch zero-fills (y32 / y16 must cover them)
     check(lib.vi_embed_compose(args, _stream()), 'vi_embed_compose')
     _launched(1)
     return y32, y16
