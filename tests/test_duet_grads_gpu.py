@@ -71,6 +71,12 @@ def test_duet_train_step_gradients(env, tag, shape, seed, stress, precision):
                 assert max_rel(got, ref) < tol, key
             else:
                 cosf = float((got * ref).sum() / (got.norm() * ref.norm()).clamp_min(1e-30))
+                noise = float(gold.get('autocast_scalar::' + key[6:], 0.0))
+                if ref.numel() == 1 and noise >= 1.0:
+                    # the reference itself gets the SIGN of this scalar wrong under autocast(bf16) on this step (relative error
+                    # >= 1: cfg-1 GASA slope, 2.1): a bf16 evaluation cannot pin it; its magnitude is bounded above (check_gradients)
+                    print('   %s: noise-dominated in bf16 (reference autocast error %.2f), cosine %.1f not asserted' % (key, noise, cosf))
+                    continue
                 assert cosf > (0.9 if ref.numel() < 8 else BF16_COSINE), (key, cosf)
 
 
