@@ -142,3 +142,66 @@ def test_attention_at_the_sequence_limits(lib_built, Lq, Lk):
     if Lk == 512:
         with pytest.raises(_lib.VlnImagineError, match='512'):
             ops.attention(q, torch.cat([k, k[:B]]), torch.cat([v, v[:B]]), B, Lq, Lk + 1)
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_shape_buckets_are_invisible(lib_built, monkeypatch, precision):
+    """graphs.ShapeBuckets: with the per-step shapes padded to multiples of 8 (G, P, O) / 4 (T) - what a rollout with changing
+    shapes switches to so that a handful of CUDA graphs serves it - every output equals the unpadded call (the padding is masked
+    exactly like batch padding) and still matches the fixtures of the real reference; a varying-shape sequence of calls ends up
+    with fewer captured graphs than distinct shapes"""
+    import importlib
+    from parity_utils import TOL, golden, manifest, max_rel, to_dev
+    from test_duet_parity_gpu import run_product as run_duet
+    from test_hamt_parity_gpu import run_product as run_hamt
+    synth = importlib.import_module('vln_imagine_b200.synth')
+    config = importlib.import_module('vln_imagine_b200.config')
+    tol = TOL[precision]
+    for kind in ('duet', 'hamt'):
+        outs = {}
+        for mode in ('0', '1'):
+            monkeypatch.setenv('VLN_IMAGINE_SHAPE_BUCKETS', mode)
+            if kind == 'duet':
+                model = importlib.import_module('vln_imagine_b200.duet').VLNBert(config.default_duet_args()).cuda().eval()
+                ep = to_dev(synth.to_torch(synth.duet_episode(synth.CFG1, 1234)))
+                run, keys = run_duet, ('gmap_embeds', 'vp_embeds', 'global_logits', 'local_logits', 'fused_logits')
+            else:
+                model = importlib.import_module('vln_imagine_b200.hamt').VLNBertCMT(config.default_hamt_args()).cuda().eval()
+                ep = to_dev(synth.to_torch(synth.hamt_episode(synth.CFG1, 1234)))
+                run, keys = run_hamt, ('act_logits', 'states')
+            model.vln_bert.load_state_dict(synth.synth_state_dict(manifest(kind), seed=0))
+            model.vln_bert.precision = precision
+            run(model, ep)                                   # first call of a signature runs eagerly, the second one is captured
+            outs[mode] = run(model, ep)
+        gold = golden(kind + '_cfg1')
+        for k in keys:
+            assert outs['1'][k].shape == outs['0'][k].shape, (kind, k)
+            assert max_rel(outs['1'][k], outs['0'][k]) < (1e-5 if precision == 'fp32' else tol), (kind, k)
+        ref_key = 'fused_logits' if kind == 'duet' else 'act_logits'
+        assert max_rel(outs['1'][ref_key], gold[ref_key]) < tol
+    # a rollout-like sequence of shapes: bucketing switches itself on after the third distinct signature
+    monkeypatch.setenv('VLN_IMAGINE_SHAPE_BUCKETS', 'auto')
+    duet = importlib.import_module('vln_imagine_b200.duet')
+    model = duet.VLNBert(config.default_duet_args()).cuda().eval()
+    model.vln_bert.load_state_dict(synth.synth_state_dict(manifest('duet'), seed=0))
+    model.vln_bert.precision = precision
+    ep = to_dev(synth.to_torch(synth.duet_episode(synth.CFG1, 1234)))
+    G0, P0 = ep['gmap_img_embeds'].shape[1], ep['vp_img_embeds'].shape[1]
+    full = run_duet(model, ep)
+    shapes = set()
+    for cut in range(1, 7):
+        G, P = G0 - cut, P0 - (cut % 3)
+        e2 = dict(ep)
+        for k in ('gmap_img_embeds', 'gmap_step_ids', 'gmap_pos_fts', 'gmap_masks', 'gmap_visited_masks'):
+            e2[k] = ep[k][:, :G].contiguous()
+        e2['gmap_pair_dists'] = ep['gmap_pair_dists'][:, :G, :G].contiguous()
+        e2['gmap_vpids'] = [row[:G] for row in ep['gmap_vpids']]
+        for k in ('vp_img_embeds', 'vp_pos_fts', 'vp_masks', 'vp_nav_masks'):
+            e2[k] = ep[k][:, :P].contiguous()
+        e2['vp_cand_vpids'] = [row[:P] for row in ep['vp_cand_vpids']]
+        shapes.add((G, P))
+        for _ in range(2):
+            out = run_duet(model, e2)
+        assert out['fused_logits'].shape == (ep['txt_ids'].shape[0], G) and out['vp_embeds'].shape[1] == P
+        assert torch.isfinite(out['gmap_embeds']).all()
+    assert len(model._g_nav.entries) < len(shapes) + 1, (len(model._g_nav.entries), len(shapes))

@@ -741,11 +741,17 @@ class GlocalTextPathNavCMT(nn.Module):
         """Viewpoint-id strings -> int32 tensors on ``dev`` (gmap padding -1, candidate padding -2).  Callers that
         already hold interned ids (a CUDA-graph replay loop, bench.py) may pass the two tensors instead of the
         lists; they are used as they are."""
+        def fit(ids, n, pad):                                  # interned rows narrower than a bucketed call: pad with the padding id
+            if ids.shape[1] >= n:
+                return ids
+            out = ids.new_full((ids.shape[0], n), pad)
+            out[:, :ids.shape[1]] = ids
+            return out
         if torch.is_tensor(gmap_vpids) and torch.is_tensor(vp_cand_vpids):
-            return gmap_vpids, vp_cand_vpids
+            return fit(gmap_vpids, G, -1), fit(vp_cand_vpids, P, -2)
         gi, ci = getattr(gmap_vpids, 'ids', None), getattr(vp_cand_vpids, 'ids', None)
         if torch.is_tensor(gi) and torch.is_tensor(ci):       # rows built by graph_map.DeviceGraphMaps: already interned
-            return gi, ci
+            return fit(gi, G, -1), fit(ci, P, -2)
         gmap_ids = torch.from_numpy(self._ids.encode(gmap_vpids, G, -1))
         cand_ids = torch.from_numpy(self._ids.encode(vp_cand_vpids, P, -2))
         if len(self._ids.ids) > (1 << 20):
@@ -828,6 +834,7 @@ class VLNBert(nn.Module):
         self._wt_cache = {}
         self._g_pano = graphs.GraphedCall(self._pano_fn)
         self._g_nav = graphs.GraphedCall(self._nav_fn)
+        self._buckets = graphs.ShapeBuckets()
 
     def _apply(self, fn, *a, **k):
         self._wt_cache = {}
@@ -878,6 +885,15 @@ class VLNBert(nn.Module):
                 tok = graphs.weights_token(m, self._wt_cache)
                 t = {k: batch[k] for k in self.NAV_TENSORS if batch[k] is not None}
                 G, P = batch['gmap_img_embeds'].shape[1], batch['vp_img_embeds'].shape[1]
+                Gb, Pb = G, P
+                if self._buckets.active((G, P)):
+                    # a rollout's (G, P) changes every step: pad to multiples of 8 so that a handful of captured graphs serves it
+                    # (graphs.ShapeBuckets); the padding is masked like the reference's own batch padding and sliced off below
+                    Gb, Pb = self._buckets.up(G), self._buckets.up(P)
+                    gdims = {'gmap_img_embeds': {1: Gb}, 'gmap_step_ids': {1: Gb}, 'gmap_pos_fts': {1: Gb}, 'gmap_masks': {1: Gb},
+                             'gmap_pair_dists': {1: Gb, 2: Gb}, 'gmap_visited_masks': {1: Gb}, 'vp_img_embeds': {1: Pb},
+                             'vp_pos_fts': {1: Pb}, 'vp_masks': {1: Pb}, 'vp_nav_masks': {1: Pb}}
+                    t = {k: (graphs.pad_to(v, gdims[k], dev) if k in gdims else v) for k, v in t.items()}
                 cfg = m.config
                 # context projections: looked up (or recomputed, eagerly) outside the graph, which only reads them
                 kv = m.context_kv(batch['txt_embeds'], batch['imagine_embeds'])
@@ -887,7 +903,11 @@ class VLNBert(nn.Module):
                 pre = self._g_nav(t, dev, extra_key=(m.precision, ops.h16(), blocks.fold_enabled(), cfg.imagine_enc_pano, cfg.concat_imagine_with if
                                                      cfg.imagine_enc_pano else None), weights_token=tok,
                                   borrowed={'ctx_kv%d' % i: x for i, x in enumerate(kv)}, no_clone_prefix='_')
-                return m.fuse_logits(pre, batch['gmap_vpids'], batch['vp_cand_vpids'], G, P)
+                out = m.fuse_logits(pre, batch['gmap_vpids'], batch['vp_cand_vpids'], Gb, Pb)
+                if (Gb, Pb) != (G, P):
+                    cut = {'gmap_embeds': G, 'global_logits': G, 'fused_logits': G, 'vp_embeds': P, 'local_logits': P}
+                    out = {k: (v[:, :cut[k]] if k in cut and v is not None else v) for k, v in out.items()}
+                return out
             return m(mode, batch)
         if mode in ('language', 'imagine', 'align_with_contrastive_loss'):
             return m(mode, batch)

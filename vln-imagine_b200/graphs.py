@@ -38,6 +38,50 @@ def capture(graph: 'torch.cuda.CUDAGraph', **kw):
             gc.enable()
 
 
+def round_up(n: int, m: int) -> int:
+    return (n + m - 1) // m * m
+
+
+def pad_to(x, sizes: Dict[int, int], device):
+    """x zero-/False-padded along the dimensions of ``sizes`` ({dim: new size}); host tensors are moved to ``device`` first"""
+    if x is None or all(x.shape[d] == n for d, n in sizes.items()):
+        return x
+    x = x if x.is_cuda else x.to(device, non_blocking=True)
+    shape = list(x.shape)
+    for d, n in sizes.items():
+        shape[d] = n
+    out = x.new_zeros(shape)
+    out[tuple(slice(0, k) for k in x.shape)] = x
+    return out
+
+
+class ShapeBuckets:
+    """Per-step shapes of a real rollout change almost every step (graph nodes G, local tokens P, history length T, observation
+    count O), and a CUDA graph is tied to one signature: without care every new (G, P) costs an eager run, a warm-up and a capture,
+    and an LRU of a few dozen graphs thrashes.  Once a mode has seen more than ``after`` distinct signatures its callers pad the
+    varying dimensions up to multiples of ``step`` - padded positions are masked out exactly as the batch padding the reference
+    itself applies, so results are unchanged - and a handful of graphs serves the whole rollout.  Fixed-shape callers (benchmarks)
+    never trigger it.  VLN_IMAGINE_SHAPE_BUCKETS=1 forces it from the first call, =0 disables it."""
+
+    def __init__(self, step: int = 8, after: int = 2):
+        import os
+        self.step, self.after = step, after
+        self.mode = os.environ.get('VLN_IMAGINE_SHAPE_BUCKETS', 'auto')
+        self.seen = set()
+
+    def active(self, signature) -> bool:
+        if self.mode == '0':
+            return False
+        if self.mode == '1':
+            return True
+        if len(self.seen) <= self.after:
+            self.seen.add(signature)
+        return len(self.seen) > self.after
+
+    def up(self, n: int, step: int = None) -> int:
+        return round_up(n, step or self.step)
+
+
 class GraphedCall:
     def __init__(self, fn: Callable[[Dict[str, torch.Tensor]], Dict[str, torch.Tensor]], max_entries: int = 24,
                  capture_after: int = 1):

@@ -536,6 +536,7 @@ class VLNBertCMT(nn.Module):
         self._wt_cache = {}
         self._g_vis = graphs.GraphedCall(self._vis_fn)
         self._g_hist = graphs.GraphedCall(self._hist_fn)
+        self._buckets = graphs.ShapeBuckets()
 
     def _apply(self, fn, *a, **k):
         self._wt_cache = {}
@@ -607,9 +608,18 @@ class VLNBertCMT(nn.Module):
                 t = {k: loc[k] for k in self.VIS_TENSORS if loc[k] is not None}
                 t['hist_embeds'] = hist
                 t['hist_masks'] = length2mask(hist_lens, hist.size(1), 'cpu').logical_not()
+                T, O = hist.size(1), ob_img_feats.shape[1]
+                if self._buckets.active((T, O)):
+                    # the history grows by one token per step and the observation count changes with it: pad T to multiples of 4 and
+                    # O to multiples of 8 (masked like the reference's batch padding) so that a few captured graphs serve a rollout
+                    Tb, Ob = self._buckets.up(T, 4), self._buckets.up(O, 8)
+                    dims = {'hist_embeds': {1: Tb}, 'hist_masks': {1: Tb}, 'ob_img_feats': {1: Ob}, 'ob_ang_feats': {1: Ob},
+                            'ob_nav_types': {1: Ob}, 'ob_masks': {1: Ob}}
+                    t = {k: (graphs.pad_to(v, dims[k], dev) if k in dims else v) for k, v in t.items()}
                 out = self._g_vis(t, dev, extra_key=(m.precision, ops.h16(), blocks.fold_enabled(), m.config.imagine_enc_pano),
                                   weights_token=graphs.weights_token(m, self._wt_cache))
-                return (out['act_logits'], out['states']) if return_states else (out['act_logits'],)
+                logits = out['act_logits'][:, :O]
+                return (logits, out['states']) if return_states else (logits,)
             hist_masks = length2mask(hist_lens, hist.size(1), hist.device).logical_not()
             act_logits, txt_o, hist_o, ob_o = m('visual', txt_embeds=txt_embeds, txt_masks=txt_masks, hist_embeds=hist,
                                                 hist_masks=hist_masks, ob_img_feats=self._env_dropout(ob_img_feats),
