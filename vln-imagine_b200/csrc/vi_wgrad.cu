@@ -235,6 +235,225 @@ wgrad_tc_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// CTA-pair form (cta_group::2), the default when N % 256 == 0: two CTAs of a cluster work on one 256 x BN tile of dW.  Each CTA
+// loads ITS 128 columns of dY (its half of the M = 256 operand) and HALF of the X columns (its half of the N operand), the leader
+// issues M = 256 MMAs that read both CTAs' shared memory, every CTA drains its own 128 TMEM lanes.  A 128 x 256 single-CTA tile
+// pulls 48 KB per k-block = 94 B/clk/SM from L2 (bound: cuBLAS was 15 - 75 % faster on these shapes); the pair pulls 32 KB per
+// CTA for the same 512 cycles of MMA.  Barrier protocol as in the forward kernel's PAIR mode (vi_gemm_tc.cu): both CTAs' TMA
+// bytes land on the LEADER's full barrier, tcgen05.commit is multicast to both CTAs' empty / accumulator-full barriers, the
+// epilogue warps of both CTAs arrive on the leader's accumulator-empty barrier.
+// ---------------------------------------------------------------------------------------------------------------------------
+constexpr uint32_t PEER_MASK_W = 0xFEFFFFFFu;          // clears the CTA-rank bit of a shared::cluster address (pair leader)
+__device__ __forceinline__ uint32_t cluster_ctarank_w() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_w() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair_w(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(tmap), "r"(bar & PEER_MASK_W), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader_w(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & PEER_MASK_W) : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair_w(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc_mma_pair_w(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__host__ __device__ constexpr uint32_t idesc_mn_m256(int n, bool f16) {
+  return (1u << 4) | (f16 ? 0u : ((1u << 7) | (1u << 10))) | (1u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(256 >> 4) << 24);
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+wgrad_pair_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p) {
+  constexpr int A_BYTES = BK * BM * 2;               // this CTA's 128 columns of dY: two boxes of 64 rows x 64 columns
+  constexpr int BN_CTA = BN / 2;                     // this CTA's half of the X columns
+  constexpr int B_BYTES = BK * BN_CTA * 2;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr uint32_t TMEM_COLS = BN + 32 <= 128 ? 128u : (BN + 32 <= 256 ? 256u : 512u);
+  static_assert(BN_CTA % 64 == 0, "a CTA stages whole 64-column blocks of X");
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* ones_smem = smem + STAGES * STAGE_BYTES;
+  uint8_t* epi_smem = ones_smem + ONES_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + STAGE_EPI);      // full[S], empty[S], tfull, tempty
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2);
+
+  const uint32_t smem_base = smem_u32(smem);
+  if (smem_base & 1023u) __trap();
+  const uint32_t bar_base = smem_u32(bars);
+  auto a_addr = [&](int s) { return smem_base + (uint32_t)(s * STAGE_BYTES); };
+  auto b_addr = [&](int s) { return smem_base + (uint32_t)(s * STAGE_BYTES + A_BYTES); };
+  auto full_bar = [&](int s) { return bar_base + 8u * (uint32_t)s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (uint32_t)(STAGES + s); };
+  const uint32_t tfull_bar = bar_base + 8u * (uint32_t)(2 * STAGES), tempty_bar = tfull_bar + 8u;
+
+  pdl_launch_dependents();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank_w();
+  const int worker = (int)(blockIdx.x >> 1), n_workers = (int)(gridDim.x >> 1);
+  if (warp == 0 && lane == 0) {
+    for (int g = 0; g < p.n_groups; ++g) { tma_prefetch_desc(&maps.dy[g]); tma_prefetch_desc(&maps.x[g]); }
+    tma_prefetch_desc(&maps.out);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(tfull_bar, 1);
+    mbar_init(tempty_bar, 8);                         // one arrive per epilogue warp of BOTH CTAs (on the leader's barrier)
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  if (warp == 3) {
+    const uint32_t one2 = p.fmt_f16 ? 0x3C003C00u : 0x3F803F80u;
+    for (int i = lane; i < ONES_BYTES / 4; i += 32) reinterpret_cast<uint32_t*>(ones_smem)[i] = one2;
+    fence_proxy_async();
+  }
+  tc_fence_before();
+  cluster_sync_w();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+
+  const int tiles_per_group = p.m_tiles * p.n_tiles;                       // m tiles of 256 rows here
+  const int total_units = p.n_groups * tiles_per_group * p.splits;
+  auto decode = [&](int u, int& g, int& mt, int& nt, int& s, int& kb0, int& kb1) {
+    s = u % p.splits; u /= p.splits;
+    nt = u % p.n_tiles; u /= p.n_tiles;
+    mt = u % p.m_tiles; g = u / p.m_tiles;
+    const int kt = p.kb_total[g];
+    kb0 = (int)((long long)s * kt / p.splits);
+    kb1 = (int)((long long)(s + 1) * kt / p.splits);
+  };
+  const bool want_db = p.db_part != nullptr;
+
+  if (warp == 0) {
+    // ------------------------------- TMA producer (both CTAs; bytes are counted on the leader's barrier) -----------
+    int st = 0;
+    uint32_t ph = 0;
+    for (int u = worker; u < total_units; u += n_workers) {
+      int g, mt, nt, s, kb0, kb1;
+      decode(u, g, mt, nt, s, kb0, kb1);
+      const int acol = mt * 256 + (int)rank * BM;                          // this CTA's 128 columns of dY
+      const int bcol = nt * BN + (int)rank * BN_CTA;                       // this CTA's half of the X columns
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(empty_bar(st), ph ^ 1u);
+        if (elect_one()) {
+          if (rank == 0) mbar_expect_tx(full_bar(st), 2 * STAGE_BYTES);
+#pragma unroll
+          for (int j = 0; j < BM / 64; ++j)
+            tma_load_2d_pair_w(a_addr(st) + (uint32_t)(j * 8192), &maps.dy[g], full_bar(st), acol + j * 64, kb * BK);
+#pragma unroll
+          for (int j = 0; j < BN_CTA / 64; ++j)
+            tma_load_2d_pair_w(b_addr(st) + (uint32_t)(j * 8192), &maps.x[g], full_bar(st), bcol + j * 64, kb * BK);
+        }
+        __syncwarp();
+        if (++st == STAGES) { st = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------- MMA issuer (leader only) -----------------------------------------------------
+    if (rank == 0) {
+      const uint32_t idesc = idesc_mn_m256(BN, p.fmt_f16 != 0), idesc1 = idesc_mn_m256(16, p.fmt_f16 != 0);
+      const uint64_t ones_desc = desc_mn_sw128(smem_u32(ones_smem));
+      int st = 0, it = 0;
+      uint32_t ph = 0;
+      for (int u = worker; u < total_units; u += n_workers, ++it) {
+        int g, mt, nt, s, kb0, kb1;
+        decode(u, g, mt, nt, s, kb0, kb1);
+        mbar_wait(tempty_bar, ((uint32_t)it & 1u) ^ 1u);                 // both CTAs' epilogues have drained the accumulator
+        tc_fence_after();
+        const bool db_unit = want_db && nt == 0;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(full_bar(st), ph);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t adesc = desc_mn_sw128(a_addr(st)), bdesc = desc_mn_sw128(b_addr(st));
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+              const uint32_t acc = (uint32_t)((kb != kb0) || k != 0);
+              tc_mma_pair_w(tmem_base, adesc + (uint64_t)(128 * k), bdesc + (uint64_t)(128 * k), idesc, acc);
+              if (db_unit) tc_mma_pair_w(tmem_base + (uint32_t)BN, adesc + (uint64_t)(128 * k), ones_desc, idesc1, acc);
+            }
+            tc_commit_pair_w(empty_bar(st));
+            if (kb == kb1 - 1) tc_commit_pair_w(tfull_bar);
+          }
+          __syncwarp();
+          if (++st == STAGES) { st = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------- epilogue (both CTAs, each its own 128 rows of the tile) ------------------------
+    const int ew = warp - 4;
+    const uint32_t my_buf = smem_u32(epi_smem) + (uint32_t)(ew * 8192);
+    int it = 0, n = 0;
+    for (int u = worker; u < total_units; u += n_workers, ++it) {
+      int g, mt, nt, s, kb0, kb1;
+      decode(u, g, mt, nt, s, kb0, kb1);
+      const int mrow0 = mt * 256 + (int)rank * BM + ew * 32;             // row of dW inside the group
+      const int orow0 = (g * p.splits + s) * p.N + mrow0;
+      mbar_wait(tfull_bar, (uint32_t)it & 1u);
+      tc_fence_after();
+      const uint32_t tbase = tmem_base + ((uint32_t)(ew * 32) << 16);
+      uint32_t r[32];
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c, ++n) {
+        tmem_ld_32x32(tbase + (uint32_t)(c * 32), r);
+        const uint32_t buf = my_buf + (uint32_t)((n & 1) * 4096);
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        __syncwarp();
+        tmem_ld_wait();
+        const uint32_t rowb = buf + (uint32_t)(lane * 128);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};"
+                       ::"r"(rowb + (uint32_t)((j ^ (lane & 7)) << 4)), "r"(r[4 * j]), "r"(r[4 * j + 1]), "r"(r[4 * j + 2]), "r"(r[4 * j + 3])
+                       : "memory");
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          if (p.accumulate) tma_reduce_add_2d(&maps.out, buf, nt * BN + c * 32, orow0);
+          else tma_store_2d(&maps.out, buf, nt * BN + c * 32, orow0);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      }
+      if (want_db && nt == 0) {
+        tmem_ld_32x32(tbase + (uint32_t)BN, r);
+        tmem_ld_wait();
+        float* dst = p.db_part + (long long)(g * p.splits + s) * p.N + mrow0 + lane;
+        *dst = p.accumulate ? *dst + __uint_as_float(r[0]) : __uint_as_float(r[0]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader_w(tempty_bar);
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+
+  tc_fence_before();
+  cluster_sync_w();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
 // out[g][i] = sum over s (fixed order) of part[g][s][i]   for two segments (weight and bias gradients)
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* part_w, float* out_w, long long per_group_w4,
                                                            const float* part_b, float* out_b, long long per_group_b4, int G, int S,
@@ -306,6 +525,50 @@ int launch_wgrad(const WgradMaps& m, const WgradParams& p, int grid, cudaStream_
   return VI_OK;
 }
 
+template <int BN, int STAGES> constexpr int wgrad_pair_smem() {
+  return STAGES * (BK * BM * 2 + BK * (BN / 2) * 2) + ONES_BYTES + STAGE_EPI + (2 * STAGES + 2) * 8 + 16;
+}
+template <int BN, int STAGES>
+int launch_wgrad_pair(const WgradMaps& m, const WgradParams& p, int pairs, cudaStream_t st) {
+  static_assert(wgrad_pair_smem<BN, STAGES>() <= 232448, "shared memory budget");
+  static bool attr_set = false;
+  auto kern = wgrad_pair_kernel<BN, STAGES>;
+  if (!attr_set) {
+    VI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, wgrad_pair_smem<BN, STAGES>()));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)(2 * pairs));
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = wgrad_pair_smem<BN, STAGES>();
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int nattr = 0;
+  if (vi_pdl_enabled()) {
+    attr[nattr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[nattr].val.programmaticStreamSerializationAllowed = 1;
+    ++nattr;
+  }
+  attr[nattr].id = cudaLaunchAttributeClusterDimension;
+  attr[nattr].val.clusterDim.x = 2;
+  attr[nattr].val.clusterDim.y = 1;
+  attr[nattr].val.clusterDim.z = 1;
+  ++nattr;
+  cfg.attrs = attr;
+  cfg.numAttrs = nattr;
+  VI_CUDA(cudaLaunchKernelEx(&cfg, kern, m, p));
+  VI_LAUNCH_CHECK();
+  return VI_OK;
+}
+
+// the CTA-pair form serves shapes whose N is a multiple of 256 and whose K is a multiple of 128 (VI_WGRAD_PAIR=0: never)
+bool wgrad_pair_ok(int N, int K) {
+  const char* e = getenv("VI_WGRAD_PAIR");
+  if (e && e[0] == '0') return false;
+  return N % 256 == 0 && K % 128 == 0;
+}
+
 }  // namespace
 
 extern "C" int64_t vi_wgrad16_workspace(int N, int K, int n_groups, const int32_t* group_rows, int splits) {
@@ -319,7 +582,9 @@ extern "C" int64_t vi_wgrad16_workspace(int N, int K, int n_groups, const int32_
 extern "C" int vi_wgrad16_splits(int N, int K, int n_groups, const int32_t* group_rows) {
   if (n_groups < 1 || n_groups > MAXG || !group_rows || N <= 0 || K <= 0) return 1;
   const int bn = K % 256 == 0 ? 256 : (K % 128 == 0 ? 128 : 64);
-  const long long tiles = (long long)n_groups * (N / BM) * (K / bn);
+  const bool pair = wgrad_pair_ok(N, K);
+  // work units: 128-row tiles on one SM each, or 256-row tiles on a pair of SMs
+  const long long tiles = pair ? (long long)n_groups * (N / 256) * (K / bn) * 2 : (long long)n_groups * (N / BM) * (K / bn);
   int min_kb = 1 << 30;
   for (int g = 0; g < n_groups; ++g) {
     const int kb = (group_rows[g] + BK - 1) / BK;
@@ -376,13 +641,20 @@ extern "C" int vi_wgrad16(const void* dy, int64_t lddy, const void* x, int64_t l
   if (int rc = make_f32_out_map(&m.out, part_w, (uint64_t)K, (uint64_t)n_groups * S * N, (uint64_t)K)) return rc;
 
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const long long units = (long long)n_groups * p.m_tiles * p.n_tiles * S;
   const int nsm = vi_num_sms();
-  const int grid = (int)(units < nsm ? units : nsm);
   int rc;
-  if (bn == 256) rc = launch_wgrad<256, 4>(m, p, grid, st);
-  else if (bn == 128) rc = launch_wgrad<128, 6>(m, p, grid, st);
-  else rc = launch_wgrad<64, 8>(m, p, grid, st);
+  if (wgrad_pair_ok(N, K)) {
+    p.m_tiles = N / 256;
+    const long long units = (long long)n_groups * p.m_tiles * p.n_tiles * S;
+    const int pairs = (int)(units < nsm / 2 ? units : nsm / 2);
+    rc = bn == 256 ? launch_wgrad_pair<256, 6>(m, p, pairs, st) : launch_wgrad_pair<128, 8>(m, p, pairs, st);
+  } else {
+    const long long units = (long long)n_groups * p.m_tiles * p.n_tiles * S;
+    const int grid = (int)(units < nsm ? units : nsm);
+    if (bn == 256) rc = launch_wgrad<256, 4>(m, p, grid, st);
+    else if (bn == 128) rc = launch_wgrad<128, 6>(m, p, grid, st);
+    else rc = launch_wgrad<64, 8>(m, p, grid, st);
+  }
   if (rc) return rc;
   if (S > 1) {
     const long long w4 = (long long)N * K / 4, b4 = db ? N / 4 : 0;
