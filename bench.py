@@ -466,10 +466,32 @@ def train_measure(args, shape, rank, local_rank, world, K, W, detail=True):
     # the caller's optimiser (r2r/agent_base.py:141-160); capturable: its step is part of the replayed graph
     opt = torch.optim.AdamW(net.parameters(), lr=1e-5, fused=True, capturable=not args.no_graph)
 
+    # data-parallel runs: the backward pass stops at the instruction embeddings, the all-reduce of everything but the text side
+    # starts there and runs under the language encoder's backward (train.GraphedIteration(tail_fn=...)); VI_TRAIN_OVERLAP_AR=0: one
+    # all-reduce after the whole backward pass
+    fused_acc = os.environ.get('VI_TRAIN_FUSED_ACC', '1') != '0'
+    lang_end = flat.prefix_end(net) if world > 1 and os.environ.get('VI_TRAIN_OVERLAP_AR', '1') != '0' else 0
+    overlap = lang_end > 0
+    pending = {}
+
     def grad_fn(ep):
         flat.zero()
-        loss, ce, aux, _ = train.duet_finetune_iteration(model, ep, n_steps=T, fused_accumulation=os.environ.get('VI_TRAIN_FUSED_ACC', '1') != '0')
-        return loss.detach()
+        out = train.duet_finetune_iteration(model, ep, n_steps=T, fused_accumulation=fused_acc, split_language_backward=overlap)
+        if overlap:
+            pending['finish'] = out[4]
+        return out[0].detach()
+
+    def tail_fn():
+        pending.pop('finish')()
+
+    def before_tail():
+        pending['work'] = flat.all_reduce_range(lang_end, flat.numel, async_op=True)
+
+    def reduce_rest():
+        w2 = flat.all_reduce_range(0, lang_end, async_op=True)
+        for w in (pending.pop('work', None), w2):
+            if w is not None:
+                w.wait()
 
     def update_fn():
         torch.nn.utils.clip_grad_norm_(net.parameters(), 40.)         # agent_base.py:225
@@ -477,7 +499,12 @@ def train_measure(args, shape, rank, local_rank, world, K, W, detail=True):
 
     def iteration(ep):
         loss = grad_fn(ep)
-        flat.all_reduce()
+        if overlap:
+            before_tail()
+            tail_fn()
+            reduce_rest()
+        else:
+            flat.all_reduce()
         update_fn()
         return loss
 
@@ -499,7 +526,10 @@ def train_measure(args, shape, rank, local_rank, world, K, W, detail=True):
     eager_iteration = iteration
     graphed = None
     if not args.no_graph:
-        graphed = train.GraphedIteration(net, grad_fn, update_fn, d, between=flat.all_reduce, warmup=0)
+        if overlap:
+            graphed = train.GraphedIteration(net, grad_fn, update_fn, d, between=reduce_rest, warmup=0, tail_fn=tail_fn, before_tail=before_tail)
+        else:
+            graphed = train.GraphedIteration(net, grad_fn, update_fn, d, between=flat.all_reduce, warmup=0)
 
         def iteration(ep):
             graphed.load(ep)
@@ -555,7 +585,7 @@ def train_measure(args, shape, rank, local_rank, world, K, W, detail=True):
     res = dict(ms=ms, ms_e2e=ms_e2e, K=K, W=W, T=T, B=B, h2d=h2d, launches=launches, loss=loss_host,
                loss_finite=bool(np.isfinite(loss_host)), allreduce_ms=ar_ms, allreduce_bytes=flat.bytes(),
                allreduce_busbw_gbs=(2.0 * (world - 1) / world * flat.bytes() / (ar_ms * 1e-3) / 1e9) if ar_ms else None,
-               clocks=sampler.summary(), graphed=graphed is not None,
+               clocks=sampler.summary(), graphed=graphed is not None, overlap=overlap,
                dropout=(net.config.hidden_dropout_prob, net.config.attention_probs_dropout_prob, model.drop_env.p))
     if graphed is not None:
         graphed.finish()
@@ -620,7 +650,10 @@ def run_train(args, shape, desc, rank, local_rank, world):
                    'dropout': 'on: hidden %.2f, attention %.2f, features %.2f, projection head 0.15'
                               % r['dropout'],
                    'l2': 'no flush: an iteration touches > 3 GB of weights, gradients and saved activations',
-                   'collective': 'one NCCL all-reduce (AVG) of the flat fp32 gradient buffer, %.0f MB' % (r['allreduce_bytes'] / 1e6),
+                   'collective': ('NCCL all-reduce (AVG) of the flat fp32 gradient buffer, %.0f MB, in two parts: everything but the text side '
+                                  'starts when the backward pass reaches the instruction embeddings and runs under the language encoder\'s '
+                                  'backward, the text side follows' if r.get('overlap') else
+                                  'one NCCL all-reduce (AVG) of the flat fp32 gradient buffer, %.0f MB') % (r['allreduce_bytes'] / 1e6),
                    'weights': 'random-init (deterministic synthetic)'},
         'clocks': r['clocks'],
         'e2e': {'value': world * B * T * K / (ms_e2e * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4,
@@ -869,7 +902,8 @@ def main():
                          'value': world * tr_['B'] * tr_['T'] * tr_['K'] / (tr_['ms'] * 1e-3), 'unit': UNIT,
                          'ms_per_iteration': tr_['ms'] / tr_['K'], 'iterations': tr_['K'], 'warmup': tr_['W'],
                          'allreduce_ms': tr_['allreduce_ms'], 'allreduce_bytes': tr_['allreduce_bytes'],
-                         'allreduce_busbw_gbs': tr_['allreduce_busbw_gbs'], 'loss': tr_['loss'], 'loss_finite': tr_['loss_finite']}
+                         'allreduce_busbw_gbs': tr_['allreduce_busbw_gbs'], 'allreduce_overlapped': tr_.get('overlap', False),
+                         'loss': tr_['loss'], 'loss_finite': tr_['loss_finite']}
         except Exception as e:                          # noqa: BLE001 - an auxiliary record must never cost the bench line
             train_rec = {'error': '%s: %s' % (type(e).__name__, str(e)[:300])}
             if world > 1:

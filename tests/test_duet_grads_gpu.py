@@ -207,3 +207,39 @@ def test_fused_gradient_accumulation_matches_autograd(env):
     for n, p in net.named_parameters():
         assert float((p.grad - 1.0 - g0[n]).abs().max()) < 1e-4 * max(1.0, float(g0[n].abs().max())), n
     net.zero_grad(set_to_none=True)
+
+
+def test_split_language_backward_matches_the_single_pass(env):
+    """train.duet_finetune_iteration(split_language_backward=True): the backward pass stops at the instruction embeddings (every
+    gradient but the text side is final there - what the overlapped all-reduce of the data-parallel runs starts on) and
+    ``finish()`` runs the language encoder's part; the sum equals the single backward pass, with and without in-kernel accumulation"""
+    train = importlib.import_module('vln_imagine_b200.train')
+    synth, model = env
+    net = model.vln_bert
+    net.load_state_dict(synth.synth_state_dict(manifest('duet'), seed=0, gasa_stress=True))
+    net.precision = 'bf16'
+    ep = to_dev(synth.to_torch(synth.duet_episode(synth.CFG1, 1234)))
+    net.zero_grad(set_to_none=True)
+    train.duet_finetune_iteration(model, ep, n_steps=2)
+    torch.cuda.synchronize()
+    ref = {n: p.grad.detach().clone() for n, p in net.named_parameters()}
+    for fused in (False, True):
+        net.zero_grad(set_to_none=True)
+        out = train.duet_finetune_iteration(model, ep, n_steps=2, fused_accumulation=fused, split_language_backward=True)
+        assert len(out) == 5
+        text = [n for n, p in net.named_parameters() if n.startswith('lang_encoder.')]
+        other = [n for n, p in net.named_parameters() if not (n.startswith('lang_encoder.') or n.startswith('embeddings.'))]
+        params = dict(net.named_parameters())
+        assert all(params[n].grad is None or float(params[n].grad.abs().max()) == 0.0 for n in text), 'text side must still be untouched'
+        for n in other:                                    # final before finish()
+            assert float((params[n].grad - ref[n]).abs().max()) <= 1e-4 * float(ref[n].abs().max()) + 1e-12, n
+        out[4]()
+        torch.cuda.synchronize()
+        for n, p in net.named_parameters():
+            assert float((p.grad - ref[n]).abs().max()) <= 1e-4 * float(ref[n].abs().max()) + 1e-12, (fused, n)
+    flat = train.FlatGradients(net)
+    end = flat.prefix_end(net)
+    names = [n for n, _ in net.named_parameters()]
+    n_text = sum(1 for n in names if n.startswith('embeddings.') or n.startswith('lang_encoder.'))
+    assert 0 < end < flat.numel and end == flat.offsets[n_text]
+    net.zero_grad(set_to_none=True)

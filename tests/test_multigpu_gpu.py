@@ -82,6 +82,55 @@ def _ddp_worker(rank, world, port, out):
     dist.destroy_process_group()
 
 
+def _overlap_worker(rank, world, port, out):
+    """graph-replayed iteration with the all-reduce in two parts (everything but the text side under the language encoder's
+    backward, train.GraphedIteration(tail_fn=...)) against the plain eager iteration + one all-reduce"""
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    train = importlib.import_module('vln_imagine_b200.train')
+    model, net, d = _model_and_episode(rank)
+    flat = train.FlatGradients(net)
+    flat.zero()
+    train.duet_finetune_iteration(model, d, n_steps=2)
+    flat.all_reduce()
+    ref = flat.buffer.clone()
+    end = flat.prefix_end(net)
+    pending = {}
+
+    def grad_fn(ep):
+        flat.zero()
+        o = train.duet_finetune_iteration(model, ep, n_steps=2, fused_accumulation=True, split_language_backward=True)
+        pending['finish'] = o[4]
+        return o[0].detach()
+
+    def tail_fn():
+        pending.pop('finish')()
+
+    def before_tail():
+        pending['work'] = flat.all_reduce_range(end, flat.numel, async_op=True)
+
+    def reduce_rest():
+        w2 = flat.all_reduce_range(0, end, async_op=True)
+        for w in (pending.pop('work', None), w2):
+            if w is not None:
+                w.wait()
+    holder = {}
+
+    def update_fn():
+        holder['grads'] = flat.buffer.clone()
+    it = train.GraphedIteration(net, grad_fn, update_fn, d, between=reduce_rest, warmup=1, tail_fn=tail_fn, before_tail=before_tail)
+    errs = []
+    for _ in range(2):
+        it.load(d)
+        it.replay()
+        torch.cuda.synchronize()
+        errs.append(float((holder['grads'] - ref).abs().max() / ref.abs().max()))
+    if rank == 0:
+        out.put((max(errs), end, flat.numel))
+    dist.destroy_process_group()
+
+
 def _spawn(worker, world=2, timeout=600):
     ctx = mp.get_context('spawn')
     out = ctx.Queue()
@@ -109,6 +158,13 @@ def test_module_trains_under_distributed_data_parallel(lib_built):
     assert loss == loss and gmax > 0
     assert same == 0.0, 'DDP must leave identical (averaged) gradients on both ranks'
     assert moved > 0
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two GPUs')
+def test_overlapped_all_reduce_equals_the_single_one(lib_built):
+    err, end, numel = _spawn(_overlap_worker)
+    assert 0 < end < numel
+    assert err < 1e-4, err            # same gradients, the fp32 additions of the steps in another order
 
 
 def test_graph_replayed_iteration_equals_the_eager_one(lib_built):

@@ -70,6 +70,33 @@ class FlatGradients:
     def bytes(self) -> int:
         return self.numel * self.buffer.element_size()
 
+    def prefix_end(self, module: torch.nn.Module, prefixes=('embeddings.', 'lang_encoder.')) -> int:
+        """Buffer offset behind the leading parameters whose names start with one of ``prefixes`` (the text side: the only
+        parameters the LAST part of the backward pass - the language encoder - still writes).  0 when the order does not allow it."""
+        names = {id(p): n for n, p in module.named_parameters()}
+        end = 0
+        for p, off in zip(self.params, self.offsets):
+            n = names.get(id(p), '')
+            if not any(n.startswith(x) for x in prefixes):
+                break
+            end = off + (p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        # every text-side parameter must sit inside the prefix
+        for p, off in zip(self.params, self.offsets):
+            if off >= end and any(names.get(id(p), '').startswith(x) for x in prefixes):
+                return 0
+        return end
+
+    def all_reduce_range(self, lo: int, hi: int, group=None, async_op: bool = False):
+        """average buffer[lo:hi] over the ranks (the two halves of an overlapped gradient all-reduce)"""
+        if hi <= lo or not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+            return None
+        seg = self.buffer[lo:hi]
+        if dist.get_backend(group) == 'nccl':
+            return dist.all_reduce(seg, op=dist.ReduceOp.AVG, group=group, async_op=async_op)
+        dist.all_reduce(seg, op=dist.ReduceOp.SUM, group=group, async_op=False)
+        seg.div_(dist.get_world_size(group))
+        return None
+
 
 def teacher_targets(gmap_masks: torch.Tensor, gmap_visited_masks: torch.Tensor) -> torch.Tensor:
     """Synthetic teacher action: the last admissible graph node (valid and not visited); [stop] (0) if none.
@@ -80,15 +107,21 @@ def teacher_targets(gmap_masks: torch.Tensor, gmap_visited_masks: torch.Tensor) 
 
 
 def duet_finetune_iteration(model, ep: dict, n_steps: int = 1, cosine_weight: float = 0.5, ml_weight: float = 1.0,
-                            backward: bool = True, fused_accumulation: bool = False):
+                            backward: bool = True, fused_accumulation: bool = False, split_language_backward: bool = False):
     """One imitation-learning iteration of the reference agent on a batch of episodes (r2r/agent.py:384-623):
     language + imagine + align once, then ``n_steps`` navigation steps (panorama -> navigation -> summed
     cross-entropy on the fused logits), loss = ml_weight * CE / B + cosine_weight * aux.  ``model`` is the drop-in
     VLNBert; ``ep`` holds device tensors (vln-imagine_b200/synth.py layout).  Returns (loss, ce, aux, last nav dict).
     ``fused_accumulation``: the per-step parameter gradients are summed inside the backward kernels instead of by one autograd
-    ``add`` per parameter per step (autograd_ops.fused_grad_accumulation); same .grad at the end, not for DDP-wrapped modules."""
+    ``add`` per parameter per step (autograd_ops.fused_grad_accumulation); same .grad at the end, not for DDP-wrapped modules.
+    ``split_language_backward``: the backward pass stops at the instruction embeddings - every gradient except the text side
+    (embeddings.*, lang_encoder.*) is then final - and a fifth return value ``finish()`` runs the rest (the language encoder's
+    backward): the caller can start the all-reduce of the finished part in between (GraphedIteration(tail_fn=...))."""
     B = ep['txt_ids'].shape[0]
     txt = model('language', {'txt_ids': ep['txt_ids'], 'txt_masks': ep['txt_masks']})
+    txt_graph = None
+    if split_language_backward and backward and txt.requires_grad:
+        txt_graph, txt = txt, txt.detach().requires_grad_(True)             # the navigation part sees a leaf
     img = model('imagine', {'imagine_feats': ep['imagine_feats'], 'imagine_masks': None})
     aux, img2 = model('align_with_contrastive_loss', {
         'align_txt_embeds': txt, 'txt_masks': ep['txt_masks'], 'align_imagine_embeds': img,
@@ -113,6 +146,15 @@ def duet_finetune_iteration(model, ep: dict, n_steps: int = 1, cosine_weight: fl
         from . import autograd_ops as ag
         with ag.fused_grad_accumulation(fused_accumulation):
             loss.backward()
+        if split_language_backward:
+            leaf = txt
+
+            def finish():
+                """second half of the backward pass: the language encoder"""
+                if txt_graph is not None and leaf.grad is not None:
+                    with ag.fused_grad_accumulation(fused_accumulation):
+                        txt_graph.backward(leaf.grad)
+            return loss, ce / B, aux, nav, finish
     return loss, ce / B, aux, nav
 
 
@@ -133,12 +175,22 @@ class GraphedIteration:
     The derived weight copies (bf16 shadows, transposes) are rebuilt INSIDE graph 1 at the start of every iteration; call
     ``finish()`` before using the model outside the graphs again."""
 
-    def __init__(self, model, grad_fn, update_fn, static_inputs: dict, between=None, warmup: int = 3):
+    def __init__(self, model, grad_fn, update_fn, static_inputs: dict, between=None, warmup: int = 3, tail_fn=None,
+                 before_tail=None):
+        """``tail_fn``: the rest of the backward pass when ``grad_fn`` stops early (duet_finetune_iteration(split_language_backward=
+        True): ``grad_fn`` keeps the ``finish`` closure, ``tail_fn`` calls it), captured into its own graph in the SAME memory pool;
+        ``before_tail`` runs eagerly between the two (start the asynchronous all-reduce of the gradients that are already final),
+        ``between`` after the tail as before (all-reduce the rest, wait for both)."""
         self.model, self.static, self.between = model, static_inputs, between
+        self.before_tail = before_tail
         dev = next(model.parameters()).device
 
         def eager():
             loss = grad_fn(static_inputs)
+            if tail_fn is not None:
+                if before_tail is not None:
+                    before_tail()
+                tail_fn()
             if between is not None:
                 between()
             update_fn()
@@ -156,6 +208,14 @@ class GraphedIteration:
         self.g_grad = torch.cuda.CUDAGraph()
         with graphs.capture(self.g_grad):
             self.loss = grad_fn(static_inputs)
+        self.g_tail = None
+        if tail_fn is not None:
+            if before_tail is not None:
+                before_tail()
+                torch.cuda.synchronize(dev)                # no collective in flight while the next capture runs
+            self.g_tail = torch.cuda.CUDAGraph()
+            with graphs.capture(self.g_tail, pool=self.g_grad.pool()):   # it reads tensors the first graph saved for backward
+                tail_fn()
         if between is not None:
             between()
         self.g_update = torch.cuda.CUDAGraph()
@@ -179,6 +239,10 @@ class GraphedIteration:
 
     def replay(self):
         self.g_grad.replay()
+        if self.g_tail is not None:
+            if self.before_tail is not None:
+                self.before_tail()
+            self.g_tail.replay()
         if self.between is not None:
             self.between()
         self.g_update.replay()
