@@ -110,10 +110,18 @@ def _acc_entry(params, shapes, device):
     """the accumulators of one pack: tensors of ``shapes`` + the parameter slices they feed"""
     key = tuple(id(p) for p in params) + tuple(tuple(s) for s in shapes)
     e = _GradAcc.buffers.get(key)
-    if e is None or e['t'][0].device != device:
+    # ids are only unique among LIVE objects: an entry of a model that is gone must not be handed to a new one whose parameters
+    # happen to reuse the ids (its slices would feed the dead parameters)
+    if e is None or e['t'][0].device != device or len(e['params']) != len(params) or any(a is not b for a, b in zip(e['params'], params)):
         e = {'t': [torch.empty(tuple(sh), dtype=F32, device=device) for sh in shapes], 'live': False, 'params': list(params)}
         _GradAcc.buffers[key] = e
     return e
+
+
+def release_accumulators():
+    """drop every accumulator (and the references to the parameters they feed): call when a model is retired"""
+    _GradAcc.buffers.clear()
+    _GradAcc.live, _GradAcc.queued = [], False
 
 
 def _acc_begin(e) -> int:

@@ -218,6 +218,8 @@ class GraphedIteration:
                 tail_fn()
         if between is not None:
             between()
+        from . import autograd_ops
+        self._keepalive = list(autograd_ops._GradAcc.buffers.values())    # the graphs hold raw pointers to these accumulators
         self.g_update = torch.cuda.CUDAGraph()
         import os
         if os.environ.get('VI_TRAIN_SHARED_POOL', '0') == '1':
@@ -256,9 +258,10 @@ class GraphedIteration:
         """Call before using the model outside the replayed iteration (validation between training phases): drops the
         derived weight copies, the inference CUDA graphs that hold raw pointers to them and the cached context projections,
         so the next eager / graphed inference call rebuilds all of them from the CURRENT parameters."""
-        from . import blocks
+        from . import autograd_ops, blocks
         blocks.touch_weights()
         self._invalidate_packs()
+        autograd_ops.release_accumulators()                   # they may live in this iteration's graph pool
         for m in self.model.modules():
             for name in ('_g_pano', '_g_nav', '_g_vis', '_g_hist'):
                 g = getattr(m, name, None)
