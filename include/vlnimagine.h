@@ -309,7 +309,9 @@ int vi_colsum(const void* x, int64_t ld, int dtype, float* out, int64_t rows, in
 int vi_act_fwd(const void* x, void* y, int64_t n, int act, int dtype, vi_stream_t stream);
 int vi_act_bwd(const void* x, const void* dy, void* dx, int64_t n, int act, int dtype, vi_stream_t stream);
 /* adjoint of vi_add_ln: dy = dy32 (+ dy16); dx (fp32 and/or bf16 copy) is the gradient of both a and b;
- * dgamma / dbeta [n_groups, 768] may be NULL; stats is a [rows, 2] fp32 scratch (mean, rstd). */
+ * dgamma / dbeta [n_groups, 768] (16-byte aligned) may be NULL; stats is a [rows, 2] fp32 scratch (mean, rstd).
+ * scratch: at least 2 * ceil(rows / 32) * 768 floats; with 2 * ceil(rows / 8) * 768 the kernel may use chunks of 8 or 16 rows
+ * (more CTAs for the short streams of this path; the summation order, hence the last bits of dgamma / dbeta, follows the chunk). */
 int vi_add_ln_bwd(const float* a, const float* b, const float* gamma, float eps, const float* dy32, const void* dy16,
                   float* dx32, void* dx16, float* dgamma, float* dbeta, float* stats, int64_t rows,
                   int n_groups, const int32_t* group_row_end, float* scratch, int64_t scratch_elems, vi_stream_t stream);

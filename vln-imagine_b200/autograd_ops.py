@@ -424,7 +424,7 @@ class LayerNormFn(Function):
             dg = torch.empty((n_groups, HIDDEN), dtype=F32, device=a.device)
             dbt = torch.empty((n_groups, HIDDEN), dtype=F32, device=a.device)
         stats = torch.empty((rows, 2), dtype=F32, device=a.device)
-        sc = reduce_scratch(a.device, 4 * rows, HIDDEN, 2)            # the fused pass reduces 32-row chunks (RED_CHUNK / 4)
+        sc = reduce_scratch(a.device, 16 * rows, HIDDEN, 2)           # the fused pass reduces chunks of 8 - 32 rows (>= RED_CHUNK / 16)
         check(lib.vi_add_ln_bwd_acc(a.data_ptr(), _ptr(b), gamma.data_ptr(), ctx.eps, _ptr(dy32), _ptr(dy16), dx.data_ptr(), None,
                                     dg.data_ptr(), dbt.data_ptr(), stats.data_ptr(), rows, n_groups,
                                     _lib.int_array(list(ends)) if ends is not None else None, sc.data_ptr(), sc.numel(), beta,
@@ -501,7 +501,7 @@ class DenseResLNFn(Function):
         dres = torch.empty((rows, HIDDEN), dtype=F32, device=dev)
         da16 = torch.empty((rows, HIDDEN), dtype=x.dtype, device=dev)
         stats = torch.empty((rows, 2), dtype=F32, device=dev)
-        sc = reduce_scratch(dev, 4 * rows, HIDDEN, 2)
+        sc = reduce_scratch(dev, 16 * rows, HIDDEN, 2)
         check(lib.vi_add_ln_drop_bwd(d.data_ptr(), res32.data_ptr() if p > 0 else None, g.data_ptr(), ctx.eps, _ptr(dy32), _ptr(dy16),
                                      dres.data_ptr(), None, da16.data_ptr(), dg.data_ptr(), dbt.data_ptr(), stats.data_ptr(), rows, n_ln,
                                      _lib.int_array(list(ln_ends)) if ln_ends is not None else None, sc.data_ptr(), sc.numel(), beta_ln,

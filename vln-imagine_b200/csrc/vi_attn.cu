@@ -327,6 +327,10 @@ __device__ __forceinline__ void attn_sp_body(const AttnProblem& pr, uint32_t ks_
       }
     }
   }
+  // ... and under the K / V / Q copies: the tiles are waited for only here (every warp of the CTA reaches this barrier)
+  cp_async_wait<0>();
+  __syncthreads();
+  if (q0 >= pr.Lq) return;
 #pragma unroll
   for (int ks = 0; ks < 4; ++ks) {
     uint32_t qa[4];
@@ -418,8 +422,8 @@ __device__ __forceinline__ void attn_sp_body(const AttnProblem& pr, uint32_t ks_
   }
 }
 
-template <bool F16>
-__global__ void __launch_bounds__(128, 4) attn_fwd_sp_kernel(const AttnParams p) {
+template <bool F16, int MINB>
+__global__ void __launch_bounds__(128, MINB) attn_fwd_sp_kernel(const AttnParams p) {
   pdl_enter();
   extern __shared__ __align__(16) uint8_t smem[];
   int z = blockIdx.z, pi = 0;
@@ -460,10 +464,7 @@ __global__ void __launch_bounds__(128, 4) attn_fwd_sp_kernel(const AttnParams p)
     else if (pr.key_mask && !pr.key_mask[(long long)b * pr.Lk + key]) m = (p.mask_mode == VI_MASK_NEG_INF) ? -INFINITY : -10000.0f * LOG2E_F;
     madd[key] = m;
   }
-  cp_async_wait<0>();
-  __syncthreads();
-  const int q0 = q_base + warp * 16;
-  if (q0 >= pr.Lq) return;
+  const int q0 = q_base + warp * 16;                         // a warp without rows still joins the barrier inside the body
   const int lm = lane >> 3, lr = lane & 7;
   const uint32_t q_frag = qs_u + (uint32_t)((warp * 16 + (lm & 1) * 8 + lr) * ROW + (lm >> 1) * 8) * 2;
   switch (LkP >> 4) {
@@ -612,8 +613,15 @@ extern "C" int vi_attn_fwd_multi(const vi_attn_problem* problems, int n_problems
     bool sp = max_lkp <= 96 && vi_attn_sp_enabled();
     for (int i = 0; i < n_problems; ++i) sp = sp && p.pr[i].drop_thresh == 0 && p.pr[i].lse == nullptr;
     if (sp) {
-      if (dtype == VI_DT_F16) VI_CUDA(vi_launch(attn_fwd_sp_kernel<true>, dim3(grid), dim3(nwarp * 32), (size_t)(smem), st, p));
-      else VI_CUDA(vi_launch(attn_fwd_sp_kernel<false>, dim3(grid), dim3(nwarp * 32), (size_t)(smem), st, p));
+      static const int minb_env = [] { const char* e = getenv("VI_ATTN_SP_MINB"); return e ? atoi(e) : 0; }();
+      const bool dense = minb_env ? minb_env == 5 : true;
+      if (dtype == VI_DT_F16) {
+        if (dense) VI_CUDA(vi_launch(attn_fwd_sp_kernel<true, 5>, dim3(grid), dim3(nwarp * 32), (size_t)(smem), st, p));
+        else VI_CUDA(vi_launch(attn_fwd_sp_kernel<true, 4>, dim3(grid), dim3(nwarp * 32), (size_t)(smem), st, p));
+      } else {
+        if (dense) VI_CUDA(vi_launch(attn_fwd_sp_kernel<false, 5>, dim3(grid), dim3(nwarp * 32), (size_t)(smem), st, p));
+        else VI_CUDA(vi_launch(attn_fwd_sp_kernel<false, 4>, dim3(grid), dim3(nwarp * 32), (size_t)(smem), st, p));
+      }
     } else if (dtype == VI_DT_F16) {
       VI_CUDA(vi_launch(attn_fwd_bf16_kernel<true>, dim3(grid), dim3(nwarp * 32), (size_t)(smem), st, p));
     } else {
@@ -649,10 +657,14 @@ int vi_attn_init() {
   VI_CUDA(cudaFuncSetAttribute(attn_fwd_bf16_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   VI_CUDA(cudaFuncSetAttribute(attn_fwd_bf16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 176 * 1024));
   VI_CUDA(cudaFuncSetAttribute(attn_fwd_bf16_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  VI_CUDA(cudaFuncSetAttribute(attn_fwd_sp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-  VI_CUDA(cudaFuncSetAttribute(attn_fwd_sp_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  VI_CUDA(cudaFuncSetAttribute(attn_fwd_sp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-  VI_CUDA(cudaFuncSetAttribute(attn_fwd_sp_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  VI_CUDA(cudaFuncSetAttribute(attn_fwd_sp_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  VI_CUDA(cudaFuncSetAttribute(attn_fwd_sp_kernel<false, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  VI_CUDA(cudaFuncSetAttribute(attn_fwd_sp_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  VI_CUDA(cudaFuncSetAttribute(attn_fwd_sp_kernel<true, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  VI_CUDA(cudaFuncSetAttribute(attn_fwd_sp_kernel<false, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  VI_CUDA(cudaFuncSetAttribute(attn_fwd_sp_kernel<false, 5>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  VI_CUDA(cudaFuncSetAttribute(attn_fwd_sp_kernel<true, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  VI_CUDA(cudaFuncSetAttribute(attn_fwd_sp_kernel<true, 5>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   VI_CUDA(cudaFuncSetAttribute(attn_fwd_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   return VI_OK;
 }

@@ -321,32 +321,39 @@ __global__ void __launch_bounds__(256) ln_bwd_param_partial_kernel(const float* 
 }
 
 // dx AND the parameter-gradient partials in ONE pass over the rows (the two-kernel form above reads a, b and dy twice): a CTA of
-// 8 warps owns LN_CHUNK = 32 consecutive rows (4 per warp), every lane keeps the dgamma / dbeta contributions of its 24 columns in
-// registers, the 8 warps are summed through shared memory in a fixed order and the chunk's partial row goes to
+// 8 warps owns chunk_rows = 8 / 16 / 32 consecutive rows (1 / 2 / 4 per warp), every lane keeps the dgamma / dbeta contributions of its
+// 24 columns in registers, the 8 warps are summed through shared memory in a fixed order and the chunk's partial row goes to
 // part[2][n_chunks][768]; ln_param_sum_kernel then adds the chunks of each row group (fixed order: deterministic).
-constexpr int LN_CHUNK = 32;
+// The chunk is sized by the row count (ln_chunk_rows): the streams of this path have 1.3k - 5k rows, and at 32 rows per CTA the
+// grid was 40 - 160 CTAs of 8 warps walking 4 dependent row round trips each on a 148-SM part.
+constexpr int LN_CHUNK_MAX = 32;
+static int ln_chunk_rows(int64_t rows, int64_t scratch_elems) {
+  int chunk = rows <= 296 * 8 ? 8 : rows <= 296 * 16 ? 16 : LN_CHUNK_MAX;
+  while (chunk < LN_CHUNK_MAX && (int64_t)2 * ((rows + chunk - 1) / chunk) * D > scratch_elems) chunk *= 2;     // caller's workspace decides
+  return chunk;
+}
 // DropArgs: the forward pass normalised dropout(a) + b (vi_add_ln_drop); then dxa16 receives dropout(dx) - the gradient of a - as the
 // 16-bit operand of the weight / input gradient GEMMs of the dense layer that produced a, and dx32 stays the gradient of b.
 struct DropArgs { uint32_t thresh; float scale; const uint32_t* seed; uint32_t site; bf16* dxa16; };
-__global__ void __launch_bounds__(256) ln_bwd_fused_kernel(const float* a, const float* b, const float* gamma, float eps,
+__global__ void __launch_bounds__(256, 2) ln_bwd_fused_kernel(const float* a, const float* b, const float* gamma, float eps,
                                                            const float* dy32, const bf16* dy16, float* __restrict__ dx32,
                                                            bf16* __restrict__ dx16, float* __restrict__ stats,
                                                            float* __restrict__ part, long long rows, int n_chunks,
-                                                           const RowGroups grp, const DropArgs dr) {
+                                                           int chunk_rows, const RowGroups grp, const DropArgs dr) {
   pdl_enter();
   const bool drop = dr.seed != nullptr;
   const uint32_t dkey = drop ? vi_drop_key(dr.seed, dr.site) : 0u;
   __shared__ float red[8][D];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const long long r0 = (long long)blockIdx.x * LN_CHUNK;
+  const long long r0 = (long long)blockIdx.x * chunk_rows;
   float ag[24], ab[24];
 #pragma unroll
   for (int i = 0; i < 24; ++i) { ag[i] = 0.f; ab[i] = 0.f; }
   const float* gm_base = gamma + group_of_row(grp, r0) * D;         // a chunk never straddles two row groups
-  for (int it = 0; it < LN_CHUNK / 8; ++it) {
+  for (int it = 0; it < chunk_rows / 8; ++it) {
     const long long row = r0 + it * 8 + warp;
     if (row >= rows) break;
-    float x[24], g[24], dv[24];
+    float x[24], dv[24];
     float s = 0.f;
 #pragma unroll
     for (int j = 0; j < 6; ++j) {
@@ -390,7 +397,6 @@ __global__ void __launch_bounds__(256) ln_bwd_fused_kernel(const float* a, const
         const float xh = (x[4 * j + e] - mean) * rstd;
         const float gg = dv[4 * j + e] * gmv[e];
         x[4 * j + e] = xh;
-        g[4 * j + e] = gg;
         sg += gg;
         sgx = fmaf(gg, xh, sgx);
         ag[4 * j + e] = fmaf(dv[4 * j + e], xh, ag[4 * j + e]);
@@ -401,9 +407,11 @@ __global__ void __launch_bounds__(256) ln_bwd_fused_kernel(const float* a, const
 #pragma unroll
     for (int j = 0; j < 6; ++j) {
       const int c = (lane + 32 * j) * 4;
+      const float4 gm = *reinterpret_cast<const float4*>(gm_base + c);      // dy * gamma again (an L1 hit) instead of 24 live registers
+      const float gmv[4] = {gm.x, gm.y, gm.z, gm.w};
       float o[4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) o[e] = rstd * (g[4 * j + e] - mg - x[4 * j + e] * mgx);
+      for (int e = 0; e < 4; ++e) o[e] = rstd * (dv[4 * j + e] * gmv[e] - mg - x[4 * j + e] * mgx);
       if (dx32) *reinterpret_cast<float4*>(dx32 + row * D + c) = make_float4(o[0], o[1], o[2], o[3]);
       if (dx16) *reinterpret_cast<uint2*>(dx16 + row * D + c) = make_uint2(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]));
       if (dr.dxa16) {
@@ -435,26 +443,43 @@ __global__ void __launch_bounds__(256) ln_bwd_fused_kernel(const float* a, const
     }
   }
 }
-// dgamma[g][c] / dbeta[g][c] = sum over the LN_CHUNK-row chunks of group g; grid (768 / 256, n_groups, 2)
-__global__ void __launch_bounds__(256) ln_param_sum_kernel(const float* part, float* dgamma, float* dbeta,
-                                                           int n_chunks, long long rows, const RowGroups grp, int accumulate) {
+// dgamma[g][c] / dbeta[g][c] = sum over the chunks of group g; grid (768 / 128, n_groups, 2), 256 threads = 32 lanes of four
+// columns x 8 chunk lanes: lane k adds the chunks k0 + k, k0 + k + 8, ... (two loads in flight), then the 8 lanes are added in
+// order - a fixed order for a given chunk size, so the result is deterministic.
+__global__ void __launch_bounds__(256) ln_param_sum_kernel(const float* part, float* dgamma, float* dbeta, int n_chunks,
+                                                           int chunk_rows, long long rows, const RowGroups grp, int accumulate) {
   pdl_enter();
-  const int c = blockIdx.x * 256 + threadIdx.x;
+  __shared__ float4 red[8][32];
+  const int cl = threadIdx.x & 31, kl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 128 + cl * 4;
   const int gi = blockIdx.y, o = blockIdx.z;
   const long long g0 = gi == 0 ? 0 : grp.end[gi - 1];
   long long g1 = gi == grp.n - 1 ? rows : grp.end[gi];
   if (g1 > rows) g1 = rows;
-  const int k0 = (int)(g0 / LN_CHUNK), k1 = (int)((g1 + LN_CHUNK - 1) / LN_CHUNK);
+  const int k0 = (int)(g0 / chunk_rows), k1 = (int)((g1 + chunk_rows - 1) / chunk_rows);
   const float* pp = part + ((long long)o * n_chunks) * D + c;
-  float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
-  int k = k0;
-  for (; k + 3 < k1; k += 4) {
-    t0 += pp[(long long)k * D]; t1 += pp[(long long)(k + 1) * D]; t2 += pp[(long long)(k + 2) * D]; t3 += pp[(long long)(k + 3) * D];
+  float4 t0 = make_float4(0.f, 0.f, 0.f, 0.f), t1 = t0;
+  int k = k0 + kl;
+  for (; k + 8 < k1; k += 16) {
+    const float4 u = *reinterpret_cast<const float4*>(pp + (long long)k * D);
+    const float4 v = *reinterpret_cast<const float4*>(pp + (long long)(k + 8) * D);
+    t0.x += u.x; t0.y += u.y; t0.z += u.z; t0.w += u.w;
+    t1.x += v.x; t1.y += v.y; t1.z += v.z; t1.w += v.w;
   }
-  for (; k < k1; ++k) t0 += pp[(long long)k * D];
-  float* dst = (o ? dbeta : dgamma) + (long long)gi * D + c;
-  const float t = (t0 + t1) + (t2 + t3);
-  *dst = accumulate ? *dst + t : t;
+  if (k < k1) {
+    const float4 u = *reinterpret_cast<const float4*>(pp + (long long)k * D);
+    t0.x += u.x; t0.y += u.y; t0.z += u.z; t0.w += u.w;
+  }
+  red[kl][cl] = make_float4(t0.x + t1.x, t0.y + t1.y, t0.z + t1.z, t0.w + t1.w);
+  __syncthreads();
+  if (kl == 0) {
+    float4 t = red[0][cl];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) { const float4 u = red[w][cl]; t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w; }
+    float4* dst = reinterpret_cast<float4*>((o ? dbeta : dgamma) + (long long)gi * D + c);
+    if (accumulate) { const float4 u = *dst; t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w; }
+    *dst = t;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1037,13 +1062,16 @@ extern "C" int vi_add_ln_drop_bwd(const float* a, const float* b, const float* g
   if (rows <= 0) return VI_OK;
   if (dgamma && dbeta) {
     // one pass: dx + per-chunk partials of dgamma / dbeta, then the fixed-order sum of the chunks of every row group
-    const int nch = (int)((rows + LN_CHUNK - 1) / LN_CHUNK);
+    VI_CHECK_ARG(aligned16(dgamma) && aligned16(dbeta) && aligned16(scratch), "vi_add_ln_bwd: dgamma / dbeta / scratch must be 16-byte aligned");
+    const int chunk = scratch ? ln_chunk_rows(rows, scratch_elems) : LN_CHUNK_MAX;
+    const int nch = (int)((rows + chunk - 1) / chunk);
     VI_CHECK_ARG(scratch && scratch_elems >= (int64_t)2 * nch * D, "vi_add_ln_bwd: scratch too small (need 2 x ceil(rows / %d) x %d floats)",
-                 LN_CHUNK, D);
+                 LN_CHUNK_MAX, D);
     VI_CUDA(vi_launch(ln_bwd_fused_kernel, dim3((unsigned)nch), dim3(256), 0, ST(stream), a, b, gamma, eps, dy32,
-                      reinterpret_cast<const bf16*>(dy16), dx32, reinterpret_cast<bf16*>(dx16), stats, scratch, (long long)rows, nch, grp, dr));
-    VI_CUDA(vi_launch(ln_param_sum_kernel, dim3(D / 256, n_groups, 2), dim3(256), 0, ST(stream), (const float*)scratch, dgamma, dbeta, nch,
-                      (long long)rows, grp, (int)(accumulate != 0)));
+                      reinterpret_cast<const bf16*>(dy16), dx32, reinterpret_cast<bf16*>(dx16), stats, scratch, (long long)rows, nch, chunk,
+                      grp, dr));
+    VI_CUDA(vi_launch(ln_param_sum_kernel, dim3(D / 128, n_groups, 2), dim3(256), 0, ST(stream), (const float*)scratch, dgamma, dbeta, nch,
+                      chunk, (long long)rows, grp, (int)(accumulate != 0)));
   } else {
     VI_CUDA(vi_launch(ln_bwd_dx_kernel, dim3((unsigned)((rows + 3) / 4)), dim3(128), 0, ST(stream), a, b, gamma, eps, dy32,
                       reinterpret_cast<const bf16*>(dy16), dx32, reinterpret_cast<bf16*>(dx16), stats, (long long)rows, grp));
