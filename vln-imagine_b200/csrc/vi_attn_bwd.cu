@@ -57,8 +57,10 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool v
 }
 
 // NT = 8-key score tiles per query row held in registers (LkP <= 8 * NT)
+// CTAs per SM asked of the register allocator: the grid is episodes x heads (768 CTAs at the fine-tuning shapes), and at the
+// 195 registers NT = 12 takes unconstrained only two CTAs fit an SM (2.6 waves); 167 registers (no spills) fit three.
 template <int NT>
-__global__ void __launch_bounds__(128) attn_bwd_bf16_kernel(const AttnBwdTcParams p) {
+__global__ void __launch_bounds__(128, NT == 12 ? 3 : NT == 6 ? 4 : 1) attn_bwd_bf16_kernel(const AttnBwdTcParams p) {
   pdl_enter();
   extern __shared__ __align__(16) uint8_t smem[];
   const int LqP = p.LqP, LkP = p.LkP;

@@ -111,6 +111,35 @@ __device__ __forceinline__ float gelu_grad(float x) {
   const float pdf = 0.39894228040143267794f * expf(-0.5f * x * x);
   return cdf + x * pdf;
 }
+// The 16-bit instances (results rounded to 8 mantissa bits) use erf(z) = 1 - (a1 t + ... + a5 t^5) exp(-z^2), t = 1 / (1 + p z)
+// (Abramowitz & Stegun 7.1.26, |error| <= 1.5e-7): one MUFU.RCP + one MUFU.EX2 + a dozen FMAs per element, and the exponential
+// is the one the density needs anyway - erff + expf made these kernels instruction-bound (ncu: 23 us for 41 MB).  The fp32
+// instances (check mode) keep erff / expf.
+__device__ __forceinline__ void gelu_terms(float x, float& cdf, float& e) {
+  const float ax = fabsf(x);
+  float ex;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(x * x * -0.72134752044448170368f));       // exp(-x^2 / 2)
+  const float t = __fdividef(1.0f, fmaf(ax, 0.3275911f * 0.70710678118654752440f, 1.0f));
+  float q = fmaf(t, 1.061405429f, -1.453152027f);
+  q = fmaf(q, t, 1.421413741f);
+  q = fmaf(q, t, -0.284496736f);
+  q = fmaf(q, t, 0.254829592f);
+  const float h = 0.5f * q * t * ex;                                                           // 0.5 * (1 - erf(|x| / sqrt 2))
+  cdf = x >= 0.f ? 1.0f - h : h;
+  e = ex;
+}
+__device__ __forceinline__ float gelu_fast(float x) {
+  float cdf, e;
+  gelu_terms(x, cdf, e);
+  return x * cdf;
+}
+__device__ __forceinline__ float gelu_grad_fast(float x) {
+  float cdf, e;
+  gelu_terms(x, cdf, e);
+  return fmaf(x * 0.39894228040143267794f, e, cdf);
+}
+template <typename T> __device__ __forceinline__ float gelu_fwd_t(float x) { return sizeof(T) == 2 ? gelu_fast(x) : gelu_erf(x); }
+template <typename T> __device__ __forceinline__ float gelu_grad_t(float x) { return sizeof(T) == 2 ? gelu_grad_fast(x) : gelu_grad(x); }
 // 8 elements per thread (16-byte accesses for bf16, 2 x 16 for fp32); n is a multiple of 8 on this path (768 / 3072 wide
 // rows); a scalar tail covers anything else
 template <typename T> struct Vec8;
@@ -154,13 +183,13 @@ __global__ void __launch_bounds__(256) act_fwd_kernel(const T* x, T* __restrict_
     float f[8];
     v.get(f);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) f[j] = act == VI_EPI_GELU ? gelu_erf(f[j]) : fmaxf(f[j], 0.f);
+    for (int j = 0; j < 8; ++j) f[j] = act == VI_EPI_GELU ? gelu_fwd_t<T>(f[j]) : fmaxf(f[j], 0.f);
     v.set(f);
     v.store(y + i);
   } else {
     for (long long j = i; j < n; ++j) {
       const float v = ldf(x, j);
-      y[j] = from_f32<T>(act == VI_EPI_GELU ? gelu_erf(v) : fmaxf(v, 0.f));
+      y[j] = from_f32<T>(act == VI_EPI_GELU ? gelu_fwd_t<T>(v) : fmaxf(v, 0.f));
     }
   }
 }
@@ -179,13 +208,13 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const T* x, const T* dy, T
     vx.get(f);
     vg.get(g);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) g[j] = act == VI_EPI_GELU ? g[j] * gelu_grad(f[j]) : (f[j] > 0.f ? g[j] : 0.f);
+    for (int j = 0; j < 8; ++j) g[j] = act == VI_EPI_GELU ? g[j] * gelu_grad_t<T>(f[j]) : (f[j] > 0.f ? g[j] : 0.f);
     vg.set(g);
     vg.store(dx + i);
   } else {
     for (long long j = i; j < n; ++j) {
       const float v = ldf(x, j), g = ldf(dy, j);
-      dx[j] = from_f32<T>(act == VI_EPI_GELU ? g * gelu_grad(v) : (v > 0.f ? g : 0.f));
+      dx[j] = from_f32<T>(act == VI_EPI_GELU ? g * gelu_grad_t<T>(v) : (v > 0.f ? g : 0.f));
     }
   }
 }
