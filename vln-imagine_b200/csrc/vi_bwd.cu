@@ -357,7 +357,8 @@ __global__ void __launch_bounds__(256) ln_bwd_param_partial_kernel(const float* 
 // grid was 40 - 160 CTAs of 8 warps walking 4 dependent row round trips each on a 148-SM part.
 constexpr int LN_CHUNK_MAX = 32;
 static int ln_chunk_rows(int64_t rows, int64_t scratch_elems) {
-  int chunk = rows <= 296 * 8 ? 8 : rows <= 296 * 16 ? 16 : LN_CHUNK_MAX;
+  static const int forced = [] { const char* e = getenv("VI_LN_CHUNK"); return e ? atoi(e) : 0; }();      // 8 / 16 / 32: A/B switch
+  int chunk = (forced == 8 || forced == 16 || forced == 32) ? forced : rows <= 296 * 8 ? 8 : rows <= 296 * 16 ? 16 : LN_CHUNK_MAX;
   while (chunk < LN_CHUNK_MAX && (int64_t)2 * ((rows + chunk - 1) / chunk) * D > scratch_elems) chunk *= 2;     // caller's workspace decides
   return chunk;
 }
