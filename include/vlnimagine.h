@@ -201,6 +201,10 @@ typedef struct {
   int64_t zero_rows;         /* rows [rows, rows + zero_rows) of y32 / y16 are zero-filled (the padding up to the next stream of a
                               * row-stacked activation: it flows through the following GEMMs and must stay finite) */
 } vi_embed_args;
+/* PARAMETER operands (feat_w, feat_b, the LayerNorm vectors, const_row / const_row2) are touched at the top of the kernel,
+ * ahead of the programmatic-dependent-launch wait, to have them in L1 when the rows arrive: they must not be outputs of another
+ * kernel of THIS library launched just before on the same stream (outputs of any other kernel, or of an earlier synchronised
+ * launch, are fine; VI_PDL=0 removes the constraint).  Row operands (a, a2, a3, feat, idx, table, pos_table) have no such rule. */
 int vi_embed_compose(const vi_embed_args* args, vi_stream_t stream);
 
 /* out[row] = LayerNorm(h[row]) . w + b   (tail of ClsPrediction / NextActionPrediction:
